@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE ONLY: Python restatement of the reference's root drivers, used to pin
+the oracle's disp() against the reference's golden scan files.
+
+secant_osc  -> src/ALPS_fns.f90:1919-2101
+secant      -> src/ALPS_fns.f90:1815-1917
+om_scan     -> src/ALPS_fns.f90:2198-2600 (wave-vector stepping only; scan types 3 and 4)
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+_F01 = float(np.float32(0.1))      # REAL*4 literals promoted to double in the reference
+_F1EM3 = float(np.float32(1.0e-3))
+
+
+def secant_osc(disp, om: complex, numiter: int, D_threshold: float, D_prec: float) -> complex:
+    delta = complex(1.0e-6, 1.0e-8)
+    lam = _F01
+    osc_threshold = _F1EM3
+    D = disp(om)
+    minom, minD = om, D
+    prevom = om * (1.0 - D_prec)
+    prev2om = prev3om = prev4om = om
+    prevD = disp(prevom)
+    if abs(prevD) < abs(minD):
+        minom, minD = prevom, prevD
+    it = 0
+    go = True
+    damping = 1.0
+    osc = 0
+    while it <= numiter - 1 and go:
+        it += 1
+        D = disp(om)
+        if abs(D - prevD) < 1.0e-80:
+            prevom = prevom + 1.0e-8
+            prevD = disp(prevom)
+        if abs(D) < D_threshold:
+            go = False
+        else:
+            if it > 4:
+                def close(a):
+                    return (abs(om.real - a.real) < abs(om.real) * osc_threshold and
+                            abs(om.imag - a.imag) < abs(om.imag) * osc_threshold)
+                if close(prevom) or close(prev2om) or close(prev3om) or close(prev4om):
+                    osc += 1
+                    damping = min(0.5, damping * 0.75)
+            if osc > 1:
+                Dprime = (disp(om * (1.0 + delta)) - disp(om * (1.0 - delta))) / (2.0 * om * delta)
+                jump = D / (Dprime + lam * D)
+            else:
+                jump = damping * D * (om - prevom) / (D - prevD)
+            if abs(jump) > _F01 * abs(om):
+                jump = (_F01 * abs(om)) * (jump / abs(jump))
+            if abs(D) > abs(prevD):
+                jump = 0.5 * jump
+            prev4om, prev3om, prev2om, prevom = prev3om, prev2om, prevom, om
+            prevD = D
+            if abs(D) < abs(minD):
+                minom, minD = om, D
+            om = om - jump
+    if it >= numiter:
+        om = minom
+    return om
+
+
+def secant(disp, om: complex, numiter: int, D_threshold: float, D_prec: float) -> complex:
+    prevom = om * (1.0 - D_prec)
+    Dprev = disp(prevom)
+    minD = disp(om)
+    minom = om
+    if abs(Dprev) < abs(minD):
+        minom, minD = prevom, Dprev
+    it = 0
+    go = True
+    while it <= numiter - 1 and go:
+        it += 1
+        D = disp(om)
+        if abs(D - Dprev) < 1.0e-80:
+            prevom = prevom + 1.0e-8
+            Dprev = disp(prevom)
+        if abs(D) < D_threshold:
+            jump = 0.0
+            go = False
+        else:
+            jump = D * (om - prevom) / (D - Dprev)
+        prevom = om
+        om = om - jump
+        Dprev = D
+        if abs(D) < abs(minD):
+            minom, minD = om, D
+    if it >= numiter:
+        om = minom
+    return om
+
+
+def scan_k(oracle, kperp0: float, kpar0: float, scan_type: int, swf: float, nsteps: int, log: bool,
+           guess: complex, numiter: int, D_threshold: float, D_prec: float, method=secant_osc):
+    """refine_guess at (kperp0,kpar0) then om_scan of type 3 (kperp) / 4 (kpar), one root.
+    Returns rows (kperp, kpar, omega) like the .scan_* file."""
+    oracle.set_k(kperp0, kpar0)
+    om = method(oracle.disp, guess, numiter, D_threshold, D_prec)
+    rows = [(kperp0, kpar0, om)]
+    last = kperp0 if scan_type == 3 else kpar0
+    diff = (math.log10(swf) - math.log10(last)) / nsteps if log else (swf - last) / nsteps
+    for it in range(1, nsteps + 1):
+        k = 10.0 ** (math.log10(last) + diff * it) if log else last + diff * it
+        kperp, kpar = (k, kpar0) if scan_type == 3 else (kperp0, k)
+        oracle.set_k(kperp, kpar)
+        om = method(oracle.disp, om, numiter, D_threshold, D_prec)
+        rows.append((kperp, kpar, om))
+    return rows

@@ -1,0 +1,150 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes wrapper of the CPU oracle (oracle/alps_oracle.c).
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs -- never by the product package alps_b200/.
+PARITY UNPINNED at 1e-9 (see alps_oracle.h): pinned to the reference by its 5-digit goldens only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OracleCfg(C.Structure):
+    _fields_ = [("nspec", C.c_int), ("nperp", C.c_int), ("npar", C.c_int), ("ngamma", C.c_int),
+                ("npparbar", C.c_int), ("vA", C.c_double), ("Bessel_zero", C.c_double),
+                ("Tlim", C.c_double), ("positions_principal", C.c_int),
+                ("n_resonance_interval", C.c_int), ("kperp_norm", C.c_int), ("nproc", C.c_int),
+                ("maxfits", C.c_int), ("maxorder", C.c_int)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libalps_oracle.so")
+    src = os.path.join(_HERE, "alps_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.oracle_bessj.restype = C.c_double
+        _LIB.oracle_bessj.argtypes = [C.c_int, C.c_double]
+        _LIB.oracle_int_ee.restype = C.c_double
+        _LIB.oracle_set_k.argtypes = [C.c_double, C.c_double, C.c_void_p]
+        _LIB.oracle_set_species.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_int, C.c_double]
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a):
+    """flat float64 copy in Fortran element order"""
+    return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))
+
+
+class Oracle:
+    """disp() of the reference restated on the CPU (one global instance at a time)."""
+
+    def __init__(self, plasma, nproc: int = 0, threads: int = 0):
+        L = lib()
+        self.L = L
+        self.pl = plasma
+        maxorder = max(s.poly_order for s in plasma.species)
+        cfg = OracleCfg(plasma.nspec, plasma.nperp, plasma.npar, plasma.ngamma, plasma.npparbar,
+                        plasma.vA, plasma.Bessel_zero, plasma.Tlim, plasma.positions_principal,
+                        plasma.n_resonance_interval, int(plasma.kperp_norm), nproc, plasma.maxfits,
+                        maxorder)
+        L.oracle_init(C.byref(cfg))
+        for i, s in enumerate(plasma.species):
+            ft = np.asarray(s.fit_type, dtype=np.int32)
+            pc = np.asarray(s.perp_correction, dtype=np.float64)
+            rc = L.oracle_set_species(i + 1, s.ns, s.qs, s.ms, int(s.relativistic), int(s.usebM),
+                                      s.ACmethod, len(s.fit_type), _p(ft), _p(pc), int(s.logfit),
+                                      s.poly_kind, s.poly_order, s.poly_log_max)
+            if rc:
+                raise RuntimeError("oracle_set_species failed: %d" % rc)
+        pp = _f(plasma.pp)
+        if plasma.df0 is None:
+            df0 = np.zeros(plasma.nspec * (plasma.nperp - 1) * (plasma.npar - 1) * 2)
+            L.oracle_derivative_f0(_p(_f(plasma.f0)), _p(pp), _p(df0), plasma.nspec, plasma.nperp,
+                                   plasma.npar)
+        else:
+            df0 = _f(plasma.df0)
+        self.df0_flat = df0
+        rc = L.oracle_upload(_p(pp), _p(df0), _p(_f(plasma.param_fit)), _p(_f(plasma.poly_fit_coeffs)))
+        if rc:
+            raise RuntimeError("oracle_upload failed")
+        if threads:
+            L.oracle_set_threads(threads)
+        self.nmax = None
+
+    def df0(self):
+        pl = self.pl
+        return self.df0_flat.reshape((pl.nspec, pl.nperp - 1, pl.npar - 1, 2), order="F")
+
+    def set_k(self, kperp: float, kpar: float):
+        nmax = np.zeros(self.pl.nspec, dtype=np.int32)
+        rc = self.L.oracle_set_k(kperp, kpar, _p(nmax))
+        if rc:
+            raise RuntimeError("oracle_set_k failed")
+        self.nmax = nmax
+        return nmax
+
+    def set_ncap(self, ncap: int):
+        self.L.oracle_set_ncap(ncap)
+
+    def disp(self, om: complex, full: bool = False):
+        n = self.pl.nspec
+        omv = np.array([om.real, om.imag])
+        D = np.zeros(2)
+        if not full:
+            self.L.oracle_disp(_p(omv), _p(D), None, None, None)
+            return complex(D[0], D[1])
+        chi0 = np.zeros(n * 9 * 2)
+        low = np.zeros(n * 27 * 2)
+        wave = np.zeros(18)
+        self.L.oracle_disp(_p(omv), _p(D), _p(chi0), _p(low), _p(wave))
+        c = lambda a, shape: (a[0::2] + 1j * a[1::2]).reshape(shape, order="F")
+        return (complex(D[0], D[1]), c(chi0, (n, 3, 3)), c(low, (n, 3, 3, 3)), c(wave, (3, 3)))
+
+    def full_integrate(self, is_: int, nn: int, mode: int, om: complex):
+        omv = np.array([om.real, om.imag])
+        out = np.zeros(2)
+        fr = C.c_int(0)
+        self.L.oracle_full_integrate(is_, nn, mode, _p(omv), _p(out), C.byref(fr))
+        return complex(out[0], out[1]), bool(fr.value)
+
+    def eval_fit(self, is_: int, iperp: int, p: complex):
+        pv = np.array([p.real, p.imag])
+        out = np.zeros(2)
+        self.L.oracle_eval_fit(is_, iperp, _p(pv), _p(out))
+        return complex(out[0], out[1])
+
+    def int_ee(self, is_: int) -> float:
+        return self.L.oracle_int_ee(is_)
+
+    def nlim(self):
+        cap = 4096
+        n = C.c_int(0)
+        a = np.zeros(cap, dtype=np.int32)
+        b = np.zeros(cap, dtype=np.int32)
+        c = np.zeros(cap, dtype=np.int32)
+        self.L.oracle_get_nlim(C.byref(n), _p(a), _p(b), _p(c), cap)
+        return [(int(a[i]), int(b[i]), int(c[i])) for i in range(n.value)]
+
+
+def bessj(n: int, x: float) -> float:
+    return lib().oracle_bessj(n, x)
