@@ -1,0 +1,80 @@
+"""ctypes binding of the C ABI in include/alps_b200.h (libalps_b200.so, built in-tree by
+alps_b200/csrc/Makefile).  There is no fallback: a missing library or a failing call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libalps_b200.so")
+_LIB = None
+
+SYMBOLS = [
+    "alps_b200_init", "alps_b200_finalize", "alps_b200_last_error", "alps_b200_set_species",
+    "alps_b200_upload", "alps_b200_derivative_f0", "alps_b200_set_k", "alps_b200_disp",
+    "alps_b200_disp_batch", "alps_b200_disp_batch_dev", "alps_b200_add_external_chi",
+    "alps_b200_set_harmonic_shard", "alps_b200_chi_partial_len", "alps_b200_chi_partial_dev",
+    "alps_b200_assemble_dev", "alps_b200_set_mode", "alps_b200_set_stream", "alps_b200_sync",
+    "alps_b200_get_info", "alps_b200_dfma_peak",
+]
+
+INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH = range(5)
+
+
+class Cfg(C.Structure):
+    _fields_ = [("nspec", C.c_int), ("nperp", C.c_int), ("npar", C.c_int), ("ngamma", C.c_int),
+                ("npparbar", C.c_int), ("vA", C.c_double), ("Bessel_zero", C.c_double),
+                ("Tlim", C.c_double), ("positions_principal", C.c_int),
+                ("n_resonance_interval", C.c_int), ("kperp_norm", C.c_int),
+                ("emulate_nproc", C.c_int), ("maxfits", C.c_int), ("maxorder", C.c_int),
+                ("device", C.c_int), ("nmax_cap", C.c_int), ("batch_max", C.c_int)]
+
+
+class AlpsB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("alps_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA extension for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.check_call(["make", "-C", csrc, "-s", "clean"])
+    subprocess.check_call(["make", "-C", csrc, "-s"])
+    return SO_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise AlpsB200Error(-1, "%s is missing: run `make -C alps_b200/csrc` (or "
+                                "__graft_entry__.build()); there is no CPU fallback" % SO_PATH)
+        L = C.CDLL(SO_PATH)
+        L.alps_b200_last_error.restype = C.c_char_p
+        L.alps_b200_set_species.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_int, C.c_double]
+        L.alps_b200_upload.argtypes = [C.c_void_p] * 4
+        L.alps_b200_derivative_f0.argtypes = [C.c_void_p] * 2
+        L.alps_b200_set_k.argtypes = [C.c_double, C.c_double, C.c_void_p]
+        L.alps_b200_disp.argtypes = [C.c_void_p] * 5
+        L.alps_b200_disp_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.alps_b200_disp_batch_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.alps_b200_add_external_chi.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.alps_b200_set_harmonic_shard.argtypes = [C.c_int, C.c_int]
+        L.alps_b200_chi_partial_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.alps_b200_assemble_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.alps_b200_set_mode.argtypes = [C.c_int]
+        L.alps_b200_set_stream.argtypes = [C.c_void_p]
+        L.alps_b200_get_info.argtypes = [C.c_int, C.c_void_p]
+        L.alps_b200_dfma_peak.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int):
+    if rc != 0:
+        raise AlpsB200Error(rc, lib().alps_b200_last_error().decode())

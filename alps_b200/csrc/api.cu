@@ -1,0 +1,761 @@
+// alps_b200: C ABI (include/alps_b200.h) and host-side state.  No CPU fallback: every entry
+// point needs an sm_100 device.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/alps_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace alps;
+
+namespace {
+
+struct SpeciesHost {
+  bool set = false;
+  std::vector<double> pperp, ppar;
+  double *d_pperp = nullptr, *d_ppar = nullptr, *d_A = nullptr, *d_C0 = nullptr, *d_Cp = nullptr;
+  double *d_J = nullptr, *d_W = nullptr, *d_pf = nullptr, *d_poly = nullptr, *d_ee = nullptr;
+  size_t cap_J = 0, cap_W = 0;
+  bool table = false;   // integrated from the f0 table by this library
+};
+
+struct State {
+  bool inited = false;
+  alps_b200_cfg cfg{};
+  int device = 0, sm_count = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  GlobalDev gh{};
+  GlobalDev* gd = nullptr;
+  SpeciesHost sp[MAXSPEC];
+  double *d_pp_f = nullptr, *d_df0_f = nullptr;   // Fortran-layout staging copies
+  bool have_tables = false, have_k = false;
+  // batch buffers
+  int batch = 0;
+  double *d_om = nullptr, *d_D = nullptr, *d_Sbulk = nullptr, *d_Sres = nullptr, *d_gwin = nullptr,
+         *d_partial = nullptr, *d_chi0 = nullptr, *d_chi0_low = nullptr, *d_wave = nullptr, *d_ext = nullptr;
+  PlanEntry* d_plan = nullptr;
+  int *d_work = nullptr, *d_work_count = nullptr, *d_err = nullptr;
+  QuadTile* d_tiles = nullptr;
+  std::vector<QuadTile> tiles;
+  QuadParams P{};
+  std::vector<double> ext;   // external chi, [nspec][PARTIAL_PER_SPEC]
+  bool ext_any = false;
+  int mode = 0;
+  int shard_rank = 0, shard_n = 1;
+  long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_kernel_ms = 0.0;
+  double *h_pin = nullptr;   // pinned staging for host <-> device omega / D traffic
+  size_t h_pin_bytes = 0;
+  char err[512] = "";
+  CUresult (*encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+} S;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(S.err, sizeof(S.err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ALPS_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  if (n == 0) return 0;
+  CK(cudaMalloc((void**)p, n * sizeof(T)));
+  return 0;
+}
+template <typename T>
+void dfree(T** p) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+}
+
+// Fortran element offsets (0-based), SURVEY.md 8.2
+inline size_t ipp(int nspec, int nperp, int npar, int is0, int iperp, int ipar, int c0) {
+  return is0 + (size_t)nspec * (iperp + (size_t)(nperp + 1) * (ipar + (size_t)(npar + 1) * c0));
+}
+
+void free_batch() {
+  dfree(&S.d_om); dfree(&S.d_D); dfree(&S.d_Sbulk); dfree(&S.d_Sres); dfree(&S.d_gwin); dfree(&S.d_partial);
+  dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work);
+  S.batch = 0;
+}
+
+int ensure_pinned(size_t bytes) {
+  if (bytes <= S.h_pin_bytes) return 0;
+  if (S.h_pin) cudaFreeHost(S.h_pin);
+  S.h_pin = nullptr;
+  S.h_pin_bytes = 0;
+  CK(cudaMallocHost((void**)&S.h_pin, bytes));
+  S.h_pin_bytes = bytes;
+  return 0;
+}
+
+// determine_nmax's "more processes than harmonics" bump and split_processes
+// (src/ALPS_fns.f90:4048-4064, 4079-4207) for an emulated MPI size: returns for each species the
+// highest harmonic any worker rank sums (ranges are contiguous from 0).
+void emulate_split(int nproc, int nspec, const bool* usebM, int* nmax, int* nhi) {
+  int max_procs = nspec;
+  for (int is = 0; is < nspec; is++) max_procs += nmax[is];
+  int is = 0;
+  while (max_procs < nproc - 1) {
+    if (!usebM[is]) nmax[is] += 1;
+    is += 1;
+    max_procs += 1;
+    if (is >= nspec) is = 0;
+  }
+  max_procs = nspec;
+  for (int i = 0; i < nspec; i++) max_procs += nmax[i];
+  int ideal_ns_per_proc = (int)ceilf((1.f * max_procs) / (1.f * nproc - 1.f));
+  std::vector<int> pps(nspec), split(nspec), rest(nspec);
+  int used = 0, largest_rest = 0, largest_spec = 0;
+  for (int i = 0; i < nspec; i++) {
+    pps[i] = (nmax[i] + 1 <= ideal_ns_per_proc) ? 1 : (nmax[i] + 1) / ideal_ns_per_proc;
+    split[i] = (nmax[i] + 1) / pps[i];
+    rest[i] = (nmax[i] + 1) % pps[i];
+    used += pps[i];
+  }
+  for (int i = 0; i < nspec; i++)
+    if (rest[i] > largest_rest) {
+      largest_spec = i;
+      largest_rest = rest[i];
+    }
+  pps[largest_spec] += (nproc - 1) - used;
+  split[largest_spec] = (int)lroundf((1.f * nmax[largest_spec] + 1.f) / (1.f * pps[largest_spec]));
+  for (int i = 0; i < nspec; i++) {
+    int hi = -1;
+    for (int local = 1; local <= pps[i]; local++) {
+      int n1 = (local - 1) * split[i], n2 = n1 + split[i] - 1;
+      if (local == pps[i] && n1 <= nmax[i]) n2 = nmax[i];
+      hi = std::max(hi, n2);
+    }
+    nhi[i] = std::max(hi, 0);
+  }
+}
+
+int build_tables_from_df0() {
+  // needs d_df0_f (Fortran layout) on the device
+  const int nspec = S.cfg.nspec, nperp = S.cfg.nperp, npar = S.cfg.npar;
+  for (int s = 0; s < nspec; s++) {
+    SpeciesHost& h = S.sp[s];
+    SpeciesDev& d = S.gh.sp[s];
+    if (!h.table) continue;
+    const int ldp = (npar - 1 + 1) & ~1;
+    d.ldp = ldp;
+    size_t n = (size_t)(nperp - 1) * ldp;
+    if (dalloc(&h.d_A, n) || dalloc(&h.d_C0, n) || dalloc(&h.d_Cp, n) || dalloc(&h.d_ee, 1)) return ALPS_B200_ERR_CUDA;
+    CK(cudaMemsetAsync(h.d_A, 0, n * sizeof(double), S.stream));
+    CK(cudaMemsetAsync(h.d_C0, 0, n * sizeof(double), S.stream));
+    launch_build_AC(S.d_df0_f, h.d_pperp, h.d_ppar, h.d_A, h.d_C0, nspec, nperp, npar, s, d.qs, d.ms, ldp, S.stream);
+    launch_int_ee(S.d_df0_f, h.d_pperp, h.d_ppar, nspec, nperp, npar, s, d.qs, d.ms, d.dpperp, d.dppar_abs, h.d_ee,
+                  S.stream);
+    S.launches += 2;
+    CK(cudaMemcpyAsync(&d.int_ee, h.d_ee, sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    d.A = h.d_A;
+    d.Cp = h.d_Cp;
+  }
+  CK(cudaStreamSynchronize(S.stream));
+  CK(cudaGetLastError());
+  dfree(&S.d_df0_f);
+  S.have_tables = true;
+  S.have_k = false;
+  return 0;
+}
+
+int make_tmap(CUtensorMap* tm, const double* base, uint64_t inner, uint64_t rows, uint64_t pitch_elems,
+              uint32_t box_inner, uint32_t box_rows) {
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {pitch_elems * sizeof(double)};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = S.encodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ALPS_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+  return 0;
+}
+
+int ensure_batch(int want) {
+  if (S.batch >= want && S.d_om) return 0;
+  free_batch();
+  const size_t NI = S.gh.NI, B = want;
+  if (dalloc(&S.d_om, 2 * B) || dalloc(&S.d_D, 2 * B) || dalloc(&S.d_Sbulk, B * NI * 12) ||
+      dalloc(&S.d_Sres, B * NI * 12) || dalloc(&S.d_gwin, B * NI * S.gh.WIN * 6) ||
+      dalloc(&S.d_partial, B * S.gh.nspec * PARTIAL_PER_SPEC) || dalloc(&S.d_chi0, B * S.gh.nspec * 18) ||
+      dalloc(&S.d_chi0_low, B * S.gh.nspec * 54) || dalloc(&S.d_wave, B * 18) || dalloc(&S.d_plan, B * NI) ||
+      dalloc(&S.d_work, B * NI))
+    return ALPS_B200_ERR_CUDA;
+  S.batch = want;
+  return 0;
+}
+
+int auto_batch() {
+  if (S.cfg.batch_max > 0) return S.cfg.batch_max;
+  const size_t per_om = (size_t)S.gh.NI * (sizeof(PlanEntry) + 2 * 96 + (size_t)S.gh.WIN * 48 + 4) + 1024;
+  size_t b = ((size_t)2 << 30) / per_om;
+  const size_t unit = S.sm_count > 0 ? S.sm_count : 148;
+  b = std::min<size_t>(b, 16384);
+  b = std::max<size_t>(b, unit);
+  b = (b / unit) * unit;
+  return (int)b;
+}
+
+// run the hot path for n omegas already on the device (n <= S.batch)
+int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, const double* d_partial_in,
+              bool want_aux) {
+  const GlobalDev* gd = S.gd;
+  if (!d_partial_in) {
+    launch_plan(gd, S.gh, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream);
+    S.P.om = d_om;
+    S.P.n_om = n;
+    cudaEventRecord(S.ev0, S.stream);
+    cudaError_t e = launch_quad(S.P, S.stream);
+    cudaEventRecord(S.ev1, S.stream);
+    if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
+    launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.stream);
+    double* part = d_partial_out ? d_partial_out : S.d_partial;
+    launch_chi_partial(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.d_Sres, part, S.stream);
+    S.launches += 4;
+    if (d_partial_out) return 0;
+    d_partial_in = part;
+  }
+  launch_assemble(gd, S.gh, d_om, n, d_partial_in, S.ext_any ? S.d_ext : nullptr, d_D,
+                  want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr, want_aux ? S.d_wave : nullptr,
+                  S.stream);
+  S.launches += 1;
+  return 0;
+}
+
+int check_ready() {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (!S.have_tables) return fail(ALPS_B200_ERR_USAGE, "no f0 tables: call alps_b200_upload (+ derivative_f0) first");
+  if (!S.have_k) return fail(ALPS_B200_ERR_USAGE, "alps_b200_set_k has not been called");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* alps_b200_last_error(void) { return S.err; }
+
+int alps_b200_init(const alps_b200_cfg* cfg) {
+  if (!cfg) return fail(ALPS_B200_ERR_USAGE, "cfg is NULL");
+  alps_b200_finalize();
+  if (cfg->nspec < 1 || cfg->nspec > MAXSPEC) return fail(ALPS_B200_ERR_USAGE, "nspec must be in [1,%d]", MAXSPEC);
+  if (cfg->nperp < 4 || cfg->npar < 8) return fail(ALPS_B200_ERR_USAGE, "grid too small");
+  if (cfg->maxfits > MAXFITS) return fail(ALPS_B200_ERR_USAGE, "maxfits > %d", MAXFITS);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(ALPS_B200_ERR_CUDA, "no CUDA device available (%s); alps_b200 has no CPU fallback",
+                cudaGetErrorString(e));
+  int dev = cfg->device;
+  if (dev < 0) CK(cudaGetDevice(&dev));
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10)
+    return fail(ALPS_B200_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", dev, prop.name,
+                prop.major, prop.minor);
+  S.device = dev;
+  S.sm_count = prop.multiProcessorCount;
+  S.cfg = *cfg;
+  if (S.cfg.nmax_cap <= 0) S.cfg.nmax_cap = 2000;
+  CK(cudaStreamCreateWithFlags(&S.own_stream, cudaStreamNonBlocking));
+  S.stream = S.own_stream;
+  CK(cudaEventCreate(&S.ev0));
+  CK(cudaEventCreate(&S.ev1));
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess)
+    return fail(ALPS_B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  S.encodeTiled = (decltype(S.encodeTiled))fn;
+  memset(&S.gh, 0, sizeof(S.gh));
+  S.gh.nspec = cfg->nspec;
+  S.gh.nperp = cfg->nperp;
+  S.gh.npar = cfg->npar;
+  S.gh.M_I = cfg->positions_principal;
+  S.gh.M_P = cfg->n_resonance_interval;
+  S.gh.WIN = 2 * cfg->positions_principal + 7;
+  S.gh.kperp_norm = cfg->kperp_norm;
+  S.gh.maxfits = cfg->maxfits > 0 ? cfg->maxfits : 1;
+  S.gh.maxorder = cfg->maxorder;
+  S.gh.vA = cfg->vA;
+  S.gh.Tlim = cfg->Tlim;
+  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 1) ||
+      dalloc(&S.d_ext, (size_t)cfg->nspec * PARTIAL_PER_SPEC))
+    return ALPS_B200_ERR_CUDA;
+  CK(cudaMemset(S.d_err, 0, sizeof(int)));
+  S.ext.assign((size_t)cfg->nspec * PARTIAL_PER_SPEC, 0.0);
+  S.ext_any = false;
+  S.mode = 0;
+  S.shard_rank = 0;
+  S.shard_n = 1;
+  S.launches = 0;
+  S.inited = true;
+  S.err[0] = 0;
+  return 0;
+}
+
+void alps_b200_finalize(void) {
+  if (!S.inited) return;
+  cudaDeviceSynchronize();
+  for (int s = 0; s < MAXSPEC; s++) {
+    SpeciesHost& h = S.sp[s];
+    dfree(&h.d_pperp); dfree(&h.d_ppar); dfree(&h.d_A); dfree(&h.d_C0); dfree(&h.d_Cp); dfree(&h.d_J);
+    dfree(&h.d_W); dfree(&h.d_pf); dfree(&h.d_poly); dfree(&h.d_ee);
+    h = SpeciesHost();
+  }
+  free_batch();
+  dfree(&S.d_pp_f); dfree(&S.d_df0_f); dfree(&S.gd); dfree(&S.d_work_count); dfree(&S.d_err); dfree(&S.d_ext);
+  dfree(&S.d_tiles);
+  if (S.h_pin) cudaFreeHost(S.h_pin);
+  S.h_pin = nullptr;
+  S.h_pin_bytes = 0;
+  if (S.ev0) cudaEventDestroy(S.ev0);
+  if (S.ev1) cudaEventDestroy(S.ev1);
+  S.ev0 = S.ev1 = nullptr;
+  if (S.own_stream) cudaStreamDestroy(S.own_stream);
+  S.own_stream = S.stream = nullptr;
+  S.tiles.clear();
+  S.have_tables = S.have_k = false;
+  S.inited = false;
+}
+
+int alps_b200_set_species(int is, double ns, double qs, double ms, int relativistic, int usebM, int ACmethod,
+                          int n_fits, const int* fit_type, const double* perp_correction, int logfit,
+                          int poly_kind, int poly_order, double poly_log_max) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (is < 1 || is > S.cfg.nspec) return fail(ALPS_B200_ERR_USAGE, "species index %d out of range", is);
+  if (n_fits > MAXFITS || n_fits > S.gh.maxfits) return fail(ALPS_B200_ERR_USAGE, "n_fits exceeds maxfits");
+  if (relativistic)
+    return fail(ALPS_B200_ERR_UNSUPPORTED, "relativistic species (ALPS_fns_rel) are not built yet");
+  SpeciesDev& d = S.gh.sp[is - 1];
+  d.ns = ns; d.qs = qs; d.ms = ms;
+  d.relativistic = relativistic; d.usebM = usebM; d.ACmethod = ACmethod; d.n_fits = n_fits;
+  for (int i = 0; i < n_fits; i++) {
+    d.fit_type[i] = fit_type[i];
+    d.perp_correction[i] = perp_correction[i];
+    if (ACmethod == 1 && (fit_type[i] == 4 || fit_type[i] == 5))
+      return fail(ALPS_B200_ERR_UNSUPPORTED, "fit types 4/5 need the relativistic grid (not built yet)");
+  }
+  d.logfit = logfit; d.poly_kind = poly_kind; d.poly_order = poly_order; d.poly_log_max = poly_log_max;
+  S.sp[is - 1].set = true;
+  S.sp[is - 1].table = !usebM && !relativistic;
+  return 0;
+}
+
+int alps_b200_upload(const double* pp, const double* df0, const double* param_fit, const double* poly_fit_coeffs) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (!pp) return fail(ALPS_B200_ERR_USAGE, "pp is NULL");
+  const int nspec = S.cfg.nspec, nperp = S.cfg.nperp, npar = S.cfg.npar;
+  for (int s = 0; s < nspec; s++)
+    if (!S.sp[s].set) return fail(ALPS_B200_ERR_USAGE, "species %d not set", s + 1);
+  // validate that the grid is separable and extract the axes the reference reads:
+  // p_perp = pp(is,iperp,1,1) (src/ALPS_fns.f90:4243, 1436), p_par = pp(is,2,ipar,2) (:957-961)
+  for (int s = 0; s < nspec; s++) {
+    SpeciesHost& h = S.sp[s];
+    SpeciesDev& d = S.gh.sp[s];
+    h.pperp.assign(nperp + 1, 0.0);
+    h.ppar.assign(npar + 1, 0.0);
+    if (h.table) {
+      for (int i = 0; i <= nperp; i++) h.pperp[i] = pp[ipp(nspec, nperp, npar, s, i, 1, 0)];
+      for (int j = 0; j <= npar; j++) h.ppar[j] = pp[ipp(nspec, nperp, npar, s, 2, j, 1)];
+      for (int j = 0; j <= npar; j++)
+        for (int i = 0; i <= nperp; i++)
+          if (pp[ipp(nspec, nperp, npar, s, i, j, 0)] != h.pperp[i] || pp[ipp(nspec, nperp, npar, s, i, j, 1)] != h.ppar[j])
+            return fail(ALPS_B200_ERR_GRID, "species %d: (p_perp,p_par) grid is not separable at (%d,%d)", s + 1, i, j);
+      for (int j = 1; j <= npar; j++)
+        if (!(h.ppar[j] > h.ppar[j - 1])) return fail(ALPS_B200_ERR_GRID, "species %d: p_par not increasing", s + 1);
+      d.dpperp = h.pperp[2] - h.pperp[1];
+      d.dppar_signed = h.ppar[2] - h.ppar[1];
+      d.dppar_abs = fabs(d.dppar_signed);
+    }
+    if (dalloc(&h.d_pperp, nperp + 1) || dalloc(&h.d_ppar, npar + 1)) return ALPS_B200_ERR_CUDA;
+    CK(cudaMemcpy(h.d_pperp, h.pperp.data(), (nperp + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.d_ppar, h.ppar.data(), (npar + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    d.pperp = h.d_pperp;
+    d.ppar = h.d_ppar;
+    d.ldj = nperp + 1;
+    // param_fit(is,iperp,ip,ifit) -> [iperp][ifit][ip] for this species
+    const int mf = S.gh.maxfits;
+    const int nperpmax = std::max(nperp, S.cfg.ngamma);
+    std::vector<double> pf((size_t)(nperp + 1) * mf * 5, 0.0);
+    if (param_fit)
+      for (int i = 0; i <= nperp; i++)
+        for (int f = 0; f < mf; f++)
+          for (int ip = 0; ip < 5; ip++)
+            pf[((size_t)i * mf + f) * 5 + ip] = param_fit[s + (size_t)nspec * (i + (size_t)(nperpmax + 1) * (ip + 5 * f))];
+    if (dalloc(&h.d_pf, pf.size())) return ALPS_B200_ERR_CUDA;
+    CK(cudaMemcpy(h.d_pf, pf.data(), pf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.param_fit = h.d_pf;
+    const int mo = S.gh.maxorder;
+    std::vector<double> po((size_t)(nperp + 1) * (mo + 1), 0.0);
+    if (poly_fit_coeffs)
+      for (int i = 0; i <= nperp; i++)
+        for (int k = 0; k <= mo; k++) po[(size_t)i * (mo + 1) + k] = poly_fit_coeffs[s + (size_t)nspec * (i + (size_t)(nperp + 1) * k)];
+    if (dalloc(&h.d_poly, po.size())) return ALPS_B200_ERR_CUDA;
+    CK(cudaMemcpy(h.d_poly, po.data(), po.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.poly = h.d_poly;
+    if (d.ACmethod == 1 && !param_fit && h.table) return fail(ALPS_B200_ERR_USAGE, "param_fit needed for species %d", s + 1);
+    if (d.ACmethod == 2 && !poly_fit_coeffs && h.table) return fail(ALPS_B200_ERR_USAGE, "poly_fit_coeffs needed for species %d", s + 1);
+  }
+  const size_t npp = (size_t)nspec * (nperp + 1) * (npar + 1) * 2;
+  if (dalloc(&S.d_pp_f, npp)) return ALPS_B200_ERR_CUDA;
+  CK(cudaMemcpy(S.d_pp_f, pp, npp * sizeof(double), cudaMemcpyHostToDevice));
+  S.have_tables = false;
+  S.have_k = false;
+  if (df0) {
+    const size_t nd = (size_t)nspec * (nperp - 1) * (npar - 1) * 2;
+    if (dalloc(&S.d_df0_f, nd)) return ALPS_B200_ERR_CUDA;
+    CK(cudaMemcpy(S.d_df0_f, df0, nd * sizeof(double), cudaMemcpyHostToDevice));
+    return build_tables_from_df0();
+  }
+  return 0;
+}
+
+int alps_b200_derivative_f0(const double* f0, double* df0_out) {
+  if (!S.inited || !S.d_pp_f) return fail(ALPS_B200_ERR_USAGE, "call alps_b200_upload before alps_b200_derivative_f0");
+  if (!f0) return fail(ALPS_B200_ERR_USAGE, "f0 is NULL");
+  const int nspec = S.cfg.nspec, nperp = S.cfg.nperp, npar = S.cfg.npar;
+  const size_t nf = (size_t)nspec * (nperp + 1) * (npar + 1), nd = (size_t)nspec * (nperp - 1) * (npar - 1) * 2;
+  double* d_f0 = nullptr;
+  if (dalloc(&d_f0, nf) || dalloc(&S.d_df0_f, nd)) return ALPS_B200_ERR_CUDA;
+  CK(cudaMemcpy(d_f0, f0, nf * sizeof(double), cudaMemcpyHostToDevice));
+  launch_derivative_f0(d_f0, S.d_pp_f, S.d_df0_f, nspec, nperp, npar, S.stream);
+  S.launches += 1;
+  CK(cudaStreamSynchronize(S.stream));
+  CK(cudaGetLastError());
+  // use_bM species: df0 = 0 (src/ALPS_fns.f90:98-100) -- their rows are never read
+  if (df0_out) CK(cudaMemcpy(df0_out, S.d_df0_f, nd * sizeof(double), cudaMemcpyDeviceToHost));
+  dfree(&d_f0);
+  return build_tables_from_df0();
+}
+
+int alps_b200_set_harmonic_shard(int rank, int nranks) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ALPS_B200_ERR_USAGE, "bad shard %d/%d", rank, nranks);
+  S.shard_rank = rank;
+  S.shard_n = nranks;
+  S.have_k = false;   // tiles and plan depend on the shard: set_k must be called again
+  return 0;
+}
+
+int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (!S.have_tables) return fail(ALPS_B200_ERR_USAGE, "no f0 tables: call alps_b200_upload (+ derivative_f0) first");
+  if (kpar == 0.0) return fail(ALPS_B200_ERR_USAGE, "kpar must be non-zero");
+  const int nspec = S.cfg.nspec, nperp = S.cfg.nperp, npar = S.cfg.npar;
+  const bool kperp_changed = !S.have_k || kperp != S.gh.kperp;
+  S.gh.kperp = kperp;
+  S.gh.kpar = kpar;
+  int nmax[MAXSPEC], nhi[MAXSPEC];
+  bool usebM[MAXSPEC];
+  // ---- determine_nmax (src/ALPS_fns.f90:4002-4046): first n with max_iperp |J_n| <= Bessel_zero
+  double* d_bm = nullptr;
+  const int CH = 64;
+  if (dalloc(&d_bm, CH)) return ALPS_B200_ERR_CUDA;
+  std::vector<double> bm(CH);
+  for (int s = 0; s < nspec; s++) {
+    usebM[s] = S.gh.sp[s].usebM != 0;
+    if (!S.sp[s].table) {
+      nmax[s] = 1;
+      continue;
+    }
+    if (!kperp_changed) {
+      nmax[s] = S.gh.sp[s].nmax;
+      continue;
+    }
+    int found = -1;
+    for (int n0 = 1; n0 <= S.cfg.nmax_cap && found < 0; n0 += CH) {
+      launch_bessel_max(S.sp[s].d_pperp, nperp, kperp, S.gh.sp[s].qs, n0, CH, d_bm, S.stream);
+      S.launches += 1;
+      CK(cudaMemcpyAsync(bm.data(), d_bm, CH * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+      CK(cudaStreamSynchronize(S.stream));
+      for (int i = 0; i < CH; i++)
+        if (!(bm[i] > S.cfg.Bessel_zero)) {
+          found = n0 + i;
+          break;
+        }
+    }
+    if (found < 0) {
+      dfree(&d_bm);
+      return fail(ALPS_B200_ERR_NMAX, "species %d: nmax exceeds nmax_cap=%d", s + 1, S.cfg.nmax_cap);
+    }
+    nmax[s] = found;
+  }
+  dfree(&d_bm);
+  if (S.cfg.emulate_nproc > 0 && kperp_changed) {
+    emulate_split(S.cfg.emulate_nproc, nspec, usebM, nmax, nhi);
+  } else if (kperp_changed) {
+    for (int s = 0; s < nspec; s++) nhi[s] = nmax[s];
+  } else {
+    for (int s = 0; s < nspec; s++) nhi[s] = S.gh.sp[s].nhi;
+  }
+  // ---- tables
+  int item_base = 0;
+  S.tiles.clear();
+  for (int s = 0; s < nspec; s++) {
+    SpeciesHost& h = S.sp[s];
+    SpeciesDev& d = S.gh.sp[s];
+    d.nmax = nmax[s];
+    d.nhi = h.table ? nhi[s] : 0;
+    d.item_base = item_base;
+    item_base += 2 * (d.nhi + 1);
+    // harmonic shard of this process: contiguous blocks of [0,nhi]
+    {
+      const int tot = d.nhi + 1, per = (tot + S.shard_n - 1) / S.shard_n;
+      d.nlo_shard = std::min(S.shard_rank * per, tot);
+      d.nhi_shard = std::min(d.nlo_shard + per, tot) - 1;
+    }
+    if (!h.table) continue;
+    if (kperp_changed) {
+      const size_t nJ = (size_t)(d.nhi + 3) * d.ldj;
+      if (nJ > h.cap_J) {
+        if (dalloc(&h.d_J, nJ)) return ALPS_B200_ERR_CUDA;
+        h.cap_J = nJ;
+      }
+      d.ldw = (3 * (d.nhi + 1) + 1) & ~1;
+      const size_t nW = (size_t)(nperp - 1) * d.ldw;
+      if (nW > h.cap_W) {
+        if (dalloc(&h.d_W, nW)) return ALPS_B200_ERR_CUDA;
+        h.cap_W = nW;
+      }
+      CK(cudaMemsetAsync(h.d_W, 0, nW * sizeof(double), S.stream));
+      launch_bessel_table(h.d_pperp, nperp, kperp, d.qs, d.nhi, h.d_J, d.ldj, S.stream);
+      launch_build_W(h.d_pperp, h.d_J, d.ldj, nperp, d.nhi, h.d_W, d.ldw, S.stream);
+      S.launches += 2;
+      d.J = h.d_J;
+      d.W = h.d_W;
+    }
+    // C' = kpar * C0
+    launch_scale(h.d_C0, h.d_Cp, kpar, (size_t)(nperp - 1) * d.ldp, S.stream);
+    S.launches += 1;
+    for (int n0 = d.nlo_shard; n0 <= d.nhi_shard; n0 += NH) S.tiles.push_back(QuadTile{s, n0});
+    if (make_tmap(&S.P.tmA[s], h.d_A, npar - 1, nperp - 1, d.ldp, BN, BK) ||
+        make_tmap(&S.P.tmC[s], h.d_Cp, npar - 1, nperp - 1, d.ldp, BN, BK) ||
+        make_tmap(&S.P.tmW[s], h.d_W, 3 * (d.nhi + 1), nperp - 1, d.ldw, BM, BK))
+      return ALPS_B200_ERR_CUDA;
+  }
+  const bool ni_changed = item_base != S.gh.NI;
+  S.gh.NI = item_base;
+  CK(cudaMemcpyAsync(S.gd, &S.gh, sizeof(GlobalDev), cudaMemcpyHostToDevice, S.stream));
+  if (dalloc(&S.d_tiles, S.tiles.size())) return ALPS_B200_ERR_CUDA;
+  if (!S.tiles.empty())
+    CK(cudaMemcpyAsync(S.d_tiles, S.tiles.data(), S.tiles.size() * sizeof(QuadTile), cudaMemcpyHostToDevice, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  CK(cudaGetLastError());
+  if (ni_changed) free_batch();
+  S.P.tiles = S.d_tiles;
+  S.P.ntiles = (int)S.tiles.size();
+  S.P.g = S.gd;
+  S.have_k = true;
+  if (nmax_out)
+    for (int s = 0; s < nspec; s++) nmax_out[s] = nmax[s];
+  return 0;
+}
+
+static int bind_batch(int n) {
+  int want = std::min(std::max(n, 1), auto_batch());
+  // keep a larger existing allocation
+  if (S.batch < want || !S.d_om) {
+    int rc = ensure_batch(want);
+    if (rc) return rc;
+  }
+  S.P.plan = S.d_plan;
+  S.P.Sbulk = S.d_Sbulk;
+  S.P.gwin = S.d_gwin;
+  return 0;
+}
+
+static int check_device_errors() {
+  int herr = 0;
+  CK(cudaMemcpyAsync(&herr, S.d_err, sizeof(int), cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  CK(cudaGetLastError());
+  if (herr) {
+    cudaMemset(S.d_err, 0, sizeof(int));
+    return fail(ALPS_B200_ERR_CUDA, "resonance window overflow in the near-pole quadrature");
+  }
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, S.ev0, S.ev1) == cudaSuccess) S.last_kernel_ms = ms;
+  return 0;
+}
+
+int alps_b200_disp_batch_dev(int n, const double* d_om, double* d_D) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (n <= 0) return 0;
+  if ((rc = bind_batch(n))) return rc;
+  for (int o = 0; o < n; o += S.batch) {
+    int m = std::min(S.batch, n - o);
+    if ((rc = run_chunk(m, d_om + 2 * (size_t)o, d_D + 2 * (size_t)o, nullptr, nullptr, false))) return rc;
+  }
+  return 0;
+}
+
+int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (n <= 0) return 0;
+  if (!om || !D) return fail(ALPS_B200_ERR_USAGE, "om / D is NULL");
+  if ((rc = bind_batch(n))) return rc;
+  const int nspec = S.cfg.nspec;
+  if ((rc = ensure_pinned((size_t)S.batch * 4 * sizeof(double)))) return rc;
+  double* h_om = S.h_pin;
+  double* h_D = S.h_pin + 2 * (size_t)S.batch;
+  for (int o = 0; o < n; o += S.batch) {
+    int m = std::min(S.batch, n - o);
+    memcpy(h_om, om + 2 * (size_t)o, (size_t)m * 2 * sizeof(double));
+    CK(cudaMemcpyAsync(S.d_om, h_om, (size_t)m * 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    if ((rc = run_chunk(m, S.d_om, S.d_D, nullptr, nullptr, chi0_opt != nullptr))) return rc;
+    CK(cudaMemcpyAsync(h_D, S.d_D, (size_t)m * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    if (chi0_opt)
+      CK(cudaMemcpyAsync(chi0_opt + (size_t)o * nspec * 18, S.d_chi0, (size_t)m * nspec * 18 * sizeof(double),
+                         cudaMemcpyDeviceToHost, S.stream));
+    if ((rc = check_device_errors())) return rc;
+    memcpy(D + 2 * (size_t)o, h_D, (size_t)m * 2 * sizeof(double));
+  }
+  return 0;
+}
+
+int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_low, double* wave) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (!om) return fail(ALPS_B200_ERR_USAGE, "om is NULL");
+  if ((rc = bind_batch(1))) return rc;
+  const int nspec = S.cfg.nspec;
+  if ((rc = ensure_pinned(64 * sizeof(double)))) return rc;
+  S.h_pin[0] = om[0];
+  S.h_pin[1] = om[1];
+  CK(cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+  const bool aux = chi0 || chi0_low || wave;
+  if ((rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, aux))) return rc;
+  CK(cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  if (chi0) CK(cudaMemcpyAsync(chi0, S.d_chi0, (size_t)nspec * 18 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  if (chi0_low)
+    CK(cudaMemcpyAsync(chi0_low, S.d_chi0_low, (size_t)nspec * 54 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  if (wave) CK(cudaMemcpyAsync(wave, S.d_wave, 18 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  if ((rc = check_device_errors())) return rc;
+  if (D) {
+    D[0] = S.h_pin[2];
+    D[1] = S.h_pin[3];
+  }
+  // external (NHDS) contributions are per omega: consumed by this call
+  if (S.ext_any) {
+    std::fill(S.ext.begin(), S.ext.end(), 0.0);
+    S.ext_any = false;
+  }
+  return 0;
+}
+
+int alps_b200_add_external_chi(int is, const double* chi, const double* chi_low) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (is < 1 || is > S.cfg.nspec || !chi) return fail(ALPS_B200_ERR_USAGE, "bad arguments");
+  // chi(3,3), chi_low(3,3,-1:1) column-major complex -> [mode][..] of PARTIAL layout
+  static const int MI[6] = {0, 1, 2, 0, 0, 1}, MJ[6] = {0, 1, 2, 1, 2, 2};
+  double* o = S.ext.data() + (size_t)(is - 1) * PARTIAL_PER_SPEC;
+  for (int c = 0; c < 6; c++) {
+    const int k = MI[c] + 3 * MJ[c];
+    o[2 * c] = chi[2 * k];
+    o[2 * c + 1] = chi[2 * k + 1];
+    for (int m = 0; m < 3; m++) {
+      const int kl = MI[c] + 3 * (MJ[c] + 3 * m);
+      o[2 * (6 + 3 * c + m)] = chi_low ? chi_low[2 * kl] : 0.0;
+      o[2 * (6 + 3 * c + m) + 1] = chi_low ? chi_low[2 * kl + 1] : 0.0;
+    }
+  }
+  CK(cudaMemcpy(S.d_ext, S.ext.data(), S.ext.size() * sizeof(double), cudaMemcpyHostToDevice));
+  S.ext_any = true;
+  return 0;
+}
+
+int alps_b200_chi_partial_len(void) { return S.inited ? S.cfg.nspec * PARTIAL_PER_SPEC : 0; }
+
+int alps_b200_chi_partial_dev(int n, const double* d_om, double* d_partial) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (n <= 0) return 0;
+  if ((rc = bind_batch(n))) return rc;
+  const size_t len = (size_t)S.cfg.nspec * PARTIAL_PER_SPEC;
+  for (int o = 0; o < n; o += S.batch) {
+    int m = std::min(S.batch, n - o);
+    if ((rc = run_chunk(m, d_om + 2 * (size_t)o, nullptr, d_partial + (size_t)o * len, nullptr, false))) return rc;
+  }
+  return 0;
+}
+
+int alps_b200_assemble_dev(int n, const double* d_om, const double* d_partial, double* d_D) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (n <= 0) return 0;
+  return run_chunk(n, d_om, d_D, nullptr, d_partial, false);
+}
+
+int alps_b200_set_mode(int mode) {
+  if (mode != 0) return fail(ALPS_B200_ERR_UNSUPPORTED, "mode %d not built yet", mode);
+  S.mode = mode;
+  return 0;
+}
+
+int alps_b200_set_stream(void* cuda_stream) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  S.stream = cuda_stream ? (cudaStream_t)cuda_stream : S.own_stream;
+  return 0;
+}
+
+int alps_b200_sync(void) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  return check_device_errors();
+}
+
+int alps_b200_get_info(int what, double* out) {
+  if (!S.inited || !out) return fail(ALPS_B200_ERR_USAGE, "bad arguments");
+  switch (what) {
+    case ALPS_B200_INFO_POINT_HARMONICS: {
+      double t = 0.0;
+      for (int s = 0; s < S.cfg.nspec; s++)
+        if (S.sp[s].table)
+          t += (2.0 * S.gh.sp[s].nhi + 1.0) * (S.cfg.nperp - 1.0) * (S.cfg.npar - 1.0);
+      *out = t;
+      return 0;
+    }
+    case ALPS_B200_INFO_LAUNCHES: *out = (double)S.launches; return 0;
+    case ALPS_B200_INFO_SM_COUNT: *out = S.sm_count; return 0;
+    case ALPS_B200_INFO_LAST_KERNEL_MS: *out = S.last_kernel_ms; return 0;
+    case ALPS_B200_INFO_BATCH: *out = S.have_k ? auto_batch() : 0; return 0;
+  }
+  return fail(ALPS_B200_ERR_USAGE, "unknown info id %d", what);
+}
+
+int alps_b200_dfma_peak(double* tflops) {
+  if (!S.inited || !tflops) return fail(ALPS_B200_ERR_USAGE, "bad arguments");
+  *tflops = run_dfma_peak(S.stream);
+  S.launches += 3;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// alps_b200: shared device-side definitions (sm_100a only).
+//
+// Data layout in HBM (per table species s; everything FP64):
+//   pperp[s][0..nperp], ppar[s][0..npar]        separable uniform grid (validated at upload)
+//   A [s][iperp-1][ipar-1]  = qs * df0/dp_perp                     row pitch ldp (ipar contiguous)
+//   Cp[s][iperp-1][ipar-1]  = qs * (kpar/ms) (p_perp df0/dp_par - p_par df0/dp_perp)   (per k)
+//   J [s][n+1][iperp]       = BESSJ(n, kperp p_perp/qs), n = -1..nhi+1, iperp = 0..nperp  (per k)
+//   W [s][iperp-1][3*n + x] = w_perp(iperp) * {J_n^2, p_perp J_n J_n', p_perp^2 J_n'^2}     (per k)
+// Per omega of a batch:
+//   plan [item]             resonance descriptor of (species, |n|, sign)
+//   Sbulk[item][6]          complex p_par-moment sums of the regular trapezoid quadrature
+//   Sres [item][6]          complex near-pole + Landau contributions (final units)
+//   gwin [item][WIN][3]     complex p_perp-sums at the p_par nodes around a resonance
+// item = omega * NI + item_base[s] + 2*|n| + sign, NI = sum_s 2 (nhi_s + 1).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace alps {
+
+constexpr int MAXSPEC = 8;
+constexpr int MAXFITS = 8;
+
+// ---- tile configuration of the quadrature kernel (see quad_kernel.cu)
+constexpr int NH = 16;           // harmonics per CTA tile
+constexpr int BM = 3 * NH;       // rows (3 Bessel weight types per harmonic)
+constexpr int BN = 128;          // p_par columns per tile
+constexpr int BK = 8;            // p_perp rows per pipeline stage
+constexpr int STAGES = 4;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int QUAD_THREADS = (CONSUMER_WARPS + 1) * 32;
+
+// ---- complex helpers (double2: x = re, y = im)
+typedef double2 cd;
+__host__ __device__ inline cd mk(double r, double i) { return make_double2(r, i); }
+__host__ __device__ inline cd operator+(cd a, cd b) { return mk(a.x + b.x, a.y + b.y); }
+__host__ __device__ inline cd operator-(cd a, cd b) { return mk(a.x - b.x, a.y - b.y); }
+__host__ __device__ inline cd operator-(cd a) { return mk(-a.x, -a.y); }
+__host__ __device__ inline cd operator*(cd a, cd b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__host__ __device__ inline cd operator*(double s, cd a) { return mk(s * a.x, s * a.y); }
+__host__ __device__ inline cd operator*(cd a, double s) { return mk(s * a.x, s * a.y); }
+__host__ __device__ inline cd operator/(cd a, double s) { return mk(a.x / s, a.y / s); }
+__host__ __device__ inline cd& operator+=(cd& a, cd b) { a.x += b.x; a.y += b.y; return a; }
+__host__ __device__ inline cd& operator-=(cd& a, cd b) { a.x -= b.x; a.y -= b.y; return a; }
+__host__ __device__ inline cd cmul_i(cd a) { return mk(-a.y, a.x); }   // i * a
+// complex division, Smith's algorithm (what libgcc's __divdc3 does in the common range)
+__host__ __device__ inline cd operator/(cd a, cd b) {
+  double r, den;
+  if (fabs(b.x) >= fabs(b.y)) {
+    r = b.y / b.x;
+    den = b.x + b.y * r;
+    return mk((a.x + a.y * r) / den, (a.y - a.x * r) / den);
+  }
+  r = b.x / b.y;
+  den = b.x * r + b.y;
+  return mk((a.x * r + a.y) / den, (a.y * r - a.x) / den);
+}
+__host__ __device__ inline cd operator/(double a, cd b) { return mk(a, 0.0) / b; }
+__host__ __device__ inline double cabs2(cd a) { return hypot(a.x, a.y); }
+
+// ---- per-species constants (device copy)
+struct SpeciesDev {
+  double ns, qs, ms;
+  int relativistic, usebM, ACmethod, n_fits;
+  int fit_type[MAXFITS];
+  double perp_correction[MAXFITS];
+  int logfit, poly_kind, poly_order;
+  double poly_log_max;
+  int nmax;        // determine_nmax result
+  int nhi;         // highest harmonic actually summed (>= nmax when emulating split_processes)
+  int nlo_shard, nhi_shard;   // harmonic shard owned by this process (inclusive)
+  int item_base;   // first item of this species in the per-omega item list
+  int ldp;         // row pitch of A / Cp (doubles)
+  int ldw;         // row pitch of W (doubles)
+  int ldj;         // row pitch of J (= nperp + 1)
+  const double* pperp;
+  const double* ppar;
+  const double* A;
+  const double* Cp;
+  const double* J;
+  const double* W;
+  const double* param_fit;   // [iperp][5][maxfits] for this species (repacked)
+  const double* poly;        // [iperp][maxorder+1]
+  double int_ee;             // omega-independent ee term, src/ALPS_fns.f90:1457-1555
+  double dpperp, dppar_abs, dppar_signed;
+};
+
+// ---- resonance plan of one (omega, species, |n|, sign), src/ALPS_fns.f90:641-745, 941-1006
+struct PlanEntry {
+  int lo1, hi1, lo2, hi2;    // p_par index ranges of the regular quadrature (hi < lo: empty)
+  int flags;                 // PLAN_*
+  int ipar_res;
+  int upperlimit;
+  int pad;
+};
+constexpr int PLAN_ACTIVE = 1;   // harmonic belongs to this process' shard and is summed
+constexpr int PLAN_RES = 2;      // determine_resonances found a resonance
+constexpr int PLAN_NEAR = 4;     // near-pole quadrature (not an edge fallback)
+constexpr int PLAN_LANDAU = 8;   // Landau residue term needed (Im(om) <= 0)
+
+struct GlobalDev {
+  int nspec, nperp, npar;
+  int NI;                    // items per omega
+  int WIN;                   // nodes per resonance window = 2*M_I + 7
+  int M_I, M_P;
+  int kperp_norm;
+  int maxfits, maxorder;
+  double vA, Tlim, kperp, kpar;
+  SpeciesDev sp[MAXSPEC];
+};
+
+// trapezoid weight of node ipar inside [lo,hi]: ends 1 (a single-node range counts twice,
+// exactly like integrate() with iparmin == iparmax, src/ALPS_fns.f90:838-862)
+__device__ __forceinline__ double range_w(int ipar, int lo, int hi) {
+  if (hi < lo || ipar < lo || ipar > hi) return 0.0;
+  return (ipar == lo ? 1.0 : 0.0) + (ipar == hi ? 1.0 : 0.0) + ((ipar > lo && ipar < hi) ? 2.0 : 0.0);
+}
+
+}  // namespace alps

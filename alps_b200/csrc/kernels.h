@@ -1,0 +1,61 @@
+// alps_b200: host-side declarations of the kernel launchers (internal; the public boundary is
+// include/alps_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace alps {
+
+struct QuadTile {
+  int s;    // species (0-based)
+  int n0;   // first harmonic of the tile
+};
+
+struct QuadParams {
+  CUtensorMap tmA[MAXSPEC];
+  CUtensorMap tmC[MAXSPEC];
+  CUtensorMap tmW[MAXSPEC];
+  const QuadTile* tiles;
+  const GlobalDev* g;
+  const double* om;        // 2 * n_om
+  const PlanEntry* plan;   // n_om * NI
+  double* Sbulk;           // n_om * NI * 12
+  double* gwin;            // n_om * NI * WIN * 6
+  int ntiles;
+  int n_om;
+};
+
+// set-up (setup_kernels.cu)
+void launch_derivative_f0(const double* f0, const double* pp, double* df0, int nspec, int nperp, int npar,
+                          cudaStream_t st);
+void launch_build_AC(const double* df0, const double* pperp, const double* ppar, double* A, double* C0, int nspec,
+                     int nperp, int npar, int is0, double qs, double ms, int ldp, cudaStream_t st);
+void launch_scale(const double* in, double* out, double s, size_t n, cudaStream_t st);
+void launch_bessel_max(const double* pperp, int nperp, double kperp, double qs, int n0, int count, double* out,
+                       cudaStream_t st);
+void launch_bessel_table(const double* pperp, int nperp, double kperp, double qs, int nhi, double* J, int ldj,
+                         cudaStream_t st);
+void launch_build_W(const double* pperp, const double* J, int ldj, int nperp, int nhi, double* W, int ldw,
+                    cudaStream_t st);
+void launch_int_ee(const double* df0, const double* pperp, const double* ppar, int nspec, int nperp, int npar,
+                   int is0, double qs, double ms, double dpperp, double dppar, double* out, cudaStream_t st);
+
+// hot path (quad_kernel.cu, resonant.cu)
+size_t quad_smem_bytes();
+cudaError_t launch_quad(const QuadParams& P, cudaStream_t st);
+void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
+                 int* work, int* work_count, cudaStream_t st);
+void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
+                     const int* work_count, const double* gwin, double* Sres, int* err_flag, cudaStream_t st);
+// chi partial layout per omega: [nspec][PARTIAL_PER_SPEC] doubles (see resonant.cu)
+constexpr int PARTIAL_PER_SPEC = 2 * (6 + 18);   // chi(6 modes) + chi_low(6 modes x 3) complex
+void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
+                        const double* Sbulk, const double* Sres, double* partial, cudaStream_t st);
+void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
+                     const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
+                     cudaStream_t st);
+double run_dfma_peak(cudaStream_t st);
+
+}  // namespace alps

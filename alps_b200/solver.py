@@ -1,0 +1,145 @@
+"""Host-side mirror of the reference's disp() interface over the C ABI.
+
+Names follow the reference (src/ALPS_fns.f90): `disp`, `derivative_f0`, `determine_nmax`
+(inside `set_k`), `map_search`, `refine_guess`, `secant_osc`, `om_scan`.  All numerical work
+happens in libalps_b200.so on the GPU; this module only marshals arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .tables import Plasma
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a):
+    """flat float64 copy in Fortran element order (what the Fortran side would hand over)"""
+    return None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))
+
+
+class Solver:
+    """One plasma (set of f0 tables) resident on one GPU.  Not re-entrant: the C ABI holds one
+    global instance, like the reference's module state."""
+
+    def __init__(self, plasma: Plasma, emulate_nproc: int = 0, device: int = -1, batch_max: int = 0,
+                 nmax_cap: int = 0):
+        self.L = _lib.lib()
+        self.pl = plasma
+        maxorder = max(s.poly_order for s in plasma.species)
+        cfg = _lib.Cfg(plasma.nspec, plasma.nperp, plasma.npar, plasma.ngamma, plasma.npparbar,
+                       plasma.vA, plasma.Bessel_zero, plasma.Tlim, plasma.positions_principal,
+                       plasma.n_resonance_interval, int(plasma.kperp_norm), emulate_nproc,
+                       plasma.maxfits, maxorder, device, nmax_cap, batch_max)
+        _lib.check(self.L.alps_b200_init(C.byref(cfg)))
+        for i, s in enumerate(plasma.species):
+            ft = np.asarray(s.fit_type, dtype=np.int32)
+            pc = np.asarray(s.perp_correction, dtype=np.float64)
+            _lib.check(self.L.alps_b200_set_species(
+                i + 1, s.ns, s.qs, s.ms, int(s.relativistic), int(s.usebM), s.ACmethod,
+                len(s.fit_type), _p(ft), _p(pc), int(s.logfit), s.poly_kind, s.poly_order,
+                s.poly_log_max))
+        pp = _f(plasma.pp)
+        df0 = _f(plasma.df0)
+        _lib.check(self.L.alps_b200_upload(_p(pp), _p(df0), _p(_f(plasma.param_fit)),
+                                           _p(_f(plasma.poly_fit_coeffs))))
+        self._df0 = None
+        if df0 is None:
+            self._df0 = self.derivative_f0(plasma.f0)
+        self.nmax = None
+        self.kperp = self.kpar = None
+
+    # ---- derivative_f0, src/ALPS_fns.f90:34-248
+    def derivative_f0(self, f0) -> np.ndarray:
+        pl = self.pl
+        out = np.zeros(pl.nspec * (pl.nperp - 1) * (pl.npar - 1) * 2)
+        _lib.check(self.L.alps_b200_derivative_f0(_p(_f(f0)), _p(out)))
+        return out.reshape((pl.nspec, pl.nperp - 1, pl.npar - 1, 2), order="F")
+
+    def df0(self):
+        return self._df0
+
+    # ---- determine_nmax / split_processes / determine_bessel_array, src/ALPS_fns.f90:3971-4255
+    def set_k(self, kperp: float, kpar: float) -> np.ndarray:
+        nmax = np.zeros(self.pl.nspec, dtype=np.int32)
+        _lib.check(self.L.alps_b200_set_k(float(kperp), float(kpar), _p(nmax)))
+        self.nmax = nmax
+        self.kperp, self.kpar = float(kperp), float(kpar)
+        return nmax
+
+    def set_harmonic_shard(self, rank: int, nranks: int):
+        _lib.check(self.L.alps_b200_set_harmonic_shard(rank, nranks))
+
+    # ---- disp(om), src/ALPS_fns.f90:252-636
+    def disp(self, om: complex, full: bool = False):
+        n = self.pl.nspec
+        omv = np.array([om.real, om.imag])
+        D = np.zeros(2)
+        if not full:
+            _lib.check(self.L.alps_b200_disp(_p(omv), _p(D), None, None, None))
+            return complex(D[0], D[1])
+        chi0 = np.zeros(n * 18)
+        low = np.zeros(n * 54)
+        wave = np.zeros(18)
+        _lib.check(self.L.alps_b200_disp(_p(omv), _p(D), _p(chi0), _p(low), _p(wave)))
+        c = lambda a, shape: (a[0::2] + 1j * a[1::2]).reshape(shape, order="F")
+        return (complex(D[0], D[1]), c(chi0, (n, 3, 3)), c(low, (n, 3, 3, 3)), c(wave, (3, 3)))
+
+    def disp_batch(self, om: Sequence[complex], want_chi0: bool = False):
+        """n independent omegas (host buffers in, host buffers out)."""
+        om = np.ascontiguousarray(np.asarray(om, dtype=np.complex128).ravel())
+        n = om.size
+        D = np.zeros(n, dtype=np.complex128)
+        chi0 = np.zeros(n * self.pl.nspec * 9, dtype=np.complex128) if want_chi0 else None
+        _lib.check(self.L.alps_b200_disp_batch(n, _p(om.view(np.float64)), _p(D.view(np.float64)),
+                                               _p(chi0.view(np.float64)) if want_chi0 else None))
+        if want_chi0:
+            return D, chi0.reshape((n, 3, 3, self.pl.nspec)).transpose(0, 3, 1, 2).swapaxes(2, 3)
+        return D
+
+    def disp_batch_dev(self, n: int, d_om_ptr: int, d_D_ptr: int):
+        """Device-resident omegas / D (raw device pointers, e.g. torch .data_ptr())."""
+        _lib.check(self.L.alps_b200_disp_batch_dev(n, C.c_void_p(d_om_ptr), C.c_void_p(d_D_ptr)))
+
+    def chi_partial_len(self) -> int:
+        return self.L.alps_b200_chi_partial_len()
+
+    def chi_partial_dev(self, n: int, d_om_ptr: int, d_partial_ptr: int):
+        _lib.check(self.L.alps_b200_chi_partial_dev(n, C.c_void_p(d_om_ptr), C.c_void_p(d_partial_ptr)))
+
+    def assemble_dev(self, n: int, d_om_ptr: int, d_partial_ptr: int, d_D_ptr: int):
+        _lib.check(self.L.alps_b200_assemble_dev(n, C.c_void_p(d_om_ptr), C.c_void_p(d_partial_ptr),
+                                                 C.c_void_p(d_D_ptr)))
+
+    def add_external_chi(self, is_: int, chi, chi_low=None):
+        c = np.ascontiguousarray(np.asarray(chi, dtype=np.complex128).ravel(order="F"))
+        cl = None if chi_low is None else np.ascontiguousarray(
+            np.asarray(chi_low, dtype=np.complex128).ravel(order="F"))
+        _lib.check(self.L.alps_b200_add_external_chi(is_, _p(c.view(np.float64)),
+                                                     None if cl is None else _p(cl.view(np.float64))))
+
+    # ---- plumbing
+    def set_stream(self, stream_ptr: Optional[int]):
+        _lib.check(self.L.alps_b200_set_stream(C.c_void_p(stream_ptr or 0)))
+
+    def sync(self):
+        _lib.check(self.L.alps_b200_sync())
+
+    def info(self, what: int) -> float:
+        out = C.c_double(0.0)
+        _lib.check(self.L.alps_b200_get_info(what, C.byref(out)))
+        return out.value
+
+    def dfma_peak(self) -> float:
+        out = C.c_double(0.0)
+        _lib.check(self.L.alps_b200_dfma_peak(C.byref(out)))
+        return out.value
+
+    def close(self):
+        self.L.alps_b200_finalize()

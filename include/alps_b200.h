@@ -1,0 +1,129 @@
+/*
+ * alps_b200 -- C ABI of the B200-native replacement for the ALPS hot path
+ *
+ *     double complex function disp(om)            (reference: src/ALPS_fns.f90:252-636)
+ *
+ * i.e. chi_s(omega,k), the dispersion tensor and its determinant D(omega,k) for tabulated
+ * gyrotropic f0(p_perp,p_par), plus the k-dependent set-up that path needs
+ * (determine_nmax / split_processes / determine_bessel_array, src/ALPS_fns.f90:3971-4255) and
+ * the f0 derivatives (derivative_f0, src/ALPS_fns.f90:34-248).
+ *
+ * The reference has no plugin/FFI interface: the boundary is that Fortran module function and
+ * the alps_var module globals it reads (src/ALPS_var.f90:174-246).  A ~60 line iso_c_binding
+ * shim keeps disp()'s signature and forwards to the entry points below.
+ * All arrays are handed over exactly as the Fortran side holds them: column-major, species
+ * index fastest, interleaved (re,im) doubles for complex values.  The library copies what it is
+ * given; the caller keeps ownership.  One host thread, not re-entrant, one CUDA stream.
+ *
+ * Return value: 0 on success, a positive ALPS error id as used by alps_error()
+ * (src/ALPS_io.f90:937-1012) or a negative value for CUDA / usage errors
+ * (see alps_b200_last_error()).  There is no CPU fallback: every call fails if no sm_100 device
+ * is usable.
+ */
+#ifndef ALPS_B200_H
+#define ALPS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALPS_B200_ERR_CUDA (-1)      /* CUDA runtime / driver failure            */
+#define ALPS_B200_ERR_USAGE (-2)     /* bad argument or call order                */
+#define ALPS_B200_ERR_UNSUPPORTED (-3) /* feature of the reference not built yet  */
+#define ALPS_B200_ERR_GRID (-4)      /* (p_perp,p_par) grid not separable/uniform */
+#define ALPS_B200_ERR_NMAX (-5)      /* determine_nmax exceeded nmax_cap          */
+
+/* Scalars of namelist &system (src/ALPS_io.f90:79-85) that the path reads. */
+typedef struct {
+  int nspec, nperp, npar;
+  int ngamma, npparbar;          /* relativistic grid (src/ALPS_var.f90:60-64)               */
+  double vA;
+  double Bessel_zero;            /* determine_nmax threshold, src/ALPS_fns.f90:4017           */
+  double Tlim;                   /* analytic switch, src/ALPS_fns.f90:1026                    */
+  int positions_principal;       /* M_I, src/ALPS_fns.f90:981-1006                            */
+  int n_resonance_interval;      /* M_P, src/ALPS_fns.f90:1019                                */
+  int kperp_norm;                /* src/ALPS_fns.f90:322-328                                  */
+  int emulate_nproc;             /* MPI size to emulate in determine_nmax/split_processes
+                                    (nmax and the summed harmonic range depend on it,
+                                    src/ALPS_fns.f90:4048-4064, 4185-4200); 0 = n in [0,nmax]  */
+  int maxfits;                   /* maxval(n_fits): extent of param_fit, src/ALPS_io.f90:181  */
+  int maxorder;                  /* max poly_order: extent of poly_fit_coeffs                 */
+  int device;                    /* CUDA device ordinal; -1 = current device                  */
+  int nmax_cap;                  /* upper bound for nmax (0 = 2000)                           */
+  int batch_max;                 /* omegas processed per internal chunk (0 = auto)            */
+} alps_b200_cfg;
+
+/* replaces: allocation + pass_instructions (src/ALPS_com.f90:28-170) for the path's scalars */
+int alps_b200_init(const alps_b200_cfg *cfg);
+void alps_b200_finalize(void);
+const char *alps_b200_last_error(void);
+
+/* replaces: the per-species namelists &spec_j/&ffit_j_i/&poly_spec_j as broadcast by
+ * pass_instructions (src/ALPS_com.f90:60-170).  is is 1-based. */
+int alps_b200_set_species(int is, double ns, double qs, double ms, int relativistic, int usebM,
+                          int ACmethod, int n_fits, const int *fit_type,
+                          const double *perp_correction, int logfit, int poly_kind,
+                          int poly_order, double poly_log_max);
+
+/* replaces: pass_distribution (src/ALPS_com.f90:175-284).  Fortran arrays as they are:
+ *   pp(nspec,0:nperp,0:npar,2), df0(nspec,1:nperp-1,1:npar-1,2),
+ *   param_fit(nspec,0:max(nperp,ngamma),5,maxfits), poly_fit_coeffs(nspec,0:nperp,0:maxorder).
+ * df0 may be NULL if alps_b200_derivative_f0 is called instead.  param_fit / poly may be NULL
+ * when no species needs them. */
+int alps_b200_upload(const double *pp, const double *df0, const double *param_fit,
+                     const double *poly_fit_coeffs);
+
+/* replaces: derivative_f0 (src/ALPS_fns.f90:96-118) -- centred differences on the device from
+ * f0(nspec,0:nperp,0:npar); optional df0_out (host, Fortran layout of df0) receives the result. */
+int alps_b200_derivative_f0(const double *f0, double *df0_out);
+
+/* replaces: determine_nmax + split_processes + determine_bessel_array
+ * (src/ALPS_fns.f90:3971-4255), called whenever k changes (src/ALPS_fns.f90:2465-2472). */
+int alps_b200_set_k(double kperp, double kpar, int *nmax_out /* nspec, may be NULL */);
+
+/* replaces: disp(om) for one omega.  Outputs (any may be NULL): D[2]; chi0(nspec,3,3);
+ * chi0_low(nspec,3,3,-1:1); wave(3,3) -- the rank-0 globals calc_eigen consumes
+ * (src/ALPS_fns.f90:2611, 2687-2702). */
+int alps_b200_disp(const double om[2], double D[2], double *chi0, double *chi0_low, double *wave);
+
+/* replaces: the serial nr x ni loop of map_search (src/ALPS_fns.f90:3697-3757) and any batch of
+ * independent root iterations: n omegas in, n D's out (host buffers; H2D/D2H inside).
+ * chi0_opt (may be NULL): n x chi0(nspec,3,3). */
+int alps_b200_disp_batch(int n, const double *om, double *D, double *chi0_opt);
+
+/* Same with device-resident buffers (om, D: 2n doubles in HBM) on the library's stream. */
+int alps_b200_disp_batch_dev(int n, const double *d_om, double *d_D);
+
+/* replaces: calc_chi (NHDS) results being summed into chi for use_bM species
+ * (src/ALPS_fns.f90:344-362): chi(3,3) and chi_low(3,3,-1:1) for the next alps_b200_disp call. */
+int alps_b200_add_external_chi(int is, const double *chi, const double *chi_low);
+
+/* Harmonic sharding (replaces split_processes + MPI_REDUCE, src/ALPS_fns.f90:4079-4207, 519-523):
+ * restrict this process to harmonics |n| in [nlo,nhi] of species is (is=0: all species),
+ * produce un-normalised partial sums (caller all-reduces them over NCCL), then assemble. */
+int alps_b200_set_harmonic_shard(int rank, int nranks);
+int alps_b200_chi_partial_len(void);                       /* doubles per omega            */
+int alps_b200_chi_partial_dev(int n, const double *d_om, double *d_partial);
+int alps_b200_assemble_dev(int n, const double *d_om, const double *d_partial, double *d_D);
+
+/* 0 = direct quadrature per omega (default); 1 = k-hoisted tables (p_perp sums precomputed in
+ * set_k, O(nmax*npar) per omega). */
+int alps_b200_set_mode(int mode);
+
+/* plumbing */
+int alps_b200_set_stream(void *cuda_stream);   /* cudaStream_t; NULL = library-owned stream */
+int alps_b200_sync(void);
+int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
+#define ALPS_B200_INFO_POINT_HARMONICS 0  /* sum_s (2 nmax_s+1)(nperp-1)(npar-1) for current k */
+#define ALPS_B200_INFO_LAUNCHES 1         /* kernels launched since init                        */
+#define ALPS_B200_INFO_SM_COUNT 2
+#define ALPS_B200_INFO_LAST_KERNEL_MS 3   /* device time of the last quadrature kernel batch    */
+#define ALPS_B200_INFO_BATCH 4            /* internal omega chunk size                          */
+
+/* FP64 FMA micro-benchmark (roofline denominator; not part of the path): returns TFLOP/s. */
+int alps_b200_dfma_peak(double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALPS_B200_H */

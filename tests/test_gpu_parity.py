@@ -1,0 +1,81 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+inputs.  Tolerances: chi0 / wave element-wise 1e-9 relative to the tensor scale, D 1e-9 relative to
+the scale of its summed products (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from alps_b200 import tables
+from tests.util import det_scale, omega_samples, tensor_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _compare(pl, kperp, kpar, oms, nproc=0, tol=TOL):
+    from alps_b200.solver import Solver
+    from oracle.oracle import Oracle
+    orc = Oracle(pl, nproc=nproc)
+    sol = Solver(pl, emulate_nproc=nproc)
+    try:
+        nmax_o = orc.set_k(kperp, kpar)
+        nmax_g = sol.set_k(kperp, kpar)
+        assert list(nmax_o) == list(nmax_g)
+        worst = 0.0
+        Db = sol.disp_batch(oms)
+        for i, om in enumerate(oms):
+            Do, chi_o, low_o, wave_o = orc.disp(complex(om), full=True)
+            Dg, chi_g, low_g, wave_g = sol.disp(complex(om), full=True)
+            for s in range(pl.nspec):
+                e = tensor_err(chi_g[s], chi_o[s])
+                assert e < tol, ("chi0", s, om, e)
+                for m in range(3):
+                    if np.max(np.abs(low_o[s, :, :, m])) > 0:
+                        el = tensor_err(low_g[s, :, :, m], low_o[s, :, :, m])
+                        assert el < tol, ("chi0_low", s, m, om, el)
+            ew = tensor_err(wave_g, wave_o)
+            assert ew < tol, ("wave", om, ew)
+            ed = abs(Dg - Do) / det_scale(wave_o)
+            assert ed < tol, ("D", om, ed)
+            assert abs(Db[i] - Dg) <= 1e-13 * det_scale(wave_o), ("batch vs single", om)
+            worst = max(worst, ew, ed)
+        return worst
+    finally:
+        sol.close()
+
+
+def test_small_bimax_all_branches():
+    pl = tables.config_small(24, 48, kind=1)
+    # resonant and non-resonant, damped / growing / real omega
+    oms = list(omega_samples(1, 12, (0.02, 1.5), (-0.05, 0.05))) + [0.3 + 0j, 0.011 - 1e-6j, 1.0 + 1e-5j]
+    _compare(pl, 0.3, 0.05, oms)
+
+
+def test_small_kappa():
+    pl = tables.config_small(28, 56, kind=2)
+    oms = list(omega_samples(2, 10, (0.02, 1.2), (-0.03, 0.03)))
+    _compare(pl, 0.2, 0.08, oms)
+
+
+def test_small_emulated_nproc():
+    pl = tables.config_small(24, 48, kind=1)
+    oms = list(omega_samples(3, 4, (0.02, 1.0), (-0.02, 0.02)))
+    _compare(pl, 0.5, 0.05, oms, nproc=8)
+
+
+def test_kpar_fast_config():
+    """C1 tables (tests/test_kpar_fast.in), omegas around the golden roots."""
+    pl = tables.config_kpar_fast()
+    oms = [9.98811e-3 - 2.31322e-7j, 9.9e-3 - 5.5e-6j, 1.2e-2 + 1e-6j, 5e-2 - 3e-4j, 0.3 + 0.01j, 0.9 + 0j]
+    _compare(pl, 1e-2, 1e-2, oms, nproc=4)
+
+
+def test_derivative_f0_matches_oracle():
+    from alps_b200.solver import Solver
+    from oracle.oracle import Oracle
+    pl = tables.config_small(24, 48, kind=2)
+    orc = Oracle(pl)
+    sol = Solver(pl)
+    try:
+        assert np.array_equal(sol.df0(), orc.df0())   # same IEEE operations: bit-exact
+    finally:
+        sol.close()
