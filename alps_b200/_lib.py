@@ -28,7 +28,8 @@ class Cfg(C.Structure):
                 ("Tlim", C.c_double), ("positions_principal", C.c_int),
                 ("n_resonance_interval", C.c_int), ("kperp_norm", C.c_int),
                 ("emulate_nproc", C.c_int), ("maxfits", C.c_int), ("maxorder", C.c_int),
-                ("device", C.c_int), ("nmax_cap", C.c_int), ("batch_max", C.c_int)]
+                ("device", C.c_int), ("nmax_cap", C.c_int), ("batch_max", C.c_int),
+                ("nmax_force", C.c_int)]
 
 
 class AlpsB200Error(RuntimeError):

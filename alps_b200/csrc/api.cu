@@ -201,7 +201,7 @@ int ensure_batch(int want) {
   free_batch();
   const size_t NI = S.gh.NI, B = want;
   if (dalloc(&S.d_om, 2 * B) || dalloc(&S.d_D, 2 * B) || dalloc(&S.d_Sbulk, B * NI * 12) ||
-      dalloc(&S.d_Sres, B * NI * 12) || dalloc(&S.d_gwin, B * NI * S.gh.WIN * 6) ||
+      dalloc(&S.d_Sres, B * NI * 12) || dalloc(&S.d_gwin, B * NI * S.gh.WINX * 6) ||
       dalloc(&S.d_partial, B * S.gh.nspec * PARTIAL_PER_SPEC) || dalloc(&S.d_chi0, B * S.gh.nspec * 18) ||
       dalloc(&S.d_chi0_low, B * S.gh.nspec * 54) || dalloc(&S.d_wave, B * 18) || dalloc(&S.d_plan, B * NI) ||
       dalloc(&S.d_work, B * NI))
@@ -212,7 +212,7 @@ int ensure_batch(int want) {
 
 int auto_batch() {
   if (S.cfg.batch_max > 0) return S.cfg.batch_max;
-  const size_t per_om = (size_t)S.gh.NI * (sizeof(PlanEntry) + 2 * 96 + (size_t)S.gh.WIN * 48 + 4) + 1024;
+  const size_t per_om = (size_t)S.gh.NI * (sizeof(PlanEntry) + 2 * 96 + (size_t)S.gh.WINX * 48 + 4) + 1024;
   size_t b = ((size_t)2 << 30) / per_om;
   const size_t unit = S.sm_count > 0 ? S.sm_count : 148;
   b = std::min<size_t>(b, 16384);
@@ -300,15 +300,16 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.gh.M_I = cfg->positions_principal;
   S.gh.M_P = cfg->n_resonance_interval;
   S.gh.WIN = 2 * cfg->positions_principal + 7;
+  S.gh.WINX = S.gh.WIN + 3;
   S.gh.kperp_norm = cfg->kperp_norm;
   S.gh.maxfits = cfg->maxfits > 0 ? cfg->maxfits : 1;
   S.gh.maxorder = cfg->maxorder;
   S.gh.vA = cfg->vA;
   S.gh.Tlim = cfg->Tlim;
-  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 1) ||
+  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8) ||
       dalloc(&S.d_ext, (size_t)cfg->nspec * PARTIAL_PER_SPEC))
     return ALPS_B200_ERR_CUDA;
-  CK(cudaMemset(S.d_err, 0, sizeof(int)));
+  CK(cudaMemset(S.d_err, 0, 8 * sizeof(int)));
   S.ext.assign((size_t)cfg->nspec * PARTIAL_PER_SPEC, 0.0);
   S.ext_any = false;
   S.mode = 0;
@@ -489,6 +490,10 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
       nmax[s] = S.gh.sp[s].nmax;
       continue;
     }
+    if (S.cfg.nmax_force > 0) {
+      nmax[s] = S.cfg.nmax_force;
+      continue;
+    }
     int found = -1;
     for (int n0 = 1; n0 <= S.cfg.nmax_cap && found < 0; n0 += CH) {
       launch_bessel_max(S.sp[s].d_pperp, nperp, kperp, S.gh.sp[s].qs, n0, CH, d_bm, S.stream);
@@ -592,13 +597,16 @@ static int bind_batch(int n) {
 }
 
 static int check_device_errors() {
-  int herr = 0;
-  CK(cudaMemcpyAsync(&herr, S.d_err, sizeof(int), cudaMemcpyDeviceToHost, S.stream));
+  int herr[8] = {0};
+  CK(cudaMemcpyAsync(herr, S.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream));
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());
-  if (herr) {
-    cudaMemset(S.d_err, 0, sizeof(int));
-    return fail(ALPS_B200_ERR_CUDA, "resonance window overflow in the near-pole quadrature");
+  if (herr[0]) {
+    cudaMemset(S.d_err, 0, 8 * sizeof(int));
+    return fail(ALPS_B200_ERR_CUDA,
+                "resonance window overflow in the near-pole quadrature (item %d of NI=%d, ipar_res=%d, "
+                "upperlimit=%d, flags=%d, code=0x%x)",
+                herr[1], S.gh.NI, herr[2], herr[3], herr[4], herr[5]);
   }
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, S.ev0, S.ev1) == cudaSuccess) S.last_kernel_ms = ms;

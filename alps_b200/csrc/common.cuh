@@ -10,7 +10,7 @@
 //   plan [item]             resonance descriptor of (species, |n|, sign)
 //   Sbulk[item][6]          complex p_par-moment sums of the regular trapezoid quadrature
 //   Sres [item][6]          complex near-pole + Landau contributions (final units)
-//   gwin [item][WIN][3]     complex p_perp-sums at the p_par nodes around a resonance
+//   gwin [item][WIN+3][3]   complex p_perp-sums at the p_par nodes around a resonance (+ nodes 1..3)
 // item = omega * NI + item_base[s] + 2*|n| + sign, NI = sum_s 2 (nhi_s + 1).
 #pragma once
 #include <cuda_runtime.h>
@@ -102,6 +102,8 @@ struct GlobalDev {
   int nspec, nperp, npar;
   int NI;                    // items per omega
   int WIN;                   // nodes per resonance window = 2*M_I + 7
+  int WINX;                  // gwin slots per item = WIN + 3: nodes 1..3 follow the window because
+                             // funct_g falls back to node 2 when no node is within dp/2 of p
   int M_I, M_P;
   int kperp_norm;
   int maxfits, maxorder;

@@ -22,7 +22,7 @@ struct QuadParams {
   const double* om;        // 2 * n_om
   const PlanEntry* plan;   // n_om * NI
   double* Sbulk;           // n_om * NI * 12
-  double* gwin;            // n_om * NI * WIN * 6
+  double* gwin;            // n_om * NI * WINX * 6
   int ntiles;
   int n_om;
 };

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(QUAD_THREADS, 1) k_quad(const __grid_constant_
   const double qs = sp.qs, ms = sp.ms, kpar = g.kpar;
   const double* __restrict__ ppar = sp.ppar;
   const size_t item0 = (size_t)iom * g.NI + sp.item_base;
-  const int WIN = g.WIN, M_I = g.M_I;
+  const int WIN = g.WIN, WINX = g.WINX, M_I = g.M_I;
 
   int stage = 0;
   uint32_t phase = 0;
@@ -222,9 +222,10 @@ __global__ void __launch_bounds__(QUAD_THREADS, 1) k_quad(const __grid_constant_
             S[10] += Vc.x;      S[11] += Vc.y;       // sum U p_perp^2 J'^2
           }
           if (pe.flags & PLAN_NEAR) {
-            const int j = ipar - (pe.ipar_res - M_I - 2);
-            if (j >= 0 && j < WIN) {
-              double* gw = P.gwin + (item * WIN + j) * 6;
+            int j = ipar - (pe.ipar_res - M_I - 2);
+            if (j < 0 || j >= WIN) j = (ipar <= 3) ? WIN + ipar - 1 : -1;   // nodes 1..3: funct_g fallback
+            if (j >= 0) {
+              double* gw = P.gwin + (item * WINX + j) * 6;
 #pragma unroll
               for (int x = 0; x < 3; x++) {
                 gw[2 * x] = ar[3 * nn + x][c];

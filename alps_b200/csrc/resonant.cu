@@ -207,11 +207,18 @@ __device__ inline void funct_g6(const GlobalDev& g, const SpeciesDev& sp, const 
     }
   if (ic >= npar - 1) ic = npar - 2;
   if (ic <= 1) ic = 2;
-  int j = ic - wbase;
-  if (j - 1 < 0 || j + 1 >= g.WIN) {
-    *err = 1;
-    six_zero(out);
-    return;
+  // window slots of nodes ic-1, ic, ic+1 (nodes 1..3 live behind the window, see GlobalDev::WINX)
+  int jm = ic - 1 - wbase, j0 = ic - wbase, jp = ic + 1 - wbase;
+  if (jm < 0 || jp >= g.WIN) {
+    if (ic == 2) {
+      jm = g.WIN;
+      j0 = g.WIN + 1;
+      jp = g.WIN + 2;
+    } else {
+      *err = 1 + (ic & 0xffff) + ((i0 & 0x7fff) << 16);
+      six_zero(out);
+      return;
+    }
   }
   const double x = p - ppar[ic];
 #pragma unroll
@@ -220,17 +227,17 @@ __device__ inline void funct_g6(const GlobalDev& g, const SpeciesDev& sp, const 
     const int m = (q < 3) ? q : (q < 5 ? q - 3 : 0);  // p_par power
     cd gm, g0, gp;
     {
-      const double* w = gw + ((size_t)(j - 1) * 3 + xt) * 2;
+      const double* w = gw + ((size_t)jm * 3 + xt) * 2;
       double pw = m == 0 ? 1.0 : (m == 1 ? ppar[ic - 1] : ppar[ic - 1] * ppar[ic - 1]);
       gm = -(mk(w[0], w[1]) * pw) / g.kpar;
     }
     {
-      const double* w = gw + ((size_t)j * 3 + xt) * 2;
+      const double* w = gw + ((size_t)j0 * 3 + xt) * 2;
       double pw = m == 0 ? 1.0 : (m == 1 ? ppar[ic] : ppar[ic] * ppar[ic]);
       g0 = -(mk(w[0], w[1]) * pw) / g.kpar;
     }
     {
-      const double* w = gw + ((size_t)(j + 1) * 3 + xt) * 2;
+      const double* w = gw + ((size_t)jp * 3 + xt) * 2;
       double pw = m == 0 ? 1.0 : (m == 1 ? ppar[ic + 1] : ppar[ic + 1] * ppar[ic + 1]);
       gp = -(mk(w[0], w[1]) * pw) / g.kpar;
     }
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
     int err = 0;
 
     if (pe.flags & PLAN_NEAR) {
-      const double* gw = gwin + idx * (size_t)g.WIN * 6;
+      const double* gw = gwin + idx * (size_t)g.WINX * 6;
       const int wbase = pe.ipar_res - M_I - 2;
       const double dppar = sp.dppar_signed;
       const double capDelta = pR - ppar[pe.ipar_res - M_I];
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
         tot.v[5] += cc;
       }
     }
-    err = __any_sync(0xffffffffu, err);
+    for (int o = 16; o > 0; o >>= 1) err = max(err, __shfl_xor_sync(0xffffffffu, err, o));
     if (lane == 0) {
       double* o = Sres + idx * 12;
 #pragma unroll
@@ -411,7 +418,14 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
         o[2 * q] = tot.v[q].x;
         o[2 * q + 1] = tot.v[q].y;
       }
-      if (err) *err_flag = 1;
+      if (err) {
+        err_flag[0] = 1;
+        err_flag[1] = (int)idx;
+        err_flag[2] = pe.ipar_res;
+        err_flag[3] = pe.upperlimit;
+        err_flag[4] = pe.flags;
+        err_flag[5] = err;
+      }
     }
   }
 }

@@ -29,14 +29,14 @@ class Solver:
     global instance, like the reference's module state."""
 
     def __init__(self, plasma: Plasma, emulate_nproc: int = 0, device: int = -1, batch_max: int = 0,
-                 nmax_cap: int = 0):
+                 nmax_cap: int = 0, nmax_force: int = 0):
         self.L = _lib.lib()
         self.pl = plasma
         maxorder = max(s.poly_order for s in plasma.species)
         cfg = _lib.Cfg(plasma.nspec, plasma.nperp, plasma.npar, plasma.ngamma, plasma.npparbar,
                        plasma.vA, plasma.Bessel_zero, plasma.Tlim, plasma.positions_principal,
                        plasma.n_resonance_interval, int(plasma.kperp_norm), emulate_nproc,
-                       plasma.maxfits, maxorder, device, nmax_cap, batch_max)
+                       plasma.maxfits, maxorder, device, nmax_cap, batch_max, nmax_force)
         _lib.check(self.L.alps_b200_init(C.byref(cfg)))
         for i, s in enumerate(plasma.species):
             ft = np.asarray(s.fit_type, dtype=np.int32)

@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- D(omega,k) evaluations per second of the disp() hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c5|c1]
+
+A "step" is one pass of the hot path over one batch of omegas taken from the complex-omega map of
+the workload (per GPU; N GPUs shard the map with no communication: weak scaling).
+  value      device-resident omegas in, D out (alps_b200_disp_batch_dev), CUDA-event timed
+  e2e        the same batch through the host-buffer call alps_b200_disp_batch (H2D of the omegas
+             and D2H of D inside the timed region)
+  roofline   the quadrature kernel (k_quad) against the FP64 FMA pipe: algorithmic flops
+             34 x point-harmonics per D / CUDA-event time of that kernel
+  cpu_baseline  the CPU oracle (restated reference, OpenMP) on a bounded sample of the same workload
+`--impl reference` times the restated reference (oracle/) alone on the host cores: the Fortran/MPI
+reference cannot be built in this image (no gfortran, no MPI).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_PER_POINT_HARMONIC = 34.0
+FP64_NOMINAL_TFLOPS = 37.2          # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+
+WORKLOADS = {
+    # name: (description, builder kwargs)
+    "c5": dict(desc="C5 synthetic 3-species bi-kappa f0, 1024x2048 (p_perp,p_par) grid, nmax=200 forced, "
+                    "k=(15.5,1e-2), omegas from the 512x512 map om_r in [0.05,3.05] x gamma in [-0.05,0.05]",
+               nperp=1024, npar=2048, nmax_force=200, kperp=15.5, kpar=1.0e-2,
+               omr=(0.05, 3.05), omi=(-0.05, 0.05), nr=512, ni=512, batch=296),
+    "c5small": dict(desc="reduced C5 (256x512 grid, nmax=48) -- smoke runs only",
+                    nperp=256, npar=512, nmax_force=48, kperp=5.0, kpar=1.0e-2,
+                    omr=(0.05, 3.05), omi=(-0.05, 0.05), nr=512, ni=512, batch=296),
+}
+
+
+def map_omegas(w, rank, world, batch):
+    """this rank's omegas: a strided sample of its contiguous block of map rows
+    (map grid of map_search, src/ALPS_fns.f90:3684-3712, linear in both directions)"""
+    nr, ni = w["nr"], w["ni"]
+    wr = w["omr"][0] + (w["omr"][1] - w["omr"][0]) * np.arange(nr) / (nr - 1)
+    wi = w["omi"][0] + (w["omi"][1] - w["omi"][0]) * np.arange(ni) / (ni - 1)
+    rows = np.array_split(np.arange(nr), world)[rank]
+    grid = (wr[rows][:, None] + 1j * wi[None, :]).ravel()
+    idx = (np.arange(batch) * (grid.size // batch) + (grid.size // (2 * batch))) % grid.size
+    return np.ascontiguousarray(grid[idx])
+
+
+def build_plasma(w):
+    from alps_b200 import tables
+    return tables.config_kappa3(w["nperp"], w["npar"])
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, smax, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # samples taken while the GPU is busy have the highest clocks; use the upper half
+        sm_sorted = sorted(sm)
+        busy = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(w, plasma, om, ncap=None, threads=0):
+    """Bounded sample of the workload on the host cores with the CPU oracle: one D evaluation
+    restricted to harmonics |n| <= ncap, scaled to all harmonics by the signed-harmonic count."""
+    from oracle.oracle import Oracle
+    cores = threads or (os.cpu_count() or 1)
+    orc = Oracle(plasma, nproc=0, threads=cores, nmax_force=w["nmax_force"])
+    nmax = orc.set_k(w["kperp"], w["kpar"])
+    if ncap is None:
+        ncap = 3
+    ncap = int(min(ncap, min(nmax)))
+    orc.set_ncap(ncap)
+    t0 = time.perf_counter()
+    orc.disp(complex(om))
+    dt = time.perf_counter() - t0
+    frac = sum(2 * ncap + 1 for _ in nmax) / float(sum(2 * int(n) + 1 for n in nmax))
+    return {"seconds_sample": dt, "fraction": frac, "d_per_s": frac / dt, "cores": cores, "ncap": ncap,
+            "nmax": [int(n) for n in nmax]}
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    plasma = build_plasma(w)
+    om = map_omegas(w, 0, 1, w["batch"])
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample(w, plasma, om[(7 * i) % om.size])
+        if i >= args.warmup:
+            vals.append(r)
+    dps = float(np.mean([v["d_per_s"] for v in vals]))
+    ms = float(np.mean([v["seconds_sample"] for v in vals])) * 1e3
+    sample = ("one D evaluation restricted to |n|<=%d (%.2f%% of the signed harmonics), scaled; restated "
+              "reference (CPU oracle, OpenMP over harmonics); Fortran/MPI build impossible here"
+              % (vals[0]["ncap"], 100 * vals[0]["fraction"]))
+    line = {"impl": "reference", "metric": "D(omega,k) evals/sec", "value": dps, "unit": "D/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": w["desc"]},
+            "cpu_baseline": {"value": dps, "unit": "D/s", "cores": vals[0]["cores"], "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": dps, "unit": "D/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from alps_b200 import _lib
+    from alps_b200.solver import Solver
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; alps_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    plasma = build_plasma(w)
+    B = args.batch or w["batch"]
+    sol = Solver(plasma, device=local_rank, nmax_force=w["nmax_force"], batch_max=B)
+    nmax = sol.set_k(w["kperp"], w["kpar"])
+    sol.set_stream(torch.cuda.current_stream().cuda_stream)
+    om_h = map_omegas(w, rank, world, B)
+    om_d = torch.from_numpy(om_h.view(np.float64).copy()).cuda()
+    D_d = torch.zeros(2 * B, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    ph = sol.info(_lib.INFO_POINT_HARMONICS)
+    flops_per_D = FLOPS_PER_POINT_HARMONIC * ph
+    peak_meas = sol.dfma_peak() if rank == 0 else None
+
+    def step_dev():
+        sol.disp_batch_dev(B, om_d.data_ptr(), D_d.data_ptr())
+
+    for _ in range(args.warmup):
+        step_dev()
+    sol.sync()
+    l0 = sol.info(_lib.INFO_LAUNCHES)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    tot_ms, kern_ms = 0.0, 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_dev()
+        e1.record()
+        e1.synchronize()
+        sol.sync()
+        tot_ms += e0.elapsed_time(e1)
+        kern_ms += sol.info(_lib.INFO_LAST_KERNEL_MS)
+    barrier()
+    clk = clocks.stop()
+    launches = int(sol.info(_lib.INFO_LAUNCHES) - l0)
+    D_first = D_d.cpu().numpy().copy()
+
+    # ---- end to end through the host-buffer call
+    D_h = np.zeros(B, dtype=np.complex128)
+    for _ in range(min(args.warmup, 2)):
+        D_h = sol.disp_batch(om_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        D_h = sol.disp_batch(om_h)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    assert np.array_equal(D_h.view(np.float64), D_first), "device-resident and host-buffer paths disagree"
+    assert np.all(np.isfinite(D_first)), "non-finite D in the benchmark batch"
+
+    times = torch.tensor([tot_ms, e2e_s * 1e3, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    tot_ms, e2e_ms, kern_ms = [float(x) for x in times.cpu()]
+    if rank == 0:
+        n_total = world * B * args.steps
+        value = n_total / (tot_ms * 1e-3)
+        e2e = n_total / (e2e_ms * 1e-3)
+        achieved = flops_per_D * B * args.steps / (kern_ms * 1e-3) / 1e12   # one GPU's kernel
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            c = cpu_sample(w, plasma, om_h[0])
+            cpu = {"value": c["d_per_s"], "unit": "D/s", "cores": c["cores"], "kind": "port",
+                   "sample": "one D restricted to |n|<=%d (%.2f%% of the signed harmonics, %.1f s), scaled; "
+                             "CPU oracle (restated reference, OpenMP); Fortran/MPI build impossible here"
+                             % (c["ncap"], 100 * c["fraction"], c["seconds_sample"])}
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_k_quad_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": "D(omega,k) evals/sec", "value": value, "unit": "D/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": w["desc"], "omegas_per_step_per_gpu": B,
+                           "nmax": [int(n) for n in nmax], "point_harmonics_per_D": ph,
+                           "flops_per_D": flops_per_D, "parallelism": "omega-shard x%d" % world,
+                           "l2": "flushed between steps (256 MiB write)", "mode": "direct quadrature"},
+                "e2e": {"value": e2e, "unit": "D/s", "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 16 * B},
+                "gpu_launches": launches,
+                "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s",
+                             "frac": achieved / peak_meas if peak_meas else None, "traffic": traffic,
+                             "peak_source": "DFMA micro-benchmark run in this job (MEASURED_PEAKS.json has no FP64 entry)",
+                             "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_nominal": achieved / FP64_NOMINAL_TFLOPS,
+                             "kernel": "k_quad", "kernel_ms_per_step": kern_ms / args.steps,
+                             "kernel_share_of_step": kern_ms / tot_ms},
+                "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    sol.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+    else:
+        run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,8 @@ typedef struct {
   int device;                    /* CUDA device ordinal; -1 = current device                  */
   int nmax_cap;                  /* upper bound for nmax (0 = 2000)                           */
   int batch_max;                 /* omegas processed per internal chunk (0 = auto)            */
+  int nmax_force;                /* >0: skip determine_nmax and sum n in [0,nmax_force] for every
+                                    table species (synthetic benchmark configs only)          */
 } alps_b200_cfg;
 
 /* replaces: allocation + pass_instructions (src/ALPS_com.f90:28-170) for the path's scalars */

@@ -620,6 +620,8 @@ static void determine_nmax(void) {
   for (is = 1; is <= S.c.nspec; is++) {
     if (S.usebM[is - 1]) {
       S.nmax[is - 1] = 1;
+    } else if (S.c.nmax_force > 0) {
+      S.nmax[is - 1] = S.c.nmax_force;
     } else {
       double besselmax = 10.0;
       nn = 0;
@@ -742,35 +744,52 @@ typedef struct {
   cplx schi_low[3][3][3]; /* (i,j,m+1) */
 } partial;
 
-/* the worker part of disp(), src/ALPS_fns.f90:333-514 */
-static void disp_worker(const struct worker *W, cplx om, partial *P) {
+/* one harmonic nn of the worker loop of disp(), src/ALPS_fns.f90:363-477.  The harmonics of a
+ * worker are independent, so the oracle may evaluate them on different threads; they are summed
+ * in the reference's order (nn ascending) afterwards. */
+static void disp_harmonic(const struct worker *W, cplx om, int nn, partial *P) {
   static const int MI[7] = {0, 0, 1, 2, 0, 0, 1}, MJ[7] = {0, 0, 1, 2, 1, 2, 2}; /* mode -> (i,j) */
-  int sp = W->sproc, nn, mode, frp, frm, n2 = W->nlim[1];
+  int mode, frp, frm;
   memset(P, 0, sizeof(*P));
-  if (sp == 0) return;
-  if (S.usebM[sp - 1]) return; /* NHDS species are added by the caller (not restated) */
-  if (S.ncap >= 0 && n2 > S.ncap) n2 = S.ncap;
-  for (nn = W->nlim[0]; nn <= n2; nn++) {
-    determine_resonances(W, om, nn, &frp, &frm);
-    if (nn == 0) {
-      static const int modes0[3] = {2, 3, 6};
-      int q;
-      for (q = 0; q < 3; q++) {
-        mode = modes0[q];
-        P->schi_low[MI[mode]][MJ[mode]][1] = full_integrate(W, om, nn, mode, frp);
-        P->schi[MI[mode]][MJ[mode]] += P->schi_low[MI[mode]][MJ[mode]][1];
-      }
-    } else if (nn == 1) {
-      for (mode = 1; mode <= 6; mode++) {
-        P->schi_low[MI[mode]][MJ[mode]][2] = full_integrate(W, om, nn, mode, frp);
-        P->schi_low[MI[mode]][MJ[mode]][0] = full_integrate(W, om, -nn, mode, frm);
-        P->schi[MI[mode]][MJ[mode]] += P->schi_low[MI[mode]][MJ[mode]][2] + P->schi_low[MI[mode]][MJ[mode]][0];
-      }
-    } else {
-      for (mode = 1; mode <= 6; mode++)
-        P->schi[MI[mode]][MJ[mode]] += full_integrate(W, om, nn, mode, frp) + full_integrate(W, om, -nn, mode, frm);
+  determine_resonances(W, om, nn, &frp, &frm);
+  if (nn == 0) {
+    static const int modes0[3] = {2, 3, 6};
+    int q;
+    for (q = 0; q < 3; q++) {
+      mode = modes0[q];
+      P->schi_low[MI[mode]][MJ[mode]][1] = full_integrate(W, om, nn, mode, frp);
+      P->schi[MI[mode]][MJ[mode]] += P->schi_low[MI[mode]][MJ[mode]][1];
     }
+  } else if (nn == 1) {
+    for (mode = 1; mode <= 6; mode++) {
+      P->schi_low[MI[mode]][MJ[mode]][2] = full_integrate(W, om, nn, mode, frp);
+      P->schi_low[MI[mode]][MJ[mode]][0] = full_integrate(W, om, -nn, mode, frm);
+      P->schi[MI[mode]][MJ[mode]] += P->schi_low[MI[mode]][MJ[mode]][2] + P->schi_low[MI[mode]][MJ[mode]][0];
+    }
+  } else {
+    for (mode = 1; mode <= 6; mode++)
+      P->schi[MI[mode]][MJ[mode]] += full_integrate(W, om, nn, mode, frp) + full_integrate(W, om, -nn, mode, frm);
   }
+}
+
+static int worker_n2(const struct worker *W) {
+  int n2 = W->nlim[1];
+  if (W->sproc == 0 || S.usebM[W->sproc - 1]) return W->nlim[0] - 1; /* NHDS species: added by the caller */
+  if (S.ncap >= 0 && n2 > S.ncap) n2 = S.ncap;
+  return n2;
+}
+
+/* the rest of the worker part of disp(): sum over nn, ee term, ns*qs (lines 478-514) */
+static void disp_worker_finish(const struct worker *W, const partial *H, int nh, partial *P) {
+  int sp = W->sproc, i, j, m, h;
+  memset(P, 0, sizeof(*P));
+  if (sp == 0 || S.usebM[sp - 1]) return;
+  for (h = 0; h < nh; h++)
+    for (i = 0; i < 3; i++)
+      for (j = i; j < 3; j++) {
+        P->schi[i][j] += H[h].schi[i][j];
+        for (m = 0; m < 3; m++) P->schi_low[i][j][m] += H[h].schi_low[i][j][m];
+      }
   if (W->nlim[0] == 0) {
     double ee = int_ee_sp(sp);
     if (S.c.kperp_norm) {
@@ -783,7 +802,6 @@ static void disp_worker(const struct worker *W, cplx om, partial *P) {
   }
   {
     double norm = S.ns[sp - 1] * S.qs[sp - 1];
-    int i, j, m;
     for (i = 0; i < 3; i++)
       for (j = i; j < 3; j++) {
         P->schi[i][j] *= norm;
@@ -802,8 +820,29 @@ int oracle_disp(const double om_[2], double D[2], double *chi0_out, double *chi0
   double kperp = S.kperp, kpar = S.kpar, vA = S.c.vA;
   if (!S.ready) return -1;
 
+  {
+    /* flatten (worker, nn) into independent tasks */
+    int ntask = 0, t, *tw, *tn, *first = calloc(S.nworkers + 1, sizeof(int));
+    partial *H;
+    for (iw = 0; iw < S.nworkers; iw++) {
+      int c = worker_n2(&S.w[iw]) - S.w[iw].nlim[0] + 1;
+      first[iw] = ntask;
+      ntask += c > 0 ? c : 0;
+    }
+    first[S.nworkers] = ntask;
+    tw = calloc(ntask + 1, sizeof(int));
+    tn = calloc(ntask + 1, sizeof(int));
+    H = calloc(ntask + 1, sizeof(partial));
+    for (iw = 0; iw < S.nworkers; iw++)
+      for (t = first[iw]; t < first[iw + 1]; t++) {
+        tw[t] = iw;
+        tn[t] = S.w[iw].nlim[0] + (t - first[iw]);
+      }
 #pragma omp parallel for schedule(dynamic, 1) num_threads(S.nthreads > 0 ? S.nthreads : omp_get_max_threads())
-  for (iw = 0; iw < S.nworkers; iw++) disp_worker(&S.w[iw], om, &P[iw]);
+    for (t = 0; t < ntask; t++) disp_harmonic(&S.w[tw[t]], om, tn[t], &H[t]);
+    for (iw = 0; iw < S.nworkers; iw++) disp_worker_finish(&S.w[iw], H + first[iw], first[iw + 1] - first[iw], &P[iw]);
+    free(first); free(tw); free(tn); free(H);
+  }
 
   /* MPI_REDUCE(SUM) over workers in rank order, lines 519-523 */
   for (iw = 0; iw < S.nworkers; iw++) {

@@ -33,6 +33,7 @@ typedef struct {
   int nproc;                  /* emulated MPI size (0 = one worker per species, n in [0,nmax]) */
   int maxfits;                /* maxval(n_fits) */
   int maxorder;               /* max poly_order */
+  int nmax_force;             /* >0: nmax(is) = nmax_force for table species (synthetic configs) */
 } oracle_cfg;
 
 int  oracle_init(const oracle_cfg *cfg);

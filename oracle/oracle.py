@@ -21,7 +21,7 @@ class OracleCfg(C.Structure):
                 ("npparbar", C.c_int), ("vA", C.c_double), ("Bessel_zero", C.c_double),
                 ("Tlim", C.c_double), ("positions_principal", C.c_int),
                 ("n_resonance_interval", C.c_int), ("kperp_norm", C.c_int), ("nproc", C.c_int),
-                ("maxfits", C.c_int), ("maxorder", C.c_int)]
+                ("maxfits", C.c_int), ("maxorder", C.c_int), ("nmax_force", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -58,7 +58,7 @@ def _f(a):
 class Oracle:
     """disp() of the reference restated on the CPU (one global instance at a time)."""
 
-    def __init__(self, plasma, nproc: int = 0, threads: int = 0):
+    def __init__(self, plasma, nproc: int = 0, threads: int = 0, nmax_force: int = 0):
         L = lib()
         self.L = L
         self.pl = plasma
@@ -66,7 +66,7 @@ class Oracle:
         cfg = OracleCfg(plasma.nspec, plasma.nperp, plasma.npar, plasma.ngamma, plasma.npparbar,
                         plasma.vA, plasma.Bessel_zero, plasma.Tlim, plasma.positions_principal,
                         plasma.n_resonance_interval, int(plasma.kperp_norm), nproc, plasma.maxfits,
-                        maxorder)
+                        maxorder, nmax_force)
         L.oracle_init(C.byref(cfg))
         for i, s in enumerate(plasma.species):
             ft = np.asarray(s.fit_type, dtype=np.int32)

@@ -1,11 +1,13 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
-inputs.  Tolerances: chi0 / wave element-wise 1e-9 relative to the tensor scale, D 1e-9 relative to
-the scale of its summed products (BASELINE.json north_star)."""
+inputs.  Tolerance 1e-9 (BASELINE.json north_star), applied as SURVEY.md section 7 prescribes:
+chi0 element-wise (tests.util.chi_err), wave(i,j) relative to the magnitude of the terms summed into
+it, D relative to the magnitude of its summed products -- at a root D and wave(1,1) are
+cancellations, so "relative to |D|" is meaningless there."""
 import numpy as np
 import pytest
 
 from alps_b200 import tables
-from tests.util import det_scale, omega_samples, tensor_err
+from tests.util import chi_err, det_scale, omega_samples, scaled_err, tensor_err, wave_scale
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -26,17 +28,18 @@ def _compare(pl, kperp, kpar, oms, nproc=0, tol=TOL):
             Do, chi_o, low_o, wave_o = orc.disp(complex(om), full=True)
             Dg, chi_g, low_g, wave_g = sol.disp(complex(om), full=True)
             for s in range(pl.nspec):
-                e = tensor_err(chi_g[s], chi_o[s])
+                e = chi_err(chi_g[s], chi_o[s])
                 assert e < tol, ("chi0", s, om, e)
                 for m in range(3):
                     if np.max(np.abs(low_o[s, :, :, m])) > 0:
-                        el = tensor_err(low_g[s, :, :, m], low_o[s, :, :, m])
+                        el = chi_err(low_g[s, :, :, m], low_o[s, :, :, m])
                         assert el < tol, ("chi0_low", s, m, om, el)
-            ew = tensor_err(wave_g, wave_o)
+            ws = wave_scale(chi_o, complex(om), pl.vA, kperp, kpar)
+            ew = scaled_err(wave_g, wave_o, ws)
             assert ew < tol, ("wave", om, ew)
-            ed = abs(Dg - Do) / det_scale(wave_o)
+            ed = abs(Dg - Do) / det_scale(ws)
             assert ed < tol, ("D", om, ed)
-            assert abs(Db[i] - Dg) <= 1e-13 * det_scale(wave_o), ("batch vs single", om)
+            assert abs(Db[i] - Dg) <= 1e-13 * det_scale(ws), ("batch vs single", om)
             worst = max(worst, ew, ed)
         return worst
     finally:
