@@ -16,7 +16,7 @@ SYMBOLS = [
     "alps_b200_disp_batch", "alps_b200_disp_batch_dev", "alps_b200_add_external_chi",
     "alps_b200_set_harmonic_shard", "alps_b200_chi_partial_len", "alps_b200_chi_partial_dev",
     "alps_b200_assemble_dev", "alps_b200_set_mode", "alps_b200_set_stream", "alps_b200_sync",
-    "alps_b200_get_info", "alps_b200_dfma_peak",
+    "alps_b200_get_info", "alps_b200_dfma_peak", "alps_b200_emulate_split",
 ]
 
 INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH = range(5)
@@ -72,6 +72,7 @@ def lib():
         L.alps_b200_set_stream.argtypes = [C.c_void_p]
         L.alps_b200_get_info.argtypes = [C.c_int, C.c_void_p]
         L.alps_b200_dfma_peak.argtypes = [C.c_void_p]
+        L.alps_b200_emulate_split.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 

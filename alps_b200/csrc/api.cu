@@ -731,7 +731,7 @@ int alps_b200_set_mode(int mode) {
 
 int alps_b200_set_stream(void* cuda_stream) {
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
-  S.stream = cuda_stream ? (cudaStream_t)cuda_stream : S.own_stream;
+  S.stream = (cudaStream_t)cuda_stream;   // NULL = the legacy default stream, like cudaStream_t 0
   return 0;
 }
 
@@ -757,6 +757,15 @@ int alps_b200_get_info(int what, double* out) {
     case ALPS_B200_INFO_BATCH: *out = S.have_k ? auto_batch() : 0; return 0;
   }
   return fail(ALPS_B200_ERR_USAGE, "unknown info id %d", what);
+}
+
+int alps_b200_emulate_split(int nproc, int nspec, const int* usebM, int* nmax, int* nhi) {
+  if (nproc < 4 || nspec < 1 || nspec > MAXSPEC || !usebM || !nmax || !nhi)
+    return fail(ALPS_B200_ERR_USAGE, "bad arguments");
+  bool bm[MAXSPEC];
+  for (int i = 0; i < nspec; i++) bm[i] = usebM[i] != 0;
+  emulate_split(nproc, nspec, bm, nmax, nhi);
+  return 0;
 }
 
 int alps_b200_dfma_peak(double* tflops) {

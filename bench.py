@@ -27,7 +27,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FLOPS_PER_POINT_HARMONIC = 34.0
+FLOPS_PER_POINT_HARMONIC = 34.0     # per (signed n, iperp, ipar), +n and -n separately
+# what k_quad executes (DESIGN.md "flop model"): per (|n|, iperp, ipar) 3 weight types x (re,im) FMA
+# = 12 flops shared by +n and -n, plus the numerator om*A'+C' (3 DFMA-pipe ops per point, shared by
+# the 4 harmonics of a thread) -> 12 + 6/4 = 13.5 flops per (|n|, point)
+FLOPS_EXECUTED_PER_ABSN_POINT = 13.5
 FP64_NOMINAL_TFLOPS = 37.2          # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 
 WORKLOADS = {
@@ -170,13 +174,17 @@ def run_ours(args, w, rank, world, local_rank):
     B = args.batch or w["batch"]
     sol = Solver(plasma, device=local_rank, nmax_force=w["nmax_force"], batch_max=B)
     nmax = sol.set_k(w["kperp"], w["kpar"])
-    sol.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sol.set_stream(stream.cuda_stream)
     om_h = map_omegas(w, rank, world, B)
     om_d = torch.from_numpy(om_h.view(np.float64).copy()).cuda()
     D_d = torch.zeros(2 * B, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     ph = sol.info(_lib.INFO_POINT_HARMONICS)
     flops_per_D = FLOPS_PER_POINT_HARMONIC * ph
+    absn_points = sum(int(n) + 1 for n in nmax) * (w["nperp"] - 1.0) * (w["npar"] - 1.0)
+    flops_exec_per_D = FLOPS_EXECUTED_PER_ABSN_POINT * absn_points
     peak_meas = sol.dfma_peak() if rank == 0 else None
 
     def step_dev():
@@ -229,7 +237,8 @@ def run_ours(args, w, rank, world, local_rank):
         n_total = world * B * args.steps
         value = n_total / (tot_ms * 1e-3)
         e2e = n_total / (e2e_ms * 1e-3)
-        achieved = flops_per_D * B * args.steps / (kern_ms * 1e-3) / 1e12   # one GPU's kernel
+        achieved = flops_exec_per_D * B * args.steps / (kern_ms * 1e-3) / 1e12   # one GPU's kernel
+        achieved34 = flops_per_D * B * args.steps / (kern_ms * 1e-3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu:
             c = cpu_sample(w, plasma, om_h[0])
@@ -250,7 +259,8 @@ def run_ours(args, w, rank, world, local_rank):
                 "data": "synthetic",
                 "config": {"workload": w["desc"], "omegas_per_step_per_gpu": B,
                            "nmax": [int(n) for n in nmax], "point_harmonics_per_D": ph,
-                           "flops_per_D": flops_per_D, "parallelism": "omega-shard x%d" % world,
+                           "flops_per_D_survey_model": flops_per_D, "flops_per_D_executed": flops_exec_per_D,
+                           "parallelism": "omega-shard x%d" % world,
                            "l2": "flushed between steps (256 MiB write)", "mode": "direct quadrature"},
                 "e2e": {"value": e2e, "unit": "D/s", "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 16 * B},
                 "gpu_launches": launches,
@@ -258,6 +268,10 @@ def run_ours(args, w, rank, world, local_rank):
                              "frac": achieved / peak_meas if peak_meas else None, "traffic": traffic,
                              "peak_source": "DFMA micro-benchmark run in this job (MEASURED_PEAKS.json has no FP64 entry)",
                              "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_nominal": achieved / FP64_NOMINAL_TFLOPS,
+                             "flop_model": "executed DFMA-pipe flops of k_quad: 13.5 per (|n|, iperp, ipar); "
+                                           "+n and -n share the p_perp sums (DESIGN.md)",
+                             "achieved_survey_34flop_model": achieved34,
+                             "frac_survey_34flop_model": achieved34 / peak_meas if peak_meas else None,
                              "kernel": "k_quad", "kernel_ms_per_step": kern_ms / args.steps,
                              "kernel_share_of_step": kern_ms / tot_ms},
                 "cpu_baseline": cpu, "clocks": clk}

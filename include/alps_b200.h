@@ -113,7 +113,8 @@ int alps_b200_assemble_dev(int n, const double *d_om, const double *d_partial, d
 int alps_b200_set_mode(int mode);
 
 /* plumbing */
-int alps_b200_set_stream(void *cuda_stream);   /* cudaStream_t; NULL = library-owned stream */
+int alps_b200_set_stream(void *cuda_stream);   /* cudaStream_t to launch on (NULL = legacy default
+                                                  stream); until called, a library-owned stream */
 int alps_b200_sync(void);
 int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
 #define ALPS_B200_INFO_POINT_HARMONICS 0  /* sum_s (2 nmax_s+1)(nperp-1)(npar-1) for current k */
@@ -121,6 +122,11 @@ int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
 #define ALPS_B200_INFO_SM_COUNT 2
 #define ALPS_B200_INFO_LAST_KERNEL_MS 3   /* device time of the last quadrature kernel batch    */
 #define ALPS_B200_INFO_BATCH 4            /* internal omega chunk size                          */
+
+/* Host-only helper (no GPU needed): determine_nmax's "more processes than harmonics" adjustment
+ * and split_processes (src/ALPS_fns.f90:4048-4064, 4079-4207) for an emulated MPI size nproc.
+ * nmax[nspec] is updated in place; nhi[nspec] receives the highest harmonic any rank sums. */
+int alps_b200_emulate_split(int nproc, int nspec, const int *usebM, int *nmax, int *nhi);
 
 /* FP64 FMA micro-benchmark (roofline denominator; not part of the path): returns TFLOP/s. */
 int alps_b200_dfma_peak(double *tflops);

@@ -1,0 +1,72 @@
+"""The C-ABI library loads and exports every symbol include/alps_b200.h declares; without a GPU the
+entry points fail loudly instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "alps_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(alps_b200_\w+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    from alps_b200 import _lib
+    L = C.CDLL(built_lib)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), n
+    assert set(_lib.SYMBOLS) == set(names)
+
+
+def test_no_cpu_fallback(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from alps_b200 import _lib, tables
+    from alps_b200.solver import Solver
+    with pytest.raises(_lib.AlpsB200Error) as e:
+        Solver(tables.config_small(16, 32))
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+    L = _lib.lib()
+    D = np.zeros(2)
+    om = np.array([0.1, 0.0])
+    rc = L.alps_b200_disp(om.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p), None, None, None)
+    assert rc != 0
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "alps_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower().replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_emulate_split_matches_oracle_split_processes(built_lib):
+    """host logic of split_processes: C++ twin (alps_b200_emulate_split) vs the oracle's restatement"""
+    from alps_b200 import _lib, tables
+    from oracle.oracle import Oracle
+    L = _lib.lib()
+    pl = tables.config_small(24, 48)
+    for nproc, k in [(4, 0.3), (6, 0.3), (8, 0.5), (12, 0.1), (40, 0.05), (64, 0.3)]:
+        orc = Oracle(pl, nproc=0)
+        base = orc.set_k(k, 0.05).copy()
+        orc = Oracle(pl, nproc=nproc)
+        adj = orc.set_k(k, 0.05)
+        want_hi = [max(n2 for s, n1, n2 in orc.nlim() if s == i + 1) for i in range(pl.nspec)]
+        nmax = base.astype(np.int32).copy()
+        nhi = np.zeros(pl.nspec, dtype=np.int32)
+        usebm = np.zeros(pl.nspec, dtype=np.int32)
+        rc = L.alps_b200_emulate_split(nproc, pl.nspec, usebm.ctypes.data_as(C.c_void_p),
+                                       nmax.ctypes.data_as(C.c_void_p), nhi.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        assert list(nmax) == list(adj), (nproc, list(nmax), list(adj))
+        assert list(nhi) == want_hi, (nproc, list(nhi), want_hi)

@@ -1,0 +1,57 @@
+"""Pins the CPU oracle (oracle/) against the reference's own golden vectors for the path:
+tests/test_kpar_fast.scan_kpara_1.root_1 (33 roots of the k_par scan, 5 significant digits) and the
+known answers in tests/test_kpar_fast.out (nmax 21/13, density integral 9.9958E-001)."""
+import os
+
+import numpy as np
+
+from alps_b200 import tables
+from oracle import driver
+from oracle.oracle import Oracle, bessj
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _fmt5(x):
+    """the reference prints es14.4e3: 5 significant digits"""
+    return float("%.4E" % x)
+
+
+def test_bessj_is_the_numerical_recipes_approximation():
+    from scipy.special import jv
+    # x >= 0 only: for x < -n the reference's BESSJ (no |x| / parity fix-up, Miller start index tuned
+    # for |x| <= n, src/ALPS_fns_rel.f90:1601-1614) is simply wrong, and parity means reproducing that.
+    xs = np.linspace(0.0, 30.0, 121)
+    for n in (0, 1, 2, 5, 13, 21):
+        ours = np.array([bessj(n, float(x)) for x in xs])
+        exact = jv(n, xs)
+        # ~1e-8 accurate, not better: parity needs the reference's approximation, not the exact J_n
+        assert np.max(np.abs(ours - exact)) < 5e-7
+    assert abs(bessj(1, 20.0) - float(jv(1, 20.0))) > 1e-12
+
+
+def test_nmax_and_density_of_test_kpar_fast():
+    pl = tables.config_kpar_fast()
+    orc = Oracle(pl, nproc=4)
+    nmax = orc.set_k(1.0e-2, 1.0e-2)
+    assert list(nmax) == [21, 13]                       # tests/test_kpar_fast.out:99-100
+    assert orc.nlim() == [(1, 0, 10), (1, 11, 21), (2, 0, 13)]
+    for i in range(2):
+        dpperp = pl.pp[i, 1, 0, 0] - pl.pp[i, 0, 0, 0]
+        dppar = pl.pp[i, 0, 1, 1] - pl.pp[i, 0, 0, 1]
+        dens = float(np.sum(pl.pp[i, :, :, 0] * pl.f0[i]) * 2 * np.pi * dpperp * dppar)
+        assert "%.4E" % dens == "9.9958E-01"            # tests/test_kpar_fast.out:53,58
+
+
+def test_golden_kpar_scan_33_rows():
+    """refine_guess + om_scan (scan_type 4, log, 32 steps, secant_osc) with the oracle's disp()."""
+    gold = np.loadtxt(os.path.join(GOLD, "test_kpar_fast.scan_kpara_1.root_1"))
+    pl = tables.config_kpar_fast()
+    orc = Oracle(pl, nproc=4)
+    rows = driver.scan_k(orc, 1.0e-2, 1.0e-2, 4, 1.0e-1, 32, True, complex(9.9e-3, -5.5e-6),
+                         numiter=50, D_threshold=1.0e-15, D_prec=1.0e-5)
+    assert len(rows) == gold.shape[0] == 33
+    for (kperp, kpar, om), g in zip(rows, gold):
+        assert _fmt5(kperp) == g[0] and _fmt5(kpar) == g[1]
+        assert _fmt5(om.real) == g[2], (kpar, om, g)
+        assert _fmt5(om.imag) == g[3], (kpar, om, g)
