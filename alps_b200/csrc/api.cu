@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -49,6 +50,7 @@ struct State {
   std::vector<double> ext;   // external chi, [nspec][PARTIAL_PER_SPEC]
   bool ext_any = false;
   int mode = 0;
+  QuadVariant qv{8, 16, 32, 2};
   int shard_rank = 0, shard_n = 1;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -230,7 +232,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     S.P.om = d_om;
     S.P.n_om = n;
     cudaEventRecord(S.ev0, S.stream);
-    cudaError_t e = launch_quad(S.P, S.stream);
+    cudaError_t e = launch_quad(S.P, S.qv.id, S.stream);
     cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.stream);
@@ -313,6 +315,10 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.ext.assign((size_t)cfg->nspec * PARTIAL_PER_SPEC, 0.0);
   S.ext_any = false;
   S.mode = 0;
+  {
+    const char* v = getenv("ALPS_B200_QUAD_VARIANT");   // tuning knob: tile shape of k_quad
+    S.qv = quad_variant(v ? atoi(v) : 8);
+  }
   S.shard_rank = 0;
   S.shard_n = 1;
   S.launches = 0;
@@ -559,10 +565,10 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
     // C' = kpar * C0
     launch_scale(h.d_C0, h.d_Cp, kpar, (size_t)(nperp - 1) * d.ldp, S.stream);
     S.launches += 1;
-    for (int n0 = d.nlo_shard; n0 <= d.nhi_shard; n0 += NH) S.tiles.push_back(QuadTile{s, n0});
-    if (make_tmap(&S.P.tmA[s], h.d_A, npar - 1, nperp - 1, d.ldp, BN, BK) ||
-        make_tmap(&S.P.tmC[s], h.d_Cp, npar - 1, nperp - 1, d.ldp, BN, BK) ||
-        make_tmap(&S.P.tmW[s], h.d_W, 3 * (d.nhi + 1), nperp - 1, d.ldw, BM, BK))
+    for (int n0 = d.nlo_shard; n0 <= d.nhi_shard; n0 += S.qv.NH) S.tiles.push_back(QuadTile{s, n0});
+    if (make_tmap(&S.P.tmA[s], h.d_A, npar - 1, nperp - 1, d.ldp, BN, S.qv.BK) ||
+        make_tmap(&S.P.tmC[s], h.d_Cp, npar - 1, nperp - 1, d.ldp, BN, S.qv.BK) ||
+        make_tmap(&S.P.tmW[s], h.d_W, 3 * (d.nhi + 1), nperp - 1, d.ldw, 3 * S.qv.NH, S.qv.BK))
       return ALPS_B200_ERR_CUDA;
   }
   const bool ni_changed = item_base != S.gh.NI;

@@ -22,13 +22,8 @@ constexpr int MAXSPEC = 8;
 constexpr int MAXFITS = 8;
 
 // ---- tile configuration of the quadrature kernel (see quad_kernel.cu)
-constexpr int NH = 16;           // harmonics per CTA tile
-constexpr int BM = 3 * NH;       // rows (3 Bessel weight types per harmonic)
-constexpr int BN = 128;          // p_par columns per tile
-constexpr int BK = 8;            // p_perp rows per pipeline stage
-constexpr int STAGES = 4;
-constexpr int CONSUMER_WARPS = 8;
-constexpr int QUAD_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int BN = 128;          // p_par columns per tile (harmonics per tile, rows per stage and
+                                 // stage count are template parameters of k_quad: QuadVariant)
 
 // ---- complex helpers (double2: x = re, y = im)
 typedef double2 cd;

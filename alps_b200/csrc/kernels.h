@@ -43,8 +43,14 @@ void launch_int_ee(const double* df0, const double* pperp, const double* ppar, i
                    int is0, double qs, double ms, double dpperp, double dppar, double* out, cudaStream_t st);
 
 // hot path (quad_kernel.cu, resonant.cu)
-size_t quad_smem_bytes();
-cudaError_t launch_quad(const QuadParams& P, cudaStream_t st);
+struct QuadVariant {
+  int id;
+  int NH;       // harmonics per CTA tile (rows = 3 NH)
+  int BK;       // p_perp rows per pipeline stage
+  int stages;
+};
+QuadVariant quad_variant(int id);
+cudaError_t launch_quad(const QuadParams& P, int variant, cudaStream_t st);
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
                  int* work, int* work_count, cudaStream_t st);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,

@@ -26,18 +26,21 @@
 
 namespace alps {
 
+// RG = row groups (4 harmonics each; 2 consumer warps per row group), BKT = p_perp rows per
+// pipeline stage, NST = stages.
+template <int RG, int BKT>
 struct alignas(128) QuadStage {
-  double A[BK * BN];
-  double C[BK * BN];
-  double W[BK * BM];
+  double A[BKT * BN];
+  double C[BKT * BN];
+  double W[BKT * 12 * RG];
 };
-constexpr uint32_t STAGE_TX_BYTES = (2 * BK * BN + BK * BM) * sizeof(double);
 
+template <int RG, int BKT, int NST>
 struct QuadSmem {
-  QuadStage st[STAGES];
-  double red[CONSUMER_WARPS][4][2][12];
-  unsigned long long full[STAGES];
-  unsigned long long empty[STAGES];
+  QuadStage<RG, BKT> st[NST];
+  double red[2 * RG][4][2][12];
+  unsigned long long full[NST];
+  unsigned long long empty[NST];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,6 +67,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ uint32_t mbar_test(unsigned long long* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -78,10 +94,19 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(QUAD_THREADS, 1) k_quad(const __grid_constant__ QuadParams P) {
+// PW = 1: dedicated TMA producer warp; PW = 0: thread 0 of consumer warp 0 issues the loads
+// (lets 12 consumer warps = 3 per SM sub-partition keep 168 registers each).
+template <int RG, int BKT, int NST, int PW, int UNR>
+__global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_constant__ QuadParams P) {
+  constexpr int CONSUMER_WARPS = 2 * RG;
+  constexpr int BM = 12 * RG;
+  constexpr int BK = BKT;
+  constexpr int STAGES = NST;
+  constexpr uint32_t STAGE_TX_BYTES = (2 * BK * BN + BK * BM) * sizeof(double);
+  typedef QuadSmem<RG, BKT, NST> Smem;
   extern __shared__ unsigned char smem_raw[];
   // 128-byte alignment for the TMA destinations; offset arithmetic keeps the shared address space
-  QuadSmem& sm = *reinterpret_cast<QuadSmem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
 
   const int tile_id = blockIdx.x % P.ntiles;
   const int iom = blockIdx.x / P.ntiles;
@@ -103,29 +128,29 @@ __global__ void __launch_bounds__(QUAD_THREADS, 1) k_quad(const __grid_constant_
   for (int i = threadIdx.x; i < CONSUMER_WARPS * 96; i += blockDim.x) (&sm.red[0][0][0][0])[i] = 0.0;
   __syncthreads();
 
-  if (warp == CONSUMER_WARPS) {
-    // ------------------------------------------------------------ TMA producer
+  const CUtensorMap* tmA = &P.tmA[tile.s];
+  const CUtensorMap* tmC = &P.tmC[tile.s];
+  const CUtensorMap* tmW = &P.tmW[tile.s];
+  const int T = NT * KC;   // pipeline iterations of this CTA
+  auto issue = [&](int it) {
+    const int stg = it % STAGES, nt = it / KC, kc = it - nt * KC;
+    mbar_expect_tx(&sm.full[stg], STAGE_TX_BYTES);
+    tma_load_2d(sm.st[stg].A, tmA, nt * BN, kc * BK, &sm.full[stg]);
+    tma_load_2d(sm.st[stg].C, tmC, nt * BN, kc * BK, &sm.full[stg]);
+    tma_load_2d(sm.st[stg].W, tmW, 3 * tile.n0, kc * BK, &sm.full[stg]);
+  };
+  if (PW && warp == CONSUMER_WARPS) {
+    // ------------------------------------------------------------ dedicated TMA producer warp
     if (lane == 0) {
-      const CUtensorMap* tmA = &P.tmA[tile.s];
-      const CUtensorMap* tmC = &P.tmC[tile.s];
-      const CUtensorMap* tmW = &P.tmW[tile.s];
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int nt = 0; nt < NT; nt++) {
-        for (int kc = 0; kc < KC; kc++) {
-          mbar_wait(&sm.empty[stage], phase ^ 1);
-          mbar_expect_tx(&sm.full[stage], STAGE_TX_BYTES);
-          tma_load_2d(sm.st[stage].A, tmA, nt * BN, kc * BK, &sm.full[stage]);
-          tma_load_2d(sm.st[stage].C, tmC, nt * BN, kc * BK, &sm.full[stage]);
-          tma_load_2d(sm.st[stage].W, tmW, 3 * tile.n0, kc * BK, &sm.full[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
+      for (int it = 0; it < T; it++) {
+        if (it >= STAGES) mbar_wait(&sm.empty[it % STAGES], ((it / STAGES) & 1) ^ 1);
+        issue(it);
       }
     }
     return;
+  }
+  if (!PW && threadIdx.x == 0) {
+    for (int it = 0; it < STAGES - 1 && it < T; it++) issue(it);
   }
 
   // ---------------------------------------------------------------- consumers
@@ -138,7 +163,8 @@ __global__ void __launch_bounds__(QUAD_THREADS, 1) k_quad(const __grid_constant_
   const int WIN = g.WIN, WINX = g.WINX, M_I = g.M_I;
 
   int stage = 0;
-  uint32_t phase = 0;
+  uint32_t phase = 0, ready = 0;
+  int git = 0;
   for (int nt = 0; nt < NT; nt++) {
     double ar[12][2], ai[12][2];
 #pragma unroll
@@ -146,30 +172,57 @@ __global__ void __launch_bounds__(QUAD_THREADS, 1) k_quad(const __grid_constant_
       ar[r][0] = ar[r][1] = 0.0;
       ai[r][0] = ai[r][1] = 0.0;
     }
-    for (int kc = 0; kc < KC; kc++) {
-      mbar_wait(&sm.full[stage], phase);
+    for (int kc = 0; kc < KC; kc++, git++) {
+      if (!PW) {
+        // inline producer: refill the stage released by iteration git-1
+        if (threadIdx.x == 0) {
+          const int nx = git + STAGES - 1;
+          if (nx < T) {
+            if (nx >= STAGES) mbar_wait(&sm.empty[nx % STAGES], ((nx / STAGES) & 1) ^ 1);
+            issue(nx);
+          }
+        }
+        __syncwarp();
+      }
+      if (!ready) mbar_wait(&sm.full[stage], phase);
+      {
+        // test the next stage's barrier now; the answer is only needed after this stage's FMAs
+        const int ns = (stage + 1 == STAGES) ? 0 : stage + 1;
+        ready = mbar_test(&sm.full[ns], (stage + 1 == STAGES) ? (phase ^ 1) : phase);
+      }
       const double* sA = sm.st[stage].A + 2 * cg;
       const double* sC = sm.st[stage].C + 2 * cg;
       const double* sW = sm.st[stage].W + 12 * rg;
+      // operands of row kk+1 are fetched from shared memory while row kk is in the FMA pipe
+      double2 a = *reinterpret_cast<const double2*>(sA);
+      double2 c = *reinterpret_cast<const double2*>(sC);
+      double2 w[6];
 #pragma unroll
+      for (int q = 0; q < 6; q++) w[q] = reinterpret_cast<const double2*>(sW)[q];
+#pragma unroll UNR
       for (int kk = 0; kk < BK; kk++) {
-        const double2 a = *reinterpret_cast<const double2*>(sA + kk * BN);
-        const double2 c = *reinterpret_cast<const double2*>(sC + kk * BN);
         // numerator of resU at this grid point: Num = om * A' + C'
         const double nr0 = fma(omr, a.x, c.x), ni0 = omi * a.x;
         const double nr1 = fma(omr, a.y, c.y), ni1 = omi * a.y;
-        const double2* wp = reinterpret_cast<const double2*>(sW + kk * BM);
+        double2 wc[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) wc[q] = w[q];
+        if (kk + 1 < BK) {
+          a = *reinterpret_cast<const double2*>(sA + (kk + 1) * BN);
+          c = *reinterpret_cast<const double2*>(sC + (kk + 1) * BN);
+#pragma unroll
+          for (int q = 0; q < 6; q++) w[q] = reinterpret_cast<const double2*>(sW + (kk + 1) * BM)[q];
+        }
 #pragma unroll
         for (int q = 0; q < 6; q++) {
-          const double2 w = wp[q];
-          ar[2 * q][0] = fma(w.x, nr0, ar[2 * q][0]);
-          ai[2 * q][0] = fma(w.x, ni0, ai[2 * q][0]);
-          ar[2 * q][1] = fma(w.x, nr1, ar[2 * q][1]);
-          ai[2 * q][1] = fma(w.x, ni1, ai[2 * q][1]);
-          ar[2 * q + 1][0] = fma(w.y, nr0, ar[2 * q + 1][0]);
-          ai[2 * q + 1][0] = fma(w.y, ni0, ai[2 * q + 1][0]);
-          ar[2 * q + 1][1] = fma(w.y, nr1, ar[2 * q + 1][1]);
-          ai[2 * q + 1][1] = fma(w.y, ni1, ai[2 * q + 1][1]);
+          ar[2 * q][0] = fma(wc[q].x, nr0, ar[2 * q][0]);
+          ai[2 * q][0] = fma(wc[q].x, ni0, ai[2 * q][0]);
+          ar[2 * q][1] = fma(wc[q].x, nr1, ar[2 * q][1]);
+          ai[2 * q][1] = fma(wc[q].x, ni1, ai[2 * q][1]);
+          ar[2 * q + 1][0] = fma(wc[q].y, nr0, ar[2 * q + 1][0]);
+          ai[2 * q + 1][0] = fma(wc[q].y, ni0, ai[2 * q + 1][0]);
+          ar[2 * q + 1][1] = fma(wc[q].y, nr1, ar[2 * q + 1][1]);
+          ai[2 * q + 1][1] = fma(wc[q].y, ni1, ai[2 * q + 1][1]);
         }
       }
       __syncwarp();
@@ -246,7 +299,7 @@ __global__ void __launch_bounds__(QUAD_THREADS, 1) k_quad(const __grid_constant_
 
   // ---------------------------------------------------------------- write the moment sums
   asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
-  for (int i = threadIdx.x; i < 4 * 96; i += CONSUMER_WARPS * 32) {
+  for (int i = threadIdx.x; i < RG * 96; i += CONSUMER_WARPS * 32) {
     const int rgq = i / 96, rem = i % 96;
     const int nn = rem / 24, sg = (rem % 24) / 12, q = rem % 12;
     const int nabs = tile.n0 + 4 * rgq + nn;
@@ -255,18 +308,54 @@ __global__ void __launch_bounds__(QUAD_THREADS, 1) k_quad(const __grid_constant_
   }
 }
 
-size_t quad_smem_bytes() { return sizeof(QuadSmem) + 128; }
-
-cudaError_t launch_quad(const QuadParams& P, cudaStream_t st) {
+// ---------------------------------------------------------------- variants / launcher
+template <int RG, int BKT, int NST, int PW, int UNR>
+static cudaError_t launch_variant(const QuadParams& P, cudaStream_t st) {
   static bool attr_set = false;
+  const size_t smem = sizeof(QuadSmem<RG, BKT, NST>) + 128;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)quad_smem_bytes());
+    cudaError_t e =
+        cudaFuncSetAttribute(k_quad<RG, BKT, NST, PW, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (P.n_om <= 0 || P.ntiles <= 0) return cudaSuccess;
-  k_quad<<<P.n_om * P.ntiles, QUAD_THREADS, quad_smem_bytes(), st>>>(P);
+  k_quad<RG, BKT, NST, PW, UNR><<<P.n_om * P.ntiles, (2 * RG + PW) * 32, smem, st>>>(P);
   return cudaGetLastError();
+}
+
+QuadVariant quad_variant(int id) {
+  switch (id) {
+    case 1: return QuadVariant{1, 16, 16, 4};    // 8 consumer warps + producer, BK=16
+    case 2: return QuadVariant{2, 24, 8, 4};     // 12 consumer warps, inline producer, BK=8
+    case 3: return QuadVariant{3, 24, 16, 3};    // 12 consumer warps, inline producer, BK=16
+    case 4: return QuadVariant{4, 16, 8, 4};     // 8 consumer warps, inline producer, BK=8
+    case 5: return QuadVariant{5, 16, 16, 4};    // 8 consumer warps, inline producer, BK=16
+    case 6: return QuadVariant{6, 24, 16, 4};    // 12 consumer warps, inline producer, BK=16, 4 stages
+    case 7: return QuadVariant{7, 24, 32, 2};    // 12 consumer warps, inline producer, BK=32, 2 stages
+    case 8: return QuadVariant{8, 16, 32, 2};    // 8 consumer warps, inline producer, BK=32, 2 stages
+    case 9: return QuadVariant{9, 24, 32, 2};    // as 7, k loop unrolled by 8 only
+    case 10: return QuadVariant{10, 24, 24, 3};  // 12 consumer warps, BK=24, 3 stages
+    case 11: return QuadVariant{11, 16, 32, 2};  // as 8, k loop unrolled by 8 only
+    default: return QuadVariant{0, 16, 8, 4};    // 8 consumer warps + producer, BK=8
+  }
+}
+
+cudaError_t launch_quad(const QuadParams& P, int variant, cudaStream_t st) {
+  if (P.n_om <= 0 || P.ntiles <= 0) return cudaSuccess;
+  switch (variant) {
+    case 1: return launch_variant<4, 16, 4, 1, 16>(P, st);
+    case 2: return launch_variant<6, 8, 4, 0, 8>(P, st);
+    case 3: return launch_variant<6, 16, 3, 0, 16>(P, st);
+    case 4: return launch_variant<4, 8, 4, 0, 8>(P, st);
+    case 5: return launch_variant<4, 16, 4, 0, 16>(P, st);
+    case 6: return launch_variant<6, 16, 4, 0, 16>(P, st);
+    case 7: return launch_variant<6, 32, 2, 0, 32>(P, st);
+    case 8: return launch_variant<4, 32, 2, 0, 32>(P, st);
+    case 9: return launch_variant<6, 32, 2, 0, 8>(P, st);
+    case 10: return launch_variant<6, 24, 3, 0, 24>(P, st);
+    case 11: return launch_variant<4, 32, 2, 0, 8>(P, st);
+    default: return launch_variant<4, 8, 4, 1, 8>(P, st);
+  }
 }
 
 }  // namespace alps
