@@ -17,6 +17,8 @@ SYMBOLS = [
     "alps_b200_set_harmonic_shard", "alps_b200_chi_partial_len", "alps_b200_chi_partial_dev",
     "alps_b200_assemble_dev", "alps_b200_set_mode", "alps_b200_set_stream", "alps_b200_sync",
     "alps_b200_get_info", "alps_b200_dfma_peak", "alps_b200_emulate_split",
+    "alps_b200_secant", "alps_b200_secant_osc", "alps_b200_rtsec", "alps_b200_refine_guess",
+    "alps_b200_map_search", "alps_b200_calc_eigen", "alps_b200_scan_setup", "alps_b200_om_scan",
 ]
 
 INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH = range(5)
@@ -30,6 +32,22 @@ class Cfg(C.Structure):
                 ("emulate_nproc", C.c_int), ("maxfits", C.c_int), ("maxorder", C.c_int),
                 ("device", C.c_int), ("nmax_cap", C.c_int), ("batch_max", C.c_int),
                 ("nmax_force", C.c_int)]
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [("numiter", C.c_int), ("D_threshold", C.c_double), ("D_prec", C.c_double),
+                ("D_tol", C.c_double), ("D_gap", C.c_double), ("secant_method", C.c_int)]
+
+
+class MapCfg(C.Structure):
+    _fields_ = [("omi", C.c_double), ("omf", C.c_double), ("gami", C.c_double), ("gamf", C.c_double),
+                ("nr", C.c_int), ("ni", C.c_int), ("loggridw", C.c_int), ("loggridg", C.c_int),
+                ("determine_minima", C.c_int)]
+
+
+class ScanCfg(C.Structure):
+    _fields_ = [("type", C.c_int), ("n_out", C.c_int), ("n_res", C.c_int), ("log_scan", C.c_int),
+                ("eigen", C.c_int), ("heat", C.c_int), ("diff", C.c_double), ("diff2", C.c_double)]
 
 
 class AlpsB200Error(RuntimeError):
@@ -73,6 +91,18 @@ def lib():
         L.alps_b200_get_info.argtypes = [C.c_int, C.c_void_p]
         L.alps_b200_dfma_peak.argtypes = [C.c_void_p]
         L.alps_b200_emulate_split.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        V = C.c_void_p
+        L.alps_b200_secant.argtypes = [V, V, V]
+        L.alps_b200_secant_osc.argtypes = [V, V, V]
+        L.alps_b200_rtsec.argtypes = [V, V, V]
+        L.alps_b200_refine_guess.argtypes = [C.c_int, V, V, C.c_char_p, V]
+        L.alps_b200_map_search.argtypes = [V, C.c_char_p, V, V, V, C.c_int, V, V]
+        L.alps_b200_calc_eigen.argtypes = [V, C.c_int, V, V, V, C.c_double, C.c_double, C.c_double,
+                                           C.c_int, C.c_int, V, V, V, V, V, V, V]
+        L.alps_b200_scan_setup.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, V, V, V]
+        L.alps_b200_om_scan.argtypes = [V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V,
+                                        C.c_char_p, C.c_int, V]
         _LIB = L
     return _LIB
 

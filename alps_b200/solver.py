@@ -124,6 +124,103 @@ class Solver:
         _lib.check(self.L.alps_b200_add_external_chi(is_, _p(c.view(np.float64)),
                                                      None if cl is None else _p(cl.view(np.float64))))
 
+    # ---- omega-point generators (C++ twins in csrc/drivers.cpp; D always comes from the GPU)
+    @staticmethod
+    def opts(numiter=50, D_threshold=1.0e-15, D_prec=1.0e-5, D_tol=1.0e-7, D_gap=1.0e-5, secant_method=2):
+        return _lib.SolverOpts(numiter, D_threshold, D_prec, D_tol, D_gap, secant_method)
+
+    def _root(self, fn, om, opts):
+        v = np.array([om.real, om.imag])
+        it = C.c_int(0)
+        _lib.check(fn(_p(v), C.byref(opts), C.byref(it)))
+        return complex(v[0], v[1]), it.value
+
+    def secant(self, om, opts):          # src/ALPS_fns.f90:1815-1917
+        return self._root(self.L.alps_b200_secant, om, opts)
+
+    def secant_osc(self, om, opts):      # src/ALPS_fns.f90:1919-2101
+        return self._root(self.L.alps_b200_secant_osc, om, opts)
+
+    def rtsec(self, om, opts):           # src/ALPS_fns.f90:2105-2195
+        return self._root(self.L.alps_b200_rtsec, om, opts)
+
+    def refine_guess(self, wroots, opts, roots_path=None):   # src/ALPS_fns.f90:3793-3856
+        w = np.ascontiguousarray(np.asarray(wroots, dtype=np.complex128).ravel())
+        D = np.zeros(w.size, dtype=np.complex128)
+        _lib.check(self.L.alps_b200_refine_guess(w.size, _p(w.view(np.float64)), C.byref(opts),
+                                                 roots_path.encode() if roots_path else None,
+                                                 _p(D.view(np.float64))))
+        return w, D
+
+    def map_search(self, omi, omf, gami, gamf, nr, ni, loggridw=False, loggridg=False,
+                   determine_minima=True, numroots=100, map_path=None):   # src/ALPS_fns.f90:3595-3788
+        m = _lib.MapCfg(omi, omf, gami, gamf, nr, ni, int(loggridw), int(loggridg), int(determine_minima))
+        n = nr * ni
+        om = np.zeros(n, dtype=np.complex128)
+        cal = np.zeros(n, dtype=np.complex128)
+        val = np.zeros(n)
+        iroots = np.zeros(2 * numroots, dtype=np.int32)
+        nfound = C.c_int(0)
+        _lib.check(self.L.alps_b200_map_search(C.byref(m), map_path.encode() if map_path else None,
+                                               _p(om.view(np.float64)), _p(val), _p(cal.view(np.float64)),
+                                               numroots, _p(iroots), C.byref(nfound)))
+        shape = (nr, ni)
+        om, cal, val = (a.reshape(shape, order="F") for a in (om, cal, val))
+        k = min(nfound.value, numroots)
+        ir = iroots[0:2 * k:2] - 1
+        ii = iroots[1:2 * k:2] - 1
+        return om, val, cal, [complex(om[a, b]) for a, b in zip(ir, ii)]
+
+    def current_int(self):
+        """n_s q_s <p_par>/m_s of derivative_f0 (src/ALPS_fns.f90:161-189), host bookkeeping"""
+        pl = self.pl
+        out = np.zeros(pl.nspec)
+        for i, s in enumerate(pl.species):
+            if s.usebM:
+                continue
+            dpperp = pl.pp[i, 2, 2, 0] - pl.pp[i, 1, 2, 0]
+            dppar = abs(pl.pp[i, 2, 2, 1] - pl.pp[i, 2, 1, 1])
+            out[i] = np.sum((s.ns * s.qs / s.ms) * pl.pp[i, :, :, 0] * pl.pp[i, :, :, 1] * pl.f0[i]
+                            * 2.0 * np.pi * dpperp * dppar)
+        return out
+
+    def calc_eigen(self, om, eigen=True, heat=True, current_int=None):   # src/ALPS_fns.f90:2605-2899
+        pl = self.pl
+        n = pl.nspec
+        ns = np.array([s.ns for s in pl.species])
+        qs = np.array([s.qs for s in pl.species])
+        ci = self.current_int() if current_int is None else np.asarray(current_int, dtype=np.float64)
+        omv = np.array([om.real, om.imag])
+        ef, bf = np.zeros(3, np.complex128), np.zeros(3, np.complex128)
+        Us, ds = np.zeros(3 * n, np.complex128), np.zeros(n, np.complex128)
+        Ps, Pss, W = np.zeros(n), np.zeros(4 * n), C.c_double(0.0)
+        f = lambda a: _p(a.view(np.float64))
+        _lib.check(self.L.alps_b200_calc_eigen(_p(omv), n, _p(ns), _p(qs), _p(ci), self.kperp, self.kpar,
+                                               pl.vA, int(eigen), int(heat), f(ef), f(bf), f(Us), f(ds),
+                                               _p(Ps), _p(Pss), C.byref(W)))
+        return dict(ef=ef, bf=bf, Us=Us.reshape((3, n), order="F"), ds=ds, Ps=Ps,
+                    Ps_split=Pss.reshape((4, n), order="F"), W_EM=W.value)
+
+    def om_scan(self, wroots, opts, scan_type, swi, swf, swlog, ns_steps, nres=1, eigen=False, heat=False,
+                prefix=None, ik=1):   # src/ALPS_fns.f90:2198-2600 (+ scan_read, src/ALPS_io.f90:455-549)
+        pl = self.pl
+        n = pl.nspec
+        kpl, kql = C.c_double(self.kperp), C.c_double(self.kpar)
+        sc = _lib.ScanCfg()
+        _lib.check(self.L.alps_b200_scan_setup(scan_type, swi, swf, int(swlog), ns_steps, nres, int(eigen),
+                                               int(heat), C.byref(kpl), C.byref(kql), C.byref(sc)))
+        w = np.ascontiguousarray(np.asarray(wroots, dtype=np.complex128).ravel())
+        ns = np.array([s.ns for s in pl.species])
+        qs = np.array([s.qs for s in pl.species])
+        ci = self.current_int()
+        kperp, kpar = C.c_double(self.kperp), C.c_double(self.kpar)
+        rows = np.zeros((ns_steps + 1, w.size, 4))
+        _lib.check(self.L.alps_b200_om_scan(C.byref(sc), w.size, _p(w.view(np.float64)), C.byref(opts), n,
+                                            _p(ns), _p(qs), _p(ci), pl.vA, C.byref(kperp), C.byref(kpar),
+                                            prefix.encode() if prefix else None, ik, _p(rows)))
+        self.kperp, self.kpar = kperp.value, kpar.value
+        return rows, w
+
     # ---- plumbing
     def set_stream(self, stream_ptr: Optional[int]):
         _lib.check(self.L.alps_b200_set_stream(C.c_void_p(stream_ptr or 0)))

@@ -123,6 +123,55 @@ int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
 #define ALPS_B200_INFO_LAST_KERNEL_MS 3   /* device time of the last quadrature kernel batch    */
 #define ALPS_B200_INFO_BATCH 4            /* internal omega chunk size                          */
 
+/* ------------------------------------------------------------------------------------------
+ * Host-side twins of the reference's omega-point generators (alps_b200/csrc/drivers.cpp).  They
+ * only produce omegas, call alps_b200_disp / alps_b200_disp_batch, and write the reference's
+ * output files; all paths may be NULL (no file output).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {      /* &system entries read by the solvers, src/ALPS_io.f90:79-85 */
+  int numiter;
+  double D_threshold, D_prec, D_tol, D_gap;
+  int secant_method;  /* 0 secant, 1 rtsec, 2 secant_osc (src/ALPS_fns.f90:2504-2516) */
+} alps_b200_solver_opts;
+
+typedef struct {      /* &maps_1, src/ALPS_io.f90:233-256 */
+  double omi, omf, gami, gamf;
+  int nr, ni, loggridw, loggridg, determine_minima;
+} alps_b200_map;
+
+typedef struct {      /* type scanner, src/ALPS_var.f90:354-386 */
+  int type;           /* 0 k1_k2, 1 theta, 2 |k| at constant theta, 3 kperp, 4 kpar */
+  int n_out, n_res, log_scan, eigen, heat;
+  double diff, diff2;
+} alps_b200_scan;
+
+/* replaces: secant (src/ALPS_fns.f90:1815-1917), secant_osc (:1919-2101), rtsec (:2105-2195) */
+int alps_b200_secant(double om[2], const alps_b200_solver_opts *o, int *iters);
+int alps_b200_secant_osc(double om[2], const alps_b200_solver_opts *o, int *iters);
+int alps_b200_rtsec(double om[2], const alps_b200_solver_opts *o, int *iflag);
+/* replaces: refine_guess (:3793-3856); writes <runname>.roots (i4,5es14.4e3) */
+int alps_b200_refine_guess(int nroots, double *wroots, const alps_b200_solver_opts *o,
+                           const char *roots_path, double *D_out);
+/* replaces: map_search (:3595-3788) + find_minima (:3860-3966); the nr x ni loop is one GPU batch;
+ * writes <runname>.map (5es16.6e3).  om/cal: nr*ni complex (ir fastest), val: nr*ni, iroots(2,numroots) */
+int alps_b200_map_search(const alps_b200_map *m, const char *map_path, double *om_out, double *val_out,
+                         double *cal_out, int numroots, int *iroots, int *nroots_found);
+/* replaces: calc_eigen (:2605-2899).  current_int(nspec) from derivative_f0 (may be NULL = 0).
+ * Outputs: ef(3), bf(3), Us(3,nspec), ds(nspec) complex; Ps(nspec), Ps_split(4,nspec), W_EM real. */
+int alps_b200_calc_eigen(const double om[2], int nspec, const double *ns, const double *qs,
+                         const double *current_int, double kperp, double kpar, double vA, int eigen,
+                         int heat, double *ef, double *bf, double *Us, double *ds, double *Ps,
+                         double *Ps_split, double *W_EM);
+/* replaces: scan_read step sizes (src/ALPS_io.f90:472-549); updates kperp_last / kpar_last */
+int alps_b200_scan_setup(int scan_type, double swi, double swf, int swlog, int ns, int nres, int eigen,
+                         int heat, double *kperp_last, double *kpar_last, alps_b200_scan *out);
+/* replaces: om_scan (:2198-2600); writes <prefix>.scan_<id><ik>.root_<in> (+ .eigen_, .heat_,
+ * .heat_mech_).  rows_out (may be NULL): (n_out+1) x nroots x 4 doubles (kperp,kpar,Re om,Im om). */
+int alps_b200_om_scan(const alps_b200_scan *sc, int nroots, double *wroots,
+                      const alps_b200_solver_opts *o, int nspec, const double *ns, const double *qs,
+                      const double *current_int, double vA, double *kperp_io, double *kpar_io,
+                      const char *prefix, int ik, double *rows_out);
+
 /* Host-only helper (no GPU needed): determine_nmax's "more processes than harmonics" adjustment
  * and split_processes (src/ALPS_fns.f90:4048-4064, 4079-4207) for an emulated MPI size nproc.
  * nmax[nspec] is updated in place; nhi[nspec] receives the highest harmonic any rank sums. */

@@ -1,0 +1,48 @@
+"""torchrun check of both multi-GPU modes on real GPUs (NCCL):
+   omega sharding (no data-path collective, one all_gather) and harmonic sharding (all_reduce of the
+   chi partials).  torchrun --nproc-per-node N scripts/multi_gpu_check.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from alps_b200 import tables, sharding
+from alps_b200.solver import Solver
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+pl = tables.config_small(48, 96, kind=2)
+sol = Solver(pl, device=lr)
+st = torch.cuda.Stream(); torch.cuda.set_stream(st); sol.set_stream(st.cuda_stream)
+kperp, kpar = 1.5, 0.05
+sol.set_k(kperp, kpar)
+rng = np.random.default_rng(7)
+n = 64
+oms = rng.uniform(0.05, 2.0, n) + 1j * rng.uniform(-0.03, 0.03, n)
+D_full = sol.disp_batch(oms)          # every rank computes the reference answer on its own GPU
+# (i) omega sharding
+lo, hi = sharding.omega_shard(n, rank, world)
+local = sol.disp_batch(oms[lo:hi])
+def all_gather(pad):
+    t = torch.from_numpy(pad.view(np.float64).copy()).cuda()
+    outs = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    return [o.cpu().numpy().view(np.complex128) for o in outs]
+D1 = sharding.gather_omega_shards(local, n, rank, world, all_gather)
+ok1 = np.array_equal(D1, D_full)
+# (ii) harmonic sharding + NCCL all_reduce of the partials
+sol.set_harmonic_shard(rank, world); sol.set_k(kperp, kpar)
+L = sol.chi_partial_len()
+om_d = torch.from_numpy(oms.view(np.float64).copy()).cuda()
+part = torch.zeros(n * L, dtype=torch.float64, device="cuda")
+sol.chi_partial_dev(n, om_d.data_ptr(), part.data_ptr())
+dist.all_reduce(part, op=dist.ReduceOp.SUM)
+D_d = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
+sol.assemble_dev(n, om_d.data_ptr(), part.data_ptr(), D_d.data_ptr())
+torch.cuda.synchronize()
+D2 = D_d.cpu().numpy().view(np.complex128)
+err2 = float(np.max(np.abs(D2 - D_full) / np.abs(D_full)))
+print("rank %d/%d omega-shard identical=%s harmonic-shard max rel err=%.2e nmax=%s" % (rank, world, ok1, err2, list(sol.nmax)), flush=True)
+assert ok1 and err2 < 1e-10
+sol.close(); dist.destroy_process_group()

@@ -1,0 +1,72 @@
+"""The reference's own golden files reproduced through the CUDA path and the C++ twin drivers:
+refine_guess + k_par scan (secant_osc) with eigenfunctions and heating for tests/test_kpar_fast.in
+(goldens: tests/test_kpar_fast.{scan,eigen,heat}_kpara_1.root_1, 5 significant digits)."""
+import os
+
+import numpy as np
+import pytest
+
+from alps_b200 import tables
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rows(path):
+    return [line.split() for line in open(path) if line.strip()]
+
+
+def test_kpar_fast_scan_eigen_heat_files(tmp_path):
+    from alps_b200.solver import Solver
+    pl = tables.config_kpar_fast()
+    sol = Solver(pl, emulate_nproc=4)
+    try:
+        sol.set_k(1.0e-2, 1.0e-2)
+        opts = sol.opts(numiter=50, D_threshold=1.0e-15, D_prec=1.0e-5, D_tol=1.0e-7, D_gap=1.0e-5,
+                        secant_method=2)
+        roots_file = str(tmp_path / "test_kpar_fast.roots")
+        w, D = sol.refine_guess([complex(9.9e-3, -5.5e-6)], opts, roots_path=roots_file)
+        prefix = str(tmp_path / "test_kpar_fast")
+        rows, w = sol.om_scan(w, opts, scan_type=4, swi=1.0e-3, swf=1.0e-1, swlog=True, ns_steps=32, nres=1,
+                              eigen=True, heat=True, prefix=prefix, ik=1)
+    finally:
+        sol.close()
+    assert rows.shape == (33, 1, 4)
+    for kind, rtol in (("scan", 0.0), ("eigen", 2e-4), ("heat", 2e-4)):
+        ours = _rows(prefix + ".%s_kpara_1.root_1" % kind)
+        gold = _rows(os.path.join(GOLD, "test_kpar_fast.%s_kpara_1.root_1" % kind))
+        assert len(ours) == len(gold) == 33, kind
+        for ro, rg in zip(ours, gold):
+            assert len(ro) == len(rg), kind
+            if kind == "scan":
+                assert ro == rg, (kind, ro, rg)        # identical text: every printed digit
+            else:
+                a = np.array([float(x) for x in ro])
+                b = np.array([float(x) for x in rg])
+                # columns are 5-digit roundings of quantities derived from the 5-digit-stable root:
+                # allow the last printed digit to move, relative to the largest column of the row group
+                assert np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), 1e-3 * np.max(np.abs(b)))), (kind, ro, rg)
+    line = open(roots_file).read().split()
+    assert line[0] == "1" and line[1] == "9.9881E-003" and line[2] == "-2.3132E-007"
+
+
+def test_map_search_finds_the_root_region(tmp_path):
+    """50x50 map (tests/test_map.in grid shape) around the C1 root: the minimum of log10|D| is the
+    cell next to the known root, the .map file has the reference's layout."""
+    from alps_b200.solver import Solver
+    pl = tables.config_kpar_fast()
+    sol = Solver(pl, emulate_nproc=4)
+    try:
+        sol.set_k(1.0e-2, 1.0e-2)
+        path = str(tmp_path / "t.map")
+        om, val, cal, roots = sol.map_search(5.0e-3, 1.5e-2, -1.0e-5, 1.0e-5, 50, 50, map_path=path)
+        D_direct = sol.disp_batch(om.ravel(order="F")).reshape(om.shape, order="F")
+    finally:
+        sol.close()
+    assert np.array_equal(cal, D_direct)
+    ir, ii = np.unravel_index(np.argmin(val), val.shape)
+    assert abs(om[ir, ii].real - 9.98811e-3) < 2.1e-4
+    assert any(abs(r.real - 9.98811e-3) < 2.1e-4 for r in roots)
+    lines = open(path).read().split("\n")
+    assert len(lines[0]) == 5 * 16 and lines[50] == ""          # 5es16.6e3 rows, blank line per ir
+    assert len([l for l in lines if l.strip()]) == 2500
