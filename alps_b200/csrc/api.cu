@@ -538,7 +538,8 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
     item_base += 2 * (d.nhi + 1);
     // harmonic shard of this process: contiguous blocks of [0,nhi]
     {
-      const int tot = d.nhi + 1, per = (tot + S.shard_n - 1) / S.shard_n;
+      // even block size: the TMA box of W starts at column 3*n0, which must be 16-byte aligned
+      const int tot = d.nhi + 1, per = (((tot + S.shard_n - 1) / S.shard_n) + 1) & ~1;
       d.nlo_shard = std::min(S.shard_rank * per, tot);
       d.nhi_shard = std::min(d.nlo_shard + per, tot) - 1;
     }

@@ -26,7 +26,7 @@ def harmonic_shard(nhi: int, rank: int, world: int) -> Tuple[int, int]:
     """[nlo, nhi_rank] (inclusive; empty if nlo > nhi_rank) of the harmonics |n| in [0, nhi] owned by
     `rank` -- the same blocks alps_b200_set_harmonic_shard uses (api.cu, alps_b200_set_k)."""
     tot = nhi + 1
-    per = (tot + world - 1) // world
+    per = ((tot + world - 1) // world + 1) & ~1   # even blocks: TMA needs 16-byte aligned W columns
     nlo = min(rank * per, tot)
     return nlo, min(nlo + per, tot) - 1
 
