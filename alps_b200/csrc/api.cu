@@ -25,7 +25,13 @@ struct SpeciesHost {
   double *d_pperp = nullptr, *d_ppar = nullptr, *d_A = nullptr, *d_C0 = nullptr, *d_Cp = nullptr;
   double *d_J = nullptr, *d_W = nullptr, *d_pf = nullptr, *d_poly = nullptr, *d_ee = nullptr;
   size_t cap_J = 0, cap_W = 0;
-  bool table = false;   // integrated from the f0 table by this library
+  bool grid = false;    // has f0 tables on the (p_perp,p_par) grid (everything but use_bM species)
+  bool table = false;   // non-relativistic table species: goes through k_quad
+  // relativistic species
+  double *d_grel = nullptr, *d_pbrel = nullptr, *d_f0rel = nullptr, *d_dfg = nullptr, *d_dfp = nullptr;
+  int *d_cone_lo = nullptr, *d_cone_up = nullptr;
+  bool have_rel = false;
+  double ee_rel = 0.0;   // int_ee_rel, src/ALPS_fns_rel.f90:1097-1215
 };
 
 struct State {
@@ -46,6 +52,8 @@ struct State {
   int *d_work = nullptr, *d_work_count = nullptr, *d_err = nullptr;
   QuadTile* d_tiles = nullptr;
   std::vector<QuadTile> tiles;
+  RelTile* d_rtiles = nullptr;
+  std::vector<RelTile> rtiles;
   QuadParams P{};
   std::vector<double> ext;   // external chi, [nspec][PARTIAL_PER_SPEC]
   bool ext_any = false;
@@ -162,7 +170,7 @@ int build_tables_from_df0() {
   for (int s = 0; s < nspec; s++) {
     SpeciesHost& h = S.sp[s];
     SpeciesDev& d = S.gh.sp[s];
-    if (!h.table) continue;
+    if (!h.grid) continue;
     const int ldp = (npar - 1 + 1) & ~1;
     d.ldp = ldp;
     size_t n = (size_t)(nperp - 1) * ldp;
@@ -176,6 +184,7 @@ int build_tables_from_df0() {
     CK(cudaMemcpyAsync(&d.int_ee, h.d_ee, sizeof(double), cudaMemcpyDeviceToHost, S.stream));
     d.A = h.d_A;
     d.Cp = h.d_Cp;
+    d.C0 = h.d_C0;
   }
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());
@@ -236,6 +245,10 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.stream);
+    if (!S.rtiles.empty()) {
+      launch_rel(gd, d_om, n, S.d_rtiles, (int)S.rtiles.size(), S.d_Sres, S.d_err + 6, S.stream);
+      S.launches += 1;
+    }
     double* part = d_partial_out ? d_partial_out : S.d_partial;
     launch_chi_partial(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.d_Sres, part, S.stream);
     S.launches += 4;
@@ -299,6 +312,8 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.gh.nspec = cfg->nspec;
   S.gh.nperp = cfg->nperp;
   S.gh.npar = cfg->npar;
+  S.gh.ngamma = cfg->ngamma;
+  S.gh.npparbar = cfg->npparbar;
   S.gh.M_I = cfg->positions_principal;
   S.gh.M_P = cfg->n_resonance_interval;
   S.gh.WIN = 2 * cfg->positions_principal + 7;
@@ -334,11 +349,14 @@ void alps_b200_finalize(void) {
     SpeciesHost& h = S.sp[s];
     dfree(&h.d_pperp); dfree(&h.d_ppar); dfree(&h.d_A); dfree(&h.d_C0); dfree(&h.d_Cp); dfree(&h.d_J);
     dfree(&h.d_W); dfree(&h.d_pf); dfree(&h.d_poly); dfree(&h.d_ee);
+    dfree(&h.d_grel); dfree(&h.d_pbrel); dfree(&h.d_f0rel); dfree(&h.d_dfg); dfree(&h.d_dfp);
+    dfree(&h.d_cone_lo); dfree(&h.d_cone_up);
     h = SpeciesHost();
   }
   free_batch();
   dfree(&S.d_pp_f); dfree(&S.d_df0_f); dfree(&S.gd); dfree(&S.d_work_count); dfree(&S.d_err); dfree(&S.d_ext);
   dfree(&S.d_tiles);
+  dfree(&S.d_rtiles);
   if (S.h_pin) cudaFreeHost(S.h_pin);
   S.h_pin = nullptr;
   S.h_pin_bytes = 0;
@@ -358,19 +376,20 @@ int alps_b200_set_species(int is, double ns, double qs, double ms, int relativis
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (is < 1 || is > S.cfg.nspec) return fail(ALPS_B200_ERR_USAGE, "species index %d out of range", is);
   if (n_fits > MAXFITS || n_fits > S.gh.maxfits) return fail(ALPS_B200_ERR_USAGE, "n_fits exceeds maxfits");
-  if (relativistic)
-    return fail(ALPS_B200_ERR_UNSUPPORTED, "relativistic species (ALPS_fns_rel) are not built yet");
   SpeciesDev& d = S.gh.sp[is - 1];
   d.ns = ns; d.qs = qs; d.ms = ms;
   d.relativistic = relativistic; d.usebM = usebM; d.ACmethod = ACmethod; d.n_fits = n_fits;
   for (int i = 0; i < n_fits; i++) {
     d.fit_type[i] = fit_type[i];
     d.perp_correction[i] = perp_correction[i];
-    if (ACmethod == 1 && (fit_type[i] == 4 || fit_type[i] == 5))
-      return fail(ALPS_B200_ERR_UNSUPPORTED, "fit types 4/5 need the relativistic grid (not built yet)");
+    if (ACmethod == 1 && (fit_type[i] == 4 || fit_type[i] == 5) && !relativistic)
+      return fail(ALPS_B200_ERR_USAGE, "fit types 4/5 are defined on the relativistic grid only");
+    if (relativistic && !(ACmethod == 1 && (fit_type[i] == 4 || fit_type[i] == 5)))
+      return fail(ALPS_B200_ERR_UNSUPPORTED, "relativistic species need ACmethod 1 with fit types 4/5");
   }
   d.logfit = logfit; d.poly_kind = poly_kind; d.poly_order = poly_order; d.poly_log_max = poly_log_max;
   S.sp[is - 1].set = true;
+  S.sp[is - 1].grid = !usebM;
   S.sp[is - 1].table = !usebM && !relativistic;
   return 0;
 }
@@ -388,7 +407,7 @@ int alps_b200_upload(const double* pp, const double* df0, const double* param_fi
     SpeciesDev& d = S.gh.sp[s];
     h.pperp.assign(nperp + 1, 0.0);
     h.ppar.assign(npar + 1, 0.0);
-    if (h.table) {
+    if (h.grid) {
       for (int i = 0; i <= nperp; i++) h.pperp[i] = pp[ipp(nspec, nperp, npar, s, i, 1, 0)];
       for (int j = 0; j <= npar; j++) h.ppar[j] = pp[ipp(nspec, nperp, npar, s, 2, j, 1)];
       for (int j = 0; j <= npar; j++)
@@ -410,9 +429,9 @@ int alps_b200_upload(const double* pp, const double* df0, const double* param_fi
     // param_fit(is,iperp,ip,ifit) -> [iperp][ifit][ip] for this species
     const int mf = S.gh.maxfits;
     const int nperpmax = std::max(nperp, S.cfg.ngamma);
-    std::vector<double> pf((size_t)(nperp + 1) * mf * 5, 0.0);
+    std::vector<double> pf((size_t)(nperpmax + 1) * mf * 5, 0.0);
     if (param_fit)
-      for (int i = 0; i <= nperp; i++)
+      for (int i = 0; i <= nperpmax; i++)
         for (int f = 0; f < mf; f++)
           for (int ip = 0; ip < 5; ip++)
             pf[((size_t)i * mf + f) * 5 + ip] = param_fit[s + (size_t)nspec * (i + (size_t)(nperpmax + 1) * (ip + 5 * f))];
@@ -427,7 +446,7 @@ int alps_b200_upload(const double* pp, const double* df0, const double* param_fi
     if (dalloc(&h.d_poly, po.size())) return ALPS_B200_ERR_CUDA;
     CK(cudaMemcpy(h.d_poly, po.data(), po.size() * sizeof(double), cudaMemcpyHostToDevice));
     d.poly = h.d_poly;
-    if (d.ACmethod == 1 && !param_fit && h.table) return fail(ALPS_B200_ERR_USAGE, "param_fit needed for species %d", s + 1);
+    if (d.ACmethod == 1 && !param_fit && h.grid) return fail(ALPS_B200_ERR_USAGE, "param_fit needed for species %d", s + 1);
     if (d.ACmethod == 2 && !poly_fit_coeffs && h.table) return fail(ALPS_B200_ERR_USAGE, "poly_fit_coeffs needed for species %d", s + 1);
   }
   const size_t npp = (size_t)nspec * (nperp + 1) * (npar + 1) * 2;
@@ -441,6 +460,71 @@ int alps_b200_upload(const double* pp, const double* df0, const double* param_fi
     CK(cudaMemcpy(S.d_df0_f, df0, nd * sizeof(double), cudaMemcpyHostToDevice));
     return build_tables_from_df0();
   }
+  return 0;
+}
+
+int alps_b200_upload_rel(int nspec_rel, const double* f0_rel, const double* df0_rel, const double* gamma_rel,
+                         const double* pparbar_rel) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (!f0_rel || !df0_rel || !gamma_rel || !pparbar_rel) return fail(ALPS_B200_ERR_USAGE, "NULL table");
+  const int ng = S.cfg.ngamma, npb = S.cfg.npparbar, nspec = S.cfg.nspec;
+  if (ng < 4 || npb < 8) return fail(ALPS_B200_ERR_USAGE, "ngamma / npparbar too small");
+  int cnt = 0;
+  for (int s = 0; s < nspec; s++) cnt += S.gh.sp[s].relativistic ? 1 : 0;
+  if (cnt != nspec_rel) return fail(ALPS_B200_ERR_USAGE, "nspec_rel=%d but %d species are relativistic", nspec_rel, cnt);
+  auto at = [&](int sr, int ig, int ip) { return sr + (size_t)nspec_rel * (ig + (size_t)(ng + 1) * ip); };
+  const size_t plane = (size_t)nspec_rel * (ng + 1) * (npb + 1);
+  int sr = -1;
+  for (int s = 0; s < nspec; s++) {
+    SpeciesHost& h = S.sp[s];
+    SpeciesDev& d = S.gh.sp[s];
+    if (!d.relativistic) continue;
+    sr++;
+    std::vector<double> g(ng + 1), p(npb + 1), f((size_t)(ng + 1) * (npb + 1)), dg(f.size()), dp(f.size());
+    std::vector<int> lo(ng + 1, 1), up(ng + 1, npb - 1);
+    for (int ig = 0; ig <= ng; ig++) g[ig] = gamma_rel[at(sr, ig, 1)];
+    for (int ip = 0; ip <= npb; ip++) p[ip] = pparbar_rel[at(sr, 2, ip)];
+    for (int ig = 0; ig <= ng; ig++)
+      for (int ip = 0; ip <= npb; ip++) {
+        if (gamma_rel[at(sr, ig, ip)] != g[ig] || pparbar_rel[at(sr, ig, ip)] != p[ip])
+          return fail(ALPS_B200_ERR_GRID, "relativistic grid of species %d is not separable", s + 1);
+        const size_t o = (size_t)ig * (npb + 1) + ip;
+        f[o] = f0_rel[at(sr, ig, ip)];
+        dg[o] = df0_rel[at(sr, ig, ip)];
+        dp[o] = df0_rel[plane + at(sr, ig, ip)];
+      }
+    // cone limits of integrate_resU_rel / int_ee_rel (src/ALPS_fns_rel.f90:582-596): index bookkeeping
+    for (int ig = 0; ig <= ng; ig++) {
+      bool fl = false, fu = false;
+      for (int ip = 1; ip <= npb - 1; ip++) {
+        const double* r = &f[(size_t)ig * (npb + 1)];
+        if (!fl && r[ip - 1] <= -1.0 && r[ip] > -1.0) { lo[ig] = ip; fl = true; }
+        if (!fu && r[ip] > -1.0 && r[ip + 1] <= -1.0) { up[ig] = ip; fu = true; }
+      }
+    }
+    if (dalloc(&h.d_grel, g.size()) || dalloc(&h.d_pbrel, p.size()) || dalloc(&h.d_f0rel, f.size()) ||
+        dalloc(&h.d_dfg, f.size()) || dalloc(&h.d_dfp, f.size()) || dalloc(&h.d_cone_lo, lo.size()) ||
+        dalloc(&h.d_cone_up, up.size()) || dalloc(&h.d_ee, 1))
+      return ALPS_B200_ERR_CUDA;
+    CK(cudaMemcpy(h.d_grel, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.d_pbrel, p.data(), p.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.d_f0rel, f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.d_dfg, dg.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.d_dfp, dp.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.d_cone_lo, lo.data(), lo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h.d_cone_up, up.data(), up.size() * sizeof(int), cudaMemcpyHostToDevice));
+    d.grel = h.d_grel; d.pbrel = h.d_pbrel; d.f0_rel = h.d_f0rel; d.dfg_rel = h.d_dfg; d.dfp_rel = h.d_dfp;
+    d.cone_lo = h.d_cone_lo; d.cone_up = h.d_cone_up;
+    d.dgamma = gamma_rel[at(sr, 2, 2)] - gamma_rel[at(sr, 1, 2)];
+    d.dpparbar = pparbar_rel[at(sr, 2, 2)] - pparbar_rel[at(sr, 2, 1)];
+    launch_int_ee_rel(h.d_pbrel, h.d_dfp, h.d_cone_lo, h.d_cone_up, ng, npb, d.qs, d.ms, S.cfg.vA, d.dgamma, d.dpparbar,
+                      h.d_ee, S.stream);
+    S.launches += 1;
+    CK(cudaMemcpyAsync(&h.ee_rel, h.d_ee, sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    h.have_rel = true;
+  }
+  S.have_k = false;
   return 0;
 }
 
@@ -488,7 +572,7 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
   std::vector<double> bm(CH);
   for (int s = 0; s < nspec; s++) {
     usebM[s] = S.gh.sp[s].usebM != 0;
-    if (!S.sp[s].table) {
+    if (!S.sp[s].grid) {
       nmax[s] = 1;
       continue;
     }
@@ -529,11 +613,12 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
   // ---- tables
   int item_base = 0;
   S.tiles.clear();
+  S.rtiles.clear();
   for (int s = 0; s < nspec; s++) {
     SpeciesHost& h = S.sp[s];
     SpeciesDev& d = S.gh.sp[s];
     d.nmax = nmax[s];
-    d.nhi = h.table ? nhi[s] : 0;
+    d.nhi = h.grid ? nhi[s] : 0;
     d.item_base = item_base;
     item_base += 2 * (d.nhi + 1);
     // harmonic shard of this process: contiguous blocks of [0,nhi]
@@ -543,7 +628,9 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
       d.nlo_shard = std::min(S.shard_rank * per, tot);
       d.nhi_shard = std::min(d.nlo_shard + per, tot) - 1;
     }
-    if (!h.table) continue;
+    if (!h.grid) continue;
+    if (d.relativistic && !h.have_rel)
+      return fail(ALPS_B200_ERR_USAGE, "species %d is relativistic: call alps_b200_upload_rel first", s + 1);
     if (kperp_changed) {
       const size_t nJ = (size_t)(d.nhi + 3) * d.ldj;
       if (nJ > h.cap_J) {
@@ -563,6 +650,11 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
       d.J = h.d_J;
       d.W = h.d_W;
     }
+    if (d.relativistic) {
+      d.int_ee = h.ee_rel;
+      for (int n = d.nlo_shard; n <= d.nhi_shard; n++) S.rtiles.push_back(RelTile{s, n});
+      continue;
+    }
     // C' = kpar * C0
     launch_scale(h.d_C0, h.d_Cp, kpar, (size_t)(nperp - 1) * d.ldp, S.stream);
     S.launches += 1;
@@ -575,7 +667,9 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
   const bool ni_changed = item_base != S.gh.NI;
   S.gh.NI = item_base;
   CK(cudaMemcpyAsync(S.gd, &S.gh, sizeof(GlobalDev), cudaMemcpyHostToDevice, S.stream));
-  if (dalloc(&S.d_tiles, S.tiles.size())) return ALPS_B200_ERR_CUDA;
+  if (dalloc(&S.d_tiles, S.tiles.size()) || dalloc(&S.d_rtiles, S.rtiles.size())) return ALPS_B200_ERR_CUDA;
+  if (!S.rtiles.empty())
+    CK(cudaMemcpyAsync(S.d_rtiles, S.rtiles.data(), S.rtiles.size() * sizeof(RelTile), cudaMemcpyHostToDevice, S.stream));
   if (!S.tiles.empty())
     CK(cudaMemcpyAsync(S.d_tiles, S.tiles.data(), S.tiles.size() * sizeof(QuadTile), cudaMemcpyHostToDevice, S.stream));
   CK(cudaStreamSynchronize(S.stream));
@@ -608,6 +702,11 @@ static int check_device_errors() {
   CK(cudaMemcpyAsync(herr, S.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream));
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());
+  if (herr[6]) {
+    cudaMemset(S.d_err, 0, 8 * sizeof(int));
+    return fail(8, "alps_error(8): the principal-value window covers the whole sub-luminal cone "
+                   "(src/ALPS_fns_rel.f90:655-656)");
+  }
   if (herr[0]) {
     cudaMemset(S.d_err, 0, 8 * sizeof(int));
     return fail(ALPS_B200_ERR_CUDA,
@@ -753,7 +852,7 @@ int alps_b200_get_info(int what, double* out) {
     case ALPS_B200_INFO_POINT_HARMONICS: {
       double t = 0.0;
       for (int s = 0; s < S.cfg.nspec; s++)
-        if (S.sp[s].table)
+        if (S.sp[s].grid)
           t += (2.0 * S.gh.sp[s].nhi + 1.0) * (S.cfg.nperp - 1.0) * (S.cfg.npar - 1.0);
       *out = t;
       return 0;

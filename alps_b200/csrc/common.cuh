@@ -76,8 +76,23 @@ struct SpeciesDev {
   const double* W;
   const double* param_fit;   // [iperp][5][maxfits] for this species (repacked)
   const double* poly;        // [iperp][maxorder+1]
-  double int_ee;             // omega-independent ee term, src/ALPS_fns.f90:1457-1555
+  double int_ee;             // omega-independent ee term, src/ALPS_fns.f90:1457-1555 (int_ee_rel if relativistic)
   double dpperp, dppar_abs, dppar_signed;
+  // relativistic species: (Gamma, pbar_par) tables of derivative_f0_rel, [igamma][ipparbar] row-major
+  const double* C0;          // (qs/ms)(p_perp d_par f0 - p_par d_perp f0), k independent
+  const double* grel;        // gamma_rel(igamma), 0..ngamma
+  const double* pbrel;       // pparbar_rel(ipparbar), 0..npparbar
+  const double* f0_rel;      // -1 outside the sub-luminal cone
+  const double* dfg_rel;     // d f0_rel / d Gamma
+  const double* dfp_rel;     // d f0_rel / d pbar_par
+  const int* cone_lo;        // ipparbar_lower(igamma), src/ALPS_fns_rel.f90:582-596
+  const int* cone_up;
+  double dgamma, dpparbar;
+};
+
+struct RelTile {
+  int s;      // species
+  int nabs;   // harmonic |n|
 };
 
 // ---- resonance plan of one (omega, species, |n|, sign), src/ALPS_fns.f90:641-745, 941-1006
@@ -92,9 +107,11 @@ constexpr int PLAN_ACTIVE = 1;   // harmonic belongs to this process' shard and 
 constexpr int PLAN_RES = 2;      // determine_resonances found a resonance
 constexpr int PLAN_NEAR = 4;     // near-pole quadrature (not an edge fallback)
 constexpr int PLAN_LANDAU = 8;   // Landau residue term needed (Im(om) <= 0)
+constexpr int PLAN_REL = 16;     // relativistic species: tensor components come from k_rel
 
 struct GlobalDev {
   int nspec, nperp, npar;
+  int ngamma, npparbar;
   int NI;                    // items per omega
   int WIN;                   // nodes per resonance window = 2*M_I + 7
   int WINX;                  // gwin slots per item = WIN + 3: nodes 1..3 follow the window because

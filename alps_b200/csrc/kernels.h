@@ -62,6 +62,10 @@ void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* o
 void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
                      const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
                      cudaStream_t st);
+void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
+                int* err_flag, cudaStream_t st);
+void launch_int_ee_rel(const double* pbv, const double* dfp, const int* lo, const int* up, int ng, int npb, double qs,
+                       double ms, double vA, double dgam, double dpb, double* out, cudaStream_t st);
 double run_dfma_peak(cudaStream_t st);
 
 }  // namespace alps

@@ -124,7 +124,12 @@ __global__ void k_plan(const GlobalDev* __restrict__ gp, const double* __restric
   const SpeciesDev& sp = g.sp[s];
   PlanEntry pe;
   pe.lo1 = 1; pe.hi1 = 0; pe.lo2 = 1; pe.hi2 = 0; pe.flags = 0; pe.ipar_res = 0; pe.upperlimit = 0; pe.pad = 0;
-  if ((nabs == 0 && sg == 1) || nabs < sp.nlo_shard || nabs > sp.nhi_shard || sp.usebM || sp.relativistic) {
+  if ((nabs == 0 && sg == 1) || nabs < sp.nlo_shard || nabs > sp.nhi_shard || sp.usebM) {
+    plan[idx] = pe;
+    return;
+  }
+  if (sp.relativistic) {   // resonance handling of relativistic species lives in k_rel
+    pe.flags = PLAN_ACTIVE | PLAN_REL;
     plan[idx] = pe;
     return;
   }
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict
     chi[c] = mk(0.0, 0.0);
     low[c][0] = low[c][1] = low[c][2] = mk(0.0, 0.0);
   }
-  const bool table = !(sp.usebM || sp.relativistic);
+  const bool table = !sp.usebM;
   if (table) {
     const double z = g.kperp_norm ? g.kperp / sp.qs : 1.0 / sp.qs;
     const double kf1 = g.kperp_norm ? 1.0 : g.kperp, kf2 = g.kperp_norm ? 1.0 : g.kperp * g.kperp;
@@ -463,22 +468,29 @@ __global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict
       if (!(pe.flags & PLAN_ACTIVE)) continue;
       const int nabs = r >> 1, sg = r & 1;
       const double nn = sg ? -(double)nabs : (double)nabs;
-      cd S[6];
-      const double* sb = Sbulk + idx * 12;
-#pragma unroll
-      for (int q = 0; q < 6; q++) S[q] = mk(cbulk * sb[2 * q], cbulk * sb[2 * q + 1]);
-      if (pe.flags & (PLAN_NEAR | PLAN_LANDAU)) {
+      cd mode[6];
+      if (pe.flags & PLAN_REL) {
+        // relativistic species: k_rel already produced the six tensor components
         const double* sr = Sres + idx * 12;
 #pragma unroll
-        for (int q = 0; q < 6; q++) S[q] += mk(sr[2 * q], sr[2 * q + 1]);
+        for (int q = 0; q < 6; q++) mode[q] = mk(sr[2 * q], sr[2 * q + 1]);
+      } else {
+        cd S[6];
+        const double* sb = Sbulk + idx * 12;
+#pragma unroll
+        for (int q = 0; q < 6; q++) S[q] = mk(cbulk * sb[2 * q], cbulk * sb[2 * q + 1]);
+        if (pe.flags & (PLAN_NEAR | PLAN_LANDAU)) {
+          const double* sr = Sres + idx * 12;
+#pragma unroll
+          for (int q = 0; q < 6; q++) S[q] += mk(sr[2 * q], sr[2 * q + 1]);
+        }
+        mode[0] = ((nn * nn) / (z * z)) * S[0];          // xx: n^2 J^2 / z^2
+        mode[1] = kf2 * S[5];                            // yy: p_perp^2 J'^2
+        mode[2] = kf2 * S[2];                            // zz: J^2 p_par^2
+        mode[3] = cmul_i((kf1 * nn / z) * S[3]);         // xy: i p_perp n J J' / z
+        mode[4] = (kf1 * nn / z) * S[1];                 // xz: n J^2 p_par / z
+        mode[5] = -cmul_i(kf2 * S[4]);                   // yz: -i J J' p_par p_perp
       }
-      cd mode[6];
-      mode[0] = ((nn * nn) / (z * z)) * S[0];          // xx: n^2 J^2 / z^2
-      mode[1] = kf2 * S[5];                            // yy: p_perp^2 J'^2
-      mode[2] = kf2 * S[2];                            // zz: J^2 p_par^2
-      mode[3] = cmul_i((kf1 * nn / z) * S[3]);         // xy: i p_perp n J J' / z
-      mode[4] = (kf1 * nn / z) * S[1];                 // xz: n J^2 p_par / z
-      mode[5] = -cmul_i(kf2 * S[4]);                   // yz: -i J J' p_par p_perp
       if (nabs == 0) {
         // n = 0: only yy, zz, yz are evaluated (src/ALPS_fns.f90:368-393)
         chi[1] += mode[1]; chi[2] += mode[2]; chi[5] += mode[5];
@@ -503,7 +515,7 @@ __global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict
     if (table && sp.nlo_shard == 0) {
       const double ee = g.kperp_norm ? sp.int_ee : g.kperp * g.kperp * sp.int_ee;
       chi[2].x += ee;
-      low[2][1].x += ee;
+      if (!sp.relativistic) low[2][1].x += ee;   // int_ee_rel goes into chi only (src/ALPS_fns.f90:481-486)
     }
     const double norm = sp.ns * sp.qs;
     double* o = partial + (size_t)w * PARTIAL_PER_SPEC;

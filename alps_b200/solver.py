@@ -49,6 +49,10 @@ class Solver:
         df0 = _f(plasma.df0)
         _lib.check(self.L.alps_b200_upload(_p(pp), _p(df0), _p(_f(plasma.param_fit)),
                                            _p(_f(plasma.poly_fit_coeffs))))
+        if plasma.f0_rel is not None:
+            _lib.check(self.L.alps_b200_upload_rel(plasma.f0_rel.shape[0], _p(_f(plasma.f0_rel)),
+                                                   _p(_f(plasma.df0_rel)), _p(_f(plasma.gamma_rel)),
+                                                   _p(_f(plasma.pparbar_rel))))
         self._df0 = None
         if df0 is None:
             self._df0 = self.derivative_f0(plasma.f0)

@@ -60,6 +60,11 @@ class Plasma:
     param_fit: np.ndarray     # (nspec, max(nperp,ngamma)+1, 5, maxfits) Fortran order
     df0: Optional[np.ndarray] = None  # (nspec, nperp-1, npar-1, 2) Fortran order
     poly_fit_coeffs: Optional[np.ndarray] = None
+    # relativistic species only (src/ALPS_fns.f90:230-233): (nspec_rel, ngamma+1, npparbar+1[, 2])
+    f0_rel: Optional[np.ndarray] = None
+    df0_rel: Optional[np.ndarray] = None
+    gamma_rel: Optional[np.ndarray] = None
+    pparbar_rel: Optional[np.ndarray] = None
     ngamma: int = 0
     npparbar: int = 0
     Bessel_zero: float = 1.0e-50
@@ -209,3 +214,31 @@ def config_small(nperp: int = 24, npar: int = 48, kind: int = 1) -> Plasma:
     specs = [DistSpec(ms=1.0, distribution=kind, alph=1.3), DistSpec(ms=5.44662e-4, distribution=kind)]
     return make_plasma(specs, ns=[1.0, 1.0], qs=[1.0, -1.0], nperp=nperp, npar=npar,
                        Bessel_zero=1.0e-30)
+
+
+def config_relativistic(nperp: int = 30, npar: int = 60, ngamma: int = 500, npparbar: int = 500) -> Plasma:
+    """C3: tests/test_relativistic.in + distribution/test_relativistic_dist.in (Juettner pair plasma,
+    vA = 1, both species relativistic, fit type 4).  The (Gamma, pbar_par) tables come from the host-side
+    restatement of derivative_f0_rel (alps_b200/relativistic.py)."""
+    from .relativistic import derivative_f0_rel
+    vA = 1.0
+    specs = [DistSpec(ms=1.0, distribution=3), DistSpec(ms=1.0, distribution=3)]
+    pp, f0, fits = generate_distribution(specs, nperp, npar, beta=1.0, vA=vA, maxP=5.0)
+    nrel = 2
+    shape = (nrel, ngamma + 1, npparbar + 1)
+    f0_rel, gam, pb = (np.zeros(shape, order="F") for _ in range(3))
+    df0_rel = np.zeros(shape + (2,), order="F")
+    pf = np.zeros((2, max(nperp, ngamma) + 1, 5, 1), order="F")
+    species = []
+    cache = None
+    for i in range(2):
+        if cache is None:     # both species have the same f0 table: one thin-plate-spline solve
+            cache = derivative_f0_rel(pp[i], f0[i], specs[i].ms, vA, ngamma, npparbar)
+        g, p, f, d, integ = cache
+        gam[i], pb[i], f0_rel[i], df0_rel[i] = g, p, f, d
+        pf[i, :, 0, 0] = fits[i]["params"][0] / integ          # amplitude of the renormalised table
+        species.append(Species(ns=1.0, qs=1.0 if i == 0 else -1.0, ms=specs[i].ms, relativistic=True,
+                               ACmethod=1, fit_type=[4], perp_correction=[fits[i]["perpcorr"]]))
+    return Plasma(nperp=nperp, npar=npar, vA=vA, species=species, pp=pp, f0=f0, param_fit=pf,
+                  f0_rel=f0_rel, df0_rel=df0_rel, gamma_rel=gam, pparbar_rel=pb, ngamma=ngamma,
+                  npparbar=npparbar, Bessel_zero=1.0e-45, positions_principal=5)

@@ -75,6 +75,12 @@ int alps_b200_set_species(int is, double ns, double qs, double ms, int relativis
 int alps_b200_upload(const double *pp, const double *df0, const double *param_fit,
                      const double *poly_fit_coeffs);
 
+/* replaces: the relativistic part of pass_distribution (src/ALPS_com.f90:252-278): the tables of
+ * derivative_f0_rel, f0_rel / gamma_rel / pparbar_rel (nspec_rel,0:ngamma,0:npparbar) and
+ * df0_rel(nspec_rel,0:ngamma,0:npparbar,2), Fortran layout.  Call after alps_b200_set_species. */
+int alps_b200_upload_rel(int nspec_rel, const double *f0_rel, const double *df0_rel,
+                         const double *gamma_rel, const double *pparbar_rel);
+
 /* replaces: derivative_f0 (src/ALPS_fns.f90:96-118) -- centred differences on the device from
  * f0(nspec,0:nperp,0:npar); optional df0_out (host, Fortran layout of df0) receives the result. */
 int alps_b200_derivative_f0(const double *f0, double *df0_out);

@@ -32,6 +32,8 @@ static struct {
   int nperpmax;             /* max(nperp,ngamma) : param_fit extent, src/ALPS_io.f90:181 */
   double kperp, kpar;
   double *pp, *df0, *param_fit, *poly_fit_coeffs;
+  double *f0_rel, *df0_rel, *gamma_rel, *pparbar_rel; /* (nspec_rel,0:ngamma,0:npparbar[,2]) */
+  int nspec_rel;
   double *ns, *qs, *ms;
   int *relativistic, *usebM, *ACmethod, *n_fits, *fit_type, *logfit, *poly_kind, *poly_order;
   double *perp_correction, *poly_log_max;
@@ -54,6 +56,14 @@ static const double pi = 3.14159265358979323846; /* 4*atan(1), src/ALPS_var.f90 
   S.param_fit[((is)-1) + (size_t)S.c.nspec * ((iperp) + (size_t)(S.nperpmax + 1) * (((ip)-1) + 5 * ((ifit)-1)))]
 #define POLY(is, iperp, k) \
   S.poly_fit_coeffs[((is)-1) + (size_t)S.c.nspec * ((iperp) + (size_t)(S.c.nperp + 1) * (k))]
+#define F0REL(isr, ig, ip) \
+  S.f0_rel[((isr)-1) + (size_t)S.nspec_rel * ((ig) + (size_t)(S.c.ngamma + 1) * (ip))]
+#define GAMREL(isr, ig, ip) \
+  S.gamma_rel[((isr)-1) + (size_t)S.nspec_rel * ((ig) + (size_t)(S.c.ngamma + 1) * (ip))]
+#define PBREL(isr, ig, ip) \
+  S.pparbar_rel[((isr)-1) + (size_t)S.nspec_rel * ((ig) + (size_t)(S.c.ngamma + 1) * (ip))]
+#define DF0REL(isr, ig, ip, comp_) \
+  S.df0_rel[((isr)-1) + (size_t)S.nspec_rel * ((ig) + (size_t)(S.c.ngamma + 1) * ((ip) + (size_t)(S.c.npparbar + 1) * ((comp_)-1)))]
 #define FIT_TYPE(is, ifit) S.fit_type[((is)-1) + S.c.nspec * ((ifit)-1)]
 #define PERP_CORR(is, ifit) S.perp_correction[((is)-1) + S.c.nspec * ((ifit)-1)]
 #define BESSEL(W, n, iperp) \
@@ -214,6 +224,17 @@ static cplx fit_function_poly(int is, int iperp, cplx ppar_val) {
   return r;
 }
 
+/* determine_sproc_rel, src/ALPS_fns_rel.f90:431-455 */
+static int sproc_rel_of(int sproc) {
+  int is, is_rel = 0, r = 0;
+  for (is = 1; is <= S.c.nspec; is++)
+    if (S.relativistic[is - 1]) {
+      is_rel++;
+      if (is == sproc) r = is_rel;
+    }
+  return r;
+}
+
 /* src/ALPS_analyt.f90:32-258 : eval_fit + fit_function.  The params(:) packing of the
  * reference is a copy of param_fit(is,iperp,1:k,ifit) in order, so it is read directly. */
 static cplx eval_fit(int is, int iperp, cplx ppar_val) {
@@ -226,7 +247,7 @@ static cplx eval_fit(int is, int iperp, cplx ppar_val) {
     case 1: break;
     default: return 0.0;
   }
-  pperp_val = PP(is, iperp, 1, 1);
+  pperp_val = (iperp <= S.c.nperp) ? PP(is, iperp, 1, 1) : 0.0; /* unused by fit types 4,5 */
   for (ifit = 1; ifit <= S.n_fits[is - 1]; ifit++) {
     double p1 = PARAM_FIT(is, iperp, 1, ifit), p2 = PARAM_FIT(is, iperp, 2, ifit),
            p3 = PARAM_FIT(is, iperp, 3, ifit), p4 = PARAM_FIT(is, iperp, 4, ifit),
@@ -252,8 +273,13 @@ static cplx eval_fit(int is, int iperp, cplx ppar_val) {
         f += p1 * cexp(0.5 * (p4 * pc * pperp_val * pperp_val + p2 * (d * d) -
                               cexp(p4 * pc * pperp_val * pperp_val + p2 * (d * d))));
         break;
-      default: /* 4,5 need gamma_rel: relativistic species are not restated yet */
+      case 4: /* Juettner in gamma only (pperp_val = gamma_rel(sproc_rel,iperp,1)) */
+        f += p1 * exp(-pc * GAMREL(sproc_rel_of(is), iperp, 1));
         break;
+      case 5: /* Juettner in gamma and pparbar */
+        f += p1 * exp(-pc * GAMREL(sproc_rel_of(is), iperp, 1)) * cexp(-p2 * (d * d));
+        break;
+      default: break;
     }
   }
   return f;
@@ -304,11 +330,14 @@ static cplx int_T_res(const struct worker *W, int nn, int iperp, cplx p_res, int
   return int_T_core(W, nn, iperp, mode, PP(W->sproc, iperp, 1, 1), p_res);
 }
 
-/* src/ALPS_fns.f90:1560-1596 (non-relativistic: gamma = 1) */
+/* src/ALPS_fns.f90:1560-1596 */
 static cplx resU(const struct worker *W, cplx om, int nn, int iperp, int ipar) {
   int sp = W->sproc;
   double gamma = 1.0;
   double qs = S.qs[sp - 1], ms = S.ms[sp - 1], kpar = S.kpar;
+  if (S.relativistic[sp - 1])
+    gamma = sqrt((PP(sp, iperp, ipar, 1) * PP(sp, iperp, ipar, 1) + PP(sp, iperp, ipar, 2) * PP(sp, iperp, ipar, 2)) *
+                     (S.c.vA * S.c.vA) / (ms * ms) + 1.0);
   return qs *
          (om * DF0(sp, iperp, ipar, 1) +
           (kpar / (gamma * ms)) *
@@ -573,6 +602,336 @@ static double int_ee_sp(int sp) {
 }
 double oracle_int_ee(int is) { return int_ee_sp(is); }
 
+
+/* ===================================================================== relativistic path */
+/* Gamma (Lanczos), Fact, CBESSJ: src/ALPS_fns_rel.f90:1738-1791, 1560-1574, 1502-1555 */
+static double Gamma_ref(double xx) {
+  static const double cof[6] = {76.18009173, -86.50532033, 24.01409822, -1.231739516, 0.120858003e-2, -0.536382e-5};
+  const double stp = 2.50662827465;
+  double x = xx - 1.0, tmp = x + 5.5, ser = 1.0;
+  int j;
+  tmp = (x + 0.5) * log(tmp) - tmp;
+  for (j = 0; j < 6; j++) {
+    x = x + 1.0;
+    ser = ser + cof[j] / x;
+  }
+  return exp(tmp + log(stp * ser));
+}
+static double Fact_ref(int k) {
+  double f = 1.0;
+  int i;
+  for (i = 2; i <= k; i++) f = f * (1.0 * i);
+  return f;
+}
+static cplx cpowi(cplx z, int k) { /* complex ** integer by repeated multiplication (libgfortran pow_c8_i4) */
+  cplx r = 1.0, b = z;
+  unsigned n = (unsigned)(k < 0 ? -k : k);
+  while (n) {
+    if (n & 1u) r *= b;
+    n >>= 1;
+    if (n) b *= b;
+  }
+  return k < 0 ? 1.0 / r : r;
+}
+static cplx CBESSJ(cplx z, int nu) {
+  int k;
+  cplx sum = 0.0, tmp;
+  for (k = 0; k <= 20; k++) {
+    tmp = cpowi(-z * z / 4.0, k);
+    tmp = tmp / Fact_ref(k);
+    tmp = tmp / Gamma_ref(1.0 * (nu + k + 1));
+    sum = sum + tmp;
+  }
+  tmp = cpowi(z / 2.0, nu);
+  return tmp * sum;
+}
+
+/* int_T_rel, src/ALPS_fns_rel.f90:1256-1369 */
+static cplx int_T_rel(int sp, int sr, int nn, int igamma, int ipparbar, int mode) {
+  double ms = S.ms[sp - 1], qs = S.qs[sp - 1], vA = S.c.vA, kperp = S.kperp;
+  int kn = S.c.kperp_norm;
+  double pb = PBREL(sr, igamma, ipparbar), g = GAMREL(sr, igamma, ipparbar);
+  double pperpbar = sqrt(g * g - 1.0 - pb * pb);
+  double z = (kperp * ms / (vA * qs)) * pperpbar;
+  double zbar = kn ? kperp * ms / (vA * qs) : ms / (vA * qs);
+  double bessel, besselP = 0.0;
+  if (nn < 0) bessel = ((-nn) % 2 ? -1.0 : 1.0) * BESSJ(-nn, z);
+  else bessel = BESSJ(nn, z);
+  if (nn >= 1) besselP = 0.5 * (BESSJ(nn - 1, z) - BESSJ(nn + 1, z));
+  else if (nn < -1)
+    besselP = 0.5 * ((((-(nn - 1)) % 2 ? -1.0 : 1.0) * BESSJ(-(nn - 1), z)) - (((-(nn + 1)) % 2 ? -1.0 : 1.0) * BESSJ(-(nn + 1), z)));
+  else if (nn == 0) besselP = -BESSJ(1, z);
+  else if (nn == -1) besselP = 0.5 * (BESSJ(2, z) - BESSJ(0, z));
+  switch (mode) {
+    case 1: return 1.0 * (nn * nn) * bessel * bessel / (zbar * zbar);
+    case 2: return (kn ? 1.0 : kperp * kperp) * besselP * besselP * pperpbar * pperpbar;
+    case 3: return (kn ? 1.0 : kperp * kperp) * bessel * bessel * (pb * pb);
+    case 4: return I * (1.0 * nn) * (kn ? 1.0 : kperp) * bessel * besselP * pperpbar / zbar;
+    case 5: return (1.0 * nn) * (kn ? 1.0 : kperp) * bessel * bessel * pb / zbar;
+    case 6: return (-1.0 * I) * (kn ? 1.0 : kperp * kperp) * bessel * besselP * pb * pperpbar;
+  }
+  return 0.0;
+}
+
+/* int_T_res_rel, src/ALPS_fns_rel.f90:1374-1495 */
+static cplx int_T_res_rel(int sp, int sr, int nn, int igamma, cplx pparbar, int mode) {
+  double ms = S.ms[sp - 1], qs = S.qs[sp - 1], vA = S.c.vA, kperp = S.kperp;
+  int kn = S.c.kperp_norm;
+  double g = GAMREL(sr, igamma, 1);
+  cplx pperpbar = csqrt(g * g - 1.0 - pparbar * pparbar);
+  cplx z = (kperp * ms / (vA * qs)) * pperpbar, bessel, besselP = 0.0, besselH;
+  double zbar = kn ? kperp * ms / (vA * qs) : ms / (vA * qs);
+  if (nn < 0) bessel = CBESSJ(z, -nn) * ((-nn) % 2 ? -1.0 : 1.0);
+  else bessel = CBESSJ(z, nn);
+  if (nn >= 1) {
+    besselP = CBESSJ(z, nn - 1);
+    besselH = CBESSJ(z, nn + 1);
+    besselP = 0.5 * (besselP - besselH);
+  } else if (nn < -1) {
+    besselP = CBESSJ(z, -(nn - 1));
+    besselH = CBESSJ(z, -(nn + 1));
+    besselP = 0.5 * ((((-(nn - 1)) % 2 ? -1.0 : 1.0) * besselP) - (((-(nn + 1)) % 2 ? -1.0 : 1.0) * besselH));
+  } else if (nn == 0) {
+    besselP = -CBESSJ(z, 1);
+  } else if (nn == -1) {
+    besselP = CBESSJ(z, 2);
+    besselH = CBESSJ(z, 0);
+    besselP = 0.5 * (besselP - besselH);
+  }
+  switch (mode) {
+    case 1: return 1.0 * (nn * nn) * bessel * bessel / (zbar * zbar);
+    case 2: return (kn ? 1.0 : kperp * kperp) * besselP * besselP * pperpbar * pperpbar;
+    case 3: return (kn ? 1.0 : kperp * kperp) * bessel * bessel * (pparbar * pparbar);
+    case 4: return I * (1.0 * nn) * (kn ? 1.0 : kperp) * bessel * besselP * pperpbar / zbar;
+    case 5: return (1.0 * nn) * (kn ? 1.0 : kperp) * bessel * bessel * pparbar / zbar;
+    case 6: return (-1.0 * I) * (kn ? 1.0 : kperp * kperp) * bessel * besselP * pparbar * pperpbar;
+  }
+  return 0.0;
+}
+
+/* resU_rel, src/ALPS_fns_rel.f90:1220-1249 */
+static cplx resU_rel(int sp, int sr, cplx om, int nn, int igamma, int ipparbar) {
+  double ms = S.ms[sp - 1], qs = S.qs[sp - 1], vA = S.c.vA, kpar = S.kpar;
+  double m3 = (ms / vA) * (ms / vA) * (ms / vA);
+  return -2.0 * pi * m3 * (qs * vA / (kpar * ms)) *
+         (om * DF0REL(sr, igamma, ipparbar, 1) + (kpar / vA) * DF0REL(sr, igamma, ipparbar, 2)) /
+         (PBREL(sr, igamma, ipparbar) - GAMREL(sr, igamma, ipparbar) * om * vA / kpar + (1.0 * nn) * qs * vA / (kpar * ms));
+}
+
+/* funct_g_rel, src/ALPS_fns_rel.f90:918-999 */
+static cplx funct_g_rel(int sp, int sr, double pparbar, int igamma, cplx om, int nn, int mode) {
+  int npb = S.c.npparbar, ip, ic = -2;
+  double ms = S.ms[sp - 1], qs = S.qs[sp - 1], vA = S.c.vA, kpar = S.kpar;
+  double dpparbar = PBREL(sr, 2, 2) - PBREL(sr, 2, 1);
+  double m3 = (ms / vA) * (ms / vA) * (ms / vA);
+  cplx gp, g0, gm;
+  for (ip = 0; ip <= npb - 1; ip++)
+    if (PBREL(sr, igamma, ip + 1) > pparbar && PBREL(sr, igamma, ip) <= pparbar) ic = ip;
+  /* the reference indexes f0_rel(ic+1), f0_rel(ic-1) even for ic = -2 (out of bounds there);
+   * guarded here: an index outside [0,npparbar] counts as "not outside the cone" */
+  if (ic + 1 >= 0 && ic + 1 <= npb && F0REL(sr, igamma, ic + 1) <= -1.0) ic = ic - 1;
+  if (ic - 1 >= 0 && ic - 1 <= npb && F0REL(sr, igamma, ic - 1) <= -1.0) ic = ic + 1;
+  if (pparbar == PBREL(sr, igamma, npb)) ic = npb - 2;
+  if (ic >= npb - 1) ic = npb - 2;
+  if (ic <= 1) ic = 2;
+#define GN(ip_)                                                                                         \
+  (-2.0 * pi * m3 * (qs * vA / (kpar * ms)) *                                                           \
+   (om * DF0REL(sr, igamma, ip_, 1) + (kpar / vA) * DF0REL(sr, igamma, ip_, 2)) * int_T_rel(sp, sr, nn, igamma, ip_, mode))
+  gp = GN(ic + 1);
+  g0 = GN(ic);
+  gm = GN(ic - 1);
+#undef GN
+  return g0 + 0.5 * ((gp - gm) / dpparbar) * (pparbar - PBREL(sr, igamma, ic));
+}
+
+/* principal_integral_rel, src/ALPS_fns_rel.f90:724-913 */
+static cplx principal_integral_rel(int sp, int sr, cplx om, int nn, int mode, int igamma, int ipparbar_res, int upperlimit) {
+  int M_I = S.c.positions_principal, M_P = S.c.n_resonance_interval, ip, ntiny;
+  double ms = S.ms[sp - 1], qs = S.qs[sp - 1], vA = S.c.vA, kpar = S.kpar, Tlim = S.c.Tlim;
+  double dpparbar = PBREL(sr, 2, 2) - PBREL(sr, 2, 1), denomR, denomI, capDelta, smdelta, correction, pb;
+  cplx ii = I, r = 0.0, pres, gprimetr;
+  denomR = creal(GAMREL(sr, igamma, ipparbar_res) * om * vA / kpar - (1.0 * nn) * (qs / ms) * vA / kpar);
+  denomI = cimag(GAMREL(sr, igamma, ipparbar_res) * om * vA / kpar);
+  pres = denomR + denomI * ii;
+  capDelta = creal(pres) - PBREL(sr, 1, ipparbar_res - M_I);
+  smdelta = capDelta / (1.0 * M_P);
+#define G(p) funct_g_rel(sp, sr, (p), igamma, om, nn, mode)
+  if (fabs(denomI) > Tlim) {
+    pb = creal(pres);
+    r = r + 1.0 * G(pb) / (pb - denomR - ii * denomI);
+    r = r - 1.0 * G(2.0 * denomR - pb) / (pb - denomR + ii * denomI);
+    pb = creal(pres) + capDelta;
+    r = r + 1.0 * G(pb) / (pb - denomR - ii * denomI);
+    r = r - 1.0 * G(2.0 * denomR - pb) / (pb - denomR + ii * denomI);
+    for (ip = 1; ip <= M_P - 1; ip++) {
+      pb = creal(pres) + smdelta * ip;
+      r = r + 2.0 * G(pb) / (pb - denomR - ii * denomI);
+      r = r - 2.0 * G(2.0 * denomR - pb) / (pb - denomR + ii * denomI);
+    }
+  } else {
+    gprimetr = (G(denomR + dpparbar) - G(denomR - dpparbar)) / (2.0 * dpparbar);
+    pb = creal(pres) + capDelta;
+    r = r + 2.0 * gprimetr * ((pb - denomR) * (pb - denomR)) / ((pb - denomR) * (pb - denomR) + denomI * denomI);
+    for (ip = 1; ip <= M_P - 1; ip++) {
+      pb = creal(pres) + smdelta * ip;
+      r = r + 2.0 * 2.0 * gprimetr * ((pb - denomR) * (pb - denomR)) / ((pb - denomR) * (pb - denomR) + denomI * denomI);
+    }
+    if (denomI > 0.0) r = r + 2.0 * ii * pi * G(denomR) / smdelta;
+    else if (denomI < 0.0) r = r - 2.0 * ii * pi * G(denomR) / smdelta;
+  }
+  ntiny = (int)((PBREL(sr, igamma, upperlimit) - creal(pres) - capDelta) / smdelta);
+  if (ntiny > 0) {
+    correction = ((PBREL(sr, igamma, upperlimit) - creal(pres) - capDelta) / (1.0 * ntiny)) / smdelta;
+    pb = creal(pres) + capDelta;
+    r = r + 1.0 * correction * (G(pb) / (pb - denomR - ii * denomI));
+    pb = creal(pres) + capDelta + correction * smdelta * ntiny;
+    r = r + 1.0 * correction * (G(pb) / (pb - denomR - ii * denomI));
+    for (ip = 1; ip <= ntiny - 1; ip++) {
+      pb = creal(pres) + capDelta + correction * smdelta * ip;
+      r = r + 2.0 * correction * (G(pb) / (pb - denomR - ii * denomI));
+    }
+  }
+#undef G
+  return r * smdelta;
+}
+
+/* cone limits used by integrate_resU_rel (lines 582-596) and int_ee_rel */
+static void cone_limits(int sr, int igamma, int *lower, int *upper) {
+  int npb = S.c.npparbar, ip, fl = 0, fu = 0;
+  *lower = 1;
+  *upper = npb - 1;
+  for (ip = 1; ip <= npb - 1; ip++) {
+    if (!fl && F0REL(sr, igamma, ip - 1) <= -1.0 && F0REL(sr, igamma, ip) > -1.0) {
+      *lower = ip;
+      fl = 1;
+    }
+    if (!fu && F0REL(sr, igamma, ip) > -1.0 && F0REL(sr, igamma, ip + 1) <= -1.0) {
+      *upper = ip;
+      fu = 1;
+    }
+  }
+}
+
+/* integrate_resU_rel, src/ALPS_fns_rel.f90:516-719; *err = 8 mirrors alps_error(8) */
+static cplx integrate_resU_rel(int sp, int sr, cplx om, int nn, int mode, int igamma, int *err) {
+  int npb = S.c.npparbar, M_I = S.c.positions_principal;
+  int ip = 0, ires = 0, found_res = 0, int_start, int_end, lowerlimit, upperlimit, lo, up;
+  double ms = S.ms[sp - 1], qs = S.qs[sp - 1], vA = S.c.vA, kpar = S.kpar;
+  double dpparbar = PBREL(sr, 2, 2) - PBREL(sr, 2, 1), g1 = GAMREL(sr, igamma, 1);
+  cplx r = 0.0, pres;
+  pres = (g1 * om - (1.0 * nn) * qs / ms) * vA / kpar;
+  if (creal(pres) * creal(pres) <= g1 * g1 - 1.0) {
+    while (ip < npb - 2 && !found_res) {
+      ip = ip + 1;
+      if (PBREL(sr, 2, ip + 1) > creal(pres) && PBREL(sr, 2, ip) <= creal(pres)) {
+        ires = ip;
+        found_res = 1;
+      }
+    }
+  }
+  for (ip = 0; ip <= M_I; ip++) {
+    if (creal(pres) >= PBREL(sr, 2, 0) - dpparbar * ip && creal(pres) < PBREL(sr, 2, 0) - dpparbar * (ip - 1)) {
+      ires = -ip;
+      found_res = 1;
+    }
+    if (creal(pres) >= PBREL(sr, 2, npb - 1) + dpparbar * ip && creal(pres) < PBREL(sr, 2, npb - 1) + dpparbar * (ip + 1)) {
+      ires = npb - 1 + ip;
+      found_res = 1;
+    }
+  }
+  cone_limits(sr, igamma, &lo, &up);
+  if (found_res) {
+    int_start = lo;
+    int_end = up;
+    lowerlimit = ires - M_I;
+    upperlimit = ires + M_I + 1;
+    if (ires >= 0 && ires <= npb)
+      if (fabs(creal(pres) - PBREL(sr, 2, ires)) > 0.5 * dpparbar) upperlimit = upperlimit + 1;
+    if (lowerlimit < lo && upperlimit > up) {
+      *err = 8;
+      return 0.0;
+    } else if (lowerlimit <= lo) {
+      int_start = 1;
+      lowerlimit = 0;
+      upperlimit = lo;
+    } else if (upperlimit >= up) {
+      lowerlimit = up;
+      upperlimit = npb;
+      int_end = npb - 1;
+    }
+  } else {
+    int_start = lo;
+    lowerlimit = up;
+    int_end = npb - 1;
+    upperlimit = npb;
+  }
+#define UT(ip_) (resU_rel(sp, sr, om, nn, igamma, ip_) * int_T_rel(sp, sr, nn, igamma, ip_, mode))
+  if (int_start <= lowerlimit) r = r + UT(int_start);
+  for (ip = int_start + 1; ip <= lowerlimit - 1; ip++) r = r + 2.0 * UT(ip);
+  if (int_start < lowerlimit) r = r + UT(lowerlimit);
+  if (upperlimit <= int_end) r = r + UT(upperlimit);
+  for (ip = upperlimit + 1; ip <= int_end - 1; ip++) r = r + 2.0 * UT(ip);
+  if (upperlimit < int_end) r = r + UT(int_end);
+#undef UT
+  r = r * dpparbar;
+  if (found_res && lowerlimit >= int_start && upperlimit <= int_end)
+    r = r + principal_integral_rel(sp, sr, om, nn, mode, igamma, ires, upperlimit);
+  return r;
+}
+
+/* integrate_res_rel, src/ALPS_fns_rel.f90:460-511 */
+static cplx integrate_res_rel(const struct worker *W, cplx om, int nn, int mode, int *err) {
+  int sp = W->sproc, sr = sproc_rel_of(sp), ng = S.c.ngamma, ig;
+  double dgamma_rel = GAMREL(sr, 2, 2) - GAMREL(sr, 1, 2);
+  cplx r = 0.0;
+  for (ig = 1; ig <= ng - 2; ig++) r = r + 2.0 * integrate_resU_rel(sp, sr, om, nn, mode, ig, err);
+  r = r + integrate_resU_rel(sp, sr, om, nn, mode, ng - 1, err);
+  return r * dgamma_rel * 0.25;
+}
+
+/* landau_integrate_rel, src/ALPS_fns_rel.f90:1005-1092 */
+static cplx landau_integrate_rel(const struct worker *W, cplx om, int nn, int mode) {
+  int sp = W->sproc, sr = sproc_rel_of(sp), ng = S.c.ngamma, ig;
+  double ms = S.ms[sp - 1], qs = S.qs[sp - 1], vA = S.c.vA, kpar = S.kpar, h;
+  double dgamma_rel = GAMREL(sr, 2, 2) - GAMREL(sr, 1, 2), dpparbar = PBREL(sr, 2, 2) - PBREL(sr, 2, 1);
+  cplx r = 0.0, pres, dfg, dfp;
+  for (ig = 1; ig <= ng - 1; ig++) {
+    double g1 = GAMREL(sr, ig, 1);
+    pres = g1 * om * vA / kpar - (1.0 * nn) * qs * vA / (kpar * ms);
+    if (creal(pres) * creal(pres) <= g1 * g1 - 1.0) {
+      h = 1.0;
+      if (ig == ng - 1) h = 0.5;
+      if (ig == 1) dfg = (eval_fit(sp, ig + 1, pres) - eval_fit(sp, ig, pres)) / dgamma_rel;
+      else dfg = (eval_fit(sp, ig + 1, pres) - eval_fit(sp, ig - 1, pres)) / (2.0 * dgamma_rel);
+      dfp = (eval_fit(sp, ig, pres + dpparbar) - eval_fit(sp, ig, pres - dpparbar)) / (2.0 * dpparbar);
+      r = r - h * (om * dfg + (kpar / vA) * dfp) * int_T_res_rel(sp, sr, nn, ig, pres, mode);
+    }
+  }
+  return r * I * dgamma_rel * pi * 2.0 * pi * (qs * vA / (kpar * ms)) * ((ms / vA) * (ms / vA) * (ms / vA));
+}
+
+/* int_ee_rel, src/ALPS_fns_rel.f90:1097-1215 */
+static double int_ee_rel_sp(int sp) {
+  int sr = sproc_rel_of(sp), ng = S.c.ngamma, ig, ip, lo, up;
+  double ms = S.ms[sp - 1], qs = S.qs[sp - 1], vA = S.c.vA, r = 0.0;
+  double dgamma_rel = GAMREL(sr, 2, 2) - GAMREL(sr, 1, 2), dpparbar = PBREL(sr, 2, 2) - PBREL(sr, 2, 1);
+  ig = ng - 1;
+  cone_limits(sr, ig, &lo, &up);
+  r = r + PBREL(sr, ig, lo) * DF0REL(sr, ig, lo, 2);
+  r = r + PBREL(sr, ig, up) * DF0REL(sr, ig, up, 2);
+  for (ip = lo + 1; ip <= up - 1; ip++) r = r + 2.0 * PBREL(sr, ig, ip) * DF0REL(sr, ig, ip, 2);
+  for (ig = 1; ig <= ng - 2; ig++) {
+    cone_limits(sr, ig, &lo, &up);
+    for (ip = lo + 1; ip <= up - 1; ip++) r = r + 4.0 * PBREL(sr, ig, ip) * DF0REL(sr, ig, ip, 2);
+    r = r + 2.0 * PBREL(sr, ig, lo) * DF0REL(sr, ig, lo, 2);
+    r = r + 2.0 * PBREL(sr, ig, up) * DF0REL(sr, ig, up, 2);
+  }
+  r = r * 2.0 * pi * qs / ms;
+  r = r * dgamma_rel * dpparbar * 0.25 * ((ms / vA) * (ms / vA) * (ms / vA));
+  return r;
+}
+double oracle_int_ee_rel(int is) { return int_ee_rel_sp(is); }
+
 /* src/ALPS_fns.f90:641-745 (non-relativistic branch) */
 static void determine_resonances(const struct worker *W, cplx om, int nn, int *found_res_plus,
                                  int *found_res_minus) {
@@ -582,6 +941,19 @@ static void determine_resonances(const struct worker *W, cplx om, int nn, int *f
   cplx p_res;
   *found_res_plus = 0;
   *found_res_minus = 0;
+  if (S.relativistic[sp - 1]) { /* lines 683-701: scan the (pperp,ppar) grid with gamma */
+    int iperp;
+    for (iperp = 0; iperp <= S.c.nperp; iperp++)
+      for (ipar = 0; ipar <= npar - 1; ipar++) {
+        double gamma = sqrt((PP(sp, iperp, ipar, 1) * PP(sp, iperp, ipar, 1) + PP(sp, iperp, ipar, 2) * PP(sp, iperp, ipar, 2)) *
+                                (S.c.vA * S.c.vA) / (ms * ms) + 1.0);
+        p_res = (gamma * ms * om - 1.0 * nn * qs) / kpar;
+        if (PP(sp, 2, ipar, 2) <= creal(p_res) && PP(sp, 2, ipar + 1, 2) > creal(p_res)) *found_res_plus = 1;
+        p_res = (gamma * ms * om + 1.0 * nn * qs) / kpar;
+        if (PP(sp, 2, ipar, 2) <= creal(p_res) && PP(sp, 2, ipar + 1, 2) > creal(p_res)) *found_res_minus = 1;
+      }
+    return;
+  }
   ipar = 0;
   p_res = (ms * om - 1.0 * nn * qs) / kpar;
   while (ipar <= npar - 2 && !*found_res_plus) {
@@ -605,8 +977,17 @@ static void determine_resonances(const struct worker *W, cplx om, int nn, int *f
 }
 
 /* src/ALPS_fns.f90:750-792 (non-relativistic branches) */
+static int g_rel_err = 0;
 static cplx full_integrate(const struct worker *W, cplx om, int nn, int mode, int found_res) {
   if (!found_res) return integrate(W, om, nn, mode, 1, S.c.npar - 1);
+  if (S.relativistic[W->sproc - 1]) { /* lines 774-781 */
+    int err = 0;
+    cplx r = integrate_res_rel(W, om, nn, mode, &err);
+    if (err) g_rel_err = err;
+    if (cimag(om) < 0.0) r = r + 2.0 * landau_integrate_rel(W, om, nn, mode);
+    else if (cimag(om) == 0.0) r = r + landau_integrate_rel(W, om, nn, mode);
+    return r;
+  }
   if (cimag(om) > 0.0) return integrate_res(W, om, nn, mode);
   if (cimag(om) < 0.0) return integrate_res(W, om, nn, mode) + 2.0 * landau_integrate(W, om, nn, mode);
   if (cimag(om) == 0.0) return integrate_res(W, om, nn, mode) + landau_integrate(W, om, nn, mode);
@@ -791,13 +1172,18 @@ static void disp_worker_finish(const struct worker *W, const partial *H, int nh,
         for (m = 0; m < 3; m++) P->schi_low[i][j][m] += H[h].schi_low[i][j][m];
       }
   if (W->nlim[0] == 0) {
-    double ee = int_ee_sp(sp);
-    if (S.c.kperp_norm) {
-      P->schi[2][2] += ee;
-      P->schi_low[2][2][1] += ee;
+    if (S.relativistic[sp - 1]) { /* lines 481-486: schi only, not schi_low */
+      double ee = int_ee_rel_sp(sp);
+      P->schi[2][2] += S.c.kperp_norm ? ee : S.kperp * S.kperp * ee;
     } else {
-      P->schi[2][2] += S.kperp * S.kperp * ee;
-      P->schi_low[2][2][1] += S.kperp * S.kperp * ee;
+      double ee = int_ee_sp(sp);
+      if (S.c.kperp_norm) {
+        P->schi[2][2] += ee;
+        P->schi_low[2][2][1] += ee;
+      } else {
+        P->schi[2][2] += S.kperp * S.kperp * ee;
+        P->schi_low[2][2][1] += S.kperp * S.kperp * ee;
+      }
     }
   }
   {
@@ -819,6 +1205,7 @@ int oracle_disp(const double om_[2], double D[2], double *chi0_out, double *chi0
   cplx eps[3][3], wave[3][3], enx2, enz2, enxnz, d, norm2;
   double kperp = S.kperp, kpar = S.kpar, vA = S.c.vA;
   if (!S.ready) return -1;
+  g_rel_err = 0;
 
   {
     /* flatten (worker, nn) into independent tasks */
@@ -938,7 +1325,7 @@ int oracle_disp(const double om_[2], double D[2], double *chi0_out, double *chi0
   free(chi);
   free(chi_low);
   free(P);
-  return 0;
+  return g_rel_err; /* 8 = alps_error(8): principal window covers the whole cone */
 }
 
 void oracle_full_integrate(int is, int nn, int mode, const double om_[2], double out[2], int *found_res) {
@@ -987,6 +1374,7 @@ void oracle_finalize(void) {
   for (i = 0; i < S.nworkers; i++) free(S.w[i].bessel_array);
   free(S.w);
   free(S.pp); free(S.df0); free(S.param_fit); free(S.poly_fit_coeffs);
+  free(S.f0_rel); free(S.df0_rel); free(S.gamma_rel); free(S.pparbar_rel);
   free(S.ns); free(S.qs); free(S.ms); free(S.relativistic); free(S.usebM); free(S.ACmethod);
   free(S.n_fits); free(S.logfit); free(S.poly_kind); free(S.poly_order); free(S.poly_log_max);
   free(S.nmax); free(S.fit_type); free(S.perp_correction);
@@ -998,7 +1386,6 @@ int oracle_set_species(int is, double ns, double qs, double ms, int relativistic
                        int poly_kind, int poly_order, double poly_log_max) {
   int i;
   if (is < 1 || is > S.c.nspec) return 1;
-  if (relativistic) return 8; /* relativistic species are not restated yet */
   S.ns[is - 1] = ns; S.qs[is - 1] = qs; S.ms[is - 1] = ms;
   S.relativistic[is - 1] = relativistic; S.usebM[is - 1] = usebM; S.ACmethod[is - 1] = ACmethod;
   S.n_fits[is - 1] = n_fits; S.logfit[is - 1] = logfit; S.poly_kind[is - 1] = poly_kind;
@@ -1026,6 +1413,18 @@ int oracle_upload(const double *pp, const double *df0, const double *param_fit, 
   S.param_fit = dup_arr(param_fit, nspec * (S.nperpmax + 1) * 5 * (S.c.maxfits > 0 ? S.c.maxfits : 1));
   S.poly_fit_coeffs = dup_arr(poly_fit_coeffs, nspec * (nperp + 1) * (S.c.maxorder + 1));
   return (S.pp && S.df0) ? 0 : 1;
+}
+
+int oracle_upload_rel(int nspec_rel, const double *f0_rel, const double *df0_rel, const double *gamma_rel,
+                      const double *pparbar_rel) {
+  size_t n = (size_t)nspec_rel * (S.c.ngamma + 1) * (S.c.npparbar + 1);
+  free(S.f0_rel); free(S.df0_rel); free(S.gamma_rel); free(S.pparbar_rel);
+  S.nspec_rel = nspec_rel;
+  S.f0_rel = dup_arr(f0_rel, n);
+  S.df0_rel = dup_arr(df0_rel, 2 * n);
+  S.gamma_rel = dup_arr(gamma_rel, n);
+  S.pparbar_rel = dup_arr(pparbar_rel, n);
+  return 0;
 }
 
 /* src/ALPS_fns.f90:96-118 */

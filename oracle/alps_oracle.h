@@ -50,6 +50,12 @@ int oracle_set_species(int is, double ns, double qs, double ms, int relativistic
 int oracle_upload(const double *pp, const double *df0, const double *param_fit,
                   const double *poly_fit_coeffs);
 
+/* relativistic tables of derivative_f0_rel (src/ALPS_fns_rel.f90:36-276):
+ * f0_rel, gamma_rel, pparbar_rel (nspec_rel,0:ngamma,0:npparbar), df0_rel (...,2) */
+int oracle_upload_rel(int nspec_rel, const double *f0_rel, const double *df0_rel, const double *gamma_rel,
+                      const double *pparbar_rel);
+double oracle_int_ee_rel(int is);
+
 /* derivative_f0: f0(nspec,0:nperp,0:npar) -> df0 (src/ALPS_fns.f90:96-118) */
 int oracle_derivative_f0(const double *f0, const double *pp, double *df0_out,
                          int nspec, int nperp, int npar);

@@ -39,6 +39,8 @@ def lib():
         _LIB.oracle_bessj.restype = C.c_double
         _LIB.oracle_bessj.argtypes = [C.c_int, C.c_double]
         _LIB.oracle_int_ee.restype = C.c_double
+        _LIB.oracle_int_ee_rel.restype = C.c_double
+        _LIB.oracle_upload_rel.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.oracle_set_k.argtypes = [C.c_double, C.c_double, C.c_void_p]
         _LIB.oracle_set_species.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -87,6 +89,9 @@ class Oracle:
         rc = L.oracle_upload(_p(pp), _p(df0), _p(_f(plasma.param_fit)), _p(_f(plasma.poly_fit_coeffs)))
         if rc:
             raise RuntimeError("oracle_upload failed")
+        if plasma.f0_rel is not None:
+            L.oracle_upload_rel(plasma.f0_rel.shape[0], _p(_f(plasma.f0_rel)), _p(_f(plasma.df0_rel)),
+                                _p(_f(plasma.gamma_rel)), _p(_f(plasma.pparbar_rel)))
         if threads:
             L.oracle_set_threads(threads)
         self.nmax = None
@@ -111,12 +116,16 @@ class Oracle:
         omv = np.array([om.real, om.imag])
         D = np.zeros(2)
         if not full:
-            self.L.oracle_disp(_p(omv), _p(D), None, None, None)
+            rc = self.L.oracle_disp(_p(omv), _p(D), None, None, None)
+            if rc:
+                raise RuntimeError("oracle_disp: alps_error(%d)" % rc)
             return complex(D[0], D[1])
         chi0 = np.zeros(n * 9 * 2)
         low = np.zeros(n * 27 * 2)
         wave = np.zeros(18)
-        self.L.oracle_disp(_p(omv), _p(D), _p(chi0), _p(low), _p(wave))
+        rc = self.L.oracle_disp(_p(omv), _p(D), _p(chi0), _p(low), _p(wave))
+        if rc:
+            raise RuntimeError("oracle_disp: alps_error(%d)" % rc)
         c = lambda a, shape: (a[0::2] + 1j * a[1::2]).reshape(shape, order="F")
         return (complex(D[0], D[1]), c(chi0, (n, 3, 3)), c(low, (n, 3, 3, 3)), c(wave, (3, 3)))
 
@@ -135,6 +144,9 @@ class Oracle:
 
     def int_ee(self, is_: int) -> float:
         return self.L.oracle_int_ee(is_)
+
+    def int_ee_rel(self, is_: int) -> float:
+        return self.L.oracle_int_ee_rel(is_)
 
     def nlim(self):
         cap = 4096

@@ -70,3 +70,30 @@ def test_map_search_finds_the_root_region(tmp_path):
     lines = open(path).read().split("\n")
     assert len(lines[0]) == 5 * 16 and lines[50] == ""          # 5es16.6e3 rows, blank line per ir
     assert len([l for l in lines if l.strip()]) == 2500
+
+
+def test_kperp_scan_roots_match_oracle_driver():
+    """C4 (tests/test_kperp.in, shortened): k_perp scan, nmax and the Bessel tables rebuilt every step
+    (src/ALPS_fns.f90:2465-2472).  Roots of the GPU path + C++ secant_osc against the oracle's disp()
+    driven by the independent Python restatement of secant_osc: 1e-8 relative (BASELINE.json)."""
+    from alps_b200.solver import Solver
+    from oracle import driver
+    from oracle.oracle import Oracle
+    pl = tables.config_kpar_fast()          # distribution/test_kperp_dist.in has the same two species
+    pl.Bessel_zero = 1.0e-50
+    steps, numiter, thr, prec = 3, 50, 1.0e-30, 1.0e-5
+    swf = 10.0 ** (np.log10(1.0e-2) + (np.log10(3.0) - np.log10(1.0e-2)) * steps / 64.0)
+    sol = Solver(pl, emulate_nproc=4)
+    try:
+        sol.set_k(1.0e-2, 1.0e-3)
+        opts = sol.opts(numiter=numiter, D_threshold=thr, D_prec=prec)
+        w, _ = sol.refine_guess([complex(9.9e-4, -5.5e-10)], opts)
+        rows, w = sol.om_scan(w, opts, scan_type=3, swi=1.0e-2, swf=swf, swlog=True, ns_steps=steps)
+    finally:
+        sol.close()
+    orc = Oracle(pl, nproc=4)
+    ref = driver.scan_k(orc, 1.0e-2, 1.0e-3, 3, swf, steps, True, complex(9.9e-4, -5.5e-10), numiter, thr, prec)
+    assert rows.shape[0] == len(ref) == steps + 1
+    for r, (kperp, kpar, om) in zip(rows[:, 0, :], ref):
+        assert abs(r[0] - kperp) <= 1e-15 * kperp and r[1] == kpar
+        assert abs(complex(r[2], r[3]) - om) <= 1e-8 * abs(om), (kperp, complex(r[2], r[3]), om)

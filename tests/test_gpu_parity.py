@@ -120,3 +120,46 @@ def test_harmonic_shards_sum_to_the_unsharded_result():
         sol.set_harmonic_shard(0, 1)
     finally:
         sol.close()
+
+
+def test_relativistic_species_small_grid():
+    """Relativistic integrators (src/ALPS_fns_rel.f90) on a reduced tests/test_relativistic.in
+    (Juettner pair plasma, vA = 1, fit type 4): resonant / non-resonant harmonics, Landau term."""
+    pl = tables.config_relativistic(nperp=20, npar=40, ngamma=60, npparbar=80)
+    oms = [6.2713e-2 - 4.662e-8j, 1.0 - 1.655e-6j, 0.5 + 0.01j, 0.3 - 0.02j, 2.5 + 0.0j, 0.9 + 1e-3j]
+    _compare(pl, 1.0e-3, 1.0e-1, oms)
+
+
+def test_relativistic_oblique_many_harmonics():
+    """k_perp ~ 1: ~30 harmonics per species, resonances inside the cone for many gamma."""
+    pl = tables.config_relativistic(nperp=20, npar=40, ngamma=120, npparbar=400)
+    _compare(pl, 0.8, 0.3, [1.0 - 1.655e-6j, 0.5 + 0.01j, 0.3 - 0.02j])
+
+
+def test_relativistic_error_8_is_reported_like_the_reference():
+    """alps_error(8) (src/ALPS_fns_rel.f90:655-656): the principal-value window covers the whole cone.
+    On a coarse relativistic grid both the oracle and the CUDA path must report it."""
+    from alps_b200 import _lib
+    from alps_b200.solver import Solver
+    from oracle.oracle import Oracle
+    pl = tables.config_relativistic(nperp=20, npar=40, ngamma=60, npparbar=80)
+    orc = Oracle(pl)
+    orc.set_k(0.8, 0.3)
+    with pytest.raises(RuntimeError, match="alps_error\\(8\\)"):
+        orc.disp(1.0 - 1.655e-6j)
+    assert abs(orc.disp(0.5 + 0.01j)) > 0          # no error at this omega
+    sol = Solver(pl)
+    try:
+        sol.set_k(0.8, 0.3)
+        with pytest.raises(_lib.AlpsB200Error) as e:
+            sol.disp(1.0 - 1.655e-6j)
+        assert e.value.code == 8
+        assert abs(sol.disp(0.5 + 0.01j) - orc.disp(0.5 + 0.01j)) < 1e-9 * abs(orc.disp(0.5 + 0.01j))
+    finally:
+        sol.close()
+
+
+def test_relativistic_config_c3():
+    """C3 at full size (ngamma = npparbar = 500, 30x60 input table) near its two roots."""
+    pl = tables.config_relativistic()
+    _compare(pl, 1.0e-3, 1.0e-1, [6.2713e-2 - 4.662e-8j, 1.0 - 1.655e-6j, 0.4 + 0.005j])
