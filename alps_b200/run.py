@@ -1,0 +1,156 @@
+"""Twin of the reference's main program (src/ALPS.f90:19-147) for the disp() path:
+
+    python -m alps_b200.run path/to/<runname>.in [--dist path/to/<arrayName>_dist.in] [--out solution]
+
+reads the `.in` namelists, obtains the f0 tables (`distribution/<arrayName>.<is>.array` if present,
+else regenerated from the `_dist.in` closed forms), then map_search or refine_guess and the k scans,
+writing `<out>/<runname>.map / .roots / .scan_* / .eigen_* / .heat_* / .heat_mech_*` in the
+reference's formats.  Every D(omega,k) comes from the GPU (libalps_b200.so).
+
+Not reproduced here (out of scope): the LM / Chebyshev fits of
+determine_param_fit -- the analytic-continuation parameters are the generator's ideal values when
+the tables are regenerated, else the initial values of the &ffit blocks; NHDS calc_chi for use_bM
+species; scan_option=2 (om_double_scan)."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from . import tables
+from .namelist import read_namelists
+from .solver import Solver
+
+
+def plasma_from_inputs(nl, dist_nl=None, base_dir="."):
+    s = nl["system"]
+    nspec, nperp, npar = int(s["nspec"]), int(s["nperp"]), int(s["npar"])
+    vA = float(s["va"])
+    name = s.get("arrayname", "")
+    species, fits_in = [], []
+    for i in range(1, nspec + 1):
+        sp = nl["spec_%d" % i]
+        nf = int(sp.get("ff", 1))
+        ft, pc, par = [], [], []
+        for j in range(1, nf + 1):
+            f = nl.get("ffit_%d_%d" % (i, j), {})
+            ft.append(int(f.get("fit_type_in", 1)))
+            pc.append(float(f.get("perpcorr", 1.0)))
+            par.append([float(f.get("fit_%d" % k, 0.0)) for k in range(1, 6)])
+        po = nl.get("poly_spec_%d" % i, {})
+        species.append(tables.Species(ns=float(sp["nn"]), qs=float(sp["qq"]), ms=float(sp["mm"]),
+                                      relativistic=bool(sp.get("relat", False)), usebM=bool(sp.get("use_bm", False)),
+                                      ACmethod=int(sp.get("ac_method", 1)), fit_type=ft, perp_correction=pc,
+                                      logfit=bool(sp.get("log_fit", True)), poly_kind=int(po.get("kind", 1)),
+                                      poly_order=int(po.get("order", 0)) if int(sp.get("ac_method", 1)) == 2 else 0,
+                                      poly_log_max=float(po.get("log_max", 18.0))))
+        fits_in.append(par)
+    pp = np.zeros((nspec, nperp + 1, npar + 1, 2), order="F")
+    f0 = np.zeros((nspec, nperp + 1, npar + 1), order="F")
+    maxfits = max(len(sp.fit_type) for sp in species)
+    ngamma = int(s.get("ngamma", 0))
+    pf = np.zeros((nspec, max(nperp, ngamma) + 1, 5, maxfits), order="F")
+    have_files = all(os.path.exists(os.path.join(base_dir, "distribution", "%s.%d.array" % (name, i + 1)))
+                     or species[i].usebM for i in range(nspec))
+    if have_files:
+        for i in range(nspec):
+            if species[i].usebM:
+                continue
+            a = np.loadtxt(os.path.join(base_dir, "distribution", "%s.%d.array" % (name, i + 1)))
+            a = a.reshape((nperp + 1, npar + 1, 3))
+            pp[i, :, :, 0], pp[i, :, :, 1], f0[i] = a[:, :, 0], a[:, :, 1], a[:, :, 2]
+            for j, par in enumerate(fits_in[i]):
+                for k in range(5):
+                    pf[i, :, k, j] = par[k]
+    else:
+        if dist_nl is None:
+            raise SystemExit("no distribution/%s.<is>.array files and no --dist file" % name)
+        ds = dist_nl["system"]
+        specs = []
+        for i in range(1, nspec + 1):
+            d = dist_nl["spec_%d" % i]
+            specs.append(tables.DistSpec(ms=float(d["ms_read"]), tau=float(d["taus"]), alph=float(d["alphs"]),
+                                         drift=float(d["ps"]), kappa=float(d["kappas"]),
+                                         distribution=int(d["distributions"]), autoscale=bool(d["autoscales"]),
+                                         maxPperp=float(d["maxpperps"]), maxPpar=float(d["maxppars"])))
+        pp, f0, fits = tables.generate_distribution(specs, nperp, npar, beta=float(ds["beta"]), vA=float(ds["va"]),
+                                                    maxP=float(ds["maxp"]))
+        for i in range(nspec):
+            species[i].fit_type = [fits[i]["fit_type"]] if not species[i].relativistic else species[i].fit_type
+            species[i].perp_correction = [fits[i]["perpcorr"]]
+            for k in range(5):
+                pf[i, :, k, 0] = fits[i]["params"][k]
+    pl = tables.Plasma(nperp=nperp, npar=npar, vA=vA, species=species, pp=pp, f0=f0, param_fit=pf,
+                       ngamma=ngamma, npparbar=int(s.get("npparbar", 0)),
+                       Bessel_zero=float(s.get("bessel_zero", 1.0e-50)), Tlim=float(s.get("tlim", 0.01)),
+                       positions_principal=int(s.get("positions_principal", 3)),
+                       n_resonance_interval=int(s.get("n_resonance_interval", 100)),
+                       kperp_norm=bool(s.get("kperp_norm", True)))
+    if any(sp.relativistic for sp in species):
+        from .relativistic import derivative_f0_rel
+        rel = [i for i, sp in enumerate(species) if sp.relativistic]
+        shape = (len(rel), pl.ngamma + 1, pl.npparbar + 1)
+        pl.f0_rel, pl.gamma_rel, pl.pparbar_rel = (np.zeros(shape, order="F") for _ in range(3))
+        pl.df0_rel = np.zeros(shape + (2,), order="F")
+        for r, i in enumerate(rel):
+            g, p, f, d, integ = derivative_f0_rel(pp[i], f0[i], species[i].ms, vA, pl.ngamma, pl.npparbar)
+            pl.gamma_rel[r], pl.pparbar_rel[r], pl.f0_rel[r], pl.df0_rel[r] = g, p, f, d
+            if not have_files:
+                pf[i, :, 0, 0] = pf[i, 0, 0, 0] / integ
+    return pl
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="alps_b200.run")
+    ap.add_argument("input")
+    ap.add_argument("--dist", default=None)
+    ap.add_argument("--out", default="solution")
+    ap.add_argument("--nproc", type=int, default=0, help="MPI size of the reference run to emulate")
+    a = ap.parse_args(argv)
+    nl = read_namelists(a.input)
+    runname = os.path.splitext(os.path.basename(a.input))[0]
+    dist_nl = read_namelists(a.dist) if a.dist else None
+    pl = plasma_from_inputs(nl, dist_nl, base_dir=os.getcwd())
+    if any(sp.usebM for sp in pl.species):
+        raise SystemExit("use_bM species need NHDS calc_chi (not built yet)")
+    s = nl["system"]
+    os.makedirs(a.out, exist_ok=True)
+    prefix = os.path.join(a.out, runname)
+    sol = Solver(pl, emulate_nproc=a.nproc)
+    try:
+        kperp, kpar = float(s["kperp"]), float(s["kpar"])
+        nmax = sol.set_k(kperp, kpar)
+        print("nmax:", list(map(int, nmax)))
+        opts = sol.opts(numiter=int(s.get("numiter", 50)), D_threshold=float(s.get("d_threshold", 1e-5)),
+                        D_prec=float(s.get("d_prec", 1e-5)), D_tol=float(s.get("d_tol", 1e-7)),
+                        D_gap=float(s.get("d_gap", 1e-5)), secant_method=int(s.get("secant_method", 0)))
+        nroots = int(s.get("nroots", 1))
+        if bool(s.get("use_map", False)):
+            m = nl["maps_1"]
+            om, val, cal, roots = sol.map_search(float(m["omi"]), float(m["omf"]), float(m["gami"]), float(m["gamf"]),
+                                                 int(m["nr"]), int(m["ni"]), bool(m.get("loggridw", False)),
+                                                 bool(m.get("loggridg", False)),
+                                                 bool(s.get("determine_minima", True)), map_path=prefix + ".map")
+            guesses = roots[:min(nroots, len(roots))] if bool(s.get("determine_minima", True)) else []
+        else:
+            guesses = [complex(float(nl["guess_%d" % i]["g_om"]), float(nl["guess_%d" % i]["g_gam"]))
+                       for i in range(1, nroots + 1)]
+        w, D = sol.refine_guess(guesses, opts, roots_path=prefix + ".roots") if guesses else (np.zeros(0, complex), None)
+        for r, d in zip(w, D if D is not None else []):
+            print("root %s  D=%s" % (r, d))
+        if int(s.get("n_scan", 0)) > 0 and int(s.get("scan_option", 1)) == 1 and len(w):
+            for ik in range(1, int(s["n_scan"]) + 1):
+                sc = nl["scan_input_%d" % ik]
+                rows, w = sol.om_scan(w, opts, int(sc["scan_type"]), float(sc["swi"]), float(sc["swf"]),
+                                      bool(sc["swlog"]), int(sc["ns"]), int(sc.get("nres", 1)),
+                                      bool(sc.get("eigen", False)), bool(sc.get("heating", False)), prefix, ik)
+                print("scan %d done: k=(%g,%g)" % (ik, sol.kperp, sol.kpar))
+    finally:
+        sol.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -97,3 +97,20 @@ def test_kperp_scan_roots_match_oracle_driver():
     for r, (kperp, kpar, om) in zip(rows[:, 0, :], ref):
         assert abs(r[0] - kperp) <= 1e-15 * kperp and r[1] == kpar
         assert abs(complex(r[2], r[3]) - om) <= 1e-8 * abs(om), (kperp, complex(r[2], r[3]), om)
+
+
+def test_cli_twin_of_the_main_program(tmp_path):
+    """`python -m alps_b200.run <runname>.in` (twin of src/ALPS.f90) writes the same
+    solution/<runname>.scan_kpara_1.root_1 as the reference's golden, character for character."""
+    from alps_b200 import run
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "solution")
+    rc = run.main([os.path.join(here, "inputs", "test_kpar_fast.in"),
+                   "--dist", os.path.join(here, "inputs", "test_kpar_fast_dist.in"), "--out", out, "--nproc", "4"])
+    assert rc == 0
+    ours = open(os.path.join(out, "test_kpar_fast.scan_kpara_1.root_1")).read().split()
+    gold = open(os.path.join(GOLD, "test_kpar_fast.scan_kpara_1.root_1")).read().split()
+    assert ours == gold
+    for kind in ("eigen", "heat", "heat_mech"):
+        assert os.path.exists(os.path.join(out, "test_kpar_fast.%s_kpara_1.root_1" % kind))
+    assert os.path.exists(os.path.join(out, "test_kpar_fast.roots"))
