@@ -14,6 +14,7 @@
 #include "../../include/alps_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "nhds.hpp"
 
 using namespace alps;
 
@@ -55,8 +56,11 @@ struct State {
   RelTile* d_rtiles = nullptr;
   std::vector<RelTile> rtiles;
   QuadParams P{};
-  std::vector<double> ext;   // external chi, [nspec][PARTIAL_PER_SPEC]
+  std::vector<double> ext;   // external chi of the next alps_b200_disp call, [nspec][PARTIAL_PER_SPEC]
   bool ext_any = false;
+  nhds::Params bm[MAXSPEC];  // &bM_spec_j of use_bM species (NHDS twin, nhds.hpp)
+  bool bm_any = false;
+  std::vector<double> ext_batch;   // per-omega external chi of a chunk, [n][nspec][PARTIAL_PER_SPEC]
   int mode = 0;
   QuadVariant qv{8, 16, 32, 2};
   int shard_rank = 0, shard_n = 1;
@@ -108,7 +112,7 @@ inline size_t ipp(int nspec, int nperp, int npar, int is0, int iperp, int ipar, 
 
 void free_batch() {
   dfree(&S.d_om); dfree(&S.d_D); dfree(&S.d_Sbulk); dfree(&S.d_Sres); dfree(&S.d_gwin); dfree(&S.d_partial);
-  dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work);
+  dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work); dfree(&S.d_ext);
   S.batch = 0;
 }
 
@@ -215,7 +219,7 @@ int ensure_batch(int want) {
       dalloc(&S.d_Sres, B * NI * 12) || dalloc(&S.d_gwin, B * NI * S.gh.WINX * 6) ||
       dalloc(&S.d_partial, B * S.gh.nspec * PARTIAL_PER_SPEC) || dalloc(&S.d_chi0, B * S.gh.nspec * 18) ||
       dalloc(&S.d_chi0_low, B * S.gh.nspec * 54) || dalloc(&S.d_wave, B * 18) || dalloc(&S.d_plan, B * NI) ||
-      dalloc(&S.d_work, B * NI))
+      dalloc(&S.d_work, B * NI) || dalloc(&S.d_ext, B * S.gh.nspec * PARTIAL_PER_SPEC))
     return ALPS_B200_ERR_CUDA;
   S.batch = want;
   return 0;
@@ -232,9 +236,55 @@ int auto_batch() {
   return (int)b;
 }
 
+// External (NHDS) chi of use_bM species for a chunk: closed-form host algebra per omega, summed into
+// chi exactly where disp() does it (src/ALPS_fns.f90:344-362).  h_om may be NULL (device-resident
+// omegas are copied back first).  Returns the device pointer to use, or nullptr if nothing to add.
+int prepare_external(int n, const double* d_om, const double* h_om, const double** d_ext_out) {
+  *d_ext_out = nullptr;
+  if (!S.bm_any && !S.ext_any) return 0;
+  const int nspec = S.cfg.nspec;
+  const size_t per = (size_t)nspec * PARTIAL_PER_SPEC;
+  S.ext_batch.assign((size_t)n * per, 0.0);
+  std::vector<double> om_copy;
+  if (S.bm_any) {
+    if (!h_om) {
+      om_copy.resize(2 * (size_t)n);
+      CK(cudaMemcpyAsync(om_copy.data(), d_om, om_copy.size() * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+      CK(cudaStreamSynchronize(S.stream));
+      h_om = om_copy.data();
+    }
+    static const int MI[6] = {0, 1, 2, 0, 0, 1}, MJ[6] = {0, 1, 2, 1, 2, 2};
+    for (int s = 0; s < nspec; s++) {
+      if (!S.gh.sp[s].usebM || !S.bm[s].set) continue;
+      for (int i = 0; i < n; i++) {
+        nhds::cplx chi[9], low[27];
+        int rc = nhds::calc_chi(chi, low, S.bm[s], S.gh.kpar, S.gh.kperp, nhds::cplx(h_om[2 * i], h_om[2 * i + 1]),
+                                S.gh.kperp_norm != 0);
+        if (rc) return fail(ALPS_B200_ERR_UNSUPPORTED, "cold-plasma species need kperp_norm=.true. (ALPS_NHDS.f90:461)");
+        double* o = S.ext_batch.data() + (size_t)i * per + (size_t)s * PARTIAL_PER_SPEC;
+        for (int c = 0; c < 6; c++) {
+          const nhds::cplx v = chi[MI[c] + 3 * MJ[c]];
+          o[2 * c] = v.real();
+          o[2 * c + 1] = v.imag();
+          for (int m = 0; m < 3; m++) {
+            const nhds::cplx vl = low[MI[c] + 3 * MJ[c] + 9 * m];
+            o[2 * (6 + 3 * c + m)] = vl.real();
+            o[2 * (6 + 3 * c + m) + 1] = vl.imag();
+          }
+        }
+      }
+    }
+  }
+  if (S.ext_any)   // caller-supplied chi (alps_b200_add_external_chi) applies to the first omega
+    for (size_t q = 0; q < per; q++) S.ext_batch[q] += S.ext[q];
+  CK(cudaMemcpyAsync(S.d_ext, S.ext_batch.data(), S.ext_batch.size() * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+  *d_ext_out = S.d_ext;
+  return 0;
+}
+
 // run the hot path for n omegas already on the device (n <= S.batch)
 int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, const double* d_partial_in,
-              bool want_aux) {
+              bool want_aux, const double* h_om = nullptr) {
   const GlobalDev* gd = S.gd;
   if (!d_partial_in) {
     launch_plan(gd, S.gh, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream);
@@ -255,7 +305,12 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     if (d_partial_out) return 0;
     d_partial_in = part;
   }
-  launch_assemble(gd, S.gh, d_om, n, d_partial_in, S.ext_any ? S.d_ext : nullptr, d_D,
+  const double* d_ext = nullptr;
+  {
+    int rc = prepare_external(n, d_om, h_om, &d_ext);
+    if (rc) return rc;
+  }
+  launch_assemble(gd, S.gh, d_om, n, d_partial_in, d_ext, d_D,
                   want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr, want_aux ? S.d_wave : nullptr,
                   S.stream);
   S.launches += 1;
@@ -323,9 +378,9 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.gh.maxorder = cfg->maxorder;
   S.gh.vA = cfg->vA;
   S.gh.Tlim = cfg->Tlim;
-  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8) ||
-      dalloc(&S.d_ext, (size_t)cfg->nspec * PARTIAL_PER_SPEC))
-    return ALPS_B200_ERR_CUDA;
+  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8)) return ALPS_B200_ERR_CUDA;
+  for (int s = 0; s < MAXSPEC; s++) S.bm[s] = nhds::Params();
+  S.bm_any = false;
   CK(cudaMemset(S.d_err, 0, 8 * sizeof(int)));
   S.ext.assign((size_t)cfg->nspec * PARTIAL_PER_SPEC, 0.0);
   S.ext_any = false;
@@ -354,7 +409,7 @@ void alps_b200_finalize(void) {
     h = SpeciesHost();
   }
   free_batch();
-  dfree(&S.d_pp_f); dfree(&S.d_df0_f); dfree(&S.gd); dfree(&S.d_work_count); dfree(&S.d_err); dfree(&S.d_ext);
+  dfree(&S.d_pp_f); dfree(&S.d_df0_f); dfree(&S.gd); dfree(&S.d_work_count); dfree(&S.d_err);
   dfree(&S.d_tiles);
   dfree(&S.d_rtiles);
   if (S.h_pin) cudaFreeHost(S.h_pin);
@@ -745,7 +800,7 @@ int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
     int m = std::min(S.batch, n - o);
     memcpy(h_om, om + 2 * (size_t)o, (size_t)m * 2 * sizeof(double));
     CK(cudaMemcpyAsync(S.d_om, h_om, (size_t)m * 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
-    if ((rc = run_chunk(m, S.d_om, S.d_D, nullptr, nullptr, chi0_opt != nullptr))) return rc;
+    if ((rc = run_chunk(m, S.d_om, S.d_D, nullptr, nullptr, chi0_opt != nullptr, h_om))) return rc;
     CK(cudaMemcpyAsync(h_D, S.d_D, (size_t)m * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
     if (chi0_opt)
       CK(cudaMemcpyAsync(chi0_opt + (size_t)o * nspec * 18, S.d_chi0, (size_t)m * nspec * 18 * sizeof(double),
@@ -767,7 +822,7 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   S.h_pin[1] = om[1];
   CK(cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
   const bool aux = chi0 || chi0_low || wave;
-  if ((rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, aux))) return rc;
+  if ((rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, aux, om))) return rc;
   CK(cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if (chi0) CK(cudaMemcpyAsync(chi0, S.d_chi0, (size_t)nspec * 18 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if (chi0_low)
@@ -802,8 +857,34 @@ int alps_b200_add_external_chi(int is, const double* chi, const double* chi_low)
       o[2 * (6 + 3 * c + m) + 1] = chi_low ? chi_low[2 * kl + 1] : 0.0;
     }
   }
-  CK(cudaMemcpy(S.d_ext, S.ext.data(), S.ext.size() * sizeof(double), cudaMemcpyHostToDevice));
   S.ext_any = true;
+  return 0;
+}
+
+int alps_b200_set_bm_species(int is, int bM_nmaxs, double bM_Bessel_zeros, double bM_betas, double bM_alphas,
+                             double bM_pdrifts) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (is < 1 || is > S.cfg.nspec || !S.sp[is - 1].set) return fail(ALPS_B200_ERR_USAGE, "species %d not set", is);
+  nhds::Params& p = S.bm[is - 1];
+  p.bMnmaxs = bM_nmaxs; p.bMBessel_zeros = bM_Bessel_zeros; p.bMbetas = bM_betas; p.bMalphas = bM_alphas;
+  p.bMpdrifts = bM_pdrifts;
+  p.ns = S.gh.sp[is - 1].ns; p.qs = S.gh.sp[is - 1].qs; p.ms = S.gh.sp[is - 1].ms;
+  p.set = true;
+  S.bm_any = S.bm_any || S.gh.sp[is - 1].usebM;
+  return 0;
+}
+
+int alps_b200_nhds_calc_chi(double ns, double qs, double ms, int bM_nmaxs, double bM_Bessel_zeros, double bM_betas,
+                            double bM_alphas, double bM_pdrifts, double kz, double kperp, const double x[2],
+                            int kperp_norm, double* chi, double* chi_low) {
+  nhds::Params p;
+  p.ns = ns; p.qs = qs; p.ms = ms; p.bMnmaxs = bM_nmaxs; p.bMBessel_zeros = bM_Bessel_zeros; p.bMbetas = bM_betas;
+  p.bMalphas = bM_alphas; p.bMpdrifts = bM_pdrifts; p.set = true;
+  nhds::cplx c[9], l[27];
+  if (nhds::calc_chi(c, l, p, kz, kperp, nhds::cplx(x[0], x[1]), kperp_norm != 0))
+    return fail(ALPS_B200_ERR_UNSUPPORTED, "cold-plasma species need kperp_norm=.true.");
+  for (int i = 0; i < 9 && chi; i++) { chi[2 * i] = c[i].real(); chi[2 * i + 1] = c[i].imag(); }
+  for (int i = 0; i < 27 && chi_low; i++) { chi_low[2 * i] = l[i].real(); chi_low[2 * i + 1] = l[i].imag(); }
   return 0;
 }
 

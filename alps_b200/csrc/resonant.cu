@@ -562,7 +562,7 @@ __global__ void k_assemble(const GlobalDev* __restrict__ gp, const double* __res
   for (int c = 0; c < 6; c++) eps[c] = mk(0.0, 0.0);
   for (int s = 0; s < nspec; s++) {
     const double* p = partial + ((size_t)iom * nspec + s) * PARTIAL_PER_SPEC;
-    const double* x = ext_chi ? ext_chi + (size_t)s * PARTIAL_PER_SPEC : nullptr;
+    const double* x = ext_chi ? ext_chi + ((size_t)iom * nspec + s) * PARTIAL_PER_SPEC : nullptr;
     const bool useext = x && g.sp[s].usebM;
     for (int c = 0; c < 6; c++) {
       cd v = mk(p[2 * c], p[2 * c + 1]);

@@ -45,6 +45,9 @@ class Solver:
                 i + 1, s.ns, s.qs, s.ms, int(s.relativistic), int(s.usebM), s.ACmethod,
                 len(s.fit_type), _p(ft), _p(pc), int(s.logfit), s.poly_kind, s.poly_order,
                 s.poly_log_max))
+            if s.usebM:
+                _lib.check(self.L.alps_b200_set_bm_species(i + 1, s.bM_nmaxs, s.bM_Bessel_zeros, s.bM_betas,
+                                                           s.bM_alphas, s.bM_pdrifts))
         pp = _f(plasma.pp)
         df0 = _f(plasma.df0)
         _lib.check(self.L.alps_b200_upload(_p(pp), _p(df0), _p(_f(plasma.param_fit)),
@@ -244,3 +247,17 @@ class Solver:
 
     def close(self):
         self.L.alps_b200_finalize()
+
+
+def nhds_calc_chi(species, om: complex, kperp: float, kpar: float, kperp_norm: bool = True):
+    """calc_chi of ALPS_NHDS.f90 for a use_bM species (stateless host closed form, no GPU):
+    returns chi(3,3), chi_low(3,3,-1:1)."""
+    L = _lib.lib()
+    x = np.array([om.real, om.imag])
+    chi = np.zeros(9, dtype=np.complex128)
+    low = np.zeros(27, dtype=np.complex128)
+    s = species
+    _lib.check(L.alps_b200_nhds_calc_chi(s.ns, s.qs, s.ms, s.bM_nmaxs, s.bM_Bessel_zeros, s.bM_betas, s.bM_alphas,
+                                         s.bM_pdrifts, kpar, kperp, _p(x), int(kperp_norm),
+                                         _p(chi.view(np.float64)), _p(low.view(np.float64))))
+    return chi.reshape((3, 3), order="F"), low.reshape((3, 3, 3), order="F")

@@ -46,6 +46,12 @@ class Species:
     poly_kind: int = 1
     poly_order: int = 0
     poly_log_max: float = 18.0
+    # &bM_spec_j (src/ALPS_io.f90:342-372), used when usebM
+    bM_nmaxs: int = 500
+    bM_Bessel_zeros: float = 1.0e-50
+    bM_betas: float = 1.0
+    bM_alphas: float = 1.0
+    bM_pdrifts: float = 0.0
 
 
 @dataclass
@@ -207,6 +213,16 @@ def config_kappa3(nperp: int = 1024, npar: int = 2048, kappa: float = 8.0) -> Pl
              DistSpec(ms=4.0, kappa=kappa, distribution=2)]
     return make_plasma(specs, ns=[1.0, 1.04, 0.02], qs=[1.0, -1.0, 2.0], nperp=nperp, npar=npar,
                        Bessel_zero=1.0e-45)
+
+
+def config_bimax(nperp: int = 150, npar: int = 300) -> Plasma:
+    """C2: tests/test_bimax.in -- protons use_bM=T (closed-form NHDS chi), electrons from the f0 table."""
+    specs = [DistSpec(ms=1.0), DistSpec(ms=5.44662e-4)]
+    pl = make_plasma(specs, ns=[1.0, 1.0], qs=[1.0, -1.0], nperp=nperp, npar=npar, Bessel_zero=1.0e-45)
+    pl.species[0].usebM = True
+    pl.pp[0] = 0.0      # read_f0 zeroes the tables of use_bM species (src/ALPS_io.f90:672-676)
+    pl.f0[0] = 0.0
+    return pl
 
 
 def config_small(nperp: int = 24, npar: int = 48, kind: int = 1) -> Plasma:

@@ -106,6 +106,16 @@ int alps_b200_disp_batch_dev(int n, const double *d_om, double *d_D);
  * (src/ALPS_fns.f90:344-362): chi(3,3) and chi_low(3,3,-1:1) for the next alps_b200_disp call. */
 int alps_b200_add_external_chi(int is, const double *chi, const double *chi_low);
 
+/* replaces: calc_chi of module alps_nhds (src/ALPS_NHDS.f90:59-464) for use_bM species: with the
+ * &bM_spec_j parameters set, every disp call computes the closed-form bi-Maxwellian / cold chi on the
+ * host (O(nmax) algebra, not a table quadrature) and sums it in like src/ALPS_fns.f90:344-362. */
+int alps_b200_set_bm_species(int is, int bM_nmaxs, double bM_Bessel_zeros, double bM_betas,
+                             double bM_alphas, double bM_pdrifts);
+/* the same closed form as a stateless host function (no GPU needed): chi(3,3), chi_low(3,3,-1:1) */
+int alps_b200_nhds_calc_chi(double ns, double qs, double ms, int bM_nmaxs, double bM_Bessel_zeros,
+                            double bM_betas, double bM_alphas, double bM_pdrifts, double kz, double kperp,
+                            const double x[2], int kperp_norm, double *chi, double *chi_low);
+
 /* Harmonic sharding (replaces split_processes + MPI_REDUCE, src/ALPS_fns.f90:4079-4207, 519-523):
  * restrict this process to harmonics |n| in [nlo,nhi] of species is (is=0: all species),
  * produce un-normalised partial sums (caller all-reduces them over NCCL), then assemble. */

@@ -978,6 +978,10 @@ static void determine_resonances(const struct worker *W, cplx om, int nn, int *f
 
 /* src/ALPS_fns.f90:750-792 (non-relativistic branches) */
 static int g_rel_err = 0;
+/* chi / chi_low of use_bM species for the next oracle_disp (what calc_chi returns, src/ALPS_fns.f90:344-362);
+ * column-major (3,3) and (3,3,-1:1) per species */
+static cplx g_ext_chi[8][9], g_ext_low[8][27];
+static int g_ext_set[8];
 static cplx full_integrate(const struct worker *W, cplx om, int nn, int mode, int found_res) {
   if (!found_res) return integrate(W, om, nn, mode, 1, S.c.npar - 1);
   if (S.relativistic[W->sproc - 1]) { /* lines 774-781 */
@@ -1231,6 +1235,18 @@ int oracle_disp(const double om_[2], double D[2], double *chi0_out, double *chi0
     free(first); free(tw); free(tn); free(H);
   }
 
+  /* use_bM species: chi_NHDS enters on the rank that owns n = 0 (lines 344-362): schi = chi_NHDS/(ns qs), then
+   * the ns*qs normalisation -> chi_NHDS itself, upper triangle only */
+  for (is = 1; is <= nspec; is++)
+    if (S.usebM[is - 1] && is <= 8 && g_ext_set[is - 1]) {
+      static const int UI[6] = {0, 1, 2, 0, 0, 1}, UJ[6] = {0, 1, 2, 1, 2, 2};
+      int q;
+      for (q = 0; q < 6; q++) {
+        double nq = S.ns[is - 1] * S.qs[is - 1];
+        chi[is - 1][UI[q]][UJ[q]] += (g_ext_chi[is - 1][UI[q] + 3 * UJ[q]] / nq) * nq;
+        for (m = 0; m < 3; m++) chi_low[is - 1][UI[q]][UJ[q]][m] += (g_ext_low[is - 1][UI[q] + 3 * UJ[q] + 9 * m] / nq) * nq;
+      }
+    }
   /* MPI_REDUCE(SUM) over workers in rank order, lines 519-523 */
   for (iw = 0; iw < S.nworkers; iw++) {
     is = S.w[iw].sproc;
@@ -1462,6 +1478,13 @@ int oracle_set_k(double kperp, double kpar, int *nmax_out) {
   return 0;
 }
 
+void oracle_set_external_chi(int is, const double *chi, const double *chi_low) {
+  int i;
+  if (is < 1 || is > 8) return;
+  for (i = 0; i < 9; i++) g_ext_chi[is - 1][i] = chi[2 * i] + I * chi[2 * i + 1];
+  for (i = 0; i < 27; i++) g_ext_low[is - 1][i] = chi_low[2 * i] + I * chi_low[2 * i + 1];
+  g_ext_set[is - 1] = 1;
+}
 void oracle_set_ncap(int ncap) { S.ncap = ncap; }
 void oracle_set_threads(int n) { S.nthreads = n; }
 

@@ -69,6 +69,8 @@ int oracle_disp(const double om[2], double D[2], double *chi0, double *chi0_low,
                 double *wave);
 
 /* Restrict every worker to harmonics |n| <= ncap (bench sampling only; <0 = off). */
+/* chi(3,3), chi_low(3,3,-1:1) of a use_bM species (NHDS calc_chi output) for the following oracle_disp calls */
+void oracle_set_external_chi(int is, const double *chi, const double *chi_low);
 void oracle_set_ncap(int ncap);
 void oracle_set_threads(int nthreads);
 

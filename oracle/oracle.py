@@ -108,6 +108,11 @@ class Oracle:
         self.nmax = nmax
         return nmax
 
+    def set_external_chi(self, is_: int, chi, chi_low):
+        c = np.ascontiguousarray(np.asarray(chi, dtype=np.complex128).ravel(order="F"))
+        cl = np.ascontiguousarray(np.asarray(chi_low, dtype=np.complex128).ravel(order="F"))
+        self.L.oracle_set_external_chi(is_, _p(c.view(np.float64)), _p(cl.view(np.float64)))
+
     def set_ncap(self, ncap: int):
         self.L.oracle_set_ncap(ncap)
 

@@ -163,3 +163,33 @@ def test_relativistic_config_c3():
     """C3 at full size (ngamma = npparbar = 500, 30x60 input table) near its two roots."""
     pl = tables.config_relativistic()
     _compare(pl, 1.0e-3, 1.0e-1, [6.2713e-2 - 4.662e-8j, 1.0 - 1.655e-6j, 0.4 + 0.005j])
+
+
+def test_bimax_config_nhds_species():
+    """C2 (tests/test_bimax.in): species 1 use_bM=T -- its chi is the closed-form NHDS calc_chi, computed on
+    the host inside alps_b200_disp; species 2 is integrated from the table.  The oracle is fed the same
+    closed form (tests/test_nhds.py checks that twin against scipy)."""
+    from alps_b200.solver import Solver, nhds_calc_chi
+    from oracle.oracle import Oracle
+    pl = tables.config_bimax(60, 120)
+    kperp, kpar = 1.0e-3, 0.03
+    orc = Oracle(pl)
+    sol = Solver(pl)
+    try:
+        assert list(orc.set_k(kperp, kpar)) == list(sol.set_k(kperp, kpar))
+        oms = np.array([3.0e-2 - 1.0e-5j, 4.5e-2 - 1.9e-2j, 0.1 + 0.002j, 0.05 + 0.0j])
+        Db = sol.disp_batch(oms)
+        for i, om in enumerate(oms):
+            chi, low = nhds_calc_chi(pl.species[0], complex(om), kperp, kpar)
+            orc.set_external_chi(1, chi, low)
+            Do, chi_o, low_o, wave_o = orc.disp(complex(om), full=True)
+            Dg, chi_g, low_g, wave_g = sol.disp(complex(om), full=True)
+            ws = wave_scale(chi_o, complex(om), pl.vA, kperp, kpar)
+            assert scaled_err(wave_g, wave_o, ws) < TOL
+            assert abs(Dg - Do) / det_scale(ws) < TOL
+            assert abs(Db[i] - Dg) <= 1e-13 * det_scale(ws)
+            for s in range(2):
+                assert chi_err(chi_g[s], chi_o[s]) < TOL
+                assert chi_err(low_g[s, :, :, 1], low_o[s, :, :, 1]) < TOL
+    finally:
+        sol.close()
