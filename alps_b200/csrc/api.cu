@@ -24,8 +24,8 @@ struct SpeciesHost {
   bool set = false;
   std::vector<double> pperp, ppar;
   double *d_pperp = nullptr, *d_ppar = nullptr, *d_A = nullptr, *d_C0 = nullptr, *d_Cp = nullptr;
-  double *d_J = nullptr, *d_W = nullptr, *d_pf = nullptr, *d_poly = nullptr, *d_ee = nullptr;
-  size_t cap_J = 0, cap_W = 0;
+  double *d_J = nullptr, *d_W = nullptr, *d_pf = nullptr, *d_poly = nullptr, *d_ee = nullptr, *d_G = nullptr;
+  size_t cap_J = 0, cap_W = 0, cap_G = 0;
   bool grid = false;    // has f0 tables on the (p_perp,p_par) grid (everything but use_bM species)
   bool table = false;   // non-relativistic table species: goes through k_quad
   // relativistic species
@@ -55,6 +55,9 @@ struct State {
   std::vector<QuadTile> tiles;
   RelTile* d_rtiles = nullptr;
   std::vector<RelTile> rtiles;
+  FastItem* d_fitems = nullptr;
+  std::vector<FastItem> fitems;
+  double* d_om_i = nullptr;   // the constant omega = i of the STORE launch
   QuadParams P{};
   std::vector<double> ext;   // external chi of the next alps_b200_disp call, [nspec][PARTIAL_PER_SPEC]
   bool ext_any = false;
@@ -211,6 +214,46 @@ int make_tmap(CUtensorMap* tm, const double* base, uint64_t inner, uint64_t rows
   return 0;
 }
 
+// mode 1: GA/GB tables of every table species for the current k (one STORE launch of k_quad with om = i)
+int build_hoisted_tables() {
+  const int nspec = S.cfg.nspec, npar = S.cfg.npar;
+  S.fitems.clear();
+  for (int s = 0; s < nspec; s++) {
+    SpeciesHost& h = S.sp[s];
+    SpeciesDev& d = S.gh.sp[s];
+    if (!h.table) continue;
+    const size_t nG = (size_t)(d.nhi + 1) * (npar - 1) * 6;
+    if (nG > h.cap_G) {
+      if (dalloc(&h.d_G, nG)) return ALPS_B200_ERR_CUDA;
+      h.cap_G = nG;
+    }
+    d.G = h.d_G;
+    S.P.gtab[s] = h.d_G;
+    for (int n = d.nlo_shard; n <= d.nhi_shard; n++) S.fitems.push_back(FastItem{s, n});
+  }
+  if (!S.d_om_i) {
+    if (dalloc(&S.d_om_i, 2)) return ALPS_B200_ERR_CUDA;
+    const double omi[2] = {0.0, 1.0};
+    CK(cudaMemcpy(S.d_om_i, omi, sizeof(omi), cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpyAsync(S.gd, &S.gh, sizeof(GlobalDev), cudaMemcpyHostToDevice, S.stream));
+  if (dalloc(&S.d_fitems, S.fitems.size())) return ALPS_B200_ERR_CUDA;
+  if (!S.fitems.empty())
+    CK(cudaMemcpyAsync(S.d_fitems, S.fitems.data(), S.fitems.size() * sizeof(FastItem), cudaMemcpyHostToDevice, S.stream));
+  QuadParams P = S.P;
+  P.om = S.d_om_i;
+  P.n_om = 1;
+  P.plan = nullptr;
+  P.Sbulk = nullptr;
+  P.gwin = nullptr;
+  cudaError_t e = launch_quad(P, S.qv.id, true, S.stream);
+  S.launches += 1;
+  if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "hoisted-table launch failed: %s", cudaGetErrorString(e));
+  CK(cudaStreamSynchronize(S.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int ensure_batch(int want) {
   if (S.batch >= want && S.d_om) return 0;
   free_batch();
@@ -291,7 +334,11 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     S.P.om = d_om;
     S.P.n_om = n;
     cudaEventRecord(S.ev0, S.stream);
-    cudaError_t e = launch_quad(S.P, S.qv.id, S.stream);
+    cudaError_t e = cudaSuccess;
+    if (S.mode == 1)
+      launch_fast(gd, d_om, n, S.d_fitems, (int)S.fitems.size(), S.d_plan, S.d_Sbulk, S.d_gwin, S.stream);
+    else
+      e = launch_quad(S.P, S.qv.id, false, S.stream);
     cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.stream);
@@ -403,7 +450,7 @@ void alps_b200_finalize(void) {
   for (int s = 0; s < MAXSPEC; s++) {
     SpeciesHost& h = S.sp[s];
     dfree(&h.d_pperp); dfree(&h.d_ppar); dfree(&h.d_A); dfree(&h.d_C0); dfree(&h.d_Cp); dfree(&h.d_J);
-    dfree(&h.d_W); dfree(&h.d_pf); dfree(&h.d_poly); dfree(&h.d_ee);
+    dfree(&h.d_W); dfree(&h.d_pf); dfree(&h.d_poly); dfree(&h.d_ee); dfree(&h.d_G);
     dfree(&h.d_grel); dfree(&h.d_pbrel); dfree(&h.d_f0rel); dfree(&h.d_dfg); dfree(&h.d_dfp);
     dfree(&h.d_cone_lo); dfree(&h.d_cone_up);
     h = SpeciesHost();
@@ -412,6 +459,8 @@ void alps_b200_finalize(void) {
   dfree(&S.d_pp_f); dfree(&S.d_df0_f); dfree(&S.gd); dfree(&S.d_work_count); dfree(&S.d_err);
   dfree(&S.d_tiles);
   dfree(&S.d_rtiles);
+  dfree(&S.d_fitems);
+  dfree(&S.d_om_i);
   if (S.h_pin) cudaFreeHost(S.h_pin);
   S.h_pin = nullptr;
   S.h_pin_bytes = 0;
@@ -734,6 +783,13 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
   S.P.ntiles = (int)S.tiles.size();
   S.P.g = S.gd;
   S.have_k = true;
+  if (S.mode == 1) {
+    int rc = build_hoisted_tables();
+    if (rc) {
+      S.have_k = false;
+      return rc;
+    }
+  }
   if (nmax_out)
     for (int s = 0; s < nspec; s++) nmax_out[s] = nmax[s];
   return 0;
@@ -911,7 +967,9 @@ int alps_b200_assemble_dev(int n, const double* d_om, const double* d_partial, d
 }
 
 int alps_b200_set_mode(int mode) {
-  if (mode != 0) return fail(ALPS_B200_ERR_UNSUPPORTED, "mode %d not built yet", mode);
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (mode != 0 && mode != 1) return fail(ALPS_B200_ERR_USAGE, "mode must be 0 (direct) or 1 (k-hoisted)");
+  if (mode != S.mode) S.have_k = false;   // the hoisted tables are built by alps_b200_set_k
   S.mode = mode;
   return 0;
 }

@@ -23,6 +23,7 @@ struct QuadParams {
   const PlanEntry* plan;   // n_om * NI
   double* Sbulk;           // n_om * NI * 12
   double* gwin;            // n_om * NI * WINX * 6
+  double* gtab[MAXSPEC];   // k-hoisted tables (STORE launches only)
   int ntiles;
   int n_om;
 };
@@ -50,7 +51,7 @@ struct QuadVariant {
   int stages;
 };
 QuadVariant quad_variant(int id);
-cudaError_t launch_quad(const QuadParams& P, int variant, cudaStream_t st);
+cudaError_t launch_quad(const QuadParams& P, int variant, bool store, cudaStream_t st);
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
                  int* work, int* work_count, cudaStream_t st);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
@@ -62,6 +63,12 @@ void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* o
 void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
                      const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
                      cudaStream_t st);
+struct FastItem {
+  int s;
+  int nabs;
+};
+void launch_fast(const GlobalDev* g, const double* om, int n_om, const FastItem* items, int nitems,
+                 const PlanEntry* plan, double* Sbulk, double* gwin, cudaStream_t st);
 void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
                 int* err_flag, cudaStream_t st);
 void launch_int_ee_rel(const double* pbv, const double* dfp, const int* lo, const int* up, int ng, int npb, double qs,

@@ -96,7 +96,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // PW = 1: dedicated TMA producer warp; PW = 0: thread 0 of consumer warp 0 issues the loads
 // (lets 12 consumer warps = 3 per SM sub-partition keep 168 registers each).
-template <int RG, int BKT, int NST, int PW, int UNR>
+template <int RG, int BKT, int NST, int PW, int UNR, bool STORE>
 __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_constant__ QuadParams P) {
   constexpr int CONSUMER_WARPS = 2 * RG;
   constexpr int BM = 12 * RG;
@@ -235,6 +235,25 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
 
     // ------------------------------------------------------------ epilogue of this p_par tile
     const int ipar0 = nt * BN + 2 * cg + 1;
+    if (STORE) {
+      // k-hoisted tables (alps_b200_set_mode(1)): launched with om = i, so Re = sum w C' (GB) and
+      // Im = sum w A' (GA).  Layout [n][ipar-1][GAa, GBa, GAb, GBb, GAc, GBc].
+      double* gt = P.gtab[tile.s];
+#pragma unroll
+      for (int nn = 0; nn < 4; nn++) {
+        const int nabs = tile.n0 + 4 * rg + nn;
+        if (nabs > sp.nhi_shard) continue;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int ipar = ipar0 + c;
+          if (ipar > npar - 1) continue;
+          double2* o = reinterpret_cast<double2*>(gt + ((size_t)nabs * (npar - 1) + (ipar - 1)) * 6);
+#pragma unroll
+          for (int x = 0; x < 3; x++) o[x] = make_double2(ai[3 * nn + x][c], ar[3 * nn + x][c]);
+        }
+      }
+      continue;
+    }
     double pp_[2];
     pp_[0] = (ipar0 <= npar - 1) ? ppar[ipar0] : 0.0;
     pp_[1] = (ipar0 + 1 <= npar - 1) ? ppar[ipar0 + 1] : 0.0;
@@ -297,6 +316,7 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
     }
   }
 
+  if (STORE) return;
   // ---------------------------------------------------------------- write the moment sums
   asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32) : "memory");
   for (int i = threadIdx.x; i < RG * 96; i += CONSUMER_WARPS * 32) {
@@ -309,18 +329,22 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
 }
 
 // ---------------------------------------------------------------- variants / launcher
-template <int RG, int BKT, int NST, int PW, int UNR>
-static cudaError_t launch_variant(const QuadParams& P, cudaStream_t st) {
+template <int RG, int BKT, int NST, int PW, int UNR, bool STORE>
+static cudaError_t launch_one(const QuadParams& P, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = sizeof(QuadSmem<RG, BKT, NST>) + 128;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(k_quad<RG, BKT, NST, PW, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_quad<RG, BKT, NST, PW, UNR, STORE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_quad<RG, BKT, NST, PW, UNR><<<P.n_om * P.ntiles, (2 * RG + PW) * 32, smem, st>>>(P);
+  k_quad<RG, BKT, NST, PW, UNR, STORE><<<P.n_om * P.ntiles, (2 * RG + PW) * 32, smem, st>>>(P);
   return cudaGetLastError();
+}
+template <int RG, int BKT, int NST, int PW, int UNR>
+static cudaError_t launch_variant(const QuadParams& P, bool store, cudaStream_t st) {
+  return store ? launch_one<RG, BKT, NST, PW, UNR, true>(P, st) : launch_one<RG, BKT, NST, PW, UNR, false>(P, st);
 }
 
 QuadVariant quad_variant(int id) {
@@ -340,21 +364,21 @@ QuadVariant quad_variant(int id) {
   }
 }
 
-cudaError_t launch_quad(const QuadParams& P, int variant, cudaStream_t st) {
+cudaError_t launch_quad(const QuadParams& P, int variant, bool store, cudaStream_t st) {
   if (P.n_om <= 0 || P.ntiles <= 0) return cudaSuccess;
   switch (variant) {
-    case 1: return launch_variant<4, 16, 4, 1, 16>(P, st);
-    case 2: return launch_variant<6, 8, 4, 0, 8>(P, st);
-    case 3: return launch_variant<6, 16, 3, 0, 16>(P, st);
-    case 4: return launch_variant<4, 8, 4, 0, 8>(P, st);
-    case 5: return launch_variant<4, 16, 4, 0, 16>(P, st);
-    case 6: return launch_variant<6, 16, 4, 0, 16>(P, st);
-    case 7: return launch_variant<6, 32, 2, 0, 32>(P, st);
-    case 8: return launch_variant<4, 32, 2, 0, 32>(P, st);
-    case 9: return launch_variant<6, 32, 2, 0, 8>(P, st);
-    case 10: return launch_variant<6, 24, 3, 0, 24>(P, st);
-    case 11: return launch_variant<4, 32, 2, 0, 8>(P, st);
-    default: return launch_variant<4, 8, 4, 1, 8>(P, st);
+    case 1: return launch_variant<4, 16, 4, 1, 16>(P, store, st);
+    case 2: return launch_variant<6, 8, 4, 0, 8>(P, store, st);
+    case 3: return launch_variant<6, 16, 3, 0, 16>(P, store, st);
+    case 4: return launch_variant<4, 8, 4, 0, 8>(P, store, st);
+    case 5: return launch_variant<4, 16, 4, 0, 16>(P, store, st);
+    case 6: return launch_variant<6, 16, 4, 0, 16>(P, store, st);
+    case 7: return launch_variant<6, 32, 2, 0, 32>(P, store, st);
+    case 8: return launch_variant<4, 32, 2, 0, 32>(P, store, st);
+    case 9: return launch_variant<6, 32, 2, 0, 8>(P, store, st);
+    case 10: return launch_variant<6, 24, 3, 0, 24>(P, store, st);
+    case 11: return launch_variant<4, 32, 2, 0, 8>(P, store, st);
+    default: return launch_variant<4, 8, 4, 1, 8>(P, store, st);
   }
 }
 

@@ -9,8 +9,8 @@ reference's formats.  Every D(omega,k) comes from the GPU (libalps_b200.so).
 
 Not reproduced here (out of scope): the LM / Chebyshev fits of
 determine_param_fit -- the analytic-continuation parameters are the generator's ideal values when
-the tables are regenerated, else the initial values of the &ffit blocks; NHDS calc_chi for use_bM
-species; scan_option=2 (om_double_scan)."""
+the tables are regenerated, else the initial values of the &ffit blocks.  NHDS calc_chi for use_bM
+species is the host twin in csrc/nhds.hpp; scan_option=2 (om_double_scan) is not built."""
 from __future__ import annotations
 
 import argparse
@@ -40,7 +40,12 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir="."):
             pc.append(float(f.get("perpcorr", 1.0)))
             par.append([float(f.get("fit_%d" % k, 0.0)) for k in range(1, 6)])
         po = nl.get("poly_spec_%d" % i, {})
-        species.append(tables.Species(ns=float(sp["nn"]), qs=float(sp["qq"]), ms=float(sp["mm"]),
+        bm = nl.get("bm_spec_%d" % i, {})
+        species.append(tables.Species(bM_nmaxs=int(bm.get("bm_nmaxs", 500)),
+                                      bM_Bessel_zeros=float(bm.get("bm_bessel_zeros", 1.0e-50)),
+                                      bM_betas=float(bm.get("bm_betas", 1.0)), bM_alphas=float(bm.get("bm_alphas", 1.0)),
+                                      bM_pdrifts=float(bm.get("bm_pdrifts", 0.0)),
+                                      ns=float(sp["nn"]), qs=float(sp["qq"]), ms=float(sp["mm"]),
                                       relativistic=bool(sp.get("relat", False)), usebM=bool(sp.get("use_bm", False)),
                                       ACmethod=int(sp.get("ac_method", 1)), fit_type=ft, perp_correction=pc,
                                       logfit=bool(sp.get("log_fit", True)), poly_kind=int(po.get("kind", 1)),
@@ -78,6 +83,10 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir="."):
         pp, f0, fits = tables.generate_distribution(specs, nperp, npar, beta=float(ds["beta"]), vA=float(ds["va"]),
                                                     maxP=float(ds["maxp"]))
         for i in range(nspec):
+            if species[i].usebM:       # read_f0 zeroes the tables of use_bM species (src/ALPS_io.f90:672-676)
+                pp[i] = 0.0
+                f0[i] = 0.0
+                continue
             species[i].fit_type = [fits[i]["fit_type"]] if not species[i].relativistic else species[i].fit_type
             species[i].perp_correction = [fits[i]["perpcorr"]]
             for k in range(5):
@@ -113,8 +122,6 @@ def main(argv=None):
     runname = os.path.splitext(os.path.basename(a.input))[0]
     dist_nl = read_namelists(a.dist) if a.dist else None
     pl = plasma_from_inputs(nl, dist_nl, base_dir=os.getcwd())
-    if any(sp.usebM for sp in pl.species):
-        raise SystemExit("use_bM species need NHDS calc_chi (not built yet)")
     s = nl["system"]
     os.makedirs(a.out, exist_ok=True)
     prefix = os.path.join(a.out, runname)

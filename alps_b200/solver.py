@@ -80,6 +80,11 @@ class Solver:
         self.kperp, self.kpar = float(kperp), float(kpar)
         return nmax
 
+    def set_mode(self, mode: int):
+        """0 = direct quadrature per omega (default); 1 = k-hoisted tables ("map fast path").
+        Call set_k afterwards."""
+        _lib.check(self.L.alps_b200_set_mode(mode))
+
     def set_harmonic_shard(self, rank: int, nranks: int):
         _lib.check(self.L.alps_b200_set_harmonic_shard(rank, nranks))
 

@@ -193,3 +193,42 @@ def test_bimax_config_nhds_species():
                 assert chi_err(low_g[s, :, :, 1], low_o[s, :, :, 1]) < TOL
     finally:
         sol.close()
+
+
+def test_fast_path_matches_direct_path_and_oracle():
+    """alps_b200_set_mode(1): the k-hoisted tables give the same chi / D as the direct quadrature
+    (rounding-level differences only) and the same parity against the oracle."""
+    from alps_b200.solver import Solver
+    from oracle.oracle import Oracle
+    pl = tables.config_small(28, 56, kind=2)
+    kperp, kpar = 0.35, 0.06
+    oms = np.array(list(omega_samples(11, 24, (0.02, 1.5), (-0.05, 0.05))) + [0.3 + 0j, 0.011 - 1e-6j])
+    sol = Solver(pl)
+    try:
+        sol.set_k(kperp, kpar)
+        D0, chi_d = sol.disp_batch(oms, want_chi0=True)
+        sol.set_mode(1)
+        sol.set_k(kperp, kpar)
+        D1, chi_f = sol.disp_batch(oms, want_chi0=True)
+        full1 = [sol.disp(complex(om), full=True) for om in oms[:6]]
+        sol.set_mode(0)
+        sol.set_k(kperp, kpar)
+        D2 = sol.disp_batch(oms)
+    finally:
+        sol.close()
+    assert np.array_equal(D0, D2)                      # switching modes back is clean
+    for i in range(oms.size):
+        for s in range(pl.nspec):
+            assert chi_err(chi_f[i, s], chi_d[i, s]) < 1e-11
+    orc = Oracle(pl)
+    orc.set_k(kperp, kpar)
+    for om, (Dg, chi_g, low_g, wave_g) in zip(oms[:6], full1):
+        Do, chi_o, low_o, wave_o = orc.disp(complex(om), full=True)
+        ws = wave_scale(chi_o, complex(om), pl.vA, kperp, kpar)
+        assert scaled_err(wave_g, wave_o, ws) < TOL
+        assert abs(Dg - Do) / det_scale(ws) < TOL
+        for s in range(pl.nspec):
+            assert chi_err(chi_g[s], chi_o[s]) < TOL
+            for m in range(3):
+                if np.max(np.abs(low_o[s, :, :, m])) > 0:
+                    assert chi_err(low_g[s, :, :, m], low_o[s, :, :, m]) < TOL
