@@ -232,3 +232,70 @@ def test_fast_path_matches_direct_path_and_oracle():
             for m in range(3):
                 if np.max(np.abs(low_o[s, :, :, m])) > 0:
                     assert chi_err(low_g[s, :, :, m], low_o[s, :, :, m]) < TOL
+
+
+def _damped(seed, n, re_range):
+    """omegas with Im <= 0 so that the Landau term (eval_fit) is exercised on resonant harmonics"""
+    return list(omega_samples(seed, n, re_range, (-0.05, 0.0))) + [0.5 * (re_range[0] + re_range[1]) + 0j]
+
+
+def test_kperp_norm_false():
+    pl = tables.config_small(24, 48, kind=1)
+    pl.kperp_norm = False
+    _compare(pl, 0.3, 0.05, _damped(21, 5, (0.02, 1.2)) + [0.4 + 0.01j])
+
+
+def test_analytic_continuation_method_0_hardcoded_maxwellians():
+    """ACmethod = 0: distribution_analyt (distribution/distribution_analyt.f90:66-85)"""
+    specs = [tables.DistSpec(ms=1.0), tables.DistSpec(ms=1.0 / 1836.0)]
+    pl = tables.make_plasma(specs, ns=[1.0, 1.0], qs=[1.0, -1.0], nperp=24, npar=48, Bessel_zero=1.0e-30)
+    for s in pl.species:
+        s.ACmethod = 0
+    _compare(pl, 0.3, 0.05, _damped(22, 5, (0.02, 1.2)))
+
+
+def test_analytic_continuation_method_2_chebyshev():
+    """ACmethod = 2: Chebyshev series of log10 f0 per p_perp row (fit_function_poly,
+    src/ALPS_analyt.f90:262-363).  The coefficients are an input (the GLLS fit is out of scope); here they
+    come from numpy's chebfit."""
+    from numpy.polynomial import chebyshev as Ch
+    pl = tables.config_small(24, 48, kind=1)
+    order = 12
+    coeffs = np.zeros((pl.nspec, pl.nperp + 1, order + 1), order="F")
+    for i in range(pl.nspec):
+        ppar = pl.pp[i, 0, :, 1]
+        x = (ppar - 0.5 * (ppar[-1] + ppar[0])) / (0.5 * (ppar[-1] - ppar[0]))
+        for ip in range(pl.nperp + 1):
+            coeffs[i, ip, :] = Ch.chebfit(x, np.log10(pl.f0[i, ip, :]), order)
+    pl.poly_fit_coeffs = coeffs
+    for s in pl.species:
+        s.ACmethod, s.poly_order, s.poly_kind, s.logfit, s.poly_log_max = 2, order, 1, True, 18.0
+    _compare(pl, 0.3, 0.05, _damped(23, 5, (0.02, 1.2)))
+
+
+def test_fit_type_6_bi_moyal():
+    pl = tables.config_small(24, 48, kind=4)
+    _compare(pl, 0.3, 0.05, _damped(24, 4, (0.02, 1.0)))
+
+
+def test_fit_type_3_juettner_nonrelativistic_species():
+    specs = [tables.DistSpec(ms=1.0, distribution=3), tables.DistSpec(ms=0.2, distribution=3)]
+    pl = tables.make_plasma(specs, ns=[1.0, 1.0], qs=[1.0, -1.0], nperp=24, npar=48, vA=0.3, maxP=4.0,
+                            Bessel_zero=1.0e-30)
+    _compare(pl, 0.3, 0.2, _damped(25, 4, (0.05, 1.0)))
+
+
+def test_two_fits_per_species_and_drift():
+    """n_fits = 2 (core + beam Maxwellians summed in fit_function) on a drifting table"""
+    specs = [tables.DistSpec(ms=1.0, drift=0.5), tables.DistSpec(ms=5.44662e-4)]
+    pl = tables.make_plasma(specs, ns=[1.0, 1.0], qs=[1.0, -1.0], nperp=24, npar=48, Bessel_zero=1.0e-30)
+    pf = np.zeros((2, pl.nperp + 1, 5, 2), order="F")
+    pf[:, :, :, 0] = pl.param_fit[:, :, :, 0]
+    pf[0, :, 0, 0] *= 0.7                       # split the proton Maxwellian into two components
+    pf[0, :, :, 1] = pl.param_fit[0, :, :, 0]
+    pf[0, :, 0, 1] *= 0.3
+    pl.param_fit = pf
+    pl.species[0].fit_type = [1, 1]
+    pl.species[0].perp_correction = [pl.species[0].perp_correction[0]] * 2
+    pl.species[1].fit_type = [1]
+    _compare(pl, 0.3, 0.05, _damped(26, 4, (0.02, 1.2)))
