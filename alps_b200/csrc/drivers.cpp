@@ -713,4 +713,169 @@ int alps_b200_om_scan(const alps_b200_scan* sc, int nroots, double* wroots, cons
   });
 }
 
+// k of scan step `it` starting from (kperp0, kpar0): the select case blocks of om_scan / om_double_scan
+static void scan_k_at(const alps_b200_scan* sc, int it, double kperp0, double kpar0, double* kperp, double* kpar) {
+  const double theta_0 = atan(kperp0 / kpar0), k_0 = sqrt(kperp0 * kperp0 + kpar0 * kpar0);
+  switch (sc->type) {
+    case 0:
+      if (sc->log_scan) {
+        *kperp = pow(10.0, log10(kperp0) + sc->diff * it);
+        *kpar = pow(10.0, log10(kpar0) + sc->diff2 * it);
+      } else {
+        *kperp = kperp0 + sc->diff * it;
+        *kpar = kpar0 + sc->diff2 * it;
+      }
+      break;
+    case 1: {
+      double theta_1 = sc->log_scan ? pow(10.0, log10(theta_0) + sc->diff * it) : theta_0 + sc->diff * it;
+      *kperp = k_0 * sin(theta_1);
+      *kpar = k_0 * cos(theta_1);
+      break;
+    }
+    case 2: {
+      double k_tmp = sc->log_scan ? pow(10.0, log10(k_0) + sc->diff * it) : k_0 + sc->diff * it;
+      *kperp = k_tmp * sin(theta_0);
+      *kpar = k_tmp * cos(theta_0);
+      break;
+    }
+    case 3: *kperp = sc->log_scan ? pow(10.0, log10(kperp0) + sc->diff * it) : kperp0 + sc->diff * it; break;
+    default: *kpar = sc->log_scan ? pow(10.0, log10(kpar0) + sc->diff * it) : kpar0 + sc->diff * it; break;
+  }
+}
+
+// replaces: om_double_scan, src/ALPS_fns.f90:2904-3591
+int alps_b200_om_double_scan(const alps_b200_scan* sc1, const alps_b200_scan* sc2, int nroots, double* wroots,
+                             const alps_b200_solver_opts* o, int nspec, const double* ns, const double* qs,
+                             const double* current_int, double vA, double* kperp_io, double* kpar_io,
+                             const char* prefix, double* rows_out) {
+  return guarded([&] {
+    static const char* ids[5] = {"k1_k2", "theta", "kcstq", "kperp", "kpara"};
+    if (sc1->type == sc2->type) throw DispError{5};          // alps_error(5)
+    if (sc1->type == 0 || sc2->type == 0) throw DispError{6};  // alps_error(6)
+    double kperp = *kperp_io, kpar = *kpar_io;
+    const int nt = sc1->n_out * sc1->n_res, nt2 = sc2->n_out * sc2->n_res;
+    const bool want = sc1->eigen || sc1->heat;
+    std::vector<bool> jump(nroots, true);
+    auto fname = [&](const char* kind, int in) {
+      char b[1024];
+      snprintf(b, sizeof(b), "%s.%s_%s_%s.root_%d", prefix, kind, ids[sc1->type], ids[sc2->type], in + 1);
+      return std::string(b);
+    };
+    auto head = [&](int in) { return es14(kperp) + es14(kpar) + es14(wroots[2 * in]) + es14(wroots[2 * in + 1]); };
+    auto lines = [&](int in, const Eigen& E, std::string& le, std::string& lh, std::string& lm) {
+      le = lh = lm = head(in);
+      for (int q = 0; q < 3; q++) le += es14(E.ef[q].real()) + es14(E.ef[q].imag());
+      for (int q = 0; q < 3; q++) le += es14(E.bf[q].real()) + es14(E.bf[q].imag());
+      for (auto& u : E.Us) le += es14(u.real()) + es14(u.imag());
+      for (auto& d : E.ds) le += es14(d.real()) + es14(d.imag());
+      for (double p : E.Ps) lh += es14(p);
+      lh += es14(E.W_EM);
+      for (double p : E.Ps_split) lm += es14(p);
+      le += "\n"; lh += "\n"; lm += "\n";
+    };
+    if (prefix)
+      for (int in = 0; in < nroots; in++) {
+        append_line(fname("scan", in), "", true);
+        if (sc1->eigen) append_line(fname("eigen", in), "", true);
+        if (sc1->heat) {
+          append_line(fname("heat", in), "", true);
+          append_line(fname("heat_mech", in), "", true);
+        }
+      }
+    const double kperp_last = kperp, kpar_last = kpar;
+    std::vector<std::complex<float> > omlast(nroots);   // single-precision COMPLEX in the reference (line 2979)
+    for (int in = 0; in < nroots; in++) omlast[in] = std::complex<float>((float)wroots[2 * in], (float)wroots[2 * in + 1]);
+    size_t row = 0;
+    const int cols = sc2->n_out + 1;
+    for (int it = 0; it <= nt; it++) {
+      scan_k_at(sc1, it, kperp_last, kpar_last, &kperp, &kpar);
+      int rc = alps_b200_set_k(kperp, kpar, nullptr);
+      if (rc) throw DispError{rc};
+      bool alljump = false;
+      for (int in = 0; in < nroots; in++) alljump = alljump || jump[in];
+      if (!alljump) throw DispError{9};
+      for (int in = 0; in < nroots; in++) {
+        if (!jump[in]) continue;
+        cplx omega((double)omlast[in].real(), (double)omlast[in].imag());
+        wroots[2 * in] = omega.real();
+        wroots[2 * in + 1] = omega.imag();
+        omega = solve_root(omega, *o);
+        wroots[2 * in] = omega.real();
+        wroots[2 * in + 1] = omega.imag();
+        omlast[in] = std::complex<float>((float)omega.real(), (float)omega.imag());
+        if (std::isnan(omega.real())) jump[in] = false;
+        for (int imm = 0; imm < in; imm++)
+          if (std::abs(cplx(wroots[2 * in], wroots[2 * in + 1]) - cplx(wroots[2 * imm], wroots[2 * imm + 1])) < o->D_gap) {
+            wroots[2 * in] = wroots[2 * in + 1] = 0.0;
+            jump[in] = false;
+          }
+      }
+      if (it % sc1->n_res != 0) continue;
+      double kperpi = kperp, kpari = kpar;
+      size_t col = 0;
+      for (int it2 = 0; it2 <= nt2; it2++) {
+        if (it2 == 0)
+          for (int in = 0; in < nroots; in++) {
+            wroots[2 * in] = (double)omlast[in].real();
+            wroots[2 * in + 1] = (double)omlast[in].imag();
+          }
+        scan_k_at(sc2, it2, kperpi, kpari, &kperp, &kpar);
+        rc = alps_b200_set_k(kperp, kpar, nullptr);
+        if (rc) throw DispError{rc};
+        const bool out_step = (it2 % sc2->n_res) == 0;
+        for (int in = 0; in < nroots; in++) {
+          if (!jump[in]) continue;
+          cplx omega = solve_root(cplx(wroots[2 * in], wroots[2 * in + 1]), *o);
+          wroots[2 * in] = omega.real();
+          wroots[2 * in + 1] = omega.imag();
+          const cplx tmp = disp1(omega);
+          Eigen E;
+          if (out_step && want)
+            calc_eigen_impl(omega, nspec, ns, qs, current_int, kperp, kpar, vA, sc1->eigen != 0, sc1->heat != 0, E);
+          if (std::isnan(omega.real())) jump[in] = false;
+          if (std::abs(tmp) > 1.e100) jump[in] = false;
+          for (int imm = 0; imm < in; imm++)
+            if (std::abs(cplx(wroots[2 * in], wroots[2 * in + 1]) - cplx(wroots[2 * imm], wroots[2 * imm + 1])) < o->D_gap) {
+              wroots[2 * in] = wroots[2 * in + 1] = 0.0;
+              jump[in] = false;
+            }
+          if (out_step) {
+            if (prefix) {
+              append_line(fname("scan", in), head(in) + "\n");
+              if (want) {
+                std::string le, lh, lm;
+                lines(in, E, le, lh, lm);
+                if (sc1->eigen) append_line(fname("eigen", in), le);
+                if (sc1->heat) {
+                  append_line(fname("heat", in), lh);
+                  append_line(fname("heat_mech", in), lm);
+                }
+              }
+            }
+            if (rows_out) {
+              double* r = rows_out + 4 * ((row * cols + col) * nroots + in);
+              r[0] = kperp; r[1] = kpar; r[2] = wroots[2 * in]; r[3] = wroots[2 * in + 1];
+            }
+          }
+        }
+        if (out_step) col++;
+      }
+      if (prefix)
+        for (int in = 0; in < nroots; in++) {
+          append_line(fname("scan", in), "\n");
+          if (sc1->eigen) append_line(fname("eigen", in), "\n");
+          if (sc1->heat) {
+            append_line(fname("heat", in), "\n");
+            append_line(fname("heat_mech", in), "\n");
+          }
+        }
+      row++;
+      // reset the second scan's variable to its start value (lines 3535-3580)
+      scan_k_at(sc2, 0, kperp_last, kpar_last, &kperp, &kpar);
+    }
+    *kperp_io = kperp;
+    *kpar_io = kpar;
+  });
+}
+
 }  // extern "C"

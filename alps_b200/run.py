@@ -10,7 +10,7 @@ reference's formats.  Every D(omega,k) comes from the GPU (libalps_b200.so).
 Not reproduced here (out of scope): the LM / Chebyshev fits of
 determine_param_fit -- the analytic-continuation parameters are the generator's ideal values when
 the tables are regenerated, else the initial values of the &ffit blocks.  NHDS calc_chi for use_bM
-species is the host twin in csrc/nhds.hpp; scan_option=2 (om_double_scan) is not built."""
+species is the host twin in csrc/nhds.hpp."""
 from __future__ import annotations
 
 import argparse
@@ -154,6 +154,13 @@ def main(argv=None):
                                       bool(sc["swlog"]), int(sc["ns"]), int(sc.get("nres", 1)),
                                       bool(sc.get("eigen", False)), bool(sc.get("heating", False)), prefix, ik)
                 print("scan %d done: k=(%g,%g)" % (ik, sol.kperp, sol.kpar))
+        elif int(s.get("n_scan", 0)) == 2 and int(s.get("scan_option", 1)) == 2 and len(w):
+            def blk(ik):
+                sc = nl["scan_input_%d" % ik]
+                return dict(scan_type=sc["scan_type"], swi=sc["swi"], swf=sc["swf"], swlog=sc["swlog"], ns=sc["ns"],
+                            nres=sc.get("nres", 1), eigen=sc.get("eigen", False), heat=sc.get("heating", False))
+            rows, w = sol.om_double_scan(w, opts, blk(1), blk(2), prefix)
+            print("double scan done: %d x %d points" % rows.shape[:2])
     finally:
         sol.close()
     return 0

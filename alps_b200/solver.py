@@ -233,6 +233,32 @@ class Solver:
         self.kperp, self.kpar = kperp.value, kpar.value
         return rows, w
 
+    def om_double_scan(self, wroots, opts, scan1, scan2, prefix=None):
+        """scan_option=2 (src/ALPS_fns.f90:2904-3591).  scan1/scan2: dicts with scan_type, swi, swf, swlog,
+        ns, nres, eigen, heat (the &scan_input_1/2 blocks, read in that order like scan_read does)."""
+        pl = self.pl
+        kpl, kql = C.c_double(self.kperp), C.c_double(self.kpar)
+        scs = []
+        for sc in (scan1, scan2):
+            c = _lib.ScanCfg()
+            _lib.check(self.L.alps_b200_scan_setup(int(sc["scan_type"]), float(sc["swi"]), float(sc["swf"]),
+                                                   int(sc["swlog"]), int(sc["ns"]), int(sc.get("nres", 1)),
+                                                   int(sc.get("eigen", False)), int(sc.get("heat", False)),
+                                                   C.byref(kpl), C.byref(kql), C.byref(c)))
+            scs.append(c)
+        w = np.ascontiguousarray(np.asarray(wroots, dtype=np.complex128).ravel())
+        ns = np.array([s.ns for s in pl.species])
+        qs = np.array([s.qs for s in pl.species])
+        ci = self.current_int()
+        kperp, kpar = C.c_double(self.kperp), C.c_double(self.kpar)
+        rows = np.zeros((int(scan1["ns"]) + 1, int(scan2["ns"]) + 1, w.size, 4))
+        _lib.check(self.L.alps_b200_om_double_scan(C.byref(scs[0]), C.byref(scs[1]), w.size, _p(w.view(np.float64)),
+                                                   C.byref(opts), pl.nspec, _p(ns), _p(qs), _p(ci), pl.vA,
+                                                   C.byref(kperp), C.byref(kpar),
+                                                   prefix.encode() if prefix else None, _p(rows)))
+        self.kperp, self.kpar = kperp.value, kpar.value
+        return rows, w
+
     # ---- plumbing
     def set_stream(self, stream_ptr: Optional[int]):
         _lib.check(self.L.alps_b200_set_stream(C.c_void_p(stream_ptr or 0)))

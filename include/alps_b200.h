@@ -188,6 +188,15 @@ int alps_b200_om_scan(const alps_b200_scan *sc, int nroots, double *wroots,
                       const double *current_int, double vA, double *kperp_io, double *kpar_io,
                       const char *prefix, int ik, double *rows_out);
 
+/* replaces: om_double_scan (:2904-3591, scan_option=2): for every output step of scan 1 a full scan 2;
+ * writes <prefix>.scan_<id1>_<id2>.root_<in> (+ .eigen_, .heat_, .heat_mech_).  The outer guesses are kept
+ * in single precision like the reference's `complex :: omlast`.  rows_out (may be NULL):
+ * (n_out1+1) x (n_out2+1) x nroots x 4 doubles. */
+int alps_b200_om_double_scan(const alps_b200_scan *sc1, const alps_b200_scan *sc2, int nroots,
+                             double *wroots, const alps_b200_solver_opts *o, int nspec, const double *ns,
+                             const double *qs, const double *current_int, double vA, double *kperp_io,
+                             double *kpar_io, const char *prefix, double *rows_out);
+
 /* Host-only helper (no GPU needed): determine_nmax's "more processes than harmonics" adjustment
  * and split_processes (src/ALPS_fns.f90:4048-4064, 4079-4207) for an emulated MPI size nproc.
  * nmax[nspec] is updated in place; nhi[nspec] receives the highest harmonic any rank sums. */

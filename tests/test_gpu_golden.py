@@ -114,3 +114,40 @@ def test_cli_twin_of_the_main_program(tmp_path):
     for kind in ("eigen", "heat", "heat_mech"):
         assert os.path.exists(os.path.join(out, "test_kpar_fast.%s_kpara_1.root_1" % kind))
     assert os.path.exists(os.path.join(out, "test_kpar_fast.roots"))
+
+
+def test_double_scan_rows_are_single_scans(tmp_path):
+    """scan_option=2 (om_double_scan, src/ALPS_fns.f90:2904-3591) on a shortened tests/test_double_scan.in:
+    every outer row is an inner k_perp scan started from the outer k_par root (kept in single precision
+    like the reference's `complex :: omlast`)."""
+    from alps_b200.solver import Solver
+    pl = tables.config_kpar_fast()
+    n1, n2 = 2, 3
+    s1 = dict(scan_type=4, swi=1.0e-3, swf=2.0e-3, swlog=True, ns=n1)
+    s2 = dict(scan_type=3, swi=1.0e-2, swf=3.0e-2, swlog=True, ns=n2)
+    sol = Solver(pl, emulate_nproc=4)
+    try:
+        opts = sol.opts(numiter=30, D_threshold=1.0e-30, D_prec=1.0e-5)
+        sol.set_k(1.0e-2, 1.0e-3)
+        w0, _ = sol.refine_guess([complex(9.9e-4, -5.5e-10)], opts)
+        prefix = str(tmp_path / "t")
+        rows, w = sol.om_double_scan(w0.copy(), opts, s1, s2, prefix)
+        assert rows.shape == (n1 + 1, n2 + 1, 1, 4)
+        # outer row 0 == a plain k_perp scan from the (float-rounded) refined root
+        sol.set_k(1.0e-2, 1.0e-3)
+        start = complex(np.complex64(w0[0]))
+        start = sol.secant_osc(start, opts)[0]
+        start = complex(np.complex64(start))
+        r1, _ = sol.om_scan([start], opts, scan_type=3, swi=1.0e-2, swf=3.0e-2, swlog=True, ns_steps=n2)
+    finally:
+        sol.close()
+    for j in range(n2 + 1):
+        a = complex(rows[0, j, 0, 2], rows[0, j, 0, 3])
+        b = complex(r1[j, 0, 2], r1[j, 0, 3])
+        assert abs(rows[0, j, 0, 0] - r1[j, 0, 0]) < 1e-15 and rows[0, j, 0, 1] == r1[j, 0, 1]
+        assert abs(a - b) < 1e-7 * abs(b), (j, a, b)
+    # k grid: k_par varies along the outer index only, k_perp along the inner only
+    assert np.allclose(rows[:, 0, 0, 1], [1.0e-3 * 2 ** (i / n1) for i in range(n1 + 1)], rtol=1e-12)
+    assert np.allclose(rows[1, :, 0, 0], [1.0e-2 * 3 ** (j / n2) for j in range(n2 + 1)], rtol=1e-12)
+    text = open(prefix + ".scan_kpara_kperp.root_1").read().split("\n")
+    assert [len(l) for l in text[: n2 + 2]] == [56] * (n2 + 1) + [0]     # 4es14.4e3 rows + blank line per outer step
