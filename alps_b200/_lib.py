@@ -20,7 +20,7 @@ SYMBOLS = [
     "alps_b200_get_info", "alps_b200_dfma_peak", "alps_b200_emulate_split",
     "alps_b200_secant", "alps_b200_secant_osc", "alps_b200_rtsec", "alps_b200_refine_guess",
     "alps_b200_map_search", "alps_b200_calc_eigen", "alps_b200_scan_setup", "alps_b200_om_scan",
-    "alps_b200_om_double_scan",
+    "alps_b200_om_double_scan", "alps_b200_set_root_batching",
 ]
 
 INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH = range(5)
@@ -109,6 +109,7 @@ def lib():
         L.alps_b200_om_scan.argtypes = [V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V,
                                         C.c_char_p, C.c_int, V]
         L.alps_b200_om_double_scan.argtypes = [V, V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V, C.c_char_p, V]
+        L.alps_b200_set_root_batching.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 

@@ -11,7 +11,11 @@
 #include <string.h>
 
 #include <complex>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/alps_b200.h"
@@ -25,11 +29,120 @@ struct DispError {
   int code;
 };
 
+// ---------------------------------------------------------------------------- root batching
+// The reference refines its roots one after the other; every iteration of every root is one
+// latency-bound disp() call.  With batching on, each root's *unchanged serial algorithm* runs on its
+// own host thread, and a broker collects the D requests of all roots that are waiting and serves
+// them with one alps_b200_disp_batch launch.  Per-root results are bit-identical to the serial order
+// (disp_batch and disp agree bitwise); only the latency is shared.
+struct Broker {
+  struct Req {
+    cplx om, D;
+    double *chi0 = nullptr, *chi0_low = nullptr, *wave = nullptr;   // full request if chi0 != nullptr
+    bool pending = false;
+    int rc = 0;
+  };
+  std::mutex m;
+  std::condition_variable cv_broker, cv_worker;
+  std::vector<Req> reqs;
+  int active = 0;
+
+  cplx request(int id, cplx om, double* chi0, double* chi0_low, double* wave) {
+    std::unique_lock<std::mutex> lk(m);
+    Req& r = reqs[id];
+    r.om = om; r.chi0 = chi0; r.chi0_low = chi0_low; r.wave = wave; r.pending = true; r.rc = 0;
+    cv_broker.notify_one();
+    cv_worker.wait(lk, [&] { return !r.pending; });
+    if (r.rc) throw DispError{r.rc};
+    return r.D;
+  }
+  void finish() {
+    std::lock_guard<std::mutex> lk(m);
+    active--;
+    cv_broker.notify_one();
+  }
+  // run the jobs (one per root) concurrently, serving their disp requests in batches
+  void run(const std::vector<std::function<void()> >& jobs);
+};
+thread_local Broker* tl_broker = nullptr;
+thread_local int tl_id = 0;
+bool g_root_batching = false;
+
 cplx disp1(cplx om) {
+  if (tl_broker) return tl_broker->request(tl_id, om, nullptr, nullptr, nullptr);
   double o[2] = {om.real(), om.imag()}, D[2] = {0, 0};
   int rc = alps_b200_disp(o, D, nullptr, nullptr, nullptr);
   if (rc) throw DispError{rc};
   return cplx(D[0], D[1]);
+}
+
+void Broker::run(const std::vector<std::function<void()> >& jobs) {
+  const int n = (int)jobs.size();
+  reqs.assign(n, Req());
+  active = n;
+  std::vector<std::thread> th;
+  std::vector<int> err(n, 0);
+  for (int i = 0; i < n; i++)
+    th.emplace_back([&, i] {
+      tl_broker = this;
+      tl_id = i;
+      try {
+        jobs[i]();
+      } catch (const DispError& e) {
+        err[i] = e.code;
+      }
+      tl_broker = nullptr;
+      finish();
+    });
+  std::vector<double> om, D;
+  std::vector<int> ids;
+  for (;;) {
+    std::unique_lock<std::mutex> lk(m);
+    cv_broker.wait(lk, [&] {
+      int pend = 0;
+      for (auto& r : reqs) pend += r.pending ? 1 : 0;
+      return active == 0 || pend == active;
+    });
+    if (active == 0) break;
+    om.clear();
+    ids.clear();
+    for (int i = 0; i < n; i++)
+      if (reqs[i].pending && !reqs[i].chi0) {
+        ids.push_back(i);
+        om.push_back(reqs[i].om.real());
+        om.push_back(reqs[i].om.imag());
+      }
+    int rc = 0;
+    if (!ids.empty()) {
+      D.assign(om.size(), 0.0);
+      rc = alps_b200_disp_batch((int)ids.size(), om.data(), D.data(), nullptr);
+      for (size_t q = 0; q < ids.size(); q++) {
+        reqs[ids[q]].D = cplx(D[2 * q], D[2 * q + 1]);
+        reqs[ids[q]].rc = rc;
+      }
+    }
+    for (int i = 0; i < n; i++)
+      if (reqs[i].pending && reqs[i].chi0) {   // calc_eigen needs chi0, chi0_low, wave: served one by one
+        double o[2] = {reqs[i].om.real(), reqs[i].om.imag()}, d[2] = {0, 0};
+        reqs[i].rc = alps_b200_disp(o, d, reqs[i].chi0, reqs[i].chi0_low, reqs[i].wave);
+        reqs[i].D = cplx(d[0], d[1]);
+      }
+    for (auto& r : reqs) r.pending = false;
+    cv_worker.notify_all();
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; i++)
+    if (err[i]) throw DispError{err[i]};
+}
+
+// run one job per root, concurrently through the broker when batching is on
+void for_each_root(const std::vector<std::function<void()> >& jobs) {
+  if (g_root_batching && jobs.size() > 1 && !tl_broker) {
+    Broker b;
+    b.run(jobs);
+  } else {
+    for (auto& j : jobs) j();
+  }
 }
 
 // Fortran ESw.dEe edit descriptor (e.g. es14.4e3 -> "   1.0000E-002")
@@ -205,6 +318,11 @@ struct Tensors {
 };
 
 void disp_full(cplx om, Tensors& t) {
+  if (tl_broker) {
+    tl_broker->request(tl_id, om, reinterpret_cast<double*>(t.chi0.data()),
+                       reinterpret_cast<double*>(t.chi0_low.data()), reinterpret_cast<double*>(t.wave));
+    return;
+  }
   double o[2] = {om.real(), om.imag()}, D[2];
   int rc = alps_b200_disp(o, D, reinterpret_cast<double*>(t.chi0.data()),
                           reinterpret_cast<double*>(t.chi0_low.data()), reinterpret_cast<double*>(t.wave));
@@ -423,11 +541,19 @@ int alps_b200_refine_guess(int nroots, double* wroots, const alps_b200_solver_op
                            double* D_out) {
   return guarded([&] {
     if (roots_path) append_line(roots_path, "", true);
+    std::vector<cplx> sol(nroots), dsol(nroots);
+    std::vector<std::function<void()> > jobs;
+    for (int iw = 0; iw < nroots; iw++)
+      jobs.push_back([&, iw] {
+        sol[iw] = solve_root(cplx(wroots[2 * iw], wroots[2 * iw + 1]), *o);
+        dsol[iw] = disp1(sol[iw]);
+      });
+    for_each_root(jobs);
     for (int iw = 0; iw < nroots; iw++) {
-      cplx om = solve_root(cplx(wroots[2 * iw], wroots[2 * iw + 1]), *o);
+      cplx om = sol[iw];
       wroots[2 * iw] = om.real();
       wroots[2 * iw + 1] = om.imag();
-      cplx d = disp1(om);
+      cplx d = dsol[iw];
       if (D_out) {
         D_out[2 * iw] = d.real();
         D_out[2 * iw + 1] = d.imag();
@@ -539,6 +665,11 @@ int alps_b200_calc_eigen(const double om[2], int nspec, const double* ns, const 
     for (size_t i = 0; i < E.Ps_split.size() && Ps_split; i++) Ps_split[i] = E.Ps_split[i];
     if (W_EM) *W_EM = E.W_EM;
   });
+}
+
+int alps_b200_set_root_batching(int on) {
+  g_root_batching = on != 0;
+  return 0;
 }
 
 int alps_b200_scan_setup(int scan_type, double swi, double swf, int swlog, int ns, int nres, int eigen, int heat,
@@ -677,15 +808,27 @@ int alps_b200_om_scan(const alps_b200_scan* sc, int nroots, double* wroots, cons
       bool alljump = false;
       for (int in = 0; in < nroots; in++) alljump = alljump || jump[in];
       if (!alljump) throw DispError{9};   // alps_error(9)
+      const bool out_step = (it % sc->n_res) == 0;
+      std::vector<Eigen> Es(nroots);
+      std::vector<cplx> sol(nroots);
+      {
+        std::vector<std::function<void()> > jobs;
+        for (int in = 0; in < nroots; in++) {
+          if (!jump[in]) continue;
+          jobs.push_back([&, in] {
+            sol[in] = solve_root(cplx(wroots[2 * in], wroots[2 * in + 1]), *o);
+            if (out_step && want)
+              calc_eigen_impl(sol[in], nspec, ns, qs, current_int, kperp, kpar, vA, sc->eigen != 0, sc->heat != 0, Es[in]);
+          });
+        }
+        for_each_root(jobs);
+      }
       for (int in = 0; in < nroots; in++) {
         if (!jump[in]) continue;
-        cplx omega = solve_root(cplx(wroots[2 * in], wroots[2 * in + 1]), *o);
+        const cplx omega = sol[in];
         wroots[2 * in] = omega.real();
         wroots[2 * in + 1] = omega.imag();
-        Eigen E;
-        const bool out_step = (it % sc->n_res) == 0;
-        if (out_step && want)
-          calc_eigen_impl(omega, nspec, ns, qs, current_int, kperp, kpar, vA, sc->eigen != 0, sc->heat != 0, E);
+        const Eigen& E = Es[in];
         if (std::isnan(omega.real())) jump[in] = false;
         for (int imm = 0; imm < in; imm++) {
           cplx a(wroots[2 * in], wroots[2 * in + 1]), b(wroots[2 * imm], wroots[2 * imm + 1]);

@@ -233,6 +233,10 @@ class Solver:
         self.kperp, self.kpar = kperp.value, kpar.value
         return rows, w
 
+    def set_root_batching(self, on: bool):
+        """advance all roots of a k step concurrently (one disp_batch per iteration); same results"""
+        _lib.check(self.L.alps_b200_set_root_batching(int(on)))
+
     def om_double_scan(self, wroots, opts, scan1, scan2, prefix=None):
         """scan_option=2 (src/ALPS_fns.f90:2904-3591).  scan1/scan2: dicts with scan_type, swi, swf, swlog,
         ns, nres, eigen, heat (the &scan_input_1/2 blocks, read in that order like scan_read does)."""

@@ -178,6 +178,11 @@ int alps_b200_calc_eigen(const double om[2], int nspec, const double *ns, const 
                          const double *current_int, double kperp, double kpar, double vA, int eigen,
                          int heat, double *ef, double *bf, double *Us, double *ds, double *Ps,
                          double *Ps_split, double *W_EM);
+/* Root batching: with on != 0, refine_guess and om_scan advance all roots of a k step concurrently --
+ * each root runs the unchanged serial algorithm on a host thread and the D requests of all waiting
+ * roots are served by one alps_b200_disp_batch launch.  Results per root are bit-identical. */
+int alps_b200_set_root_batching(int on);
+
 /* replaces: scan_read step sizes (src/ALPS_io.f90:472-549); updates kperp_last / kpar_last */
 int alps_b200_scan_setup(int scan_type, double swi, double swf, int swlog, int ns, int nres, int eigen,
                          int heat, double *kperp_last, double *kpar_last, alps_b200_scan *out);

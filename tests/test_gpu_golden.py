@@ -151,3 +151,35 @@ def test_double_scan_rows_are_single_scans(tmp_path):
     assert np.allclose(rows[1, :, 0, 0], [1.0e-2 * 3 ** (j / n2) for j in range(n2 + 1)], rtol=1e-12)
     text = open(prefix + ".scan_kpara_kperp.root_1").read().split("\n")
     assert [len(l) for l in text[: n2 + 2]] == [56] * (n2 + 1) + [0]     # 4es14.4e3 rows + blank line per outer step
+
+
+def test_root_batching_is_bit_identical_to_the_serial_order():
+    """alps_b200_set_root_batching: all roots advance concurrently (one disp_batch per iteration), each
+    root still runs the reference's serial secant_osc -- the refined roots and the k scan are identical."""
+    import time
+    from alps_b200.solver import Solver
+    pl = tables.config_kpar_fast()
+    sol = Solver(pl, emulate_nproc=4)
+    try:
+        sol.set_k(1.0e-2, 1.0e-2)
+        opts = sol.opts(numiter=40, D_threshold=1.0e-15, D_prec=1.0e-5)
+        guesses = [complex(9.9e-3, -5.5e-6), complex(1.2e-2, -1.0e-4), complex(2.0e-2, -5.0e-4),
+                   complex(5.0e-3, -2.0e-4), complex(3.0e-2, -1.0e-3), complex(1.0e-2, -3.0e-3)]
+        t0 = time.perf_counter()
+        w_ser, D_ser = sol.refine_guess(guesses, opts)
+        rows_ser, _ = sol.om_scan(w_ser.copy(), opts, scan_type=4, swi=1.0e-3, swf=2.0e-2, swlog=True, ns_steps=4,
+                                  eigen=True, heat=True)
+        t_ser = time.perf_counter() - t0
+        sol.set_k(1.0e-2, 1.0e-2)
+        sol.set_root_batching(True)
+        t0 = time.perf_counter()
+        w_bat, D_bat = sol.refine_guess(guesses, opts)
+        rows_bat, _ = sol.om_scan(w_bat.copy(), opts, scan_type=4, swi=1.0e-3, swf=2.0e-2, swlog=True, ns_steps=4,
+                                  eigen=True, heat=True)
+        t_bat = time.perf_counter() - t0
+        sol.set_root_batching(False)
+    finally:
+        sol.close()
+    assert np.array_equal(w_ser, w_bat) and np.array_equal(D_ser, D_bat)
+    assert np.array_equal(rows_ser, rows_bat)
+    print("serial %.3f s, batched %.3f s" % (t_ser, t_bat))
