@@ -243,6 +243,7 @@ int build_hoisted_tables() {
   QuadParams P = S.P;
   P.om = S.d_om_i;
   P.n_om = 1;
+  P.nsplit = 1;
   P.plan = nullptr;
   P.Sbulk = nullptr;
   P.gwin = nullptr;
@@ -254,11 +255,19 @@ int build_hoisted_tables() {
   return 0;
 }
 
+constexpr int SMALL_BATCH = 64;
+int nsplit_small() {
+  const int NT = (S.cfg.npar - 1 + BN - 1) / BN;
+  return std::max(1, std::min(NT, (2 * S.sm_count) / std::max(1, (int)S.tiles.size())));
+}
+
 int ensure_batch(int want) {
   if (S.batch >= want && S.d_om) return 0;
   free_batch();
   const size_t NI = S.gh.NI, B = want;
-  if (dalloc(&S.d_om, 2 * B) || dalloc(&S.d_D, 2 * B) || dalloc(&S.d_Sbulk, B * NI * 12) ||
+  // Sbulk rows: n * nsplit(n) <= max(B, SMALL_BATCH * nsplit_small()) (see run_chunk)
+  if (dalloc(&S.d_om, 2 * B) || dalloc(&S.d_D, 2 * B) ||
+      dalloc(&S.d_Sbulk, std::max(B, (size_t)SMALL_BATCH * nsplit_small()) * NI * 12) ||
       dalloc(&S.d_Sres, B * NI * 12) || dalloc(&S.d_gwin, B * NI * S.gh.WINX * 6) ||
       dalloc(&S.d_partial, B * S.gh.nspec * PARTIAL_PER_SPEC) || dalloc(&S.d_chi0, B * S.gh.nspec * 18) ||
       dalloc(&S.d_chi0_low, B * S.gh.nspec * 54) || dalloc(&S.d_wave, B * 18) || dalloc(&S.d_plan, B * NI) ||
@@ -333,6 +342,10 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     launch_plan(gd, S.gh, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream);
     S.P.om = d_om;
     S.P.n_om = n;
+    // few omegas in flight (sequential root finding, batched roots): spread each (omega, tile) over
+    // several CTAs along p_par.  The split depends only on the configuration for n <= SMALL_BATCH, so a
+    // single disp() and a small disp_batch() give bitwise identical D.
+    S.P.nsplit = (S.mode == 1 || n > SMALL_BATCH) ? 1 : nsplit_small();
     cudaEventRecord(S.ev0, S.stream);
     cudaError_t e = cudaSuccess;
     if (S.mode == 1)
@@ -347,7 +360,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       S.launches += 1;
     }
     double* part = d_partial_out ? d_partial_out : S.d_partial;
-    launch_chi_partial(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.d_Sres, part, S.stream);
+    launch_chi_partial(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, part, S.stream);
     S.launches += 4;
     if (d_partial_out) return 0;
     d_partial_in = part;

@@ -26,6 +26,7 @@ struct QuadParams {
   double* gtab[MAXSPEC];   // k-hoisted tables (STORE launches only)
   int ntiles;
   int n_om;
+  int nsplit;              // CTAs per (omega, tile) along p_par; Sbulk then holds nsplit partial rows per item
 };
 
 // set-up (setup_kernels.cu)
@@ -59,7 +60,7 @@ void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanE
 // chi partial layout per omega: [nspec][PARTIAL_PER_SPEC] doubles (see resonant.cu)
 constexpr int PARTIAL_PER_SPEC = 2 * (6 + 18);   // chi(6 modes) + chi_low(6 modes x 3) complex
 void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
-                        const double* Sbulk, const double* Sres, double* partial, cudaStream_t st);
+                        const double* Sbulk, int nsplit, const double* Sres, double* partial, cudaStream_t st);
 void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
                      const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
                      cudaStream_t st);

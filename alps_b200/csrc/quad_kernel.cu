@@ -108,14 +108,19 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
   // 128-byte alignment for the TMA destinations; offset arithmetic keeps the shared address space
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
 
-  const int tile_id = blockIdx.x % P.ntiles;
-  const int iom = blockIdx.x / P.ntiles;
+  // CTA -> (omega, tile, p_par split): with nsplit > 1 (few omegas in flight) the p_par tiles of one
+  // (omega, tile) are spread over nsplit CTAs, each leaving its own partial moment sums
+  const int nsplit = P.nsplit;
+  const int jsplit = blockIdx.x % nsplit;
+  const int tile_id = (blockIdx.x / nsplit) % P.ntiles;
+  const int iom = blockIdx.x / (nsplit * P.ntiles);
   const QuadTile tile = P.tiles[tile_id];
   const GlobalDev& g = *P.g;
   const SpeciesDev& sp = g.sp[tile.s];
   const int nperp = g.nperp, npar = g.npar;
   const int KC = (nperp - 1 + BK - 1) / BK;
-  const int NT = (npar - 1 + BN - 1) / BN;
+  const int NTall = (npar - 1 + BN - 1) / BN;
+  const int NT = (NTall - jsplit + nsplit - 1) / nsplit;   // p_par tiles of this CTA: jsplit, jsplit+nsplit, ...
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
   const CUtensorMap* tmW = &P.tmW[tile.s];
   const int T = NT * KC;   // pipeline iterations of this CTA
   auto issue = [&](int it) {
-    const int stg = it % STAGES, nt = it / KC, kc = it - nt * KC;
+    const int stg = it % STAGES, ntl = it / KC, kc = it - ntl * KC, nt = jsplit + ntl * nsplit;
     mbar_expect_tx(&sm.full[stg], STAGE_TX_BYTES);
     tma_load_2d(sm.st[stg].A, tmA, nt * BN, kc * BK, &sm.full[stg]);
     tma_load_2d(sm.st[stg].C, tmC, nt * BN, kc * BK, &sm.full[stg]);
@@ -165,7 +170,8 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
   int stage = 0;
   uint32_t phase = 0, ready = 0;
   int git = 0;
-  for (int nt = 0; nt < NT; nt++) {
+  for (int ntl = 0; ntl < NT; ntl++) {
+    const int nt = jsplit + ntl * nsplit;
     double ar[12][2], ai[12][2];
 #pragma unroll
     for (int r = 0; r < 12; r++) {
@@ -324,7 +330,8 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
     const int nn = rem / 24, sg = (rem % 24) / 12, q = rem % 12;
     const int nabs = tile.n0 + 4 * rgq + nn;
     if (nabs > sp.nhi_shard) continue;
-    P.Sbulk[(item0 + 2 * nabs + sg) * 12 + q] = sm.red[2 * rgq][nn][sg][q] + sm.red[2 * rgq + 1][nn][sg][q];
+    P.Sbulk[((item0 + 2 * nabs + sg) * nsplit + jsplit) * 12 + q] =
+        sm.red[2 * rgq][nn][sg][q] + sm.red[2 * rgq + 1][nn][sg][q];
   }
 }
 
@@ -339,7 +346,7 @@ static cudaError_t launch_one(const QuadParams& P, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_quad<RG, BKT, NST, PW, UNR, STORE><<<P.n_om * P.ntiles, (2 * RG + PW) * 32, smem, st>>>(P);
+  k_quad<RG, BKT, NST, PW, UNR, STORE><<<P.n_om * P.ntiles * P.nsplit, (2 * RG + PW) * 32, smem, st>>>(P);
   return cudaGetLastError();
 }
 template <int RG, int BKT, int NST, int PW, int UNR>

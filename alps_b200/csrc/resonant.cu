@@ -259,17 +259,48 @@ __device__ __forceinline__ cd warp_sum_c(cd v) {
   return v;
 }
 
-__global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
+constexpr int RES_THREADS = 128;
+// sum over the cooperating threads (block or warp): every thread gets the total, deterministic order
+template <bool BLOCK>
+__device__ __forceinline__ void block_sum6(Six& v, cd (*s_part)[6], int wlane, int wid) {
+  if (!BLOCK) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) v.v[q] = warp_sum_c(v.v[q]);
+    return;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    cd t = warp_sum_c(v.v[q]);
+    if (wlane == 0) s_part[wid][q] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    cd t = s_part[0][q];
+    for (int w = 1; w < RES_THREADS / 32; w++) t += s_part[w][q];
+    v.v[q] = t;
+  }
+}
+
+// BLOCK = true: one block per resonant harmonic (few omegas in flight, latency matters);
+// BLOCK = false: one warp per resonant harmonic (large batches, throughput matters).
+template <bool BLOCK>
+__global__ void __launch_bounds__(RES_THREADS) k_resonant(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
                                                   const PlanEntry* __restrict__ plan, const int* __restrict__ work,
                                                   const int* __restrict__ work_count,
                                                   const double* __restrict__ gwin, double* __restrict__ Sres,
                                                   int* __restrict__ err_flag) {
+  // one 128-thread block per resonant harmonic: the sub-step / p_perp loops are spread over all threads
   const GlobalDev& g = *gp;
-  const int lane = threadIdx.x & 31;
-  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  constexpr int STRIDE = BLOCK ? RES_THREADS : 32;      // threads cooperating on one harmonic
+  const int wlane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = BLOCK ? threadIdx.x : wlane;         // index inside the cooperative loops
+  __shared__ cd s_part[RES_THREADS / 32][6];
   const int nwork = *work_count;
-  for (int wi = wglobal; wi < nwork; wi += nwarps) {
+  const int first = BLOCK ? blockIdx.x : (blockIdx.x * (RES_THREADS / 32) + wid);
+  const int step = BLOCK ? gridDim.x : gridDim.x * (RES_THREADS / 32);
+  for (int wi = first; wi < nwork; wi += step) {
     const size_t idx = (size_t)work[wi];
     const int iom = (int)(idx / g.NI), it = (int)(idx % g.NI);
     int s, nabs, sg;
@@ -298,7 +329,7 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
       six_zero(acc);
       if (fabs(pI) > g.Tlim) {
         // Eq. (3.5): symmetric pairing around the pole, src/ALPS_fns.f90:1026-1082
-        for (int j = lane; j <= M_P; j += 32) {
+        for (int j = lane; j <= M_P; j += STRIDE) {
           const double wj = (j == 0 || j == M_P) ? 1.0 : 2.0;
           const double p = (j == 0) ? pR : (j == M_P ? pR + capDelta : pR + smdelta * j);
           Six f1, f2;
@@ -316,7 +347,7 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
         Six gprime;
 #pragma unroll
         for (int q = 0; q < 6; q++) gprime.v[q] = (fp.v[q] - fm.v[q]) / (2.0 * dppar);
-        for (int j = 1 + lane; j <= M_P; j += 32) {
+        for (int j = 1 + lane; j <= M_P; j += STRIDE) {
           const double wj = (j == M_P) ? 1.0 : 2.0;
           const double p = (j == M_P) ? pR + capDelta : pR + smdelta * j;
           const double x2 = (p - pR) * (p - pR);
@@ -336,7 +367,7 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
       const int ntiny = (int)(rest / smdelta);
       if (ntiny > 0) {
         const double correction = (rest / (1.0 * ntiny)) / smdelta;
-        for (int j = lane; j <= ntiny; j += 32) {
+        for (int j = lane; j <= ntiny; j += STRIDE) {
           const double wj = (j == 0 || j == ntiny) ? 1.0 : 2.0;
           const double p = (j == 0) ? pR + capDelta : pR + capDelta + correction * smdelta * j;
           Six f1;
@@ -347,8 +378,9 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
         }
       }
       const double fac = 2.0 * PI * smdelta * sp.dpperp * 0.25;
+      block_sum6<BLOCK>(acc, s_part, wlane, wid);
 #pragma unroll
-      for (int q = 0; q < 6; q++) tot.v[q] += fac * warp_sum_c(acc.v[q]);
+      for (int q = 0; q < 6; q++) tot.v[q] += fac * acc.v[q];
     }
 
     if (pe.flags & PLAN_LANDAU) {
@@ -360,7 +392,7 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
       cd La = mk(0.0, 0.0), Lb = La, Lc = La;
       int zero = 0;
       const cd ppl = mk(pR + dppar, pI), pmi = mk(pR - dppar, pI);
-      for (int iperp = 1 + lane; iperp <= nperp - 1; iperp += 32) {
+      for (int iperp = 1 + lane; iperp <= nperp - 1; iperp += STRIDE) {
         const double h = (iperp == nperp - 1) ? 0.5 : 1.0;
         const cd fpar_i = eval_fit(g, s, iperp, ppl);
         const cd fpar_f = eval_fit(g, s, iperp, pmi);
@@ -398,10 +430,14 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
           Lc += (0.5 * ((pperp * pperp) * (bp * bp))) * Q;
         }
       }
-      zero = __any_sync(0xffffffffu, zero);
-      La = warp_sum_c(La);
-      Lb = warp_sum_c(Lb);
-      Lc = warp_sum_c(Lc);
+      zero = BLOCK ? __syncthreads_or(zero) : __any_sync(0xffffffffu, zero);
+      {
+        Six L3;
+        L3.v[0] = La; L3.v[1] = Lb; L3.v[2] = Lc;
+        L3.v[3] = L3.v[4] = L3.v[5] = mk(0.0, 0.0);
+        block_sum6<BLOCK>(L3, s_part, wlane, wid);
+        La = L3.v[0]; Lb = L3.v[1]; Lc = L3.v[2];
+      }
       if (!zero) {
         // landau = -(sum) * i * dpperp * pi * 2 pi ; factor 2 (Im om < 0) or 1 (Im om == 0),
         // full_integrate src/ALPS_fns.f90:782-789
@@ -416,6 +452,7 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
       }
     }
     for (int o = 16; o > 0; o >>= 1) err = max(err, __shfl_xor_sync(0xffffffffu, err, o));
+    if (wlane == 0 && err) err_flag[0] = 1;
     if (lane == 0) {
       double* o = Sres + idx * 12;
 #pragma unroll
@@ -442,7 +479,7 @@ __global__ void __launch_bounds__(128) k_resonant(const GlobalDev* __restrict__ 
 // c = 6 + 3*(mode-1) + (m+1) for chi_low(mode, m), m = -1,0,1.
 __global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
                                                      int n_om, const PlanEntry* __restrict__ plan,
-                                                     const double* __restrict__ Sbulk,
+                                                     const double* __restrict__ Sbulk, int nsplit,
                                                      const double* __restrict__ Sres, double* __restrict__ partial) {
   const GlobalDev& g = *gp;
   const int lane = threadIdx.x & 31;
@@ -476,9 +513,15 @@ __global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict
         for (int q = 0; q < 6; q++) mode[q] = mk(sr[2 * q], sr[2 * q + 1]);
       } else {
         cd S[6];
-        const double* sb = Sbulk + idx * 12;
 #pragma unroll
-        for (int q = 0; q < 6; q++) S[q] = mk(cbulk * sb[2 * q], cbulk * sb[2 * q + 1]);
+        for (int q = 0; q < 6; q++) S[q] = mk(0.0, 0.0);
+        for (int j = 0; j < nsplit; j++) {   // partial rows of the p_par splits of k_quad
+          const double* sb = Sbulk + (idx * nsplit + j) * 12;
+#pragma unroll
+          for (int q = 0; q < 6; q++) S[q] += mk(sb[2 * q], sb[2 * q + 1]);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) S[q] = cbulk * S[q];
         if (pe.flags & (PLAN_NEAR | PLAN_LANDAU)) {
           const double* sr = Sres + idx * 12;
 #pragma unroll
@@ -635,13 +678,16 @@ void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int 
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, cudaStream_t st) {
   if (n_om <= 0) return;
-  k_resonant<<<148 * 8, 128, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
+  if (n_om <= 64)
+    k_resonant<true><<<148 * 4, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
+  else
+    k_resonant<false><<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
 }
 void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
-                        const double* Sbulk, const double* Sres, double* partial, cudaStream_t st) {
+                        const double* Sbulk, int nsplit, const double* Sres, double* partial, cudaStream_t st) {
   int warps = n_om * gh.nspec;
   if (warps <= 0) return;
-  k_chi_partial<<<(warps + 3) / 4, 128, 0, st>>>(g, om, n_om, plan, Sbulk, Sres, partial);
+  k_chi_partial<<<(warps + 3) / 4, 128, 0, st>>>(g, om, n_om, plan, Sbulk, nsplit, Sres, partial);
 }
 void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
                      const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
