@@ -263,61 +263,84 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
     double pp_[2];
     pp_[0] = (ipar0 <= npar - 1) ? ppar[ipar0] : 0.0;
     pp_[1] = (ipar0 + 1 <= npar - 1) ? ppar[ipar0 + 1] : 0.0;
+    // two chunks of two harmonics: 2 x 2 signs x 12 = 48 partial sums per thread and chunk, reduced over
+    // the 32 lanes by recursive halving (93 shuffles per 96 sums instead of 480 butterfly shuffles)
 #pragma unroll
-    for (int nn = 0; nn < 4; nn++) {
-      const int nabs = tile.n0 + 4 * rg + nn;
-      if (nabs > sp.nhi_shard) continue;   // warp-uniform
+    for (int h = 0; h < 2; h++) {
+      double Sv[48];
 #pragma unroll
-      for (int sg = 0; sg < 2; sg++) {
-        if (nabs == 0 && sg == 1) continue;
-        const size_t item = item0 + 2 * nabs + sg;
-        const PlanEntry pe = P.plan[item];
-        if (!(pe.flags & PLAN_ACTIVE)) continue;   // warp-uniform
-        const double nq = (sg ? -1.0 : 1.0) * (double)nabs * qs;
-        double S[12];
+      for (int q = 0; q < 48; q++) Sv[q] = 0.0;
 #pragma unroll
-        for (int q = 0; q < 12; q++) S[q] = 0.0;
+      for (int nnl = 0; nnl < 2; nnl++) {
+        const int nn = 2 * h + nnl;
+        const int nabs = tile.n0 + 4 * rg + nn;
+        if (nabs > sp.nhi_shard) continue;   // warp-uniform
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const int ipar = ipar0 + c;
-          if (ipar > npar - 1) continue;
-          const double w = range_w(ipar, pe.lo1, pe.hi1) + range_w(ipar, pe.lo2, pe.hi2);
-          const double p = pp_[c];
-          if (w != 0.0) {
-            // 1/den with den = ms om - kpar p_par - n qs   (resU, src/ALPS_fns.f90:1591-1592)
-            const double dr = ms * omr - kpar * p - nq, di = ms * omi;
-            const double t = w / (dr * dr + di * di);
-            const cd R = mk(dr * t, -di * t);
-            const cd Va = R * mk(ar[3 * nn + 0][c], ai[3 * nn + 0][c]);
-            const cd Vb = R * mk(ar[3 * nn + 1][c], ai[3 * nn + 1][c]);
-            const cd Vc = R * mk(ar[3 * nn + 2][c], ai[3 * nn + 2][c]);
-            const double p2 = p * p;
-            S[0] += Va.x;       S[1] += Va.y;        // sum U J^2
-            S[2] += p * Va.x;   S[3] += p * Va.y;    // sum U J^2 p_par
-            S[4] += p2 * Va.x;  S[5] += p2 * Va.y;   // sum U J^2 p_par^2
-            S[6] += Vb.x;       S[7] += Vb.y;        // sum U p_perp J J'
-            S[8] += p * Vb.x;   S[9] += p * Vb.y;    // sum U p_perp J J' p_par
-            S[10] += Vc.x;      S[11] += Vc.y;       // sum U p_perp^2 J'^2
-          }
-          if (pe.flags & PLAN_NEAR) {
-            int j = ipar - (pe.ipar_res - M_I - 2);
-            if (j < 0 || j >= WIN) j = (ipar <= 3) ? WIN + ipar - 1 : -1;   // nodes 1..3: funct_g fallback
-            if (j >= 0) {
-              double* gw = P.gwin + (item * WINX + j) * 6;
+        for (int sg = 0; sg < 2; sg++) {
+          if (nabs == 0 && sg == 1) continue;
+          const size_t item = item0 + 2 * nabs + sg;
+          const PlanEntry pe = P.plan[item];
+          if (!(pe.flags & PLAN_ACTIVE)) continue;   // warp-uniform
+          const double nq = (sg ? -1.0 : 1.0) * (double)nabs * qs;
+          double* S = &Sv[(nnl * 2 + sg) * 12];
 #pragma unroll
-              for (int x = 0; x < 3; x++) {
-                gw[2 * x] = ar[3 * nn + x][c];
-                gw[2 * x + 1] = ai[3 * nn + x][c];
+          for (int c = 0; c < 2; c++) {
+            const int ipar = ipar0 + c;
+            if (ipar > npar - 1) continue;
+            const double w = range_w(ipar, pe.lo1, pe.hi1) + range_w(ipar, pe.lo2, pe.hi2);
+            const double p = pp_[c];
+            if (w != 0.0) {
+              // 1/den with den = ms om - kpar p_par - n qs   (resU, src/ALPS_fns.f90:1591-1592)
+              const double dr = ms * omr - kpar * p - nq, di = ms * omi;
+              const double t = w / (dr * dr + di * di);
+              const cd R = mk(dr * t, -di * t);
+              const cd Va = R * mk(ar[3 * nn + 0][c], ai[3 * nn + 0][c]);
+              const cd Vb = R * mk(ar[3 * nn + 1][c], ai[3 * nn + 1][c]);
+              const cd Vc = R * mk(ar[3 * nn + 2][c], ai[3 * nn + 2][c]);
+              const double p2 = p * p;
+              S[0] += Va.x;       S[1] += Va.y;        // sum U J^2
+              S[2] += p * Va.x;   S[3] += p * Va.y;    // sum U J^2 p_par
+              S[4] += p2 * Va.x;  S[5] += p2 * Va.y;   // sum U J^2 p_par^2
+              S[6] += Vb.x;       S[7] += Vb.y;        // sum U p_perp J J'
+              S[8] += p * Vb.x;   S[9] += p * Vb.y;    // sum U p_perp J J' p_par
+              S[10] += Vc.x;      S[11] += Vc.y;       // sum U p_perp^2 J'^2
+            }
+            if (pe.flags & PLAN_NEAR) {
+              int j = ipar - (pe.ipar_res - M_I - 2);
+              if (j < 0 || j >= WIN) j = (ipar <= 3) ? WIN + ipar - 1 : -1;   // nodes 1..3: funct_g fallback
+              if (j >= 0) {
+                double* gw = P.gwin + (item * WINX + j) * 6;
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                  gw[2 * x] = ar[3 * nn + x][c];
+                  gw[2 * x + 1] = ai[3 * nn + x][c];
+                }
               }
             }
           }
         }
+      }
+      // recursive halving: after the step with mask m a lane keeps the half selected by its bit m
 #pragma unroll
-        for (int q = 0; q < 12; q++) S[q] = warp_sum(S[q]);
-        if (lane == 0) {
+      for (int step = 0; step < 4; step++) {
+        const int N = 24 >> step, mask = 16 >> step;
+        const bool up = (lane & mask) != 0;
 #pragma unroll
-          for (int q = 0; q < 12; q++) sm.red[warp][nn][sg][q] += S[q];
+        for (int i = 0; i < 24; i++) {
+          if (i < N) {
+            const double send = up ? Sv[i] : Sv[i + N];
+            const double keep = up ? Sv[i + N] : Sv[i];
+            Sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+          }
         }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) Sv[i] += __shfl_xor_sync(0xffffffffu, Sv[i], 1);
+      if (!(lane & 1)) {
+        const int base = 24 * ((lane >> 4) & 1) + 12 * ((lane >> 3) & 1) + 6 * ((lane >> 2) & 1) + 3 * ((lane >> 1) & 1);
+        double* red = &sm.red[warp][0][0][0] + 48 * h + base;
+#pragma unroll
+        for (int i = 0; i < 3; i++) red[i] += Sv[i];
       }
     }
   }
