@@ -183,3 +183,45 @@ def test_root_batching_is_bit_identical_to_the_serial_order():
     assert np.array_equal(w_ser, w_bat) and np.array_equal(D_ser, D_bat)
     assert np.array_equal(rows_ser, rows_bat)
     print("serial %.3f s, batched %.3f s" % (t_ser, t_bat))
+
+
+def test_cli_map_search_flow(tmp_path):
+    """use_map=.true.: map_search -> find_minima -> refine_guess through the twin main program; the
+    Alfven root of the test_kpar_fast tables must be among the refined roots."""
+    from alps_b200 import run
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "solution")
+    assert run.main([os.path.join(here, "inputs", "test_map_small.in"),
+                     "--dist", os.path.join(here, "inputs", "test_kpar_fast_dist.in"), "--out", out, "--nproc", "4"]) == 0
+    m = np.loadtxt(os.path.join(out, "test_map_small.map"))
+    assert m.shape == (40 * 24, 5)
+    roots = [l.split() for l in open(os.path.join(out, "test_map_small.roots")) if l.strip()]
+    assert len(roots) >= 1
+    assert any(abs(float(r[1]) - 9.9881e-3) < 2e-7 and abs(float(r[2]) + 2.3132e-7) < 2e-10 for r in roots), roots
+
+
+def test_cli_relativistic_scan(tmp_path):
+    """C3 flow (reduced relativistic grid): refine the two guesses of tests/test_relativistic.in and scan
+    k_par; every reported root must actually be a root of the GPU's D (|D| collapses by > 6 decades)."""
+    from alps_b200 import run, tables
+    from alps_b200.namelist import read_namelists
+    from alps_b200.solver import Solver
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "solution")
+    inp = os.path.join(here, "inputs", "test_relativistic_small.in")
+    dist = os.path.join(here, "inputs", "test_relativistic_dist.in")
+    assert run.main([inp, "--dist", dist, "--out", out]) == 0
+    rows = np.array([[float(x) for x in l.split()] for l in open(os.path.join(out, "test_relativistic_small.scan_kpara_1.root_1"))
+                     if l.strip()])
+    assert rows.shape == (5, 4) and abs(rows[-1, 1] - 0.2) < 1e-12
+    pl = run.plasma_from_inputs(read_namelists(inp), read_namelists(dist), base_dir=str(tmp_path))
+    sol = Solver(pl)
+    try:
+        for kperp, kpar, wr, wi in rows[[0, -1]]:
+            sol.set_k(kperp, kpar)
+            om = complex(wr, wi)
+            d_root = abs(sol.disp(om))
+            d_near = abs(sol.disp(om * 1.05))
+            assert d_root < 1e-3 * d_near      # the file carries 5 digits of the root
+    finally:
+        sol.close()
