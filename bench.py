@@ -28,10 +28,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOPS_PER_POINT_HARMONIC = 34.0     # per (signed n, iperp, ipar), +n and -n separately
-# what k_quad executes (DESIGN.md "flop model"): per (|n|, iperp, ipar) 3 weight types x (re,im) FMA
-# = 12 flops shared by +n and -n, plus the numerator om*A'+C' (3 DFMA-pipe ops per point, shared by
-# the 4 harmonics of a thread) -> 12 + 6/4 = 13.5 flops per (|n|, point)
-FLOPS_EXECUTED_PER_ABSN_POINT = 13.5
+# useful flops of k_quad's formulation (DESIGN.md "flop model"): per (|n|, iperp, ipar) 3 weight types x
+# (re,im) FMA = 12 flops shared by +n and -n, plus the numerator om*A'+C' (one FMA + one MUL = 3 flops
+# per grid point, shared by the 4 harmonics of a thread) -> 12 + 3/4 = 12.75 flops per (|n|, point).
+# Tile padding and the epilogue are NOT counted (ncu's executed count is ~5 % higher).
+FLOPS_EXECUTED_PER_ABSN_POINT = 12.75
 FP64_NOMINAL_TFLOPS = 37.2          # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 
 WORKLOADS = {
@@ -283,7 +284,8 @@ def run_ours(args, w, rank, world, local_rank):
         tp = os.path.join(ROOT, "profiles", "r01_k_quad_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj["dram_bytes_per_launch"] / tj["omegas_per_launch"] * B   # scaled to this launch size
             except Exception:
                 traffic = None
         line = {"metric": "D(omega,k) evals/sec", "value": value, "unit": "D/s", "n_gpus": world,
@@ -301,8 +303,8 @@ def run_ours(args, w, rank, world, local_rank):
                              "frac": achieved / peak_meas if peak_meas else None, "traffic": traffic,
                              "peak_source": "DFMA micro-benchmark run in this job (MEASURED_PEAKS.json has no FP64 entry)",
                              "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_nominal": achieved / FP64_NOMINAL_TFLOPS,
-                             "flop_model": "executed DFMA-pipe flops of k_quad: 13.5 per (|n|, iperp, ipar); "
-                                           "+n and -n share the p_perp sums (DESIGN.md)",
+                             "flop_model": "useful FP64 flops of k_quad's formulation: 12.75 per (|n|, iperp, ipar); "
+                                           "+n and -n share the p_perp sums; padding/epilogue not counted (DESIGN.md)",
                              "achieved_survey_34flop_model": achieved34,
                              "frac_survey_34flop_model": achieved34 / peak_meas if peak_meas else None,
                              "kernel": "k_quad", "kernel_ms_per_step": kern_ms / args.steps,

@@ -1,0 +1,35 @@
+"""Host-side relativistic set-up (alps_b200/relativistic.py, twin of derivative_f0_rel,
+src/ALPS_fns_rel.f90:36-426): thin-plate-spline regrid of a Juettner table, cone sentinel,
+normalisation and derivatives against the analytic distribution."""
+import numpy as np
+
+from alps_b200 import tables
+
+
+def test_regrid_of_a_juettner_table():
+    pl = tables.config_relativistic(nperp=20, npar=40, ngamma=40, npparbar=60)
+    g, p, f, d = pl.gamma_rel[0], pl.pparbar_rel[0], pl.f0_rel[0], pl.df0_rel[0]
+    # uniform separable grid
+    assert np.allclose(np.diff(g[:, 0]), g[1, 0] - g[0, 0]) and np.all(g == g[:, :1])
+    assert np.allclose(np.diff(p[0, :]), p[0, 1] - p[0, 0]) and np.all(p == p[:1, :])
+    # cone sentinel exactly where gamma^2 - 1 < pparbar^2
+    outside = (g ** 2 - 1.0) < p ** 2
+    assert np.all(f[outside] == -1.0) and np.all(f[~outside] > 0.0)
+    # normalisation: sum gamma f 2 pi dgamma dpparbar (ms/vA)^3 = 1
+    dg, dp = g[2, 2] - g[1, 2], p[2, 2] - p[2, 1]
+    assert abs(np.sum(g[~outside] * f[~outside]) * 2 * np.pi * dg * dp - 1.0) < 1e-12
+    # f ~ exp(-2 gamma): d ln f / d gamma = -2, no pparbar dependence (interior of the cone)
+    inner = np.zeros_like(outside)
+    inner[2:-2, 2:-2] = True
+    inner &= ~outside
+    inner[1:, :] &= ~outside[:-1, :]
+    inner[:-1, :] &= ~outside[1:, :]
+    inner[:, 1:] &= ~outside[:, :-1]
+    inner[:, :-1] &= ~outside[:, 1:]
+    ratio = d[:, :, 0][inner] / f[inner]
+    assert np.max(np.abs(ratio + 2.0)) < 0.05
+    assert np.max(np.abs(d[:, :, 1][inner] / f[inner])) < 0.05
+    # the fit amplitude handed to eval_fit reproduces the table: f = p1 exp(-2 gamma)
+    p1 = pl.param_fit[0, 0, 0, 0]
+    model = p1 * np.exp(-pl.species[0].perp_correction[0] * g)
+    assert np.max(np.abs(model[inner] / f[inner] - 1.0)) < 0.02
