@@ -23,7 +23,7 @@ SYMBOLS = [
     "alps_b200_om_double_scan", "alps_b200_set_root_batching",
 ]
 
-INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH = range(5)
+INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH, INFO_DFMA_NOREUSE = range(6)
 
 
 class Cfg(C.Structure):

@@ -1013,6 +1013,7 @@ int alps_b200_get_info(int what, double* out) {
     case ALPS_B200_INFO_SM_COUNT: *out = S.sm_count; return 0;
     case ALPS_B200_INFO_LAST_KERNEL_MS: *out = S.last_kernel_ms; return 0;
     case ALPS_B200_INFO_BATCH: *out = S.have_k ? auto_batch() : 0; return 0;
+    case ALPS_B200_INFO_DFMA_NOREUSE: *out = run_dfma_peak_noreuse(S.stream); S.launches += 3; return 0;
   }
   return fail(ALPS_B200_ERR_USAGE, "unknown info id %d", what);
 }

@@ -75,5 +75,6 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
 void launch_int_ee_rel(const double* pbv, const double* dfp, const int* lo, const int* up, int ng, int npb, double qs,
                        double ms, double vA, double dgam, double dpb, double* out, cudaStream_t st);
 double run_dfma_peak(cudaStream_t st);
+double run_dfma_peak_noreuse(cudaStream_t st);
 
 }  // namespace alps

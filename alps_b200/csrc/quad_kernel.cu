@@ -219,16 +219,27 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
 #pragma unroll
           for (int q = 0; q < 6; q++) w[q] = reinterpret_cast<const double2*>(sW + (kk + 1) * BM)[q];
         }
+        // numerator-major order: 12 consecutive FMAs share one multiplicand, which the operand
+        // reuse cache keeps (a DFMA with three fresh 64-bit operands costs a third register-read cycle)
 #pragma unroll
         for (int q = 0; q < 6; q++) {
-          ar[2 * q][0] = fma(wc[q].x, nr0, ar[2 * q][0]);
-          ai[2 * q][0] = fma(wc[q].x, ni0, ai[2 * q][0]);
-          ar[2 * q][1] = fma(wc[q].x, nr1, ar[2 * q][1]);
-          ai[2 * q][1] = fma(wc[q].x, ni1, ai[2 * q][1]);
-          ar[2 * q + 1][0] = fma(wc[q].y, nr0, ar[2 * q + 1][0]);
-          ai[2 * q + 1][0] = fma(wc[q].y, ni0, ai[2 * q + 1][0]);
-          ar[2 * q + 1][1] = fma(wc[q].y, nr1, ar[2 * q + 1][1]);
-          ai[2 * q + 1][1] = fma(wc[q].y, ni1, ai[2 * q + 1][1]);
+          ar[2 * q][0] = fma(nr0, wc[q].x, ar[2 * q][0]);
+          ar[2 * q + 1][0] = fma(nr0, wc[q].y, ar[2 * q + 1][0]);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          ai[2 * q][0] = fma(ni0, wc[q].x, ai[2 * q][0]);
+          ai[2 * q + 1][0] = fma(ni0, wc[q].y, ai[2 * q + 1][0]);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          ar[2 * q][1] = fma(nr1, wc[q].x, ar[2 * q][1]);
+          ar[2 * q + 1][1] = fma(nr1, wc[q].y, ar[2 * q + 1][1]);
+        }
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          ai[2 * q][1] = fma(ni1, wc[q].x, ai[2 * q][1]);
+          ai[2 * q + 1][1] = fma(ni1, wc[q].y, ai[2 * q + 1][1]);
         }
       }
       __syncwarp();

@@ -138,6 +138,8 @@ int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
 #define ALPS_B200_INFO_SM_COUNT 2
 #define ALPS_B200_INFO_LAST_KERNEL_MS 3   /* device time of the last quadrature kernel batch    */
 #define ALPS_B200_INFO_BATCH 4            /* internal omega chunk size                          */
+#define ALPS_B200_INFO_DFMA_NOREUSE 5     /* DFMA micro-benchmark with three fresh operands per FMA,
+                                             TFLOP/s (register-read limit of tiled FP64 kernels)  */
 
 /* ------------------------------------------------------------------------------------------
  * Host-side twins of the reference's omega-point generators (alps_b200/csrc/drivers.cpp).  They
