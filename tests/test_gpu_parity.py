@@ -299,3 +299,42 @@ def test_two_fits_per_species_and_drift():
     pl.species[0].perp_correction = [pl.species[0].perp_correction[0]] * 2
     pl.species[1].fit_type = [1]
     _compare(pl, 0.3, 0.05, _damped(26, 4, (0.02, 1.2)))
+
+
+def test_batch_chunking_and_api_errors():
+    """alps_b200_disp_batch splits large batches into internal chunks (batch_max) -- same D; and the
+    entry points report usage / grid / nmax errors instead of computing garbage."""
+    from alps_b200 import _lib
+    from alps_b200.solver import Solver
+    pl = tables.config_small(24, 48, kind=1)
+    oms = np.array(list(omega_samples(31, 23, (0.02, 1.4), (-0.04, 0.04))))
+    sol = Solver(pl)
+    try:
+        with pytest.raises(_lib.AlpsB200Error) as e:
+            sol.disp(0.3 + 0.01j)                       # set_k not called yet
+        assert e.value.code == -2
+        sol.set_k(0.3, 0.05)
+        D_ref, chi_ref = sol.disp_batch(oms, want_chi0=True)
+    finally:
+        sol.close()
+    sol = Solver(pl, batch_max=5)
+    try:
+        sol.set_k(0.3, 0.05)
+        D, chi = sol.disp_batch(oms, want_chi0=True)    # 5 chunks of <= 5 omegas
+        assert np.array_equal(D, D_ref) and np.array_equal(chi, chi_ref)
+    finally:
+        sol.close()
+    sol = Solver(pl, nmax_cap=8)
+    try:
+        with pytest.raises(_lib.AlpsB200Error) as e:
+            sol.set_k(0.3, 0.05)                        # needs nmax ~ 29 > cap
+        assert e.value.code == -5
+    finally:
+        sol.close()
+    bad = tables.config_small(24, 48, kind=1)
+    bad.pp = bad.pp.copy(order="F")
+    bad.pp[0, 3, 7, 1] *= 1.0000001                     # no longer a separable grid
+    with pytest.raises(_lib.AlpsB200Error) as e:
+        Solver(bad)
+    assert e.value.code == -4
+    _lib.lib().alps_b200_finalize()
