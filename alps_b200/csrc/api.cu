@@ -713,7 +713,7 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
           break;
         }
     }
-    if (found < 0) {
+    if (found < 0 || found > S.cfg.nmax_cap) {
       dfree(&d_bm);
       return fail(ALPS_B200_ERR_NMAX, "species %d: nmax exceeds nmax_cap=%d", s + 1, S.cfg.nmax_cap);
     }
