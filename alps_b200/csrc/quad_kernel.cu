@@ -10,7 +10,9 @@
 //      t   = one of {J_n^2, p_perp J_n J_n', p_perp^2 J_n'^2} times constants (same for +n/-n).
 // One CTA owns (omega, species, 16 harmonics) and walks the whole grid: for each tile of 128
 // p_par columns it forms   G_x(n, ipar) = sum_iperp w_perp t_x(n,iperp) Num(iperp,ipar)
-// (x = a,b,c) with Num evaluated at every grid point from the TMA-staged A / C' tiles, then the
+// (x = a,b,c) from the TMA-staged A' / C' tiles -- Num = om A' + C' is linear in the two real tables,
+// so the kernel accumulates sum W A' and sum W C' (48 FMAs per thread and grid row) and forms
+// om * (sum W A') + (sum W C') once per column -- then the
 // epilogue divides by the two resonance denominators (+n, -n), applies the p_par trapezoid
 // weights of the resonance plan and the p_par^m moments, and reduces over p_par with warp
 // shuffles.  Six complex moment sums per (n, sign) leave the kernel; all six tensor components
@@ -207,9 +209,11 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
       for (int q = 0; q < 6; q++) w[q] = reinterpret_cast<const double2*>(sW)[q];
 #pragma unroll UNR
       for (int kk = 0; kk < BK; kk++) {
-        // numerator of resU at this grid point: Num = om * A' + C'
-        const double nr0 = fma(omr, a.x, c.x), ni0 = omi * a.x;
-        const double nr1 = fma(omr, a.y, c.y), ni1 = omi * a.y;
+        // Num = om*A' + C' is linear in the two real tables, so the p_perp sums of A' and of C' are
+        // accumulated separately (same 48 FMAs) and combined with om in the epilogue:
+        //   sum_iperp W Num = om * sum W A' + sum W C'
+        const double nr0 = c.x, ni0 = a.x;   // "real" accumulators collect C', "imaginary" ones A'
+        const double nr1 = c.y, ni1 = a.y;
         double2 wc[6];
 #pragma unroll
         for (int q = 0; q < 6; q++) wc[q] = w[q];
@@ -252,9 +256,21 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
 
     // ------------------------------------------------------------ epilogue of this p_par tile
     const int ipar0 = nt * BN + 2 * cg + 1;
+    if (!STORE) {
+      // G = om * GA + GB  (ai holds GA = sum W A', ar holds GB = sum W C')
+#pragma unroll
+      for (int r = 0; r < 12; r++) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const double ga = ai[r][c];
+          ar[r][c] = fma(omr, ga, ar[r][c]);
+          ai[r][c] = omi * ga;
+        }
+      }
+    }
     if (STORE) {
-      // k-hoisted tables (alps_b200_set_mode(1)): launched with om = i, so Re = sum w C' (GB) and
-      // Im = sum w A' (GA).  Layout [n][ipar-1][GAa, GBa, GAb, GBb, GAc, GBc].
+      // k-hoisted tables (alps_b200_set_mode(1)): the raw sums GA = sum W A' (ai) and GB = sum W C' (ar).
+      // Layout [n][ipar-1][GAa, GBa, GAb, GBb, GAc, GBc].
       double* gt = P.gtab[tile.s];
 #pragma unroll
       for (int nn = 0; nn < 4; nn++) {

@@ -29,10 +29,9 @@ if ROOT not in sys.path:
 
 FLOPS_PER_POINT_HARMONIC = 34.0     # per (signed n, iperp, ipar), +n and -n separately
 # useful flops of k_quad's formulation (DESIGN.md "flop model"): per (|n|, iperp, ipar) 3 weight types x
-# (re,im) FMA = 12 flops shared by +n and -n, plus the numerator om*A'+C' (one FMA + one MUL = 3 flops
-# per grid point, shared by the 4 harmonics of a thread) -> 12 + 3/4 = 12.75 flops per (|n|, point).
-# Tile padding and the epilogue are NOT counted (ncu's executed count is ~5 % higher).
-FLOPS_EXECUTED_PER_ABSN_POINT = 12.75
+# 2 real tables (A', C') x one FMA = 12 flops, shared by +n and -n.  Tile padding and the epilogue are
+# NOT counted (ncu's executed count is ~5 % higher).
+FLOPS_EXECUTED_PER_ABSN_POINT = 12.0
 FP64_NOMINAL_TFLOPS = 37.2          # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
 
 WORKLOADS = {
@@ -303,7 +302,7 @@ def run_ours(args, w, rank, world, local_rank):
                              "frac": achieved / peak_meas if peak_meas else None, "traffic": traffic,
                              "peak_source": "DFMA micro-benchmark run in this job (MEASURED_PEAKS.json has no FP64 entry)",
                              "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_nominal": achieved / FP64_NOMINAL_TFLOPS,
-                             "flop_model": "useful FP64 flops of k_quad's formulation: 12.75 per (|n|, iperp, ipar); "
+                             "flop_model": "useful FP64 flops of k_quad's formulation: 12 per (|n|, iperp, ipar); "
                                            "+n and -n share the p_perp sums; padding/epilogue not counted (DESIGN.md)",
                              "achieved_survey_34flop_model": achieved34,
                              "frac_survey_34flop_model": achieved34 / peak_meas if peak_meas else None,
