@@ -40,7 +40,7 @@ struct alignas(128) QuadStage {
 template <int RG, int BKT, int NST>
 struct QuadSmem {
   QuadStage<RG, BKT> st[NST];
-  double red[2 * RG][4][2][12];
+  double red[2 * RG][RG][4][2][12];   // [warp][row group][harmonic][sign][12]
   unsigned long long full[NST];
   unsigned long long empty[NST];
 };
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < CONSUMER_WARPS * 96; i += blockDim.x) (&sm.red[0][0][0][0])[i] = 0.0;
+  for (int i = threadIdx.x; i < CONSUMER_WARPS * RG * 96; i += blockDim.x) (&sm.red[0][0][0][0][0])[i] = 0.0;
   __syncthreads();
 
   const CUtensorMap* tmA = &P.tmA[tile.s];
@@ -161,8 +161,11 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
   }
 
   // ---------------------------------------------------------------- consumers
-  const int rg = warp >> 1;                    // row group: harmonics n0 + 4 rg .. +3
-  const int cg = ((warp & 1) << 5) | lane;     // column group: columns 2 cg, 2 cg + 1 of the tile
+  // a warp covers all 4 row groups x 8 column groups: the A'/C' operands are then shared by 4 lanes
+  // (one shared-memory wavefront per half-warp instead of two), the W operands by 8 lanes
+  static_assert(RG == 4, "lane mapping assumes 4 row groups");
+  const int rg = lane >> 3;                    // row group: harmonics n0 + 4 rg .. +3
+  const int cg = (warp << 3) | (lane & 7);     // column group: columns 2 cg, 2 cg + 1 of the tile
   const double omr = P.om[2 * iom], omi = P.om[2 * iom + 1];
   const double qs = sp.qs, ms = sp.ms, kpar = g.kpar;
   const double* __restrict__ ppar = sp.ppar;
@@ -301,13 +304,13 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
       for (int nnl = 0; nnl < 2; nnl++) {
         const int nn = 2 * h + nnl;
         const int nabs = tile.n0 + 4 * rg + nn;
-        if (nabs > sp.nhi_shard) continue;   // warp-uniform
+        if (nabs > sp.nhi_shard) continue;
 #pragma unroll
         for (int sg = 0; sg < 2; sg++) {
           if (nabs == 0 && sg == 1) continue;
           const size_t item = item0 + 2 * nabs + sg;
           const PlanEntry pe = P.plan[item];
-          if (!(pe.flags & PLAN_ACTIVE)) continue;   // warp-uniform
+          if (!(pe.flags & PLAN_ACTIVE)) continue;
           const double nq = (sg ? -1.0 : 1.0) * (double)nabs * qs;
           double* S = &Sv[(nnl * 2 + sg) * 12];
 #pragma unroll
@@ -347,10 +350,11 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
           }
         }
       }
-      // recursive halving: after the step with mask m a lane keeps the half selected by its bit m
+      // recursive halving over the 8 lanes of a row group (lane bits 2,1,0): after the step with mask m
+      // a lane keeps the half selected by its bit m
 #pragma unroll
-      for (int step = 0; step < 4; step++) {
-        const int N = 24 >> step, mask = 16 >> step;
+      for (int step = 0; step < 3; step++) {
+        const int N = 24 >> step, mask = 4 >> step;
         const bool up = (lane & mask) != 0;
 #pragma unroll
         for (int i = 0; i < 24; i++) {
@@ -361,13 +365,11 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
           }
         }
       }
+      {
+        const int base = 24 * ((lane >> 2) & 1) + 12 * ((lane >> 1) & 1) + 6 * (lane & 1);
+        double* red = &sm.red[warp][rg][0][0][0] + 48 * h + base;
 #pragma unroll
-      for (int i = 0; i < 3; i++) Sv[i] += __shfl_xor_sync(0xffffffffu, Sv[i], 1);
-      if (!(lane & 1)) {
-        const int base = 24 * ((lane >> 4) & 1) + 12 * ((lane >> 3) & 1) + 6 * ((lane >> 2) & 1) + 3 * ((lane >> 1) & 1);
-        double* red = &sm.red[warp][0][0][0] + 48 * h + base;
-#pragma unroll
-        for (int i = 0; i < 3; i++) red[i] += Sv[i];
+        for (int i = 0; i < 6; i++) red[i] += Sv[i];
       }
     }
   }
@@ -380,8 +382,10 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
     const int nn = rem / 24, sg = (rem % 24) / 12, q = rem % 12;
     const int nabs = tile.n0 + 4 * rgq + nn;
     if (nabs > sp.nhi_shard) continue;
-    P.Sbulk[((item0 + 2 * nabs + sg) * nsplit + jsplit) * 12 + q] =
-        sm.red[2 * rgq][nn][sg][q] + sm.red[2 * rgq + 1][nn][sg][q];
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < CONSUMER_WARPS; w++) t += sm.red[w][rgq][nn][sg][q];
+    P.Sbulk[((item0 + 2 * nabs + sg) * nsplit + jsplit) * 12 + q] = t;
   }
 }
 
@@ -407,15 +411,9 @@ static cudaError_t launch_variant(const QuadParams& P, bool store, cudaStream_t 
 QuadVariant quad_variant(int id) {
   switch (id) {
     case 1: return QuadVariant{1, 16, 16, 4};    // 8 consumer warps + producer, BK=16
-    case 2: return QuadVariant{2, 24, 8, 4};     // 12 consumer warps, inline producer, BK=8
-    case 3: return QuadVariant{3, 24, 16, 3};    // 12 consumer warps, inline producer, BK=16
     case 4: return QuadVariant{4, 16, 8, 4};     // 8 consumer warps, inline producer, BK=8
     case 5: return QuadVariant{5, 16, 16, 4};    // 8 consumer warps, inline producer, BK=16
-    case 6: return QuadVariant{6, 24, 16, 4};    // 12 consumer warps, inline producer, BK=16, 4 stages
-    case 7: return QuadVariant{7, 24, 32, 2};    // 12 consumer warps, inline producer, BK=32, 2 stages
     case 8: return QuadVariant{8, 16, 32, 2};    // 8 consumer warps, inline producer, BK=32, 2 stages
-    case 9: return QuadVariant{9, 24, 32, 2};    // as 7, k loop unrolled by 8 only
-    case 10: return QuadVariant{10, 24, 24, 3};  // 12 consumer warps, BK=24, 3 stages
     case 11: return QuadVariant{11, 16, 32, 2};  // as 8, k loop unrolled by 8 only
     default: return QuadVariant{0, 16, 8, 4};    // 8 consumer warps + producer, BK=8
   }
@@ -425,15 +423,9 @@ cudaError_t launch_quad(const QuadParams& P, int variant, bool store, cudaStream
   if (P.n_om <= 0 || P.ntiles <= 0) return cudaSuccess;
   switch (variant) {
     case 1: return launch_variant<4, 16, 4, 1, 16>(P, store, st);
-    case 2: return launch_variant<6, 8, 4, 0, 8>(P, store, st);
-    case 3: return launch_variant<6, 16, 3, 0, 16>(P, store, st);
     case 4: return launch_variant<4, 8, 4, 0, 8>(P, store, st);
     case 5: return launch_variant<4, 16, 4, 0, 16>(P, store, st);
-    case 6: return launch_variant<6, 16, 4, 0, 16>(P, store, st);
-    case 7: return launch_variant<6, 32, 2, 0, 32>(P, store, st);
     case 8: return launch_variant<4, 32, 2, 0, 32>(P, store, st);
-    case 9: return launch_variant<6, 32, 2, 0, 8>(P, store, st);
-    case 10: return launch_variant<6, 24, 3, 0, 24>(P, store, st);
     case 11: return launch_variant<4, 32, 2, 0, 8>(P, store, st);
     default: return launch_variant<4, 8, 4, 1, 8>(P, store, st);
   }
