@@ -274,11 +274,14 @@ def run_ours(args, w, rank, world, local_rank):
         achieved34 = flops_per_D * B * args.steps / (kern_ms * 1e-3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu:
-            c = cpu_sample(w, plasma, om_h[0])
-            cpu = {"value": c["d_per_s"], "unit": "D/s", "cores": c["cores"], "kind": "port",
-                   "sample": "one D restricted to |n|<=%d (%.2f%% of the signed harmonics, %.1f s), scaled; "
-                             "CPU oracle (restated reference, OpenMP); Fortran/MPI build impossible here"
-                             % (c["ncap"], 100 * c["fraction"], c["seconds_sample"])}
+            # the CPU leg runs in a fresh interpreter (no torch / CUDA threads competing with OpenMP)
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload",
+                                      args.workload, "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                                     timeout=900, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+                cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception as e:     # the baseline is reported, never required
+                cpu = {"value": None, "unit": "D/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r01_k_quad_traffic.json")
         if os.path.exists(tp):
