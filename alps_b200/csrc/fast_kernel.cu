@@ -14,6 +14,16 @@
 
 namespace alps {
 
+// 1/x for normal, finite x: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps; avoids the
+// IEEE-division slow path.  Relative error ~1e-16, far inside the 1e-9 parity budget.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(y, fma(-x, y, 1.0), y);
+  y = fma(y, fma(-x, y, 1.0), y);
+  return y;
+}
+
 __global__ void __launch_bounds__(128) k_fast(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om,
                                               const FastItem* __restrict__ items, const PlanEntry* __restrict__ plan,
                                               double* __restrict__ Sbulk, double* __restrict__ gwin) {
@@ -36,7 +46,11 @@ __global__ void __launch_bounds__(128) k_fast(const GlobalDev* __restrict__ gp, 
   double S[2][12];
 #pragma unroll
   for (int q = 0; q < 12; q++) S[0][q] = S[1][q] = 0.0;
-  const double dre = ms * omr, dim = ms * omi;
+  const double dre = ms * omr, dim = ms * omi, dim2 = dim * dim;
+  const double nq = (double)nabs * qs;
+  // non-resonant harmonics (the vast majority) use the plain trapezoid weights 1,2,...,2,1
+  const bool plain0 = act0 && !(pe[0].flags & PLAN_RES), plain1 = act1 && !(pe[1].flags & PLAN_RES);
+  const bool simple = (plain0 || !act0) && (plain1 || !act1);
   for (int ipar = 1; ipar <= npar - 1; ipar++) {
     const double2 t0 = __ldg(reinterpret_cast<const double2*>(G + (size_t)(ipar - 1) * 6));
     const double2 t1 = __ldg(reinterpret_cast<const double2*>(G + (size_t)(ipar - 1) * 6 + 2));
@@ -46,29 +60,51 @@ __global__ void __launch_bounds__(128) k_fast(const GlobalDev* __restrict__ gp, 
     const cd Gb = mk(fma(omr, t1.x, t1.y), omi * t1.x);
     const cd Gc = mk(fma(omr, t2.x, t2.y), omi * t2.x);
     const double p = __ldg(ppar + ipar), p2 = p * p;
+    const double x = dre - kpar * p;            // Re(den) before the -+ n qs shift
+    const double drp = x - nq, drm = x + nq;    // den = ms om - kpar p_par -+ n qs (resU, src/ALPS_fns.f90:1591)
+    const double dp = drp * drp + dim2, dm = drm * drm + dim2;
+    double wp, wm;
+    if (simple) {
+      const double we = (ipar == 1 || ipar == npar - 1) ? 1.0 : 2.0;
+      wp = act0 ? we : 0.0;
+      wm = act1 ? we : 0.0;
+    } else {
+      wp = act0 ? range_w(ipar, pe[0].lo1, pe[0].hi1) + range_w(ipar, pe[0].lo2, pe[0].hi2) : 0.0;
+      wm = act1 ? range_w(ipar, pe[1].lo1, pe[1].hi1) + range_w(ipar, pe[1].lo2, pe[1].hi2) : 0.0;
+    }
+    // both reciprocals from one: 1/dp = dm/(dp dm), 1/dm = dp/(dp dm)
+    const double inv = fast_rcp(dp * dm);
+    const double tp = wp * dm * inv, tm = wm * dp * inv;
+    {
+      const cd R = mk(drp * tp, -dim * tp);
+      const cd Va = R * Ga, Vb = R * Gb, Vc = R * Gc;
+      S[0][0] += Va.x;       S[0][1] += Va.y;
+      S[0][2] += p * Va.x;   S[0][3] += p * Va.y;
+      S[0][4] += p2 * Va.x;  S[0][5] += p2 * Va.y;
+      S[0][6] += Vb.x;       S[0][7] += Vb.y;
+      S[0][8] += p * Vb.x;   S[0][9] += p * Vb.y;
+      S[0][10] += Vc.x;      S[0][11] += Vc.y;
+    }
+    {
+      const cd R = mk(drm * tm, -dim * tm);
+      const cd Va = R * Ga, Vb = R * Gb, Vc = R * Gc;
+      S[1][0] += Va.x;       S[1][1] += Va.y;
+      S[1][2] += p * Va.x;   S[1][3] += p * Va.y;
+      S[1][4] += p2 * Va.x;  S[1][5] += p2 * Va.y;
+      S[1][6] += Vb.x;       S[1][7] += Vb.y;
+      S[1][8] += p * Vb.x;   S[1][9] += p * Vb.y;
+      S[1][10] += Vc.x;      S[1][11] += Vc.y;
+    }
+    if (!simple) {
 #pragma unroll
-    for (int sg = 0; sg < 2; sg++) {
-      if (sg == 0 ? !act0 : !act1) continue;
-      const double w = range_w(ipar, pe[sg].lo1, pe[sg].hi1) + range_w(ipar, pe[sg].lo2, pe[sg].hi2);
-      if (w != 0.0) {
-        const double nq = (sg ? -1.0 : 1.0) * (double)nabs * qs;
-        const double dr = dre - kpar * p - nq;
-        const double t = w / (dr * dr + dim * dim);
-        const cd R = mk(dr * t, -dim * t);
-        const cd Va = R * Ga, Vb = R * Gb, Vc = R * Gc;
-        S[sg][0] += Va.x;       S[sg][1] += Va.y;
-        S[sg][2] += p * Va.x;   S[sg][3] += p * Va.y;
-        S[sg][4] += p2 * Va.x;  S[sg][5] += p2 * Va.y;
-        S[sg][6] += Vb.x;       S[sg][7] += Vb.y;
-        S[sg][8] += p * Vb.x;   S[sg][9] += p * Vb.y;
-        S[sg][10] += Vc.x;      S[sg][11] += Vc.y;
-      }
-      if (pe[sg].flags & PLAN_NEAR) {
-        int j = ipar - (pe[sg].ipar_res - M_I - 2);
-        if (j < 0 || j >= WIN) j = (ipar <= 3) ? WIN + ipar - 1 : -1;
-        if (j >= 0) {
-          double* gw = gwin + ((item0 + sg) * WINX + j) * 6;
-          gw[0] = Ga.x; gw[1] = Ga.y; gw[2] = Gb.x; gw[3] = Gb.y; gw[4] = Gc.x; gw[5] = Gc.y;
+      for (int sg = 0; sg < 2; sg++) {
+        if ((sg == 0 ? act0 : act1) && (pe[sg].flags & PLAN_NEAR)) {
+          int j = ipar - (pe[sg].ipar_res - M_I - 2);
+          if (j < 0 || j >= WIN) j = (ipar <= 3) ? WIN + ipar - 1 : -1;
+          if (j >= 0) {
+            double* gw = gwin + ((item0 + sg) * WINX + j) * 6;
+            gw[0] = Ga.x; gw[1] = Ga.y; gw[2] = Gb.x; gw[3] = Gb.y; gw[4] = Gc.x; gw[5] = Gc.y;
+          }
         }
       }
     }
