@@ -14,16 +14,6 @@
 
 namespace alps {
 
-// 1/x for normal, finite x: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps; avoids the
-// IEEE-division slow path.  Relative error ~1e-16, far inside the 1e-9 parity budget.
-__device__ __forceinline__ double fast_rcp(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  y = fma(y, fma(-x, y, 1.0), y);
-  y = fma(y, fma(-x, y, 1.0), y);
-  return y;
-}
-
 __global__ void __launch_bounds__(128) k_fast(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om,
                                               const FastItem* __restrict__ items, const PlanEntry* __restrict__ plan,
                                               double* __restrict__ Sbulk, double* __restrict__ gwin) {
@@ -73,8 +63,10 @@ __global__ void __launch_bounds__(128) k_fast(const GlobalDev* __restrict__ gp, 
       wm = act1 ? range_w(ipar, pe[1].lo1, pe[1].hi1) + range_w(ipar, pe[1].lo2, pe[1].hi2) : 0.0;
     }
     // both reciprocals from one: 1/dp = dm/(dp dm), 1/dm = dp/(dp dm)
-    const double inv = fast_rcp(dp * dm);
-    const double tp = wp * dm * inv, tm = wm * dp * inv;
+    // a sign with zero weight must not poison the shared reciprocal (real omega exactly on a node)
+    const double dps = wp != 0.0 ? dp : 1.0, dms = wm != 0.0 ? dm : 1.0;
+    const double inv = fast_rcp(dps * dms);
+    const double tp = wp * dms * inv, tm = wm * dps * inv;
     {
       const cd R = mk(drp * tp, -dim * tp);
       const cd Va = R * Ga, Vb = R * Gb, Vc = R * Gc;

@@ -338,3 +338,30 @@ def test_batch_chunking_and_api_errors():
         Solver(bad)
     assert e.value.code == -4
     _lib.lib().alps_b200_finalize()
+
+
+def test_real_omega_exactly_on_a_resonant_node():
+    """Im(om) = 0 and Re(p_res) exactly on a p_par node: the node itself sits in the excluded window
+    (weight 0), its 1/den would be infinite.  Both GPU modes must stay finite and agree with the oracle."""
+    from alps_b200.solver import Solver
+    from oracle.oracle import Oracle
+    pl = tables.config_small(24, 48, kind=1)
+    kperp, kpar = 0.3, 0.05
+    ppar = pl.pp[0, 0, :, 1]
+    oms = [complex(kpar * ppar[30] / pl.species[0].ms, 0.0), complex((kpar * ppar[20] + 1.0) / pl.species[0].ms, 0.0)]
+    orc = Oracle(pl)
+    orc.set_k(kperp, kpar)
+    sol = Solver(pl)
+    try:
+        for mode in (0, 1):
+            sol.set_mode(mode)
+            sol.set_k(kperp, kpar)
+            for om in oms:
+                Do, chi_o, _, wave_o = orc.disp(om, full=True)
+                Dg, chi_g, _, wave_g = sol.disp(om, full=True)
+                assert np.all(np.isfinite(chi_g)) and np.isfinite(Dg.real)
+                ws = wave_scale(chi_o, om, pl.vA, kperp, kpar)
+                assert scaled_err(wave_g, wave_o, ws) < TOL, (mode, om)
+                assert abs(Dg - Do) / det_scale(ws) < TOL, (mode, om)
+    finally:
+        sol.close()
