@@ -63,7 +63,7 @@ def build(force: bool = False) -> str:
     csrc = os.path.join(_HERE, "csrc")
     if force:
         subprocess.check_call(["make", "-C", csrc, "-s", "clean"])
-    subprocess.check_call(["make", "-C", csrc, "-s"])
+    subprocess.check_call(["make", "-C", csrc, "-s", "-j", str(min(8, os.cpu_count() or 1))])
     return SO_PATH
 
 

@@ -147,7 +147,7 @@ void for_each_root(const std::vector<std::function<void()> >& jobs) {
 
 // Fortran ESw.dEe edit descriptor (e.g. es14.4e3 -> "   1.0000E-002")
 std::string es(double v, int w, int d, int e) {
-  char buf[64];
+  char buf[128];
   if (std::isnan(v)) {
     snprintf(buf, sizeof(buf), "%*s", w, "NaN");
     return buf;
@@ -161,7 +161,7 @@ std::string es(double v, int w, int d, int e) {
   char* ep = strchr(m, 'E');
   int ex = atoi(ep + 1);
   *ep = 0;
-  char body[64];
+  char body[96];
   snprintf(body, sizeof(body), "%sE%c%0*d", m, ex < 0 ? '-' : '+', e, ex < 0 ? -ex : ex);
   snprintf(buf, sizeof(buf), "%*s", w, body);
   return buf;

@@ -410,11 +410,8 @@ static cudaError_t launch_variant(const QuadParams& P, bool store, cudaStream_t 
 
 QuadVariant quad_variant(int id) {
   switch (id) {
-    case 1: return QuadVariant{1, 16, 16, 4};    // 8 consumer warps + producer, BK=16
-    case 4: return QuadVariant{4, 16, 8, 4};     // 8 consumer warps, inline producer, BK=8
     case 5: return QuadVariant{5, 16, 16, 4};    // 8 consumer warps, inline producer, BK=16
     case 8: return QuadVariant{8, 16, 32, 2};    // 8 consumer warps, inline producer, BK=32, 2 stages
-    case 11: return QuadVariant{11, 16, 32, 2};  // as 8, k loop unrolled by 8 only
     default: return QuadVariant{0, 16, 8, 4};    // 8 consumer warps + producer, BK=8
   }
 }
@@ -422,11 +419,8 @@ QuadVariant quad_variant(int id) {
 cudaError_t launch_quad(const QuadParams& P, int variant, bool store, cudaStream_t st) {
   if (P.n_om <= 0 || P.ntiles <= 0) return cudaSuccess;
   switch (variant) {
-    case 1: return launch_variant<4, 16, 4, 1, 16>(P, store, st);
-    case 4: return launch_variant<4, 8, 4, 0, 8>(P, store, st);
     case 5: return launch_variant<4, 16, 4, 0, 16>(P, store, st);
     case 8: return launch_variant<4, 32, 2, 0, 32>(P, store, st);
-    case 11: return launch_variant<4, 32, 2, 0, 8>(P, store, st);
     default: return launch_variant<4, 8, 4, 1, 8>(P, store, st);
   }
 }
