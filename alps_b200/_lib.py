@@ -23,7 +23,8 @@ SYMBOLS = [
     "alps_b200_om_double_scan", "alps_b200_set_root_batching",
 ]
 
-INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH, INFO_DFMA_NOREUSE = range(6)
+INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH, INFO_DFMA_NOREUSE, \
+    INFO_DMMA_PEAK, INFO_QUAD_VARIANT = range(8)
 
 
 class Cfg(C.Structure):

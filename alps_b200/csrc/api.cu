@@ -26,6 +26,10 @@ struct SpeciesHost {
   double *d_pperp = nullptr, *d_ppar = nullptr, *d_A = nullptr, *d_C0 = nullptr, *d_Cp = nullptr;
   double *d_J = nullptr, *d_W = nullptr, *d_pf = nullptr, *d_poly = nullptr, *d_ee = nullptr, *d_G = nullptr;
   size_t cap_J = 0, cap_W = 0, cap_G = 0;
+  // fragment-ordered operands of the DMMA quadrature variants (quad_mma.cu)
+  double *d_Af = nullptr, *d_Cf = nullptr, *d_Wf = nullptr;
+  size_t cap_Xf = 0, cap_Wf = 0;
+  bool af_valid = false;
   bool grid = false;    // has f0 tables on the (p_perp,p_par) grid (everything but use_bM species)
   bool table = false;   // non-relativistic table species: goes through k_quad
   // relativistic species
@@ -192,6 +196,7 @@ int build_tables_from_df0() {
     d.A = h.d_A;
     d.Cp = h.d_Cp;
     d.C0 = h.d_C0;
+    h.af_valid = false;
   }
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());
@@ -247,7 +252,7 @@ int build_hoisted_tables() {
   P.plan = nullptr;
   P.Sbulk = nullptr;
   P.gwin = nullptr;
-  cudaError_t e = launch_quad(P, S.qv.id, true, S.stream);
+  cudaError_t e = S.qv.id >= 9 ? launch_quad_mma(P, S.qv.id, true, S.stream) : launch_quad(P, S.qv.id, true, S.stream);
   S.launches += 1;
   if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "hoisted-table launch failed: %s", cudaGetErrorString(e));
   CK(cudaStreamSynchronize(S.stream));
@@ -351,7 +356,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     if (S.mode == 1)
       launch_fast(gd, d_om, n, S.d_fitems, (int)S.fitems.size(), S.d_plan, S.d_Sbulk, S.d_gwin, S.stream);
     else
-      e = launch_quad(S.P, S.qv.id, false, S.stream);
+      e = S.qv.id >= 9 ? launch_quad_mma(S.P, S.qv.id, false, S.stream) : launch_quad(S.P, S.qv.id, false, S.stream);
     cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.stream);
@@ -447,7 +452,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.mode = 0;
   {
     const char* v = getenv("ALPS_B200_QUAD_VARIANT");   // tuning knob: tile shape of k_quad
-    S.qv = quad_variant(v ? atoi(v) : 8);
+    S.qv = quad_variant(v ? atoi(v) : 9);
   }
   S.shard_rank = 0;
   S.shard_n = 1;
@@ -463,6 +468,9 @@ void alps_b200_finalize(void) {
   for (int s = 0; s < MAXSPEC; s++) {
     SpeciesHost& h = S.sp[s];
     dfree(&h.d_pperp); dfree(&h.d_ppar); dfree(&h.d_A); dfree(&h.d_C0); dfree(&h.d_Cp); dfree(&h.d_J);
+    dfree(&h.d_Af); dfree(&h.d_Cf); dfree(&h.d_Wf);
+    h.cap_Xf = h.cap_Wf = 0;
+    h.af_valid = false;
     dfree(&h.d_W); dfree(&h.d_pf); dfree(&h.d_poly); dfree(&h.d_ee); dfree(&h.d_G);
     dfree(&h.d_grel); dfree(&h.d_pbrel); dfree(&h.d_f0rel); dfree(&h.d_dfg); dfree(&h.d_dfp);
     dfree(&h.d_cone_lo); dfree(&h.d_cone_up);
@@ -728,6 +736,8 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
     for (int s = 0; s < nspec; s++) nhi[s] = S.gh.sp[s].nhi;
   }
   // ---- tables
+  const bool mma = S.qv.id >= 9;                                   // DMMA variants: fragment-ordered operands
+  const int nks = ((((nperp - 1) + 3) / 4) + 7) & ~7;              // k-steps of 4 p_perp rows, padded to 8
   int item_base = 0;
   S.tiles.clear();
   S.rtiles.clear();
@@ -754,22 +764,55 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
         if (dalloc(&h.d_J, nJ)) return ALPS_B200_ERR_CUDA;
         h.cap_J = nJ;
       }
-      d.ldw = (3 * (d.nhi + 1) + 1) & ~1;
-      const size_t nW = (size_t)(nperp - 1) * d.ldw;
-      if (nW > h.cap_W) {
-        if (dalloc(&h.d_W, nW)) return ALPS_B200_ERR_CUDA;
-        h.cap_W = nW;
-      }
-      CK(cudaMemsetAsync(h.d_W, 0, nW * sizeof(double), S.stream));
       launch_bessel_table(h.d_pperp, nperp, kperp, d.qs, d.nhi, h.d_J, d.ldj, S.stream);
-      launch_build_W(h.d_pperp, h.d_J, d.ldj, nperp, d.nhi, h.d_W, d.ldw, S.stream);
-      S.launches += 2;
       d.J = h.d_J;
-      d.W = h.d_W;
+      if (mma && h.table) {
+        const int nhb = (d.nhi + MMA_NH) / MMA_NH;
+        const size_t nW = (size_t)nhb * nks * 192;
+        if (nW > h.cap_Wf) {
+          if (dalloc(&h.d_Wf, nW)) return ALPS_B200_ERR_CUDA;
+          h.cap_Wf = nW;
+        }
+        launch_build_Wf(h.d_pperp, h.d_J, d.ldj, nperp, d.nhi, h.d_Wf, nks, nhb, S.stream);
+      } else {
+        d.ldw = (3 * (d.nhi + 1) + 1) & ~1;
+        const size_t nW = (size_t)(nperp - 1) * d.ldw;
+        if (nW > h.cap_W) {
+          if (dalloc(&h.d_W, nW)) return ALPS_B200_ERR_CUDA;
+          h.cap_W = nW;
+        }
+        CK(cudaMemsetAsync(h.d_W, 0, nW * sizeof(double), S.stream));
+        launch_build_W(h.d_pperp, h.d_J, d.ldj, nperp, d.nhi, h.d_W, d.ldw, S.stream);
+        d.W = h.d_W;
+      }
+      S.launches += 2;
     }
     if (d.relativistic) {
       d.int_ee = h.ee_rel;
       for (int n = d.nlo_shard; n <= d.nhi_shard; n++) S.rtiles.push_back(RelTile{s, n});
+      continue;
+    }
+    if (mma) {
+      // fragment-ordered A' (once per upload) and C' = kpar * C0 (per k)
+      const int ntp = (npar - 1 + BN - 1) / BN;
+      const size_t nX = (size_t)ntp * nks * 512;
+      if (nX > h.cap_Xf) {
+        if (dalloc(&h.d_Af, nX) || dalloc(&h.d_Cf, nX)) return ALPS_B200_ERR_CUDA;
+        h.cap_Xf = nX;
+        h.af_valid = false;
+      }
+      if (!h.af_valid) {
+        launch_frag_table(h.d_A, d.ldp, nperp - 1, npar - 1, 1.0, h.d_Af, nks, ntp, S.stream);
+        S.launches += 1;
+        h.af_valid = true;
+      }
+      launch_frag_table(h.d_C0, d.ldp, nperp - 1, npar - 1, kpar, h.d_Cf, nks, ntp, S.stream);
+      S.launches += 1;
+      S.P.Af[s] = h.d_Af;
+      S.P.Cf[s] = h.d_Cf;
+      S.P.Wf[s] = h.d_Wf;
+      S.P.nks = nks;
+      for (int n0 = (d.nlo_shard / MMA_NH) * MMA_NH; n0 <= d.nhi_shard; n0 += MMA_NH) S.tiles.push_back(QuadTile{s, n0});
       continue;
     }
     // C' = kpar * C0
@@ -1014,6 +1057,8 @@ int alps_b200_get_info(int what, double* out) {
     case ALPS_B200_INFO_LAST_KERNEL_MS: *out = S.last_kernel_ms; return 0;
     case ALPS_B200_INFO_BATCH: *out = S.have_k ? auto_batch() : 0; return 0;
     case ALPS_B200_INFO_DFMA_NOREUSE: *out = run_dfma_peak_noreuse(S.stream); S.launches += 3; return 0;
+    case ALPS_B200_INFO_DMMA_PEAK: *out = run_dmma_peak(S.stream); S.launches += 3; return 0;
+    case ALPS_B200_INFO_QUAD_VARIANT: *out = S.qv.id; return 0;
   }
   return fail(ALPS_B200_ERR_USAGE, "unknown info id %d", what);
 }

@@ -27,7 +27,13 @@ struct QuadParams {
   int ntiles;
   int n_om;
   int nsplit;              // CTAs per (omega, tile) along p_par; Sbulk then holds nsplit partial rows per item
+  // DMMA variants (quad_mma.cu): fragment-ordered copies of A', C', W and their padded k-step count
+  const double* Af[MAXSPEC];
+  const double* Cf[MAXSPEC];
+  const double* Wf[MAXSPEC];
+  int nks;
 };
+constexpr int MMA_NH = 16;   // harmonics per CTA tile of the DMMA variants
 
 // set-up (setup_kernels.cu)
 void launch_derivative_f0(const double* f0, const double* pp, double* df0, int nspec, int nperp, int npar,
@@ -41,6 +47,11 @@ void launch_bessel_table(const double* pperp, int nperp, double kperp, double qs
                          cudaStream_t st);
 void launch_build_W(const double* pperp, const double* J, int ldj, int nperp, int nhi, double* W, int ldw,
                     cudaStream_t st);
+// fragment-ordered operands of the DMMA quadrature kernel (layouts: quad_mma.cu)
+void launch_frag_table(const double* X, int ldp, int nrows, int ncols, double scale, double* Xf, int nks, int ntiles,
+                       cudaStream_t st);
+void launch_build_Wf(const double* pperp, const double* J, int ldj, int nperp, int nhi, double* Wf, int nks, int nhb,
+                     cudaStream_t st);
 void launch_int_ee(const double* df0, const double* pperp, const double* ppar, int nspec, int nperp, int npar,
                    int is0, double qs, double ms, double dpperp, double dppar, double* out, cudaStream_t st);
 
@@ -53,6 +64,8 @@ struct QuadVariant {
 };
 QuadVariant quad_variant(int id);
 cudaError_t launch_quad(const QuadParams& P, int variant, bool store, cudaStream_t st);
+cudaError_t launch_quad_mma(const QuadParams& P, int variant, bool store, cudaStream_t st);   // variants >= 9
+double run_dmma_peak(cudaStream_t st);
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
                  int* work, int* work_count, cudaStream_t st);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,

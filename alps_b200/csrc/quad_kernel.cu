@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "pipe.cuh"
 
 namespace alps {
 
@@ -44,51 +45,6 @@ struct QuadSmem {
   unsigned long long full[NST];
   unsigned long long empty[NST];
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ uint32_t mbar_test(unsigned long long* b, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(b)), "r"(parity)
-      : "memory");
-  return ok;
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -410,6 +366,7 @@ static cudaError_t launch_variant(const QuadParams& P, bool store, cudaStream_t 
 
 QuadVariant quad_variant(int id) {
   switch (id) {
+    case 9: case 10: case 11: return QuadVariant{id, MMA_NH, id == 9 ? 32 : 16, id == 9 ? 2 : (id == 10 ? 4 : 3)};   // DMMA (quad_mma.cu)
     case 5: return QuadVariant{5, 16, 16, 4};    // 8 consumer warps, inline producer, BK=16
     case 8: return QuadVariant{8, 16, 32, 2};    // 8 consumer warps, inline producer, BK=32, 2 stages
     default: return QuadVariant{0, 16, 8, 4};    // 8 consumer warps + producer, BK=8

@@ -1,0 +1,326 @@
+// alps_b200: the regular (p_perp, p_par) quadrature of chi_s(omega,k) on the FP64 tensor pipe (DMMA).
+//
+// Replaces: integrate() and its resU()/int_T() calls, src/ALPS_fns.f90:799-864, 1560-1707 -- the same
+// formulation as quad_kernel.cu (which stays as the DFMA variants 0/5/8):
+//     G_x(n, ipar) = sum_iperp W_x(n, iperp) * {A', C'}(iperp, ipar),      x = a, b, c
+// is a real contraction over p_perp with omega-independent operands; omega enters once per column,
+// G = om * GA + GB, in the epilogue that applies the resonance denominators, the p_par trapezoid
+// weights of the resonance plan and the p_par moments.  Here the contraction is issued as
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): the same 64 FMA/clk/SM FP64 units as DFMA, but one warp
+// instruction carries 256 FMAs and reads 4 registers, so the pipe is not limited by instruction issue,
+// register-file bandwidth or shared-memory operand traffic (measured: DMMA 37.07 TFLOP/s, DFMA 33.3).
+//
+// Operands are pre-arranged in HBM in fragment order (setup_kernels.cu: k_frag_table, k_build_Wf):
+//   Xf[nt][ks][512]  table tile of 128 p_par columns x 4 p_perp rows (k-step ks): element
+//                    (row 4 ks + t, column 128 nt + 16 w + 8 j + g) at 64 w + 2 (4 g + t) + j
+//   Wf[hb][ks][192]  weights of harmonics 16 hb .. 16 hb + 15: element (row 4 ks + t, type x,
+//                    harmonic 16 hb + 8 h + g) at 6 (4 g + t) + 2 x + h
+// so a pipeline stage is one contiguous TMA bulk copy per operand and every thread fetches its DMMA
+// fragments with conflict-free LDS.128.  Zero padding (rows to 32, columns to 128, harmonics to 16)
+// lives in the buffers.
+//
+// CTA = (omega, species, 16 harmonics) x all p_par tiles (or every nsplit-th), 8 warps; warp w owns the
+// 48 x 16 block of columns 16 w .. 16 w + 15 for both tables: 6 M-tiles x (2 + 2) N-tiles = 24 DMMA per
+// k-step, 48 FP64 accumulators per thread.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "pipe.cuh"
+
+namespace alps {
+
+constexpr int KS_A = 4 * BN;            // doubles per k-step of one table tile
+constexpr int KS_W = 4 * 3 * MMA_NH;    // doubles per k-step of one weight tile
+
+template <int KSTG>
+struct alignas(128) MmaStage {
+  double A[KSTG * KS_A];
+  double C[KSTG * KS_A];
+  double W[KSTG * KS_W];
+};
+
+template <int KSTG, int NST>
+struct MmaSmem {
+  MmaStage<KSTG> st[NST];
+  double red[8][MMA_NH][2][12];   // [warp][harmonic][sign][12]
+  unsigned long long full[NST];
+  unsigned long long empty[NST];
+};
+
+// D(8x8) += A(8x4, row) * B(4x8, col); lane = 4 g + t holds A[g][t], B[t][g], C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+template <int KSTG, int NST, bool STORE>
+__global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ QuadParams P) {
+  constexpr uint32_t BYTES_A = KSTG * KS_A * sizeof(double);
+  constexpr uint32_t BYTES_W = KSTG * KS_W * sizeof(double);
+  typedef MmaSmem<KSTG, NST> Smem;
+  extern __shared__ unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+
+  const int nsplit = P.nsplit;
+  const int jsplit = blockIdx.x % nsplit;
+  const int tile_id = (blockIdx.x / nsplit) % P.ntiles;
+  const int iom = blockIdx.x / (nsplit * P.ntiles);
+  const QuadTile tile = P.tiles[tile_id];
+  const GlobalDev& g = *P.g;
+  const SpeciesDev& sp = g.sp[tile.s];
+  const int npar = g.npar;
+  const int NKS = P.nks;
+  const int KC = NKS / KSTG;
+  const int NTall = (npar - 1 + BN - 1) / BN;
+  const int NT = (NTall - jsplit + nsplit - 1) / nsplit;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; s++) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const double* __restrict__ gA = P.Af[tile.s];
+  const double* __restrict__ gC = P.Cf[tile.s];
+  const double* __restrict__ gW = P.Wf[tile.s] + (size_t)(tile.n0 / MMA_NH) * NKS * KS_W;
+  const int T = NT * KC;
+  auto issue = [&](int it) {
+    const int stg = it % NST, ntl = it / KC, kc = it - ntl * KC, nt = jsplit + ntl * nsplit;
+    const size_t ks0 = (size_t)nt * NKS + (size_t)kc * KSTG;
+    mbar_expect_tx(&sm.full[stg], 2 * BYTES_A + BYTES_W);
+    tma_load_1d(sm.st[stg].A, gA + ks0 * KS_A, BYTES_A, &sm.full[stg]);
+    tma_load_1d(sm.st[stg].C, gC + ks0 * KS_A, BYTES_A, &sm.full[stg]);
+    tma_load_1d(sm.st[stg].W, gW + (size_t)kc * KSTG * KS_W, BYTES_W, &sm.full[stg]);
+  };
+  if (threadIdx.x == 0)
+    for (int it = 0; it < NST - 1 && it < T; it++) issue(it);
+
+  const double omr = P.om[2 * iom], omi = P.om[2 * iom + 1];
+  const double qs = sp.qs, ms = sp.ms, kpar = g.kpar;
+  const double* __restrict__ ppar = sp.ppar;
+  const size_t item0 = (size_t)iom * g.NI + sp.item_base;
+  const int WIN = g.WIN, WINX = g.WINX, M_I = g.M_I;
+
+  double mine[12];   // this lane's share of the moment sums: harmonic n0 + 8 (tq >> 1) + gq, sign tq & 1
+#pragma unroll
+  for (int q = 0; q < 12; q++) mine[q] = 0.0;
+
+  int stage = 0;
+  uint32_t phase = 0, ready = 0;
+  int git = 0;
+  for (int ntl = 0; ntl < NT; ntl++) {
+    const int nt = jsplit + ntl * nsplit;
+    double acc[6][2][2][2];   // [M-tile 2 x + h][table: 0 = A', 1 = C'][N-tile j][column pair]
+#pragma unroll
+    for (int m = 0; m < 6; m++)
+#pragma unroll
+      for (int q = 0; q < 8; q++) (&acc[m][0][0][0])[q] = 0.0;
+
+    for (int kc = 0; kc < KC; kc++, git++) {
+      if (threadIdx.x == 0) {
+        const int nx = git + NST - 1;
+        if (nx < T) {
+          if (nx >= NST) mbar_wait(&sm.empty[nx % NST], ((nx / NST) & 1) ^ 1);
+          issue(nx);
+        }
+      }
+      __syncwarp();
+      if (!ready) mbar_wait(&sm.full[stage], phase);
+      {
+        const int ns = (stage + 1 == NST) ? 0 : stage + 1;
+        ready = mbar_test(&sm.full[ns], (stage + 1 == NST) ? (phase ^ 1) : phase);
+      }
+      const double* sA = sm.st[stage].A + 64 * warp + 2 * lane;
+      const double* sC = sm.st[stage].C + 64 * warp + 2 * lane;
+      const double* sW = sm.st[stage].W + 6 * lane;
+#pragma unroll
+      for (int ks = 0; ks < KSTG; ks++) {
+        const double2 a = *reinterpret_cast<const double2*>(sA + ks * KS_A);
+        const double2 c = *reinterpret_cast<const double2*>(sC + ks * KS_A);
+        const double2 w0 = reinterpret_cast<const double2*>(sW + ks * KS_W)[0];
+        const double2 w1 = reinterpret_cast<const double2*>(sW + ks * KS_W)[1];
+        const double2 w2 = reinterpret_cast<const double2*>(sW + ks * KS_W)[2];
+        const double wv[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+          dmma(acc[m][0][0], wv[m], a.x);
+          dmma(acc[m][0][1], wv[m], a.y);
+          dmma(acc[m][1][0], wv[m], c.x);
+          dmma(acc[m][1][1], wv[m], c.y);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+      if (++stage == NST) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+
+    // ------------------------------------------------------------ epilogue of this p_par tile
+    // this thread: harmonics n0 + 8 h + gq (h = 0,1), columns ipar = ipar0 + 8 j + e (j, e = 0,1)
+    const int ipar0 = nt * BN + 16 * warp + 2 * tq + 1;
+    if (STORE) {
+      // k-hoisted tables (alps_b200_set_mode(1)): layout [n][ipar-1][GAa, GBa, GAb, GBb, GAc, GBc]
+      double* gt = P.gtab[tile.s];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int nabs = tile.n0 + 8 * h + gq;
+        if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int ipar = ipar0 + 8 * j + e;
+            if (ipar > npar - 1) continue;
+            double2* o = reinterpret_cast<double2*>(gt + ((size_t)nabs * (npar - 1) + (ipar - 1)) * 6);
+#pragma unroll
+            for (int x = 0; x < 3; x++) o[x] = make_double2(acc[2 * x + h][0][j][e], acc[2 * x + h][1][j][e]);
+          }
+      }
+      continue;
+    }
+    // G = om * GA + GB: real part into the C' slot, imaginary part into the A' slot
+#pragma unroll
+    for (int m = 0; m < 6; m++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double ga = (&acc[m][0][0][0])[q];
+        (&acc[m][1][0][0])[q] = fma(omr, ga, (&acc[m][1][0][0])[q]);
+        (&acc[m][0][0][0])[q] = omi * ga;
+      }
+    double pp_[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int ipar = ipar0 + 8 * j + e;
+        pp_[j][e] = (ipar <= npar - 1) ? ppar[ipar] : 0.0;
+      }
+    double Sv[48];   // [h][sign][12]
+#pragma unroll
+    for (int q = 0; q < 48; q++) Sv[q] = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int nabs = tile.n0 + 8 * h + gq;
+      if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
+#pragma unroll
+      for (int sg = 0; sg < 2; sg++) {
+        if (nabs == 0 && sg == 1) continue;
+        const size_t item = item0 + 2 * nabs + sg;
+        const PlanEntry pe = P.plan[item];
+        if (!(pe.flags & PLAN_ACTIVE)) continue;
+        const double nq = (sg ? -1.0 : 1.0) * (double)nabs * qs;
+        double* S = &Sv[(h * 2 + sg) * 12];
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int ipar = ipar0 + 8 * j + e;
+            if (ipar > npar - 1) continue;
+            const double w = range_w(ipar, pe.lo1, pe.hi1) + range_w(ipar, pe.lo2, pe.hi2);
+            const double p = pp_[j][e];
+            if (w != 0.0) {
+              // 1/den with den = ms om - kpar p_par - n qs   (resU, src/ALPS_fns.f90:1591-1592)
+              const double dr = ms * omr - kpar * p - nq, di = ms * omi;
+              const double t = w / (dr * dr + di * di);
+              const cd R = mk(dr * t, -di * t);
+              const cd Va = R * mk(acc[0 + h][1][j][e], acc[0 + h][0][j][e]);
+              const cd Vb = R * mk(acc[2 + h][1][j][e], acc[2 + h][0][j][e]);
+              const cd Vc = R * mk(acc[4 + h][1][j][e], acc[4 + h][0][j][e]);
+              const double p2 = p * p;
+              S[0] += Va.x;       S[1] += Va.y;        // sum U J^2
+              S[2] += p * Va.x;   S[3] += p * Va.y;    // sum U J^2 p_par
+              S[4] += p2 * Va.x;  S[5] += p2 * Va.y;   // sum U J^2 p_par^2
+              S[6] += Vb.x;       S[7] += Vb.y;        // sum U p_perp J J'
+              S[8] += p * Vb.x;   S[9] += p * Vb.y;    // sum U p_perp J J' p_par
+              S[10] += Vc.x;      S[11] += Vc.y;       // sum U p_perp^2 J'^2
+            }
+            if (pe.flags & PLAN_NEAR) {
+              int jw = ipar - (pe.ipar_res - M_I - 2);
+              if (jw < 0 || jw >= WIN) jw = (ipar <= 3) ? WIN + ipar - 1 : -1;   // nodes 1..3: funct_g fallback
+              if (jw >= 0) {
+                double* gw = P.gwin + (item * WINX + jw) * 6;
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                  gw[2 * x] = acc[2 * x + h][1][j][e];
+                  gw[2 * x + 1] = acc[2 * x + h][0][j][e];
+                }
+              }
+            }
+          }
+      }
+    }
+    // recursive halving over the 4 lanes that share gq (lane bits 1, 0): the lane with tq = 2 h + sg
+    // ends with the 12 sums of (harmonic h, sign sg)
+#pragma unroll
+    for (int step = 0; step < 2; step++) {
+      const int N = 24 >> step, mask = 2 >> step;
+      const bool up = (lane & mask) != 0;
+#pragma unroll
+      for (int i = 0; i < 24; i++) {
+        if (i < N) {
+          const double send = up ? Sv[i] : Sv[i + N];
+          const double keep = up ? Sv[i + N] : Sv[i];
+          Sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 12; q++) mine[q] += Sv[q];
+  }
+
+  if (STORE) return;
+  // ---------------------------------------------------------------- write the moment sums
+  {
+    double* red = &sm.red[warp][8 * (tq >> 1) + gq][tq & 1][0];
+#pragma unroll
+    for (int q = 0; q < 12; q++) red[q] = mine[q];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < MMA_NH * 24; i += 256) {
+    const int nn = i / 24, sg = (i % 24) / 12, q = i % 12;
+    const int nabs = tile.n0 + nn;
+    if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) t += sm.red[w][nn][sg][q];
+    P.Sbulk[((item0 + 2 * nabs + sg) * nsplit + jsplit) * 12 + q] = t;
+  }
+}
+
+template <int KSTG, int NST, bool STORE>
+static cudaError_t launch_mma_one(const QuadParams& P, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = sizeof(MmaSmem<KSTG, NST>) + 128;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_quad_mma<KSTG, NST, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_quad_mma<KSTG, NST, STORE><<<P.n_om * P.ntiles * P.nsplit, 256, smem, st>>>(P);
+  return cudaGetLastError();
+}
+template <int KSTG, int NST>
+static cudaError_t launch_mma_variant(const QuadParams& P, bool store, cudaStream_t st) {
+  return store ? launch_mma_one<KSTG, NST, true>(P, st) : launch_mma_one<KSTG, NST, false>(P, st);
+}
+
+cudaError_t launch_quad_mma(const QuadParams& P, int variant, bool store, cudaStream_t st) {
+  if (P.n_om <= 0 || P.ntiles <= 0) return cudaSuccess;
+  switch (variant) {
+    case 10: return launch_mma_variant<4, 4>(P, store, st);
+    case 11: return launch_mma_variant<4, 3>(P, store, st);
+    default: return launch_mma_variant<8, 2>(P, store, st);
+  }
+}
+
+}  // namespace alps

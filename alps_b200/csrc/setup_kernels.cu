@@ -1,4 +1,6 @@
 // alps_b200: table set-up kernels (run at upload and whenever k changes; not the hot loop).
+#include <algorithm>
+
 #include "bessel.cuh"
 #include "kernels.h"
 
@@ -110,6 +112,44 @@ __global__ void k_build_W(const double* __restrict__ pperp, const double* __rest
   w[2] = wc;
 }
 
+// Fragment-ordered operands of the DMMA kernel (quad_mma.cu).  Xf[nt][ks][512]: the 4 x 128 block of
+// rows 4 ks .. 4 ks + 3 and columns 128 nt .. 128 nt + 127 of scale * X, element (t, 16 w + 8 j + g) at
+// 64 w + 2 (4 g + t) + j.  One thread per output element; padding elements are written as zero.
+__global__ void k_frag_table(const double* __restrict__ X, int ldp, int nrows, int ncols, double scale,
+                             double* __restrict__ Xf, int nks, size_t total) {
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int in = (int)(o & 511);
+    const size_t blk = o >> 9;
+    const int ks = (int)(blk % nks), nt = (int)(blk / nks);
+    const int w = in >> 6, l = (in >> 1) & 31, j = in & 1, g = l >> 2, t = l & 3;
+    const int r = 4 * ks + t, c = 128 * nt + 16 * w + 8 * j + g;
+    Xf[o] = (r < nrows && c < ncols) ? scale * X[(size_t)r * ldp + c] : 0.0;
+  }
+}
+
+// Wf[hb][ks][192]: weights (same values as k_build_W) of harmonics 16 hb .. 16 hb + 15 on rows
+// iperp - 1 = 4 ks + t: element (t, type x, harmonic 16 hb + 8 h + g) at 6 (4 g + t) + 2 x + h.
+__global__ void k_build_Wf(const double* __restrict__ pperp, const double* __restrict__ J, int ldj, int nperp,
+                           int nhi, double* __restrict__ Wf, int nks, size_t total) {
+  for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+    const int in = (int)(o % 192);
+    const size_t blk = o / 192;
+    const int ks = (int)(blk % nks), hb = (int)(blk / nks);
+    const int l = in / 6, m = in % 6, x = m >> 1, h = m & 1, g = l >> 2, t = l & 3;
+    const int iperp = 4 * ks + t + 1, n = 16 * hb + 8 * h + g;
+    double v = 0.0;
+    if (iperp <= nperp - 1 && n <= nhi) {
+      double wperp = (iperp == nperp - 1) ? 1.0 : 2.0;
+      double bj = J[(size_t)(n + 1) * ldj + iperp];
+      double bp = (n >= 1) ? 0.5 * (J[(size_t)n * ldj + iperp] - J[(size_t)(n + 2) * ldj + iperp])
+                           : -J[(size_t)2 * ldj + iperp];
+      double p = pperp[iperp];
+      v = (x == 0) ? wperp * (bj * bj) : (x == 1) ? wperp * (p * (bj * bp)) : wperp * ((p * p) * (bp * bp));
+    }
+    Wf[o] = v;
+  }
+}
+
 // int_ee, src/ALPS_fns.f90:1457-1555 (omega independent): one block per species, read from
 // the Fortran-layout df0.  Weights: iperp=1 -> 2, interior -> 2, nperp-1 -> 1 ; ipar ends -> 1,
 // interior -> 2; the (1,1) corner multiplies d_perp f0 by p_perp where every other term uses
@@ -172,6 +212,18 @@ void launch_build_W(const double* pperp, const double* J, int ldj, int nperp, in
   int ncols = ldw / 3 + 1;
   dim3 g((ncols + 63) / 64, nperp - 1);
   k_build_W<<<g, 64, 0, st>>>(pperp, J, ldj, nperp, nhi, W, ldw);
+}
+void launch_frag_table(const double* X, int ldp, int nrows, int ncols, double scale, double* Xf, int nks, int ntiles,
+                       cudaStream_t st) {
+  const size_t total = (size_t)ntiles * nks * 512;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+  k_frag_table<<<blocks, 256, 0, st>>>(X, ldp, nrows, ncols, scale, Xf, nks, total);
+}
+void launch_build_Wf(const double* pperp, const double* J, int ldj, int nperp, int nhi, double* Wf, int nks, int nhb,
+                     cudaStream_t st) {
+  const size_t total = (size_t)nhb * nks * 192;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+  k_build_Wf<<<blocks, 256, 0, st>>>(pperp, J, ldj, nperp, nhi, Wf, nks, total);
 }
 void launch_int_ee(const double* df0, const double* pperp, const double* ppar, int nspec, int nperp, int npar,
                    int is0, double qs, double ms, double dpperp, double dppar, double* out, cudaStream_t st) {

@@ -140,6 +140,8 @@ int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
 #define ALPS_B200_INFO_BATCH 4            /* internal omega chunk size                          */
 #define ALPS_B200_INFO_DFMA_NOREUSE 5     /* DFMA micro-benchmark with three fresh operands per FMA,
                                              TFLOP/s (register-read limit of tiled FP64 kernels)  */
+#define ALPS_B200_INFO_DMMA_PEAK 6        /* FP64 tensor-pipe micro-benchmark (mma.sync.m8n8k4.f64), TFLOP/s */
+#define ALPS_B200_INFO_QUAD_VARIANT 7     /* id of the quadrature kernel variant in use (>= 9: DMMA) */
 
 /* ------------------------------------------------------------------------------------------
  * Host-side twins of the reference's omega-point generators (alps_b200/csrc/drivers.cpp).  They
