@@ -262,7 +262,7 @@ int build_hoisted_tables() {
 
 constexpr int SMALL_BATCH = 64;
 int nsplit_small() {
-  const int NT = (S.cfg.npar - 1 + BN - 1) / BN;
+  const int NT = (S.cfg.npar - 1 + S.qv.bn - 1) / S.qv.bn;
   return std::max(1, std::min(NT, (2 * S.sm_count) / std::max(1, (int)S.tiles.size())));
 }
 
@@ -452,7 +452,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.mode = 0;
   {
     const char* v = getenv("ALPS_B200_QUAD_VARIANT");   // tuning knob: tile shape of k_quad
-    S.qv = quad_variant(v ? atoi(v) : 9);
+    S.qv = quad_variant(v ? atoi(v) : 15);
   }
   S.shard_rank = 0;
   S.shard_n = 1;
@@ -794,19 +794,19 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
     }
     if (mma) {
       // fragment-ordered A' (once per upload) and C' = kpar * C0 (per k)
-      const int ntp = (npar - 1 + BN - 1) / BN;
-      const size_t nX = (size_t)ntp * nks * 512;
+      const int tw = S.qv.bn, ntp = (npar - 1 + tw - 1) / tw;
+      const size_t nX = (size_t)ntp * nks * 4 * tw;
       if (nX > h.cap_Xf) {
         if (dalloc(&h.d_Af, nX) || dalloc(&h.d_Cf, nX)) return ALPS_B200_ERR_CUDA;
         h.cap_Xf = nX;
         h.af_valid = false;
       }
       if (!h.af_valid) {
-        launch_frag_table(h.d_A, d.ldp, nperp - 1, npar - 1, 1.0, h.d_Af, nks, ntp, S.stream);
+        launch_frag_table(h.d_A, d.ldp, nperp - 1, npar - 1, 1.0, h.d_Af, nks, tw, ntp, S.stream);
         S.launches += 1;
         h.af_valid = true;
       }
-      launch_frag_table(h.d_C0, d.ldp, nperp - 1, npar - 1, kpar, h.d_Cf, nks, ntp, S.stream);
+      launch_frag_table(h.d_C0, d.ldp, nperp - 1, npar - 1, kpar, h.d_Cf, nks, tw, ntp, S.stream);
       S.launches += 1;
       S.P.Af[s] = h.d_Af;
       S.P.Cf[s] = h.d_Cf;

@@ -48,8 +48,8 @@ void launch_bessel_table(const double* pperp, int nperp, double kperp, double qs
 void launch_build_W(const double* pperp, const double* J, int ldj, int nperp, int nhi, double* W, int ldw,
                     cudaStream_t st);
 // fragment-ordered operands of the DMMA quadrature kernel (layouts: quad_mma.cu)
-void launch_frag_table(const double* X, int ldp, int nrows, int ncols, double scale, double* Xf, int nks, int ntiles,
-                       cudaStream_t st);
+void launch_frag_table(const double* X, int ldp, int nrows, int ncols, double scale, double* Xf, int nks, int tw,
+                       int ntiles, cudaStream_t st);
 void launch_build_Wf(const double* pperp, const double* J, int ldj, int nperp, int nhi, double* Wf, int nks, int nhb,
                      cudaStream_t st);
 void launch_int_ee(const double* df0, const double* pperp, const double* ppar, int nspec, int nperp, int npar,
@@ -61,6 +61,7 @@ struct QuadVariant {
   int NH;       // harmonics per CTA tile (rows = 3 NH)
   int BK;       // p_perp rows per pipeline stage
   int stages;
+  int bn;       // p_par columns per tile
 };
 QuadVariant quad_variant(int id);
 cudaError_t launch_quad(const QuadParams& P, int variant, bool store, cudaStream_t st);

@@ -366,10 +366,16 @@ static cudaError_t launch_variant(const QuadParams& P, bool store, cudaStream_t 
 
 QuadVariant quad_variant(int id) {
   switch (id) {
-    case 9: case 10: case 11: return QuadVariant{id, MMA_NH, id == 9 ? 32 : 16, id == 9 ? 2 : (id == 10 ? 4 : 3)};   // DMMA (quad_mma.cu)
-    case 5: return QuadVariant{5, 16, 16, 4};    // 8 consumer warps, inline producer, BK=16
-    case 8: return QuadVariant{8, 16, 32, 2};    // 8 consumer warps, inline producer, BK=32, 2 stages
-    default: return QuadVariant{0, 16, 8, 4};    // 8 consumer warps + producer, BK=8
+    // DMMA (quad_mma.cu)
+    case 9: return QuadVariant{9, MMA_NH, 32, 2, 128};
+    case 12: return QuadVariant{12, MMA_NH, 32, 2, 64};
+    case 15: case 91: case 92: case 93: return QuadVariant{id, MMA_NH, 32, 2, 128};
+    case 16: return QuadVariant{16, MMA_NH, 16, 4, 128};
+    case 17: return QuadVariant{17, MMA_NH, 32, 2, 64};
+    // DFMA
+    case 5: return QuadVariant{5, 16, 16, 4, BN};    // 8 consumer warps, inline producer, BK=16
+    case 8: return QuadVariant{8, 16, 32, 2, BN};    // 8 consumer warps, inline producer, BK=32, 2 stages
+    default: return QuadVariant{0, 16, 8, 4, BN};    // 8 consumer warps + producer, BK=8
   }
 }
 

@@ -11,17 +11,18 @@
 // register-file bandwidth or shared-memory operand traffic (measured: DMMA 37.07 TFLOP/s, DFMA 33.3).
 //
 // Operands are pre-arranged in HBM in fragment order (setup_kernels.cu: k_frag_table, k_build_Wf):
-//   Xf[nt][ks][512]  table tile of 128 p_par columns x 4 p_perp rows (k-step ks): element
-//                    (row 4 ks + t, column 128 nt + 16 w + 8 j + g) at 64 w + 2 (4 g + t) + j
+//   Xf[nt][ks][4 TW] table tile of TW = 16 NW p_par columns x 4 p_perp rows (k-step ks): element
+//                    (row 4 ks + t, column TW nt + 16 w + 8 j + g) at 64 w + 2 (4 g + t) + j
 //   Wf[hb][ks][192]  weights of harmonics 16 hb .. 16 hb + 15: element (row 4 ks + t, type x,
 //                    harmonic 16 hb + 8 h + g) at 6 (4 g + t) + 2 x + h
 // so a pipeline stage is one contiguous TMA bulk copy per operand and every thread fetches its DMMA
 // fragments with conflict-free LDS.128.  Zero padding (rows to 32, columns to 128, harmonics to 16)
 // lives in the buffers.
 //
-// CTA = (omega, species, 16 harmonics) x all p_par tiles (or every nsplit-th), 8 warps; warp w owns the
+// CTA = (omega, species, 16 harmonics) x all p_par tiles (or every nsplit-th), NW warps; warp w owns the
 // 48 x 16 block of columns 16 w .. 16 w + 15 for both tables: 6 M-tiles x (2 + 2) N-tiles = 24 DMMA per
-// k-step, 48 FP64 accumulators per thread.
+// k-step, 48 FP64 accumulators per thread.  NW = 4 runs two CTAs per SM, so that the epilogue of one
+// CTA (FP64 pipe, shuffles) overlaps the DMMA stream of the other.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,20 +31,20 @@
 
 namespace alps {
 
-constexpr int KS_A = 4 * BN;            // doubles per k-step of one table tile
 constexpr int KS_W = 4 * 3 * MMA_NH;    // doubles per k-step of one weight tile
 
-template <int KSTG>
+// NW = warps per CTA = 16-column blocks per p_par tile (tile width TW = 16 NW), KSTG = k-steps per stage
+template <int NW, int KSTG>
 struct alignas(128) MmaStage {
-  double A[KSTG * KS_A];
-  double C[KSTG * KS_A];
+  double A[KSTG * 64 * NW];
+  double C[KSTG * 64 * NW];
   double W[KSTG * KS_W];
 };
 
-template <int KSTG, int NST>
+template <int NW, int KSTG, int NST>
 struct MmaSmem {
-  MmaStage<KSTG> st[NST];
-  double red[8][MMA_NH][2][12];   // [warp][harmonic][sign][12]
+  MmaStage<NW, KSTG> st[NST];
+  double red[NW][MMA_NH][2][12];   // [warp][harmonic][sign][12]
   unsigned long long full[NST];
   unsigned long long empty[NST];
 };
@@ -55,11 +56,19 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-template <int KSTG, int NST, bool STORE>
-__global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ QuadParams P) {
+// HS = 1: a warp owns all 16 harmonics of its 16 columns (6 M-tiles); HS = 2: two warps share the column
+// block, one per group of 8 harmonics (3 M-tiles each) -- 4 warps per SM sub-partition instead of 2 hide
+// the stage hand-over (barrier wait, first fragment loads) of one warp behind the DMMAs of the others.
+template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0>
+__global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : 1) k_quad_mma(const __grid_constant__ QuadParams P) {
+  constexpr int TW = 16 * NW;     // p_par columns per tile
+  constexpr int MT = 6 / HS;      // M-tiles per warp
+  constexpr int HP = 2 / HS;      // harmonics per thread
+  constexpr int NSUM = 12 / HS;   // moment sums a lane keeps after the lane reduction
+  constexpr int KS_A = 4 * TW;    // doubles per k-step of one table tile
   constexpr uint32_t BYTES_A = KSTG * KS_A * sizeof(double);
   constexpr uint32_t BYTES_W = KSTG * KS_W * sizeof(double);
-  typedef MmaSmem<KSTG, NST> Smem;
+  typedef MmaSmem<NW, KSTG, NST> Smem;
   extern __shared__ unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
 
@@ -73,15 +82,17 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
   const int npar = g.npar;
   const int NKS = P.nks;
   const int KC = NKS / KSTG;
-  const int NTall = (npar - 1 + BN - 1) / BN;
+  const int NTall = (npar - 1 + TW - 1) / TW;
   const int NT = (NTall - jsplit + nsplit - 1) / nsplit;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) % NW;    // column block of this warp
+  const int hsel = (threadIdx.x >> 5) / NW;    // HS = 2: harmonic group of this warp
   const int gq = lane >> 2, tq = lane & 3;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; s++) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 8);
+      mbar_init(&sm.empty[s], NW * HS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
     tma_load_1d(sm.st[stg].C, gC + ks0 * KS_A, BYTES_A, &sm.full[stg]);
     tma_load_1d(sm.st[stg].W, gW + (size_t)kc * KSTG * KS_W, BYTES_W, &sm.full[stg]);
   };
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0 && DBG != 3)
     for (int it = 0; it < NST - 1 && it < T; it++) issue(it);
 
   const double omr = P.om[2 * iom], omi = P.om[2 * iom + 1];
@@ -108,23 +119,25 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
   const size_t item0 = (size_t)iom * g.NI + sp.item_base;
   const int WIN = g.WIN, WINX = g.WINX, M_I = g.M_I;
 
-  double mine[12];   // this lane's share of the moment sums: harmonic n0 + 8 (tq >> 1) + gq, sign tq & 1
+  // this lane's share of the moment sums.  HS = 1: harmonic n0 + 8 (tq >> 1) + gq, sign tq & 1, all 12;
+  // HS = 2: harmonic n0 + 8 hsel + gq, sign tq >> 1, sums 6 (tq & 1) .. + 5
+  double mine[NSUM];
 #pragma unroll
-  for (int q = 0; q < 12; q++) mine[q] = 0.0;
+  for (int q = 0; q < NSUM; q++) mine[q] = 0.0;
 
   int stage = 0;
   uint32_t phase = 0, ready = 0;
   int git = 0;
   for (int ntl = 0; ntl < NT; ntl++) {
     const int nt = jsplit + ntl * nsplit;
-    double acc[6][2][2][2];   // [M-tile 2 x + h][table: 0 = A', 1 = C'][N-tile j][column pair]
+    double acc[MT][2][2][2];   // [M-tile HP x + h][table: 0 = A', 1 = C'][N-tile j][column pair]
 #pragma unroll
-    for (int m = 0; m < 6; m++)
+    for (int m = 0; m < MT; m++)
 #pragma unroll
       for (int q = 0; q < 8; q++) (&acc[m][0][0][0])[q] = 0.0;
 
     for (int kc = 0; kc < KC; kc++, git++) {
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 0 && DBG != 3) {
         const int nx = git + NST - 1;
         if (nx < T) {
           if (nx >= NST) mbar_wait(&sm.empty[nx % NST], ((nx / NST) & 1) ^ 1);
@@ -132,8 +145,8 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
         }
       }
       __syncwarp();
-      if (!ready) mbar_wait(&sm.full[stage], phase);
-      {
+      if (!ready && DBG != 3) mbar_wait(&sm.full[stage], phase);
+      if (DBG != 3) {
         const int ns = (stage + 1 == NST) ? 0 : stage + 1;
         ready = mbar_test(&sm.full[ns], (stage + 1 == NST) ? (phase ^ 1) : phase);
       }
@@ -142,14 +155,20 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
       const double* sW = sm.st[stage].W + 6 * lane;
 #pragma unroll
       for (int ks = 0; ks < KSTG; ks++) {
-        const double2 a = *reinterpret_cast<const double2*>(sA + ks * KS_A);
-        const double2 c = *reinterpret_cast<const double2*>(sC + ks * KS_A);
-        const double2 w0 = reinterpret_cast<const double2*>(sW + ks * KS_W)[0];
-        const double2 w1 = reinterpret_cast<const double2*>(sW + ks * KS_W)[1];
-        const double2 w2 = reinterpret_cast<const double2*>(sW + ks * KS_W)[2];
-        const double wv[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+        const int kq = (DBG == 1) ? 0 : ks;   // DBG 1: one fragment load per stage
+        const double2 a = *reinterpret_cast<const double2*>(sA + kq * KS_A);
+        const double2 c = *reinterpret_cast<const double2*>(sC + kq * KS_A);
+        const double2 w0 = reinterpret_cast<const double2*>(sW + kq * KS_W)[0];
+        const double2 w1 = reinterpret_cast<const double2*>(sW + kq * KS_W)[1];
+        const double2 w2 = reinterpret_cast<const double2*>(sW + kq * KS_W)[2];
+        double wv[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+        if (HS == 2) {
+          wv[0] = hsel ? w0.y : w0.x;
+          wv[1] = hsel ? w1.y : w1.x;
+          wv[2] = hsel ? w2.y : w2.x;
+        }
 #pragma unroll
-        for (int m = 0; m < 6; m++) {
+        for (int m = 0; m < MT; m++) {
           dmma(acc[m][0][0], wv[m], a.x);
           dmma(acc[m][0][1], wv[m], a.y);
           dmma(acc[m][1][0], wv[m], c.x);
@@ -157,7 +176,7 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+      if (lane == 0 && DBG != 3) mbar_arrive(&sm.empty[stage]);
       if (++stage == NST) {
         stage = 0;
         phase ^= 1;
@@ -165,14 +184,14 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
     }
 
     // ------------------------------------------------------------ epilogue of this p_par tile
-    // this thread: harmonics n0 + 8 h + gq (h = 0,1), columns ipar = ipar0 + 8 j + e (j, e = 0,1)
-    const int ipar0 = nt * BN + 16 * warp + 2 * tq + 1;
+    // this thread: harmonics n0 + 8 h + gq (HS = 1: h = 0,1; HS = 2: h = hsel), columns ipar0 + 8 j + e
+    const int ipar0 = nt * TW + 16 * warp + 2 * tq + 1;
     if (STORE) {
       // k-hoisted tables (alps_b200_set_mode(1)): layout [n][ipar-1][GAa, GBa, GAb, GBb, GAc, GBc]
       double* gt = P.gtab[tile.s];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int nabs = tile.n0 + 8 * h + gq;
+      for (int h = 0; h < HP; h++) {
+        const int nabs = tile.n0 + 8 * (HS == 2 ? hsel : h) + gq;
         if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
 #pragma unroll
         for (int j = 0; j < 2; j++)
@@ -182,14 +201,23 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
             if (ipar > npar - 1) continue;
             double2* o = reinterpret_cast<double2*>(gt + ((size_t)nabs * (npar - 1) + (ipar - 1)) * 6);
 #pragma unroll
-            for (int x = 0; x < 3; x++) o[x] = make_double2(acc[2 * x + h][0][j][e], acc[2 * x + h][1][j][e]);
+            for (int x = 0; x < 3; x++) o[x] = make_double2(acc[HP * x + h][0][j][e], acc[HP * x + h][1][j][e]);
           }
       }
       continue;
     }
+    if (DBG == 2) {   // no epilogue
+      double t = 0.0;
+#pragma unroll
+      for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) t += (&acc[m][0][0][0])[q];
+      mine[0] += t;
+      continue;
+    }
     // G = om * GA + GB: real part into the C' slot, imaginary part into the A' slot
 #pragma unroll
-    for (int m = 0; m < 6; m++)
+    for (int m = 0; m < MT; m++)
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const double ga = (&acc[m][0][0][0])[q];
@@ -204,12 +232,12 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
         const int ipar = ipar0 + 8 * j + e;
         pp_[j][e] = (ipar <= npar - 1) ? ppar[ipar] : 0.0;
       }
-    double Sv[48];   // [h][sign][12]
+    double Sv[24 * HP];   // [h][sign][12]
 #pragma unroll
-    for (int q = 0; q < 48; q++) Sv[q] = 0.0;
+    for (int q = 0; q < 24 * HP; q++) Sv[q] = 0.0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int nabs = tile.n0 + 8 * h + gq;
+    for (int h = 0; h < HP; h++) {
+      const int nabs = tile.n0 + 8 * (HS == 2 ? hsel : h) + gq;
       if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
 #pragma unroll
       for (int sg = 0; sg < 2; sg++) {
@@ -232,9 +260,9 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
               const double dr = ms * omr - kpar * p - nq, di = ms * omi;
               const double t = w / (dr * dr + di * di);
               const cd R = mk(dr * t, -di * t);
-              const cd Va = R * mk(acc[0 + h][1][j][e], acc[0 + h][0][j][e]);
-              const cd Vb = R * mk(acc[2 + h][1][j][e], acc[2 + h][0][j][e]);
-              const cd Vc = R * mk(acc[4 + h][1][j][e], acc[4 + h][0][j][e]);
+              const cd Va = R * mk(acc[0 * HP + h][1][j][e], acc[0 * HP + h][0][j][e]);
+              const cd Vb = R * mk(acc[1 * HP + h][1][j][e], acc[1 * HP + h][0][j][e]);
+              const cd Vc = R * mk(acc[2 * HP + h][1][j][e], acc[2 * HP + h][0][j][e]);
               const double p2 = p * p;
               S[0] += Va.x;       S[1] += Va.y;        // sum U J^2
               S[2] += p * Va.x;   S[3] += p * Va.y;    // sum U J^2 p_par
@@ -250,8 +278,8 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
                 double* gw = P.gwin + (item * WINX + jw) * 6;
 #pragma unroll
                 for (int x = 0; x < 3; x++) {
-                  gw[2 * x] = acc[2 * x + h][1][j][e];
-                  gw[2 * x + 1] = acc[2 * x + h][0][j][e];
+                  gw[2 * x] = acc[HP * x + h][1][j][e];
+                  gw[2 * x + 1] = acc[HP * x + h][0][j][e];
                 }
               }
             }
@@ -259,13 +287,13 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
       }
     }
     // recursive halving over the 4 lanes that share gq (lane bits 1, 0): the lane with tq = 2 h + sg
-    // ends with the 12 sums of (harmonic h, sign sg)
+    // ends with the 12 sums of (harmonic h, sign sg)  [HS = 2: sign tq >> 1, half tq & 1 of its 12 sums]
 #pragma unroll
     for (int step = 0; step < 2; step++) {
-      const int N = 24 >> step, mask = 2 >> step;
+      const int N = (12 * HP) >> step, mask = 2 >> step;
       const bool up = (lane & mask) != 0;
 #pragma unroll
-      for (int i = 0; i < 24; i++) {
+      for (int i = 0; i < 12 * HP; i++) {
         if (i < N) {
           const double send = up ? Sv[i] : Sv[i + N];
           const double keep = up ? Sv[i + N] : Sv[i];
@@ -274,52 +302,61 @@ __global__ void __launch_bounds__(256, 1) k_quad_mma(const __grid_constant__ Qua
       }
     }
 #pragma unroll
-    for (int q = 0; q < 12; q++) mine[q] += Sv[q];
+    for (int q = 0; q < NSUM; q++) mine[q] += Sv[q];
   }
 
   if (STORE) return;
   // ---------------------------------------------------------------- write the moment sums
   {
-    double* red = &sm.red[warp][8 * (tq >> 1) + gq][tq & 1][0];
+    double* red = (HS == 2) ? &sm.red[warp][8 * hsel + gq][tq >> 1][6 * (tq & 1)]
+                            : &sm.red[warp][8 * (tq >> 1) + gq][tq & 1][0];
 #pragma unroll
-    for (int q = 0; q < 12; q++) red[q] = mine[q];
+    for (int q = 0; q < NSUM; q++) red[q] = mine[q];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < MMA_NH * 24; i += 256) {
+  for (int i = threadIdx.x; i < MMA_NH * 24; i += 32 * NW * HS) {
     const int nn = i / 24, sg = (i % 24) / 12, q = i % 12;
     const int nabs = tile.n0 + nn;
     if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) t += sm.red[w][nn][sg][q];
+    for (int w = 0; w < NW; w++) t += sm.red[w][nn][sg][q];
     P.Sbulk[((item0 + 2 * nabs + sg) * nsplit + jsplit) * 12 + q] = t;
   }
 }
 
-template <int KSTG, int NST, bool STORE>
+template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0>
 static cudaError_t launch_mma_one(const QuadParams& P, cudaStream_t st) {
   static bool attr_set = false;
-  const size_t smem = sizeof(MmaSmem<KSTG, NST>) + 128;
+  const size_t smem = sizeof(MmaSmem<NW, KSTG, NST>) + 128;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_quad_mma<KSTG, NST, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_quad_mma<NW, HS, KSTG, NST, STORE, DBG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_quad_mma<KSTG, NST, STORE><<<P.n_om * P.ntiles * P.nsplit, 256, smem, st>>>(P);
+  k_quad_mma<NW, HS, KSTG, NST, STORE, DBG><<<P.n_om * P.ntiles * P.nsplit, 32 * NW * HS, smem, st>>>(P);
   return cudaGetLastError();
 }
-template <int KSTG, int NST>
+template <int NW, int HS, int KSTG, int NST>
 static cudaError_t launch_mma_variant(const QuadParams& P, bool store, cudaStream_t st) {
-  return store ? launch_mma_one<KSTG, NST, true>(P, st) : launch_mma_one<KSTG, NST, false>(P, st);
+  return store ? launch_mma_one<NW, HS, KSTG, NST, true>(P, st) : launch_mma_one<NW, HS, KSTG, NST, false>(P, st);
 }
 
+// variant ids >= 9; the tile width (QuadVariant::bn) fixes the fragment layout built by set_k
 cudaError_t launch_quad_mma(const QuadParams& P, int variant, bool store, cudaStream_t st) {
   if (P.n_om <= 0 || P.ntiles <= 0) return cudaSuccess;
   switch (variant) {
-    case 10: return launch_mma_variant<4, 4>(P, store, st);
-    case 11: return launch_mma_variant<4, 3>(P, store, st);
-    default: return launch_mma_variant<8, 2>(P, store, st);
+    case 12: return launch_mma_variant<4, 1, 8, 2>(P, store, st);   // 2 CTAs of 4 warps per SM
+    case 15: return launch_mma_variant<8, 2, 8, 2>(P, store, st);   // 16 warps: 4 per SM sub-partition
+#ifdef ALPS_QUAD_DEBUG
+    case 91: return launch_mma_one<8, 2, 8, 2, false, 1>(P, st);
+    case 92: return launch_mma_one<8, 2, 8, 2, false, 2>(P, st);
+    case 93: return launch_mma_one<8, 2, 8, 2, false, 3>(P, st);
+#endif
+    case 16: return launch_mma_variant<8, 2, 4, 4>(P, store, st);
+    case 17: return launch_mma_variant<4, 2, 8, 2>(P, store, st);   // 2 CTAs of 8 warps per SM
+    default: return launch_mma_variant<8, 1, 8, 2>(P, store, st);   // 9: one 8-warp CTA per SM (2 warps per sub-partition)
   }
 }
 

@@ -112,17 +112,17 @@ __global__ void k_build_W(const double* __restrict__ pperp, const double* __rest
   w[2] = wc;
 }
 
-// Fragment-ordered operands of the DMMA kernel (quad_mma.cu).  Xf[nt][ks][512]: the 4 x 128 block of
-// rows 4 ks .. 4 ks + 3 and columns 128 nt .. 128 nt + 127 of scale * X, element (t, 16 w + 8 j + g) at
+// Fragment-ordered operands of the DMMA kernel (quad_mma.cu).  Xf[nt][ks][4 tw]: the 4 x tw block of
+// rows 4 ks .. 4 ks + 3 and columns tw nt .. tw nt + tw - 1 of scale * X, element (t, 16 w + 8 j + g) at
 // 64 w + 2 (4 g + t) + j.  One thread per output element; padding elements are written as zero.
 __global__ void k_frag_table(const double* __restrict__ X, int ldp, int nrows, int ncols, double scale,
-                             double* __restrict__ Xf, int nks, size_t total) {
+                             double* __restrict__ Xf, int nks, int tw, size_t total) {
   for (size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
-    const int in = (int)(o & 511);
-    const size_t blk = o >> 9;
+    const int in = (int)(o % (size_t)(4 * tw));
+    const size_t blk = o / (size_t)(4 * tw);
     const int ks = (int)(blk % nks), nt = (int)(blk / nks);
     const int w = in >> 6, l = (in >> 1) & 31, j = in & 1, g = l >> 2, t = l & 3;
-    const int r = 4 * ks + t, c = 128 * nt + 16 * w + 8 * j + g;
+    const int r = 4 * ks + t, c = tw * nt + 16 * w + 8 * j + g;
     Xf[o] = (r < nrows && c < ncols) ? scale * X[(size_t)r * ldp + c] : 0.0;
   }
 }
@@ -213,11 +213,11 @@ void launch_build_W(const double* pperp, const double* J, int ldj, int nperp, in
   dim3 g((ncols + 63) / 64, nperp - 1);
   k_build_W<<<g, 64, 0, st>>>(pperp, J, ldj, nperp, nhi, W, ldw);
 }
-void launch_frag_table(const double* X, int ldp, int nrows, int ncols, double scale, double* Xf, int nks, int ntiles,
-                       cudaStream_t st) {
-  const size_t total = (size_t)ntiles * nks * 512;
+void launch_frag_table(const double* X, int ldp, int nrows, int ncols, double scale, double* Xf, int nks, int tw,
+                       int ntiles, cudaStream_t st) {
+  const size_t total = (size_t)ntiles * nks * 4 * tw;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-  k_frag_table<<<blocks, 256, 0, st>>>(X, ldp, nrows, ncols, scale, Xf, nks, total);
+  k_frag_table<<<blocks, 256, 0, st>>>(X, ldp, nrows, ncols, scale, Xf, nks, tw, total);
 }
 void launch_build_Wf(const double* pperp, const double* J, int ldj, int nperp, int nhi, double* Wf, int nks, int nhb,
                      cudaStream_t st) {

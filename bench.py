@@ -185,7 +185,11 @@ def run_ours(args, w, rank, world, local_rank):
     flops_per_D = FLOPS_PER_POINT_HARMONIC * ph
     absn_points = sum(int(n) + 1 for n in nmax) * (w["nperp"] - 1.0) * (w["npar"] - 1.0)
     flops_exec_per_D = FLOPS_EXECUTED_PER_ABSN_POINT * absn_points
-    peak_meas = sol.dfma_peak() if rank == 0 else None
+    variant = int(sol.info(_lib.INFO_QUAD_VARIANT))
+    dmma = variant >= 9     # quadrature on the FP64 tensor pipe (same FP64 units, DMMA.8x8x4 issue)
+    peak_dfma = sol.dfma_peak() if rank == 0 else None
+    peak_dmma = sol.info(_lib.INFO_DMMA_PEAK) if rank == 0 else None
+    peak_meas = peak_dmma if dmma else peak_dfma
 
     def step_dev():
         sol.disp_batch_dev(B, om_d.data_ptr(), D_d.data_ptr())
@@ -303,13 +307,16 @@ def run_ours(args, w, rank, world, local_rank):
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s",
                              "frac": achieved / peak_meas if peak_meas else None, "traffic": traffic,
-                             "peak_source": "DFMA micro-benchmark run in this job (MEASURED_PEAKS.json has no FP64 entry)",
+                             "peak_source": ("DMMA (mma.sync.m8n8k4.f64)" if dmma else "DFMA") +
+                                            " micro-benchmark run in this job (MEASURED_PEAKS.json has no FP64 entry)",
+                             "peak_dfma_microbench": peak_dfma, "peak_dmma_microbench": peak_dmma,
                              "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_nominal": achieved / FP64_NOMINAL_TFLOPS,
-                             "flop_model": "useful FP64 flops of k_quad's formulation: 12 per (|n|, iperp, ipar); "
+                             "flop_model": "useful FP64 flops of the quadrature kernel's formulation: 12 per (|n|, iperp, ipar); "
                                            "+n and -n share the p_perp sums; padding/epilogue not counted (DESIGN.md)",
                              "achieved_survey_34flop_model": achieved34,
                              "frac_survey_34flop_model": achieved34 / peak_meas if peak_meas else None,
-                             "kernel": "k_quad", "kernel_ms_per_step": kern_ms / args.steps,
+                             "kernel": "k_quad_mma" if dmma else "k_quad", "quad_variant": variant,
+                             "kernel_ms_per_step": kern_ms / args.steps,
                              "kernel_share_of_step": kern_ms / tot_ms},
                 "cpu_baseline": cpu, "clocks": clk, "fast_path": fast}
         print(json.dumps(line), flush=True)
