@@ -27,7 +27,8 @@ struct SpeciesHost {
   double *d_J = nullptr, *d_W = nullptr, *d_pf = nullptr, *d_poly = nullptr, *d_ee = nullptr, *d_G = nullptr;
   size_t cap_J = 0, cap_W = 0, cap_G = 0;
   // fragment-ordered operands of the DMMA quadrature variants (quad_mma.cu)
-  double *d_Af = nullptr, *d_Cf = nullptr, *d_Wf = nullptr;
+  double *d_Af = nullptr, *d_Cf = nullptr, *d_Wf = nullptr, *d_Jrel = nullptr;
+  size_t cap_Jrel = 0;
   size_t cap_Xf = 0, cap_Wf = 0;
   bool af_valid = false;
   bool grid = false;    // has f0 tables on the (p_perp,p_par) grid (everything but use_bM species)
@@ -55,6 +56,8 @@ struct State {
          *d_partial = nullptr, *d_chi0 = nullptr, *d_chi0_low = nullptr, *d_wave = nullptr, *d_ext = nullptr;
   PlanEntry* d_plan = nullptr;
   int *d_work = nullptr, *d_work_count = nullptr, *d_err = nullptr;
+  double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
+  int* d_reltick = nullptr;
   QuadTile* d_tiles = nullptr;
   std::vector<QuadTile> tiles;
   RelTile* d_rtiles = nullptr;
@@ -120,6 +123,7 @@ inline size_t ipp(int nspec, int nperp, int npar, int is0, int iperp, int ipar, 
 void free_batch() {
   dfree(&S.d_om); dfree(&S.d_D); dfree(&S.d_Sbulk); dfree(&S.d_Sres); dfree(&S.d_gwin); dfree(&S.d_partial);
   dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work); dfree(&S.d_ext);
+  dfree(&S.d_relpart); dfree(&S.d_reltick);
   S.batch = 0;
 }
 
@@ -266,6 +270,11 @@ int nsplit_small() {
   return std::max(1, std::min(NT, (2 * S.sm_count) / std::max(1, (int)S.tiles.size())));
 }
 
+int nsplit_rel() {
+  if (S.rtiles.empty()) return 1;
+  return std::max(1, std::min(16, (2 * S.sm_count + (int)S.rtiles.size() - 1) / (int)S.rtiles.size()));
+}
+
 int ensure_batch(int want) {
   if (S.batch >= want && S.d_om) return 0;
   free_batch();
@@ -278,6 +287,15 @@ int ensure_batch(int want) {
       dalloc(&S.d_chi0_low, B * S.gh.nspec * 54) || dalloc(&S.d_wave, B * 18) || dalloc(&S.d_plan, B * NI) ||
       dalloc(&S.d_work, B * NI) || dalloc(&S.d_ext, B * S.gh.nspec * PARTIAL_PER_SPEC))
     return ALPS_B200_ERR_CUDA;
+  bool any_rel = false;
+  for (int s = 0; s < S.cfg.nspec; s++) any_rel = any_rel || S.gh.sp[s].relativistic;
+  if (any_rel) {
+    // sized for the largest split (16) and any harmonic shard (tiles <= NI)
+    const size_t nt = (size_t)SMALL_BATCH * NI;
+    if (dalloc(&S.d_relpart, (size_t)SMALL_BATCH * NI * 16 * 12) || dalloc(&S.d_reltick, nt))
+      return ALPS_B200_ERR_CUDA;
+    CK(cudaMemsetAsync(S.d_reltick, 0, nt * sizeof(int), S.stream));
+  }
   S.batch = want;
   return 0;
 }
@@ -361,7 +379,11 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.stream);
     if (!S.rtiles.empty()) {
-      launch_rel(gd, d_om, n, S.d_rtiles, (int)S.rtiles.size(), S.d_Sres, S.d_err + 6, S.stream);
+      // few omegas in flight: spread each (omega, species, |n|) over several CTAs (configuration-only
+      // rule, like nsplit_small, so disp() and a small disp_batch() stay bitwise identical)
+      const int rsplit = (n <= SMALL_BATCH) ? nsplit_rel() : 1;
+      launch_rel(gd, d_om, n, S.d_rtiles, (int)S.rtiles.size(), S.d_Sres, S.d_err + 6, rsplit, S.d_relpart,
+                 S.d_reltick, S.stream);
       S.launches += 1;
     }
     double* part = d_partial_out ? d_partial_out : S.d_partial;
@@ -468,7 +490,8 @@ void alps_b200_finalize(void) {
   for (int s = 0; s < MAXSPEC; s++) {
     SpeciesHost& h = S.sp[s];
     dfree(&h.d_pperp); dfree(&h.d_ppar); dfree(&h.d_A); dfree(&h.d_C0); dfree(&h.d_Cp); dfree(&h.d_J);
-    dfree(&h.d_Af); dfree(&h.d_Cf); dfree(&h.d_Wf);
+    dfree(&h.d_Af); dfree(&h.d_Cf); dfree(&h.d_Wf); dfree(&h.d_Jrel);
+    h.cap_Jrel = 0;
     h.cap_Xf = h.cap_Wf = 0;
     h.af_valid = false;
     dfree(&h.d_W); dfree(&h.d_pf); dfree(&h.d_poly); dfree(&h.d_ee); dfree(&h.d_G);
@@ -789,6 +812,22 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
     }
     if (d.relativistic) {
       d.int_ee = h.ee_rel;
+      if (kperp_changed) {
+        // Bessel factors of int_T_rel on the (Gamma, pbar_par) grid, orders 0..nhi+1; skipped (k_rel then
+        // evaluates BESSJ per point) if the table would exceed 8 GB
+        const size_t nJr = (size_t)(d.nhi + 2) * (S.cfg.ngamma + 1) * (S.cfg.npparbar + 1);
+        d.Jrel = nullptr;
+        if (nJr * sizeof(double) <= ((size_t)8 << 30) && !getenv("ALPS_B200_REL_NOTABLE")) {
+          if (nJr > h.cap_Jrel) {
+            if (dalloc(&h.d_Jrel, nJr)) return ALPS_B200_ERR_CUDA;
+            h.cap_Jrel = nJr;
+          }
+          launch_rel_bessel_table(h.d_grel, h.d_pbrel, S.cfg.ngamma, S.cfg.npparbar,
+                                  kperp * d.ms / (S.gh.vA * d.qs), d.nhi + 1, h.d_Jrel, S.stream);
+          S.launches += 1;
+          d.Jrel = h.d_Jrel;
+        }
+      }
       for (int n = d.nlo_shard; n <= d.nhi_shard; n++) S.rtiles.push_back(RelTile{s, n});
       continue;
     }

@@ -89,6 +89,9 @@ struct SpeciesDev {
   const int* cone_lo;        // ipparbar_lower(igamma), src/ALPS_fns_rel.f90:582-596
   const int* cone_up;
   double dgamma, dpparbar;
+  // per-k table of BESSJ(n, kperp ms/(vA qs) pperpbar(igamma, ipparbar)), n = 0..nhi+1, layout
+  // [n][igamma][ipparbar] (0 outside the sub-luminal cone); NULL: k_rel evaluates BESSJ per point
+  const double* Jrel;
 };
 
 struct RelTile {

@@ -85,7 +85,9 @@ struct FastItem {
 void launch_fast(const GlobalDev* g, const double* om, int n_om, const FastItem* items, int nitems,
                  const PlanEntry* plan, double* Sbulk, double* gwin, cudaStream_t st);
 void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
-                int* err_flag, cudaStream_t st);
+                int* err_flag, int nsplit, double* Mpart, int* tickets, cudaStream_t st);
+void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, int npb, double zfac, int nmaxord,
+                             double* Jrel, cudaStream_t st);
 void launch_int_ee_rel(const double* pbv, const double* dfp, const int* lo, const int* up, int ng, int npb, double qs,
                        double ms, double vA, double dgam, double dpb, double* out, cudaStream_t st);
 double run_dfma_peak(cudaStream_t st);

@@ -143,8 +143,18 @@ __device__ inline void node_values(const RelCtx& c, int ig, int ip, Six2& Tp, Si
   const double gam = sp.grel[ig], pb = sp.pbrel[ip];
   const double pperpbar = sqrt(gam * gam - 1.0 - pb * pb);
   const double z = c.zfac * pperpbar;
-  const double j0 = bessj_ref(c.nabs, z), jp = bessj_ref(c.nabs + 1, z);
-  const double jm = c.nabs >= 1 ? bessj_ref(c.nabs - 1, z) : 0.0;
+  double j0, jp, jm;
+  if (sp.Jrel) {
+    // the same BESSJ values, tabulated once per k (k_rel_bessel_table)
+    const size_t plane = (size_t)(c.g->ngamma + 1) * ldr, o = (size_t)ig * ldr + ip;
+    j0 = sp.Jrel[(size_t)c.nabs * plane + o];
+    jp = sp.Jrel[(size_t)(c.nabs + 1) * plane + o];
+    jm = c.nabs >= 1 ? sp.Jrel[(size_t)(c.nabs - 1) * plane + o] : 0.0;
+  } else {
+    j0 = bessj_ref(c.nabs, z);
+    jp = bessj_ref(c.nabs + 1, z);
+    jm = c.nabs >= 1 ? bessj_ref(c.nabs - 1, z) : 0.0;
+  }
   double bj, bp;
   bessel_pair(c.nabs, 0, z, jm, j0, jp, bj, bp);
   modes_real(bj, bp, pperpbar, pb, c.zbar, (double)c.nabs, c.kf1, c.kf2, Tp);
@@ -202,12 +212,18 @@ __device__ __forceinline__ cd warp_sum_cd(cd v) {
 
 constexpr int REL_THREADS = 256;
 
+// nsplit > 1 (few omegas in flight: sequential root finding is latency bound): the gamma rows / grid points
+// of one (omega, species, |n|) are dealt round-robin to nsplit CTAs; each leaves a partial row in Mpart and
+// the last one to finish (ticket counter) adds them up in a fixed order.
 __global__ void __launch_bounds__(REL_THREADS) k_rel(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
                                                      int n_om, const RelTile* __restrict__ tiles, int ntiles,
-                                                     double* __restrict__ Mrel, int* __restrict__ err_flag) {
+                                                     double* __restrict__ Mrel, int* __restrict__ err_flag, int nsplit,
+                                                     double* __restrict__ Mpart, int* __restrict__ tickets) {
   const GlobalDev& g = *gp;
-  const int iom = blockIdx.x / ntiles;
-  const RelTile tl = tiles[blockIdx.x % ntiles];
+  const int js = blockIdx.x % nsplit;
+  const int iom = (blockIdx.x / nsplit) / ntiles;
+  const int tile_id = (blockIdx.x / nsplit) % ntiles;
+  const RelTile tl = tiles[tile_id];
   const SpeciesDev& sp = g.sp[tl.s];
   const int nabs = tl.nabs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = REL_THREADS / 32;
@@ -258,7 +274,7 @@ __global__ void __launch_bounds__(REL_THREADS) k_rel(const GlobalDev* __restrict
       const double* Jn = sp.J + (size_t)(nabs + 1) * sp.ldj;
       const double* Jm = sp.J + (size_t)nabs * sp.ldj;
       const double* Jp = sp.J + (size_t)(nabs + 2) * sp.ldj;
-      for (int idx = tid; idx < (nperp - 1) * (npar - 1); idx += REL_THREADS) {
+      for (int idx = tid + REL_THREADS * js; idx < (nperp - 1) * (npar - 1); idx += REL_THREADS * nsplit) {
         const int iperp = idx / (npar - 1) + 1, ipar = idx % (npar - 1) + 1;
         const double wperp = (iperp == nperp - 1) ? 1.0 : 2.0;
         const double wpar = (ipar == 1 || ipar == npar - 1) ? 1.0 : 2.0;
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(REL_THREADS) k_rel(const GlobalDev* __restrict
       const double dpb = sp.dpparbar, dgam = sp.dgamma;
       const double* pbv = sp.pbrel;
       const int ldr = npb + 1;
-      for (int ig = 1 + warp; ig <= ng - 1; ig += nwarps) {
+      for (int ig = 1 + warp + nwarps * js; ig <= ng - 1; ig += nwarps * nsplit) {
         const double wg = (ig == ng - 1) ? 1.0 : 2.0;
         const double g1 = sp.grel[ig];
         const cd pres = (g1 * omc - mk(nn * qs / ms, 0.0)) * vA / kpar;
@@ -418,7 +434,7 @@ __global__ void __launch_bounds__(REL_THREADS) k_rel(const GlobalDev* __restrict
       if (omc.y <= 0.0) {
         Six2 L;
         zero6(L);
-        for (int ig = 1 + tid; ig <= ng - 1; ig += REL_THREADS) {
+        for (int ig = 1 + tid + REL_THREADS * js; ig <= ng - 1; ig += REL_THREADS * nsplit) {
           const double g1 = sp.grel[ig];
           const cd pres = (g1 * omc) * vA / kpar - mk((1.0 * nn) * qs * vA / (kpar * ms), 0.0);
           if (!(pres.x * pres.x <= g1 * g1 - 1.0)) continue;
@@ -469,11 +485,49 @@ __global__ void __launch_bounds__(REL_THREADS) k_rel(const GlobalDev* __restrict
       cd t = mk(0.0, 0.0);
       for (int w = 0; w < nwarps; w++) t += s_red[w][tid];
       const size_t item = (size_t)iom * g.NI + sp.item_base + 2 * nabs + sg;
-      Mrel[item * 12 + 2 * tid] = t.x;
-      Mrel[item * 12 + 2 * tid + 1] = t.y;
+      double* o = (nsplit == 1) ? Mrel + item * 12 : Mpart + (item * nsplit + js) * 12;
+      o[2 * tid] = t.x;
+      o[2 * tid + 1] = t.y;
     }
     __syncthreads();
   }
+  if (nsplit > 1) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&tickets[iom * ntiles + tile_id], 1) == nsplit - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (tid < 24) {
+        const int sg = tid / 12, q = tid % 12;
+        if (!(nabs == 0 && sg == 1)) {
+          const size_t item = (size_t)iom * g.NI + sp.item_base + 2 * nabs + sg;
+          double t = 0.0;
+          for (int j = 0; j < nsplit; j++) t += __ldcg(Mpart + (item * nsplit + j) * 12 + q);
+          Mrel[item * 12 + q] = t;
+        }
+      }
+      if (tid == 0) tickets[iom * ntiles + tile_id] = 0;   // ready for the next launch
+    }
+  }
+}
+
+// Bessel factors of int_T_rel (src/ALPS_fns_rel.f90:1297-1322) depend on (igamma, ipparbar) through
+// pperpbar = sqrt(gamma^2 - 1 - pparbar^2) but not on omega: tabulated once per k with the same literal BESSJ.
+__global__ void k_rel_bessel_table(const double* __restrict__ grel, const double* __restrict__ pbrel, int ng, int npb,
+                                   double zfac, int nmaxord, double* __restrict__ Jrel) {
+  const int ldr = npb + 1;
+  const size_t plane = (size_t)(ng + 1) * ldr;
+  const size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (o >= plane || n > nmaxord) return;
+  const int ig = (int)(o / ldr), ip = (int)(o % ldr);
+  const double gam = grel[ig], pb = pbrel[ip];
+  const double a = gam * gam - 1.0 - pb * pb;
+  double v = 0.0;
+  if (a >= 0.0) v = bessj_ref(n, zfac * sqrt(a));
+  Jrel[(size_t)n * plane + o] = v;
 }
 
 // int_ee_rel, src/ALPS_fns_rel.f90:1097-1215: one block
@@ -504,9 +558,17 @@ __global__ void k_int_ee_rel(const double* __restrict__ pbv, const double* __res
 }
 
 void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
-                int* err_flag, cudaStream_t st) {
+                int* err_flag, int nsplit, double* Mpart, int* tickets, cudaStream_t st) {
   if (n_om <= 0 || ntiles <= 0) return;
-  k_rel<<<n_om * ntiles, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag);
+  if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
+  k_rel<<<n_om * ntiles * nsplit, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, nsplit, Mpart,
+                                                          tickets);
+}
+void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, int npb, double zfac, int nmaxord,
+                             double* Jrel, cudaStream_t st) {
+  const size_t plane = (size_t)(ng + 1) * (npb + 1);
+  dim3 grid((unsigned)((plane + 127) / 128), nmaxord + 1);
+  k_rel_bessel_table<<<grid, 128, 0, st>>>(grel, pbrel, ng, npb, zfac, nmaxord, Jrel);
 }
 void launch_int_ee_rel(const double* pbv, const double* dfp, const int* lo, const int* up, int ng, int npb, double qs,
                        double ms, double vA, double dgam, double dpb, double* out, cudaStream_t st) {

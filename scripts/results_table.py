@@ -35,6 +35,11 @@ def measure(name, pl, kperp, kpar, om0, nbatch, nproc=0, ncpu=3, modes=(0, 1)):
     print(json.dumps(out), flush=True)
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    _measure = measure
+    def measure(name, *a, **k):
+        if not only or any(name.startswith(o) for o in only):
+            _measure(name, *a, **k)
     measure("C1 test_kpar_fast (120x240, nmax 21/13)", tables.config_kpar_fast(), 1e-2, 1e-2, 9.98811e-3, 4096, nproc=4)
     measure("test_map-like 50x50 map on the C1 tables", tables.config_kpar_fast(), 1e-2, 1e-2, 1.0e-2, 2500, nproc=4)
     measure("C2 test_bimax (150x300, protons NHDS, electrons table)", tables.config_bimax(), 1e-3, 0.03, 3.0e-2, 4096)
