@@ -56,6 +56,8 @@ struct State {
          *d_partial = nullptr, *d_chi0 = nullptr, *d_chi0_low = nullptr, *d_wave = nullptr, *d_ext = nullptr;
   PlanEntry* d_plan = nullptr;
   int *d_work = nullptr, *d_work_count = nullptr, *d_err = nullptr;
+  double* d_respart = nullptr;   // k_resonant_lat partial rows (small batches)
+  int* d_restick = nullptr;
   double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
   int* d_reltick = nullptr;
   QuadTile* d_tiles = nullptr;
@@ -123,7 +125,7 @@ inline size_t ipp(int nspec, int nperp, int npar, int is0, int iperp, int ipar, 
 void free_batch() {
   dfree(&S.d_om); dfree(&S.d_D); dfree(&S.d_Sbulk); dfree(&S.d_Sres); dfree(&S.d_gwin); dfree(&S.d_partial);
   dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work); dfree(&S.d_ext);
-  dfree(&S.d_relpart); dfree(&S.d_reltick);
+  dfree(&S.d_relpart); dfree(&S.d_reltick); dfree(&S.d_respart); dfree(&S.d_restick);
   S.batch = 0;
 }
 
@@ -287,6 +289,11 @@ int ensure_batch(int want) {
       dalloc(&S.d_chi0_low, B * S.gh.nspec * 54) || dalloc(&S.d_wave, B * 18) || dalloc(&S.d_plan, B * NI) ||
       dalloc(&S.d_work, B * NI) || dalloc(&S.d_ext, B * S.gh.nspec * PARTIAL_PER_SPEC))
     return ALPS_B200_ERR_CUDA;
+  {
+    const size_t nt = (size_t)std::min<size_t>(B, SMALL_BATCH) * NI;
+    if (dalloc(&S.d_respart, nt * RES_PART_DOUBLES) || dalloc(&S.d_restick, nt)) return ALPS_B200_ERR_CUDA;
+    CK(cudaMemsetAsync(S.d_restick, 0, nt * sizeof(int), S.stream));
+  }
   bool any_rel = false;
   for (int s = 0; s < S.cfg.nspec; s++) any_rel = any_rel || S.gh.sp[s].relativistic;
   if (any_rel) {
@@ -377,7 +384,8 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       e = S.qv.id >= 9 ? launch_quad_mma(S.P, S.qv.id, false, S.stream) : launch_quad(S.P, S.qv.id, false, S.stream);
     cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
-    launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.stream);
+    launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.d_respart,
+                    S.d_restick, S.stream);
     if (!S.rtiles.empty()) {
       // few omegas in flight: spread each (omega, species, |n|) over several CTAs (configuration-only
       // rule, like nsplit_small, so disp() and a small disp_batch() stay bitwise identical)

@@ -70,7 +70,9 @@ double run_dmma_peak(cudaStream_t st);
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
                  int* work, int* work_count, cudaStream_t st);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
-                     const int* work_count, const double* gwin, double* Sres, int* err_flag, cudaStream_t st);
+                     const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
+                     int* tickets, cudaStream_t st);
+constexpr int RES_PART_DOUBLES = 11 * 16;   // k_resonant_lat: partial rows per item (LAT_PARTS x LAT_STRIDE)
 // chi partial layout per omega: [nspec][PARTIAL_PER_SPEC] doubles (see resonant.cu)
 constexpr int PARTIAL_PER_SPEC = 2 * (6 + 18);   // chi(6 modes) + chi_low(6 modes x 3) complex
 void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,

@@ -199,7 +199,7 @@ __device__ __forceinline__ void six_zero(Six& s) {
 // combinations at real p; linear interpolation around the nearest grid node exactly as
 // funct_g does per iperp (src/ALPS_fns.f90:1284-1319).
 __device__ inline void funct_g6(const GlobalDev& g, const SpeciesDev& sp, const double* __restrict__ gw, int wbase,
-                                double p, Six& out, int* err) {
+                                double p, Six& out, int* err, int q0 = 0, int nq = 6) {
   const int npar = g.npar;
   const double* ppar = sp.ppar;
   const double dp = sp.dppar_abs;
@@ -228,6 +228,10 @@ __device__ inline void funct_g6(const GlobalDev& g, const SpeciesDev& sp, const 
   const double x = p - ppar[ic];
 #pragma unroll
   for (int q = 0; q < 6; q++) {
+    if (q < q0 || q >= q0 + nq) {   // latency variant: the six combinations are dealt to different blocks
+      out.v[q] = mk(0.0, 0.0);
+      continue;
+    }
     const int xt = (q < 3) ? 0 : (q < 5 ? 1 : 2);   // weight type a,b,c
     const int m = (q < 3) ? q : (q < 5 ? q - 3 : 0);  // p_par power
     cd gm, g0, gp;
@@ -472,6 +476,251 @@ __global__ void __launch_bounds__(RES_THREADS) k_resonant(const GlobalDev* __res
   }
 }
 
+// Latency variant (few omegas in flight: sequential root finding).  The independent pieces of one
+// resonant harmonic go to LAT_PARTS different 256-thread blocks (blockIdx.y), i.e. to different SMs;
+// each near-pole piece is further split by (weight, moment) combination, two per block:
+//   parts 0..2  near-pole terms g(p)/(p - p_res)        (or the whole analytic branch)
+//   parts 3..5  mirrored terms  g(2 p_R - p)/(p - p_res*)
+//   parts 6..8  tiny rest
+//   parts 9,10  Landau residue, alternating groups of 64 p_perp rows: 4 threads per row, one eval_fit
+//               each; the two end rows (iperp = 0, nperp) are ordinary rows of the same scheme
+// Each block leaves 6 complex partial sums (+ zero / error flags); the last block of an item to finish
+// (ticket counter) combines them in a fixed order.  Same arithmetic per term as k_resonant; only the
+// (fixed) summation order differs.
+constexpr int LAT_THREADS = 256;
+constexpr int LAT_PARTS = 11;
+constexpr int LAT_STRIDE = 16;   // doubles per partial row: 12 sums, zero flag, error code
+static_assert(LAT_PARTS * LAT_STRIDE == RES_PART_DOUBLES, "partial-row buffer size");
+__global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* __restrict__ gp,
+                                                              const double* __restrict__ om,
+                                                              const PlanEntry* __restrict__ plan,
+                                                              const int* __restrict__ work,
+                                                              const int* __restrict__ work_count,
+                                                              const double* __restrict__ gwin, double* __restrict__ Sres,
+                                                              int* __restrict__ err_flag, double* __restrict__ Spart,
+                                                              int* __restrict__ tickets) {
+  const GlobalDev& g = *gp;
+  const int tid = threadIdx.x, wlane = tid & 31, wid = tid >> 5, part = blockIdx.y;
+  __shared__ cd s_part[LAT_THREADS / 32][6];
+  __shared__ cd s_f[3][2];   // analytic branch: g(p_R + dp), g(p_R - dp), g(p_R) for this block's two combinations
+  __shared__ int s_err, s_last;
+  const int nwork = *work_count;
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const size_t idx = (size_t)work[wi];
+    const int iom = (int)(idx / g.NI), it = (int)(idx % g.NI);
+    int s, nabs, sg;
+    decode_item(g, it, s, nabs, sg);
+    const SpeciesDev& sp = g.sp[s];
+    const PlanEntry pe = plan[idx];
+    const int nperp = g.nperp, M_I = g.M_I, M_P = g.M_P;
+    const double* ppar = sp.ppar;
+    const cd omc = mk(om[2 * iom], om[2 * iom + 1]);
+    const int nn = sg ? -nabs : nabs;
+    const double qs = sp.qs, ms = sp.ms, kpar = g.kpar;
+    const double pR = (ms * omc.x - 1.0 * nn * qs) / kpar;
+    const double pI = (ms * omc.y) / kpar;
+    const cd p_res = mk(pR, pI);
+    if (tid == 0) s_err = 0;
+    __syncthreads();
+    Six acc;
+    six_zero(acc);
+    int err = 0, zero = 0;
+
+    if ((pe.flags & PLAN_NEAR) && part <= 8) {
+      const double* gw = gwin + idx * (size_t)g.WINX * 6;
+      const int wbase = pe.ipar_res - M_I - 2;
+      const double dppar = sp.dppar_signed;
+      const double capDelta = pR - ppar[pe.ipar_res - M_I];
+      const double smdelta = capDelta / (1.0 * M_P);
+      const bool pairing = fabs(pI) > g.Tlim;
+      const int piece = part / 3, q0 = 2 * (part % 3);   // this block: combinations q0, q0 + 1
+      if (pairing && piece <= 1) {
+        // Eq. (3.5): symmetric pairing around the pole, src/ALPS_fns.f90:1026-1082
+        for (int j = tid; j <= M_P; j += LAT_THREADS) {
+          const double wj = (j == 0 || j == M_P) ? 1.0 : 2.0;
+          const double p = (j == 0) ? pR : (j == M_P ? pR + capDelta : pR + smdelta * j);
+          Six f;
+          if (piece == 0) {
+            funct_g6(g, sp, gw, wbase, p, f, &err, q0, 2);
+            const cd d1 = mk(p - pR, -pI);
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              if (q >= q0 && q < q0 + 2) acc.v[q] += wj * (f.v[q] / d1);
+          } else {
+            funct_g6(g, sp, gw, wbase, 2.0 * pR - p, f, &err, q0, 2);
+            const cd d2 = mk(p - pR, pI);
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              if (q >= q0 && q < q0 + 2) acc.v[q] -= wj * (f.v[q] / d2);
+          }
+        }
+      } else if (!pairing && piece == 0) {
+        // Eq. (3.6): linearised integrand + pole term, src/ALPS_fns.f90:1088-1165; the three g values
+        // are evaluated once, by three different warps
+        if (wlane == 0 && wid < 3) {
+          Six f;
+          funct_g6(g, sp, gw, wbase, wid == 0 ? pR + dppar : (wid == 1 ? pR - dppar : pR), f, &err, q0, 2);
+#pragma unroll
+          for (int q = 0; q < 6; q++)
+            if (q >= q0 && q < q0 + 2) s_f[wid][q - q0] = f.v[q];
+        }
+        __syncthreads();
+        cd gprime[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) gprime[e] = (s_f[0][e] - s_f[1][e]) / (2.0 * dppar);
+        for (int j = 1 + tid; j <= M_P; j += LAT_THREADS) {
+          const double wj = (j == M_P) ? 1.0 : 2.0;
+          const double p = (j == M_P) ? pR + capDelta : pR + smdelta * j;
+          const double x2 = (p - pR) * (p - pR);
+          const double lor = x2 / (x2 + pI * pI);
+#pragma unroll
+          for (int q = 0; q < 6; q++)
+            if (q >= q0 && q < q0 + 2) acc.v[q] += (wj * 2.0) * gprime[q - q0] * lor;
+        }
+        if (tid == 0 && pI != 0.0) {
+          const double sgn = pI > 0.0 ? 1.0 : -1.0;
+#pragma unroll
+          for (int q = 0; q < 6; q++)
+            if (q >= q0 && q < q0 + 2) acc.v[q] += sgn * (cmul_i((2.0 * PI) * s_f[2][q - q0]) / smdelta);
+        }
+      }
+      if (piece == 2) {
+        // tiny rest between p_res + capDelta and the first regular node, :1168-1230
+        const double rest = ppar[pe.upperlimit] - pR - capDelta;
+        const int ntiny = (int)(rest / smdelta);
+        if (ntiny > 0) {
+          const double correction = (rest / (1.0 * ntiny)) / smdelta;
+          for (int j = tid; j <= ntiny; j += LAT_THREADS) {
+            const double wj = (j == 0 || j == ntiny) ? 1.0 : 2.0;
+            const double p = (j == 0) ? pR + capDelta : pR + capDelta + correction * smdelta * j;
+            Six f1;
+            funct_g6(g, sp, gw, wbase, p, f1, &err, q0, 2);
+            const cd d1 = mk(p - pR, -pI);
+#pragma unroll
+            for (int q = 0; q < 6; q++)
+              if (q >= q0 && q < q0 + 2) acc.v[q] += (wj * correction) * (f1.v[q] / d1);
+          }
+        }
+      }
+    }
+
+    if ((pe.flags & PLAN_LANDAU) && part >= 9) {
+      // landau_integrate, src/ALPS_fns.f90:1327-1452; acc.v[0..2] collect La, Lb, Lc
+      const double dpperp = sp.dpperp, dppar = sp.dppar_abs;
+      const double* Jn = sp.J + (size_t)(nabs + 1) * sp.ldj;
+      const double* Jm = sp.J + (size_t)nabs * sp.ldj;
+      const double* Jp = sp.J + (size_t)(nabs + 2) * sp.ldj;
+      const cd ppl = mk(pR + dppar, pI), pmi = mk(pR - dppar, pI);
+      const int gidx = tid >> 2, sub = tid & 3, lbase = wlane & ~3;
+      for (int r0 = 64 * (part - 9); r0 <= nperp; r0 += 128) {
+        const int r = r0 + gidx;
+        const bool valid = r <= nperp;
+        const bool interior = r >= 1 && r <= nperp - 1;
+        const int hi = (r == 0) ? 1 : (r == nperp ? nperp : r + 1);
+        const int lo = (r == 0) ? 0 : (r == nperp ? nperp - 1 : r - 1);
+        cd v = mk(0.0, 0.0);
+        if (valid) {
+          if (sub == 0) v = eval_fit(g, s, r, ppl);
+          else if (sub == 1) v = eval_fit(g, s, r, pmi);
+          else if (sub == 2) v = eval_fit(g, s, hi, p_res);
+          else v = eval_fit(g, s, lo, p_res);
+        }
+        cd fpar_i, fpar_f, fperp_i, fperp_f;
+        fpar_i.x = __shfl_sync(0xffffffffu, v.x, lbase + 0);  fpar_i.y = __shfl_sync(0xffffffffu, v.y, lbase + 0);
+        fpar_f.x = __shfl_sync(0xffffffffu, v.x, lbase + 1);  fpar_f.y = __shfl_sync(0xffffffffu, v.y, lbase + 1);
+        fperp_i.x = __shfl_sync(0xffffffffu, v.x, lbase + 2); fperp_i.y = __shfl_sync(0xffffffffu, v.y, lbase + 2);
+        fperp_f.x = __shfl_sync(0xffffffffu, v.x, lbase + 3); fperp_f.y = __shfl_sync(0xffffffffu, v.y, lbase + 3);
+        if (valid && sub == 0) {
+          // the reference tests fpar_f twice and never fperp_f (lines 1404-1405); interior rows only
+          if (interior && ((fpar_i.x == 0.0 && fpar_i.y == 0.0) || (fpar_f.x == 0.0 && fpar_f.y == 0.0) ||
+                           (fperp_i.x == 0.0 && fperp_i.y == 0.0)))
+            zero = 1;
+          const double h = (r == 0 || r >= nperp - 1) ? 0.5 : 1.0;
+          const cd dfperp = (fperp_i - fperp_f) / (interior ? 2.0 * dpperp : dpperp);
+          const cd dfpar = (fpar_i - fpar_f) / (2.0 * dppar);
+          const double pperp = sp.pperp[r];
+          const cd Q = (qs / fabs(kpar)) * (((pperp * dfpar - p_res * dfperp) * kpar) / ms + omc * dfperp);
+          const double bj = Jn[r];
+          const double bp = (nabs >= 1) ? 0.5 * (Jm[r] - Jp[r]) : -Jp[r];
+          acc.v[0] += (h * (bj * bj)) * Q;
+          acc.v[1] += (h * (pperp * (bj * bp))) * Q;
+          acc.v[2] += (h * ((pperp * pperp) * (bp * bp))) * Q;
+        }
+      }
+    }
+
+    // ---- block sum -> partial row of this part
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      const cd t = warp_sum_c(acc.v[q]);
+      if (wlane == 0) s_part[wid][q] = t;
+    }
+    if (err) atomicMax(&s_err, err);
+    zero = __syncthreads_or(zero);
+    double* prow = Spart + (idx * LAT_PARTS + part) * LAT_STRIDE;
+    if (tid < 6) {
+      cd t = s_part[0][tid];
+      for (int w = 1; w < LAT_THREADS / 32; w++) t += s_part[w][tid];
+      prow[2 * tid] = t.x;
+      prow[2 * tid + 1] = t.y;
+    }
+    if (tid == 6) {
+      prow[12] = zero ? 1.0 : 0.0;
+      prow[13] = (double)s_err;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&tickets[idx], 1) == LAT_PARTS - 1);
+    __syncthreads();
+    if (s_last && tid == 0) {
+      __threadfence();
+      tickets[idx] = 0;   // ready for the next launch
+      const double* pr = Spart + idx * LAT_PARTS * LAT_STRIDE;
+      auto ld = [&](int prt, int q) { return mk(__ldcg(pr + prt * LAT_STRIDE + 2 * q), __ldcg(pr + prt * LAT_STRIDE + 2 * q + 1)); };
+      Six tot;
+      six_zero(tot);
+      int e = 0;
+      for (int prt = 0; prt < LAT_PARTS; prt++) e = max(e, (int)__ldcg(pr + prt * LAT_STRIDE + 13));
+      if (pe.flags & PLAN_NEAR) {
+        const double capDelta = pR - ppar[pe.ipar_res - M_I];
+        const double smdelta = capDelta / (1.0 * M_P);
+        const double near_fac = 2.0 * PI * smdelta * sp.dpperp * 0.25;
+#pragma unroll
+        for (int q = 0; q < 6; q++) tot.v[q] += near_fac * ((ld(q / 2, q) + ld(3 + q / 2, q)) + ld(6 + q / 2, q));
+      }
+      const bool zr = __ldcg(pr + 9 * LAT_STRIDE + 12) != 0.0 || __ldcg(pr + 10 * LAT_STRIDE + 12) != 0.0;
+      if ((pe.flags & PLAN_LANDAU) && !zr) {
+        // landau = -(sum) * i * dpperp * pi * 2 pi ; factor 2 (Im om < 0) or 1 (Im om == 0),
+        // full_integrate src/ALPS_fns.f90:782-789
+        const double mult = (omc.y < 0.0 ? 2.0 : 1.0) * sp.dpperp * PI * 2.0 * PI;
+        const cd ca = cmul_i(-(ld(9, 0) + ld(10, 0))) * mult, cb = cmul_i(-(ld(9, 1) + ld(10, 1))) * mult,
+                 cc = cmul_i(-(ld(9, 2) + ld(10, 2))) * mult;
+        tot.v[0] += ca;
+        tot.v[1] += p_res * ca;
+        tot.v[2] += (p_res * p_res) * ca;
+        tot.v[3] += cb;
+        tot.v[4] += p_res * cb;
+        tot.v[5] += cc;
+      }
+      double* o = Sres + idx * 12;
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        o[2 * q] = tot.v[q].x;
+        o[2 * q + 1] = tot.v[q].y;
+      }
+      if (e) {
+        err_flag[0] = 1;
+        err_flag[1] = (int)idx;
+        err_flag[2] = pe.ipar_res;
+        err_flag[3] = pe.upperlimit;
+        err_flag[4] = pe.flags;
+        err_flag[5] = e;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------- chi partial
 // One warp per (omega, species): tensor components of every (n, sign) from its six moment
 // sums, summed over the harmonics of this process' shard.
@@ -676,10 +925,12 @@ void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int 
   k_plan<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, om, n_om, plan, work, work_count);
 }
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
-                     const int* work_count, const double* gwin, double* Sres, int* err_flag, cudaStream_t st) {
+                     const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
+                     int* tickets, cudaStream_t st) {
   if (n_om <= 0) return;
-  if (n_om <= 64)
-    k_resonant<true><<<148 * 4, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
+  if (n_om <= 64 && Spart && tickets)
+    k_resonant_lat<<<dim3(148, LAT_PARTS), LAT_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag,
+                                                                 Spart, tickets);
   else
     k_resonant<false><<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
 }
