@@ -28,6 +28,9 @@ struct SpeciesHost {
   size_t cap_J = 0, cap_W = 0, cap_G = 0;
   // fragment-ordered operands of the DMMA quadrature variants (quad_mma.cu)
   double *d_Af = nullptr, *d_Cf = nullptr, *d_Wf = nullptr, *d_Jrel = nullptr;
+  double *d_Afs = nullptr, *d_Cfs = nullptr;   // the same tables in LAT_BN-column tiles (latency variant)
+  size_t cap_Xfs = 0;
+  bool afs_valid = false;
   size_t cap_Jrel = 0;
   size_t cap_Xf = 0, cap_Wf = 0;
   bool af_valid = false;
@@ -56,6 +59,14 @@ struct State {
          *d_partial = nullptr, *d_chi0 = nullptr, *d_chi0_low = nullptr, *d_wave = nullptr, *d_ext = nullptr;
   PlanEntry* d_plan = nullptr;
   int *d_work = nullptr, *d_work_count = nullptr, *d_err = nullptr;
+  // alps_b200_disp (one omega, no aux outputs, no NHDS species): the whole chain -- H2D of omega, five
+  // kernels, D2H of D and of the error words -- is captured once into a CUDA graph and replayed while the
+  // baked launch parameters (DispSig) stay the same; sequential root finding is bound by launch latency
+  cudaGraphExec_t disp_graph = nullptr;
+  std::vector<unsigned char> disp_sig;
+  long long disp_graph_launches = 0;
+  int disp_plain_calls = 0;      // plain calls since the signature last changed (the first one warms up)
+  bool capturing = false, graph_off = false;
   double* d_respart = nullptr;   // k_resonant_lat partial rows (small batches)
   int* d_restick = nullptr;
   double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
@@ -68,6 +79,10 @@ struct State {
   std::vector<FastItem> fitems;
   double* d_om_i = nullptr;   // the constant omega = i of the STORE launch
   QuadParams P{};
+  // latency variant of the DMMA quadrature (few omegas in flight on a small grid): narrow p_par tiles so
+  // that one D spreads over many SMs; needs its own fragment-ordered copies of A' and C'
+  QuadParams Plat{};
+  bool have_lat = false;
   std::vector<double> ext;   // external chi of the next alps_b200_disp call, [nspec][PARTIAL_PER_SPEC]
   bool ext_any = false;
   nhds::Params bm[MAXSPEC];  // &bM_spec_j of use_bM species (NHDS twin, nhds.hpp)
@@ -122,7 +137,15 @@ inline size_t ipp(int nspec, int nperp, int npar, int is0, int iperp, int ipar, 
   return is0 + (size_t)nspec * (iperp + (size_t)(nperp + 1) * (ipar + (size_t)(npar + 1) * c0));
 }
 
+void drop_disp_graph() {
+  if (S.disp_graph) cudaGraphExecDestroy(S.disp_graph);
+  S.disp_graph = nullptr;
+  S.disp_sig.clear();
+  S.disp_plain_calls = 0;
+}
+
 void free_batch() {
+  drop_disp_graph();
   dfree(&S.d_om); dfree(&S.d_D); dfree(&S.d_Sbulk); dfree(&S.d_Sres); dfree(&S.d_gwin); dfree(&S.d_partial);
   dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work); dfree(&S.d_ext);
   dfree(&S.d_relpart); dfree(&S.d_reltick); dfree(&S.d_respart); dfree(&S.d_restick);
@@ -203,6 +226,7 @@ int build_tables_from_df0() {
     d.Cp = h.d_Cp;
     d.C0 = h.d_C0;
     h.af_valid = false;
+    h.afs_valid = false;
   }
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());
@@ -267,8 +291,13 @@ int build_hoisted_tables() {
 }
 
 constexpr int SMALL_BATCH = 64;
-int nsplit_small() {
-  const int NT = (S.cfg.npar - 1 + S.qv.bn - 1) / S.qv.bn;
+constexpr int LAT_VARIANT = 20, LAT_BN = 32, LAT_NPAR_MAX = 1024, LAT_BATCH = 8;
+bool use_lat(int n) { return S.have_lat && S.mode == 0 && n <= LAT_BATCH; }
+// p_par split of the quadrature kernel for n <= SMALL_BATCH omegas; a function of the configuration and of
+// the batch class (n <= LAT_BATCH or not) only
+int nsplit_small(int n) {
+  const int bn = use_lat(n) ? LAT_BN : S.qv.bn;
+  const int NT = (S.cfg.npar - 1 + bn - 1) / bn;
   return std::max(1, std::min(NT, (2 * S.sm_count) / std::max(1, (int)S.tiles.size())));
 }
 
@@ -281,9 +310,10 @@ int ensure_batch(int want) {
   if (S.batch >= want && S.d_om) return 0;
   free_batch();
   const size_t NI = S.gh.NI, B = want;
-  // Sbulk rows: n * nsplit(n) <= max(B, SMALL_BATCH * nsplit_small()) (see run_chunk)
+  // Sbulk rows: n * nsplit(n) <= max(B, SMALL_BATCH * nsplit_small(SMALL_BATCH), LAT_BATCH * nsplit_small(1))
   if (dalloc(&S.d_om, 2 * B) || dalloc(&S.d_D, 2 * B) ||
-      dalloc(&S.d_Sbulk, std::max(B, (size_t)SMALL_BATCH * nsplit_small()) * NI * 12) ||
+      dalloc(&S.d_Sbulk, std::max({B, (size_t)SMALL_BATCH * nsplit_small(SMALL_BATCH),
+                                   (size_t)LAT_BATCH * nsplit_small(1)}) * NI * 12) ||
       dalloc(&S.d_Sres, B * NI * 12) || dalloc(&S.d_gwin, B * NI * S.gh.WINX * 6) ||
       dalloc(&S.d_partial, B * S.gh.nspec * PARTIAL_PER_SPEC) || dalloc(&S.d_chi0, B * S.gh.nspec * 18) ||
       dalloc(&S.d_chi0_low, B * S.gh.nspec * 54) || dalloc(&S.d_wave, B * 18) || dalloc(&S.d_plan, B * NI) ||
@@ -373,16 +403,27 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     S.P.om = d_om;
     S.P.n_om = n;
     // few omegas in flight (sequential root finding, batched roots): spread each (omega, tile) over
-    // several CTAs along p_par.  The split depends only on the configuration for n <= SMALL_BATCH, so a
-    // single disp() and a small disp_batch() give bitwise identical D.
-    S.P.nsplit = (S.mode == 1 || n > SMALL_BATCH) ? 1 : nsplit_small();
-    cudaEventRecord(S.ev0, S.stream);
+    // several CTAs along p_par.  The split depends only on the configuration and on the batch class
+    // (n <= LAT_BATCH: narrow-tile latency variant; n <= SMALL_BATCH), so a single disp() and a
+    // disp_batch() of up to LAT_BATCH omegas (batched roots) give bitwise identical D.
+    S.P.nsplit = (S.mode == 1 || n > SMALL_BATCH) ? 1 : nsplit_small(n);
+    if (use_lat(n)) {
+      S.Plat.om = d_om;
+      S.Plat.n_om = n;
+      S.Plat.nsplit = S.P.nsplit;
+      S.Plat.plan = S.P.plan;
+      S.Plat.Sbulk = S.P.Sbulk;
+      S.Plat.gwin = S.P.gwin;
+    }
+    if (!S.capturing) cudaEventRecord(S.ev0, S.stream);
     cudaError_t e = cudaSuccess;
     if (S.mode == 1)
       launch_fast(gd, d_om, n, S.d_fitems, (int)S.fitems.size(), S.d_plan, S.d_Sbulk, S.d_gwin, S.stream);
     else
-      e = S.qv.id >= 9 ? launch_quad_mma(S.P, S.qv.id, false, S.stream) : launch_quad(S.P, S.qv.id, false, S.stream);
-    cudaEventRecord(S.ev1, S.stream);
+      e = use_lat(n)      ? launch_quad_mma(S.Plat, LAT_VARIANT, false, S.stream)
+          : S.qv.id >= 9 ? launch_quad_mma(S.P, S.qv.id, false, S.stream)
+                         : launch_quad(S.P, S.qv.id, false, S.stream);
+    if (!S.capturing) cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.d_respart,
                     S.d_restick, S.stream);
@@ -481,6 +522,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.ext_any = false;
   S.mode = 0;
   {
+    S.graph_off = getenv("ALPS_B200_NO_GRAPH") != nullptr;   // plain launches for alps_b200_disp
     const char* v = getenv("ALPS_B200_QUAD_VARIANT");   // tuning knob: tile shape of k_quad
     S.qv = quad_variant(v ? atoi(v) : 15);
   }
@@ -498,7 +540,9 @@ void alps_b200_finalize(void) {
   for (int s = 0; s < MAXSPEC; s++) {
     SpeciesHost& h = S.sp[s];
     dfree(&h.d_pperp); dfree(&h.d_ppar); dfree(&h.d_A); dfree(&h.d_C0); dfree(&h.d_Cp); dfree(&h.d_J);
-    dfree(&h.d_Af); dfree(&h.d_Cf); dfree(&h.d_Wf); dfree(&h.d_Jrel);
+    dfree(&h.d_Af); dfree(&h.d_Cf); dfree(&h.d_Wf); dfree(&h.d_Jrel); dfree(&h.d_Afs); dfree(&h.d_Cfs);
+    h.cap_Xfs = 0;
+    h.afs_valid = false;
     h.cap_Jrel = 0;
     h.cap_Xf = h.cap_Wf = 0;
     h.af_valid = false;
@@ -516,6 +560,8 @@ void alps_b200_finalize(void) {
   if (S.h_pin) cudaFreeHost(S.h_pin);
   S.h_pin = nullptr;
   S.h_pin_bytes = 0;
+  drop_disp_graph();
+  S.graph_off = false;
   if (S.ev0) cudaEventDestroy(S.ev0);
   if (S.ev1) cudaEventDestroy(S.ev1);
   S.ev0 = S.ev1 = nullptr;
@@ -768,6 +814,8 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
   }
   // ---- tables
   const bool mma = S.qv.id >= 9;                                   // DMMA variants: fragment-ordered operands
+  const bool lat = mma && npar - 1 <= LAT_NPAR_MAX && !getenv("ALPS_B200_NO_LAT");
+  const double *Afs[MAXSPEC] = {nullptr}, *Cfs[MAXSPEC] = {nullptr};
   const int nks = ((((nperp - 1) + 3) / 4) + 7) & ~7;              // k-steps of 4 p_perp rows, padded to 8
   int item_base = 0;
   S.tiles.clear();
@@ -859,6 +907,24 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
       S.P.Cf[s] = h.d_Cf;
       S.P.Wf[s] = h.d_Wf;
       S.P.nks = nks;
+      if (lat) {
+        const int ntl = (npar - 1 + LAT_BN - 1) / LAT_BN;
+        const size_t nXs = (size_t)ntl * nks * 4 * LAT_BN;
+        if (nXs > h.cap_Xfs) {
+          if (dalloc(&h.d_Afs, nXs) || dalloc(&h.d_Cfs, nXs)) return ALPS_B200_ERR_CUDA;
+          h.cap_Xfs = nXs;
+          h.afs_valid = false;
+        }
+        if (!h.afs_valid) {
+          launch_frag_table(h.d_A, d.ldp, nperp - 1, npar - 1, 1.0, h.d_Afs, nks, LAT_BN, ntl, S.stream);
+          S.launches += 1;
+          h.afs_valid = true;
+        }
+        launch_frag_table(h.d_C0, d.ldp, nperp - 1, npar - 1, kpar, h.d_Cfs, nks, LAT_BN, ntl, S.stream);
+        S.launches += 1;
+        Afs[s] = h.d_Afs;
+        Cfs[s] = h.d_Cfs;
+      }
       for (int n0 = (d.nlo_shard / MMA_NH) * MMA_NH; n0 <= d.nhi_shard; n0 += MMA_NH) S.tiles.push_back(QuadTile{s, n0});
       continue;
     }
@@ -885,6 +951,14 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
   S.P.tiles = S.d_tiles;
   S.P.ntiles = (int)S.tiles.size();
   S.P.g = S.gd;
+  S.have_lat = lat && !S.tiles.empty();
+  if (S.have_lat) {
+    memcpy(&S.Plat, &S.P, sizeof(QuadParams));
+    for (int s = 0; s < nspec; s++) {
+      S.Plat.Af[s] = Afs[s];
+      S.Plat.Cf[s] = Cfs[s];
+    }
+  }
   S.have_k = true;
   if (S.mode == 1) {
     int rc = build_hoisted_tables();
@@ -970,6 +1044,74 @@ int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
   return 0;
 }
 
+// Signature of everything a captured single-omega chain bakes in.
+static void disp_signature(std::vector<unsigned char>& sig) {
+  QuadParams P;
+  memcpy(&P, use_lat(1) ? &S.Plat : &S.P, sizeof(P));
+  P.plan = S.P.plan;
+  P.Sbulk = S.P.Sbulk;
+  P.gwin = S.P.gwin;
+  P.om = S.d_om;
+  P.n_om = 1;
+  P.nsplit = (S.mode == 1) ? 1 : nsplit_small(1);
+  const void* ptrs[] = {S.stream, S.gd, S.d_om, S.d_D, S.d_plan, S.d_work, S.d_work_count, S.d_Sbulk, S.d_Sres,
+                        S.d_gwin, S.d_partial, S.d_err, S.d_rtiles, S.d_fitems, S.d_respart, S.d_restick,
+                        S.d_relpart, S.d_reltick, S.h_pin};
+  const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)S.rtiles.size(), (long long)S.fitems.size(), S.mode,
+                            S.qv.id, nsplit_rel()};
+  sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
+  memcpy(sig.data(), &P, sizeof(P));
+  memcpy(sig.data() + sizeof(P), ptrs, sizeof(ptrs));
+  memcpy(sig.data() + sizeof(P) + sizeof(ptrs), ints, sizeof(ints));
+}
+
+// omega is in S.h_pin[0..1]; on success with *used = 1, D is in S.h_pin[2..3]
+static int disp_via_graph(int* used) {
+  *used = 0;
+  std::vector<unsigned char> sig;
+  disp_signature(sig);
+  if (sig != S.disp_sig) {
+    drop_disp_graph();
+    S.disp_sig = sig;
+  }
+  if (!S.disp_graph) {
+    // the first call after a change runs the plain path (first-use kernel attributes, lazy module loading)
+    if (S.disp_plain_calls++ < 1) return 0;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(S.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      S.graph_off = true;
+      return 0;
+    }
+    S.capturing = true;
+    const long long l0 = S.launches;
+    cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream);
+    const int rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, false, S.h_pin);
+    cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream);
+    cudaMemcpyAsync(S.h_pin + 8, S.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream);
+    S.capturing = false;
+    S.disp_graph_launches = S.launches - l0;
+    S.launches = l0;
+    const cudaError_t e1 = cudaStreamEndCapture(S.stream, &graph);
+    cudaError_t e2 = cudaSuccess;
+    if (e1 == cudaSuccess && !rc) e2 = cudaGraphInstantiate(&S.disp_graph, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || rc) {
+      cudaGetLastError();
+      S.disp_graph = nullptr;
+      S.graph_off = true;   // fall back to plain launches for the rest of the session
+      return 0;
+    }
+  }
+  CK(cudaGraphLaunch(S.disp_graph, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  S.launches += S.disp_graph_launches;
+  const int* herr = reinterpret_cast<const int*>(S.h_pin + 8);
+  if (herr[0] || herr[6]) return check_device_errors();   // reports and clears the device error words
+  *used = 1;
+  return 0;
+}
+
 int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_low, double* wave) {
   int rc = check_ready();
   if (rc) return rc;
@@ -979,6 +1121,17 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   if ((rc = ensure_pinned(64 * sizeof(double)))) return rc;
   S.h_pin[0] = om[0];
   S.h_pin[1] = om[1];
+  if (!chi0 && !chi0_low && !wave && !S.bm_any && !S.ext_any && !S.graph_off && S.stream != nullptr) {
+    int used = 0;
+    if ((rc = disp_via_graph(&used))) return rc;
+    if (used) {
+      if (D) {
+        D[0] = S.h_pin[2];
+        D[1] = S.h_pin[3];
+      }
+      return 0;
+    }
+  }
   CK(cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
   const bool aux = chi0 || chi0_low || wave;
   if ((rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, aux, om))) return rc;
@@ -1079,6 +1232,7 @@ int alps_b200_set_mode(int mode) {
 
 int alps_b200_set_stream(void* cuda_stream) {
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  drop_disp_graph();
   S.stream = (cudaStream_t)cuda_stream;   // NULL = the legacy default stream, like cudaStream_t 0
   return 0;
 }

@@ -60,7 +60,7 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // block, one per group of 8 harmonics (3 M-tiles each) -- 4 warps per SM sub-partition instead of 2 hide
 // the stage hand-over (barrier wait, first fragment loads) of one warp behind the DMMAs of the others.
 template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0>
-__global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : 1) k_quad_mma(const __grid_constant__ QuadParams P) {
+__global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1)) k_quad_mma(const __grid_constant__ QuadParams P) {
   constexpr int TW = 16 * NW;     // p_par columns per tile
   constexpr int MT = 6 / HS;      // M-tiles per warp
   constexpr int HP = 2 / HS;      // harmonics per thread
@@ -356,6 +356,7 @@ cudaError_t launch_quad_mma(const QuadParams& P, int variant, bool store, cudaSt
 #endif
     case 16: return launch_mma_variant<8, 2, 4, 4>(P, store, st);
     case 17: return launch_mma_variant<4, 2, 8, 2>(P, store, st);   // 2 CTAs of 8 warps per SM
+    case 20: return launch_mma_variant<2, 2, 8, 5>(P, store, st);   // latency: 32-column tiles, 4 warps, 4 stages in flight (api.cu LAT_VARIANT)
     default: return launch_mma_variant<8, 1, 8, 2>(P, store, st);   // 9: one 8-warp CTA per SM (2 warps per sub-partition)
   }
 }
