@@ -7,10 +7,11 @@ else regenerated from the `_dist.in` closed forms), then map_search or refine_gu
 writing `<out>/<runname>.map / .roots / .scan_* / .eigen_* / .heat_* / .heat_mech_*` in the
 reference's formats.  Every D(omega,k) comes from the GPU (libalps_b200.so).
 
-Not reproduced here (out of scope): the LM / Chebyshev fits of
-determine_param_fit -- the analytic-continuation parameters are the generator's ideal values when
-the tables are regenerated, else the initial values of the &ffit blocks.  NHDS calc_chi for use_bM
-species is the host twin in csrc/nhds.hpp."""
+Analytic-continuation parameters: with --fit the twin of determine_param_fit (alps_b200/fits.py:
+Levenberg-Marquardt rows started from the &ffit blocks, Chebyshev series for ac_method = 2) runs like in
+the reference; without it they are the generator's ideal values when the tables are regenerated, else
+the initial values of the &ffit blocks.  NHDS calc_chi for use_bM species is the host twin in
+csrc/nhds.hpp."""
 from __future__ import annotations
 
 import argparse
@@ -24,7 +25,7 @@ from .namelist import read_namelists
 from .solver import Solver
 
 
-def plasma_from_inputs(nl, dist_nl=None, base_dir="."):
+def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False):
     s = nl["system"]
     nspec, nperp, npar = int(s["nspec"]), int(s["nperp"]), int(s["npar"])
     vA = float(s["va"])
@@ -87,6 +88,8 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir="."):
                 pp[i] = 0.0
                 f0[i] = 0.0
                 continue
+            if fit:     # the reference's flow: fit types, perpcorr and start values come from the .in file
+                continue
             species[i].fit_type = [fits[i]["fit_type"]] if not species[i].relativistic else species[i].fit_type
             species[i].perp_correction = [fits[i]["perpcorr"]]
             for k in range(5):
@@ -106,8 +109,24 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir="."):
         for r, i in enumerate(rel):
             g, p, f, d, integ = derivative_f0_rel(pp[i], f0[i], species[i].ms, vA, pl.ngamma, pl.npparbar)
             pl.gamma_rel[r], pl.pparbar_rel[r], pl.f0_rel[r], pl.df0_rel[r] = g, p, f, d
-            if not have_files:
+            if not have_files and not fit:
                 pf[i, :, 0, 0] = pf[i, 0, 0, 0] / integ
+    if fit:
+        from .fits import FitOptions, determine_param_fit
+        opt = FitOptions(maxsteps_fit=int(s.get("maxsteps_fit", 500)),
+                         lambda_initial_fit=float(s.get("lambda_initial_fit", 1.0)),
+                         lambdafac_fit=float(s.get("lambdafac_fit", 10.0)), epsilon_fit=float(s.get("epsilon_fit", 1.0e-8)))
+        initial = np.zeros((nspec, 5, maxfits))
+        for i in range(nspec):
+            for j, par in enumerate(fits_in[i]):
+                initial[i, :, j] = par
+        rel_in = None
+        if any(sp.relativistic for sp in species):
+            rel_in = {i: (pl.f0_rel[r], pl.gamma_rel[r], pl.pparbar_rel[r])
+                      for r, i in enumerate(k for k, sp in enumerate(species) if sp.relativistic)}
+        pl.param_fit, poly, pl.fit_quality = determine_param_fit(pl, initial, opt, rel_in)
+        if poly is not None:
+            pl.poly_fit_coeffs = poly
     return pl
 
 
@@ -117,12 +136,19 @@ def main(argv=None):
     ap.add_argument("--dist", default=None)
     ap.add_argument("--out", default="solution")
     ap.add_argument("--nproc", type=int, default=0, help="MPI size of the reference run to emulate")
+    ap.add_argument("--fit", action="store_true",
+                    help="run the twin of determine_param_fit (LM / Chebyshev fits) instead of using ideal parameters")
     a = ap.parse_args(argv)
     nl = read_namelists(a.input)
     runname = os.path.splitext(os.path.basename(a.input))[0]
     dist_nl = read_namelists(a.dist) if a.dist else None
-    pl = plasma_from_inputs(nl, dist_nl, base_dir=os.getcwd())
+    pl = plasma_from_inputs(nl, dist_nl, base_dir=os.getcwd(), fit=a.fit)
     s = nl["system"]
+    if a.fit:
+        # what output_fit prints (src/ALPS_analyt.f90:942-943)
+        q = pl.fit_quality
+        print(" Sum of all least-squares: %14.4E" % q)
+        print(" Standard error of the estimate: %14.4E" % np.sqrt(q / (1.0 * pl.nspec * pl.nperp * pl.npar)))
     os.makedirs(a.out, exist_ok=True)
     prefix = os.path.join(a.out, runname)
     sol = Solver(pl, emulate_nproc=a.nproc)

@@ -78,6 +78,7 @@ class Plasma:
     positions_principal: int = 3
     n_resonance_interval: int = 100
     kperp_norm: bool = True
+    fit_quality: float = 0.0   # qualitytotal of determine_param_fit when the fits were run (alps_b200.fits)
 
     @property
     def nspec(self) -> int:

@@ -116,6 +116,20 @@ def test_cli_twin_of_the_main_program(tmp_path):
     assert os.path.exists(os.path.join(out, "test_kpar_fast.roots"))
 
 
+def test_cli_twin_with_the_fit_producers(tmp_path):
+    """Same run with --fit: the analytic-continuation parameters come from the twin of determine_param_fit
+    started from the &ffit blocks (what the reference run that wrote the goldens did), not from the ideal values."""
+    from alps_b200 import run
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "solution")
+    rc = run.main([os.path.join(here, "inputs", "test_kpar_fast.in"), "--fit",
+                   "--dist", os.path.join(here, "inputs", "test_kpar_fast_dist.in"), "--out", out, "--nproc", "4"])
+    assert rc == 0
+    ours = open(os.path.join(out, "test_kpar_fast.scan_kpara_1.root_1")).read().split()
+    gold = open(os.path.join(GOLD, "test_kpar_fast.scan_kpara_1.root_1")).read().split()
+    assert ours == gold
+
+
 def test_double_scan_rows_are_single_scans(tmp_path):
     """scan_option=2 (om_double_scan, src/ALPS_fns.f90:2904-3591) on a shortened tests/test_double_scan.in:
     every outer row is an inner k_perp scan started from the outer k_par root (kept in single precision
