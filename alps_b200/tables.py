@@ -111,7 +111,15 @@ def generate_distribution(specs: Sequence[DistSpec], nperp: int, npar: int, beta
         ms, tau, alph, drift, kap = sp.ms, sp.tau, sp.alph, sp.drift, sp.kappa
         ifit = [0.0] * 5
         iperpcorr = 1.0
-        if sp.distribution == 1:
+        if sp.distribution == 0:
+            # table from distribution/distribution_analyt.f90:66-85 (hard-coded beta = 1 Maxwellians of
+            # species 1 and 2), no normalisation, limits always maxPperpS / maxPparS (lines 177-181)
+            if i > 1:
+                raise ValueError("distribution_analyt defines species 1 and 2 only")
+            norm = 1.0
+            pperp_max, ppar_max = sp.maxPperp, sp.maxPpar
+            ftype = 1
+        elif sp.distribution == 1:
             norm = pi ** (-1.5) / ((ms * beta * tau) ** 1.5 * alph)
             pperp_max = maxP * math.sqrt(ms * tau * alph)
             ppar_max = maxP * math.sqrt(ms * tau)
@@ -145,7 +153,7 @@ def generate_distribution(specs: Sequence[DistSpec], nperp: int, npar: int, beta
             ftype = 6
         else:
             raise ValueError("distribution type %d not supported" % sp.distribution)
-        if not sp.autoscale:
+        if not sp.autoscale and sp.distribution != 0:
             pperp_max, ppar_max = sp.maxPperp, sp.maxPpar
         dpperp = pperp_max / float(nperp)
         dppar = 2.0 * ppar_max / float(npar)
@@ -153,7 +161,10 @@ def generate_distribution(specs: Sequence[DistSpec], nperp: int, npar: int, beta
         ppar = np.arange(npar + 1, dtype=np.float64) * dppar - ppar_max + drift
         P, Q = np.meshgrid(pperp, ppar, indexing="ij")
         dq = Q - drift
-        if sp.distribution == 1:
+        if sp.distribution == 0:
+            ms_a = 1.0 if i == 0 else 1.0 / 1836.0
+            f = (pi ** (-1.5) / ((ms_a * 1.0) ** 1.5)) * np.exp(-(Q * Q / (1.0 * ms_a) + (P * P) / (1.0 * ms_a)))
+        elif sp.distribution == 1:
             f = np.exp(-((dq * dq) / (beta * ms * tau) + (P * P) / (tau * beta * ms * alph)))
         elif sp.distribution == 2:
             f = (1.0 + (dq * dq) / (beta * ms * kap * a * a * tau)
