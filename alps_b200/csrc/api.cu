@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "../../include/alps_b200.h"
@@ -368,23 +370,42 @@ int prepare_external(int n, const double* d_om, const double* h_om, const double
     static const int MI[6] = {0, 1, 2, 0, 0, 1}, MJ[6] = {0, 1, 2, 1, 2, 2};
     for (int s = 0; s < nspec; s++) {
       if (!S.gh.sp[s].usebM || !S.bm[s].set) continue;
-      for (int i = 0; i < n; i++) {
-        nhds::cplx chi[9], low[27];
-        int rc = nhds::calc_chi(chi, low, S.bm[s], S.gh.kpar, S.gh.kperp, nhds::cplx(h_om[2 * i], h_om[2 * i + 1]),
-                                S.gh.kperp_norm != 0);
-        if (rc) return fail(ALPS_B200_ERR_UNSUPPORTED, "cold-plasma species need kperp_norm=.true. (ALPS_NHDS.f90:461)");
-        double* o = S.ext_batch.data() + (size_t)i * per + (size_t)s * PARTIAL_PER_SPEC;
-        for (int c = 0; c < 6; c++) {
-          const nhds::cplx v = chi[MI[c] + 3 * MJ[c]];
-          o[2 * c] = v.real();
-          o[2 * c + 1] = v.imag();
-          for (int m = 0; m < 3; m++) {
-            const nhds::cplx vl = low[MI[c] + 3 * MJ[c] + 9 * m];
-            o[2 * (6 + 3 * c + m)] = vl.real();
-            o[2 * (6 + 3 * c + m) + 1] = vl.imag();
+      // independent per omega: large batches (maps) are spread over the host cores, like the reference
+      // spreads its ranks; a single omega stays on the calling thread
+      std::atomic<int> bad{0};
+      auto body = [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++) {
+          nhds::cplx chi[9], low[27];
+          int rc = nhds::calc_chi(chi, low, S.bm[s], S.gh.kpar, S.gh.kperp, nhds::cplx(h_om[2 * i], h_om[2 * i + 1]),
+                                  S.gh.kperp_norm != 0);
+          if (rc) {
+            bad = 1;
+            return;
+          }
+          double* o = S.ext_batch.data() + (size_t)i * per + (size_t)s * PARTIAL_PER_SPEC;
+          for (int c = 0; c < 6; c++) {
+            const nhds::cplx v = chi[MI[c] + 3 * MJ[c]];
+            o[2 * c] = v.real();
+            o[2 * c + 1] = v.imag();
+            for (int m = 0; m < 3; m++) {
+              const nhds::cplx vl = low[MI[c] + 3 * MJ[c] + 9 * m];
+              o[2 * (6 + 3 * c + m)] = vl.real();
+              o[2 * (6 + 3 * c + m) + 1] = vl.imag();
+            }
           }
         }
+      };
+      const int hw = (int)std::thread::hardware_concurrency();
+      const int nthr = (n >= 512 && hw > 1) ? std::min(hw, n / 128) : 1;
+      if (nthr <= 1) {
+        body(0, n);
+      } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthr; t++)
+          pool.emplace_back(body, (int)((long long)n * t / nthr), (int)((long long)n * (t + 1) / nthr));
+        for (auto& th : pool) th.join();
       }
+      if (bad) return fail(ALPS_B200_ERR_UNSUPPORTED, "cold-plasma species need kperp_norm=.true. (ALPS_NHDS.f90:461)");
     }
   }
   if (S.ext_any)   // caller-supplied chi (alps_b200_add_external_chi) applies to the first omega
