@@ -45,6 +45,7 @@ template <int NW, int KSTG, int NST>
 struct MmaSmem {
   MmaStage<NW, KSTG> st[NST];
   double red[NW][MMA_NH][2][12];   // [warp][harmonic][sign][12]
+  PlanEntry plan[MMA_NH][2];       // resonance plan of this CTA's (harmonic, sign) items: the same for every p_par tile
   unsigned long long full[NST];
   unsigned long long empty[NST];
 };
@@ -95,6 +96,14 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
       mbar_init(&sm.empty[s], NW * HS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (!STORE && threadIdx.x < 2 * MMA_NH) {
+    const int nabs = tile.n0 + (threadIdx.x >> 1), sg = threadIdx.x & 1;
+    PlanEntry pe;
+    pe.lo1 = 1; pe.hi1 = 0; pe.lo2 = 1; pe.hi2 = 0; pe.flags = 0; pe.ipar_res = 0; pe.upperlimit = 0; pe.pad = 0;
+    if (nabs <= sp.nhi_shard && nabs >= sp.nlo_shard && !(nabs == 0 && sg == 1))
+      pe = P.plan[(size_t)iom * g.NI + sp.item_base + 2 * nabs + sg];
+    sm.plan[threadIdx.x >> 1][sg] = pe;
   }
   __syncthreads();
 
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
       for (int sg = 0; sg < 2; sg++) {
         if (nabs == 0 && sg == 1) continue;
         const size_t item = item0 + 2 * nabs + sg;
-        const PlanEntry pe = P.plan[item];
+        const PlanEntry pe = sm.plan[nabs - tile.n0][sg];
         if (!(pe.flags & PLAN_ACTIVE)) continue;
         const double nq = (sg ? -1.0 : 1.0) * (double)nabs * qs;
         double* S = &Sv[(h * 2 + sg) * 12];

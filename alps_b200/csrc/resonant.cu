@@ -264,46 +264,25 @@ __device__ __forceinline__ cd warp_sum_c(cd v) {
 }
 
 constexpr int RES_THREADS = 128;
-// sum over the cooperating threads (block or warp): every thread gets the total, deterministic order
-template <bool BLOCK>
-__device__ __forceinline__ void block_sum6(Six& v, cd (*s_part)[6], int wlane, int wid) {
-  if (!BLOCK) {
+// sum over the 32 lanes cooperating on one harmonic: every lane gets the total, deterministic order
+__device__ __forceinline__ void warp_sum6(Six& v) {
 #pragma unroll
-    for (int q = 0; q < 6; q++) v.v[q] = warp_sum_c(v.v[q]);
-    return;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 6; q++) {
-    cd t = warp_sum_c(v.v[q]);
-    if (wlane == 0) s_part[wid][q] = t;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < 6; q++) {
-    cd t = s_part[0][q];
-    for (int w = 1; w < RES_THREADS / 32; w++) t += s_part[w][q];
-    v.v[q] = t;
-  }
+  for (int q = 0; q < 6; q++) v.v[q] = warp_sum_c(v.v[q]);
 }
 
-// BLOCK = true: one block per resonant harmonic (few omegas in flight, latency matters);
-// BLOCK = false: one warp per resonant harmonic (large batches, throughput matters).
-template <bool BLOCK>
+// One warp per resonant harmonic (batches > 64: throughput matters; k_resonant_lat below serves small ones).
 __global__ void __launch_bounds__(RES_THREADS) k_resonant(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
                                                   const PlanEntry* __restrict__ plan, const int* __restrict__ work,
                                                   const int* __restrict__ work_count,
                                                   const double* __restrict__ gwin, double* __restrict__ Sres,
                                                   int* __restrict__ err_flag) {
-  // one 128-thread block per resonant harmonic: the sub-step / p_perp loops are spread over all threads
   const GlobalDev& g = *gp;
-  constexpr int STRIDE = BLOCK ? RES_THREADS : 32;      // threads cooperating on one harmonic
+  constexpr int STRIDE = 32;      // threads cooperating on one harmonic
   const int wlane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int lane = BLOCK ? threadIdx.x : wlane;         // index inside the cooperative loops
-  __shared__ cd s_part[RES_THREADS / 32][6];
+  const int lane = wlane;         // index inside the cooperative loops
   const int nwork = *work_count;
-  const int first = BLOCK ? blockIdx.x : (blockIdx.x * (RES_THREADS / 32) + wid);
-  const int step = BLOCK ? gridDim.x : gridDim.x * (RES_THREADS / 32);
+  const int first = blockIdx.x * (RES_THREADS / 32) + wid;
+  const int step = gridDim.x * (RES_THREADS / 32);
   for (int wi = first; wi < nwork; wi += step) {
     const size_t idx = (size_t)work[wi];
     const int iom = (int)(idx / g.NI), it = (int)(idx % g.NI);
@@ -382,7 +361,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resonant(const GlobalDev* __res
         }
       }
       const double fac = 2.0 * PI * smdelta * sp.dpperp * 0.25;
-      block_sum6<BLOCK>(acc, s_part, wlane, wid);
+      warp_sum6(acc);
 #pragma unroll
       for (int q = 0; q < 6; q++) tot.v[q] += fac * acc.v[q];
     }
@@ -434,12 +413,12 @@ __global__ void __launch_bounds__(RES_THREADS) k_resonant(const GlobalDev* __res
           Lc += (0.5 * ((pperp * pperp) * (bp * bp))) * Q;
         }
       }
-      zero = BLOCK ? __syncthreads_or(zero) : __any_sync(0xffffffffu, zero);
+      zero = __any_sync(0xffffffffu, zero);
       {
         Six L3;
         L3.v[0] = La; L3.v[1] = Lb; L3.v[2] = Lc;
         L3.v[3] = L3.v[4] = L3.v[5] = mk(0.0, 0.0);
-        block_sum6<BLOCK>(L3, s_part, wlane, wid);
+        warp_sum6(L3);
         La = L3.v[0]; Lb = L3.v[1]; Lc = L3.v[2];
       }
       if (!zero) {
@@ -932,7 +911,7 @@ void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanE
     k_resonant_lat<<<dim3(148, LAT_PARTS), LAT_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag,
                                                                  Spart, tickets);
   else
-    k_resonant<false><<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
+    k_resonant<<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
 }
 void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
                         const double* Sbulk, int nsplit, const double* Sres, double* partial, cudaStream_t st) {

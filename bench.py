@@ -305,7 +305,10 @@ def run_ours(args, w, rank, world, local_rank):
                            "l2": "flushed between steps (256 MiB write)", "mode": "direct quadrature"},
                 "e2e": {"value": e2e, "unit": "D/s", "h2d_bytes_per_step": 16 * B, "d2h_bytes_per_step": 16 * B},
                 "gpu_launches": launches,
-                "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s",
+                "roofline": {"bound": "tensor" if dmma else "fp64_fma",
+                             "pipe": ("FP64 tensor pipe (DMMA.8x8x4: the 64 FMA/clk/SM FP64 units)" if dmma
+                                      else "FP64 FMA pipe (DFMA)"),
+                             "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s",
                              "frac": achieved / peak_meas if peak_meas else None, "traffic": traffic,
                              "peak_source": ("DMMA (mma.sync.m8n8k4.f64)" if dmma else "DFMA") +
                                             " micro-benchmark run in this job (MEASURED_PEAKS.json has no FP64 entry)",
