@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libalps_b200.so")
+SO_PATH = os.environ.get("ALPS_B200_LIB") or os.path.join(_HERE, "libalps_b200.so")   # override: A/B builds only
 _LIB = None
 
 SYMBOLS = [

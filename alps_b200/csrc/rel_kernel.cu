@@ -58,7 +58,10 @@ __device__ inline cd cpowi(cd z, int k) {
   }
   return k < 0 ? mk(1.0, 0.0) / r : r;
 }
-__device__ inline cd cbessj(cd z, int nu) {
+// cold paths (principal-value window, Landau term) stay out of line: the hot loop then fits the
+// instruction cache (ncu: no_instruction stalls 1.6 -> per issue before)
+#define REL_NOINLINE __noinline__
+__device__ REL_NOINLINE cd cbessj(cd z, int nu) {
   cd sum = mk(0.0, 0.0);
   const cd mz2 = (-(z * z)) / 4.0;
   double fact = 1.0;
@@ -136,8 +139,8 @@ struct RelCtx {
   double kf1, kf2;
 };
 
-// G_mode(ig, ip) for both signs: pref (om dfg + (kpar/vA) dfp) T_mode   (numerator of resU_rel x int_T_rel)
-__device__ inline void node_values(const RelCtx& c, int ig, int ip, Six2& Tp, Six2& Tm, cd& num) {
+// G_mode(ig, ip) for sign sg: pref (om dfg + (kpar/vA) dfp) T_mode   (numerator of resU_rel x int_T_rel)
+__device__ inline void node_values(const RelCtx& c, int ig, int ip, int sg, Six2& T, cd& num) {
   const SpeciesDev& sp = *c.sp;
   const int ldr = c.g->npparbar + 1;
   const double gam = sp.grel[ig], pb = sp.pbrel[ip];
@@ -156,16 +159,14 @@ __device__ inline void node_values(const RelCtx& c, int ig, int ip, Six2& Tp, Si
     jm = c.nabs >= 1 ? bessj_ref(c.nabs - 1, z) : 0.0;
   }
   double bj, bp;
-  bessel_pair(c.nabs, 0, z, jm, j0, jp, bj, bp);
-  modes_real(bj, bp, pperpbar, pb, c.zbar, (double)c.nabs, c.kf1, c.kf2, Tp);
-  bessel_pair(c.nabs, 1, z, jm, j0, jp, bj, bp);
-  modes_real(bj, bp, pperpbar, pb, c.zbar, -(double)c.nabs, c.kf1, c.kf2, Tm);
+  bessel_pair(c.nabs, sg, z, jm, j0, jp, bj, bp);
+  modes_real(bj, bp, pperpbar, pb, c.zbar, sg ? -(double)c.nabs : (double)c.nabs, c.kf1, c.kf2, T);
   const double dfg = sp.dfg_rel[(size_t)ig * ldr + ip], dfp = sp.dfp_rel[(size_t)ig * ldr + ip];
   num = c.pref * (c.om * dfg + mk((c.g->kpar / c.g->vA) * dfp, 0.0));
 }
 
 // funct_g_rel for one sign (src/ALPS_fns_rel.f90:918-999), all six components
-__device__ inline void funct_g_rel6(const RelCtx& c, int sg, double p, int ig, Six2& out) {
+__device__ REL_NOINLINE void funct_g_rel6(const RelCtx& c, int sg, double p, int ig, Six2& out) {
   const SpeciesDev& sp = *c.sp;
   const int npb = c.g->npparbar, ldr = npb + 1;
   const double* pbv = sp.pbrel;
@@ -185,17 +186,17 @@ __device__ inline void funct_g_rel6(const RelCtx& c, int sg, double p, int ig, S
   if (p == pbv[npb]) ic = npb - 2;
   if (ic >= npb - 1) ic = npb - 2;
   if (ic <= 1) ic = 2;
-  Six2 Tp, Tm;
+  Six2 T;
   cd num, gm[6], g0[6], gp[6];
-  node_values(c, ig, ic - 1, Tp, Tm, num);
+  node_values(c, ig, ic - 1, sg, T, num);
 #pragma unroll
-  for (int q = 0; q < 6; q++) gm[q] = num * (sg ? Tm.v[q] : Tp.v[q]);
-  node_values(c, ig, ic, Tp, Tm, num);
+  for (int q = 0; q < 6; q++) gm[q] = num * T.v[q];
+  node_values(c, ig, ic, sg, T, num);
 #pragma unroll
-  for (int q = 0; q < 6; q++) g0[q] = num * (sg ? Tm.v[q] : Tp.v[q]);
-  node_values(c, ig, ic + 1, Tp, Tm, num);
+  for (int q = 0; q < 6; q++) g0[q] = num * T.v[q];
+  node_values(c, ig, ic + 1, sg, T, num);
 #pragma unroll
-  for (int q = 0; q < 6; q++) gp[q] = num * (sg ? Tm.v[q] : Tp.v[q]);
+  for (int q = 0; q < 6; q++) gp[q] = num * T.v[q];
   const double x = p - pbv[ic];
 #pragma unroll
   for (int q = 0; q < 6; q++) out.v[q] = g0[q] + (0.5 * ((gp[q] - gm[q]) / dpb)) * x;
@@ -215,7 +216,9 @@ constexpr int REL_THREADS = 256;
 // nsplit > 1 (few omegas in flight: sequential root finding is latency bound): the gamma rows / grid points
 // of one (omega, species, |n|) are dealt round-robin to nsplit CTAs; each leaves a partial row in Mpart and
 // the last one to finish (ticket counter) adds them up in a fixed order.
-__global__ void __launch_bounds__(REL_THREADS) k_rel(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
+// MINB = 2 (throughput batches): 128 registers, two CTAs per SM; MINB = 1 (latency batches): 255 registers
+template <int MINB>
+__global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
                                                      int n_om, const RelTile* __restrict__ tiles, int ntiles,
                                                      double* __restrict__ Mrel, int* __restrict__ err_flag, int nsplit,
                                                      double* __restrict__ Mpart, int* __restrict__ tickets) {
@@ -359,13 +362,13 @@ __global__ void __launch_bounds__(REL_THREADS) k_rel(const GlobalDev* __restrict
         for (int ip = 1 + lane; ip <= npb - 1; ip += 32) {
           const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
           if (w == 0.0) continue;
-          Six2 Tp, Tm;
+          Six2 T;
           cd num;
-          node_values(c, ig, ip, Tp, Tm, num);
+          node_values(c, ig, ip, sg, T, num);
           const cd den = mk(pbv[ip], 0.0) - (g1 * omc) * vA / kpar + mk(nn * qs * vA / (kpar * ms), 0.0);
           const cd U = (wg * dpb * w) * (num / den);
 #pragma unroll
-          for (int q = 0; q < 6; q++) acc.v[q] += U * (sg ? Tm.v[q] : Tp.v[q]);
+          for (int q = 0; q < 6; q++) acc.v[q] += U * T.v[q];
         }
         // principal part
         if (found && lowerlimit >= int_start && upperlimit <= int_end) {
@@ -561,8 +564,12 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
                 int* err_flag, int nsplit, double* Mpart, int* tickets, cudaStream_t st) {
   if (n_om <= 0 || ntiles <= 0) return;
   if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
-  k_rel<<<n_om * ntiles * nsplit, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, nsplit, Mpart,
-                                                          tickets);
+  if (nsplit > 1 || n_om * ntiles <= 2 * 148)
+    k_rel<1><<<n_om * ntiles * nsplit, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, nsplit,
+                                                             Mpart, tickets);
+  else
+    k_rel<2><<<n_om * ntiles * nsplit, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, nsplit,
+                                                             Mpart, tickets);
 }
 void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, int npb, double zfac, int nmaxord,
                              double* Jrel, cudaStream_t st) {
