@@ -16,7 +16,6 @@
 #include "../../include/alps_b200.h"
 #include "common.cuh"
 #include "kernels.h"
-#include "nhds.hpp"
 
 using namespace alps;
 
@@ -45,6 +44,12 @@ struct SpeciesHost {
   double ee_rel = 0.0;   // int_ee_rel, src/ALPS_fns_rel.f90:1097-1215
 };
 
+struct BmParams {   // &bM_spec_j (src/ALPS_io.f90:342-372)
+  int bMnmaxs = 500;
+  double bMBessel_zeros = 1.e-50, bMbetas = 1.0, bMalphas = 1.0, bMpdrifts = 0.0;
+  bool set = false;
+};
+
 struct State {
   bool inited = false;
   alps_b200_cfg cfg{};
@@ -68,7 +73,7 @@ struct State {
   std::vector<unsigned char> disp_sig;
   long long disp_graph_launches = 0;
   int disp_plain_calls = 0;      // plain calls since the signature last changed (the first one warms up)
-  bool capturing = false, graph_off = false;
+  bool capturing = false, graph_off = false, omega_major = false;
   double* d_respart = nullptr;   // k_resonant_lat partial rows (small batches)
   int* d_restick = nullptr;
   double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
@@ -87,9 +92,12 @@ struct State {
   bool have_lat = false;
   std::vector<double> ext;   // external chi of the next alps_b200_disp call, [nspec][PARTIAL_PER_SPEC]
   bool ext_any = false;
-  nhds::Params bm[MAXSPEC];  // &bM_spec_j of use_bM species (NHDS twin, nhds.hpp)
-  bool bm_any = false;
-  std::vector<double> ext_batch;   // per-omega external chi of a chunk, [n][nspec][PARTIAL_PER_SPEC]
+  BmParams bm[MAXSPEC];      // &bM_spec_j of use_bM species (closed-form chi on the device, nhds_kernel.cu)
+  bool bm_any = false, nh_dirty = false;
+  NhdsDev nh{};              // per-k constants of calc_chi; device copy d_nh
+  NhdsDev* d_nh = nullptr;
+  double* d_nhI[MAXSPEC] = {nullptr};   // BESSI(n, z) tables
+  int cap_nhI[MAXSPEC] = {0};
   int mode = 0;
   QuadVariant qv{8, 16, 32, 2};
   int shard_rank = 0, shard_n = 1;
@@ -281,6 +289,7 @@ int build_hoisted_tables() {
   P.om = S.d_om_i;
   P.n_om = 1;
   P.nsplit = 1;
+  P.tile_major = 0;
   P.plan = nullptr;
   P.Sbulk = nullptr;
   P.gwin = nullptr;
@@ -350,74 +359,82 @@ int auto_batch() {
   return (int)b;
 }
 
-// External (NHDS) chi of use_bM species for a chunk: closed-form host algebra per omega, summed into
-// chi exactly where disp() does it (src/ALPS_fns.f90:344-362).  h_om may be NULL (device-resident
-// omegas are copied back first).  Returns the device pointer to use, or nullptr if nothing to add.
-int prepare_external(int n, const double* d_om, const double* h_om, const double** d_ext_out) {
+// Per-k constants of the closed-form chi of use_bM species (calc_chi, src/ALPS_NHDS.f90:59-141): thermal
+// speed, gyro-frequency, z = k_perp^2 rho^2 / 2, the BESSI(n, z) table and the harmonic cut-off.  Runs after
+// set_k / set_bm_species (S.nh_dirty).
+int prepare_nhds() {
+  S.nh_dirty = false;
+  if (!S.bm_any) return 0;
+  NhdsDev& nd = S.nh;
+  nd.kperp_norm = S.gh.kperp_norm;
+  nd.kz = S.gh.kpar;
+  nd.kperp = S.gh.kperp;
+  std::vector<double> tab;
+  for (int s = 0; s < MAXSPEC; s++) {
+    NhdsSpec& q = nd.sp[s];
+    q = NhdsSpec{};
+    if (s >= S.cfg.nspec || !S.gh.sp[s].usebM || !S.bm[s].set) continue;
+    const BmParams& p = S.bm[s];
+    const double ns = S.gh.sp[s].ns, qs = S.gh.sp[s].qs, ms = S.gh.sp[s].ms;
+    q.active = 1;
+    q.cold = p.bMbetas == 0.0;
+    q.Omega = qs / ms;
+    q.vtherm = sqrt(p.bMbetas / (ns * ms));
+    q.vdrift = p.bMpdrifts / ms;
+    q.al = p.bMalphas;
+    const double ell = sqrt(ms / (ns * qs * qs));
+    q.l2 = ell * ell;
+    q.z = 0.5 * (nd.kperp * q.vtherm / q.Omega) * (nd.kperp * q.vtherm / q.Omega) * q.al;
+    q.zp = 0.5 * (q.vtherm / q.Omega) * (q.vtherm / q.Omega) * q.al;
+    if (q.cold) {
+      if (!nd.kperp_norm)
+        return fail(ALPS_B200_ERR_UNSUPPORTED, "cold-plasma species need kperp_norm=.true. (ALPS_NHDS.f90:461)");
+      continue;
+    }
+    const int count = std::max(p.bMnmaxs, 0) + 2;
+    if (count > S.cap_nhI[s]) {
+      if (dalloc(&S.d_nhI[s], count)) return ALPS_B200_ERR_CUDA;
+      S.cap_nhI[s] = count;
+    }
+    launch_nhds_bessel(q.z, count, S.d_nhI[s], S.stream);
+    S.launches += 1;
+    tab.resize(count);
+    CK(cudaMemcpyAsync(tab.data(), S.d_nhI[s], count * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    // nmaxrun: first n with n >= bMnmaxs or I_n(z) < bMBessel_zeros (:129-141)
+    int n = 0;
+    while (!(n >= p.bMnmaxs || tab[n] < p.bMBessel_zeros)) n++;
+    q.nmaxrun = n;
+    q.I = S.d_nhI[s];
+  }
+  if (!S.d_nh && dalloc(&S.d_nh, 1)) return ALPS_B200_ERR_CUDA;
+  CK(cudaMemcpyAsync(S.d_nh, &S.nh, sizeof(NhdsDev), cudaMemcpyHostToDevice, S.stream));
+  CK(cudaStreamSynchronize(S.stream));
+  return 0;
+}
+
+// External chi of a chunk: the closed-form chi of use_bM species (k_nhds, one warp per (omega, species)), summed
+// into chi exactly where disp() does it (src/ALPS_fns.f90:344-362), plus the caller-supplied chi of
+// alps_b200_add_external_chi for the first omega.  Returns the device rows k_assemble adds, or nullptr.
+int prepare_external(int n, const double* d_om, const double** d_ext_out) {
   *d_ext_out = nullptr;
   if (!S.bm_any && !S.ext_any) return 0;
-  const int nspec = S.cfg.nspec;
-  const size_t per = (size_t)nspec * PARTIAL_PER_SPEC;
-  S.ext_batch.assign((size_t)n * per, 0.0);
-  std::vector<double> om_copy;
-  if (S.bm_any) {
-    if (!h_om) {
-      om_copy.resize(2 * (size_t)n);
-      CK(cudaMemcpyAsync(om_copy.data(), d_om, om_copy.size() * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
-      CK(cudaStreamSynchronize(S.stream));
-      h_om = om_copy.data();
-    }
-    static const int MI[6] = {0, 1, 2, 0, 0, 1}, MJ[6] = {0, 1, 2, 1, 2, 2};
-    for (int s = 0; s < nspec; s++) {
-      if (!S.gh.sp[s].usebM || !S.bm[s].set) continue;
-      // independent per omega: large batches (maps) are spread over the host cores, like the reference
-      // spreads its ranks; a single omega stays on the calling thread
-      std::atomic<int> bad{0};
-      auto body = [&](int i0, int i1) {
-        for (int i = i0; i < i1; i++) {
-          nhds::cplx chi[9], low[27];
-          int rc = nhds::calc_chi(chi, low, S.bm[s], S.gh.kpar, S.gh.kperp, nhds::cplx(h_om[2 * i], h_om[2 * i + 1]),
-                                  S.gh.kperp_norm != 0);
-          if (rc) {
-            bad = 1;
-            return;
-          }
-          double* o = S.ext_batch.data() + (size_t)i * per + (size_t)s * PARTIAL_PER_SPEC;
-          for (int c = 0; c < 6; c++) {
-            const nhds::cplx v = chi[MI[c] + 3 * MJ[c]];
-            o[2 * c] = v.real();
-            o[2 * c + 1] = v.imag();
-            for (int m = 0; m < 3; m++) {
-              const nhds::cplx vl = low[MI[c] + 3 * MJ[c] + 9 * m];
-              o[2 * (6 + 3 * c + m)] = vl.real();
-              o[2 * (6 + 3 * c + m) + 1] = vl.imag();
-            }
-          }
-        }
-      };
-      const int hw = (int)std::thread::hardware_concurrency();
-      const int nthr = (n >= 512 && hw > 1) ? std::min(hw, n / 128) : 1;
-      if (nthr <= 1) {
-        body(0, n);
-      } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nthr; t++)
-          pool.emplace_back(body, (int)((long long)n * t / nthr), (int)((long long)n * (t + 1) / nthr));
-        for (auto& th : pool) th.join();
-      }
-      if (bad) return fail(ALPS_B200_ERR_UNSUPPORTED, "cold-plasma species need kperp_norm=.true. (ALPS_NHDS.f90:461)");
-    }
+  const size_t per = (size_t)S.cfg.nspec * PARTIAL_PER_SPEC;
+  if (S.ext_any) {
+    CK(cudaMemsetAsync(S.d_ext, 0, (size_t)n * per * sizeof(double), S.stream));
+    CK(cudaMemcpyAsync(S.d_ext, S.ext.data(), per * sizeof(double), cudaMemcpyHostToDevice, S.stream));
   }
-  if (S.ext_any)   // caller-supplied chi (alps_b200_add_external_chi) applies to the first omega
-    for (size_t q = 0; q < per; q++) S.ext_batch[q] += S.ext[q];
-  CK(cudaMemcpyAsync(S.d_ext, S.ext_batch.data(), S.ext_batch.size() * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+  if (S.bm_any) {
+    launch_nhds(S.d_nh, d_om, n, S.cfg.nspec, S.ext_any ? 1 : 0, S.d_ext, S.stream);
+    S.launches += 1;
+  }
   *d_ext_out = S.d_ext;
   return 0;
 }
 
 // run the hot path for n omegas already on the device (n <= S.batch)
 int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, const double* d_partial_in,
-              bool want_aux, const double* h_om = nullptr) {
+              bool want_aux) {
   const GlobalDev* gd = S.gd;
   if (!d_partial_in) {
     launch_plan(gd, S.gh, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream);
@@ -428,6 +445,9 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     // (n <= LAT_BATCH: narrow-tile latency variant; n <= SMALL_BATCH), so a single disp() and a
     // disp_batch() of up to LAT_BATCH omegas (batched roots) give bitwise identical D.
     S.P.nsplit = (S.mode == 1 || n > SMALL_BATCH) ? 1 : nsplit_small(n);
+    // throughput batches: the CTAs of one (species, harmonic group) tile are adjacent, so the SMs walk the same
+    // species table and weight block together (working set in L2: one species instead of all of them)
+    S.P.tile_major = (n > SMALL_BATCH && !S.omega_major) ? 1 : 0;
     if (use_lat(n)) {
       S.Plat.om = d_om;
       S.Plat.n_om = n;
@@ -464,7 +484,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
   }
   const double* d_ext = nullptr;
   {
-    int rc = prepare_external(n, d_om, h_om, &d_ext);
+    int rc = prepare_external(n, d_om, &d_ext);
     if (rc) return rc;
   }
   launch_assemble(gd, S.gh, d_om, n, d_partial_in, d_ext, d_D,
@@ -478,6 +498,7 @@ int check_ready() {
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (!S.have_tables) return fail(ALPS_B200_ERR_USAGE, "no f0 tables: call alps_b200_upload (+ derivative_f0) first");
   if (!S.have_k) return fail(ALPS_B200_ERR_USAGE, "alps_b200_set_k has not been called");
+  if (S.nh_dirty) return prepare_nhds();
   return 0;
 }
 
@@ -536,14 +557,16 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.gh.vA = cfg->vA;
   S.gh.Tlim = cfg->Tlim;
   if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8)) return ALPS_B200_ERR_CUDA;
-  for (int s = 0; s < MAXSPEC; s++) S.bm[s] = nhds::Params();
+  for (int s = 0; s < MAXSPEC; s++) S.bm[s] = BmParams();
   S.bm_any = false;
+  S.nh_dirty = false;
   CK(cudaMemset(S.d_err, 0, 8 * sizeof(int)));
   S.ext.assign((size_t)cfg->nspec * PARTIAL_PER_SPEC, 0.0);
   S.ext_any = false;
   S.mode = 0;
   {
     S.graph_off = getenv("ALPS_B200_NO_GRAPH") != nullptr;   // plain launches for alps_b200_disp
+    S.omega_major = getenv("ALPS_B200_OMEGA_MAJOR") != nullptr;   // A/B knob: previous block order of k_quad_mma
     const char* v = getenv("ALPS_B200_QUAD_VARIANT");   // tuning knob: tile shape of k_quad
     S.qv = quad_variant(v ? atoi(v) : 15);
   }
@@ -578,6 +601,11 @@ void alps_b200_finalize(void) {
   dfree(&S.d_rtiles);
   dfree(&S.d_fitems);
   dfree(&S.d_om_i);
+  dfree(&S.d_nh);
+  for (int s = 0; s < MAXSPEC; s++) {
+    dfree(&S.d_nhI[s]);
+    S.cap_nhI[s] = 0;
+  }
   if (S.h_pin) cudaFreeHost(S.h_pin);
   S.h_pin = nullptr;
   S.h_pin_bytes = 0;
@@ -981,6 +1009,7 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
     }
   }
   S.have_k = true;
+  S.nh_dirty = S.bm_any;
   if (S.mode == 1) {
     int rc = build_hoisted_tables();
     if (rc) {
@@ -1054,7 +1083,7 @@ int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
     int m = std::min(S.batch, n - o);
     memcpy(h_om, om + 2 * (size_t)o, (size_t)m * 2 * sizeof(double));
     CK(cudaMemcpyAsync(S.d_om, h_om, (size_t)m * 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
-    if ((rc = run_chunk(m, S.d_om, S.d_D, nullptr, nullptr, chi0_opt != nullptr, h_om))) return rc;
+    if ((rc = run_chunk(m, S.d_om, S.d_D, nullptr, nullptr, chi0_opt != nullptr))) return rc;
     CK(cudaMemcpyAsync(h_D, S.d_D, (size_t)m * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
     if (chi0_opt)
       CK(cudaMemcpyAsync(chi0_opt + (size_t)o * nspec * 18, S.d_chi0, (size_t)m * nspec * 18 * sizeof(double),
@@ -1077,9 +1106,9 @@ static void disp_signature(std::vector<unsigned char>& sig) {
   P.nsplit = (S.mode == 1) ? 1 : nsplit_small(1);
   const void* ptrs[] = {S.stream, S.gd, S.d_om, S.d_D, S.d_plan, S.d_work, S.d_work_count, S.d_Sbulk, S.d_Sres,
                         S.d_gwin, S.d_partial, S.d_err, S.d_rtiles, S.d_fitems, S.d_respart, S.d_restick,
-                        S.d_relpart, S.d_reltick, S.h_pin};
+                        S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
   const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)S.rtiles.size(), (long long)S.fitems.size(), S.mode,
-                            S.qv.id, nsplit_rel()};
+                            S.qv.id, nsplit_rel(), (long long)S.bm_any};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
   memcpy(sig.data(), &P, sizeof(P));
   memcpy(sig.data() + sizeof(P), ptrs, sizeof(ptrs));
@@ -1107,7 +1136,7 @@ static int disp_via_graph(int* used) {
     S.capturing = true;
     const long long l0 = S.launches;
     cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream);
-    const int rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, false, S.h_pin);
+    const int rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, false);
     cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream);
     cudaMemcpyAsync(S.h_pin + 8, S.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream);
     S.capturing = false;
@@ -1142,7 +1171,7 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   if ((rc = ensure_pinned(64 * sizeof(double)))) return rc;
   S.h_pin[0] = om[0];
   S.h_pin[1] = om[1];
-  if (!chi0 && !chi0_low && !wave && !S.bm_any && !S.ext_any && !S.graph_off && S.stream != nullptr) {
+  if (!chi0 && !chi0_low && !wave && !S.ext_any && !S.graph_off && S.stream != nullptr) {
     int used = 0;
     if ((rc = disp_via_graph(&used))) return rc;
     if (used) {
@@ -1155,7 +1184,7 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   }
   CK(cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
   const bool aux = chi0 || chi0_low || wave;
-  if ((rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, aux, om))) return rc;
+  if ((rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, aux))) return rc;
   CK(cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if (chi0) CK(cudaMemcpyAsync(chi0, S.d_chi0, (size_t)nspec * 18 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if (chi0_low)
@@ -1198,26 +1227,91 @@ int alps_b200_set_bm_species(int is, int bM_nmaxs, double bM_Bessel_zeros, doubl
                              double bM_pdrifts) {
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (is < 1 || is > S.cfg.nspec || !S.sp[is - 1].set) return fail(ALPS_B200_ERR_USAGE, "species %d not set", is);
-  nhds::Params& p = S.bm[is - 1];
+  BmParams& p = S.bm[is - 1];
   p.bMnmaxs = bM_nmaxs; p.bMBessel_zeros = bM_Bessel_zeros; p.bMbetas = bM_betas; p.bMalphas = bM_alphas;
   p.bMpdrifts = bM_pdrifts;
-  p.ns = S.gh.sp[is - 1].ns; p.qs = S.gh.sp[is - 1].qs; p.ms = S.gh.sp[is - 1].ms;
   p.set = true;
   S.bm_any = S.bm_any || S.gh.sp[is - 1].usebM;
+  S.nh_dirty = S.bm_any;
   return 0;
 }
 
+// calc_chi for one use_bM species and one omega, stateless: the same two kernels the hot path runs
+// (k_nhds_bessel, k_nhds) on the current device.  Needs a GPU like every other entry point.
 int alps_b200_nhds_calc_chi(double ns, double qs, double ms, int bM_nmaxs, double bM_Bessel_zeros, double bM_betas,
                             double bM_alphas, double bM_pdrifts, double kz, double kperp, const double x[2],
                             int kperp_norm, double* chi, double* chi_low) {
-  nhds::Params p;
-  p.ns = ns; p.qs = qs; p.ms = ms; p.bMnmaxs = bM_nmaxs; p.bMBessel_zeros = bM_Bessel_zeros; p.bMbetas = bM_betas;
-  p.bMalphas = bM_alphas; p.bMpdrifts = bM_pdrifts; p.set = true;
-  nhds::cplx c[9], l[27];
-  if (nhds::calc_chi(c, l, p, kz, kperp, nhds::cplx(x[0], x[1]), kperp_norm != 0))
-    return fail(ALPS_B200_ERR_UNSUPPORTED, "cold-plasma species need kperp_norm=.true.");
-  for (int i = 0; i < 9 && chi; i++) { chi[2 * i] = c[i].real(); chi[2 * i + 1] = c[i].imag(); }
-  for (int i = 0; i < 27 && chi_low; i++) { chi_low[2 * i] = l[i].real(); chi_low[2 * i + 1] = l[i].imag(); }
+  if (!x) return fail(ALPS_B200_ERR_USAGE, "x is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(ALPS_B200_ERR_CUDA, "no CUDA device available; alps_b200 has no CPU fallback");
+  }
+  NhdsDev nd{};
+  nd.kperp_norm = kperp_norm;
+  nd.kz = kz;
+  nd.kperp = kperp;
+  NhdsSpec& q = nd.sp[0];
+  q.active = 1;
+  q.cold = bM_betas == 0.0;
+  q.Omega = qs / ms;
+  q.vtherm = sqrt(bM_betas / (ns * ms));
+  q.vdrift = bM_pdrifts / ms;
+  q.al = bM_alphas;
+  const double ell = sqrt(ms / (ns * qs * qs));
+  q.l2 = ell * ell;
+  q.z = 0.5 * (kperp * q.vtherm / q.Omega) * (kperp * q.vtherm / q.Omega) * q.al;
+  q.zp = 0.5 * (q.vtherm / q.Omega) * (q.vtherm / q.Omega) * q.al;
+  if (q.cold && !kperp_norm) return fail(ALPS_B200_ERR_UNSUPPORTED, "cold-plasma species need kperp_norm=.true.");
+  const int count = std::max(bM_nmaxs, 0) + 2;
+  double *d_I = nullptr, *d_x = nullptr, *d_o = nullptr;
+  NhdsDev* d_nd = nullptr;
+  std::vector<double> tab(count), out(PARTIAL_PER_SPEC);
+  auto cleanup = [&]() { cudaFree(d_I); cudaFree(d_x); cudaFree(d_o); cudaFree(d_nd); };
+  cudaError_t e = cudaMalloc((void**)&d_I, count * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_x, 2 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, PARTIAL_PER_SPEC * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_nd, sizeof(NhdsDev));
+  if (e == cudaSuccess && !q.cold) {
+    launch_nhds_bessel(q.z, count, d_I, nullptr);
+    e = cudaMemcpy(tab.data(), d_I, count * sizeof(double), cudaMemcpyDeviceToHost);
+    int n = 0;
+    while (e == cudaSuccess && !(n >= bM_nmaxs || tab[n] < bM_Bessel_zeros)) n++;
+    q.nmaxrun = n;
+    q.I = d_I;
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(d_nd, &nd, sizeof(NhdsDev), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_x, x, 2 * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    launch_nhds(d_nd, d_x, 1, 1, 0, d_o, nullptr);
+    e = cudaMemcpy(out.data(), d_o, PARTIAL_PER_SPEC * sizeof(double), cudaMemcpyDeviceToHost);
+  }
+  cleanup();
+  if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "nhds_calc_chi failed: %s", cudaGetErrorString(e));
+  // partial rows -> chi(3,3), chi_low(3,3,-1:1) column-major with the symmetries of calc_chi
+  // (chi(2,1) = -chi(1,2), chi(3,1) = chi(1,3), chi(3,2) = -chi(2,3))
+  static const int MI[6] = {0, 1, 2, 0, 0, 1}, MJ[6] = {0, 1, 2, 1, 2, 2};
+  static const double SYM[6] = {0.0, 0.0, 0.0, -1.0, 1.0, -1.0};
+  for (int c = 0; c < 6; c++) {
+    const int k = MI[c] + 3 * MJ[c], kt = MJ[c] + 3 * MI[c];
+    if (chi) {
+      chi[2 * k] = out[2 * c];
+      chi[2 * k + 1] = out[2 * c + 1];
+      if (SYM[c] != 0.0) {
+        chi[2 * kt] = SYM[c] * out[2 * c];
+        chi[2 * kt + 1] = SYM[c] * out[2 * c + 1];
+      }
+    }
+    for (int m = 0; m < 3 && chi_low; m++) {
+      const double re = out[2 * (6 + 3 * c + m)], im = out[2 * (6 + 3 * c + m) + 1];
+      chi_low[2 * (k + 9 * m)] = re;
+      chi_low[2 * (k + 9 * m) + 1] = im;
+      if (SYM[c] != 0.0) {
+        chi_low[2 * (kt + 9 * m)] = SYM[c] * re;
+        chi_low[2 * (kt + 9 * m) + 1] = SYM[c] * im;
+      }
+    }
+  }
   return 0;
 }
 

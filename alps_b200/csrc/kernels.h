@@ -32,6 +32,8 @@ struct QuadParams {
   const double* Cf[MAXSPEC];
   const double* Wf[MAXSPEC];
   int nks;
+  int tile_major;          // block order: 1 = all omegas of a tile are adjacent (concurrent CTAs share the species tables
+                           // and W in L2), 0 = all tiles of an omega are adjacent
 };
 constexpr int MMA_NH = 16;   // harmonics per CTA tile of the DMMA variants
 
@@ -92,6 +94,22 @@ void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, in
                              double* Jrel, cudaStream_t st);
 void launch_int_ee_rel(const double* pbv, const double* dfp, const int* lo, const int* up, int ng, int npb, double qs,
                        double ms, double vA, double dgam, double dpb, double* out, cudaStream_t st);
+// use_bM species on the device (nhds_kernel.cu): per-k constants of calc_chi, src/ALPS_NHDS.f90:59-242
+struct NhdsSpec {
+  int active;        // use_bM species with &bM_spec parameters
+  int cold;          // bMbetas == 0: calc_chi_cold
+  int nmaxrun;       // harmonic cut-off of the current k (bMnmaxs / bMBessel_zeros rule, :129-141)
+  int pad;
+  double Omega, vtherm, vdrift, al, z, zp, l2;
+  const double* I;   // BESSI(n, z), n = 0 .. nmaxrun + 1
+};
+struct NhdsDev {
+  int kperp_norm, pad;
+  double kz, kperp;
+  NhdsSpec sp[MAXSPEC];
+};
+void launch_nhds_bessel(double z, int count, double* I, cudaStream_t st);
+void launch_nhds(const NhdsDev* nd, const double* om, int n_om, int nspec, int accumulate, double* ext, cudaStream_t st);
 double run_dfma_peak(cudaStream_t st);
 double run_dfma_peak_noreuse(cudaStream_t st);
 

@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
 
   const int nsplit = P.nsplit;
   const int jsplit = blockIdx.x % nsplit;
-  const int tile_id = (blockIdx.x / nsplit) % P.ntiles;
-  const int iom = blockIdx.x / (nsplit * P.ntiles);
+  const int bq = blockIdx.x / nsplit;
+  const int tile_id = P.tile_major ? bq / P.n_om : bq % P.ntiles;
+  const int iom = P.tile_major ? bq % P.n_om : bq / P.ntiles;
   const QuadTile tile = P.tiles[tile_id];
   const GlobalDev& g = *P.g;
   const SpeciesDev& sp = g.sp[tile.s];

@@ -10,8 +10,8 @@ reference's formats.  Every D(omega,k) comes from the GPU (libalps_b200.so).
 Analytic-continuation parameters: with --fit the twin of determine_param_fit (alps_b200/fits.py:
 Levenberg-Marquardt rows started from the &ffit blocks, Chebyshev series for ac_method = 2) runs like in
 the reference; without it they are the generator's ideal values when the tables are regenerated, else
-the initial values of the &ffit blocks.  NHDS calc_chi for use_bM species is the host twin in
-csrc/nhds.hpp."""
+the initial values of the &ffit blocks.  NHDS calc_chi for use_bM species runs on the device
+(csrc/nhds_kernel.cu)."""
 from __future__ import annotations
 
 import argparse

@@ -285,8 +285,8 @@ class Solver:
 
 
 def nhds_calc_chi(species, om: complex, kperp: float, kpar: float, kperp_norm: bool = True):
-    """calc_chi of ALPS_NHDS.f90 for a use_bM species (stateless host closed form, no GPU):
-    returns chi(3,3), chi_low(3,3,-1:1)."""
+    """calc_chi of ALPS_NHDS.f90 for a use_bM species and one omega, evaluated by the device kernels the hot
+    path uses (k_nhds_bessel + k_nhds; stateless, needs a GPU): returns chi(3,3), chi_low(3,3,-1:1)."""
     L = _lib.lib()
     x = np.array([om.real, om.imag])
     chi = np.zeros(9, dtype=np.complex128)

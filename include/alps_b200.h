@@ -108,10 +108,12 @@ int alps_b200_add_external_chi(int is, const double *chi, const double *chi_low)
 
 /* replaces: calc_chi of module alps_nhds (src/ALPS_NHDS.f90:59-464) for use_bM species: with the
  * &bM_spec_j parameters set, every disp call computes the closed-form bi-Maxwellian / cold chi on the
- * host (O(nmax) algebra, not a table quadrature) and sums it in like src/ALPS_fns.f90:344-362. */
+ * device (k_nhds: one warp per (omega, species), O(nmax) terms; the BESSI(n,z) table and the harmonic
+ * cut-off are rebuilt by alps_b200_set_k) and sums it in like src/ALPS_fns.f90:344-362. */
 int alps_b200_set_bm_species(int is, int bM_nmaxs, double bM_Bessel_zeros, double bM_betas,
                              double bM_alphas, double bM_pdrifts);
-/* the same closed form as a stateless host function (no GPU needed): chi(3,3), chi_low(3,3,-1:1) */
+/* the same device kernels for one species and one omega, stateless (needs a GPU like every entry point):
+ * chi(3,3), chi_low(3,3,-1:1), column-major complex */
 int alps_b200_nhds_calc_chi(double ns, double qs, double ms, int bM_nmaxs, double bM_Bessel_zeros,
                             double bM_betas, double bM_alphas, double bM_pdrifts, double kz, double kperp,
                             const double x[2], int kperp_norm, double *chi, double *chi_low);

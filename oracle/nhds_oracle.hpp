@@ -1,10 +1,12 @@
-// alps_b200: closed-form susceptibility of bi-Maxwellian / cold species (host code, O(nmax) per
-// omega) -- twin of the reference's NHDS module for species flagged use_bM:
+// TEST INFRASTRUCTURE ONLY (oracle): CPU restatement of the reference's NHDS module for species flagged
+// use_bM -- closed-form susceptibility of bi-Maxwellian / cold species, O(nmax) per omega:
 //   calc_chi      src/ALPS_NHDS.f90:59-242      calc_ypsilon  :250-375     calc_chi_cold :379-464
 //   dispfunct     :492-533                      WOFZ          :536-745 (ACM Algorithm 680)
 //   BESSI/BESSI0/BESSI1  :750-865 (exp(-x)-scaled modified Bessel functions)
-// Not a table quadrature, so it never goes to the GPU; its result is summed into chi exactly where
-// disp() does it (src/ALPS_fns.f90:344-362).
+// The product computes the same thing on the device (alps_b200/csrc/nhds_kernel.cu); this file is the
+// checker: tests/test_nhds.py pins it against scipy's Faddeeva / Bessel functions, the GPU parity tests
+// compare k_nhds with it.  Parity status: the reference ships no NHDS golden vector -> unpinned by the
+// reference itself, cross-checked only (scipy, 2e-6: BESSI is the 1e-7 Numerical-Recipes polynomial).
 #pragma once
 #include <cmath>
 #include <complex>

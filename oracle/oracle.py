@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY: ctypes wrapper of the CPU oracle (oracle/alps_oracle.c).
+"""TEST INFRASTRUCTURE ONLY: ctypes wrapper of the CPU oracle (oracle/alps_oracle.c, and
+oracle/nhds_oracle.cpp for use_bM species).
 
 May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs -- never by the product package alps_b200/.
@@ -14,6 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_NHDS = None
 
 
 class OracleCfg(C.Structure):
@@ -106,6 +108,7 @@ class Oracle:
         if rc:
             raise RuntimeError("oracle_set_k failed")
         self.nmax = nmax
+        self.kperp, self.kpar = kperp, kpar
         return nmax
 
     def set_external_chi(self, is_: int, chi, chi_low):
@@ -116,8 +119,15 @@ class Oracle:
     def set_ncap(self, ncap: int):
         self.L.oracle_set_ncap(ncap)
 
-    def disp(self, om: complex, full: bool = False):
+    def disp(self, om: complex, full: bool = False, nhds: bool = True):
+        """disp(om) of the reference; use_bM species get their chi from the NHDS restatement
+        (src/ALPS_fns.f90:344-362) unless nhds=False (the caller then feeds set_external_chi itself)."""
         n = self.pl.nspec
+        if nhds:
+            for i, s in enumerate(self.pl.species):
+                if s.usebM:
+                    chi, low = nhds_calc_chi(s, om, self.kperp, self.kpar, bool(self.pl.kperp_norm))
+                    self.set_external_chi(i + 1, chi, low)
         omv = np.array([om.real, om.imag])
         D = np.zeros(2)
         if not full:
@@ -165,3 +175,28 @@ class Oracle:
 
 def bessj(n: int, x: float) -> float:
     return lib().oracle_bessj(n, x)
+
+
+def nhds_calc_chi(species, om: complex, kperp: float, kpar: float, kperp_norm: bool = True):
+    """calc_chi of src/ALPS_NHDS.f90:59-242 for a use_bM species, CPU restatement (oracle/nhds_oracle.hpp):
+    returns chi(3,3), chi_low(3,3,-1:1)."""
+    global _NHDS
+    if _NHDS is None:
+        build()
+        so = os.path.join(_HERE, "libnhds_oracle.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", _HERE, "-s"])
+        _NHDS = C.CDLL(so)
+        _NHDS.oracle_nhds_calc_chi.argtypes = ([C.c_double] * 3 + [C.c_int] + [C.c_double] * 6
+                                               + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p])
+    om = complex(om)
+    x = np.array([om.real, om.imag])
+    chi = np.zeros(9, dtype=np.complex128)
+    low = np.zeros(27, dtype=np.complex128)
+    s = species
+    rc = _NHDS.oracle_nhds_calc_chi(s.ns, s.qs, s.ms, s.bM_nmaxs, s.bM_Bessel_zeros, s.bM_betas, s.bM_alphas,
+                                    s.bM_pdrifts, kpar, kperp, _p(x), int(kperp_norm),
+                                    _p(chi.view(np.float64)), _p(low.view(np.float64)))
+    if rc:
+        raise RuntimeError("oracle_nhds_calc_chi: cold-plasma species need kperp_norm=.true.")
+    return chi.reshape((3, 3), order="F"), low.reshape((3, 3, 3), order="F")

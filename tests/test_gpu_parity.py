@@ -166,31 +166,36 @@ def test_relativistic_config_c3():
 
 
 def test_bimax_config_nhds_species():
-    """C2 (tests/test_bimax.in): species 1 use_bM=T -- its chi is the closed-form NHDS calc_chi, computed on
-    the host inside alps_b200_disp; species 2 is integrated from the table.  The oracle is fed the same
-    closed form (tests/test_nhds.py checks that twin against scipy)."""
-    from alps_b200.solver import Solver, nhds_calc_chi
+    """C2 (tests/test_bimax.in): species 1 use_bM=T -- its chi is the closed-form NHDS calc_chi, computed by
+    k_nhds on the device inside alps_b200_disp*; species 2 is integrated from the table.  The oracle uses its own
+    CPU restatement of calc_chi (oracle/nhds_oracle.hpp, pinned against scipy by tests/test_nhds.py)."""
+    from alps_b200.solver import Solver
     from oracle.oracle import Oracle
     pl = tables.config_bimax(60, 120)
     kperp, kpar = 1.0e-3, 0.03
     orc = Oracle(pl)
     sol = Solver(pl)
     try:
-        assert list(orc.set_k(kperp, kpar)) == list(sol.set_k(kperp, kpar))
-        oms = np.array([3.0e-2 - 1.0e-5j, 4.5e-2 - 1.9e-2j, 0.1 + 0.002j, 0.05 + 0.0j])
-        Db = sol.disp_batch(oms)
-        for i, om in enumerate(oms):
-            chi, low = nhds_calc_chi(pl.species[0], complex(om), kperp, kpar)
-            orc.set_external_chi(1, chi, low)
-            Do, chi_o, low_o, wave_o = orc.disp(complex(om), full=True)
-            Dg, chi_g, low_g, wave_g = sol.disp(complex(om), full=True)
-            ws = wave_scale(chi_o, complex(om), pl.vA, kperp, kpar)
-            assert scaled_err(wave_g, wave_o, ws) < TOL
-            assert abs(Dg - Do) / det_scale(ws) < TOL
-            assert abs(Db[i] - Dg) <= 1e-13 * det_scale(ws)
-            for s in range(2):
-                assert chi_err(chi_g[s], chi_o[s]) < TOL
-                assert chi_err(low_g[s, :, :, 1], low_o[s, :, :, 1]) < TOL
+        for kperp, kpar in ((1.0e-3, 0.03), (0.8, 0.05)):
+            assert list(orc.set_k(kperp, kpar)) == list(sol.set_k(kperp, kpar))
+            oms = np.array([3.0e-2 - 1.0e-5j, 4.5e-2 - 1.9e-2j, 0.1 + 0.002j, 0.05 + 0.0j])
+            Db = sol.disp_batch(oms)
+            Dbig = sol.disp_batch(np.tile(oms, 40))      # throughput batch class
+            for i, om in enumerate(oms):
+                Do, chi_o, low_o, wave_o = orc.disp(complex(om), full=True)
+                Dg, chi_g, low_g, wave_g = sol.disp(complex(om), full=True)
+                ws = wave_scale(chi_o, complex(om), pl.vA, kperp, kpar)
+                assert scaled_err(wave_g, wave_o, ws) < TOL
+                assert abs(Dg - Do) / det_scale(ws) < TOL
+                assert abs(Db[i] - Dg) <= 1e-13 * det_scale(ws)
+                assert abs(Dbig[i] - Dg) <= 1e-11 * det_scale(ws) and abs(Dbig[i + 4 * 39] - Dbig[i]) == 0.0
+                # the CUDA-graph replay of the single-omega chain (second and later plain calls) includes k_nhds
+                for _ in range(3):
+                    assert abs(sol.disp(complex(om)) - Dg) <= 1e-13 * det_scale(ws)
+                for s in range(2):
+                    assert chi_err(chi_g[s], chi_o[s]) < TOL
+                    for m in range(3):
+                        assert chi_err(low_g[s, :, :, m], low_o[s, :, :, m]) < TOL
     finally:
         sol.close()
 
