@@ -920,7 +920,7 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
       if (kperp_changed) {
         // Bessel factors of int_T_rel on the (Gamma, pbar_par) grid, orders 0..nhi+1; skipped (k_rel then
         // evaluates BESSJ per point) if the table would exceed 8 GB
-        const size_t nJr = (size_t)(d.nhi + 2) * (S.cfg.ngamma + 1) * (S.cfg.npparbar + 1);
+        const size_t nJr = (size_t)(d.nhi + 3) * (S.cfg.ngamma + 1) * (S.cfg.npparbar + 1);   // + the pperpbar plane
         d.Jrel = nullptr;
         if (nJr * sizeof(double) <= ((size_t)8 << 30) && !getenv("ALPS_B200_REL_NOTABLE")) {
           if (nJr > h.cap_Jrel) {

@@ -9,6 +9,8 @@
 //                 landau_integrate_rel, int_T_res_rel, CBESSJ, Gamma, Fact   :1005-1092, 1374-1574
 // The Bessel factors of int_T_rel depend on both grid indices, so J_{n-1}, J_n, J_{n+1} are
 // evaluated (literal BESSJ) once per grid point and shared by the two signs' six components.
+#include <stdlib.h>
+
 #include "bessel.cuh"
 #include "kernels.h"
 
@@ -202,6 +204,42 @@ __device__ REL_NOINLINE void funct_g_rel6(const RelCtx& c, int sg, double p, int
   for (int q = 0; q < 6; q++) out.v[q] = g0[q] + (0.5 * ((gp[q] - gm[q]) / dpb)) * x;
 }
 
+// funct_g_rel for the principal-value window: the node values G(ig, node) = num T of the 2 M_I + 7 nodes
+// around the resonance are evaluated once per (row, sign) into shared memory (win[node - W0][6]); every
+// quadrature point then only selects its node (the same search and cone rules as funct_g_rel6) and
+// interpolates.  Falls back to funct_g_rel6 if a node outside the window is asked for.
+constexpr int REL_WIN = 32;
+__device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, int ig, const cd (*win)[6], int W0,
+                                            int nwin, double inv_dpb, Six2& out) {
+  const SpeciesDev& sp = *c.sp;
+  const int npb = c.g->npparbar, ldr = npb + 1;
+  const double* pbv = sp.pbrel;
+  const double* f0r = sp.f0_rel + (size_t)ig * ldr;
+  const double dpb = sp.dpparbar;
+  int ic = -2;
+  {
+    int i0 = (int)floor((p - pbv[0]) * inv_dpb);
+    for (int q = min(i0 + 2, npb - 1); q >= max(i0 - 2, 0); q--)
+      if (pbv[q + 1] > p && pbv[q] <= p) {
+        ic = q;
+        break;
+      }
+  }
+  if (ic + 1 >= 0 && ic + 1 <= npb && f0r[ic + 1] <= -1.0) ic = ic - 1;
+  if (ic - 1 >= 0 && ic - 1 <= npb && f0r[ic - 1] <= -1.0) ic = ic + 1;
+  if (p == pbv[npb]) ic = npb - 2;
+  if (ic >= npb - 1) ic = npb - 2;
+  if (ic <= 1) ic = 2;
+  const int k = ic - W0;
+  if (k < 1 || k + 1 >= nwin) {
+    funct_g_rel6(c, sg, p, ig, out);
+    return;
+  }
+  const double x = p - pbv[ic];
+#pragma unroll
+  for (int q = 0; q < 6; q++) out.v[q] = win[k][q] + (0.5 * ((win[k + 1][q] - win[k - 1][q]) / dpb)) * x;
+}
+
 __device__ __forceinline__ cd warp_sum_cd(cd v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -235,6 +273,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
   const double qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar, kperp = g.kperp;
   __shared__ int s_found[2];
   __shared__ cd s_red[REL_THREADS / 32][6];
+  __shared__ cd s_win[REL_THREADS / 32][REL_WIN][6];   // node values of the principal-value window, per warp
   if (tid < 2) s_found[tid] = 0;
   __syncthreads();
 
@@ -303,6 +342,8 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
       const double dpb = sp.dpparbar, dgam = sp.dgamma;
       const double* pbv = sp.pbrel;
       const int ldr = npb + 1;
+      Six2 Sd;   // Bessel moments of the direct part (tabulated Bessel factors)
+      zero6(Sd);
       for (int ig = 1 + warp + nwarps * js; ig <= ng - 1; ig += nwarps * nsplit) {
         const double wg = (ig == ng - 1) ? 1.0 : 2.0;
         const double g1 = sp.grel[ig];
@@ -359,16 +400,62 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           upperlimit = npb;
         }
         // direct part
-        for (int ip = 1 + lane; ip <= npb - 1; ip += 32) {
-          const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
-          if (w == 0.0) continue;
-          Six2 T;
-          cd num;
-          node_values(c, ig, ip, sg, T, num);
-          const cd den = mk(pbv[ip], 0.0) - (g1 * omc) * vA / kpar + mk(nn * qs * vA / (kpar * ms), 0.0);
-          const cd U = (wg * dpb * w) * (num / den);
+        if (sp.Jrel) {
+          // hot loop: the six T components are real multiples of six Bessel moments (like the table species'
+          // p_par moments), so the loop accumulates sum U {J^2, J^2 p, J^2 p^2, J J' pp, J J' pp p, J'^2 pp^2}
+          // with one reciprocal per node; Bessel factors and pperpbar come from the per-k tables
+          const size_t plane = (size_t)(ng + 1) * ldr;
+          const double* __restrict__ J0 = sp.Jrel + (size_t)nabs * plane + (size_t)ig * ldr;
+          const double* __restrict__ JP = J0 + plane;
+          const double* __restrict__ JM = nabs >= 1 ? J0 - plane : J0;
+          const double* __restrict__ PP = sp.Jrel + (size_t)(sp.nhi + 2) * plane + (size_t)ig * ldr;
+          const double* __restrict__ DG = sp.dfg_rel + (size_t)ig * ldr;
+          const double* __restrict__ DP = sp.dfp_rel + (size_t)ig * ldr;
+          const cd gom = (g1 * omc) * vA / kpar;
+          const double nqv = nn * qs * vA / (kpar * ms), kv = kpar / vA, cw = wg * dpb;
+          const double par = (nabs & 1) ? -1.0 : 1.0;
+          // the node range with non-zero weight: [int_start, lowerlimit] and [upperlimit, int_end]
+          for (int ip = 1 + lane; ip <= npb - 1; ip += 32) {
+            const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
+            if (w == 0.0) continue;
+            const double j0 = J0[ip], jp = JP[ip], jm = nabs >= 1 ? JM[ip] : 0.0;
+            double bj, bp;
+            if (nabs == 0) {
+              bj = j0;
+              bp = -jp;
+            } else if (!sg) {
+              bj = j0;
+              bp = 0.5 * (jm - jp);
+            } else {
+              bj = par * j0;
+              bp = (nabs == 1) ? 0.5 * (jp - jm) : 0.5 * ((-par) * jp - (-par) * jm);
+            }
+            const double pb = pbv[ip], pq = PP[ip], dfg = DG[ip], dfp = DP[ip];
+            const double nr = c.pref * fma(omc.x, dfg, kv * dfp), ni = c.pref * (omc.y * dfg);
+            const double dr = pb - gom.x + nqv, di = -gom.y;
+            const double t = (cw * w) / fma(dr, dr, di * di);
+            const double ur = fma(nr, dr, ni * di) * t, ui = fma(ni, dr, -(nr * di)) * t;
+            const double b2 = bj * bj, bb = bj * bp * pq, q2 = (bp * pq) * (bp * pq);
+            const double b2p = b2 * pb, b2pp = b2p * pb, bbp = bb * pb;
+            Sd.v[0].x = fma(ur, b2, Sd.v[0].x);   Sd.v[0].y = fma(ui, b2, Sd.v[0].y);
+            Sd.v[1].x = fma(ur, b2p, Sd.v[1].x);  Sd.v[1].y = fma(ui, b2p, Sd.v[1].y);
+            Sd.v[2].x = fma(ur, b2pp, Sd.v[2].x); Sd.v[2].y = fma(ui, b2pp, Sd.v[2].y);
+            Sd.v[3].x = fma(ur, bb, Sd.v[3].x);   Sd.v[3].y = fma(ui, bb, Sd.v[3].y);
+            Sd.v[4].x = fma(ur, bbp, Sd.v[4].x);  Sd.v[4].y = fma(ui, bbp, Sd.v[4].y);
+            Sd.v[5].x = fma(ur, q2, Sd.v[5].x);   Sd.v[5].y = fma(ui, q2, Sd.v[5].y);
+          }
+        } else {
+          for (int ip = 1 + lane; ip <= npb - 1; ip += 32) {
+            const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
+            if (w == 0.0) continue;
+            Six2 T;
+            cd num;
+            node_values(c, ig, ip, sg, T, num);
+            const cd den = mk(pbv[ip], 0.0) - (g1 * omc) * vA / kpar + mk(nn * qs * vA / (kpar * ms), 0.0);
+            const cd U = (wg * dpb * w) * (num / den);
 #pragma unroll
-          for (int q = 0; q < 6; q++) acc.v[q] += U * T.v[q];
+            for (int q = 0; q < 6; q++) acc.v[q] += U * T.v[q];
+          }
         }
         // principal part
         if (found && lowerlimit >= int_start && upperlimit <= int_end) {
@@ -379,21 +466,36 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           const double smdelta = capDelta / (1.0 * M_P);
           Six2 pr;
           zero6(pr);
+          // node values of the window [ires - M_I - 2, ires + M_I + 4]: one node per lane
+          const int W0 = ires - M_I - 2, nwin = (2 * M_I + 7 <= REL_WIN) ? 2 * M_I + 7 : 0;
+          const cd(*win)[6] = s_win[warp];
+          const double inv_dpb = 1.0 / dpb;
+          __syncwarp();
+          if (lane < nwin && W0 + lane >= 0 && W0 + lane <= npb) {
+            Six2 T;
+            cd num;
+            node_values(c, ig, W0 + lane, sg, T, num);
+#pragma unroll
+            for (int q = 0; q < 6; q++) s_win[warp][lane][q] = num * T.v[q];
+          }
+          __syncwarp();
           if (fabs(denomI) > g.Tlim) {
             for (int j = lane; j <= M_P; j += 32) {
               const double wj = (j == 0 || j == M_P) ? 1.0 : 2.0;
               const double p = (j == 0) ? denomR : (j == M_P ? denomR + capDelta : denomR + smdelta * j);
               Six2 f1, f2;
-              funct_g_rel6(c, sg, p, ig, f1);
-              funct_g_rel6(c, sg, 2.0 * denomR - p, ig, f2);
-              const cd d1 = mk(p - denomR, -denomI), d2 = mk(p - denomR, denomI);
+              funct_g_win(c, sg, p, ig, win, W0, nwin, inv_dpb, f1);
+              funct_g_win(c, sg, 2.0 * denomR - p, ig, win, W0, nwin, inv_dpb, f2);
+              // wj / d1 and wj / d2 with d2 = conj(d1): one reciprocal for the twelve quotients
+              const double dx = p - denomR, tt = wj / (dx * dx + denomI * denomI);
+              const cd r1 = mk(dx * tt, denomI * tt), r2 = mk(dx * tt, -(denomI * tt));
 #pragma unroll
-              for (int q = 0; q < 6; q++) pr.v[q] += wj * (f1.v[q] / d1) - wj * (f2.v[q] / d2);
+              for (int q = 0; q < 6; q++) pr.v[q] += f1.v[q] * r1 - f2.v[q] * r2;
             }
           } else {
             Six2 fp_, fm_;
-            funct_g_rel6(c, sg, denomR + dpb, ig, fp_);
-            funct_g_rel6(c, sg, denomR - dpb, ig, fm_);
+            funct_g_win(c, sg, denomR + dpb, ig, win, W0, nwin, inv_dpb, fp_);
+            funct_g_win(c, sg, denomR - dpb, ig, win, W0, nwin, inv_dpb, fm_);
             for (int j = 1 + lane; j <= M_P; j += 32) {
               const double wj = (j == M_P) ? 1.0 : 2.0;
               const double p = (j == M_P) ? denomR + capDelta : denomR + smdelta * j;
@@ -406,7 +508,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
             }
             if (lane == 0 && denomI != 0.0) {
               Six2 f0_;
-              funct_g_rel6(c, sg, denomR, ig, f0_);
+              funct_g_win(c, sg, denomR, ig, win, W0, nwin, inv_dpb, f0_);
               const double sgn = denomI > 0.0 ? 1.0 : -1.0;
 #pragma unroll
               for (int q = 0; q < 6; q++) pr.v[q] += sgn * (cmul_i((2.0 * PI_) * f0_.v[q]) / smdelta);
@@ -420,15 +522,26 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
               const double wj = (j == 0 || j == ntiny) ? 1.0 : 2.0;
               const double p = (j == 0) ? denomR + capDelta : denomR + capDelta + correction * smdelta * j;
               Six2 f1;
-              funct_g_rel6(c, sg, p, ig, f1);
-              const cd d1 = mk(p - denomR, -denomI);
+              funct_g_win(c, sg, p, ig, win, W0, nwin, inv_dpb, f1);
+              const double dx = p - denomR, tt = (wj * correction) / (dx * dx + denomI * denomI);
+              const cd r1 = mk(dx * tt, denomI * tt);
 #pragma unroll
-              for (int q = 0; q < 6; q++) pr.v[q] += (wj * correction) * (f1.v[q] / d1);
+              for (int q = 0; q < 6; q++) pr.v[q] += f1.v[q] * r1;
             }
           }
 #pragma unroll
           for (int q = 0; q < 6; q++) acc.v[q] += (wg * smdelta) * pr.v[q];
         }
+      }
+      {
+        // moments -> tensor components (int_T_rel, src/ALPS_fns_rel.f90:1256-1369)
+        const double c0 = (nn * nn) / (c.zbar * c.zbar), c3 = c.kf1 * nn / c.zbar;
+        acc.v[0] += c0 * Sd.v[0];
+        acc.v[1] += c.kf2 * Sd.v[5];
+        acc.v[2] += c.kf2 * Sd.v[2];
+        acc.v[3] += cmul_i(c3 * Sd.v[3]);
+        acc.v[4] += c3 * Sd.v[1];
+        acc.v[5] += -cmul_i(c.kf2 * Sd.v[4]);
       }
 #pragma unroll
       for (int q = 0; q < 6; q++) acc.v[q] = (dgam * 0.25) * acc.v[q];
@@ -518,18 +631,23 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
 
 // Bessel factors of int_T_rel (src/ALPS_fns_rel.f90:1297-1322) depend on (igamma, ipparbar) through
 // pperpbar = sqrt(gamma^2 - 1 - pparbar^2) but not on omega: tabulated once per k with the same literal BESSJ.
+// Planes 0..nmaxord hold J_n, plane nmaxord + 1 holds pperpbar.
 __global__ void k_rel_bessel_table(const double* __restrict__ grel, const double* __restrict__ pbrel, int ng, int npb,
                                    double zfac, int nmaxord, double* __restrict__ Jrel) {
   const int ldr = npb + 1;
   const size_t plane = (size_t)(ng + 1) * ldr;
   const size_t o = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
-  if (o >= plane || n > nmaxord) return;
+  if (o >= plane || n > nmaxord + 1) return;
   const int ig = (int)(o / ldr), ip = (int)(o % ldr);
   const double gam = grel[ig], pb = pbrel[ip];
   const double a = gam * gam - 1.0 - pb * pb;
   double v = 0.0;
-  if (a >= 0.0) v = bessj_ref(n, zfac * sqrt(a));
+  if (n == nmaxord + 1) {
+    if (a >= 0.0) v = sqrt(a);   // plane nmaxord + 1: pperpbar itself
+  } else if (a >= 0.0) {
+    v = bessj_ref(n, zfac * sqrt(a));
+  }
   Jrel[(size_t)n * plane + o] = v;
 }
 
@@ -564,7 +682,8 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
                 int* err_flag, int nsplit, double* Mpart, int* tickets, cudaStream_t st) {
   if (n_om <= 0 || ntiles <= 0) return;
   if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
-  if (nsplit > 1 || n_om * ntiles <= 2 * 148)
+  static const char* force = getenv("ALPS_B200_REL_MINB");   // A/B knob: "1" = 255-register variant always
+  if (nsplit > 1 || n_om * ntiles <= 2 * 148 || (force && force[0] == '1'))
     k_rel<1><<<n_om * ntiles * nsplit, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, nsplit,
                                                              Mpart, tickets);
   else
@@ -574,7 +693,7 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
 void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, int npb, double zfac, int nmaxord,
                              double* Jrel, cudaStream_t st) {
   const size_t plane = (size_t)(ng + 1) * (npb + 1);
-  dim3 grid((unsigned)((plane + 127) / 128), nmaxord + 1);
+  dim3 grid((unsigned)((plane + 127) / 128), nmaxord + 2);   // + the pperpbar plane
   k_rel_bessel_table<<<grid, 128, 0, st>>>(grel, pbrel, ng, npb, zfac, nmaxord, Jrel);
 }
 void launch_int_ee_rel(const double* pbv, const double* dfp, const int* lo, const int* up, int ng, int npb, double qs,

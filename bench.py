@@ -294,6 +294,9 @@ def run_ours(args, w, rank, world, local_rank):
                 traffic = tj["dram_bytes_per_launch"] / tj["omegas_per_launch"] * B   # scaled to this launch size
             except Exception:
                 traffic = None
+        # one read of A', C' (fragment order, padded) and W per launch + plan (32 B) and moment sums (96 B) per item
+        alg_bytes = float(sum(2 * 8 * (w["nperp"] - 1) * (w["npar"] - 1) + 8 * (w["nperp"] - 1) * 3 * (int(n) + 1)
+                              for n in nmax) + B * sum(2 * (int(n) + 1) for n in nmax) * (32 + 96))
         line = {"metric": "D(omega,k) evals/sec", "value": value, "unit": "D/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -310,6 +313,7 @@ def run_ours(args, w, rank, world, local_rank):
                                       else "FP64 FMA pipe (DFMA)"),
                              "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s",
                              "frac": achieved / peak_meas if peak_meas else None, "traffic": traffic,
+                             "algorithmic_bytes": alg_bytes,
                              "peak_source": ("DMMA (mma.sync.m8n8k4.f64)" if dmma else "DFMA") +
                                             " micro-benchmark run in this job (MEASURED_PEAKS.json has no FP64 entry)",
                              "peak_dfma_microbench": peak_dfma, "peak_dmma_microbench": peak_dmma,

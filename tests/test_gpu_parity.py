@@ -372,6 +372,45 @@ def test_real_omega_exactly_on_a_resonant_node():
         sol.close()
 
 
+def test_resonance_at_the_grid_edges_and_outside_the_grid():
+    """integrate_res edge fall-backs (src/ALPS_fns.f90:971-992: the near-pole piece is dropped when the window
+    touches either end of the p_par grid), resonances up to positions_principal cells outside the grid
+    (determine_resonances :641-745), the dp/2 rule of upperlimit (:1002-1006) and funct_g's mid-cell ties:
+    Re(p_res) of the protons' n = 0 and n = 1 harmonics swept over nodes next to both grid ends, with exact
+    node / mid-cell / generic offsets, for damped, growing and real omega."""
+    pl = tables.config_small(24, 48, kind=1)
+    kperp, kpar = 0.3, 0.05
+    ms, qs = pl.species[0].ms, pl.species[0].qs
+    ppar = pl.pp[0, 0, :, 1]
+    dp = ppar[1] - ppar[0]
+    npar = pl.npar
+    M_I = pl.positions_principal
+    nodes = sorted(set([0, 1, 2, 3, M_I + 1, M_I + 2, M_I + 3, npar - M_I - 3, npar - M_I - 2, npar - 3, npar - 2,
+                        npar - 1, npar]))
+    oms = []
+    for j in nodes:
+        for off in (0.0, 0.31, 0.5, -0.5):
+            pres = ppar[j] + off * dp
+            for n in (0, 1):
+                re = (kpar * pres + n * qs) / ms
+                for im in (-3e-4, 0.0, 2e-4):
+                    oms.append(complex(re, im))
+    for c in (0.5, 1.0, M_I - 0.5, M_I, M_I + 0.5, M_I + 1.5):     # outside the grid, both sides
+        for pres in (ppar[0] - c * dp, ppar[npar] + c * dp):
+            oms.append(complex(kpar * pres / ms, -1e-4))
+            oms.append(complex((kpar * pres + qs) / ms, 1e-4))
+    oms = [om for om in oms if abs(om) > 1e-6]
+    _compare(pl, kperp, kpar, oms)
+
+
+def test_negative_kpar_and_drifting_species():
+    """k_par < 0 flips the side of the Landau contour (abs(kpar) and sign(kpar) in landau_integrate /
+    integrate_res, src/ALPS_fns.f90:1088-1165, 1327-1452)."""
+    pl = tables.config_small(24, 48, kind=1)
+    oms = list(omega_samples(7, 8, (0.02, 1.4), (-0.04, 0.04))) + [0.3 + 0j, 0.011 - 1e-6j]
+    _compare(pl, 0.3, -0.05, oms)
+
+
 def test_quadrature_variants_and_batch_classes_agree(monkeypatch):
     """The same D from every execution path of the non-relativistic chain: CUDA-graph replay of disp()
     (third call on), plain disp(), batches of the latency class (<= 8), the small-batch class (<= 64) and
