@@ -63,18 +63,26 @@ __device__ inline cd cpowi(cd z, int k) {
 // cold paths (principal-value window, Landau term) stay out of line: the hot loop then fits the
 // instruction cache (ncu: no_instruction stalls 1.6 -> per issue before)
 #define REL_NOINLINE __noinline__
-__device__ REL_NOINLINE cd cbessj(cd z, int nu) {
-  cd sum = mk(0.0, 0.0);
-  const cd mz2 = (-(z * z)) / 4.0;
-  double fact = 1.0;
+// CBESSJ (src/ALPS_fns_rel.f90:1502-1555): J_{nu0}, J_{nu0+1}, J_{nu0+2} at complex z by its 21-term series
+// sum_k (-z^2/4)^k / (k! Gamma(nu+k+1)) (z/2)^nu, sharing the powers
+// (-z^2/4)^k / k! between the three orders; rfact[k] = 1/k!, rgam[i] = 1/Gamma(nu0 + 1 + i) from the
+// literal Lanczos Gamma (tables per CTA).  nu0 = -1 (|n| = 0): the first order is skipped.
+__device__ __forceinline__ void cbessj3(cd z, int nu0, const double* rfact, const double* rgam, cd& jm, cd& j0, cd& jp) {
+  const cd mz2 = (-(z * z)) * 0.25;
+  cd pw = mk(1.0, 0.0), sm_ = mk(0.0, 0.0), s0 = mk(0.0, 0.0), sp_ = mk(0.0, 0.0);
+#pragma unroll 3
   for (int k = 0; k <= 20; k++) {
-    if (k >= 2) fact = fact * (1.0 * k);
-    cd tmp = cpowi(mz2, k);
-    tmp = tmp / fact;
-    tmp = tmp / gamma_ref(1.0 * (nu + k + 1));
-    sum = sum + tmp;
+    const cd t = rfact[k] * pw;
+    if (nu0 >= 0) sm_ += rgam[k] * t;
+    s0 += rgam[k + 1] * t;
+    sp_ += rgam[k + 2] * t;
+    pw = pw * mz2;
   }
-  return cpowi(z / 2.0, nu) * sum;
+  const cd zh = 0.5 * z;
+  const cd p0 = cpowi(zh, nu0 + 1);
+  j0 = p0 * s0;
+  jp = (p0 * zh) * sp_;
+  jm = nu0 >= 0 ? cpowi(zh, nu0) * sm_ : mk(0.0, 0.0);
 }
 __device__ inline cd csqrt_(cd z) {
   double m = hypot(z.x, z.y);
@@ -215,7 +223,6 @@ __device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, i
   const int npb = c.g->npparbar, ldr = npb + 1;
   const double* pbv = sp.pbrel;
   const double* f0r = sp.f0_rel + (size_t)ig * ldr;
-  const double dpb = sp.dpparbar;
   int ic = -2;
   {
     int i0 = (int)floor((p - pbv[0]) * inv_dpb);
@@ -235,9 +242,12 @@ __device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, i
     funct_g_rel6(c, sg, p, ig, out);
     return;
   }
-  const double x = p - pbv[ic];
+  const double sx = (0.5 * inv_dpb) * (p - pbv[ic]);   // central-difference slope factor times the offset
 #pragma unroll
-  for (int q = 0; q < 6; q++) out.v[q] = win[k][q] + (0.5 * ((win[k + 1][q] - win[k - 1][q]) / dpb)) * x;
+  for (int q = 0; q < 6; q++) {
+    const cd a = win[k][q], lo = win[k - 1][q], hi = win[k + 1][q];
+    out.v[q] = mk(fma(sx, hi.x - lo.x, a.x), fma(sx, hi.y - lo.y, a.y));
+  }
 }
 
 __device__ __forceinline__ cd warp_sum_cd(cd v) {
@@ -274,6 +284,15 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
   __shared__ int s_found[2];
   __shared__ cd s_red[REL_THREADS / 32][6];
   __shared__ cd s_win[REL_THREADS / 32][REL_WIN][6];   // node values of the principal-value window, per warp
+  __shared__ double s_rfact[21], s_rgam[23];           // 1/k!, 1/Gamma(|n| + i): series of the Landau term
+  if (tid < 21) {
+    double fact = 1.0;
+    for (int k = 2; k <= tid; k++) fact = fact * (1.0 * k);   // Fact, src/ALPS_fns_rel.f90:1560-1574
+    s_rfact[tid] = 1.0 / fact;
+  } else if (tid >= 32 && tid < 32 + 23) {
+    const int m = nabs + (tid - 32);                          // Gamma(m), m = |n| .. |n| + 22
+    s_rgam[tid - 32] = m >= 1 ? 1.0 / gamma_ref(1.0 * m) : 0.0;
+  }
   if (tid < 2) s_found[tid] = 0;
   __syncthreads();
 
@@ -433,7 +452,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
             const double pb = pbv[ip], pq = PP[ip], dfg = DG[ip], dfp = DP[ip];
             const double nr = c.pref * fma(omc.x, dfg, kv * dfp), ni = c.pref * (omc.y * dfg);
             const double dr = pb - gom.x + nqv, di = -gom.y;
-            const double t = (cw * w) / fma(dr, dr, di * di);
+            const double t = (cw * w) * fast_rcp(fma(dr, dr, di * di));
             const double ur = fma(nr, dr, ni * di) * t, ui = fma(ni, dr, -(nr * di)) * t;
             const double b2 = bj * bj, bb = bj * bp * pq, q2 = (bp * pq) * (bp * pq);
             const double b2p = b2 * pb, b2pp = b2p * pb, bbp = bb * pb;
@@ -487,7 +506,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
               funct_g_win(c, sg, p, ig, win, W0, nwin, inv_dpb, f1);
               funct_g_win(c, sg, 2.0 * denomR - p, ig, win, W0, nwin, inv_dpb, f2);
               // wj / d1 and wj / d2 with d2 = conj(d1): one reciprocal for the twelve quotients
-              const double dx = p - denomR, tt = wj / (dx * dx + denomI * denomI);
+              const double dx = p - denomR, tt = wj * fast_rcp(fma(dx, dx, denomI * denomI));
               const cd r1 = mk(dx * tt, denomI * tt), r2 = mk(dx * tt, -(denomI * tt));
 #pragma unroll
               for (int q = 0; q < 6; q++) pr.v[q] += f1.v[q] * r1 - f2.v[q] * r2;
@@ -523,7 +542,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
               const double p = (j == 0) ? denomR + capDelta : denomR + capDelta + correction * smdelta * j;
               Six2 f1;
               funct_g_win(c, sg, p, ig, win, W0, nwin, inv_dpb, f1);
-              const double dx = p - denomR, tt = (wj * correction) / (dx * dx + denomI * denomI);
+              const double dx = p - denomR, tt = (wj * correction) * fast_rcp(fma(dx, dx, denomI * denomI));
               const cd r1 = mk(dx * tt, denomI * tt);
 #pragma unroll
               for (int q = 0; q < 6; q++) pr.v[q] += f1.v[q] * r1;
@@ -565,12 +584,12 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           const cd pperpbar = csqrt_(mk(g1 * g1 - 1.0, 0.0) - pres * pres);
           const cd z = c.zfac * pperpbar;
           const double par = (nabs & 1) ? -1.0 : 1.0;
-          cd bj = cbessj(z, nabs), bp;
+          cd bj, bp, b1, b2;
+          cbessj3(z, nabs - 1, s_rfact, s_rgam, b1, bj, b2);   // J_{|n|-1}, J_|n|, J_{|n|+1}
           if (sg) bj = par * bj;
           if (nabs == 0) {
-            bp = -cbessj(z, 1);
+            bp = -b2;
           } else {
-            const cd b1 = cbessj(z, nabs - 1), b2 = cbessj(z, nabs + 1);
             if (!sg) bp = 0.5 * (b1 - b2);
             else bp = (nabs == 1) ? 0.5 * (b2 - b1) : 0.5 * ((-par) * b2 - (-par) * b1);
           }

@@ -16,7 +16,8 @@ for r in rows:
         hdr = r
         i_s, i_x = hdr.index("# Samples"), hdr.index("Instructions Executed")
     elif hdr and len(r) >= len(hdr) and r[0].isdigit():
-        lines.append((fname, int(r[0]), float(r[i_s] or 0), float(r[i_x] or 0), r[1].strip()))
+        num = lambda v: float(v) if v not in ("", "-") else 0.0
+        lines.append((fname, int(r[0]), num(r[i_s]), num(r[i_x]), r[1].strip()))
 tot_s = sum(l[2] for l in lines) or 1.0
 tot_x = sum(l[3] for l in lines) or 1.0
 print("total samples %d, warp instructions %d" % (tot_s, tot_x))
