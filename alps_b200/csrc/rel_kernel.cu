@@ -149,8 +149,10 @@ struct RelCtx {
   double kf1, kf2;
 };
 
-// G_mode(ig, ip) for sign sg: pref (om dfg + (kpar/vA) dfp) T_mode   (numerator of resU_rel x int_T_rel)
-__device__ inline void node_values(const RelCtx& c, int ig, int ip, int sg, Six2& T, cd& num) {
+// Node (ig, ip), sign sg: num = pref (om dfg + (kpar/vA) dfp) (numerator of resU_rel) and the six real Bessel
+// moments M = {J^2, J^2 p, J^2 p^2, J J' pp, J J' pp p, J'^2 pp^2} (J, J' with the sign rules for n < 0, pp =
+// pperpbar, p = pparbar) of which the six components of int_T_rel are constant multiples (moments_to_modes).
+__device__ inline void node_moments(const RelCtx& c, int ig, int ip, int sg, double* M, cd& num) {
   const SpeciesDev& sp = *c.sp;
   const int ldr = c.g->npparbar + 1;
   const double gam = sp.grel[ig], pb = sp.pbrel[ip];
@@ -170,59 +172,32 @@ __device__ inline void node_values(const RelCtx& c, int ig, int ip, int sg, Six2
   }
   double bj, bp;
   bessel_pair(c.nabs, sg, z, jm, j0, jp, bj, bp);
-  modes_real(bj, bp, pperpbar, pb, c.zbar, sg ? -(double)c.nabs : (double)c.nabs, c.kf1, c.kf2, T);
+  const double b2 = bj * bj, bb = bj * bp * pperpbar, q2 = (bp * pperpbar) * (bp * pperpbar);
+  M[0] = b2;
+  M[1] = b2 * pb;
+  M[2] = (b2 * pb) * pb;
+  M[3] = bb;
+  M[4] = bb * pb;
+  M[5] = q2;
   const double dfg = sp.dfg_rel[(size_t)ig * ldr + ip], dfp = sp.dfp_rel[(size_t)ig * ldr + ip];
   num = c.pref * (c.om * dfg + mk((c.g->kpar / c.g->vA) * dfp, 0.0));
 }
 
-// funct_g_rel for one sign (src/ALPS_fns_rel.f90:918-999), all six components
-__device__ REL_NOINLINE void funct_g_rel6(const RelCtx& c, int sg, double p, int ig, Six2& out) {
-  const SpeciesDev& sp = *c.sp;
-  const int npb = c.g->npparbar, ldr = npb + 1;
-  const double* pbv = sp.pbrel;
-  const double* f0r = sp.f0_rel + (size_t)ig * ldr;
-  const double dpb = sp.dpparbar;
-  int ic = -2;
-  {
-    int i0 = (int)floor((p - pbv[0]) / dpb);
-    for (int q = min(i0 + 2, npb - 1); q >= max(i0 - 2, 0); q--)
-      if (pbv[q + 1] > p && pbv[q] <= p) {
-        ic = q;
-        break;
-      }
-  }
-  if (ic + 1 >= 0 && ic + 1 <= npb && f0r[ic + 1] <= -1.0) ic = ic - 1;
-  if (ic - 1 >= 0 && ic - 1 <= npb && f0r[ic - 1] <= -1.0) ic = ic + 1;
-  if (p == pbv[npb]) ic = npb - 2;
-  if (ic >= npb - 1) ic = npb - 2;
-  if (ic <= 1) ic = 2;
-  Six2 T;
-  cd num, gm[6], g0[6], gp[6];
-  node_values(c, ig, ic - 1, sg, T, num);
-#pragma unroll
-  for (int q = 0; q < 6; q++) gm[q] = num * T.v[q];
-  node_values(c, ig, ic, sg, T, num);
-#pragma unroll
-  for (int q = 0; q < 6; q++) g0[q] = num * T.v[q];
-  node_values(c, ig, ic + 1, sg, T, num);
-#pragma unroll
-  for (int q = 0; q < 6; q++) gp[q] = num * T.v[q];
-  const double x = p - pbv[ic];
-#pragma unroll
-  for (int q = 0; q < 6; q++) out.v[q] = g0[q] + (0.5 * ((gp[q] - gm[q]) / dpb)) * x;
+// moment sums -> tensor components (int_T_rel, src/ALPS_fns_rel.f90:1256-1369), nn = signed harmonic
+__device__ __forceinline__ void moments_to_modes(const RelCtx& c, double nn, const Six2& S, Six2& T) {
+  const double c0 = (nn * nn) / (c.zbar * c.zbar), c3 = c.kf1 * nn / c.zbar;
+  T.v[0] = c0 * S.v[0];
+  T.v[1] = c.kf2 * S.v[5];
+  T.v[2] = c.kf2 * S.v[2];
+  T.v[3] = cmul_i(c3 * S.v[3]);
+  T.v[4] = c3 * S.v[1];
+  T.v[5] = -cmul_i(c.kf2 * S.v[4]);
 }
 
-// funct_g_rel for the principal-value window: the node values G(ig, node) = num T of the 2 M_I + 7 nodes
-// around the resonance are evaluated once per (row, sign) into shared memory (win[node - W0][6]); every
-// quadrature point then only selects its node (the same search and cone rules as funct_g_rel6) and
-// interpolates.  Falls back to funct_g_rel6 if a node outside the window is asked for.
-constexpr int REL_WIN = 32;
-__device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, int ig, const cd (*win)[6], int W0,
-                                            int nwin, double inv_dpb, Six2& out) {
-  const SpeciesDev& sp = *c.sp;
-  const int npb = c.g->npparbar, ldr = npb + 1;
+// node selection of funct_g_rel (src/ALPS_fns_rel.f90:918-999)
+__device__ __forceinline__ int funct_g_node(const SpeciesDev& sp, int npb, int ig, double p, double inv_dpb) {
   const double* pbv = sp.pbrel;
-  const double* f0r = sp.f0_rel + (size_t)ig * ldr;
+  const double* f0r = sp.f0_rel + (size_t)ig * (npb + 1);
   int ic = -2;
   {
     int i0 = (int)floor((p - pbv[0]) * inv_dpb);
@@ -237,12 +212,39 @@ __device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, i
   if (p == pbv[npb]) ic = npb - 2;
   if (ic >= npb - 1) ic = npb - 2;
   if (ic <= 1) ic = 2;
+  return ic;
+}
+
+// funct_g_rel for one sign, moment form, nodes evaluated on the spot (fallback of funct_g_win)
+__device__ REL_NOINLINE void funct_g_rel6(const RelCtx& c, int sg, double p, int ig, int ic, double inv_dpb, Six2& out) {
+  double Mm[6], M0[6], Mp[6];
+  cd nm, n0, np_;
+  node_moments(c, ig, ic - 1, sg, Mm, nm);
+  node_moments(c, ig, ic, sg, M0, n0);
+  node_moments(c, ig, ic + 1, sg, Mp, np_);
+  const double sx = (0.5 * inv_dpb) * (p - c.sp->pbrel[ic]);
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    const cd a = M0[q] * n0, lo = Mm[q] * nm, hi = Mp[q] * np_;
+    out.v[q] = mk(fma(sx, hi.x - lo.x, a.x), fma(sx, hi.y - lo.y, a.y));
+  }
+}
+
+// funct_g_rel for the principal-value window: the node values num M (moment form) of the 2 M_I + 7 nodes
+// around the resonance are evaluated once per (row, sign) into shared memory (win[node - W0][6]); every
+// quadrature point then only selects its node (the same search and cone rules as funct_g_rel6) and
+// interpolates.  Falls back to funct_g_rel6 if a node outside the window is asked for.
+constexpr int REL_WIN = 32;
+__device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, int ig, const cd (*win)[6], int W0,
+                                            int nwin, double inv_dpb, Six2& out) {
+  const SpeciesDev& sp = *c.sp;
+  const int ic = funct_g_node(sp, c.g->npparbar, ig, p, inv_dpb);
   const int k = ic - W0;
   if (k < 1 || k + 1 >= nwin) {
-    funct_g_rel6(c, sg, p, ig, out);
+    funct_g_rel6(c, sg, p, ig, ic, inv_dpb, out);
     return;
   }
-  const double sx = (0.5 * inv_dpb) * (p - pbv[ic]);   // central-difference slope factor times the offset
+  const double sx = (0.5 * inv_dpb) * (p - sp.pbrel[ic]);   // central-difference slope factor times the offset
 #pragma unroll
   for (int q = 0; q < 6; q++) {
     const cd a = win[k][q], lo = win[k - 1][q], hi = win[k + 1][q];
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
       const double dpb = sp.dpparbar, dgam = sp.dgamma;
       const double* pbv = sp.pbrel;
       const int ldr = npb + 1;
-      Six2 Sd;   // Bessel moments of the direct part (tabulated Bessel factors)
+      Six2 Sd;   // Bessel-moment sums of the direct and principal parts
       zero6(Sd);
       for (int ig = 1 + warp + nwarps * js; ig <= ng - 1; ig += nwarps * nsplit) {
         const double wg = (ig == ng - 1) ? 1.0 : 2.0;
@@ -467,13 +469,13 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           for (int ip = 1 + lane; ip <= npb - 1; ip += 32) {
             const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
             if (w == 0.0) continue;
-            Six2 T;
+            double M[6];
             cd num;
-            node_values(c, ig, ip, sg, T, num);
+            node_moments(c, ig, ip, sg, M, num);
             const cd den = mk(pbv[ip], 0.0) - (g1 * omc) * vA / kpar + mk(nn * qs * vA / (kpar * ms), 0.0);
             const cd U = (wg * dpb * w) * (num / den);
 #pragma unroll
-            for (int q = 0; q < 6; q++) acc.v[q] += U * T.v[q];
+            for (int q = 0; q < 6; q++) Sd.v[q] += M[q] * U;
           }
         }
         // principal part
@@ -491,11 +493,11 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           const double inv_dpb = 1.0 / dpb;
           __syncwarp();
           if (lane < nwin && W0 + lane >= 0 && W0 + lane <= npb) {
-            Six2 T;
+            double M[6];
             cd num;
-            node_values(c, ig, W0 + lane, sg, T, num);
+            node_moments(c, ig, W0 + lane, sg, M, num);
 #pragma unroll
-            for (int q = 0; q < 6; q++) s_win[warp][lane][q] = num * T.v[q];
+            for (int q = 0; q < 6; q++) s_win[warp][lane][q] = M[q] * num;
           }
           __syncwarp();
           if (fabs(denomI) > g.Tlim) {
@@ -515,16 +517,17 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
             Six2 fp_, fm_;
             funct_g_win(c, sg, denomR + dpb, ig, win, W0, nwin, inv_dpb, fp_);
             funct_g_win(c, sg, denomR - dpb, ig, win, W0, nwin, inv_dpb, fm_);
+            // sum_j 2 wj g' x^2 / (x^2 + denomI^2): g' does not depend on j
+            double sj = 0.0;
             for (int j = 1 + lane; j <= M_P; j += 32) {
               const double wj = (j == M_P) ? 1.0 : 2.0;
               const double p = (j == M_P) ? denomR + capDelta : denomR + smdelta * j;
               const double x2 = (p - denomR) * (p - denomR);
-#pragma unroll
-              for (int q = 0; q < 6; q++) {
-                const cd gprime = (fp_.v[q] - fm_.v[q]) / (2.0 * dpb);
-                pr.v[q] += ((wj * 2.0) * gprime * x2) / (x2 + denomI * denomI);
-              }
+              sj += ((wj * 2.0) * x2) * fast_rcp(x2 + denomI * denomI);
             }
+            const double h2 = 0.5 * inv_dpb;
+#pragma unroll
+            for (int q = 0; q < 6; q++) pr.v[q] += (sj * h2) * (fp_.v[q] - fm_.v[q]);
             if (lane == 0 && denomI != 0.0) {
               Six2 f0_;
               funct_g_win(c, sg, denomR, ig, win, W0, nwin, inv_dpb, f0_);
@@ -549,19 +552,11 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
             }
           }
 #pragma unroll
-          for (int q = 0; q < 6; q++) acc.v[q] += (wg * smdelta) * pr.v[q];
+          for (int q = 0; q < 6; q++) Sd.v[q] += (wg * smdelta) * pr.v[q];
         }
       }
-      {
-        // moments -> tensor components (int_T_rel, src/ALPS_fns_rel.f90:1256-1369)
-        const double c0 = (nn * nn) / (c.zbar * c.zbar), c3 = c.kf1 * nn / c.zbar;
-        acc.v[0] += c0 * Sd.v[0];
-        acc.v[1] += c.kf2 * Sd.v[5];
-        acc.v[2] += c.kf2 * Sd.v[2];
-        acc.v[3] += cmul_i(c3 * Sd.v[3]);
-        acc.v[4] += c3 * Sd.v[1];
-        acc.v[5] += -cmul_i(c.kf2 * Sd.v[4]);
-      }
+      // moment sums of the direct and principal parts -> tensor components
+      moments_to_modes(c, nn, Sd, acc);
 #pragma unroll
       for (int q = 0; q < 6; q++) acc.v[q] = (dgam * 0.25) * acc.v[q];
 
