@@ -435,10 +435,23 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           const cd gom = (g1 * omc) * vA / kpar;
           const double nqv = nn * qs * vA / (kpar * ms), kv = kpar / vA, cw = wg * dpb;
           const double par = (nabs & 1) ? -1.0 : 1.0;
-          // the node range with non-zero weight: [int_start, lowerlimit] and [upperlimit, int_end]
-          for (int ip = 1 + lane; ip <= npb - 1; ip += 32) {
+          // the node range with non-zero weight: the union of [int_start, lowerlimit] and [upperlimit, int_end];
+          // nodes in the gap between them have weight 0 and are predicated off, so the loads of two
+          // iterations can be in flight together
+          int a0 = npb, b0 = 0;
+          if (int_start <= lowerlimit) {
+            a0 = int_start;
+            b0 = lowerlimit;
+          }
+          if (upperlimit <= int_end) {
+            a0 = min(a0, upperlimit);
+            b0 = max(b0, int_end);
+          }
+          a0 = max(a0, 1);
+          b0 = min(b0, npb - 1);
+#pragma unroll 2
+          for (int ip = a0 + lane; ip <= b0; ip += 32) {
             const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
-            if (w == 0.0) continue;
             const double j0 = J0[ip], jp = JP[ip], jm = nabs >= 1 ? JM[ip] : 0.0;
             double bj, bp;
             if (nabs == 0) {
@@ -454,7 +467,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
             const double pb = pbv[ip], pq = PP[ip], dfg = DG[ip], dfp = DP[ip];
             const double nr = c.pref * fma(omc.x, dfg, kv * dfp), ni = c.pref * (omc.y * dfg);
             const double dr = pb - gom.x + nqv, di = -gom.y;
-            const double t = (cw * w) * fast_rcp(fma(dr, dr, di * di));
+            const double t = (w != 0.0) ? (cw * w) * fast_rcp(fma(dr, dr, di * di)) : 0.0;
             const double ur = fma(nr, dr, ni * di) * t, ui = fma(ni, dr, -(nr * di)) * t;
             const double b2 = bj * bj, bb = bj * bp * pq, q2 = (bp * pq) * (bp * pq);
             const double b2p = b2 * pb, b2pp = b2p * pb, bbp = bb * pb;
