@@ -19,7 +19,7 @@ SYMBOLS = [
     "alps_b200_assemble_dev", "alps_b200_set_mode", "alps_b200_set_stream", "alps_b200_sync",
     "alps_b200_get_info", "alps_b200_dfma_peak", "alps_b200_emulate_split",
     "alps_b200_secant", "alps_b200_secant_osc", "alps_b200_rtsec", "alps_b200_refine_guess",
-    "alps_b200_map_search", "alps_b200_calc_eigen", "alps_b200_scan_setup", "alps_b200_om_scan",
+    "alps_b200_map_search", "alps_b200_map_grid", "alps_b200_map_finish", "alps_b200_calc_eigen", "alps_b200_scan_setup", "alps_b200_om_scan",
     "alps_b200_om_double_scan", "alps_b200_set_root_batching",
 ]
 
@@ -103,6 +103,8 @@ def lib():
         L.alps_b200_rtsec.argtypes = [V, V, V]
         L.alps_b200_refine_guess.argtypes = [C.c_int, V, V, C.c_char_p, V]
         L.alps_b200_map_search.argtypes = [V, C.c_char_p, V, V, V, C.c_int, V, V]
+        L.alps_b200_map_grid.argtypes = [V, V]
+        L.alps_b200_map_finish.argtypes = [V, V, C.c_char_p, V, C.c_int, V, V]
         L.alps_b200_calc_eigen.argtypes = [V, C.c_int, V, V, V, C.c_double, C.c_double, C.c_double,
                                            C.c_int, C.c_int, V, V, V, V, V, V, V]
         L.alps_b200_scan_setup.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,

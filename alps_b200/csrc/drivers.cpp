@@ -568,84 +568,128 @@ int alps_b200_refine_guess(int nroots, double* wroots, const alps_b200_solver_op
   });
 }
 
-int alps_b200_map_search(const alps_b200_map* m, const char* map_path, double* om_out, double* val_out,
-                         double* cal_out, int numroots, int* iroots, int* nroots_found) {
-  return guarded([&] {
-    const int nr = m->nr, ni = m->ni;
-    const size_t n = (size_t)nr * ni;
-    std::vector<cplx> om(n), cal(n);
-    std::vector<double> val(n);
-    double dr = m->omf - m->omi, di = m->gamf - m->gami;
-    if (nr > 1) dr = (m->omf - m->omi) / (1.0 * (nr - 1));
-    if (ni > 1) di = (m->gamf - m->gami) / (1.0 * (ni - 1));
-    for (int ir = 1; ir <= nr; ir++) {
-      double wr;
-      if (m->loggridw) {
-        wr = m->omi;
-        if (nr > 1) wr = m->omi * pow(m->omf / m->omi, (1.0 * (ir - 1)) / (1.0 * (nr - 1)));
-      } else {
-        wr = m->omi + dr * (1.0 * (ir - 1));
-      }
-      for (int ii = 1; ii <= ni; ii++) {
-        double wi;
-        if (m->loggridg) {
-          wi = m->gami;
-          if (ni > 1) wi = m->gami * pow(m->gamf / m->gami, (1.0 * (ii - 1)) / (1.0 * (ni - 1)));
-        } else {
-          wi = m->gami + di * (1.0 * (ii - 1));
-        }
-        om[(ir - 1) + (size_t)nr * (ii - 1)] = cplx(wr, wi);
-      }
+// map grid of map_search (src/ALPS_fns.f90:3684-3712), ir fastest
+static void map_grid(const alps_b200_map* m, std::vector<cplx>& om) {
+  const int nr = m->nr, ni = m->ni;
+  om.resize((size_t)nr * ni);
+  double dr = m->omf - m->omi, di = m->gamf - m->gami;
+  if (nr > 1) dr = (m->omf - m->omi) / (1.0 * (nr - 1));
+  if (ni > 1) di = (m->gamf - m->gami) / (1.0 * (ni - 1));
+  for (int ir = 1; ir <= nr; ir++) {
+    double wr;
+    if (m->loggridw) {
+      wr = m->omi;
+      if (nr > 1) wr = m->omi * pow(m->omf / m->omi, (1.0 * (ir - 1)) / (1.0 * (nr - 1)));
+    } else {
+      wr = m->omi + dr * (1.0 * (ir - 1));
     }
-    // the nr x ni serial loop of the reference becomes one batch on the GPU
-    int rc = alps_b200_disp_batch((int)n, reinterpret_cast<const double*>(om.data()),
-                                  reinterpret_cast<double*>(cal.data()), nullptr);
-    if (rc) throw DispError{rc};
-    for (size_t i = 0; i < n; i++) {
-      const double tmp = cal[i].real();
-      val[i] = log10(std::abs(cal[i]));
-      // NaN / infinity sentinels exactly as written in the reference (lines 3726-3742)
-      if (cal[i].imag() != 0.0) {
-        if (!(cplx(tmp, 0.0) != cal[i])) {
-          cal[i] = 999999.0;
-          val[i] = 999999.0;
-        }
-      } else if (cplx(tmp, 0.0) != cal[i]) {
+    for (int ii = 1; ii <= ni; ii++) {
+      double wi;
+      if (m->loggridg) {
+        wi = m->gami;
+        if (ni > 1) wi = m->gami * pow(m->gamf / m->gami, (1.0 * (ii - 1)) / (1.0 * (ni - 1)));
+      } else {
+        wi = m->gami + di * (1.0 * (ii - 1));
+      }
+      om[(ir - 1) + (size_t)nr * (ii - 1)] = cplx(wr, wi);
+    }
+  }
+}
+
+// everything map_search does after the nr x ni loop of disp calls (:3722-3786): val = log10|D|, the NaN /
+// infinity sentinels, the .map file, find_minima
+static void map_finish(const alps_b200_map* m, const std::vector<cplx>& om, std::vector<cplx>& cal,
+                       std::vector<double>& val, const char* map_path, int numroots, int* iroots,
+                       int* nroots_found) {
+  const int nr = m->nr, ni = m->ni;
+  const size_t n = (size_t)nr * ni;
+  val.resize(n);
+  for (size_t i = 0; i < n; i++) {
+    const double tmp = cal[i].real();
+    val[i] = log10(std::abs(cal[i]));
+    // NaN / infinity sentinels exactly as written in the reference (lines 3726-3742)
+    if (cal[i].imag() != 0.0) {
+      if (!(cplx(tmp, 0.0) != cal[i])) {
         cal[i] = 999999.0;
         val[i] = 999999.0;
       }
-      if (std::fabs(tmp) > 1.e100) {
-        cal[i] = 899999.0;
-        val[i] = 899999.0;
-      }
+    } else if (cplx(tmp, 0.0) != cal[i]) {
+      cal[i] = 999999.0;
+      val[i] = 999999.0;
     }
-    if (map_path) {
-      std::string out;
-      for (int ir = 1; ir <= nr; ir++) {
-        for (int ii = 1; ii <= ni; ii++) {
-          size_t i = (ir - 1) + (size_t)nr * (ii - 1);
-          out += es16(om[i].real()) + es16(om[i].imag()) + es16(val[i]) + es16(cal[i].real()) + es16(cal[i].imag()) + "\n";
-        }
-        out += "\n";
-      }
-      append_line(map_path, out, true);
+    if (std::fabs(tmp) > 1.e100) {
+      cal[i] = 899999.0;
+      val[i] = 899999.0;
     }
-    for (size_t i = 0; i < n; i++) {
-      if (om_out) {
-        om_out[2 * i] = om[i].real();
-        om_out[2 * i + 1] = om[i].imag();
+  }
+  if (map_path) {
+    std::string out;
+    for (int ir = 1; ir <= nr; ir++) {
+      for (int ii = 1; ii <= ni; ii++) {
+        size_t i = (ir - 1) + (size_t)nr * (ii - 1);
+        out += es16(om[i].real()) + es16(om[i].imag()) + es16(val[i]) + es16(cal[i].real()) + es16(cal[i].imag()) + "\n";
       }
-      if (val_out) val_out[i] = val[i];
-      if (cal_out) {
-        cal_out[2 * i] = cal[i].real();
-        cal_out[2 * i + 1] = cal[i].imag();
-      }
+      out += "\n";
     }
-    if (iroots && nroots_found) {
-      *nroots_found = 0;
-      if (m->determine_minima && nr > 1 && ni > 1) *nroots_found = find_minima(val, nr, ni, numroots, iroots);
+    append_line(map_path, out, true);
+  }
+  if (iroots && nroots_found) {
+    *nroots_found = 0;
+    if (m->determine_minima && nr > 1 && ni > 1) *nroots_found = find_minima(val, nr, ni, numroots, iroots);
+  }
+}
+
+static void map_export(const std::vector<cplx>& om, const std::vector<cplx>& cal, const std::vector<double>& val,
+                       double* om_out, double* val_out, double* cal_out) {
+  for (size_t i = 0; i < om.size(); i++) {
+    if (om_out) {
+      om_out[2 * i] = om[i].real();
+      om_out[2 * i + 1] = om[i].imag();
     }
+    if (val_out) val_out[i] = val[i];
+    if (cal_out) {
+      cal_out[2 * i] = cal[i].real();
+      cal_out[2 * i + 1] = cal[i].imag();
+    }
+  }
+}
+
+int alps_b200_map_search(const alps_b200_map* m, const char* map_path, double* om_out, double* val_out,
+                         double* cal_out, int numroots, int* iroots, int* nroots_found) {
+  return guarded([&] {
+    std::vector<cplx> om, cal;
+    std::vector<double> val;
+    map_grid(m, om);
+    cal.resize(om.size());
+    // the nr x ni serial loop of the reference becomes one batch on the GPU
+    int rc = alps_b200_disp_batch((int)om.size(), reinterpret_cast<const double*>(om.data()),
+                                  reinterpret_cast<double*>(cal.data()), nullptr);
+    if (rc) throw DispError{rc};
+    map_finish(m, om, cal, val, map_path, numroots, iroots, nroots_found);
+    map_export(om, cal, val, om_out, val_out, cal_out);
   });
+}
+
+// Multi-GPU map_search (omega sharding): every rank generates the grid, evaluates its slice of it
+// with alps_b200_disp_batch, the slices are gathered by the caller, and rank 0 (or every rank) finishes.
+int alps_b200_map_grid(const alps_b200_map* m, double* om_out) {
+  if (!m || !om_out || m->nr < 1 || m->ni < 1) return ALPS_B200_ERR_USAGE;
+  std::vector<cplx> om;
+  map_grid(m, om);
+  map_export(om, om, std::vector<double>(), om_out, nullptr, nullptr);
+  return 0;
+}
+
+int alps_b200_map_finish(const alps_b200_map* m, double* cal_io, const char* map_path, double* val_out,
+                         int numroots, int* iroots, int* nroots_found) {
+  if (!m || !cal_io || m->nr < 1 || m->ni < 1) return ALPS_B200_ERR_USAGE;
+  std::vector<cplx> om, cal((size_t)m->nr * m->ni);
+  std::vector<double> val;
+  map_grid(m, om);
+  for (size_t i = 0; i < cal.size(); i++) cal[i] = cplx(cal_io[2 * i], cal_io[2 * i + 1]);
+  map_finish(m, om, cal, val, map_path, numroots, iroots, nroots_found);
+  map_export(om, cal, val, nullptr, val_out, cal_io);
+  return 0;
 }
 
 int alps_b200_calc_eigen(const double om[2], int nspec, const double* ns, const double* qs,

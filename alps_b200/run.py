@@ -11,7 +11,12 @@ Analytic-continuation parameters: with --fit the twin of determine_param_fit (al
 Levenberg-Marquardt rows started from the &ffit blocks, Chebyshev series for ac_method = 2) runs like in
 the reference; without it they are the generator's ideal values when the tables are regenerated, else
 the initial values of the &ffit blocks.  NHDS calc_chi for use_bM species runs on the device
-(csrc/nhds_kernel.cu)."""
+(csrc/nhds_kernel.cu).
+
+Several GPUs of one box (replaces `mpirun -np N`): `python -m torch.distributed.run --nproc-per-node N
+--master-addr 127.0.0.1 -m alps_b200.run ...` -- one process per GPU; the nr x ni loop of map_search is sharded over
+the ranks (sharding.map_search_sharded, one NCCL all_gather of D), rank 0 alone writes the files and runs the
+sequential root refinement and k scans."""
 from __future__ import annotations
 
 import argparse
@@ -151,7 +156,17 @@ def main(argv=None):
         print(" Standard error of the estimate: %14.4E" % np.sqrt(q / (1.0 * pl.nspec * pl.nperp * pl.npar)))
     os.makedirs(a.out, exist_ok=True)
     prefix = os.path.join(a.out, runname)
-    sol = Solver(pl, emulate_nproc=a.nproc)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    shard = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        from . import sharding
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        shard = (rank, world, sharding.torch_all_gather())
+    sol = Solver(pl, emulate_nproc=a.nproc, device=local_rank if world > 1 else -1)
     try:
         kperp, kpar = float(s["kperp"]), float(s["kpar"])
         nmax = sol.set_k(kperp, kpar)
@@ -165,11 +180,14 @@ def main(argv=None):
             om, val, cal, roots = sol.map_search(float(m["omi"]), float(m["omf"]), float(m["gami"]), float(m["gamf"]),
                                                  int(m["nr"]), int(m["ni"]), bool(m.get("loggridw", False)),
                                                  bool(m.get("loggridg", False)),
-                                                 bool(s.get("determine_minima", True)), map_path=prefix + ".map")
+                                                 bool(s.get("determine_minima", True)), map_path=prefix + ".map",
+                                                 shard=shard)
             guesses = roots[:min(nroots, len(roots))] if bool(s.get("determine_minima", True)) else []
         else:
             guesses = [complex(float(nl["guess_%d" % i]["g_om"]), float(nl["guess_%d" % i]["g_gam"]))
                        for i in range(1, nroots + 1)]
+        if rank != 0:      # the root refinement and the k scans are sequential: rank 0 alone
+            return 0
         w, D = sol.refine_guess(guesses, opts, roots_path=prefix + ".roots") if guesses else (np.zeros(0, complex), None)
         for r, d in zip(w, D if D is not None else []):
             print("root %s  D=%s" % (r, d))
@@ -189,6 +207,9 @@ def main(argv=None):
             print("double scan done: %d x %d points" % rows.shape[:2])
     finally:
         sol.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
     return 0
 
 

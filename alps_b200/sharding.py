@@ -43,3 +43,54 @@ def gather_omega_shards(local: np.ndarray, n: int, rank: int, world: int, all_ga
         lo, hi = omega_shard(n, r, world)
         out[lo:hi] = parts[r][: hi - lo]
     return out
+
+
+def map_search_sharded(disp_batch: Callable, rank: int, world: int, all_gather: Callable, omi, omf, gami, gamf,
+                       nr: int, ni: int, loggridw=False, loggridg=False, determine_minima=True, numroots=100,
+                       map_path=None):
+    """map_search (src/ALPS_fns.f90:3595-3788) with its nr x ni loop of disp calls sharded over `world`
+    processes (one per GPU): every rank builds the grid (alps_b200_map_grid), evaluates its contiguous slice
+    with `disp_batch` (Solver.disp_batch), the slices are gathered with `all_gather`, and every rank runs the
+    rest of map_search (sentinels, find_minima; the .map file on rank 0) on the full D array
+    (alps_b200_map_finish).  Returns (om, val, cal, roots) like Solver.map_search."""
+    import ctypes as C
+
+    from . import _lib
+    L = _lib.lib()
+    m = _lib.MapCfg(omi, omf, gami, gamf, nr, ni, int(loggridw), int(loggridg), int(determine_minima))
+    n = nr * ni
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    om = np.zeros(n, dtype=np.complex128)
+    val = np.zeros(n)
+    iroots = np.zeros(2 * numroots, dtype=np.int32)
+    nfound = C.c_int(0)
+    _lib.check(L.alps_b200_map_grid(C.byref(m), p(om.view(np.float64))))
+    lo, hi = omega_shard(n, rank, world)
+    local = np.asarray(disp_batch(om[lo:hi]), dtype=np.complex128) if hi > lo else np.zeros(0, dtype=np.complex128)
+    cal = np.ascontiguousarray(gather_omega_shards(local, n, rank, world, all_gather))
+    path = map_path.encode() if (map_path and rank == 0) else None
+    _lib.check(L.alps_b200_map_finish(C.byref(m), p(cal.view(np.float64)), path, p(val), numroots, p(iroots),
+                                      C.byref(nfound)))
+    om, cal, val = (a.reshape((nr, ni), order="F") for a in (om, cal, val))
+    k = min(nfound.value, numroots)
+    ir = iroots[0:2 * k:2] - 1
+    ii = iroots[1:2 * k:2] - 1
+    return om, val, cal, [complex(om[a, b]) for a, b in zip(ir, ii)]
+
+
+def torch_all_gather(group=None) -> Callable:
+    """`all_gather` callable for gather_omega_shards / map_search_sharded over torch.distributed (NCCL on GPUs:
+    the padded slice goes through the current CUDA device; gloo: host tensors)."""
+    import torch
+    import torch.distributed as dist
+
+    def all_gather(pad: np.ndarray):
+        t = torch.from_numpy(pad.view(np.float64).copy())
+        nccl = dist.get_backend(group) == "nccl"
+        if nccl:
+            t = t.cuda()
+        outs = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(outs, t, group=group)
+        return [o.cpu().numpy().view(np.complex128) for o in outs]
+
+    return all_gather

@@ -165,7 +165,16 @@ class Solver:
         return w, D
 
     def map_search(self, omi, omf, gami, gamf, nr, ni, loggridw=False, loggridg=False,
-                   determine_minima=True, numroots=100, map_path=None):   # src/ALPS_fns.f90:3595-3788
+                   determine_minima=True, numroots=100, map_path=None, shard=None):   # src/ALPS_fns.f90:3595-3788
+        """shard = (rank, world, all_gather): omega sharding over one process per GPU (sharding.py) -- this
+        rank evaluates its contiguous slice of the nr x ni grid, `all_gather(padded_slice)` returns every rank's
+        slice (torch.distributed.all_gather semantics), every rank finishes the map; only rank 0 writes
+        map_path.  The gathered map is bitwise the single-GPU map (batch classes)."""
+        if shard is not None:
+            from . import sharding
+            rank, world, all_gather = shard
+            return sharding.map_search_sharded(self.disp_batch, rank, world, all_gather, omi, omf, gami, gamf, nr, ni,
+                                               loggridw, loggridg, determine_minima, numroots, map_path)
         m = _lib.MapCfg(omi, omf, gami, gamf, nr, ni, int(loggridw), int(loggridg), int(determine_minima))
         n = nr * ni
         om = np.zeros(n, dtype=np.complex128)

@@ -117,7 +117,7 @@ def cpu_sample(w, plasma, om, ncap=None, threads=0):
     orc = Oracle(plasma, nproc=0, threads=cores, nmax_force=w["nmax_force"])
     nmax = orc.set_k(w["kperp"], w["kpar"])
     if ncap is None:
-        ncap = 3
+        ncap = 48      # ~10-20 s of CPU work per sample on 16 cores at C5 (|n| <= 3 took 0.9 s)
     ncap = int(min(ncap, min(nmax)))
     orc.set_ncap(ncap)
     t0 = time.perf_counter()

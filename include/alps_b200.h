@@ -178,6 +178,16 @@ int alps_b200_refine_guess(int nroots, double *wroots, const alps_b200_solver_op
  * writes <runname>.map (5es16.6e3).  om/cal: nr*ni complex (ir fastest), val: nr*ni, iroots(2,numroots) */
 int alps_b200_map_search(const alps_b200_map *m, const char *map_path, double *om_out, double *val_out,
                          double *cal_out, int numroots, int *iroots, int *nroots_found);
+/* Multi-GPU map_search (omega sharding: replaces the MPI harmonic split for maps).  Host-only
+ * halves of alps_b200_map_search so that the nr x ni grid can be evaluated in slices by several processes
+ * (one per GPU, alps_b200_disp_batch on each slice, slices gathered by the caller -- NCCL / torch.distributed):
+ *   alps_b200_map_grid    the omega grid of :3684-3712, nr*ni complex, ir fastest;
+ *   alps_b200_map_finish  everything after the loop of disp calls (:3722-3786) on the gathered D: cal_io
+ *                         (nr*ni complex, D in, D with the NaN / infinity sentinels out), val = log10|D|,
+ *                         the .map file (map_path may be NULL) and find_minima. */
+int alps_b200_map_grid(const alps_b200_map *m, double *om_out);
+int alps_b200_map_finish(const alps_b200_map *m, double *cal_io, const char *map_path, double *val_out,
+                         int numroots, int *iroots, int *nroots_found);
 /* replaces: calc_eigen (:2605-2899).  current_int(nspec) from derivative_f0 (may be NULL = 0).
  * Outputs: ef(3), bf(3), Us(3,nspec), ds(nspec) complex; Ps(nspec), Ps_split(4,nspec), W_EM real. */
 int alps_b200_calc_eigen(const double om[2], int nspec, const double *ns, const double *qs,

@@ -32,6 +32,15 @@ def all_gather(pad):
     return [o.cpu().numpy().view(np.complex128) for o in outs]
 D1 = sharding.gather_omega_shards(local, n, rank, world, all_gather)
 ok1 = np.array_equal(D1, D_full)
+# (ib) map_search sharded over the ranks (alps_b200_map_grid / disp_batch slices / all_gather / alps_b200_map_finish)
+# against the single-process alps_b200_map_search on this rank's GPU: same D, same val, same minima
+margs = (0.05, 2.0, -0.03, 0.03, 40, 32)
+om_s, val_s, cal_s, roots_s = sol.map_search(*margs, shard=(rank, world, sharding.torch_all_gather()))
+om_1, val_1, cal_1, roots_1 = sol.map_search(*margs)
+ok_map = (np.array_equal(om_s, om_1) and np.array_equal(cal_s, cal_1) and np.array_equal(val_s, val_1)
+          and roots_s == roots_1)
+print("rank %d/%d sharded map_search identical=%s minima=%d" % (rank, world, ok_map, len(roots_1)), flush=True)
+assert ok_map
 # (ii) harmonic sharding + NCCL all_reduce of the partials
 sol.set_harmonic_shard(rank, world); sol.set_k(kperp, kpar)
 L = sol.chi_partial_len()

@@ -1,6 +1,6 @@
 """The reference's own golden files reproduced through the CUDA path and the C++ twin drivers:
 refine_guess + k_par scan (secant_osc) with eigenfunctions and heating for tests/test_kpar_fast.in
-(goldens: tests/test_kpar_fast.{scan,eigen,heat}_kpara_1.root_1, 5 significant digits)."""
+(goldens: tests/test_kpar_fast.{scan,eigen,heat,heat_mech}_kpara_1.root_1, 5 significant digits)."""
 import os
 
 import numpy as np
@@ -32,7 +32,7 @@ def test_kpar_fast_scan_eigen_heat_files(tmp_path):
     finally:
         sol.close()
     assert rows.shape == (33, 1, 4)
-    for kind, rtol in (("scan", 0.0), ("eigen", 2e-4), ("heat", 2e-4)):
+    for kind, rtol in (("scan", 0.0), ("eigen", 2e-4), ("heat", 2e-4), ("heat_mech", 2e-4)):
         ours = _rows(prefix + ".%s_kpara_1.root_1" % kind)
         gold = _rows(os.path.join(GOLD, "test_kpar_fast.%s_kpara_1.root_1" % kind))
         assert len(ours) == len(gold) == 33, kind
