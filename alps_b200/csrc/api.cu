@@ -19,6 +19,8 @@
 
 using namespace alps;
 
+bool alps::g_pdl_launch = false;
+
 namespace {
 
 struct SpeciesHost {
@@ -74,6 +76,10 @@ struct State {
   long long disp_graph_launches = 0;
   int disp_plain_calls = 0;      // plain calls since the signature last changed (the first one warms up)
   bool capturing = false, graph_off = false, omega_major = false;
+  bool pdl_on = false;                // programmatic dependent launches inside the single-omega graph
+  bool fuse_off = false;              // k_chi_partial + k_assemble as two launches for every batch size
+  bool zc = false, zc_off = false;   // zero-copy chain while capturing: omega read from / D and the error words written to
+                                     // pinned host memory by the first / last kernel (no memcpy or memset nodes)
   double* d_respart = nullptr;   // k_resonant_lat partial rows (small batches)
   int* d_restick = nullptr;
   double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
@@ -302,6 +308,9 @@ int build_hoisted_tables() {
 }
 
 constexpr int SMALL_BATCH = 64;
+// defaults of the latency knobs (ALPS_B200_ZC / _FUSE / _PDL): zero-copy graph chain, fused harmonic-sum +
+// determinant kernel, programmatic dependent launches inside the graph
+constexpr bool LAT_DEFAULT_ZC = false, LAT_DEFAULT_FUSE = false, LAT_DEFAULT_PDL = false;
 constexpr int LAT_VARIANT = 20, LAT_BN = 32, LAT_NPAR_MAX = 1024, LAT_BATCH = 8;
 bool use_lat(int n) { return S.have_lat && S.mode == 0 && n <= LAT_BATCH; }
 // p_par split of the quadrature kernel for n <= SMALL_BATCH omegas; a function of the configuration and of
@@ -437,7 +446,8 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
               bool want_aux) {
   const GlobalDev* gd = S.gd;
   if (!d_partial_in) {
-    launch_plan(gd, S.gh, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream);
+    launch_plan(gd, S.gh, S.zc ? S.h_pin : d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream,
+                S.zc ? S.d_om : nullptr);
     S.P.om = d_om;
     S.P.n_om = n;
     // few omegas in flight (sequential root finding, batched roots): spread each (omega, tile) over
@@ -477,6 +487,18 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       S.launches += 1;
     }
     double* part = d_partial_out ? d_partial_out : S.d_partial;
+    if (!d_partial_out && n <= SMALL_BATCH && !S.fuse_off) {
+      // small batches: harmonic sums and the determinant in one launch (bitwise the two-kernel result)
+      const double* d_ext = nullptr;
+      int rc = prepare_external(n, d_om, &d_ext);
+      if (rc) return rc;
+      launch_chi_assemble(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, part, d_ext,
+                          S.zc ? S.h_pin + 2 : d_D, want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr,
+                          want_aux ? S.d_wave : nullptr, S.stream, S.zc ? S.d_err : nullptr,
+                          S.zc ? reinterpret_cast<int*>(S.h_pin + 8) : nullptr);
+      S.launches += 4;
+      return 0;
+    }
     launch_chi_partial(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, part, S.stream);
     S.launches += 4;
     if (d_partial_out) return 0;
@@ -487,9 +509,9 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     int rc = prepare_external(n, d_om, &d_ext);
     if (rc) return rc;
   }
-  launch_assemble(gd, S.gh, d_om, n, d_partial_in, d_ext, d_D,
+  launch_assemble(gd, S.gh, d_om, n, d_partial_in, d_ext, S.zc ? S.h_pin + 2 : d_D,
                   want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr, want_aux ? S.d_wave : nullptr,
-                  S.stream);
+                  S.stream, S.zc ? S.d_err : nullptr, S.zc ? reinterpret_cast<int*>(S.h_pin + 8) : nullptr);
   S.launches += 1;
   return 0;
 }
@@ -566,6 +588,14 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.mode = 0;
   {
     S.graph_off = getenv("ALPS_B200_NO_GRAPH") != nullptr;   // plain launches for alps_b200_disp
+    // latency knobs of the single-omega chain (A/B and tests; "0" / "1"), defaults below
+    auto knob = [](const char* name, bool dflt) {
+      const char* v = getenv(name);
+      return v ? v[0] != '0' : dflt;
+    };
+    S.pdl_on = knob("ALPS_B200_PDL", LAT_DEFAULT_PDL);
+    S.fuse_off = !knob("ALPS_B200_FUSE", LAT_DEFAULT_FUSE);
+    S.zc_off = !knob("ALPS_B200_ZC", LAT_DEFAULT_ZC);
     S.omega_major = getenv("ALPS_B200_OMEGA_MAJOR") != nullptr;   // A/B knob: previous block order of k_quad_mma
     const char* v = getenv("ALPS_B200_QUAD_VARIANT");   // tuning knob: tile shape of k_quad
     S.qv = quad_variant(v ? atoi(v) : 15);
@@ -1108,7 +1138,7 @@ static void disp_signature(std::vector<unsigned char>& sig) {
                         S.d_gwin, S.d_partial, S.d_err, S.d_rtiles, S.d_fitems, S.d_respart, S.d_restick,
                         S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
   const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)S.rtiles.size(), (long long)S.fitems.size(), S.mode,
-                            S.qv.id, nsplit_rel(), (long long)S.bm_any};
+                            S.qv.id, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off, (long long)S.pdl_on};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
   memcpy(sig.data(), &P, sizeof(P));
   memcpy(sig.data() + sizeof(P), ptrs, sizeof(ptrs));
@@ -1134,11 +1164,17 @@ static int disp_via_graph(int* used) {
       return 0;
     }
     S.capturing = true;
+    S.zc = !S.zc_off && plan_fused_ok(S.gh, 1);
+    g_pdl_launch = S.pdl_on && S.zc;
     const long long l0 = S.launches;
-    cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream);
+    if (!S.zc) cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream);
     const int rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, false);
-    cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream);
-    cudaMemcpyAsync(S.h_pin + 8, S.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream);
+    if (!S.zc) {
+      cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream);
+      cudaMemcpyAsync(S.h_pin + 8, S.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream);
+    }
+    S.zc = false;
+    g_pdl_launch = false;
     S.capturing = false;
     S.disp_graph_launches = S.launches - l0;
     S.launches = l0;

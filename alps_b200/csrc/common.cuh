@@ -134,6 +134,12 @@ __device__ __forceinline__ double range_w(int ipar, int lo, int hi) {
   return (ipar == lo ? 1.0 : 0.0) + (ipar == hi ? 1.0 : 0.0) + ((ipar > lo && ipar < hi) ? 2.0 : 0.0);
 }
 
+// Programmatic dependent launch (single-omega graph, api.cu): a kernel launched with the programmatic-serialisation
+// attribute may start while its predecessor still runs; pdl_wait() blocks until the predecessor grid has completed
+// and its writes are visible, pdl_trigger() lets the successor grid be scheduled.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 1/x for normal, finite x: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps; avoids the
 // IEEE-division slow path.  Relative error ~1e-16, far inside the 1e-9 parity budget.
 __device__ __forceinline__ double fast_rcp(double x) {

@@ -37,6 +37,25 @@ struct QuadParams {
 };
 constexpr int MMA_NH = 16;   // harmonics per CTA tile of the DMMA variants
 
+// set by api.cu while it captures the single-omega chain: kernels after the first are launched with the
+// programmatic-serialisation attribute (they call pdl_wait() before touching their predecessor's output)
+extern bool g_pdl_launch;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_launch ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // set-up (setup_kernels.cu)
 void launch_derivative_f0(const double* f0, const double* pp, double* df0, int nspec, int nperp, int npar,
                           cudaStream_t st);
@@ -69,8 +88,12 @@ QuadVariant quad_variant(int id);
 cudaError_t launch_quad(const QuadParams& P, int variant, bool store, cudaStream_t st);
 cudaError_t launch_quad_mma(const QuadParams& P, int variant, bool store, cudaStream_t st);   // variants >= 9
 double run_dmma_peak(cudaStream_t st);
+// om_stage != nullptr: fused single-block variant (needs plan_fused_ok): om may be pinned host memory, the block
+// copies it to om_stage (device) and resets work_count itself
+constexpr int PLAN_FUSED_MAX_OM = 8;
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
-                 int* work, int* work_count, cudaStream_t st);
+                 int* work, int* work_count, cudaStream_t st, double* om_stage = nullptr);
+bool plan_fused_ok(const GlobalDev& gh, int n_om);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
                      int* tickets, cudaStream_t st);
@@ -81,7 +104,12 @@ void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* o
                         const double* Sbulk, int nsplit, const double* Sres, double* partial, cudaStream_t st);
 void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
                      const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
-                     cudaStream_t st);
+                     cudaStream_t st, const int* err_src = nullptr, int* err_dst = nullptr);
+// both in one launch for small batches (one block per omega, one warp per species; bitwise the two-kernel result)
+void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
+                         const double* Sbulk, int nsplit, const double* Sres, double* partial, const double* ext_chi,
+                         double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
+                         const int* err_src = nullptr, int* err_dst = nullptr);
 struct FastItem {
   int s;
   int nabs;

@@ -98,16 +98,6 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (!STORE && threadIdx.x < 2 * MMA_NH) {
-    const int nabs = tile.n0 + (threadIdx.x >> 1), sg = threadIdx.x & 1;
-    PlanEntry pe;
-    pe.lo1 = 1; pe.hi1 = 0; pe.lo2 = 1; pe.hi2 = 0; pe.flags = 0; pe.ipar_res = 0; pe.upperlimit = 0; pe.pad = 0;
-    if (nabs <= sp.nhi_shard && nabs >= sp.nlo_shard && !(nabs == 0 && sg == 1))
-      pe = P.plan[(size_t)iom * g.NI + sp.item_base + 2 * nabs + sg];
-    sm.plan[threadIdx.x >> 1][sg] = pe;
-  }
-  __syncthreads();
-
   const double* __restrict__ gA = P.Af[tile.s];
   const double* __restrict__ gC = P.Cf[tile.s];
   const double* __restrict__ gW = P.Wf[tile.s] + (size_t)(tile.n0 / MMA_NH) * NKS * KS_W;
@@ -122,6 +112,20 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
   };
   if (threadIdx.x == 0 && DBG != 3)
     for (int it = 0; it < NST - 1 && it < T; it++) issue(it);
+
+  // single-omega chain: launched while k_plan still runs; the barrier set-up and the first table stages above do not depend
+  // on it, the resonance plan and omega do
+  pdl_trigger();
+  pdl_wait();
+  if (!STORE && threadIdx.x < 2 * MMA_NH) {
+    const int nabs = tile.n0 + (threadIdx.x >> 1), sg = threadIdx.x & 1;
+    PlanEntry pe;
+    pe.lo1 = 1; pe.hi1 = 0; pe.lo2 = 1; pe.hi2 = 0; pe.flags = 0; pe.ipar_res = 0; pe.upperlimit = 0; pe.pad = 0;
+    if (nabs <= sp.nhi_shard && nabs >= sp.nlo_shard && !(nabs == 0 && sg == 1))
+      pe = P.plan[(size_t)iom * g.NI + sp.item_base + 2 * nabs + sg];
+    sm.plan[threadIdx.x >> 1][sg] = pe;
+  }
+  __syncthreads();
 
   const double omr = P.om[2 * iom], omi = P.om[2 * iom + 1];
   const double qs = sp.qs, ms = sp.ms, kpar = g.kpar;
@@ -345,8 +349,8 @@ static cudaError_t launch_mma_one(const QuadParams& P, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_quad_mma<NW, HS, KSTG, NST, STORE, DBG><<<P.n_om * P.ntiles * P.nsplit, 32 * NW * HS, smem, st>>>(P);
-  return cudaGetLastError();
+  return launch_chain(k_quad_mma<NW, HS, KSTG, NST, STORE, DBG>, dim3(P.n_om * P.ntiles * P.nsplit), dim3(32 * NW * HS),
+                      smem, st, P);
 }
 template <int NW, int HS, int KSTG, int NST>
 static cudaError_t launch_mma_variant(const QuadParams& P, bool store, cudaStream_t st) {

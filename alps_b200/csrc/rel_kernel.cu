@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
                                                      double* __restrict__ Mrel, int* __restrict__ err_flag, int nsplit,
                                                      double* __restrict__ Mpart, int* __restrict__ tickets) {
   const GlobalDev& g = *gp;
+  pdl_trigger();
+  pdl_wait();
   const int js = blockIdx.x % nsplit;
   const int iom = (blockIdx.x / nsplit) / ntiles;
   const int tile_id = (blockIdx.x / nsplit) % ntiles;
@@ -711,11 +713,11 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
   if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
   static const char* force = getenv("ALPS_B200_REL_MINB");   // A/B knob: "1" = 255-register variant always
   if (nsplit > 1 || n_om * ntiles <= 2 * 148 || (force && force[0] == '1'))
-    k_rel<1><<<n_om * ntiles * nsplit, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, nsplit,
-                                                             Mpart, tickets);
+    launch_chain(k_rel<1>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
+                 err_flag, nsplit, Mpart, tickets);
   else
-    k_rel<2><<<n_om * ntiles * nsplit, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, nsplit,
-                                                             Mpart, tickets);
+    launch_chain(k_rel<2>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
+                 err_flag, nsplit, Mpart, tickets);
 }
 void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, int npb, double zfac, int nmaxord,
                              double* Jrel, cudaStream_t st) {

@@ -114,9 +114,27 @@ __device__ __forceinline__ void decode_item(const GlobalDev& g, int it, int& s, 
   sg = r & 1;
 }
 
-__global__ void k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om,
-                       PlanEntry* __restrict__ plan, int* __restrict__ work, int* __restrict__ work_count) {
+// FUSED (single-block launches of the single-omega graph, api.cu): the block resets the work counter itself and
+// stages the omegas -- read from pinned host memory -- into om_stage for the kernels downstream, so the chain
+// needs neither a memset nor a host-to-device copy node.
+template <bool FUSED>
+__global__ void __launch_bounds__(FUSED ? 1024 : 256)
+k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n_om, PlanEntry* __restrict__ plan,
+       int* __restrict__ work, int* __restrict__ work_count, double* __restrict__ om_stage) {
   const GlobalDev& g = *gp;
+  __shared__ double s_om[FUSED ? 2 * PLAN_FUSED_MAX_OM : 2];
+  const double* om = om_in;
+  if (FUSED) {
+    pdl_trigger();
+    if (threadIdx.x < 2 * n_om) {
+      const double v = om_in[threadIdx.x];
+      s_om[threadIdx.x] = v;
+      om_stage[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) *work_count = 0;
+    __syncthreads();
+    om = s_om;
+  }
   size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= (size_t)n_om * g.NI) return;
   int iom = (int)(idx / g.NI), it = (int)(idx % g.NI), s, nabs, sg;
@@ -483,6 +501,8 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
   __shared__ cd s_part[LAT_THREADS / 32][6];
   __shared__ cd s_f[3][2];   // analytic branch: g(p_R + dp), g(p_R - dp), g(p_R) for this block's two combinations
   __shared__ int s_err, s_last;
+  pdl_trigger();
+  pdl_wait();
   const int nwork = *work_count;
   for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
     const size_t idx = (size_t)work[wi];
@@ -705,15 +725,11 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
 // sums, summed over the harmonics of this process' shard.
 // partial[(iom*nspec + s)*PARTIAL_PER_SPEC + 2*c .. ]: c = mode-1 (0..5) for chi,
 // c = 6 + 3*(mode-1) + (m+1) for chi_low(mode, m), m = -1,0,1.
-__global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
-                                                     int n_om, const PlanEntry* __restrict__ plan,
-                                                     const double* __restrict__ Sbulk, int nsplit,
-                                                     const double* __restrict__ Sres, double* __restrict__ partial) {
-  const GlobalDev& g = *gp;
-  const int lane = threadIdx.x & 31;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= n_om * g.nspec) return;
-  const int iom = w / g.nspec, s = w % g.nspec;
+// one warp: the partial row of (omega iom, species s)
+__device__ __forceinline__ void chi_partial_warp(const GlobalDev& g, int iom, int s, int lane,
+                                                 const PlanEntry* __restrict__ plan, const double* __restrict__ Sbulk,
+                                                 int nsplit, const double* __restrict__ Sres, double* partial) {
+  const int w = iom * g.nspec + s;
   const SpeciesDev& sp = g.sp[s];
   cd chi[6], low[6][3];
 #pragma unroll
@@ -803,15 +819,23 @@ __global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict
   }
 }
 
+__global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
+                                                     int n_om, const PlanEntry* __restrict__ plan,
+                                                     const double* __restrict__ Sbulk, int nsplit,
+                                                     const double* __restrict__ Sres, double* __restrict__ partial) {
+  (void)om;
+  const GlobalDev& g = *gp;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_om * g.nspec) return;
+  chi_partial_warp(g, w / g.nspec, w % g.nspec, threadIdx.x & 31, plan, Sbulk, nsplit, Sres, partial);
+}
+
 // -------------------------------------------------------------------- assemble
 // One thread per omega: src/ALPS_fns.f90:536-624.
-__global__ void k_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om,
-                           const double* __restrict__ partial, const double* __restrict__ ext_chi,
-                           double* __restrict__ D, double* __restrict__ chi0_out, double* __restrict__ chi0_low_out,
-                           double* __restrict__ wave_out) {
-  const GlobalDev& g = *gp;
-  const int iom = blockIdx.x * blockDim.x + threadIdx.x;
-  if (iom >= n_om) return;
+__device__ __forceinline__ void assemble_one(const GlobalDev& g, const double* __restrict__ om, int iom,
+                                             const double* partial, const double* __restrict__ ext_chi,
+                                             double* __restrict__ D, double* __restrict__ chi0_out,
+                                             double* __restrict__ chi0_low_out, double* __restrict__ wave_out) {
   const int nspec = g.nspec;
   const cd omc = mk(om[2 * iom], om[2 * iom + 1]);
   const double kperp = g.kperp, kpar = g.kpar, vA = g.vA;
@@ -895,21 +919,58 @@ __global__ void k_assemble(const GlobalDev* __restrict__ gp, const double* __res
   }
 }
 
+__global__ void k_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om,
+                           const double* __restrict__ partial, const double* __restrict__ ext_chi,
+                           double* __restrict__ D, double* __restrict__ chi0_out, double* __restrict__ chi0_low_out,
+                           double* __restrict__ wave_out, const int* __restrict__ err_src, int* __restrict__ err_dst) {
+  const int iom = blockIdx.x * blockDim.x + threadIdx.x;
+  // single-omega graph (api.cu): D and err_dst are pinned host memory, so the chain needs no device-to-host copies
+  if (err_dst && iom < 8) err_dst[iom] = err_src[iom];
+  if (iom >= n_om) return;
+  assemble_one(*gp, om, iom, partial, ext_chi, D, chi0_out, chi0_low_out, wave_out);
+}
+
+// k_chi_partial + k_assemble of a small batch in one launch (the single-omega graph and batched roots): block =
+// one omega, warp s = species s; the partial rows go through global memory exactly as between the two kernels
+// (same code, same order of operations: bitwise the two-kernel result), thread 0 assembles after the barrier.
+__global__ void __launch_bounds__(32 * MAXSPEC)
+k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, const PlanEntry* __restrict__ plan,
+               const double* __restrict__ Sbulk, int nsplit, const double* __restrict__ Sres, double* partial,
+               const double* __restrict__ ext_chi, double* __restrict__ D, double* __restrict__ chi0_out,
+               double* __restrict__ chi0_low_out, double* __restrict__ wave_out, const int* __restrict__ err_src,
+               int* __restrict__ err_dst) {
+  const GlobalDev& g = *gp;
+  const int iom = blockIdx.x, s = threadIdx.x >> 5;
+  pdl_trigger();
+  pdl_wait();
+  if (s < g.nspec) chi_partial_warp(g, iom, s, threadIdx.x & 31, plan, Sbulk, nsplit, Sres, partial);
+  if (err_dst && iom == 0 && threadIdx.x >= 32 && threadIdx.x < 40) err_dst[threadIdx.x - 32] = err_src[threadIdx.x - 32];
+  __syncthreads();
+  if (threadIdx.x == 0) assemble_one(g, om, iom, partial, ext_chi, D, chi0_out, chi0_low_out, wave_out);
+}
+
 // ------------------------------------------------------------------ launchers
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan, int* work,
-                 int* work_count, cudaStream_t st) {
-  cudaMemsetAsync(work_count, 0, sizeof(int), st);
+                 int* work_count, cudaStream_t st, double* om_stage) {
   size_t total = (size_t)n_om * gh.NI;
+  if (om_stage) {   // fused single-block variant: caller checked plan_fused_ok()
+    k_plan<true><<<1, 1024, 0, st>>>(g, om, n_om, plan, work, work_count, om_stage);
+    return;
+  }
+  cudaMemsetAsync(work_count, 0, sizeof(int), st);
   if (!total) return;
-  k_plan<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, om, n_om, plan, work, work_count);
+  k_plan<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, om, n_om, plan, work, work_count, nullptr);
+}
+bool plan_fused_ok(const GlobalDev& gh, int n_om) {
+  return n_om >= 1 && n_om <= PLAN_FUSED_MAX_OM && (size_t)n_om * gh.NI <= 1024;
 }
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
                      int* tickets, cudaStream_t st) {
   if (n_om <= 0) return;
   if (n_om <= 64 && Spart && tickets)
-    k_resonant_lat<<<dim3(148, LAT_PARTS), LAT_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag,
-                                                                 Spart, tickets);
+    launch_chain(k_resonant_lat, dim3(148, LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan, work, work_count, gwin, Sres,
+                 err_flag, Spart, tickets);
   else
     k_resonant<<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
 }
@@ -921,10 +982,19 @@ void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* o
 }
 void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
                      const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
-                     cudaStream_t st) {
+                     cudaStream_t st, const int* err_src, int* err_dst) {
   (void)gh;
   if (n_om <= 0) return;
-  k_assemble<<<(n_om + 127) / 128, 128, 0, st>>>(g, om, n_om, partial, ext_chi, D, chi0, chi0_low, wave);
+  k_assemble<<<(n_om + 127) / 128, 128, 0, st>>>(g, om, n_om, partial, ext_chi, D, chi0, chi0_low, wave, err_src,
+                                                 err_dst);
+}
+void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
+                         const double* Sbulk, int nsplit, const double* Sres, double* partial, const double* ext_chi,
+                         double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st, const int* err_src,
+                         int* err_dst) {
+  if (n_om <= 0) return;
+  launch_chain(k_chi_assemble, dim3(n_om), dim3(32 * ((gh.nspec + 1) & ~1)), 0, st, g, om, plan, Sbulk, nsplit, Sres,
+               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst);
 }
 
 }  // namespace alps

@@ -455,3 +455,45 @@ def test_quadrature_variants_and_batch_classes_agree(monkeypatch):
             assert np.max(np.abs(got - ref[:4]) / np.abs(ref[:4])) < 1e-9, kp
     finally:
         sol.close()
+
+
+KNOBS = ("ALPS_B200_ZC", "ALPS_B200_FUSE", "ALPS_B200_PDL")
+
+
+def test_single_omega_graph_knobs_are_bitwise_neutral(monkeypatch):
+    """The latency chain of alps_b200_disp -- fused plan kernel reading omega from pinned host memory, fused
+    harmonic-sum + determinant kernel writing D and the error words to pinned host memory -- against the plain
+    chain (H2D / memset / D2H nodes, k_chi_partial and k_assemble as two launches): bitwise the same D, chi0,
+    chi0_low and wave, for table species, a use_bM species and a relativistic pair plasma."""
+    from alps_b200.solver import Solver
+    cases = [(tables.config_kpar_fast(), dict(emulate_nproc=4), (1e-2, 2e-2),
+              list(omega_samples(5, 12, (5e-3, 0.4), (-2e-3, 2e-3))) + [2e-2 + 0j]),
+             (tables.config_bimax(60, 120), {}, (1.0e-3, 0.03),
+              [3.0e-2 - 1.0e-5j, 4.5e-2 - 1.9e-2j, 0.1 + 0.002j, 0.05 + 0.0j]),
+             (tables.config_relativistic(nperp=20, npar=40, ngamma=60, npparbar=80), {}, (1.0e-3, 1.0e-1),
+              [6.2713e-2 - 4.662e-8j, 1.0 - 1.655e-6j, 0.5 + 0.01j, 0.3 - 0.02j, 2.5 + 0.0j, 0.9 + 1e-3j])]
+    for icase, (pl, kw, k, oms) in enumerate(cases):
+        out = {}
+        for tag, env in (("fused", "110"), ("plain", "000"), ("pdl", "111")):
+            for name, v in zip(KNOBS, env):
+                monkeypatch.setenv(name, v)
+            sol = Solver(pl, **kw)
+            try:
+                sol.set_k(*k)
+                singles = np.array([sol.disp(complex(o)) for o in oms])      # graph replay from the 2nd call on
+                again = np.array([sol.disp(complex(o)) for o in oms])
+                assert np.array_equal(singles, again)
+                full = [sol.disp(complex(o), full=True) for o in oms[:3]]
+                batch = sol.disp_batch(np.array(oms[:8]))
+                out[tag] = (singles, full, batch)
+            finally:
+                sol.close()
+        assert np.array_equal(out["fused"][0], out["plain"][0])
+        assert np.array_equal(out["fused"][0], out["pdl"][0])       # programmatic dependent launches in the graph
+        assert np.array_equal(out["fused"][2], out["plain"][2])
+        if icase == 0:
+            assert np.array_equal(out["fused"][0][:8], out["fused"][2])      # disp() and a small disp_batch(): same class
+        for a, b in zip(out["fused"][1], out["plain"][1]):
+            assert a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
+    for name in KNOBS:
+        monkeypatch.delenv(name, raising=False)
