@@ -310,7 +310,7 @@ int build_hoisted_tables() {
 constexpr int SMALL_BATCH = 64;
 // defaults of the latency knobs (ALPS_B200_ZC / _FUSE / _PDL): zero-copy graph chain, fused harmonic-sum +
 // determinant kernel, programmatic dependent launches inside the graph
-constexpr bool LAT_DEFAULT_ZC = false, LAT_DEFAULT_FUSE = false, LAT_DEFAULT_PDL = false;
+constexpr bool LAT_DEFAULT_ZC = true, LAT_DEFAULT_FUSE = true, LAT_DEFAULT_PDL = false;
 constexpr int LAT_VARIANT = 20, LAT_BN = 32, LAT_NPAR_MAX = 1024, LAT_BATCH = 8;
 bool use_lat(int n) { return S.have_lat && S.mode == 0 && n <= LAT_BATCH; }
 // p_par split of the quadrature kernel for n <= SMALL_BATCH omegas; a function of the configuration and of

@@ -173,11 +173,12 @@ k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n
   // integrate_res: the step left of the resonance, ipar in [1,npar-2]
   int ipar_res = 0;
   if (pr >= ppar[1] && pr < ppar[npar - 1]) {
-    int lo = 1, hi = npar - 2;   // largest ipar with ppar[ipar] <= pr
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (ppar[mid] <= pr) lo = mid; else hi = mid - 1;
-    }
+    // largest ipar in [1, npar-2] with ppar[ipar] <= pr: index guess on the (uniform) grid, corrected with the
+    // actual node values -- the same index a search over the nodes finds, without its chain of dependent loads
+    int lo = (int)floor((pr - ppar[1]) / dppar) + 1;
+    lo = min(max(lo, 1), npar - 2);
+    while (lo > 1 && ppar[lo] > pr) lo--;
+    while (lo < npar - 2 && ppar[lo + 1] <= pr) lo++;
     if (ppar[lo + 1] > pr && ppar[lo] <= pr) ipar_res = lo;
   }
   for (int ipar = 0; ipar <= M_I; ipar++) {
@@ -759,10 +760,23 @@ __device__ __forceinline__ void chi_partial_warp(const GlobalDev& g, int iom, in
         cd S[6];
 #pragma unroll
         for (int q = 0; q < 6; q++) S[q] = mk(0.0, 0.0);
-        for (int j = 0; j < nsplit; j++) {   // partial rows of the p_par splits of k_quad
-          const double* sb = Sbulk + (idx * nsplit + j) * 12;
+        // partial rows of the p_par splits of k_quad, added in order; four rows are fetched before they are
+        // added so that a row costs one L2 round trip per four instead of one each (latency chain)
+        for (int j0 = 0; j0 < nsplit; j0 += 4) {
+          double2 row[4][6];
 #pragma unroll
-          for (int q = 0; q < 6; q++) S[q] += mk(sb[2 * q], sb[2 * q + 1]);
+          for (int u = 0; u < 4; u++)
+            if (j0 + u < nsplit) {
+              const double2* sb = reinterpret_cast<const double2*>(Sbulk + (idx * nsplit + j0 + u) * 12);
+#pragma unroll
+              for (int q = 0; q < 6; q++) row[u][q] = sb[q];
+            }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (j0 + u < nsplit) {
+#pragma unroll
+              for (int q = 0; q < 6; q++) S[q] += mk(row[u][q].x, row[u][q].y);
+            }
         }
 #pragma unroll
         for (int q = 0; q < 6; q++) S[q] = cbulk * S[q];
@@ -969,7 +983,8 @@ void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanE
                      int* tickets, cudaStream_t st) {
   if (n_om <= 0) return;
   if (n_om <= 64 && Spart && tickets)
-    launch_chain(k_resonant_lat, dim3(148, LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan, work, work_count, gwin, Sres,
+    // work items (resonant harmonics) are few per omega -- typically n = 0 only; the blocks loop over the list
+    launch_chain(k_resonant_lat, dim3(n_om < 10 ? 16 * n_om : 148, LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan, work, work_count, gwin, Sres,
                  err_flag, Spart, tickets);
   else
     k_resonant<<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
