@@ -20,11 +20,11 @@ SYMBOLS = [
     "alps_b200_get_info", "alps_b200_dfma_peak", "alps_b200_emulate_split",
     "alps_b200_secant", "alps_b200_secant_osc", "alps_b200_rtsec", "alps_b200_refine_guess",
     "alps_b200_map_search", "alps_b200_map_grid", "alps_b200_map_finish", "alps_b200_calc_eigen", "alps_b200_scan_setup", "alps_b200_om_scan",
-    "alps_b200_om_double_scan", "alps_b200_set_root_batching",
+    "alps_b200_om_double_scan", "alps_b200_set_root_batching", "alps_b200_tps_eval",
 ]
 
 INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH, INFO_DFMA_NOREUSE, \
-    INFO_DMMA_PEAK, INFO_QUAD_VARIANT = range(8)
+    INFO_DMMA_PEAK, INFO_QUAD_VARIANT, INFO_D_EVALS, INFO_SET_K_CALLS = range(10)
 
 
 class Cfg(C.Structure):
@@ -113,6 +113,7 @@ def lib():
                                         C.c_char_p, C.c_int, V]
         L.alps_b200_om_double_scan.argtypes = [V, V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V, C.c_char_p, V]
         L.alps_b200_set_root_batching.argtypes = [C.c_int]
+        L.alps_b200_tps_eval.argtypes = [C.c_int, V, V, V, C.c_int, V, V, V]
         _LIB = L
     return _LIB
 

@@ -107,7 +107,7 @@ struct State {
   int mode = 0;
   QuadVariant qv{8, 16, 32, 2};
   int shard_rank = 0, shard_n = 1;
-  long long launches = 0;
+  long long launches = 0, d_evals = 0, set_k_calls = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_kernel_ms = 0.0;
   double *h_pin = nullptr;   // pinned staging for host <-> device omega / D traffic
@@ -445,6 +445,7 @@ int prepare_external(int n, const double* d_om, const double** d_ext_out) {
 int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, const double* d_partial_in,
               bool want_aux) {
   const GlobalDev* gd = S.gd;
+  if (!d_partial_out && !S.capturing) S.d_evals += n;
   if (!d_partial_in) {
     launch_plan(gd, S.gh, S.zc ? S.h_pin : d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream,
                 S.zc ? S.d_om : nullptr);
@@ -603,6 +604,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.shard_rank = 0;
   S.shard_n = 1;
   S.launches = 0;
+  S.d_evals = S.set_k_calls = 0;
   S.inited = true;
   S.err[0] = 0;
   return 0;
@@ -840,6 +842,7 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (!S.have_tables) return fail(ALPS_B200_ERR_USAGE, "no f0 tables: call alps_b200_upload (+ derivative_f0) first");
   if (kpar == 0.0) return fail(ALPS_B200_ERR_USAGE, "kpar must be non-zero");
+  S.set_k_calls++;
   const int nspec = S.cfg.nspec, nperp = S.cfg.nperp, npar = S.cfg.npar;
   const bool kperp_changed = !S.have_k || kperp != S.gh.kperp;
   S.gh.kperp = kperp;
@@ -1192,6 +1195,7 @@ static int disp_via_graph(int* used) {
   CK(cudaGraphLaunch(S.disp_graph, S.stream));
   CK(cudaStreamSynchronize(S.stream));
   S.launches += S.disp_graph_launches;
+  S.d_evals += 1;
   const int* herr = reinterpret_cast<const int*>(S.h_pin + 8);
   if (herr[0] || herr[6]) return check_device_errors();   // reports and clears the device error words
   *used = 1;
@@ -1411,6 +1415,8 @@ int alps_b200_get_info(int what, double* out) {
     case ALPS_B200_INFO_DFMA_NOREUSE: *out = run_dfma_peak_noreuse(S.stream); S.launches += 3; return 0;
     case ALPS_B200_INFO_DMMA_PEAK: *out = run_dmma_peak(S.stream); S.launches += 3; return 0;
     case ALPS_B200_INFO_QUAD_VARIANT: *out = S.qv.id; return 0;
+    case ALPS_B200_INFO_D_EVALS: *out = (double)S.d_evals; return 0;
+    case ALPS_B200_INFO_SET_K_CALLS: *out = (double)S.set_k_calls; return 0;
   }
   return fail(ALPS_B200_ERR_USAGE, "unknown info id %d", what);
 }
@@ -1421,6 +1427,37 @@ int alps_b200_emulate_split(int nproc, int nspec, const int* usebM, int* nmax, i
   bool bm[MAXSPEC];
   for (int i = 0; i < nspec; i++) bm[i] = usebM[i] != 0;
   emulate_split(nproc, nspec, bm, nmax, nhi);
+  return 0;
+}
+
+// Evaluation half of polyharmonic_spline (src/ALPS_fns_rel.f90:300-331, 407-423) on the device, stateless: the
+// relativistic regrid of derivative_f0_rel evaluates the spline at (ngamma+1)(npparbar+1) points over all table
+// nodes -- 4.7e8 kernel evaluations at C3, 13 s per species in numpy.  Host buffers in and out.
+int alps_b200_tps_eval(int n, const double* gc, const double* pc, const double* w, int npts, const double* gx,
+                       const double* px, double* out) {
+  if (n < 1 || npts < 0 || !gc || !pc || !w || (npts && (!gx || !px || !out)))
+    return fail(ALPS_B200_ERR_USAGE, "alps_b200_tps_eval: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(ALPS_B200_ERR_CUDA, "no CUDA device available; alps_b200 has no CPU fallback");
+  }
+  double *d_c = nullptr, *d_p = nullptr;
+  const size_t nc = 3 * (size_t)n + 3, np = 3 * (size_t)npts;
+  cudaError_t e = cudaMalloc((void**)&d_c, nc * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_p, (np ? np : 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(d_c, gc, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_c + n, pc, n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_c + 2 * (size_t)n, w, ((size_t)n + 3) * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && npts) e = cudaMemcpy(d_p, gx, npts * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && npts) e = cudaMemcpy(d_p + npts, px, npts * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && npts) {
+    launch_tps_eval(n, d_c, d_c + n, d_c + 2 * (size_t)n, npts, d_p, d_p + npts, d_p + 2 * (size_t)npts, nullptr);
+    e = cudaMemcpy(out, d_p + 2 * (size_t)npts, npts * sizeof(double), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_c);
+  cudaFree(d_p);
+  if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "alps_b200_tps_eval failed: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -73,6 +73,8 @@ void launch_frag_table(const double* X, int ldp, int nrows, int ncols, double sc
                        int ntiles, cudaStream_t st);
 void launch_build_Wf(const double* pperp, const double* J, int ldj, int nperp, int nhi, double* Wf, int nks, int nhb,
                      cudaStream_t st);
+void launch_tps_eval(int n, const double* gc, const double* pc, const double* w, int npts, const double* gx,
+                     const double* px, double* out, cudaStream_t st);
 void launch_int_ee(const double* df0, const double* pperp, const double* ppar, int nspec, int nperp, int npar,
                    int is0, double qs, double ms, double dpperp, double dppar, double* out, cudaStream_t st);
 

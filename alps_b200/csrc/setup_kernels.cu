@@ -230,4 +230,42 @@ void launch_int_ee(const double* df0, const double* pperp, const double* ppar, i
   k_int_ee<<<1, 1024, 0, st>>>(df0, pperp, ppar, nspec, nperp, npar, is0, qs, ms, dpperp, dppar, out);
 }
 
+// polyharmonic_spline evaluation of derivative_f0_rel, src/ALPS_fns_rel.f90:300-331, 407-423: for every point of the
+// (Gamma, pbar_par) grid  sum_i w_i phi(r_i) + w_n + w_{n+1} Gamma + w_{n+2} pbar_par  over the n table nodes, with the
+// reference's kernel (r >= 1: r^2 log r; 0 < r < 1: r log(r**r); r = 0: 0, lines 385-391), summed in node order.
+// One thread per grid point, the nodes staged through shared memory in chunks.
+constexpr int TPS_CHUNK = 256;
+__global__ void __launch_bounds__(TPS_CHUNK) k_tps_eval(int n, const double* __restrict__ gc,
+                                                        const double* __restrict__ pc, const double* __restrict__ w,
+                                                        int npts, const double* __restrict__ gx,
+                                                        const double* __restrict__ px, double* __restrict__ out) {
+  __shared__ double sg[TPS_CHUNK], sp[TPS_CHUNK], sw[TPS_CHUNK];
+  const int j = blockIdx.x * TPS_CHUNK + threadIdx.x;
+  const double x = j < npts ? gx[j] : 0.0, y = j < npts ? px[j] : 0.0;
+  double acc = 0.0;
+  for (int i0 = 0; i0 < n; i0 += TPS_CHUNK) {
+    const int i = i0 + threadIdx.x;
+    __syncthreads();
+    sg[threadIdx.x] = i < n ? gc[i] : 0.0;
+    sp[threadIdx.x] = i < n ? pc[i] : 0.0;
+    sw[threadIdx.x] = i < n ? w[i] : 0.0;
+    __syncthreads();
+    const int m = min(TPS_CHUNK, n - i0);
+    for (int k = 0; k < m; k++) {
+      const double dx = x - sg[k], dy = y - sp[k];
+      const double r = sqrt(dx * dx + dy * dy);
+      double phi = 0.0;
+      if (r >= 1.0) phi = r * r * log(r);
+      else if (r > 0.0) phi = r * log(pow(r, r));
+      acc += sw[k] * phi;
+    }
+  }
+  if (j < npts) out[j] = acc + w[n] + w[n + 1] * x + w[n + 2] * y;
+}
+void launch_tps_eval(int n, const double* gc, const double* pc, const double* w, int npts, const double* gx,
+                     const double* px, double* out, cudaStream_t st) {
+  if (npts <= 0) return;
+  k_tps_eval<<<(npts + TPS_CHUNK - 1) / TPS_CHUNK, TPS_CHUNK, 0, st>>>(n, gc, pc, w, npts, gx, px, out);
+}
+
 }  // namespace alps

@@ -1,6 +1,9 @@
 """Host-side set-up of the relativistic (Gamma, pbar_par) tables -- the input producer of the
-relativistic integrators (one-off rank-0 work in the reference, a dense
-1894^2 LAPACK solve; it stays on the host here too).
+relativistic integrators (one-off rank-0 work in the reference).  The dense 1894^2
+solve is LAPACK dgesv on the host like in the reference; the evaluation of the spline on the (Gamma, pbar_par)
+grid -- 4.7e8 kernel evaluations at C3 -- runs on the device with backend="device" (alps_b200_tps_eval,
+csrc/setup_kernels.cu: k_tps_eval), which is what the twin main program uses; backend="host" is the numpy
+statement of the same loop (set-up checks without a GPU).
 
 Follows derivative_f0_rel and polyharmonic_spline, src/ALPS_fns_rel.f90:36-426: thin-plate-spline
 regrid of log f0 from the (p_perp,p_par) table onto a uniform (Gamma, pbar_par) grid, cone sentinel
@@ -21,7 +24,18 @@ def _tps_kernel(r):
     return out
 
 
-def derivative_f0_rel(pp_s, f0_s, ms, vA, ngamma, npparbar, smoothing=0.0):
+def _tps_eval_device(gc, pc, w, gx, px):
+    import ctypes as C
+
+    from . import _lib
+    gc, pc, w, gx, px = (np.ascontiguousarray(a, dtype=np.float64).ravel() for a in (gc, pc, w, gx, px))
+    out = np.zeros(gx.size)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.lib().alps_b200_tps_eval(gc.size, p(gc), p(pc), p(w), gx.size, p(gx), p(px), p(out)))
+    return out
+
+
+def derivative_f0_rel(pp_s, f0_s, ms, vA, ngamma, npparbar, smoothing=0.0, backend="host"):
     """One species: pp_s (nperp+1, npar+1, 2), f0_s (nperp+1, npar+1) ->
     gamma_rel, pparbar_rel, f0_rel (ngamma+1, npparbar+1), df0_rel (ngamma+1, npparbar+1, 2)."""
     from scipy.linalg import solve
@@ -49,9 +63,14 @@ def derivative_f0_rel(pp_s, f0_s, ms, vA, ngamma, npparbar, smoothing=0.0):
     rhs[:n] = grid
     w = solve(M, rhs)          # LAPACK dgesv, like the reference (line 402)
     f0_rel = np.zeros_like(gamma_rel)
-    for i in range(ngamma + 1):
-        rr = np.sqrt((gamma_rel[i, :, None] - gc[None, :]) ** 2 + (pparbar_rel[i, :, None] - pc[None, :]) ** 2)
-        f0_rel[i] = _tps_kernel(rr) @ w[:n] + w[n] + w[n + 1] * gamma_rel[i] + w[n + 2] * pparbar_rel[i]
+    if backend == "device":
+        f0_rel = _tps_eval_device(gc, pc, w, gamma_rel, pparbar_rel).reshape(gamma_rel.shape)
+    elif backend == "host":
+        for i in range(ngamma + 1):
+            rr = np.sqrt((gamma_rel[i, :, None] - gc[None, :]) ** 2 + (pparbar_rel[i, :, None] - pc[None, :]) ** 2)
+            f0_rel[i] = _tps_kernel(rr) @ w[:n] + w[n] + w[n + 1] * gamma_rel[i] + w[n + 2] * pparbar_rel[i]
+    else:
+        raise ValueError("backend must be 'host' or 'device'")
     f0_rel = np.exp(f0_rel)
     f0_rel[(gamma_rel ** 2 - 1.0) < pparbar_rel ** 2] = -1.0           # outside the cone
     dgamma = gamma_rel[2, 2] - gamma_rel[1, 2]

@@ -14,7 +14,7 @@ the initial values of the &ffit blocks.  NHDS calc_chi for use_bM species runs o
 (csrc/nhds_kernel.cu).
 
 Several GPUs of one box (replaces `mpirun -np N`): `python -m torch.distributed.run --nproc-per-node N
---master-addr 127.0.0.1 -m alps_b200.run ...` -- one process per GPU; the nr x ni loop of map_search is sharded over
+--master-addr 127.0.0.1 -m alps_b200.run x.in --emulate-nproc 4 ...` -- one process per GPU; the nr x ni loop of map_search is sharded over
 the ranks (sharding.map_search_sharded, one NCCL all_gather of D), rank 0 alone writes the files and runs the
 sequential root refinement and k scans."""
 from __future__ import annotations
@@ -111,8 +111,15 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False):
         shape = (len(rel), pl.ngamma + 1, pl.npparbar + 1)
         pl.f0_rel, pl.gamma_rel, pl.pparbar_rel = (np.zeros(shape, order="F") for _ in range(3))
         pl.df0_rel = np.zeros(shape + (2,), order="F")
+        done = []      # species with identical tables and mass share one regrid (pair plasmas)
         for r, i in enumerate(rel):
-            g, p, f, d, integ = derivative_f0_rel(pp[i], f0[i], species[i].ms, vA, pl.ngamma, pl.npparbar)
+            hit = [c for j, c in done if species[j].ms == species[i].ms and np.array_equal(pp[j], pp[i])
+                   and np.array_equal(f0[j], f0[i])]
+            if not hit:
+                done.append((i, derivative_f0_rel(pp[i], f0[i], species[i].ms, vA, pl.ngamma, pl.npparbar,
+                                                  backend="device")))
+                hit = [done[-1][1]]
+            g, p, f, d, integ = hit[0]
             pl.gamma_rel[r], pl.pparbar_rel[r], pl.f0_rel[r], pl.df0_rel[r] = g, p, f, d
             if not have_files and not fit:
                 pf[i, :, 0, 0] = pf[i, 0, 0, 0] / integ
@@ -140,7 +147,9 @@ def main(argv=None):
     ap.add_argument("input")
     ap.add_argument("--dist", default=None)
     ap.add_argument("--out", default="solution")
-    ap.add_argument("--nproc", type=int, default=0, help="MPI size of the reference run to emulate")
+    ap.add_argument("--emulate-nproc", "--nproc", dest="nproc", type=int, default=0,
+                    help="MPI size of the reference run to emulate (under torchrun spell it --emulate-nproc: "
+                         "torchrun's own parser claims --nproc as an abbreviation of --nproc-per-node)")
     ap.add_argument("--fit", action="store_true",
                     help="run the twin of determine_param_fit (LM / Chebyshev fits) instead of using ideal parameters")
     a = ap.parse_args(argv)
@@ -206,6 +215,13 @@ def main(argv=None):
             rows, w = sol.om_double_scan(w, opts, blk(1), blk(2), prefix)
             print("double scan done: %d x %d points" % rows.shape[:2])
     finally:
+        from . import _lib
+        try:
+            stats = (int(sol.info(_lib.INFO_D_EVALS)), int(sol.info(_lib.INFO_SET_K_CALLS)))
+            print("D(omega,k) evaluations: %d, set_k calls: %d" % stats)
+            main.last_stats = stats
+        except Exception:
+            pass
         sol.close()
         if world > 1:
             dist.barrier()

@@ -118,6 +118,13 @@ int alps_b200_nhds_calc_chi(double ns, double qs, double ms, int bM_nmaxs, doubl
                             double bM_betas, double bM_alphas, double bM_pdrifts, double kz, double kperp,
                             const double x[2], int kperp_norm, double *chi, double *chi_low);
 
+/* replaces: the evaluation loop of polyharmonic_spline inside derivative_f0_rel (src/ALPS_fns_rel.f90:300-331,
+ * 407-423): out[j] = sum_i w[i] phi(|(gx[j],px[j]) - (gc[i],pc[i])|) + w[n] + w[n+1] gx[j] + w[n+2] px[j]
+ * with the reference's thin-plate kernel phi, over the n table nodes in order.  Host buffers; stateless; needs a GPU.
+ * The dense (n+3)^2 solve for w stays with LAPACK on the host like in the reference (line 402). */
+int alps_b200_tps_eval(int n, const double *gc, const double *pc, const double *w, int npts, const double *gx,
+                       const double *px, double *out);
+
 /* Harmonic sharding (replaces split_processes + MPI_REDUCE, src/ALPS_fns.f90:4079-4207, 519-523):
  * restrict this process to harmonics |n| in [nlo,nhi] of species is (is=0: all species),
  * produce un-normalised partial sums (caller all-reduces them over NCCL), then assemble. */
@@ -144,6 +151,8 @@ int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
                                              TFLOP/s (register-read limit of tiled FP64 kernels)  */
 #define ALPS_B200_INFO_DMMA_PEAK 6        /* FP64 tensor-pipe micro-benchmark (mma.sync.m8n8k4.f64), TFLOP/s */
 #define ALPS_B200_INFO_QUAD_VARIANT 7     /* id of the quadrature kernel variant in use (>= 9: DMMA) */
+#define ALPS_B200_INFO_D_EVALS 8          /* D(omega,k) evaluations since init (every entry point)             */
+#define ALPS_B200_INFO_SET_K_CALLS 9      /* alps_b200_set_k calls since init                                   */
 
 /* ------------------------------------------------------------------------------------------
  * Host-side twins of the reference's omega-point generators (alps_b200/csrc/drivers.cpp).  They

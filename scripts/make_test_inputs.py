@@ -1,15 +1,20 @@
 """Writes compact copies of the reference's remaining test configurations into tests/inputs/suite/
 (this container only: reads /root/reference/tests/*.in and distribution/*_dist.in).  Comments are dropped,
 the scans are shortened (ns <= 4 with the reference's step size, numiter <= 40) so that the GPU suite runs each in about a second, and the
-namelists are re-emitted in a canonical form.  The physics parameters are untouched."""
+namelists are re-emitted in a canonical form.  The physics parameters are untouched.
+With --full the scans, maps and iteration limits are left at the reference's values and the files go to
+tests/inputs/full/ (timed end to end by scripts/full_configs.py)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alps_b200.namelist import read_namelists
 
 REF = "/root/reference"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "inputs", "suite")
+FULL = "--full" in sys.argv
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "inputs",
+                   "full" if FULL else "suite")
 NAMES = ["test_ICW", "test_electron_mode", "test_analytical", "test_chebyshev", "test_cold_plasma", "test_bimax",
-         "test_kperp", "test_double_scan", "test_map"]
+         "test_kperp", "test_double_scan", "test_map"] + (["test_kpar_fast", "test_relativistic"] if FULL else [])
+os.makedirs(OUT, exist_ok=True)
 
 
 def fmt(v):
@@ -34,8 +39,9 @@ def emit(nl, path):
 for name in NAMES:
     nl = read_namelists(os.path.join(REF, "tests", name + ".in"))
     s = nl["system"]
-    s["numiter"] = min(int(s.get("numiter", 50)), 40)
-    for k, d in nl.items():
+    if not FULL:
+        s["numiter"] = min(int(s.get("numiter", 50)), 40)
+    for k, d in (nl.items() if not FULL else []):
         if k.startswith("scan_input_"):
             ns_old = int(d["ns"]) * int(d.get("nres", 1))
             ns_new = min(ns_old, 4 if int(s.get("scan_option", 1)) == 1 else 2)

@@ -33,3 +33,26 @@ def test_regrid_of_a_juettner_table():
     p1 = pl.param_fit[0, 0, 0, 0]
     model = p1 * np.exp(-pl.species[0].perp_correction[0] * g)
     assert np.max(np.abs(model[inner] / f[inner] - 1.0)) < 0.02
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_device_spline_evaluation_matches_the_host_statement():
+    """alps_b200_tps_eval (k_tps_eval: the evaluation loop of polyharmonic_spline, src/ALPS_fns_rel.f90:300-331,
+    407-423) against the numpy statement of the same loop: log f0_rel to 1e-11 absolute (the sums run over ~900
+    nodes with weights of both signs; numpy's matmul blocks the sum, the kernel adds in node order), the cone
+    sentinel identical, normalised f0_rel and its derivatives to 1e-9 relative."""
+    from alps_b200.relativistic import derivative_f0_rel
+    pl = tables.config_relativistic(nperp=20, npar=40, ngamma=40, npparbar=60)
+    host = derivative_f0_rel(pl.pp[0], pl.f0[0], 1.0, 1.0, 40, 60, backend="host")
+    dev = derivative_f0_rel(pl.pp[0], pl.f0[0], 1.0, 1.0, 40, 60, backend="device")
+    assert np.array_equal(host[0], dev[0]) and np.array_equal(host[1], dev[1])
+    fh, fd = host[2], dev[2]
+    assert np.array_equal(fh == -1.0, fd == -1.0)
+    inside = fh > 0.0
+    assert np.max(np.abs(np.log(fh[inside]) - np.log(fd[inside]))) < 1e-9
+    scale = np.max(np.abs(host[3]))
+    assert np.max(np.abs(host[3] - dev[3])) < 1e-8 * scale
+    assert abs(host[4] - dev[4]) < 1e-9 * abs(host[4])
