@@ -76,6 +76,8 @@ struct State {
   long long disp_graph_launches = 0;
   int disp_plain_calls = 0;      // plain calls since the signature last changed (the first one warms up)
   bool capturing = false, graph_off = false, omega_major = false;
+  int reslat_gx = RESLAT_GX_NARROW;   // grid width of k_resonant_lat, adapted to the number of resonant harmonics of the
+                                      // previous single-omega call (they change slowly along a scan)
   bool pdl_on = false;                // programmatic dependent launches inside the single-omega graph
   bool fuse_off = false;              // k_chi_partial + k_assemble as two launches for every batch size
   bool zc = false, zc_off = false;   // zero-copy chain while capturing: omega read from / D and the error words written to
@@ -478,7 +480,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     if (!S.capturing) cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.d_respart,
-                    S.d_restick, S.stream);
+                    S.d_restick, S.stream, S.reslat_gx);
     if (!S.rtiles.empty()) {
       // few omegas in flight: spread each (omega, species, |n|) over several CTAs (configuration-only
       // rule, like nsplit_small, so disp() and a small disp_batch() stay bitwise identical)
@@ -1141,7 +1143,7 @@ static void disp_signature(std::vector<unsigned char>& sig) {
                         S.d_gwin, S.d_partial, S.d_err, S.d_rtiles, S.d_fitems, S.d_respart, S.d_restick,
                         S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
   const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)S.rtiles.size(), (long long)S.fitems.size(), S.mode,
-                            S.qv.id, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off, (long long)S.pdl_on};
+                            S.qv.id, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off, (long long)S.pdl_on, (long long)S.reslat_gx};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
   memcpy(sig.data(), &P, sizeof(P));
   memcpy(sig.data() + sizeof(P), ptrs, sizeof(ptrs));
@@ -1198,6 +1200,10 @@ static int disp_via_graph(int* used) {
   S.d_evals += 1;
   const int* herr = reinterpret_cast<const int*>(S.h_pin + 8);
   if (herr[0] || herr[6]) return check_device_errors();   // reports and clears the device error words
+  // herr[7] = resonant harmonics of this call: widen / narrow the next call's k_resonant_lat grid (the signature
+  // changes, so the graph is captured again -- rare, the count changes slowly along a scan)
+  if (herr[7] > RESLAT_GX_NARROW) S.reslat_gx = RESLAT_GX_WIDE;
+  else if (herr[7] <= RESLAT_GX_NARROW / 2) S.reslat_gx = RESLAT_GX_NARROW;
   *used = 1;
   return 0;
 }

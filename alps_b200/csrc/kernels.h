@@ -98,7 +98,8 @@ void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int 
 bool plan_fused_ok(const GlobalDev& gh, int n_om);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
-                     int* tickets, cudaStream_t st);
+                     int* tickets, cudaStream_t st, int gx = 148);
+constexpr int RESLAT_GX_NARROW = 16, RESLAT_GX_WIDE = 148;   // block columns per omega of k_resonant_lat (api.cu adapts)
 constexpr int RES_PART_DOUBLES = 11 * 16;   // k_resonant_lat: partial rows per item (LAT_PARTS x LAT_STRIDE)
 // chi partial layout per omega: [nspec][PARTIAL_PER_SPEC] doubles (see resonant.cu)
 constexpr int PARTIAL_PER_SPEC = 2 * (6 + 18);   // chi(6 modes) + chi_low(6 modes x 3) complex

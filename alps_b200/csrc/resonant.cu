@@ -9,6 +9,8 @@
 //   k_chi_partial  the harmonic sums of disp() (:363-514): tensor components from the moment
 //                sums, chi_low for n = 0, +-1, the ee term, the ns*qs normalisation
 //   k_assemble   the rank-0 part of disp() (:536-624): chi0, eps, wave, determinant
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -505,6 +507,7 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
   pdl_trigger();
   pdl_wait();
   const int nwork = *work_count;
+  if (blockIdx.x == 0 && part == 0 && tid == 0) err_flag[7] = nwork;   // feedback for the host's choice of grid width
   for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
     const size_t idx = (size_t)work[wi];
     const int iom = (int)(idx / g.NI), it = (int)(idx % g.NI);
@@ -980,12 +983,14 @@ bool plan_fused_ok(const GlobalDev& gh, int n_om) {
 }
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
-                     int* tickets, cudaStream_t st) {
+                     int* tickets, cudaStream_t st, int gx) {
   if (n_om <= 0) return;
-  if (n_om <= 64 && Spart && tickets)
-    // work items (resonant harmonics) are few per omega -- typically n = 0 only; the blocks loop over the list
-    launch_chain(k_resonant_lat, dim3(n_om < 10 ? 16 * n_om : 148, LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan, work, work_count, gwin, Sres,
-                 err_flag, Spart, tickets);
+  if (n_om <= 64 && Spart && tickets) {
+    // gx block columns per omega loop over the list of resonant harmonics: usually only n = 0 is resonant and a
+    // narrow grid saves waves of idle blocks (C1: -2.8 us per D), many resonances (large k_par) want all SMs
+    launch_chain(k_resonant_lat, dim3(min(148, max(1, gx * n_om)), LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan,
+                 work, work_count, gwin, Sres, err_flag, Spart, tickets);
+  }
   else
     k_resonant<<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
 }
