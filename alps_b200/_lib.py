@@ -24,7 +24,7 @@ SYMBOLS = [
 ]
 
 INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH, INFO_DFMA_NOREUSE, \
-    INFO_DMMA_PEAK, INFO_QUAD_VARIANT, INFO_D_EVALS, INFO_SET_K_CALLS = range(10)
+    INFO_DMMA_PEAK, INFO_QUAD_VARIANT, INFO_D_EVALS, INFO_SET_K_CALLS, INFO_MEMO_HITS = range(11)
 
 
 class Cfg(C.Structure):

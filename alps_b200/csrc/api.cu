@@ -109,7 +109,16 @@ struct State {
   int mode = 0;
   QuadVariant qv{8, 16, 32, 2};
   int shard_rank = 0, shard_n = 1;
-  long long launches = 0, d_evals = 0, set_k_calls = 0;
+  long long launches = 0, d_evals = 0, set_k_calls = 0, memo_hits = 0;
+  // alps_b200_disp memo: D is a pure, bitwise-deterministic function of omega for a given state, and the reference's
+  // solvers re-evaluate identical omegas (secant_osc starts with disp(om) twice, src/ALPS_fns.f90:1986/2015, and keeps
+  // calling disp at a converged om and om(1 +- delta) until numiter when D_threshold is unreachable): the last MEMO_N
+  // (omega -> D) pairs of the current state are answered without a launch.  Any state change clears it.
+  static constexpr int MEMO_N = 8;
+  unsigned long long memo_key[MEMO_N][2] = {};
+  double memo_D[MEMO_N][2] = {};
+  int memo_n = 0, memo_next = 0;
+  bool memo_on = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_kernel_ms = 0.0;
   double *h_pin = nullptr;   // pinned staging for host <-> device omega / D traffic
@@ -160,6 +169,29 @@ void drop_disp_graph() {
   S.disp_graph = nullptr;
   S.disp_sig.clear();
   S.disp_plain_calls = 0;
+}
+
+void memo_clear() { S.memo_n = S.memo_next = 0; }
+bool memo_lookup(const double om[2], double D[2]) {
+  unsigned long long k[2];
+  memcpy(k, om, sizeof(k));
+  for (int i = 0; i < S.memo_n; i++)
+    if (S.memo_key[i][0] == k[0] && S.memo_key[i][1] == k[1]) {
+      if (D) {
+        D[0] = S.memo_D[i][0];
+        D[1] = S.memo_D[i][1];
+      }
+      return true;
+    }
+  return false;
+}
+void memo_store(const double om[2], const double D[2]) {
+  const int i = S.memo_next;
+  memcpy(S.memo_key[i], om, 2 * sizeof(double));
+  S.memo_D[i][0] = D[0];
+  S.memo_D[i][1] = D[1];
+  S.memo_next = (i + 1) % State::MEMO_N;
+  S.memo_n = std::min(S.memo_n + 1, (int)State::MEMO_N);
 }
 
 void free_batch() {
@@ -596,6 +628,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
       const char* v = getenv(name);
       return v ? v[0] != '0' : dflt;
     };
+    S.memo_on = knob("ALPS_B200_MEMO", true);
     S.pdl_on = knob("ALPS_B200_PDL", LAT_DEFAULT_PDL);
     S.fuse_off = !knob("ALPS_B200_FUSE", LAT_DEFAULT_FUSE);
     S.zc_off = !knob("ALPS_B200_ZC", LAT_DEFAULT_ZC);
@@ -606,7 +639,8 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.shard_rank = 0;
   S.shard_n = 1;
   S.launches = 0;
-  S.d_evals = S.set_k_calls = 0;
+  S.d_evals = S.set_k_calls = S.memo_hits = 0;
+  memo_clear();
   S.inited = true;
   S.err[0] = 0;
   return 0;
@@ -658,6 +692,7 @@ void alps_b200_finalize(void) {
 int alps_b200_set_species(int is, double ns, double qs, double ms, int relativistic, int usebM, int ACmethod,
                           int n_fits, const int* fit_type, const double* perp_correction, int logfit,
                           int poly_kind, int poly_order, double poly_log_max) {
+  memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (is < 1 || is > S.cfg.nspec) return fail(ALPS_B200_ERR_USAGE, "species index %d out of range", is);
   if (n_fits > MAXFITS || n_fits > S.gh.maxfits) return fail(ALPS_B200_ERR_USAGE, "n_fits exceeds maxfits");
@@ -680,6 +715,7 @@ int alps_b200_set_species(int is, double ns, double qs, double ms, int relativis
 }
 
 int alps_b200_upload(const double* pp, const double* df0, const double* param_fit, const double* poly_fit_coeffs) {
+  memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (!pp) return fail(ALPS_B200_ERR_USAGE, "pp is NULL");
   const int nspec = S.cfg.nspec, nperp = S.cfg.nperp, npar = S.cfg.npar;
@@ -750,6 +786,7 @@ int alps_b200_upload(const double* pp, const double* df0, const double* param_fi
 
 int alps_b200_upload_rel(int nspec_rel, const double* f0_rel, const double* df0_rel, const double* gamma_rel,
                          const double* pparbar_rel) {
+  memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (!f0_rel || !df0_rel || !gamma_rel || !pparbar_rel) return fail(ALPS_B200_ERR_USAGE, "NULL table");
   const int ng = S.cfg.ngamma, npb = S.cfg.npparbar, nspec = S.cfg.nspec;
@@ -814,6 +851,7 @@ int alps_b200_upload_rel(int nspec_rel, const double* f0_rel, const double* df0_
 }
 
 int alps_b200_derivative_f0(const double* f0, double* df0_out) {
+  memo_clear();
   if (!S.inited || !S.d_pp_f) return fail(ALPS_B200_ERR_USAGE, "call alps_b200_upload before alps_b200_derivative_f0");
   if (!f0) return fail(ALPS_B200_ERR_USAGE, "f0 is NULL");
   const int nspec = S.cfg.nspec, nperp = S.cfg.nperp, npar = S.cfg.npar;
@@ -832,6 +870,7 @@ int alps_b200_derivative_f0(const double* f0, double* df0_out) {
 }
 
 int alps_b200_set_harmonic_shard(int rank, int nranks) {
+  memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ALPS_B200_ERR_USAGE, "bad shard %d/%d", rank, nranks);
   S.shard_rank = rank;
@@ -841,6 +880,7 @@ int alps_b200_set_harmonic_shard(int rank, int nranks) {
 }
 
 int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
+  memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (!S.have_tables) return fail(ALPS_B200_ERR_USAGE, "no f0 tables: call alps_b200_upload (+ derivative_f0) first");
   if (kpar == 0.0) return fail(ALPS_B200_ERR_USAGE, "kpar must be non-zero");
@@ -1212,12 +1252,17 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   int rc = check_ready();
   if (rc) return rc;
   if (!om) return fail(ALPS_B200_ERR_USAGE, "om is NULL");
+  const bool plain_D = !chi0 && !chi0_low && !wave && !S.ext_any;
+  if (plain_D && S.memo_on && memo_lookup(om, D)) {
+    S.memo_hits++;
+    return 0;
+  }
   if ((rc = bind_batch(1))) return rc;
   const int nspec = S.cfg.nspec;
   if ((rc = ensure_pinned(64 * sizeof(double)))) return rc;
   S.h_pin[0] = om[0];
   S.h_pin[1] = om[1];
-  if (!chi0 && !chi0_low && !wave && !S.ext_any && !S.graph_off && S.stream != nullptr) {
+  if (plain_D && !S.graph_off && S.stream != nullptr) {
     int used = 0;
     if ((rc = disp_via_graph(&used))) return rc;
     if (used) {
@@ -1225,6 +1270,7 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
         D[0] = S.h_pin[2];
         D[1] = S.h_pin[3];
       }
+      if (S.memo_on) memo_store(om, S.h_pin + 2);
       return 0;
     }
   }
@@ -1241,6 +1287,7 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
     D[0] = S.h_pin[2];
     D[1] = S.h_pin[3];
   }
+  if (plain_D && S.memo_on) memo_store(om, S.h_pin + 2);
   // external (NHDS) contributions are per omega: consumed by this call
   if (S.ext_any) {
     std::fill(S.ext.begin(), S.ext.end(), 0.0);
@@ -1271,6 +1318,7 @@ int alps_b200_add_external_chi(int is, const double* chi, const double* chi_low)
 
 int alps_b200_set_bm_species(int is, int bM_nmaxs, double bM_Bessel_zeros, double bM_betas, double bM_alphas,
                              double bM_pdrifts) {
+  memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (is < 1 || is > S.cfg.nspec || !S.sp[is - 1].set) return fail(ALPS_B200_ERR_USAGE, "species %d not set", is);
   BmParams& p = S.bm[is - 1];
@@ -1384,6 +1432,7 @@ int alps_b200_assemble_dev(int n, const double* d_om, const double* d_partial, d
 }
 
 int alps_b200_set_mode(int mode) {
+  memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (mode != 0 && mode != 1) return fail(ALPS_B200_ERR_USAGE, "mode must be 0 (direct) or 1 (k-hoisted)");
   if (mode != S.mode) S.have_k = false;   // the hoisted tables are built by alps_b200_set_k
@@ -1423,6 +1472,7 @@ int alps_b200_get_info(int what, double* out) {
     case ALPS_B200_INFO_QUAD_VARIANT: *out = S.qv.id; return 0;
     case ALPS_B200_INFO_D_EVALS: *out = (double)S.d_evals; return 0;
     case ALPS_B200_INFO_SET_K_CALLS: *out = (double)S.set_k_calls; return 0;
+    case ALPS_B200_INFO_MEMO_HITS: *out = (double)S.memo_hits; return 0;
   }
   return fail(ALPS_B200_ERR_USAGE, "unknown info id %d", what);
 }

@@ -30,7 +30,9 @@ from .namelist import read_namelists
 from .solver import Solver
 
 
-def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False):
+def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False, rel_backend="host"):
+    """rel_backend: where the spline of the relativistic regrid is evaluated (relativistic.derivative_f0_rel):
+    "device" in the twin main program, "host" (numpy statement of the same loop) for set-up checks without a GPU."""
     s = nl["system"]
     nspec, nperp, npar = int(s["nspec"]), int(s["nperp"]), int(s["npar"])
     vA = float(s["va"])
@@ -117,7 +119,7 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False):
                    and np.array_equal(f0[j], f0[i])]
             if not hit:
                 done.append((i, derivative_f0_rel(pp[i], f0[i], species[i].ms, vA, pl.ngamma, pl.npparbar,
-                                                  backend="device")))
+                                                  backend=rel_backend)))
                 hit = [done[-1][1]]
             g, p, f, d, integ = hit[0]
             pl.gamma_rel[r], pl.pparbar_rel[r], pl.f0_rel[r], pl.df0_rel[r] = g, p, f, d
@@ -156,7 +158,7 @@ def main(argv=None):
     nl = read_namelists(a.input)
     runname = os.path.splitext(os.path.basename(a.input))[0]
     dist_nl = read_namelists(a.dist) if a.dist else None
-    pl = plasma_from_inputs(nl, dist_nl, base_dir=os.getcwd(), fit=a.fit)
+    pl = plasma_from_inputs(nl, dist_nl, base_dir=os.getcwd(), fit=a.fit, rel_backend="device")
     s = nl["system"]
     if a.fit:
         # what output_fit prints (src/ALPS_analyt.f90:942-943)
@@ -217,8 +219,9 @@ def main(argv=None):
     finally:
         from . import _lib
         try:
-            stats = (int(sol.info(_lib.INFO_D_EVALS)), int(sol.info(_lib.INFO_SET_K_CALLS)))
-            print("D(omega,k) evaluations: %d, set_k calls: %d" % stats)
+            stats = (int(sol.info(_lib.INFO_D_EVALS)), int(sol.info(_lib.INFO_SET_K_CALLS)),
+                     int(sol.info(_lib.INFO_MEMO_HITS)))
+            print("D(omega,k) evaluations: %d, set_k calls: %d, disp() calls answered from the memo: %d" % stats)
             main.last_stats = stats
         except Exception:
             pass

@@ -153,6 +153,8 @@ int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
 #define ALPS_B200_INFO_QUAD_VARIANT 7     /* id of the quadrature kernel variant in use (>= 9: DMMA) */
 #define ALPS_B200_INFO_D_EVALS 8          /* D(omega,k) evaluations since init (every entry point)             */
 #define ALPS_B200_INFO_SET_K_CALLS 9      /* alps_b200_set_k calls since init                                   */
+#define ALPS_B200_INFO_MEMO_HITS 10       /* alps_b200_disp calls answered from the memo of the last omegas (same
+                                             omega bits, same state: no launch; not counted in D_EVALS)          */
 
 /* ------------------------------------------------------------------------------------------
  * Host-side twins of the reference's omega-point generators (alps_b200/csrc/drivers.cpp).  They

@@ -242,3 +242,38 @@ def test_cli_relativistic_scan(tmp_path):
             assert d_root < 1e-3 * d_near      # the file carries 5 digits of the root
     finally:
         sol.close()
+
+
+def test_disp_memo_is_transparent(tmp_path, monkeypatch):
+    """alps_b200_disp answers a repeated omega (same bits, same state) from its memo of the last evaluations -- the
+    reference's secant_osc evaluates its start value twice (src/ALPS_fns.f90:1986, 2015) and keeps evaluating a
+    converged omega until numiter when D_threshold is out of reach.  With and without the memo the scan files are
+    identical, and the memo is dropped when k changes."""
+    from alps_b200 import _lib
+    from alps_b200.solver import Solver
+    pl = tables.config_kpar_fast()
+    out = {}
+    for memo in ("1", "0"):
+        monkeypatch.setenv("ALPS_B200_MEMO", memo)
+        sol = Solver(pl, emulate_nproc=4)
+        try:
+            sol.set_k(1.0e-2, 1.0e-2)
+            opts = sol.opts(numiter=60, D_threshold=1.0e-30, D_prec=1.0e-5, secant_method=2)   # never "converges"
+            w, D = sol.refine_guess([complex(9.9e-3, -5.5e-6)], opts)
+            prefix = str(tmp_path / ("memo" + memo))
+            rows, w2 = sol.om_scan(w, opts, scan_type=4, swi=1.0e-3, swf=2.0e-2, swlog=True, ns_steps=4, nres=1,
+                                   eigen=True, heat=True, prefix=prefix, ik=1)
+            hits, evals = int(sol.info(_lib.INFO_MEMO_HITS)), int(sol.info(_lib.INFO_D_EVALS))
+            d1 = sol.disp(0.01 - 1e-6j)
+            sol.set_k(1.0e-2, 3.0e-2)
+            d2 = sol.disp(0.01 - 1e-6j)          # same omega, other k: must not come from the memo
+            out[memo] = (w, D, rows, open(prefix + ".scan_kpara_1.root_1").read(),
+                         open(prefix + ".heat_kpara_1.root_1").read(), hits, evals, d1, d2)
+        finally:
+            sol.close()
+    monkeypatch.delenv("ALPS_B200_MEMO")
+    a, b = out["1"], out["0"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[3] == b[3] and a[4] == b[4]
+    assert a[5] > 0 and b[5] == 0 and a[5] + a[6] == b[6]       # every call is either evaluated or answered
+    assert a[7] == b[7] and a[8] == b[8] and a[7] != a[8]
