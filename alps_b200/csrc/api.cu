@@ -112,12 +112,16 @@ struct State {
   long long launches = 0, d_evals = 0, set_k_calls = 0, memo_hits = 0;
   // alps_b200_disp memo: D is a pure, bitwise-deterministic function of omega for a given state, and the reference's
   // solvers re-evaluate identical omegas (secant_osc starts with disp(om) twice, src/ALPS_fns.f90:1986/2015, and keeps
-  // calling disp at a converged om and om(1 +- delta) until numiter when D_threshold is unreachable): the last MEMO_N
-  // (omega -> D) pairs of the current state are answered without a launch.  Any state change clears it.
-  static constexpr int MEMO_N = 8;
-  unsigned long long memo_key[MEMO_N][2] = {};
-  double memo_D[MEMO_N][2] = {};
-  int memo_n = 0, memo_next = 0;
+  // calling disp at a converged om and om(1 +- delta), or wandering over a few ulp-neighbours of it, until numiter when
+  // D_threshold is unreachable): recent (omega -> D) pairs of the current state are answered without a launch.  Any state change clears it.
+  static constexpr int MEMO_BITS = 13, MEMO_N = 1 << MEMO_BITS;   // hashed, 2-way; cleared by bumping the generation
+  struct MemoEntry {
+    unsigned long long key[2];
+    double D[2];
+    unsigned long long gen;
+  };
+  std::vector<MemoEntry> memo;
+  unsigned long long memo_gen = 1;
   bool memo_on = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_kernel_ms = 0.0;
@@ -171,27 +175,42 @@ void drop_disp_graph() {
   S.disp_plain_calls = 0;
 }
 
-void memo_clear() { S.memo_n = S.memo_next = 0; }
+void memo_clear() { S.memo_gen++; }
+inline size_t memo_slot(const unsigned long long k[2]) {
+  const unsigned long long h = (k[0] * 0x9E3779B97F4A7C15ull) ^ (k[1] * 0xC2B2AE3D27D4EB4Full);
+  return (size_t)(h >> (64 - State::MEMO_BITS));
+}
 bool memo_lookup(const double om[2], double D[2]) {
+  if (S.memo.empty()) return false;
   unsigned long long k[2];
   memcpy(k, om, sizeof(k));
-  for (int i = 0; i < S.memo_n; i++)
-    if (S.memo_key[i][0] == k[0] && S.memo_key[i][1] == k[1]) {
+  const size_t s0 = memo_slot(k);
+  for (size_t s : {s0, s0 ^ 1}) {
+    const State::MemoEntry& e = S.memo[s];
+    if (e.gen == S.memo_gen && e.key[0] == k[0] && e.key[1] == k[1]) {
       if (D) {
-        D[0] = S.memo_D[i][0];
-        D[1] = S.memo_D[i][1];
+        D[0] = e.D[0];
+        D[1] = e.D[1];
       }
       return true;
     }
+  }
   return false;
 }
 void memo_store(const double om[2], const double D[2]) {
-  const int i = S.memo_next;
-  memcpy(S.memo_key[i], om, 2 * sizeof(double));
-  S.memo_D[i][0] = D[0];
-  S.memo_D[i][1] = D[1];
-  S.memo_next = (i + 1) % State::MEMO_N;
-  S.memo_n = std::min(S.memo_n + 1, (int)State::MEMO_N);
+  if (S.memo.empty()) S.memo.assign(State::MEMO_N, State::MemoEntry{{0, 0}, {0.0, 0.0}, 0});
+  unsigned long long k[2];
+  memcpy(k, om, sizeof(k));
+  const size_t s0 = memo_slot(k);
+  // free or stale way first, else replace the primary way
+  size_t s = s0;
+  if (S.memo[s0].gen == S.memo_gen && S.memo[s0 ^ 1].gen != S.memo_gen) s = s0 ^ 1;
+  State::MemoEntry& e = S.memo[s];
+  e.key[0] = k[0];
+  e.key[1] = k[1];
+  e.D[0] = D[0];
+  e.D[1] = D[1];
+  e.gen = S.memo_gen;
 }
 
 void free_batch() {
