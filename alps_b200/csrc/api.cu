@@ -109,7 +109,7 @@ struct State {
   int mode = 0;
   QuadVariant qv{8, 16, 32, 2};
   int shard_rank = 0, shard_n = 1;
-  long long launches = 0, d_evals = 0, set_k_calls = 0, memo_hits = 0;
+  long long launches = 0, d_evals = 0, set_k_calls = 0, memo_hits = 0, prefetched = 0;
   // alps_b200_disp memo: D is a pure, bitwise-deterministic function of omega for a given state, and the reference's
   // solvers re-evaluate identical omegas (secant_osc starts with disp(om) twice, src/ALPS_fns.f90:1986/2015, and keeps
   // calling disp at a converged om and om(1 +- delta), or wandering over a few ulp-neighbours of it, until numiter when
@@ -658,7 +658,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.shard_rank = 0;
   S.shard_n = 1;
   S.launches = 0;
-  S.d_evals = S.set_k_calls = S.memo_hits = 0;
+  S.d_evals = S.set_k_calls = S.memo_hits = S.prefetched = 0;
   memo_clear();
   S.inited = true;
   S.err[0] = 0;
@@ -1315,6 +1315,32 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   return 0;
 }
 
+// Evaluate up to 8 omegas that a solver is about to ask for one by one (e.g. om, om(1+delta), om(1-delta) of a
+// finite-difference Newton step) as ONE small batch and keep the results in the memo: the following alps_b200_disp
+// calls return them without a launch.  A batch of <= 8 omegas is in the same batch class as a single call, so the
+// values are bitwise the ones alps_b200_disp would have computed.  No-op when the memo is off.
+int alps_b200_disp_prefetch(int n, const double* om) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (n <= 0 || !om || !S.memo_on || S.ext_any) return 0;
+  double todo[2 * LAT_BATCH], D[2 * LAT_BATCH];
+  int m = 0;
+  for (int i = 0; i < n && m < LAT_BATCH; i++) {
+    if (memo_lookup(om + 2 * i, nullptr)) continue;
+    bool dup = false;
+    for (int j = 0; j < m; j++) dup = dup || (memcmp(todo + 2 * j, om + 2 * i, 2 * sizeof(double)) == 0);
+    if (dup) continue;
+    todo[2 * m] = om[2 * i];
+    todo[2 * m + 1] = om[2 * i + 1];
+    m++;
+  }
+  if (m < 2) return 0;   // a single omega is faster through the graph of alps_b200_disp
+  if ((rc = alps_b200_disp_batch(m, todo, D, nullptr))) return rc;
+  for (int j = 0; j < m; j++) memo_store(todo + 2 * j, D + 2 * j);
+  S.prefetched += m;
+  return 0;
+}
+
 int alps_b200_add_external_chi(int is, const double* chi, const double* chi_low) {
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (is < 1 || is > S.cfg.nspec || !chi) return fail(ALPS_B200_ERR_USAGE, "bad arguments");
@@ -1492,6 +1518,7 @@ int alps_b200_get_info(int what, double* out) {
     case ALPS_B200_INFO_D_EVALS: *out = (double)S.d_evals; return 0;
     case ALPS_B200_INFO_SET_K_CALLS: *out = (double)S.set_k_calls; return 0;
     case ALPS_B200_INFO_MEMO_HITS: *out = (double)S.memo_hits; return 0;
+    case ALPS_B200_INFO_PREFETCHED: *out = (double)S.prefetched; return 0;
   }
   return fail(ALPS_B200_ERR_USAGE, "unknown info id %d", what);
 }

@@ -13,6 +13,7 @@
 #include <complex>
 #include <condition_variable>
 #include <functional>
+#include <initializer_list>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -74,6 +75,22 @@ cplx disp1(cplx om) {
   int rc = alps_b200_disp(o, D, nullptr, nullptr, nullptr);
   if (rc) throw DispError{rc};
   return cplx(D[0], D[1]);
+}
+
+// omegas the serial algorithm is about to evaluate one after the other: one small batch into the memo of
+// alps_b200_disp (bitwise the same values); the algorithm itself is untouched
+void prefetch(std::initializer_list<cplx> oms) {
+  if (tl_broker) return;
+  double o[16];
+  int n = 0;
+  for (const cplx& w : oms) {
+    if (n == 8) break;
+    o[2 * n] = w.real();
+    o[2 * n + 1] = w.imag();
+    n++;
+  }
+  int rc = alps_b200_disp_prefetch(n, o);
+  if (rc) throw DispError{rc};
 }
 
 void Broker::run(const std::vector<std::function<void()> >& jobs) {
@@ -175,6 +192,7 @@ const double F1EM3 = (double)1.0e-3f;
 // ----------------------------------------------------------------------------- root finders
 int secant_impl(cplx& om, const alps_b200_solver_opts& o) {
   cplx prevom = om * (1.0 - o.D_prec);
+  prefetch({prevom, om});
   cplx Dprev = disp1(prevom);
   cplx minD = disp1(om), minom = om, D, jump;
   if (std::abs(Dprev) < std::abs(minD)) {
@@ -211,6 +229,7 @@ int secant_impl(cplx& om, const alps_b200_solver_opts& o) {
 int secant_osc_impl(cplx& om, const alps_b200_solver_opts& o) {
   const cplx delta(1.e-6, 1.e-8);
   const double lambda = F01, osc_threshold = F1EM3;
+  prefetch({om, om * (1.0 - o.D_prec)});
   cplx D = disp1(om), minom = om, minD = D;
   cplx prevom = om * (1.0 - o.D_prec), prev2om = om, prev3om = om, prev4om = om;
   cplx prevD = disp1(prevom), jump;
@@ -227,6 +246,10 @@ int secant_osc_impl(cplx& om, const alps_b200_solver_opts& o) {
   };
   while (iter <= o.numiter - 1 && go) {
     iter++;
+    // the oscillation test below depends on the omegas only: when this iteration will take the finite-difference
+    // Newton step, its three evaluations are independent and go out together
+    if (oscillation_count + ((iter > 4 && (close(prevom) || close(prev2om) || close(prev3om) || close(prev4om))) ? 1 : 0) > 1)
+      prefetch({om, om * (1.0 + delta), om * (1.0 - delta)});
     D = disp1(om);
     if (std::abs(D - prevD) < 1.e-80) {
       prevom = prevom + 1.e-8;
@@ -266,7 +289,9 @@ int secant_osc_impl(cplx& om, const alps_b200_solver_opts& o) {
 }
 
 cplx rtsec_impl(cplx xin, const alps_b200_solver_opts& o, int* iflag) {
-  cplx x1 = xin * 1.0, x2 = xin * (1.0 + o.D_prec), fl = disp1(x1), f = disp1(x2), xl, r, dx;
+  cplx x1 = xin * 1.0, x2 = xin * (1.0 + o.D_prec);
+  prefetch({x1, x2});
+  cplx fl = disp1(x1), f = disp1(x2), xl, r, dx;
   if (std::abs(fl) < std::abs(f)) {
     r = x1;
     xl = x2;

@@ -220,8 +220,9 @@ def main(argv=None):
         from . import _lib
         try:
             stats = (int(sol.info(_lib.INFO_D_EVALS)), int(sol.info(_lib.INFO_SET_K_CALLS)),
-                     int(sol.info(_lib.INFO_MEMO_HITS)))
-            print("D(omega,k) evaluations: %d, set_k calls: %d, disp() calls answered from the memo: %d" % stats)
+                     int(sol.info(_lib.INFO_MEMO_HITS)), int(sol.info(_lib.INFO_PREFETCHED)))
+            print("D(omega,k) evaluations: %d (%d of them batched ahead of their request), set_k calls: %d, "
+                  "disp() calls answered from the memo: %d" % (stats[0], stats[3], stats[1], stats[2]))
             main.last_stats = stats
         except Exception:
             pass

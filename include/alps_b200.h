@@ -99,6 +99,11 @@ int alps_b200_disp(const double om[2], double D[2], double *chi0, double *chi0_l
  * chi0_opt (may be NULL): n x chi0(nspec,3,3). */
 int alps_b200_disp_batch(int n, const double *om, double *D, double *chi0_opt);
 
+/* Solver aid: evaluate up to 8 omegas that are about to be requested one by one (the start pair of secant / rtsec, the
+ * om, om(1 +- delta) triple of secant_osc's Newton step, src/ALPS_fns.f90:2046) as one small batch and keep the results in
+ * the memo of alps_b200_disp; the single calls that follow return the bitwise same values without a launch. */
+int alps_b200_disp_prefetch(int n, const double *om);
+
 /* Same with device-resident buffers (om, D: 2n doubles in HBM) on the library's stream. */
 int alps_b200_disp_batch_dev(int n, const double *d_om, double *d_D);
 
@@ -153,6 +158,7 @@ int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
 #define ALPS_B200_INFO_QUAD_VARIANT 7     /* id of the quadrature kernel variant in use (>= 9: DMMA) */
 #define ALPS_B200_INFO_D_EVALS 8          /* D(omega,k) evaluations since init (every entry point)             */
 #define ALPS_B200_INFO_SET_K_CALLS 9      /* alps_b200_set_k calls since init                                   */
+#define ALPS_B200_INFO_PREFETCHED 11      /* omegas evaluated ahead of their request by alps_b200_disp_prefetch (part of D_EVALS) */
 #define ALPS_B200_INFO_MEMO_HITS 10       /* alps_b200_disp calls answered from the memo of the last omegas (same
                                              omega bits, same state: no launch; not counted in D_EVALS)          */
 

@@ -41,9 +41,9 @@ with open(out_path, "w") as fh:
                 rc = repr(e)
             t1 = time.perf_counter() - t0
             dt = t1 if dt is None else min(dt, t1)
-        d_evals, set_k, memo = getattr(run.main, "last_stats", (0, 0, 0))
+        d_evals, set_k, memo, pref = getattr(run.main, "last_stats", (0, 0, 0, 0))
         files = sorted(os.listdir(out))
-        rec = {"config": name, "rc": rc, "wall_s": dt, "D_evals": d_evals, "set_k_calls": set_k, "memo_hits": memo,
-               "disp_calls_per_s_end_to_end": (d_evals + memo) / dt if dt > 0 else None, "files": len(files)}
+        rec = {"config": name, "rc": rc, "wall_s": dt, "D_evals": d_evals, "set_k_calls": set_k, "memo_hits": memo, "prefetched": pref,
+               "disp_calls_per_s_end_to_end": (d_evals + memo - pref) / dt if dt > 0 else None, "files": len(files)}
         print(json.dumps(rec), flush=True)
         fh.write(json.dumps(rec) + "\n")

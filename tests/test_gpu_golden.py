@@ -264,6 +264,7 @@ def test_disp_memo_is_transparent(tmp_path, monkeypatch):
             rows, w2 = sol.om_scan(w, opts, scan_type=4, swi=1.0e-3, swf=2.0e-2, swlog=True, ns_steps=4, nres=1,
                                    eigen=True, heat=True, prefix=prefix, ik=1)
             hits, evals = int(sol.info(_lib.INFO_MEMO_HITS)), int(sol.info(_lib.INFO_D_EVALS))
+            evals -= int(sol.info(_lib.INFO_PREFETCHED))       # prefetched omegas are evaluated, then served as hits
             d1 = sol.disp(0.01 - 1e-6j)
             sol.set_k(1.0e-2, 3.0e-2)
             d2 = sol.disp(0.01 - 1e-6j)          # same omega, other k: must not come from the memo
@@ -275,5 +276,7 @@ def test_disp_memo_is_transparent(tmp_path, monkeypatch):
     a, b = out["1"], out["0"]
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert a[3] == b[3] and a[4] == b[4]
-    assert a[5] > 0 and b[5] == 0 and a[5] + a[6] == b[6]       # every call is either evaluated or answered
+    # every call of the serial algorithm is either evaluated or answered from the memo (a prefetched omega that the
+    # algorithm then does not ask for -- it converged first -- is the only extra work)
+    assert a[5] > 0 and b[5] == 0 and a[5] + a[6] >= b[6] and a[5] + a[6] <= b[6] + 8
     assert a[7] == b[7] and a[8] == b[8] and a[7] != a[8]
