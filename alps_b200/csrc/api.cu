@@ -71,10 +71,12 @@ struct State {
   // alps_b200_disp (one omega, no aux outputs, no NHDS species): the whole chain -- H2D of omega, five
   // kernels, D2H of D and of the error words -- is captured once into a CUDA graph and replayed while the
   // baked launch parameters (DispSig) stay the same; sequential root finding is bound by launch latency
-  cudaGraphExec_t disp_graph = nullptr;
-  std::vector<unsigned char> disp_sig;
-  long long disp_graph_launches = 0;
-  int disp_plain_calls = 0;      // plain calls since the signature last changed (the first one warms up)
+  struct GraphSlot {               // one captured chain per batch size 1..8 (the latency batch class)
+    cudaGraphExec_t exec = nullptr;
+    std::vector<unsigned char> sig;
+    long long launches = 0;
+    int plain_calls = 0;           // plain calls since the signature last changed (the first one warms up)
+  } gslot[9];
   bool capturing = false, graph_off = false, omega_major = false;
   int reslat_gx = RESLAT_GX_NARROW;   // grid width of k_resonant_lat, adapted to the number of resonant harmonics of the
                                       // previous single-omega call (they change slowly along a scan)
@@ -169,11 +171,15 @@ inline size_t ipp(int nspec, int nperp, int npar, int is0, int iperp, int ipar, 
 }
 
 void drop_disp_graph() {
-  if (S.disp_graph) cudaGraphExecDestroy(S.disp_graph);
-  S.disp_graph = nullptr;
-  S.disp_sig.clear();
-  S.disp_plain_calls = 0;
+  for (auto& g : S.gslot) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+    g.sig.clear();
+    g.plain_calls = 0;
+  }
 }
+// pinned staging of the captured chains (doubles): omegas, D, error words
+constexpr int ZC_OM = 0, ZC_D = 16, ZC_ERR = 32;
 
 void memo_clear() { S.memo_gen++; }
 inline size_t memo_slot(const unsigned long long k[2]) {
@@ -547,9 +553,9 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       int rc = prepare_external(n, d_om, &d_ext);
       if (rc) return rc;
       launch_chi_assemble(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, part, d_ext,
-                          S.zc ? S.h_pin + 2 : d_D, want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr,
+                          S.zc ? S.h_pin + ZC_D : d_D, want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr,
                           want_aux ? S.d_wave : nullptr, S.stream, S.zc ? S.d_err : nullptr,
-                          S.zc ? reinterpret_cast<int*>(S.h_pin + 8) : nullptr);
+                          S.zc ? reinterpret_cast<int*>(S.h_pin + ZC_ERR) : nullptr);
       S.launches += 4;
       return 0;
     }
@@ -563,9 +569,9 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     int rc = prepare_external(n, d_om, &d_ext);
     if (rc) return rc;
   }
-  launch_assemble(gd, S.gh, d_om, n, d_partial_in, d_ext, S.zc ? S.h_pin + 2 : d_D,
+  launch_assemble(gd, S.gh, d_om, n, d_partial_in, d_ext, S.zc ? S.h_pin + ZC_D : d_D,
                   want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr, want_aux ? S.d_wave : nullptr,
-                  S.stream, S.zc ? S.d_err : nullptr, S.zc ? reinterpret_cast<int*>(S.h_pin + 8) : nullptr);
+                  S.stream, S.zc ? S.d_err : nullptr, S.zc ? reinterpret_cast<int*>(S.h_pin + ZC_ERR) : nullptr);
   S.launches += 1;
   return 0;
 }
@@ -1163,11 +1169,18 @@ int alps_b200_disp_batch_dev(int n, const double* d_om, double* d_D) {
   return 0;
 }
 
+static int small_batch_graph(int n, const double* om, double* D, int* used);
+
 int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
   int rc = check_ready();
   if (rc) return rc;
   if (n <= 0) return 0;
   if (!om || !D) return fail(ALPS_B200_ERR_USAGE, "om / D is NULL");
+  if (!chi0_opt && n <= LAT_BATCH) {   // latency batch class: captured chain (batched roots, prefetched solver steps)
+    int used = 0;
+    if ((rc = small_batch_graph(n, om, D, &used))) return rc;
+    if (used) return 0;
+  }
   if ((rc = bind_batch(n))) return rc;
   const int nspec = S.cfg.nspec;
   if ((rc = ensure_pinned((size_t)S.batch * 4 * sizeof(double)))) return rc;
@@ -1188,39 +1201,45 @@ int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
   return 0;
 }
 
-// Signature of everything a captured single-omega chain bakes in.
-static void disp_signature(std::vector<unsigned char>& sig) {
+// Signature of everything a captured chain of n omegas bakes in.
+static void disp_signature(std::vector<unsigned char>& sig, int n) {
   QuadParams P;
-  memcpy(&P, use_lat(1) ? &S.Plat : &S.P, sizeof(P));
+  memcpy(&P, use_lat(n) ? &S.Plat : &S.P, sizeof(P));
   P.plan = S.P.plan;
   P.Sbulk = S.P.Sbulk;
   P.gwin = S.P.gwin;
   P.om = S.d_om;
-  P.n_om = 1;
-  P.nsplit = (S.mode == 1) ? 1 : nsplit_small(1);
+  P.n_om = n;
+  P.nsplit = (S.mode == 1) ? 1 : nsplit_small(n);
   const void* ptrs[] = {S.stream, S.gd, S.d_om, S.d_D, S.d_plan, S.d_work, S.d_work_count, S.d_Sbulk, S.d_Sres,
                         S.d_gwin, S.d_partial, S.d_err, S.d_rtiles, S.d_fitems, S.d_respart, S.d_restick,
                         S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
   const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)S.rtiles.size(), (long long)S.fitems.size(), S.mode,
-                            S.qv.id, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off, (long long)S.pdl_on, (long long)S.reslat_gx};
+                            S.qv.id, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off,
+                            (long long)S.pdl_on, (long long)S.reslat_gx, (long long)n};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
   memcpy(sig.data(), &P, sizeof(P));
   memcpy(sig.data() + sizeof(P), ptrs, sizeof(ptrs));
   memcpy(sig.data() + sizeof(P) + sizeof(ptrs), ints, sizeof(ints));
 }
 
-// omega is in S.h_pin[0..1]; on success with *used = 1, D is in S.h_pin[2..3]
-static int disp_via_graph(int* used) {
+// n <= LAT_BATCH omegas are in S.h_pin[ZC_OM ..]; on success with *used = 1 the D's are in S.h_pin[ZC_D ..]
+static int disp_via_graph(int n, int* used) {
   *used = 0;
+  static_assert(LAT_BATCH + 1 <= (int)(sizeof(S.gslot) / sizeof(S.gslot[0])) && 2 * LAT_BATCH <= ZC_D, "graph slots");
+  if (n < 1 || n > LAT_BATCH) return 0;
+  State::GraphSlot& gs = S.gslot[n];
   std::vector<unsigned char> sig;
-  disp_signature(sig);
-  if (sig != S.disp_sig) {
-    drop_disp_graph();
-    S.disp_sig = sig;
+  disp_signature(sig, n);
+  if (sig != gs.sig) {
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+    gs.exec = nullptr;
+    gs.plain_calls = 0;
+    gs.sig = sig;
   }
-  if (!S.disp_graph) {
+  if (!gs.exec) {
     // the first call after a change runs the plain path (first-use kernel attributes, lazy module loading)
-    if (S.disp_plain_calls++ < 1) return 0;
+    if (gs.plain_calls++ < 1) return 0;
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(S.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       cudaGetLastError();
@@ -1228,42 +1247,55 @@ static int disp_via_graph(int* used) {
       return 0;
     }
     S.capturing = true;
-    S.zc = !S.zc_off && plan_fused_ok(S.gh, 1);
+    S.zc = !S.zc_off && plan_fused_ok(S.gh, n);
     g_pdl_launch = S.pdl_on && S.zc;
     const long long l0 = S.launches;
-    if (!S.zc) cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream);
-    const int rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, false);
+    if (!S.zc) cudaMemcpyAsync(S.d_om, S.h_pin + ZC_OM, 2 * n * sizeof(double), cudaMemcpyHostToDevice, S.stream);
+    const int rc = run_chunk(n, S.d_om, S.d_D, nullptr, nullptr, false);
     if (!S.zc) {
-      cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream);
-      cudaMemcpyAsync(S.h_pin + 8, S.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream);
+      cudaMemcpyAsync(S.h_pin + ZC_D, S.d_D, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, S.stream);
+      cudaMemcpyAsync(S.h_pin + ZC_ERR, S.d_err, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream);
     }
     S.zc = false;
     g_pdl_launch = false;
     S.capturing = false;
-    S.disp_graph_launches = S.launches - l0;
+    gs.launches = S.launches - l0;
     S.launches = l0;
     const cudaError_t e1 = cudaStreamEndCapture(S.stream, &graph);
     cudaError_t e2 = cudaSuccess;
-    if (e1 == cudaSuccess && !rc) e2 = cudaGraphInstantiate(&S.disp_graph, graph, 0);
+    if (e1 == cudaSuccess && !rc) e2 = cudaGraphInstantiate(&gs.exec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
     if (e1 != cudaSuccess || e2 != cudaSuccess || rc) {
       cudaGetLastError();
-      S.disp_graph = nullptr;
+      gs.exec = nullptr;
       S.graph_off = true;   // fall back to plain launches for the rest of the session
       return 0;
     }
   }
-  CK(cudaGraphLaunch(S.disp_graph, S.stream));
+  CK(cudaGraphLaunch(gs.exec, S.stream));
   CK(cudaStreamSynchronize(S.stream));
-  S.launches += S.disp_graph_launches;
-  S.d_evals += 1;
-  const int* herr = reinterpret_cast<const int*>(S.h_pin + 8);
+  S.launches += gs.launches;
+  S.d_evals += n;
+  const int* herr = reinterpret_cast<const int*>(S.h_pin + ZC_ERR);
   if (herr[0] || herr[6]) return check_device_errors();   // reports and clears the device error words
   // herr[7] = resonant harmonics of this call: widen / narrow the next call's k_resonant_lat grid (the signature
   // changes, so the graph is captured again -- rare, the count changes slowly along a scan)
-  if (herr[7] > RESLAT_GX_NARROW) S.reslat_gx = RESLAT_GX_WIDE;
-  else if (herr[7] <= RESLAT_GX_NARROW / 2) S.reslat_gx = RESLAT_GX_NARROW;
+  if (herr[7] > RESLAT_GX_NARROW * n) S.reslat_gx = RESLAT_GX_WIDE;
+  else if (herr[7] <= (RESLAT_GX_NARROW / 2) * n) S.reslat_gx = RESLAT_GX_NARROW;
   *used = 1;
+  return 0;
+}
+
+// n <= LAT_BATCH omegas (host) through the captured chain when possible; *used = 0: caller takes the plain path
+static int small_batch_graph(int n, const double* om, double* D, int* used) {
+  *used = 0;
+  if (S.graph_off || S.stream == nullptr || S.ext_any || n < 1 || n > LAT_BATCH) return 0;
+  int rc;
+  if ((rc = bind_batch(n))) return rc;
+  if ((rc = ensure_pinned(64 * sizeof(double)))) return rc;
+  memcpy(S.h_pin + ZC_OM, om, 2 * (size_t)n * sizeof(double));
+  if ((rc = disp_via_graph(n, used))) return rc;
+  if (*used && D) memcpy(D, S.h_pin + ZC_D, 2 * (size_t)n * sizeof(double));
   return 0;
 }
 
@@ -1279,34 +1311,34 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   if ((rc = bind_batch(1))) return rc;
   const int nspec = S.cfg.nspec;
   if ((rc = ensure_pinned(64 * sizeof(double)))) return rc;
-  S.h_pin[0] = om[0];
-  S.h_pin[1] = om[1];
+  S.h_pin[ZC_OM] = om[0];
+  S.h_pin[ZC_OM + 1] = om[1];
   if (plain_D && !S.graph_off && S.stream != nullptr) {
     int used = 0;
-    if ((rc = disp_via_graph(&used))) return rc;
+    if ((rc = disp_via_graph(1, &used))) return rc;
     if (used) {
       if (D) {
-        D[0] = S.h_pin[2];
-        D[1] = S.h_pin[3];
+        D[0] = S.h_pin[ZC_D];
+        D[1] = S.h_pin[ZC_D + 1];
       }
-      if (S.memo_on) memo_store(om, S.h_pin + 2);
+      if (S.memo_on) memo_store(om, S.h_pin + ZC_D);
       return 0;
     }
   }
-  CK(cudaMemcpyAsync(S.d_om, S.h_pin, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+  CK(cudaMemcpyAsync(S.d_om, S.h_pin + ZC_OM, 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
   const bool aux = chi0 || chi0_low || wave;
   if ((rc = run_chunk(1, S.d_om, S.d_D, nullptr, nullptr, aux))) return rc;
-  CK(cudaMemcpyAsync(S.h_pin + 2, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  CK(cudaMemcpyAsync(S.h_pin + ZC_D, S.d_D, 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if (chi0) CK(cudaMemcpyAsync(chi0, S.d_chi0, (size_t)nspec * 18 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if (chi0_low)
     CK(cudaMemcpyAsync(chi0_low, S.d_chi0_low, (size_t)nspec * 54 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if (wave) CK(cudaMemcpyAsync(wave, S.d_wave, 18 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   if ((rc = check_device_errors())) return rc;
   if (D) {
-    D[0] = S.h_pin[2];
-    D[1] = S.h_pin[3];
+    D[0] = S.h_pin[ZC_D];
+    D[1] = S.h_pin[ZC_D + 1];
   }
-  if (plain_D && S.memo_on) memo_store(om, S.h_pin + 2);
+  if (plain_D && S.memo_on) memo_store(om, S.h_pin + ZC_D);
   // external (NHDS) contributions are per omega: consumed by this call
   if (S.ext_any) {
     std::fill(S.ext.begin(), S.ext.end(), 0.0);
@@ -1335,7 +1367,7 @@ int alps_b200_disp_prefetch(int n, const double* om) {
     m++;
   }
   if (m < 2) return 0;   // a single omega is faster through the graph of alps_b200_disp
-  if ((rc = alps_b200_disp_batch(m, todo, D, nullptr))) return rc;
+  if ((rc = alps_b200_disp_batch(m, todo, D, nullptr))) return rc;   // <= LAT_BATCH omegas: the captured chain
   for (int j = 0; j < m; j++) memo_store(todo + 2 * j, D + 2 * j);
   S.prefetched += m;
   return 0;
