@@ -536,6 +536,9 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
                          : launch_quad(S.P, S.qv.id, false, S.stream);
     if (!S.capturing) cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
+    if (S.mode == 0 && !use_lat(n) && S.qv.id == 15 && S.P.tile_major && S.P.ntiles_rem > 0 &&
+        S.P.ntiles_rem < S.P.ntiles)
+      S.launches += 1;   // regular tiles + packed remainder tiles: two launches of k_quad_mma
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.d_respart,
                     S.d_restick, S.stream, S.reslat_gx);
     if (!S.rtiles.empty()) {
@@ -1086,6 +1089,16 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
         make_tmap(&S.P.tmW[s], h.d_W, 3 * (d.nhi + 1), nperp - 1, d.ldw, 3 * S.qv.NH, S.qv.BK))
       return ALPS_B200_ERR_CUDA;
   }
+  // DMMA variants: tiles whose upper 8-harmonic group holds at most two harmonics of the summed range go last; throughput
+  // launches run them through the packed instantiation of k_quad_mma (quad_mma.cu, PK)
+  int ntiles_rem = 0;
+  static const bool no_pack = getenv("ALPS_B200_NO_PACK") != nullptr;   // A/B knob
+  if (S.qv.id >= 9 && !no_pack) {
+    auto is_rem = [&](const QuadTile& t) { return S.gh.sp[t.s].nhi_shard <= t.n0 + 9; };
+    std::stable_partition(S.tiles.begin(), S.tiles.end(), [&](const QuadTile& t) { return !is_rem(t); });
+    for (const QuadTile& t : S.tiles) ntiles_rem += is_rem(t) ? 1 : 0;
+  }
+  S.P.ntiles_rem = ntiles_rem;
   const bool ni_changed = item_base != S.gh.NI;
   S.gh.NI = item_base;
   CK(cudaMemcpyAsync(S.gd, &S.gh, sizeof(GlobalDev), cudaMemcpyHostToDevice, S.stream));

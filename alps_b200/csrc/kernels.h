@@ -25,6 +25,8 @@ struct QuadParams {
   double* gwin;            // n_om * NI * WINX * 6
   double* gtab[MAXSPEC];   // k-hoisted tables (STORE launches only)
   int ntiles;
+  int ntiles_rem;          // the last ntiles_rem tiles are species' last tiles whose upper 8-harmonic group holds <= 2
+                           // harmonics of the summed range (quad_mma.cu, PK instantiation); 0: none / not sorted
   int n_om;
   int nsplit;              // CTAs per (omega, tile) along p_par; Sbulk then holds nsplit partial rows per item
   // DMMA variants (quad_mma.cu): fragment-ordered copies of A', C', W and their padded k-step count

@@ -60,7 +60,8 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // HS = 1: a warp owns all 16 harmonics of its 16 columns (6 M-tiles); HS = 2: two warps share the column
 // block, one per group of 8 harmonics (3 M-tiles each) -- 4 warps per SM sub-partition instead of 2 hide
 // the stage hand-over (barrier wait, first fragment loads) of one warp behind the DMMAs of the others.
-template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0>
+// PK = 1: instantiation for the species' last tiles when their upper harmonic group is (nearly) empty -- see `pack`
+template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0, int PK = 0>
 __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1)) k_quad_mma(const __grid_constant__ QuadParams P) {
   constexpr int TW = 16 * NW;     // p_par columns per tile
   constexpr int MT = 6 / HS;      // M-tiles per warp
@@ -133,6 +134,21 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
   const size_t item0 = (size_t)iom * g.NI + sp.item_base;
   const int WIN = g.WIN, WINX = g.WINX, M_I = g.M_I;
 
+  // PK = 1, HS = 2: the 8 harmonics n0 + 8 hsel .. + 7 of this warp's group.  In a species' last tile the group may
+  // hold only one or two harmonics of the summed range, or none (201 harmonics = 12 1/2 tiles + 1): their 3 r weight
+  // rows then go into ONE M-tile (row 3 j + x = harmonic j, weight type x; the other rows zero) instead of one M-tile
+  // per weight type, and an empty group issues no DMMA at all.  Same products, same order over p_perp: the sums are
+  // bitwise those of the regular layout.  A separate instantiation, so that the regular tiles keep their code.
+  int pack = 0;   // 0 regular: 3 M-tiles;  1 packed: 1 M-tile;  2 empty
+  int pack_hi = 0;
+  if (PK == 1 && HS == 2) {
+    const int g0 = tile.n0 + 8 * hsel;
+    const int lo = max(sp.nlo_shard, g0), hi = min(sp.nhi_shard, g0 + 7);
+    if (hi < lo) pack = 2;
+    else if (lo == g0 && hi - g0 <= 1) pack = 1;
+    pack_hi = hi - g0;
+  }
+
   // this lane's share of the moment sums.  HS = 1: harmonic n0 + 8 (tq >> 1) + gq, sign tq & 1, all 12;
   // HS = 2: harmonic n0 + 8 hsel + gq, sign tq >> 1, sums 6 (tq & 1) .. + 5
   double mine[NSUM];
@@ -167,6 +183,25 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
       const double* sA = sm.st[stage].A + 64 * warp + 2 * lane;
       const double* sC = sm.st[stage].C + 64 * warp + 2 * lane;
       const double* sW = sm.st[stage].W + 6 * lane;
+      if (PK == 1 && HS == 2 && pack != 0) {
+        if (pack == 1) {
+          // packed M-tile: this lane's A operand is row gq = 3 j + x, i.e. W_x of harmonic j of the group, which the
+          // regular fragment layout keeps at lane (j, tq), slot 2 x + hsel
+          const int j = gq / 3, x = gq - 3 * j;
+          const bool on = gq < 6 && j <= pack_hi;
+          const double* sWp = sm.st[stage].W + 6 * (4 * (on ? j : 0) + tq) + 2 * (on ? x : 0) + hsel;
+#pragma unroll
+          for (int ks = 0; ks < KSTG; ks++) {
+            const double2 a = *reinterpret_cast<const double2*>(sA + ks * KS_A);
+            const double2 c = *reinterpret_cast<const double2*>(sC + ks * KS_A);
+            const double wv = on ? sWp[ks * KS_W] : 0.0;
+            dmma(acc[0][0][0], wv, a.x);
+            dmma(acc[0][0][1], wv, a.y);
+            dmma(acc[0][1][0], wv, c.x);
+            dmma(acc[0][1][1], wv, c.y);
+          }
+        }
+      } else
 #pragma unroll
       for (int ks = 0; ks < KSTG; ks++) {
         const int kq = (DBG == 1) ? 0 : ks;   // DBG 1: one fragment load per stage
@@ -197,6 +232,18 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
       }
     }
 
+    if (PK == 1 && HS == 2 && pack == 1) {
+      // unpack: lane (gq = j, tq) collects the three weight types of harmonic j from rows 3 j + x of the packed
+      // M-tile (lanes 4 (3 j + x) + tq); lanes with gq >= 2 hold no harmonic of the summed range and are skipped
+      // by the epilogue
+#pragma unroll
+      for (int x = 2; x >= 0; x--) {
+        const int src = (4 * (3 * gq + x) + tq) & 31;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          (&acc[x % MT][0][0][0])[q] = __shfl_sync(0xffffffffu, (&acc[0][0][0][0])[q], src);
+      }
+    }
     // ------------------------------------------------------------ epilogue of this p_par tile
     // this thread: harmonics n0 + 8 h + gq (HS = 1: h = 0,1; HS = 2: h = hsel), columns ipar0 + 8 j + e
     const int ipar0 = nt * TW + 16 * warp + 2 * tq + 1;
@@ -339,18 +386,18 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
   }
 }
 
-template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0>
+template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0, int PK = 0>
 static cudaError_t launch_mma_one(const QuadParams& P, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = sizeof(MmaSmem<NW, KSTG, NST>) + 128;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_quad_mma<NW, HS, KSTG, NST, STORE, DBG>,
+    cudaError_t e = cudaFuncSetAttribute(k_quad_mma<NW, HS, KSTG, NST, STORE, DBG, PK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_chain(k_quad_mma<NW, HS, KSTG, NST, STORE, DBG>, dim3(P.n_om * P.ntiles * P.nsplit), dim3(32 * NW * HS),
-                      smem, st, P);
+  return launch_chain(k_quad_mma<NW, HS, KSTG, NST, STORE, DBG, PK>, dim3(P.n_om * P.ntiles * P.nsplit),
+                      dim3(32 * NW * HS), smem, st, P);
 }
 template <int NW, int HS, int KSTG, int NST>
 static cudaError_t launch_mma_variant(const QuadParams& P, bool store, cudaStream_t st) {
@@ -362,7 +409,20 @@ cudaError_t launch_quad_mma(const QuadParams& P, int variant, bool store, cudaSt
   if (P.n_om <= 0 || P.ntiles <= 0) return cudaSuccess;
   switch (variant) {
     case 12: return launch_mma_variant<4, 1, 8, 2>(P, store, st);   // 2 CTAs of 4 warps per SM
-    case 15: return launch_mma_variant<8, 2, 8, 2>(P, store, st);   // 16 warps: 4 per SM sub-partition
+    case 15: {   // 16 warps: 4 per SM sub-partition
+      // throughput batches: the species' last tiles with a (nearly) empty upper harmonic group (the last P.ntiles_rem
+      // entries of P.tiles) go through the PK = 1 instantiation in a second launch
+      if (!store && P.tile_major && P.ntiles_rem > 0 && P.ntiles_rem <= P.ntiles) {
+        QuadParams A = P, B = P;
+        A.ntiles = P.ntiles - P.ntiles_rem;
+        B.tiles = P.tiles + A.ntiles;
+        B.ntiles = P.ntiles_rem;
+        cudaError_t e = A.ntiles > 0 ? launch_mma_one<8, 2, 8, 2, false>(A, st) : cudaSuccess;
+        if (e != cudaSuccess) return e;
+        return launch_mma_one<8, 2, 8, 2, false, 0, 1>(B, st);
+      }
+      return launch_mma_variant<8, 2, 8, 2>(P, store, st);
+    }
 #ifdef ALPS_QUAD_DEBUG
     case 91: return launch_mma_one<8, 2, 8, 2, false, 1>(P, st);
     case 92: return launch_mma_one<8, 2, 8, 2, false, 2>(P, st);

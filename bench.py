@@ -64,7 +64,10 @@ def build_plasma(w):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampled every 50 ms during the timed region; the reported clock is the median over the samples taken
+    while the GPU was busy (utilisation >= 50 %), with the minimum and the power draw beside it, so a power- or
+    thermally-limited clock under the FP64 load shows up instead of hiding behind the idle boost clock."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -75,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.p = None
@@ -89,24 +92,34 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
             out, _ = self.p.communicate()
-        sm, smax, reasons = [], [], set()
+        rows, smax, reasons = [], [], set()
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
+                sm, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
+            try:
+                pw = float(f[3])
+            except ValueError:
+                pw = None
+            try:
+                ut = float(f[4])
+            except ValueError:
+                ut = None
+            rows.append((sm, pw, ut))
+            smax.append(mx)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        # samples taken while the GPU is busy have the highest clocks; use the upper half
-        sm_sorted = sorted(sm)
-        busy = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None,
-                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+        busy = [r for r in rows if r[2] is not None and r[2] >= 50.0] or rows
+        sm_b = [r[0] for r in busy]
+        pw_b = [r[1] for r in busy if r[1] is not None]
+        return {"sm_mhz": float(np.median(sm_b)) if sm_b else None, "sm_mhz_min": min(sm_b) if sm_b else None,
+                "sm_max_mhz": max(smax) if smax else None, "power_w": float(np.median(pw_b)) if pw_b else None,
+                "reasons": sorted(reasons), "samples": len(rows), "samples_busy": len(busy) if rows else 0}
 
 
 def cpu_sample(w, plasma, om, ncap=None, threads=0):

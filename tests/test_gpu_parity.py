@@ -3,6 +3,8 @@ inputs.  Tolerance 1e-9 (BASELINE.json north_star), applied as SURVEY.md section
 chi0 element-wise (tests.util.chi_err), wave(i,j) relative to the magnitude of the terms summed into
 it, D relative to the magnitude of its summed products -- at a root D and wave(1,1) are
 cancellations, so "relative to |D|" is meaningless there."""
+import os
+
 import numpy as np
 import pytest
 
@@ -10,6 +12,7 @@ from alps_b200 import tables
 from tests.util import chi_err, det_scale, omega_samples, scaled_err, tensor_err, wave_scale
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-9
 
 
@@ -497,3 +500,37 @@ def test_single_omega_graph_knobs_are_bitwise_neutral(monkeypatch):
             assert a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
     for name in KNOBS:
         monkeypatch.delenv(name, raising=False)
+
+
+def test_packed_remainder_tiles_are_bitwise_neutral(monkeypatch):
+    """Throughput batches send a species' last harmonic tile through the packed instantiation of k_quad_mma when its
+    upper group of 8 harmonics holds at most two harmonics of the summed range (their weight rows share one M-tile,
+    an empty group issues no DMMA).  Same products in the same order: bitwise the D of the regular layout
+    (ALPS_B200_NO_PACK=1), for 1, 2, 9 and 10 harmonics in the last tile."""
+    import subprocess, sys, json
+    code = r"""
+import json, sys, numpy as np
+sys.path.insert(0, %r)
+from alps_b200 import tables
+from alps_b200.solver import Solver
+from tests.util import omega_samples
+pl = tables.config_small(48, 96, kind=2)
+oms = np.array(list(omega_samples(21, 96, (0.05, 2.0), (-0.03, 0.03))))
+out = {}
+for nmax in (16, 17, 24, 25, 31):
+    sol = Solver(pl, nmax_force=nmax)
+    sol.set_k(1.5, 0.05)
+    out[nmax] = sol.disp_batch(oms).view(np.float64).tolist()
+    sol.close()
+print(json.dumps(out))
+""" % ROOT
+    res = {}
+    for tag, env in (("packed", {}), ("regular", {"ALPS_B200_NO_PACK": "1"})):
+        e = {k: v for k, v in os.environ.items() if k != "ALPS_B200_NO_PACK"}
+        e.update(env)
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[tag] = json.loads(p.stdout.strip().splitlines()[-1])
+    for nmax in res["packed"]:
+        a, b = np.array(res["packed"][nmax]), np.array(res["regular"][nmax])
+        assert np.all(np.isfinite(a)) and np.array_equal(a, b), nmax
