@@ -150,6 +150,9 @@ def cpu_sample(w, plasma, om, ncap=None, threads=0):
     orc.disp(complex(om))
     dt = time.perf_counter() - t0
     frac = sum(2 * ncap + 1 for _ in nmax) / float(sum(2 * int(n) + 1 for n in nmax))
+    if getattr(cpu_sample, "_ncap", None) == ncap and dt < 0.6 * CPU_SAMPLE_TARGET_S:
+        # the small calibration run over-estimates the cost per harmonic (fixed work, load balance): grow the next sample
+        cpu_sample._ncap = max(ncap, min(int((2 * ncap + 1) * CPU_SAMPLE_TARGET_S / dt - 1) // 2, int(min(nmax))))
     return {"seconds_sample": dt, "fraction": frac, "d_per_s": frac / dt, "cores": cores, "ncap": ncap,
             "nmax": [int(n) for n in nmax]}
 
