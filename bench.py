@@ -171,7 +171,9 @@ def run_reference(args, w, rank, world):
     ms = float(np.mean([v["seconds_sample"] for v in vals])) * 1e3
     sample = ("one D evaluation restricted to |n|<=%d (%.2f%% of the signed harmonics), scaled; restated "
               "reference (CPU oracle, OpenMP over harmonics); Fortran/MPI build impossible here"
-              % (vals[0]["ncap"], 100 * vals[0]["fraction"]))
+              % (vals[-1]["ncap"], 100 * vals[-1]["fraction"]))
+    if len({v["ncap"] for v in vals}) > 1:
+        sample += "; |n| cap per timed step: %s" % [v["ncap"] for v in vals]
     line = {"impl": "reference", "metric": "D(omega,k) evals/sec", "value": dps, "unit": "D/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
