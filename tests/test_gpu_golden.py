@@ -280,3 +280,40 @@ def test_disp_memo_is_transparent(tmp_path, monkeypatch):
     # algorithm then does not ask for -- it converged first -- is the only extra work)
     assert a[5] > 0 and b[5] == 0 and a[5] + a[6] >= b[6] and a[5] + a[6] <= b[6] + 8
     assert a[7] == b[7] and a[8] == b[8] and a[7] != a[8]
+
+
+def test_newton_step_speculation_for_serial_callers(monkeypatch):
+    """A serial solver that only ever calls disp(om) -- the Fortran secant_osc behind the shim; here its Python
+    restatement (oracle/driver.py, test infrastructure) driving Solver.disp -- gets its finite-difference Newton triple
+    om, om(1+delta), om(1-delta) evaluated as one batch once alps_b200_disp has seen that request pattern.  Same
+    omegas, same D's, same root; fewer launches."""
+    import time
+    from alps_b200 import _lib
+    from alps_b200.solver import Solver
+    from oracle import driver
+    pl = tables.config_kpar_fast()
+    out = {}
+    for spec in ("1", "0"):
+        monkeypatch.setenv("ALPS_B200_SPECULATE", spec)
+        sol = Solver(pl, emulate_nproc=4)
+        try:
+            sol.set_k(1.0e-2, 2.0e-2)
+            seen = []
+
+            def disp(om):
+                d = sol.disp(complex(om))
+                seen.append((complex(om), d))
+                return d
+            t0 = time.perf_counter()
+            root = driver.secant_osc(disp, complex(1.99e-2, -1.0e-5), 80, 1.0e-30, 1.0e-5)
+            dt = time.perf_counter() - t0
+            out[spec] = (root, seen, int(sol.info(_lib.INFO_PREFETCHED)), int(sol.info(_lib.INFO_D_EVALS)),
+                         int(sol.info(_lib.INFO_MEMO_HITS)), dt)
+        finally:
+            sol.close()
+    monkeypatch.delenv("ALPS_B200_SPECULATE")
+    a, b = out["1"], out["0"]
+    assert a[0] == b[0] and a[1] == b[1]                     # identical request / answer sequence, identical root
+    assert b[2] == 0 and a[2] > 0                            # triples went out as batches
+    assert a[3] + a[4] >= b[3] + b[4]                        # nothing asked for was skipped
+    print("speculation: %d omegas batched ahead, %.1f ms vs %.1f ms" % (a[2], a[5] * 1e3, b[5] * 1e3))
