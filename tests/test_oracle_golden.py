@@ -55,3 +55,22 @@ def test_golden_kpar_scan_33_rows():
         assert _fmt5(kperp) == g[0] and _fmt5(kpar) == g[1]
         assert _fmt5(om.real) == g[2], (kpar, om, g)
         assert _fmt5(om.imag) == g[3], (kpar, om, g)
+
+
+def test_chi_known_answers_of_the_survey_probe():
+    """un-normalised chi diagonals at the last golden root (k = (1e-2, 1e-1)), computed there
+    independently of this repository with scipy's Bessel functions (trusted to ~7 digits): pins chi itself, not only
+    the roots.  Only n = 0 is resonant for both species at this omega."""
+    pl = tables.config_kpar_fast()
+    orc = Oracle(pl, nproc=4)
+    assert list(orc.set_k(1.0e-2, 1.0e-1)) == [21, 13]
+    om = complex(9.2594146e-2, -2.8659349e-4)
+    D, chi0, low, wave = orc.disp(om, full=True)
+    un = chi0 * (om ** 2 * pl.vA ** 2)
+    want = [[8.79481e-3 - 5.4906e-5j, 8.6933e-3 + 1.4282e-5j, 1.58714e-3 + 1.1828035j],
+            [8.83923e-6 - 2.8932e-8j, 8.34002e-6 + 3.78767e-6j, 1.7251811 + 1.2189672e-1j]]
+    for s in range(2):
+        for i in range(3):
+            assert abs(un[s, i, i] - want[s][i]) <= 5e-6 * abs(want[s][i]), (s, i, un[s, i, i], want[s][i])
+    # and omega is the root of the golden scan's last row to its printed digits: |D| is ~1e-13 of its term scale
+    assert abs(D) < 1e-9 * float(np.max(np.abs(wave))) ** 3
