@@ -111,3 +111,40 @@ def scan_k(oracle, kperp0: float, kpar0: float, scan_type: int, swf: float, nste
         om = method(oracle.disp, om, numiter, D_threshold, D_prec)
         rows.append((kperp, kpar, om))
     return rows
+
+
+def calc_eigen(oracle, omega: complex, kperp: float, kpar: float, vA: float, ns, qs, current_int=None):
+    """calc_eigen, src/ALPS_fns.f90:2605-2899, on top of the oracle's disp(full=True): electric and magnetic
+    eigenfunctions (E_x = 1), species velocity and density fluctuations, heating rates P_s and the wave energy W_EM
+    (chi at real omega and at 1.000001 omega for d(chi_h)/d(omega)).  Returns (ef[3], bf[3], Us[nspec,3], ds[nspec],
+    Ps[nspec], W_EM) -- the columns of the .eigen_* and .heat_* files (:2334-2340)."""
+    nspec = len(ns)
+    _, chi0, _, w = oracle.disp(omega, full=True)
+    e = np.zeros(3, dtype=complex)
+    e[0] = 1.0
+    e[2] = -e[0] * (w[1, 0] * w[2, 1] - w[2, 0] * w[1, 1]) / (w[1, 2] * w[2, 1] - w[2, 2] * w[1, 1])
+    if abs(w[2, 1]) != 0.0:
+        e[1] = (-e[2] * w[2, 2] - e[0] * w[2, 0]) / w[2, 1]
+    else:
+        e[1] = (w[1, 0] * w[0, 2] - w[0, 0] * w[1, 2]) / (w[1, 2] * w[0, 1] - w[1, 1] * w[0, 2])
+    b = np.array([-kpar * e[1], -(kperp * e[2] - kpar * e[0]), kperp * e[1]]) / (omega * vA)
+    pflow = np.zeros(nspec) if current_int is None else np.asarray(current_int) / (np.asarray(ns) * np.asarray(qs))
+    Us = np.zeros((nspec, 3), dtype=complex)
+    ds = np.zeros(nspec, dtype=complex)
+    for s in range(nspec):
+        base = [-(vA * vA / (qs[s] * ns[s])) * 1j * omega * sum(e[q] * chi0[s, j, q] for q in range(3)) for j in range(3)]
+        Us[s] = base
+        if pflow[s] != 0.0:
+            Us[s, 2] = (base[2] - pflow[s] * kperp * Us[s, 0] / (omega - kpar * pflow[s])) / \
+                       (1.0 + (kpar * pflow[s]) / (omega - kpar * pflow[s]))
+        ds[s] = (1.0 / vA) * (Us[s, 0] * kperp + Us[s, 2] * kpar) / (omega - kpar * pflow[s])
+    # heating: anti-Hermitian part of chi at real omega, Hermitian part at omega and 1.000001 omega
+    _, c_r, _, _ = oracle.disp(complex(omega.real, 0.0), full=True)
+    chia = np.array([-0.5j * (c_r[s] - c_r[s].conj().T) for s in range(nspec)])
+    chih_old = 0.5 * sum(c_r[s] + c_r[s].conj().T for s in range(nspec))
+    Psc = np.array([np.conj(e) @ chia[s] @ e for s in range(nspec)])
+    _, c_p, _, _ = oracle.disp(complex((omega * 1.000001).real, 0.0), full=True)
+    chih = 0.5 * sum(c_p[s] + c_p[s].conj().T for s in range(nspec))
+    dchih = (1.000001 * chih - chih_old) / 0.000001
+    W_EM = float((np.conj(e) @ dchih @ e + np.sum(b * np.conj(b))).real)
+    return e, b, Us, ds, Psc.real / W_EM, W_EM

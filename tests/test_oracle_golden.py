@@ -55,6 +55,25 @@ def test_golden_kpar_scan_33_rows():
         assert _fmt5(kperp) == g[0] and _fmt5(kpar) == g[1]
         assert _fmt5(om.real) == g[2], (kpar, om, g)
         assert _fmt5(om.imag) == g[3], (kpar, om, g)
+    # the .eigen_* and .heat_* goldens of the same run pin the side outputs of disp() -- wave (E, B), chi0 per species
+    # (velocity / density fluctuations, heating rates at real omega) and d(chi_h)/d(omega) (W_EM) -- through the
+    # restatement of calc_eigen (oracle/driver.py): every column of every row to the 5 printed digits (last digit free)
+    ge = np.loadtxt(os.path.join(GOLD, "test_kpar_fast.eigen_kpara_1.root_1"))
+    gh = np.loadtxt(os.path.join(GOLD, "test_kpar_fast.heat_kpara_1.root_1"))
+    ns = [sp.ns for sp in pl.species]
+    qs = [sp.qs for sp in pl.species]
+    for row, (kperp, kpar, om) in enumerate(rows):
+        if row % 4 and row != 32:
+            continue                                  # every fourth row and the last: keeps the CPU suite short
+        orc.set_k(kperp, kpar)
+        e, b, Us, ds, Ps, W = driver.calc_eigen(orc, om, kperp, kpar, pl.vA, ns, qs)
+        ri = lambda z: np.array([np.ravel(z).real, np.ravel(z).imag]).T.ravel()
+        mine = np.concatenate([[kperp, kpar, om.real, om.imag], ri(e), ri(b), ri(Us), ri(ds)])
+        assert mine.shape == ge[row].shape
+        tol = 2e-4 * np.maximum(np.abs(ge[row]), 1e-3 * np.max(np.abs(ge[row])))
+        assert np.all(np.abs(mine - ge[row]) <= tol), (row, mine, ge[row])
+        heat = np.concatenate([[kperp, kpar, om.real, om.imag], Ps, [W]])
+        assert np.all(np.abs(heat[4:] - gh[row][4:]) <= 2e-4 * np.abs(gh[row][4:])), (row, heat, gh[row])
 
 
 def test_chi_known_answers_of_the_survey_probe():
