@@ -160,5 +160,9 @@ def test_map_grid_and_finish_are_host_only_and_follow_map_search(tmp_path):
         lines = open(path).read().split("\n")
         assert len(lines[0]) == 5 * 16 and lines[ni] == ""
         assert len([l for l in lines if l.strip()]) == nr * ni
+        def es16(v):      # Fortran es16.6e3
+            m, ex = ("%.6E" % v).split("E")
+            return ("%sE%s%03d" % (m, "-" if int(ex) < 0 else "+", abs(int(ex)))).rjust(16)
+        assert lines[0] == "".join(es16(v) for v in (om[0, 0].real, om[0, 0].imag, val[0, 0], cal[0, 0].real, cal[0, 0].imag))
         first = [float(x) for x in lines[0].split()]
         assert abs(first[0] - wr[0]) <= 1e-6 * wr[0] and abs(first[2] - val[0, 0]) <= 1e-6 * abs(val[0, 0])
