@@ -534,3 +534,33 @@ print(json.dumps(out))
     for nmax in res["packed"]:
         a, b = np.array(res["packed"][nmax]), np.array(res["regular"][nmax])
         assert np.all(np.isfinite(a)) and np.array_equal(a, b), nmax
+
+
+def test_committed_oracle_vectors():
+    """The CUDA path against the committed oracle fixture tests/golden/oracle_vectors.npz (no oracle call here):
+    chi0 / chi0_low element-wise, wave and D with the scale-aware 1e-9 criterion of the live parity tests."""
+    from alps_b200.solver import Solver
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "oracle_vectors.npz"))
+    makers = {"small_bimax": (lambda: tables.config_small(24, 48, kind=1), 0),
+              "small_kappa": (lambda: tables.config_small(24, 48, kind=2), 0),
+              "kpar_fast": (tables.config_kpar_fast, 4)}
+    for name, (make, nproc) in makers.items():
+        pl = make()
+        kperp, kpar = (float(x) for x in ref[name + "_k"])
+        sol = Solver(pl, emulate_nproc=nproc)
+        try:
+            assert list(sol.set_k(kperp, kpar)) == list(ref[name + "_nmax"])
+            oms = ref[name + "_om"]
+            Db = sol.disp_batch(oms)
+            for i, om in enumerate(oms):
+                Dg, chi_g, low_g, wave_g = sol.disp(complex(om), full=True)
+                chi_o, low_o, wave_o, Do = ref[name + "_chi0"][i], ref[name + "_chi0_low"][i], ref[name + "_wave"][i], ref[name + "_D"][i]
+                ws = wave_scale(chi_o, complex(om), pl.vA, kperp, kpar)
+                assert scaled_err(wave_g, wave_o, ws) < TOL, (name, om)
+                assert abs(Dg - Do) / det_scale(ws) < TOL and abs(Db[i] - Do) / det_scale(ws) < TOL, (name, om)
+                for s in range(pl.nspec):
+                    assert chi_err(chi_g[s], chi_o[s]) < TOL, (name, om, s)
+                    for m in range(3):
+                        assert chi_err(low_g[s, :, :, m], low_o[s, :, :, m]) < TOL, (name, om, s, m)
+        finally:
+            sol.close()

@@ -93,3 +93,21 @@ def test_chi_known_answers_of_the_survey_probe():
             assert abs(un[s, i, i] - want[s][i]) <= 5e-6 * abs(want[s][i]), (s, i, un[s, i, i], want[s][i])
     # and omega is the root of the golden scan's last row to its printed digits: |D| is ~1e-13 of its term scale
     assert abs(D) < 1e-9 * float(np.max(np.abs(wave))) ** 3
+
+
+def test_oracle_reproduces_its_committed_vectors():
+    """tests/golden/oracle_vectors.npz (written by tests/golden/make_oracle_vectors.py): the oracle of today gives the
+    D, chi0, chi0_low and wave it gave when the fixture was committed -- the CUDA path is compared with the same file
+    on the GPU (tests/test_gpu_parity.py::test_committed_oracle_vectors)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_oracle_vectors", os.path.join(GOLD, "make_oracle_vectors.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.compute()
+    ref = np.load(os.path.join(GOLD, "oracle_vectors.npz"))
+    assert sorted(now) == sorted(ref.files)
+    for k in ref.files:
+        a, b = np.asarray(now[k]), ref[k]
+        assert a.shape == b.shape, k
+        scale = np.max(np.abs(b)) if b.size else 1.0
+        assert np.max(np.abs(a - b)) <= 1e-12 * scale, k        # OpenMP reduction order only
