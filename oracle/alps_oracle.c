@@ -8,7 +8,10 @@
  * reference lines it follows (paths relative to the reference root).
  *
  * PARITY UNPINNED at 1e-9: the reference cannot be built here; this file is
- * pinned to the reference's own 5-digit goldens by tests/test_oracle_golden.py.
+ * pinned to the reference's own 5-digit goldens by tests/test_oracle_golden.py
+ * (all 33 roots of the .scan file; E, B, fluctuations, heating rates and W_EM of
+ * the .eigen / .heat files through oracle/driver.py::calc_eigen; nmax; density)
+ * and to the survey's independent chi known answers (~7 digits).
  */
 #include "alps_oracle.h"
 
