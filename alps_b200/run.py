@@ -152,6 +152,10 @@ def main(argv=None):
     ap.add_argument("--emulate-nproc", "--nproc", dest="nproc", type=int, default=0,
                     help="MPI size of the reference run to emulate (under torchrun spell it --emulate-nproc: "
                          "torchrun's own parser claims --nproc as an abbreviation of --nproc-per-node)")
+    ap.add_argument("--map-mode", choices=["direct", "hoisted"], default="direct",
+                    help="map_search only: 'hoisted' evaluates the map with the k-hoisted p_perp sums "
+                         "(alps_b200_set_mode(1): O(nmax*npar) per omega instead of O(nmax*nperp*npar), same D to rounding, "
+                         "DESIGN.md 4b); the root refinement that follows always uses the direct quadrature")
     ap.add_argument("--fit", action="store_true",
                     help="run the twin of determine_param_fit (LM / Chebyshev fits) instead of using ideal parameters")
     a = ap.parse_args(argv)
@@ -188,11 +192,17 @@ def main(argv=None):
         nroots = int(s.get("nroots", 1))
         if bool(s.get("use_map", False)):
             m = nl["maps_1"]
+            if a.map_mode == "hoisted":
+                sol.set_mode(1)
+                sol.set_k(kperp, kpar)
             om, val, cal, roots = sol.map_search(float(m["omi"]), float(m["omf"]), float(m["gami"]), float(m["gamf"]),
                                                  int(m["nr"]), int(m["ni"]), bool(m.get("loggridw", False)),
                                                  bool(m.get("loggridg", False)),
                                                  bool(s.get("determine_minima", True)), map_path=prefix + ".map",
                                                  shard=shard)
+            if a.map_mode == "hoisted":
+                sol.set_mode(0)
+                sol.set_k(kperp, kpar)
             guesses = roots[:min(nroots, len(roots))] if bool(s.get("determine_minima", True)) else []
         else:
             guesses = [complex(float(nl["guess_%d" % i]["g_om"]), float(nl["guess_%d" % i]["g_gam"]))

@@ -317,3 +317,22 @@ def test_newton_step_speculation_for_serial_callers(monkeypatch):
     assert b[2] == 0 and a[2] > 0                            # triples went out as batches
     assert a[3] + a[4] >= b[3] + b[4]                        # nothing asked for was skipped
     print("speculation: %d omegas batched ahead, %.1f ms vs %.1f ms" % (a[2], a[5] * 1e3, b[5] * 1e3))
+
+
+def test_cli_map_search_with_hoisted_map_mode(tmp_path):
+    """--map-mode hoisted: the map comes from the k-hoisted p_perp sums (alps_b200_set_mode(1)), the refinement from the
+    direct quadrature: same minima, same refined roots file as the direct run, map values equal to rounding."""
+    from alps_b200 import run
+    here = os.path.dirname(os.path.abspath(__file__))
+    outs = {}
+    for mode in ("direct", "hoisted"):
+        out = str(tmp_path / mode)
+        assert run.main([os.path.join(here, "inputs", "test_map_small.in"), "--dist",
+                         os.path.join(here, "inputs", "test_kpar_fast_dist.in"), "--out", out, "--nproc", "4",
+                         "--map-mode", mode]) == 0
+        outs[mode] = (np.loadtxt(os.path.join(out, "test_map_small.map")),
+                      open(os.path.join(out, "test_map_small.roots")).read())
+    a, b = outs["direct"], outs["hoisted"]
+    assert a[1] == b[1]
+    assert np.array_equal(a[0][:, :2], b[0][:, :2])
+    assert np.max(np.abs(a[0][:, 3:] - b[0][:, 3:])) <= 1e-6 * np.max(np.abs(a[0][:, 3:]))     # 7 printed digits
