@@ -58,3 +58,30 @@ def test_reference_configuration_runs(name, tmp_path, capsys):
         for f in files:
             data = np.loadtxt(os.path.join(out, f), ndmin=2)
             assert np.all(np.isfinite(data))
+
+
+FULL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "inputs", "full")
+
+
+@pytest.mark.parametrize("name", ["cfg_ICW", "cfg_electron_mode", "cfg_cold_plasma"])
+def test_full_size_runs_are_identical_with_and_without_the_memo(name, tmp_path, monkeypatch, capsys):
+    """The reference's inputs at full size (tests/inputs/full/, scripts/make_test_inputs.py --full): every output file
+    of the twin main program is byte-identical with the disp() memo / prefetch / speculation on (default) and off
+    (ALPS_B200_MEMO=0), while most of the solvers' disp() calls never reach the GPU with it on."""
+    from alps_b200 import run
+    inp = os.path.join(FULL, name + ".in")
+    dist = os.path.join(FULL, name + "_dist.in")
+    files, stats = {}, {}
+    for memo in ("1", "0"):
+        monkeypatch.setenv("ALPS_B200_MEMO", memo)
+        out = str(tmp_path / ("memo" + memo))
+        args = [inp, "--out", out, "--nproc", "4", "--fit"] + (["--dist", dist] if os.path.exists(dist) else [])
+        assert run.main(args) == 0
+        files[memo] = {f: open(os.path.join(out, f)).read() for f in sorted(os.listdir(out))}
+        stats[memo] = run.main.last_stats
+    monkeypatch.delenv("ALPS_B200_MEMO")
+    capsys.readouterr()
+    assert files["1"].keys() == files["0"].keys() and len(files["1"]) >= 2
+    for f in files["1"]:
+        assert files["1"][f] == files["0"][f], f
+    assert stats["0"][2] == 0 and stats["1"][2] > 0 and stats["1"][0] < stats["0"][0]
