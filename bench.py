@@ -8,9 +8,11 @@ the workload (per GPU; N GPUs shard the map with no communication: weak scaling)
   value      device-resident omegas in, D out (alps_b200_disp_batch_dev), CUDA-event timed
   e2e        the same batch through the host-buffer call alps_b200_disp_batch (H2D of the omegas
              and D2H of D inside the timed region)
-  roofline   the quadrature kernel (k_quad) against the FP64 FMA pipe: algorithmic flops
-             34 x point-harmonics per D / CUDA-event time of that kernel
+  roofline   the quadrature kernel (k_quad_mma: DMMA.8x8x4 on the FP64 units) against the DMMA micro-benchmark of
+             the same job: useful flops 12 per (|n|, iperp, ipar) (the survey's 34-flop figure is
+             reported beside it) / CUDA-event time of that kernel
   cpu_baseline  the CPU oracle (restated reference, OpenMP) on a bounded sample of the same workload
+  clocks     nvidia-smi every 50 ms during the timed region: median / minimum SM clock over the busy samples, power
 `--impl reference` times the restated reference (oracle/) alone on the host cores: the Fortran/MPI
 reference cannot be built in this image (no gfortran, no MPI).
 """
