@@ -60,10 +60,19 @@ def _f(a):
 
 
 class Oracle:
-    """disp() of the reference restated on the CPU (one global instance at a time)."""
+    """disp() of the reference restated on the CPU.  The C library mirrors module alps_var in ONE static state: the
+    newest Oracle owns it, and using an older instance afterwards raises instead of silently answering for the
+    wrong plasma."""
+    _owner = None
+
+    def _check_owner(self):
+        if Oracle._owner is not self:
+            raise RuntimeError("this Oracle was superseded by a newer one (the C oracle has one global state); "
+                               "create it again")
 
     def __init__(self, plasma, nproc: int = 0, threads: int = 0, nmax_force: int = 0):
         L = lib()
+        Oracle._owner = self
         self.L = L
         self.pl = plasma
         maxorder = max(s.poly_order for s in plasma.species)
@@ -103,6 +112,7 @@ class Oracle:
         return self.df0_flat.reshape((pl.nspec, pl.nperp - 1, pl.npar - 1, 2), order="F")
 
     def set_k(self, kperp: float, kpar: float):
+        self._check_owner()
         nmax = np.zeros(self.pl.nspec, dtype=np.int32)
         rc = self.L.oracle_set_k(kperp, kpar, _p(nmax))
         if rc:
@@ -122,6 +132,7 @@ class Oracle:
     def disp(self, om: complex, full: bool = False, nhds: bool = True):
         """disp(om) of the reference; use_bM species get their chi from the NHDS restatement
         (src/ALPS_fns.f90:344-362) unless nhds=False (the caller then feeds set_external_chi itself)."""
+        self._check_owner()
         n = self.pl.nspec
         if nhds:
             for i, s in enumerate(self.pl.species):
