@@ -113,7 +113,7 @@ def scan_k(oracle, kperp0: float, kpar0: float, scan_type: int, swf: float, nste
     return rows
 
 
-def calc_eigen(oracle, omega: complex, kperp: float, kpar: float, vA: float, ns, qs, current_int=None):
+def calc_eigen(oracle, omega: complex, kperp: float, kpar: float, vA: float, ns, qs, current_int=None, split=False):
     """calc_eigen, src/ALPS_fns.f90:2605-2899, on top of the oracle's disp(full=True): electric and magnetic
     eigenfunctions (E_x = 1), species velocity and density fluctuations, heating rates P_s and the wave energy W_EM
     (chi at real omega and at 1.000001 omega for d(chi_h)/d(omega)).  Returns (ef[3], bf[3], Us[nspec,3], ds[nspec],
@@ -143,8 +143,24 @@ def calc_eigen(oracle, omega: complex, kperp: float, kpar: float, vA: float, ns,
     chia = np.array([-0.5j * (c_r[s] - c_r[s].conj().T) for s in range(nspec)])
     chih_old = 0.5 * sum(c_r[s] + c_r[s].conj().T for s in range(nspec))
     Psc = np.array([np.conj(e) @ chia[s] @ e for s in range(nspec)])
-    _, c_p, _, _ = oracle.disp(complex((omega * 1.000001).real, 0.0), full=True)
+    _, c_p, low, _ = oracle.disp(complex((omega * 1.000001).real, 0.0), full=True)
     chih = 0.5 * sum(c_p[s] + c_p[s].conj().T for s in range(nspec))
     dchih = (1.000001 * chih - chih_old) / 0.000001
     W_EM = float((np.conj(e) @ dchih @ e + np.sum(b * np.conj(b))).real)
-    return e, b, Us, ds, Psc.real / W_EM, W_EM
+    if not split:
+        return e, b, Us, ds, Psc.real / W_EM, W_EM
+    # heating split by mechanism (:2800-2890) from chi0_low of the LAST disp call (the one at 1.000001 Re omega):
+    # n = 0 yy and yz parts (transit-time damping), n = 0 zy and zz parts (Landau damping), n = +1 and n = -1
+    # (cyclotron) with the perpendicular field only; columns of the .heat_mech_* file, four per species
+    Ps_split = np.zeros((nspec, 4))
+    exy = np.array([e[0], e[1], 0.0])
+    for s in range(nspec):
+        l0 = low[s, :, :, 1]
+        Ps_split[s, 0] = ((-0.5j * np.conj(e[1]) * e[1] * (l0[1, 1] - np.conj(l0[1, 1]))).real +
+                          (-0.5j * (e[2] * np.conj(e[1]) * l0[1, 2] - np.conj(e[2]) * e[1] * np.conj(l0[1, 2]))).real)
+        Ps_split[s, 1] = ((-0.5j * (e[1] * np.conj(e[2]) * l0[2, 1] - np.conj(e[1]) * e[2] * np.conj(l0[2, 1]))).real +
+                          (-0.5j * np.conj(e[2]) * e[2] * (l0[2, 2] - np.conj(l0[2, 2]))).real)
+        for col, m in ((2, 2), (3, 0)):          # n = +1, n = -1
+            lm = low[s, :, :, m]
+            Ps_split[s, col] = (np.conj(exy) @ (-0.5j * (lm - lm.conj().T)) @ exy).real
+    return e, b, Us, ds, Psc.real / W_EM, W_EM, Ps_split / W_EM

@@ -60,13 +60,14 @@ def test_golden_kpar_scan_33_rows():
     # restatement of calc_eigen (oracle/driver.py): every column of every row to the 5 printed digits (last digit free)
     ge = np.loadtxt(os.path.join(GOLD, "test_kpar_fast.eigen_kpara_1.root_1"))
     gh = np.loadtxt(os.path.join(GOLD, "test_kpar_fast.heat_kpara_1.root_1"))
+    gm = np.loadtxt(os.path.join(GOLD, "test_kpar_fast.heat_mech_kpara_1.root_1"))
     ns = [sp.ns for sp in pl.species]
     qs = [sp.qs for sp in pl.species]
     for row, (kperp, kpar, om) in enumerate(rows):
         if row % 4 and row != 32:
             continue                                  # every fourth row and the last: keeps the CPU suite short
         orc.set_k(kperp, kpar)
-        e, b, Us, ds, Ps, W = driver.calc_eigen(orc, om, kperp, kpar, pl.vA, ns, qs)
+        e, b, Us, ds, Ps, W, Psplit = driver.calc_eigen(orc, om, kperp, kpar, pl.vA, ns, qs, split=True)
         ri = lambda z: np.array([np.ravel(z).real, np.ravel(z).imag]).T.ravel()
         mine = np.concatenate([[kperp, kpar, om.real, om.imag], ri(e), ri(b), ri(Us), ri(ds)])
         assert mine.shape == ge[row].shape
@@ -74,6 +75,11 @@ def test_golden_kpar_scan_33_rows():
         assert np.all(np.abs(mine - ge[row]) <= tol), (row, mine, ge[row])
         heat = np.concatenate([[kperp, kpar, om.real, om.imag], Ps, [W]])
         assert np.all(np.abs(heat[4:] - gh[row][4:]) <= 2e-4 * np.abs(gh[row][4:])), (row, heat, gh[row])
+        # heating by mechanism (chi0_low, the n = 0, +-1 parts): the shipped .heat_mech_* file is from another build
+        # than the other goldens (its own gamma column differs by 0.36 %), hence only the 1e-2 level of the
+        # reference's own pytest, with margin
+        gm_row = gm[row][4:]
+        assert np.all(np.abs(Psplit.ravel() - gm_row) <= 3e-2 * np.maximum(np.abs(gm_row), 1e-3 * np.max(np.abs(gm_row))))
 
 
 def test_chi_known_answers_of_the_survey_probe():
