@@ -231,9 +231,10 @@ def run_ours(args, w, rank, world, local_rank):
         step_dev()
     sol.sync()
     l0 = sol.info(_lib.INFO_LAUNCHES)
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank) if rank == 0 else None   # one nvidia-smi loop per job, on rank 0's GPU
     barrier()
-    clocks.start()
+    if clocks:
+        clocks.start()
     tot_ms, kern_ms = 0.0, 0.0
     for _ in range(args.steps):
         flush.zero_()
@@ -246,7 +247,7 @@ def run_ours(args, w, rank, world, local_rank):
         tot_ms += e0.elapsed_time(e1)
         kern_ms += sol.info(_lib.INFO_LAST_KERNEL_MS)
     barrier()
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     launches = int(sol.info(_lib.INFO_LAUNCHES) - l0)
     D_first = D_d.cpu().numpy().copy()
 
