@@ -70,3 +70,21 @@ def test_emulate_split_matches_oracle_split_processes(built_lib):
         assert rc == 0
         assert list(nmax) == list(adj), (nproc, list(nmax), list(adj))
         assert list(nhi) == want_hi, (nproc, list(nhi), want_hi)
+
+
+def test_fortran_shim_binds_only_declared_entry_points():
+    """integration/alps_b200_shim.f90 (source only -- no Fortran compiler here): every bind(c) interface it declares
+    is an entry point of include/alps_b200.h, with the same number of arguments."""
+    shim = open(os.path.join(ROOT, "integration", "alps_b200_shim.f90")).read()
+    shim = re.sub(r"&\s*\n\s*", " ", shim)                      # join continuation lines
+    hdr = open(os.path.join(ROOT, "include", "alps_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    bound = re.findall(r"(?:function|subroutine)\s+(alps_b200_\w+)\s*\(([^)]*)\)\s*bind\(c\)", shim, flags=re.I)
+    assert len(bound) >= 10
+    for name, args in bound:
+        m = re.search(r"\b%s\s*\(([^)]*)\)" % name, hdr)
+        assert m, name
+        n_f = len([a for a in args.split(",") if a.strip()])
+        c_args = m.group(1).strip()
+        n_c = 0 if c_args in ("", "void") else len(c_args.split(","))
+        assert n_f == n_c, (name, n_f, n_c)
