@@ -88,3 +88,32 @@ def test_fortran_shim_binds_only_declared_entry_points():
         c_args = m.group(1).strip()
         n_c = 0 if c_args in ("", "void") else len(c_args.split(","))
         assert n_f == n_c, (name, n_f, n_c)
+
+
+def test_cfg_struct_layout_is_the_same_in_header_ctypes_and_shim():
+    """alps_b200_cfg: field order and C types in include/alps_b200.h, alps_b200/_lib.py (ctypes) and the Fortran
+    bind(c) type of the shim."""
+    from alps_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "alps_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} alps_b200_cfg;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        typ, names = decl.split(None, 1)
+        fields += [(n.strip(), typ) for n in names.split(",")]
+    ctypes_fields = [(n, "int" if t is C.c_int else "double") for n, t in _lib.Cfg._fields_]
+    assert fields == ctypes_fields
+    shim = open(os.path.join(ROOT, "integration", "alps_b200_shim.f90")).read()
+    tbody = re.search(r"type, bind\(c\) :: alps_b200_cfg(.*?)end type", shim, flags=re.S | re.I).group(1)
+    shim_fields = []
+    for line in tbody.splitlines():
+        line = line.split("!")[0].strip()
+        if "::" not in line:
+            continue
+        typ, names = line.split("::")
+        kind = "int" if "c_int" in typ else "double"
+        shim_fields += [(n.strip(), kind) for n in names.split(",")]
+    assert shim_fields == fields
