@@ -117,3 +117,22 @@ def test_cfg_struct_layout_is_the_same_in_header_ctypes_and_shim():
         kind = "int" if "c_int" in typ else "double"
         shim_fields += [(n.strip(), kind) for n in names.split(",")]
     assert shim_fields == fields
+
+
+def test_every_header_struct_matches_its_ctypes_mirror():
+    from alps_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "alps_b200.h")).read()
+    mirrors = {"alps_b200_cfg": _lib.Cfg, "alps_b200_solver_opts": _lib.SolverOpts, "alps_b200_map": _lib.MapCfg,
+               "alps_b200_scan": _lib.ScanCfg}
+    found = re.findall(r"typedef struct \{(.*?)\} (\w+);", hdr, flags=re.S)
+    assert sorted(n for _, n in found) == sorted(mirrors)
+    for body, name in found:
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                typ, names = decl.split(None, 1)
+                fields += [(n.strip(), typ) for n in names.split(",")]
+        got = [(n, "int" if t is C.c_int else "double") for n, t in mirrors[name]._fields_]
+        assert fields == got, name
