@@ -136,3 +136,20 @@ def test_every_header_struct_matches_its_ctypes_mirror():
                 fields += [(n.strip(), typ) for n in names.split(",")]
         got = [(n, "int" if t is C.c_int else "double") for n, t in mirrors[name]._fields_]
         assert fields == got, name
+
+
+def test_ctypes_argument_counts_match_the_header(built_lib):
+    from alps_b200 import _lib
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "alps_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    checked = 0
+    for name, args in re.findall(r"\b(alps_b200_\w+)\s*\(([^)]*)\)\s*;", hdr):
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        args = args.strip()
+        n_c = 0 if args in ("", "void") else len(args.split(","))
+        assert len(fn.argtypes) == n_c, (name, len(fn.argtypes), n_c)
+        checked += 1
+    assert checked >= 25
