@@ -13,7 +13,7 @@ _LIB = None
 SYMBOLS = [
     "alps_b200_init", "alps_b200_finalize", "alps_b200_last_error", "alps_b200_set_species",
     "alps_b200_upload", "alps_b200_upload_rel", "alps_b200_derivative_f0", "alps_b200_set_k", "alps_b200_disp",
-    "alps_b200_disp_batch", "alps_b200_disp_batch_dev", "alps_b200_disp_prefetch", "alps_b200_add_external_chi",
+    "alps_b200_disp_batch", "alps_b200_disp_batch_full", "alps_b200_disp_batch_dev", "alps_b200_disp_prefetch", "alps_b200_add_external_chi",
     "alps_b200_set_bm_species", "alps_b200_nhds_calc_chi",
     "alps_b200_set_harmonic_shard", "alps_b200_chi_partial_len", "alps_b200_chi_partial_dev",
     "alps_b200_assemble_dev", "alps_b200_set_mode", "alps_b200_set_stream", "alps_b200_sync",
@@ -85,6 +85,7 @@ def lib():
         L.alps_b200_set_k.argtypes = [C.c_double, C.c_double, C.c_void_p]
         L.alps_b200_disp.argtypes = [C.c_void_p] * 5
         L.alps_b200_disp_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.alps_b200_disp_batch_full.argtypes = [C.c_int] + [C.c_void_p] * 5
         L.alps_b200_disp_batch_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.alps_b200_disp_prefetch.argtypes = [C.c_int, C.c_void_p]
         L.alps_b200_add_external_chi.argtypes = [C.c_int, C.c_void_p, C.c_void_p]

@@ -64,6 +64,7 @@ struct State {
   bool have_tables = false, have_k = false;
   // batch buffers
   int batch = 0;
+  size_t sbulk_rows = 0;   // rows of d_Sbulk per item (sbulk_rows_needed at allocation time)
   double *d_om = nullptr, *d_D = nullptr, *d_Sbulk = nullptr, *d_Sres = nullptr, *d_gwin = nullptr,
          *d_partial = nullptr, *d_chi0 = nullptr, *d_chi0_low = nullptr, *d_wave = nullptr, *d_ext = nullptr;
   PlanEntry* d_plan = nullptr;
@@ -235,6 +236,7 @@ void free_batch() {
   dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work); dfree(&S.d_ext);
   dfree(&S.d_relpart); dfree(&S.d_reltick); dfree(&S.d_respart); dfree(&S.d_restick);
   S.batch = 0;
+  S.sbulk_rows = 0;
 }
 
 int ensure_pinned(size_t bytes) {
@@ -395,14 +397,20 @@ int nsplit_rel() {
   return std::max(1, std::min(16, (2 * S.sm_count + (int)S.rtiles.size() - 1) / (int)S.rtiles.size()));
 }
 
+// Sbulk rows per item: n * nsplit(n) <= max(B, SMALL_BATCH * nsplit_small(SMALL_BATCH), LAT_BATCH * nsplit_small(1)).
+// nsplit_small depends on the tile list (harmonic shard, mode, latency variant), not only on NI: bind_batch checks
+// the allocation against the current value before every use.
+size_t sbulk_rows_needed(size_t B) {
+  return std::max({B, (size_t)SMALL_BATCH * nsplit_small(SMALL_BATCH), (size_t)LAT_BATCH * nsplit_small(1)});
+}
+
 int ensure_batch(int want) {
-  if (S.batch >= want && S.d_om) return 0;
+  if (S.batch >= want && S.d_om && sbulk_rows_needed(S.batch) <= S.sbulk_rows) return 0;
+  want = std::max(want, S.batch);
   free_batch();
   const size_t NI = S.gh.NI, B = want;
-  // Sbulk rows: n * nsplit(n) <= max(B, SMALL_BATCH * nsplit_small(SMALL_BATCH), LAT_BATCH * nsplit_small(1))
-  if (dalloc(&S.d_om, 2 * B) || dalloc(&S.d_D, 2 * B) ||
-      dalloc(&S.d_Sbulk, std::max({B, (size_t)SMALL_BATCH * nsplit_small(SMALL_BATCH),
-                                   (size_t)LAT_BATCH * nsplit_small(1)}) * NI * 12) ||
+  S.sbulk_rows = sbulk_rows_needed(B);
+  if (dalloc(&S.d_om, 2 * B) || dalloc(&S.d_D, 2 * B) || dalloc(&S.d_Sbulk, S.sbulk_rows * NI * 12) ||
       dalloc(&S.d_Sres, B * NI * 12) || dalloc(&S.d_gwin, B * NI * S.gh.WINX * 6) ||
       dalloc(&S.d_partial, B * S.gh.nspec * PARTIAL_PER_SPEC) || dalloc(&S.d_chi0, B * S.gh.nspec * 18) ||
       dalloc(&S.d_chi0_low, B * S.gh.nspec * 54) || dalloc(&S.d_wave, B * 18) || dalloc(&S.d_plan, B * NI) ||
@@ -915,6 +923,7 @@ int alps_b200_set_harmonic_shard(int rank, int nranks) {
   S.shard_rank = rank;
   S.shard_n = nranks;
   S.have_k = false;   // tiles and plan depend on the shard: set_k must be called again
+  free_batch();       // and so do the split factors the batch buffers were sized for
   return 0;
 }
 
@@ -1148,8 +1157,9 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
 
 static int bind_batch(int n) {
   int want = std::min(std::max(n, 1), auto_batch());
-  // keep a larger existing allocation
-  if (S.batch < want || !S.d_om) {
+  // keep a larger existing allocation, unless the p_par split of small batches outgrew its Sbulk rows (a harmonic
+  // shard shrinks the tile list and raises nsplit_small without changing NI)
+  if (S.batch < want || !S.d_om || sbulk_rows_needed(S.batch) > S.sbulk_rows) {
     int rc = ensure_batch(want);
     if (rc) return rc;
   }
@@ -1196,11 +1206,17 @@ int alps_b200_disp_batch_dev(int n, const double* d_om, double* d_D) {
 static int small_batch_graph(int n, const double* om, double* D, int* used);
 
 int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
+  return alps_b200_disp_batch_full(n, om, D, chi0_opt, nullptr, nullptr);
+}
+
+int alps_b200_disp_batch_full(int n, const double* om, double* D, double* chi0_opt, double* chi0_low_opt,
+                              double* wave_opt) {
   int rc = check_ready();
   if (rc) return rc;
   if (n <= 0) return 0;
   if (!om || !D) return fail(ALPS_B200_ERR_USAGE, "om / D is NULL");
-  if (!chi0_opt && n <= LAT_BATCH) {   // latency batch class: captured chain (batched roots, prefetched solver steps)
+  const bool aux = chi0_opt || chi0_low_opt || wave_opt;
+  if (!aux && n <= LAT_BATCH) {   // latency batch class: captured chain (batched roots, prefetched solver steps)
     int used = 0;
     if ((rc = small_batch_graph(n, om, D, &used))) return rc;
     if (used) return 0;
@@ -1214,11 +1230,17 @@ int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
     int m = std::min(S.batch, n - o);
     memcpy(h_om, om + 2 * (size_t)o, (size_t)m * 2 * sizeof(double));
     CK(cudaMemcpyAsync(S.d_om, h_om, (size_t)m * 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
-    if ((rc = run_chunk(m, S.d_om, S.d_D, nullptr, nullptr, chi0_opt != nullptr))) return rc;
+    if ((rc = run_chunk(m, S.d_om, S.d_D, nullptr, nullptr, aux))) return rc;
     CK(cudaMemcpyAsync(h_D, S.d_D, (size_t)m * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
     if (chi0_opt)
       CK(cudaMemcpyAsync(chi0_opt + (size_t)o * nspec * 18, S.d_chi0, (size_t)m * nspec * 18 * sizeof(double),
                          cudaMemcpyDeviceToHost, S.stream));
+    if (chi0_low_opt)
+      CK(cudaMemcpyAsync(chi0_low_opt + (size_t)o * nspec * 54, S.d_chi0_low, (size_t)m * nspec * 54 * sizeof(double),
+                         cudaMemcpyDeviceToHost, S.stream));
+    if (wave_opt)
+      CK(cudaMemcpyAsync(wave_opt + (size_t)o * 18, S.d_wave, (size_t)m * 18 * sizeof(double), cudaMemcpyDeviceToHost,
+                         S.stream));
     if ((rc = check_device_errors())) return rc;
     memcpy(D + 2 * (size_t)o, h_D, (size_t)m * 2 * sizeof(double));
   }

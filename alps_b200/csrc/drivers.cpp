@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <complex>
 #include <condition_variable>
 #include <functional>
@@ -34,8 +35,9 @@ struct DispError {
 // The reference refines its roots one after the other; every iteration of every root is one
 // latency-bound disp() call.  With batching on, each root's *unchanged serial algorithm* runs on its
 // own host thread, and a broker collects the D requests of all roots that are waiting and serves
-// them with one alps_b200_disp_batch launch.  Per-root results are bit-identical to the serial order
-// (disp_batch and disp agree bitwise); only the latency is shared.
+// them with alps_b200_disp_batch launches of at most 8 omegas (the batch class of a single disp() call).  Per-root
+// results are bit-identical to the serial order for any number of roots (disp_batch and disp agree bitwise within
+// that class); only the latency is shared.
 struct Broker {
   struct Req {
     cplx om, D;
@@ -132,7 +134,11 @@ void Broker::run(const std::vector<std::function<void()> >& jobs) {
     int rc = 0;
     if (!ids.empty()) {
       D.assign(om.size(), 0.0);
-      rc = alps_b200_disp_batch((int)ids.size(), om.data(), D.data(), nullptr);
+      // chunks of at most 8 omegas (LAT_BATCH in api.cu): every evaluation stays in the batch class of a single
+      // disp() call, so a root's D bits -- and its iteration path -- do not depend on how many other roots are pending
+      const int CHUNK = 8;
+      for (int q0 = 0; q0 < (int)ids.size() && !rc; q0 += CHUNK)
+        rc = alps_b200_disp_batch(std::min(CHUNK, (int)ids.size() - q0), om.data() + 2 * q0, D.data() + 2 * q0, nullptr);
       for (size_t q = 0; q < ids.size(); q++) {
         reqs[ids[q]].D = cplx(D[2 * q], D[2 * q + 1]);
         reqs[ids[q]].rc = rc;

@@ -2,15 +2,15 @@
 
     python -m alps_b200.run path/to/<runname>.in [--dist path/to/<arrayName>_dist.in] [--out solution]
 
-reads the `.in` namelists, obtains the f0 tables (`distribution/<arrayName>.<is>.array` if present,
+reads the `.in` namelists (omitted keys: the defaults of src/ALPS_var.f90), obtains the f0 tables (`distribution/<arrayName>.<is>.array` if present,
 else regenerated from the `_dist.in` closed forms), then map_search or refine_guess and the k scans,
 writing `<out>/<runname>.map / .roots / .scan_* / .eigen_* / .heat_* / .heat_mech_*` in the
 reference's formats.  Every D(omega,k) comes from the GPU (libalps_b200.so).
 
-Analytic-continuation parameters: with --fit the twin of determine_param_fit (alps_b200/fits.py:
-Levenberg-Marquardt rows started from the &ffit blocks, Chebyshev series for ac_method = 2) runs like in
-the reference; without it they are the generator's ideal values when the tables are regenerated, else
-the initial values of the &ffit blocks.  NHDS calc_chi for use_bM species runs on the device
+Analytic-continuation parameters: the twin of determine_param_fit (alps_b200/fits.py: Levenberg-Marquardt rows
+started from the &ffit blocks, Chebyshev series for ac_method = 2) runs like in the reference whenever the tables
+come from distribution/*.array files, or with --fit; tables regenerated from a _dist.in use the generator's ideal
+parameters unless --fit is given.  NHDS calc_chi for use_bM species runs on the device
 (csrc/nhds_kernel.cu).
 
 Several GPUs of one box (replaces `mpirun -np N`): `python -m torch.distributed.run --nproc-per-node N
@@ -30,8 +30,11 @@ from .namelist import read_namelists
 from .solver import Solver
 
 
-def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False, rel_backend="host"):
-    """rel_backend: where the spline of the relativistic regrid is evaluated (relativistic.derivative_f0_rel):
+def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=None, rel_backend="host"):
+    """fit: run the twin of determine_param_fit (the reference always does, src/ALPS.f90:114); None = only when the
+    tables are read from distribution/*.array files (regenerated tables come with their ideal fit parameters).
+    Omitted &system keys take the defaults of src/ALPS_var.f90.
+    rel_backend: where the spline of the relativistic regrid is evaluated (relativistic.derivative_f0_rel):
     "device" in the twin main program, "host" (numpy statement of the same loop) for set-up checks without a GPU."""
     s = nl["system"]
     nspec, nperp, npar = int(s["nspec"]), int(s["nperp"]), int(s["npar"])
@@ -63,10 +66,15 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False, rel_backend="h
     pp = np.zeros((nspec, nperp + 1, npar + 1, 2), order="F")
     f0 = np.zeros((nspec, nperp + 1, npar + 1), order="F")
     maxfits = max(len(sp.fit_type) for sp in species)
-    ngamma = int(s.get("ngamma", 0))
+    ngamma = int(s.get("ngamma", 100))      # src/ALPS_var.f90:128, 132
     pf = np.zeros((nspec, max(nperp, ngamma) + 1, 5, maxfits), order="F")
     have_files = all(os.path.exists(os.path.join(base_dir, "distribution", "%s.%d.array" % (name, i + 1)))
                      or species[i].usebM for i in range(nspec))
+    if fit is None:
+        fit = have_files
+    if have_files and not fit:
+        raise SystemExit("distribution/%s.<is>.array tables need the fit producers (the &ffit blocks only hold start "
+                         "values; the reference always runs determine_param_fit): drop --no-fit" % name)
     if have_files:
         for i in range(nspec):
             if species[i].usebM:
@@ -102,9 +110,9 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False, rel_backend="h
             for k in range(5):
                 pf[i, :, k, 0] = fits[i]["params"][k]
     pl = tables.Plasma(nperp=nperp, npar=npar, vA=vA, species=species, pp=pp, f0=f0, param_fit=pf,
-                       ngamma=ngamma, npparbar=int(s.get("npparbar", 0)),
-                       Bessel_zero=float(s.get("bessel_zero", 1.0e-50)), Tlim=float(s.get("tlim", 0.01)),
-                       positions_principal=int(s.get("positions_principal", 3)),
+                       ngamma=ngamma, npparbar=int(s.get("npparbar", 200)),
+                       Bessel_zero=float(s.get("bessel_zero", 1.0e-45)), Tlim=float(s.get("tlim", 0.01)),
+                       positions_principal=int(s.get("positions_principal", 5)),
                        n_resonance_interval=int(s.get("n_resonance_interval", 100)),
                        kperp_norm=bool(s.get("kperp_norm", True)))
     if any(sp.relativistic for sp in species):
@@ -139,6 +147,7 @@ def plasma_from_inputs(nl, dist_nl=None, base_dir=".", fit=False, rel_backend="h
             rel_in = {i: (pl.f0_rel[r], pl.gamma_rel[r], pl.pparbar_rel[r])
                       for r, i in enumerate(k for k, sp in enumerate(species) if sp.relativistic)}
         pl.param_fit, poly, pl.fit_quality = determine_param_fit(pl, initial, opt, rel_in)
+        pl.fit_ran = True
         if poly is not None:
             pl.poly_fit_coeffs = poly
     return pl
@@ -156,15 +165,21 @@ def main(argv=None):
                     help="map_search only: 'hoisted' evaluates the map with the k-hoisted p_perp sums "
                          "(alps_b200_set_mode(1): O(nmax*npar) per omega instead of O(nmax*nperp*npar), same D to rounding, "
                          "DESIGN.md 4b); the root refinement that follows always uses the direct quadrature")
-    ap.add_argument("--fit", action="store_true",
-                    help="run the twin of determine_param_fit (LM / Chebyshev fits) instead of using ideal parameters")
+    ap.add_argument("--fit", dest="fit", action="store_true", default=None,
+                    help="run the twin of determine_param_fit (LM / Chebyshev fits) like the reference always does "
+                         "(src/ALPS.f90:114: determine_param_fit before the first disp).  Default whenever the f0 tables "
+                         "are read from distribution/*.array files")
+    ap.add_argument("--no-fit", dest="fit", action="store_false",
+                    help="skip the fits: only allowed when the tables are regenerated from the _dist.in closed forms, whose "
+                         "ideal fit parameters are then used; refused for file-based tables (their &ffit blocks hold "
+                         "start values, not fitted parameters)")
     a = ap.parse_args(argv)
     nl = read_namelists(a.input)
     runname = os.path.splitext(os.path.basename(a.input))[0]
     dist_nl = read_namelists(a.dist) if a.dist else None
     pl = plasma_from_inputs(nl, dist_nl, base_dir=os.getcwd(), fit=a.fit, rel_backend="device")
     s = nl["system"]
-    if a.fit:
+    if getattr(pl, "fit_ran", False):
         # what output_fit prints (src/ALPS_analyt.f90:942-943)
         q = pl.fit_quality
         print(" Sum of all least-squares: %14.4E" % q)
@@ -188,7 +203,7 @@ def main(argv=None):
         print("nmax:", list(map(int, nmax)))
         opts = sol.opts(numiter=int(s.get("numiter", 50)), D_threshold=float(s.get("d_threshold", 1e-5)),
                         D_prec=float(s.get("d_prec", 1e-5)), D_tol=float(s.get("d_tol", 1e-7)),
-                        D_gap=float(s.get("d_gap", 1e-5)), secant_method=int(s.get("secant_method", 0)))
+                        D_gap=float(s.get("d_gap", 1e-5)), secant_method=int(s.get("secant_method", 2)))
         nroots = int(s.get("nroots", 1))
         if bool(s.get("use_map", False)):
             m = nl["maps_1"]

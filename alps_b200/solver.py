@@ -115,6 +115,20 @@ class Solver:
             return D, chi0.reshape((n, 3, 3, self.pl.nspec)).transpose(0, 3, 1, 2).swapaxes(2, 3)
         return D
 
+    def disp_batch_full(self, om: Sequence[complex]):
+        """n independent omegas with every side output of disp(): (D[n], chi0[n,nspec,3,3], chi0_low[n,nspec,3,3,3],
+        wave[n,3,3]) -- element [i] is what Solver.disp(om[i], full=True) returns."""
+        om = np.ascontiguousarray(np.asarray(om, dtype=np.complex128).ravel())
+        n, ns = om.size, self.pl.nspec
+        D = np.zeros(n, dtype=np.complex128)
+        chi0 = np.zeros(n * ns * 9, dtype=np.complex128)
+        low = np.zeros(n * ns * 27, dtype=np.complex128)
+        wave = np.zeros(n * 9, dtype=np.complex128)
+        f = lambda a: _p(a.view(np.float64))
+        _lib.check(self.L.alps_b200_disp_batch_full(n, f(om), f(D), f(chi0), f(low), f(wave)))
+        return (D, chi0.reshape((n, 3, 3, ns)).transpose(0, 3, 2, 1), low.reshape((n, 3, 3, 3, ns)).transpose(0, 4, 3, 2, 1),
+                wave.reshape((n, 3, 3)).transpose(0, 2, 1))
+
     def disp_batch_dev(self, n: int, d_om_ptr: int, d_D_ptr: int):
         """Device-resident omegas / D (raw device pointers, e.g. torch .data_ptr())."""
         _lib.check(self.L.alps_b200_disp_batch_dev(n, C.c_void_p(d_om_ptr), C.c_void_p(d_D_ptr)))
@@ -138,7 +152,7 @@ class Solver:
 
     # ---- omega-point generators (C++ twins in csrc/drivers.cpp; D always comes from the GPU)
     @staticmethod
-    def opts(numiter=50, D_threshold=1.0e-15, D_prec=1.0e-5, D_tol=1.0e-7, D_gap=1.0e-5, secant_method=2):
+    def opts(numiter=50, D_threshold=1.0e-5, D_prec=1.0e-5, D_tol=1.0e-7, D_gap=1.0e-5, secant_method=2):
         return _lib.SolverOpts(numiter, D_threshold, D_prec, D_tol, D_gap, secant_method)
 
     def _root(self, fn, om, opts):
@@ -197,7 +211,8 @@ class Solver:
         pl = self.pl
         out = np.zeros(pl.nspec)
         for i, s in enumerate(pl.species):
-            if s.usebM:
+            if s.usebM:     # src/ALPS_fns.f90:161-166: the drift of the closed-form bi-Maxwellian
+                out[i] = s.ns * s.qs * s.bM_pdrifts / s.ms
                 continue
             dpperp = pl.pp[i, 2, 2, 0] - pl.pp[i, 1, 2, 0]
             dppar = abs(pl.pp[i, 2, 2, 1] - pl.pp[i, 2, 1, 1])

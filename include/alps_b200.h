@@ -98,6 +98,10 @@ int alps_b200_disp(const double om[2], double D[2], double *chi0, double *chi0_l
  * independent root iterations: n omegas in, n D's out (host buffers; H2D/D2H inside).
  * chi0_opt (may be NULL): n x chi0(nspec,3,3). */
 int alps_b200_disp_batch(int n, const double *om, double *D, double *chi0_opt);
+/* the same with every side output of disp() per omega (any may be NULL): n x chi0(nspec,3,3), n x chi0_low(nspec,3,3,-1:1),
+ * n x wave(3,3) -- what calc_eigen would read after each of the n disp calls (src/ALPS_fns.f90:2687-2702) */
+int alps_b200_disp_batch_full(int n, const double *om, double *D, double *chi0_opt, double *chi0_low_opt,
+                              double *wave_opt);
 
 /* Solver aid: evaluate up to 8 omegas that are about to be requested one by one (the start pair of secant / rtsec, the
  * om, om(1 +- delta) triple of secant_osc's Newton step, src/ALPS_fns.f90:2046) as one small batch and keep the results in
@@ -213,7 +217,8 @@ int alps_b200_calc_eigen(const double om[2], int nspec, const double *ns, const 
                          double *Ps_split, double *W_EM);
 /* Root batching: with on != 0, refine_guess and om_scan advance all roots of a k step concurrently --
  * each root runs the unchanged serial algorithm on a host thread and the D requests of all waiting
- * roots are served by one alps_b200_disp_batch launch.  Results per root are bit-identical. */
+ * roots are served by alps_b200_disp_batch launches of at most 8 omegas (the batch class of a single disp() call),
+ * so the results per root are bit-identical to the serial order for any number of roots. */
 int alps_b200_set_root_batching(int on);
 
 /* replaces: scan_read step sizes (src/ALPS_io.f90:472-549); updates kperp_last / kpar_last */

@@ -5,7 +5,7 @@ from alps_b200 import tables
 from alps_b200.solver import Solver
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 pl = tables.config_kpar_fast(); sol = Solver(pl, emulate_nproc=4); sol.set_k(1e-2, 1e-2)
-opts = sol.opts()
+opts = sol.opts(D_threshold=1.0e-15)
 d = tempfile.mkdtemp(); prefix = os.path.join(d, "t")
 w, D = sol.refine_guess([complex(9.9e-3, -5.5e-6)], opts)
 rows, w = sol.om_scan(w, opts, 4, 1e-3, 1e-1, True, 32, 1, True, True, prefix, 1)

@@ -202,6 +202,30 @@ def test_root_batching_is_bit_identical_to_the_serial_order():
     print("serial %.3f s, batched %.3f s" % (t_ser, t_bat))
 
 
+def test_root_batching_with_more_than_eight_roots_is_bit_identical():
+    """More pending roots than one latency-class batch holds (8): the broker serves them in chunks of <= 8 omegas, so
+    every D -- and every root's iteration path -- is still bitwise the serial one."""
+    from alps_b200.solver import Solver
+    pl = tables.config_kpar_fast()
+    sol = Solver(pl, emulate_nproc=4)
+    try:
+        sol.set_k(1.0e-2, 1.0e-2)
+        opts = sol.opts(numiter=25, D_threshold=1.0e-15, D_prec=1.0e-5)
+        rng = np.random.default_rng(11)
+        guesses = [complex(9.9e-3, -5.5e-6)] + [complex(a, -b) for a, b in
+                                                zip(rng.uniform(5e-3, 4e-2, 12), rng.uniform(1e-5, 2e-3, 12))]
+        w_ser, D_ser = sol.refine_guess(guesses, opts)
+        sol.set_k(1.0e-2, 1.0e-2)       # drops the disp() memo: the batched pass evaluates everything again
+        sol.set_root_batching(True)
+        w_bat, D_bat = sol.refine_guess(guesses, opts)
+        sol.set_root_batching(False)
+    finally:
+        sol.close()
+    assert len(guesses) == 13
+    assert np.array_equal(w_ser.view(np.float64), w_bat.view(np.float64))
+    assert np.array_equal(D_ser.view(np.float64), D_bat.view(np.float64))
+
+
 def test_cli_map_search_flow(tmp_path):
     """use_map=.true.: map_search -> find_minima -> refine_guess through the twin main program; the
     Alfven root of the test_kpar_fast tables must be among the refined roots."""
