@@ -28,7 +28,8 @@ struct SpeciesHost {
   std::vector<double> pperp, ppar;
   double *d_pperp = nullptr, *d_ppar = nullptr, *d_A = nullptr, *d_C0 = nullptr, *d_Cp = nullptr;
   double *d_J = nullptr, *d_W = nullptr, *d_pf = nullptr, *d_poly = nullptr, *d_ee = nullptr, *d_G = nullptr;
-  size_t cap_J = 0, cap_W = 0, cap_G = 0;
+  size_t cap_J = 0, cap_W = 0, cap_G = 0, cap_T = 0;
+  double* d_T = nullptr;   // weighted p_par moments of the hoisted tables (k_fast_tiled)
   // fragment-ordered operands of the DMMA quadrature variants (quad_mma.cu)
   double *d_Af = nullptr, *d_Cf = nullptr, *d_Wf = nullptr, *d_Jrel = nullptr;
   double *d_Afs = nullptr, *d_Cfs = nullptr;   // the same tables in LAT_BN-column tiles (latency variant)
@@ -110,6 +111,7 @@ struct State {
   double* d_nhI[MAXSPEC] = {nullptr};   // BESSI(n, z) tables
   int cap_nhI[MAXSPEC] = {0};
   int mode = 0;
+  int fast_variant = 1;      // mode 1 kernel: 0 = k_fast, 1 = k_fast_tiled (ALPS_B200_FAST_VARIANT, A/B knob)
   QuadVariant qv{8, 16, 32, 2};
   int shard_rank = 0, shard_n = 1;
   long long launches = 0, d_evals = 0, set_k_calls = 0, memo_hits = 0, prefetched = 0;
@@ -373,6 +375,23 @@ int build_hoisted_tables() {
   cudaError_t e = S.qv.id >= 9 ? launch_quad_mma(P, S.qv.id, true, S.stream) : launch_quad(P, S.qv.id, true, S.stream);
   S.launches += 1;
   if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "hoisted-table launch failed: %s", cudaGetErrorString(e));
+  if (S.fast_variant >= 1) {
+    // real moment tables of k_fast_tiled: T[n][ipar-1][12] = w_tab p^m {GA_x, GB_x}
+    for (int s = 0; s < nspec; s++) {
+      SpeciesHost& h = S.sp[s];
+      if (!h.table) continue;
+      const int rows = S.gh.sp[s].nhi + 1;
+      const size_t nT = (size_t)rows * (npar - 1) * 12;
+      if (nT > h.cap_T) {
+        if (dalloc(&h.d_T, nT)) return ALPS_B200_ERR_CUDA;
+        h.cap_T = nT;
+      }
+      launch_fast_tables(h.d_G, h.d_ppar, npar, rows, h.d_T, S.stream);
+      S.launches += 1;
+      S.gh.sp[s].T = h.d_T;
+    }
+    CK(cudaMemcpyAsync(S.gd, &S.gh, sizeof(GlobalDev), cudaMemcpyHostToDevice, S.stream));
+  }
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());
   return 0;
@@ -547,7 +566,8 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     if (!S.capturing) cudaEventRecord(S.ev0, S.stream);
     cudaError_t e = cudaSuccess;
     if (S.mode == 1)
-      launch_fast(gd, d_om, n, S.d_fitems, (int)S.fitems.size(), S.d_plan, S.d_Sbulk, S.d_gwin, S.stream);
+      launch_fast(gd, d_om, n, S.d_fitems, (int)S.fitems.size(), S.d_plan, S.d_Sbulk, S.d_gwin, S.cfg.npar,
+                  S.gh.kpar, S.fast_variant, S.stream);
     else
       e = use_lat(n)      ? launch_quad_mma(S.Plat, LAT_VARIANT, false, S.stream)
           : S.qv.id >= 9 ? launch_quad_mma(S.P, S.qv.id, false, S.stream)
@@ -682,6 +702,8 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
     S.omega_major = getenv("ALPS_B200_OMEGA_MAJOR") != nullptr;   // A/B knob: previous block order of k_quad_mma
     const char* v = getenv("ALPS_B200_QUAD_VARIANT");   // tuning knob: tile shape of k_quad
     S.qv = quad_variant(v ? atoi(v) : 15);
+    const char* fv = getenv("ALPS_B200_FAST_VARIANT");
+    S.fast_variant = fv ? atoi(fv) : 1;
   }
   S.shard_rank = 0;
   S.shard_n = 1;
@@ -705,7 +727,7 @@ void alps_b200_finalize(void) {
     h.cap_Jrel = 0;
     h.cap_Xf = h.cap_Wf = 0;
     h.af_valid = false;
-    dfree(&h.d_W); dfree(&h.d_pf); dfree(&h.d_poly); dfree(&h.d_ee); dfree(&h.d_G);
+    dfree(&h.d_W); dfree(&h.d_pf); dfree(&h.d_poly); dfree(&h.d_ee); dfree(&h.d_G); dfree(&h.d_T);
     dfree(&h.d_grel); dfree(&h.d_pbrel); dfree(&h.d_f0rel); dfree(&h.d_dfg); dfree(&h.d_dfp);
     dfree(&h.d_cone_lo); dfree(&h.d_cone_up);
     h = SpeciesHost();
@@ -1261,7 +1283,7 @@ static void disp_signature(std::vector<unsigned char>& sig, int n) {
                         S.d_gwin, S.d_partial, S.d_err, S.d_rtiles, S.d_fitems, S.d_respart, S.d_restick,
                         S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
   const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)S.rtiles.size(), (long long)S.fitems.size(), S.mode,
-                            S.qv.id, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off,
+                            S.qv.id, S.fast_variant, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off,
                             (long long)S.pdl_on, (long long)S.reslat_gx, (long long)n};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
   memcpy(sig.data(), &P, sizeof(P));

@@ -75,6 +75,7 @@ struct SpeciesDev {
   const double* J;
   const double* W;
   const double* G;           // k-hoisted p_perp sums [n][ipar-1][GAa,GBa,GAb,GBb,GAc,GBc] (mode 1 only)
+  const double* T;           // their weighted p_par moments [n][ipar-1][12] (fast_kernel.cu, k_fast_tables; mode 1 only)
   const double* param_fit;   // [iperp][5][maxfits] for this species (repacked)
   const double* poly;        // [iperp][maxorder+1]
   double int_ee;             // omega-independent ee term, src/ALPS_fns.f90:1457-1555 (int_ee_rel if relativistic)

@@ -119,8 +119,11 @@ struct FastItem {
   int s;
   int nabs;
 };
+// variant 0: k_fast (one thread per omega over the G tables); 1: k_fast_tiled (real moment tables T through a TMA ring)
 void launch_fast(const GlobalDev* g, const double* om, int n_om, const FastItem* items, int nitems,
-                 const PlanEntry* plan, double* Sbulk, double* gwin, cudaStream_t st);
+                 const PlanEntry* plan, double* Sbulk, double* gwin, int npar, double kpar, int variant,
+                 cudaStream_t st);
+void launch_fast_tables(const double* G, const double* ppar, int npar, int nrows, double* T, cudaStream_t st);
 void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
                 int* err_flag, int nsplit, double* Mpart, int* tickets, cudaStream_t st);
 void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, int npb, double zfac, int nmaxord,

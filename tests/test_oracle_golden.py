@@ -117,3 +117,27 @@ def test_oracle_reproduces_its_committed_vectors():
         assert a.shape == b.shape, k
         scale = np.max(np.abs(b)) if b.size else 1.0
         assert np.max(np.abs(a - b)) <= 1e-12 * scale, k        # OpenMP reduction order only
+
+
+def test_oracle_reproduces_its_operating_point_vectors():
+    """tests/golden/oracle_vectors_ops.npz (tests/golden/make_oracle_vectors_ops.py): the C4 (k_perp = 3, nmax 88 / 29,
+    mpirun -np 4 emulated) and C2 (150x300, use_bM protons) vectors are recomputed here; the C5 nmax = 200 vectors cost
+    the oracle minutes per omega and are only checked for shape and finiteness on the CPU (the CUDA path is compared
+    with all of them on the GPU, tests/test_gpu_ops.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_ops", os.path.join(GOLD, "make_oracle_vectors_ops.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ref = np.load(os.path.join(GOLD, "oracle_vectors_ops.npz"))
+    now = mod.compute(["c4", "c2"])
+    for k, a in now.items():
+        b = ref[k]
+        assert np.asarray(a).shape == b.shape, k
+        scale = np.max(np.abs(b)) if b.size else 1.0
+        assert np.max(np.abs(np.asarray(a) - b)) <= 1e-12 * scale, k
+    assert list(ref["c4_nmax"]) == [88, 29]
+    assert list(ref["c5_nmax"]) == [200, 200, 200] and ref["c5_om"].size >= 3
+    for k in ("c5_D", "c5_chi0", "c5_chi0_low", "c5_wave"):
+        assert ref[k].shape[0] == ref["c5_om"].size and np.all(np.isfinite(ref[k].view(np.float64))), k
+    im = ref["c5_om"].imag
+    assert np.any(im < 0) and np.any(im > 0) and np.any(im == 0)
