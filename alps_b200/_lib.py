@@ -21,10 +21,13 @@ SYMBOLS = [
     "alps_b200_secant", "alps_b200_secant_osc", "alps_b200_rtsec", "alps_b200_refine_guess",
     "alps_b200_map_search", "alps_b200_map_grid", "alps_b200_map_finish", "alps_b200_calc_eigen", "alps_b200_scan_setup", "alps_b200_om_scan",
     "alps_b200_om_double_scan", "alps_b200_set_root_batching", "alps_b200_tps_eval",
+    "alps_b200_set_partition", "alps_b200_comm_unique_id", "alps_b200_comm_init", "alps_b200_comm_finalize",
+    "alps_b200_omega_slice",
 ]
 
 INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH, INFO_DFMA_NOREUSE, \
-    INFO_DMMA_PEAK, INFO_QUAD_VARIANT, INFO_D_EVALS, INFO_SET_K_CALLS, INFO_MEMO_HITS, INFO_PREFETCHED = range(12)
+    INFO_DMMA_PEAK, INFO_QUAD_VARIANT, INFO_D_EVALS, INFO_SET_K_CALLS, INFO_MEMO_HITS, INFO_PREFETCHED, INFO_NGPU = range(13)
+PARTITION_OMEGA, PARTITION_HARMONIC = 0, 1
 
 
 class Cfg(C.Structure):
@@ -34,7 +37,7 @@ class Cfg(C.Structure):
                 ("n_resonance_interval", C.c_int), ("kperp_norm", C.c_int),
                 ("emulate_nproc", C.c_int), ("maxfits", C.c_int), ("maxorder", C.c_int),
                 ("device", C.c_int), ("nmax_cap", C.c_int), ("batch_max", C.c_int),
-                ("nmax_force", C.c_int)]
+                ("nmax_force", C.c_int), ("ngpu", C.c_int)]
 
 
 class SolverOpts(C.Structure):
@@ -116,6 +119,10 @@ def lib():
         L.alps_b200_om_double_scan.argtypes = [V, V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V, C.c_char_p, V]
         L.alps_b200_set_root_batching.argtypes = [C.c_int]
         L.alps_b200_tps_eval.argtypes = [C.c_int, V, V, V, C.c_int, V, V, V]
+        L.alps_b200_set_partition.argtypes = [C.c_int]
+        L.alps_b200_comm_unique_id.argtypes = [V]
+        L.alps_b200_comm_init.argtypes = [C.c_int, C.c_int, V]
+        L.alps_b200_omega_slice.argtypes = [C.c_int, C.c_int, C.c_int, V, V]
         _LIB = L
     return _LIB
 

@@ -8,8 +8,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+#include <nccl.h>      // types and enums only: the library is resolved at run time (dlopen), see NcclApi below
+
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -143,7 +149,20 @@ struct State {
   CUresult (*encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
-} S;
+  int class_n = 0;           // batch class override: omegas of the whole API call when a call is evaluated in pieces
+                             // (internal chunks, device slices of a group, rank slices): the summation order then
+                             // depends on the call, not on how it was cut
+  cudaEvent_t ev_part = nullptr;   // group / harmonic partition: this device's chi partials are complete
+  double* d_gather = nullptr;      // one process per GPU, OMEGA partition: every rank's D slice (ncclAllGather in place)
+  size_t gather_cap = 0;
+};
+
+// One State per device driven by this process (alps_b200_cfg.ngpu, "device group"); every host thread works on the
+// state tl_S points to: the caller's thread on device 0 of the group, one worker thread per further device.
+constexpr int MAXDEV = 8;
+State g_states[MAXDEV];
+thread_local State* tl_S = &g_states[0];
+#define S (*tl_S)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -537,10 +556,26 @@ int prepare_external(int n, const double* d_om, const double** d_ext_out) {
   return 0;
 }
 
+bool comm_harmonic();                                           // multi-process harmonic partition (bottom of the file)
+bool comm_omega_active();
+bool group_harmonic_active();                                   // device group of this process: partition in use
+bool group_omega_active();
+int group_harmonic_eval(int n, const double* om, double* D, double* chi0, double* chi0_low, double* wave);
+int group_omega_eval(int n, const double* om, double* D, double* chi0, double* chi0_low, double* wave);
+int comm_omega_eval(int n, const double* om, double* D);
+struct ClassScope {      // sets the batch class of the enclosing API call for the chunks evaluated inside it
+  int prev;
+  explicit ClassScope(int n) : prev(S.class_n) { if (S.class_n <= 0) S.class_n = n; }
+  ~ClassScope() { S.class_n = prev; }
+};
+int comm_allreduce_partials(double* d_partial, size_t count);    // ncclAllReduce(sum) on the library stream
+
 // run the hot path for n omegas already on the device (n <= S.batch)
 int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, const double* d_partial_in,
               bool want_aux) {
   const GlobalDev* gd = S.gd;
+  // batch class (summation order): that of the whole API call when this chunk is a piece of one (S.class_n)
+  const int cn = S.class_n > 0 ? std::max(S.class_n, n) : n;
   if (!d_partial_out && !S.capturing) S.d_evals += n;
   if (!d_partial_in) {
     launch_plan(gd, S.gh, S.zc ? S.h_pin : d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream,
@@ -551,11 +586,11 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     // several CTAs along p_par.  The split depends only on the configuration and on the batch class
     // (n <= LAT_BATCH: narrow-tile latency variant; n <= SMALL_BATCH), so a single disp() and a
     // disp_batch() of up to LAT_BATCH omegas (batched roots) give bitwise identical D.
-    S.P.nsplit = (S.mode == 1 || n > SMALL_BATCH) ? 1 : nsplit_small(n);
+    S.P.nsplit = (S.mode == 1 || cn > SMALL_BATCH) ? 1 : nsplit_small(cn);
     // throughput batches: the CTAs of one (species, harmonic group) tile are adjacent, so the SMs walk the same
     // species table and weight block together (working set in L2: one species instead of all of them)
-    S.P.tile_major = (n > SMALL_BATCH && !S.omega_major) ? 1 : 0;
-    if (use_lat(n)) {
+    S.P.tile_major = (cn > SMALL_BATCH && !S.omega_major) ? 1 : 0;
+    if (use_lat(cn)) {
       S.Plat.om = d_om;
       S.Plat.n_om = n;
       S.Plat.nsplit = S.P.nsplit;
@@ -569,26 +604,26 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       launch_fast(gd, d_om, n, S.d_fitems, (int)S.fitems.size(), S.d_plan, S.d_Sbulk, S.d_gwin, S.cfg.npar,
                   S.gh.kpar, S.fast_variant, S.stream);
     else
-      e = use_lat(n)      ? launch_quad_mma(S.Plat, LAT_VARIANT, false, S.stream)
+      e = use_lat(cn)     ? launch_quad_mma(S.Plat, LAT_VARIANT, false, S.stream)
           : S.qv.id >= 9 ? launch_quad_mma(S.P, S.qv.id, false, S.stream)
                          : launch_quad(S.P, S.qv.id, false, S.stream);
     if (!S.capturing) cudaEventRecord(S.ev1, S.stream);
     if (e != cudaSuccess) return fail(ALPS_B200_ERR_CUDA, "quadrature kernel launch failed: %s", cudaGetErrorString(e));
-    if (S.mode == 0 && !use_lat(n) && S.qv.id == 15 && S.P.tile_major && S.P.ntiles_rem > 0 &&
+    if (S.mode == 0 && !use_lat(cn) && S.qv.id == 15 && S.P.tile_major && S.P.ntiles_rem > 0 &&
         S.P.ntiles_rem < S.P.ntiles)
       S.launches += 1;   // regular tiles + packed remainder tiles: two launches of k_quad_mma
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.d_respart,
-                    S.d_restick, S.stream, S.reslat_gx);
+                    S.d_restick, S.stream, S.reslat_gx, cn);
     if (!S.rtiles.empty()) {
       // few omegas in flight: spread each (omega, species, |n|) over several CTAs (configuration-only
       // rule, like nsplit_small, so disp() and a small disp_batch() stay bitwise identical)
-      const int rsplit = (n <= SMALL_BATCH) ? nsplit_rel() : 1;
+      const int rsplit = (cn <= SMALL_BATCH) ? nsplit_rel() : 1;
       launch_rel(gd, d_om, n, S.d_rtiles, (int)S.rtiles.size(), S.d_Sres, S.d_err + 6, rsplit, S.d_relpart,
                  S.d_reltick, S.stream);
       S.launches += 1;
     }
     double* part = d_partial_out ? d_partial_out : S.d_partial;
-    if (!d_partial_out && n <= SMALL_BATCH && !S.fuse_off) {
+    if (!d_partial_out && cn <= SMALL_BATCH && !S.fuse_off && !comm_harmonic()) {
       // small batches: harmonic sums and the determinant in one launch (bitwise the two-kernel result)
       const double* d_ext = nullptr;
       int rc = prepare_external(n, d_om, &d_ext);
@@ -603,6 +638,12 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     launch_chi_partial(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, part, S.stream);
     S.launches += 4;
     if (d_partial_out) return 0;
+    if (comm_harmonic()) {
+      // harmonic partition over processes (one GPU each): the chi partials of the shards are summed over NVLink on
+      // the library's stream -- what the two MPI_REDUCEs of disp() do (src/ALPS_fns.f90:519-523)
+      int rc = comm_allreduce_partials(part, (size_t)n * S.gh.nspec * PARTIAL_PER_SPEC);
+      if (rc) return rc;
+    }
     d_partial_in = part;
   }
   const double* d_ext = nullptr;
@@ -625,6 +666,188 @@ int check_ready() {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------ device group
+// alps_b200_cfg.ngpu > 1: ONE process drives ngpu devices (what a Fortran caller behind the shim gets: rank 0 calls,
+// the library uses every GPU of the box).  Device d of the group has its own State, stream and -- for d >= 1 -- its
+// own host thread, which executes the jobs the caller's thread posts: the replicated set-up calls (tables live on
+// every device), its slice of an omega batch, or its harmonic shard.
+struct Worker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<int()> job;
+  std::atomic<unsigned> posted{0}, finished{0};
+  bool quit = false;
+  int rc = 0;
+};
+
+// NCCL entry points, resolved with dlopen("libnccl.so.2") on first use: inside a torch process that is the copy torch
+// already loaded, behind a Fortran/MPI driver the system library.  libalps_b200.so has no link-time dependency on it.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+struct Group {
+  int ngpu = 1;                       // devices driven by this process
+  int partition = 0;                  // ALPS_B200_PARTITION_OMEGA / _HARMONIC
+  Worker* w[MAXDEV] = {nullptr};
+  bool p2p = false;                   // peer access between device 0 and every other device of the group
+  bool reduce_nccl = false;           // harmonic partition of the group: ncclAllReduce instead of the peer-memory sum
+  ncclComm_t dev_comm[MAXDEV] = {nullptr};
+  // one process per GPU (mpirun / torchrun): library-owned communicator over all ranks
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  NcclApi nccl;
+} G;
+thread_local bool tl_worker = false;     // this thread is a group worker
+thread_local bool tl_in_group = false;   // the caller's thread is inside group_all (its own share runs on state 0)
+
+int nccl_load() {
+  NcclApi& a = G.nccl;
+  if (a.lib) return 0;
+  const char* names[] = {getenv("ALPS_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm || !*nm) continue;
+    a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) return fail(ALPS_B200_ERR_CUDA, "NCCL not found (dlopen libnccl.so.2: %s)", dlerror());
+  bool ok = true;
+  auto sym = [&](const char* nm) {
+    void* f = dlsym(a.lib, nm);
+    ok = ok && f != nullptr;
+    return f;
+  };
+  a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+  a.CommInitAll = (decltype(a.CommInitAll))sym("ncclCommInitAll");
+  a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+  a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+  a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+  a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+  a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+  if (!ok) {
+    a = NcclApi();
+    return fail(ALPS_B200_ERR_CUDA, "libnccl lacks an entry point alps_b200 needs");
+  }
+  return 0;
+}
+#define NCK(call)                                                                                          \
+  do {                                                                                                     \
+    ncclResult_t r_ = (call);                                                                              \
+    if (r_ != ncclSuccess)                                                                                 \
+      return fail(ALPS_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, G.nccl.GetErrorString(r_), __FILE__, \
+                  __LINE__);                                                                               \
+  } while (0)
+
+void worker_main(int d) {
+  tl_S = &g_states[d];
+  tl_worker = true;
+  Worker& w = *G.w[d];
+  unsigned seen = 0;
+  for (;;) {
+    // a short spin keeps the hand-over of back-to-back jobs (set_k + disp chains) at a few microseconds
+    for (int spin = 0; spin < 4000 && w.posted.load(std::memory_order_acquire) == seen; spin++) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::function<int()> job;
+    {
+      std::unique_lock<std::mutex> lk(w.m);
+      w.cv.wait(lk, [&] { return w.quit || w.posted.load(std::memory_order_acquire) != seen; });
+      if (w.quit) return;
+      seen = w.posted.load(std::memory_order_acquire);
+      job = std::move(w.job);
+    }
+    const int rc = job();
+    {
+      std::lock_guard<std::mutex> lk(w.m);
+      w.rc = rc;
+      w.finished.store(seen, std::memory_order_release);
+    }
+    w.cv.notify_all();
+  }
+}
+void group_post(int d, std::function<int()> job) {
+  Worker& w = *G.w[d];
+  {
+    std::lock_guard<std::mutex> lk(w.m);
+    w.job = std::move(job);
+    w.posted.fetch_add(1, std::memory_order_release);
+  }
+  w.cv.notify_all();
+}
+int group_wait(int d) {
+  Worker& w = *G.w[d];
+  const unsigned want = w.posted.load(std::memory_order_acquire);
+  for (int spin = 0; spin < 4000 && w.finished.load(std::memory_order_acquire) != want; spin++) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::unique_lock<std::mutex> lk(w.m);
+  w.cv.wait(lk, [&] { return w.finished.load(std::memory_order_acquire) == want; });
+  return w.rc;
+}
+// fn(d) on every device of the group: d = 0 on the caller's thread, the others on their workers, concurrently.
+// Returns the first failure; its message ends up in alps_b200_last_error().
+template <class F>
+int group_all(F fn) {
+  const int N = G.ngpu;
+  for (int d = 1; d < N; d++) group_post(d, [fn, d]() { return fn(d); });
+  const bool was = tl_in_group;
+  tl_in_group = true;
+  int rc = fn(0);
+  tl_in_group = was;
+  for (int d = 1; d < N; d++) {
+    const int r = group_wait(d);
+    if (r && !rc) {
+      rc = r;
+      memcpy(g_states[0].err, g_states[d].err, sizeof(g_states[0].err));
+    }
+  }
+  return rc;
+}
+// a public entry point called by the user on a group: run it on every device
+inline bool group_forward() { return G.ngpu > 1 && !tl_worker && !tl_in_group; }
+void group_stop_workers() {
+  for (int d = 1; d < MAXDEV; d++) {
+    if (!G.w[d]) continue;
+    {
+      std::lock_guard<std::mutex> lk(G.w[d]->m);
+      G.w[d]->quit = true;
+    }
+    G.w[d]->cv.notify_all();
+    if (G.w[d]->th.joinable()) G.w[d]->th.join();
+    delete G.w[d];
+    G.w[d] = nullptr;
+  }
+  G.ngpu = 1;
+  G.p2p = false;
+}
+
+bool comm_harmonic() { return G.comm != nullptr && G.nranks > 1 && G.partition == ALPS_B200_PARTITION_HARMONIC; }
+bool comm_omega_active() { return G.comm != nullptr && G.nranks > 1 && G.partition == ALPS_B200_PARTITION_OMEGA; }
+bool group_harmonic_active() { return group_forward() && G.partition == ALPS_B200_PARTITION_HARMONIC; }
+bool group_omega_active() { return group_forward() && G.partition == ALPS_B200_PARTITION_OMEGA; }
+
+int comm_allreduce_partials(double* d_partial, size_t count) {
+  NCK(G.nccl.AllReduce(d_partial, d_partial, count, ncclDouble, ncclSum, G.comm, S.stream));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -633,6 +856,57 @@ const char* alps_b200_last_error(void) { return S.err; }
 
 int alps_b200_init(const alps_b200_cfg* cfg) {
   if (!cfg) return fail(ALPS_B200_ERR_USAGE, "cfg is NULL");
+  if (!tl_worker && !tl_in_group) {
+    alps_b200_finalize();      // whole group, workers stopped
+    G.partition = ALPS_B200_PARTITION_OMEGA;
+    if (cfg->ngpu > 1) {
+      // device group: one State + host thread per device, every device initialised like a single one
+      if (cfg->ngpu > MAXDEV) return fail(ALPS_B200_ERR_USAGE, "ngpu must be <= %d", MAXDEV);
+      int ndev = 0, base = cfg->device;
+      if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ALPS_B200_ERR_CUDA, "no CUDA device available; alps_b200 has no CPU fallback");
+      }
+      if (base < 0) CK(cudaGetDevice(&base));
+      if (base + cfg->ngpu > ndev)
+        return fail(ALPS_B200_ERR_USAGE, "ngpu=%d from device %d, but only %d devices are visible", cfg->ngpu, base, ndev);
+      for (int d = 1; d < cfg->ngpu; d++) {
+        G.w[d] = new Worker();
+        G.w[d]->th = std::thread(worker_main, d);
+      }
+      G.ngpu = cfg->ngpu;
+      const alps_b200_cfg c0 = *cfg;
+      int rc = group_all([&](int d) {
+        alps_b200_cfg c = c0;
+        c.ngpu = 1;
+        c.device = base + d;
+        return alps_b200_init(&c);
+      });
+      if (!rc) {
+        // peer access for the harmonic partition's sum over NVLink (device 0 reads its peers' partial rows)
+        bool p2p = true;
+        for (int d = 1; d < G.ngpu && p2p; d++) {
+          int can = 0;
+          p2p = cudaDeviceCanAccessPeer(&can, base, base + d) == cudaSuccess && can;
+          if (p2p) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(base + d, 0);
+            p2p = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+          }
+        }
+        cudaGetLastError();
+        G.p2p = p2p;
+        const char* r = getenv("ALPS_B200_REDUCE");
+        G.reduce_nccl = !p2p || (r && !strcmp(r, "nccl"));
+      }
+      if (rc) {
+        char msg[sizeof(g_states[0].err)];
+        memcpy(msg, g_states[0].err, sizeof(msg));
+        alps_b200_finalize();
+        memcpy(g_states[0].err, msg, sizeof(msg));
+      }
+      return rc;
+    }
+  }
   alps_b200_finalize();
   if (cfg->nspec < 1 || cfg->nspec > MAXSPEC) return fail(ALPS_B200_ERR_USAGE, "nspec must be in [1,%d]", MAXSPEC);
   if (cfg->nperp < 4 || cfg->npar < 8) return fail(ALPS_B200_ERR_USAGE, "grid too small");
@@ -658,6 +932,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.stream = S.own_stream;
   CK(cudaEventCreate(&S.ev0));
   CK(cudaEventCreate(&S.ev1));
+  CK(cudaEventCreateWithFlags(&S.ev_part, cudaEventDisableTiming));
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -716,7 +991,23 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
 }
 
 void alps_b200_finalize(void) {
+  if (!tl_worker && !tl_in_group) {
+    if (G.ngpu > 1) {
+      for (int d = 0; d < G.ngpu; d++)
+        if (G.dev_comm[d] && G.nccl.CommDestroy) {
+          G.nccl.CommDestroy(G.dev_comm[d]);
+          G.dev_comm[d] = nullptr;
+        }
+      group_all([](int) {
+        alps_b200_finalize();
+        return 0;
+      });
+      group_stop_workers();
+      return;
+    }
+  }
   if (!S.inited) return;
+  cudaSetDevice(S.device);
   cudaDeviceSynchronize();
   for (int s = 0; s < MAXSPEC; s++) {
     SpeciesHost& h = S.sp[s];
@@ -750,7 +1041,10 @@ void alps_b200_finalize(void) {
   S.graph_off = false;
   if (S.ev0) cudaEventDestroy(S.ev0);
   if (S.ev1) cudaEventDestroy(S.ev1);
-  S.ev0 = S.ev1 = nullptr;
+  if (S.ev_part) cudaEventDestroy(S.ev_part);
+  S.ev0 = S.ev1 = S.ev_part = nullptr;
+  dfree(&S.d_gather);
+  S.gather_cap = 0;
   if (S.own_stream) cudaStreamDestroy(S.own_stream);
   S.own_stream = S.stream = nullptr;
   S.tiles.clear();
@@ -761,6 +1055,7 @@ void alps_b200_finalize(void) {
 int alps_b200_set_species(int is, double ns, double qs, double ms, int relativistic, int usebM, int ACmethod,
                           int n_fits, const int* fit_type, const double* perp_correction, int logfit,
                           int poly_kind, int poly_order, double poly_log_max) {
+  if (group_forward()) return group_all([&](int d) { (void)d; return alps_b200_set_species(is, ns, qs, ms, relativistic, usebM, ACmethod, n_fits, fit_type, perp_correction, logfit, poly_kind, poly_order, poly_log_max); });
   memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (is < 1 || is > S.cfg.nspec) return fail(ALPS_B200_ERR_USAGE, "species index %d out of range", is);
@@ -784,6 +1079,7 @@ int alps_b200_set_species(int is, double ns, double qs, double ms, int relativis
 }
 
 int alps_b200_upload(const double* pp, const double* df0, const double* param_fit, const double* poly_fit_coeffs) {
+  if (group_forward()) return group_all([&](int d) { (void)d; return alps_b200_upload(pp, df0, param_fit, poly_fit_coeffs); });
   memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (!pp) return fail(ALPS_B200_ERR_USAGE, "pp is NULL");
@@ -855,6 +1151,7 @@ int alps_b200_upload(const double* pp, const double* df0, const double* param_fi
 
 int alps_b200_upload_rel(int nspec_rel, const double* f0_rel, const double* df0_rel, const double* gamma_rel,
                          const double* pparbar_rel) {
+  if (group_forward()) return group_all([&](int d) { (void)d; return alps_b200_upload_rel(nspec_rel, f0_rel, df0_rel, gamma_rel, pparbar_rel); });
   memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (!f0_rel || !df0_rel || !gamma_rel || !pparbar_rel) return fail(ALPS_B200_ERR_USAGE, "NULL table");
@@ -920,6 +1217,7 @@ int alps_b200_upload_rel(int nspec_rel, const double* f0_rel, const double* df0_
 }
 
 int alps_b200_derivative_f0(const double* f0, double* df0_out) {
+  if (group_forward()) return group_all([&](int d) { (void)d; return alps_b200_derivative_f0(f0, d == 0 ? df0_out : nullptr); });
   memo_clear();
   if (!S.inited || !S.d_pp_f) return fail(ALPS_B200_ERR_USAGE, "call alps_b200_upload before alps_b200_derivative_f0");
   if (!f0) return fail(ALPS_B200_ERR_USAGE, "f0 is NULL");
@@ -939,6 +1237,8 @@ int alps_b200_derivative_f0(const double* f0, double* df0_out) {
 }
 
 int alps_b200_set_harmonic_shard(int rank, int nranks) {
+  if (group_forward())
+    return fail(ALPS_B200_ERR_USAGE, "device group (ngpu > 1): use alps_b200_set_partition instead of set_harmonic_shard");
   memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ALPS_B200_ERR_USAGE, "bad shard %d/%d", rank, nranks);
@@ -950,6 +1250,7 @@ int alps_b200_set_harmonic_shard(int rank, int nranks) {
 }
 
 int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
+  if (group_forward()) return group_all([&](int d) { (void)d; return alps_b200_set_k(kperp, kpar, d == 0 ? nmax_out : nullptr); });
   memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (!S.have_tables) return fail(ALPS_B200_ERR_USAGE, "no f0 tables: call alps_b200_upload (+ derivative_f0) first");
@@ -1217,7 +1518,11 @@ int alps_b200_disp_batch_dev(int n, const double* d_om, double* d_D) {
   int rc = check_ready();
   if (rc) return rc;
   if (n <= 0) return 0;
+  if (group_harmonic_active() || comm_harmonic())
+    return fail(ALPS_B200_ERR_USAGE, "alps_b200_disp_batch_dev serves one device: use alps_b200_disp_batch with the "
+                                     "harmonic partition");
   if ((rc = bind_batch(n))) return rc;
+  ClassScope cls(n);     // every internal chunk sums in the order of the whole call
   for (int o = 0; o < n; o += S.batch) {
     int m = std::min(S.batch, n - o);
     if ((rc = run_chunk(m, d_om + 2 * (size_t)o, d_D + 2 * (size_t)o, nullptr, nullptr, false))) return rc;
@@ -1227,18 +1532,14 @@ int alps_b200_disp_batch_dev(int n, const double* d_om, double* d_D) {
 
 static int small_batch_graph(int n, const double* om, double* D, int* used);
 
-int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
-  return alps_b200_disp_batch_full(n, om, D, chi0_opt, nullptr, nullptr);
-}
-
-int alps_b200_disp_batch_full(int n, const double* om, double* D, double* chi0_opt, double* chi0_low_opt,
-                              double* wave_opt) {
-  int rc = check_ready();
-  if (rc) return rc;
-  if (n <= 0) return 0;
-  if (!om || !D) return fail(ALPS_B200_ERR_USAGE, "om / D is NULL");
+// n omegas in host memory on THIS device (state S): H2D, chunks of S.batch, D2H.  class_n = omegas of the API call
+// these n belong to.
+static int eval_host(int n, const double* om, double* D, double* chi0_opt, double* chi0_low_opt, double* wave_opt,
+                     int class_n) {
+  int rc;
   const bool aux = chi0_opt || chi0_low_opt || wave_opt;
-  if (!aux && n <= LAT_BATCH) {   // latency batch class: captured chain (batched roots, prefetched solver steps)
+  ClassScope cls(class_n);
+  if (!aux && std::max(n, class_n) <= LAT_BATCH) {   // latency batch class: captured chain (batched roots, prefetched solver steps)
     int used = 0;
     if ((rc = small_batch_graph(n, om, D, &used))) return rc;
     if (used) return 0;
@@ -1267,6 +1568,24 @@ int alps_b200_disp_batch_full(int n, const double* om, double* D, double* chi0_o
     memcpy(D + 2 * (size_t)o, h_D, (size_t)m * 2 * sizeof(double));
   }
   return 0;
+}
+
+int alps_b200_disp_batch(int n, const double* om, double* D, double* chi0_opt) {
+  return alps_b200_disp_batch_full(n, om, D, chi0_opt, nullptr, nullptr);
+}
+
+int alps_b200_disp_batch_full(int n, const double* om, double* D, double* chi0_opt, double* chi0_low_opt,
+                              double* wave_opt) {
+  int rc = check_ready();
+  if (rc) return rc;
+  if (n <= 0) return 0;
+  if (!om || !D) return fail(ALPS_B200_ERR_USAGE, "om / D is NULL");
+  const bool aux = chi0_opt || chi0_low_opt || wave_opt;
+  // partitions over the GPUs of the box (bottom of the file): device group of this process, or one process per GPU
+  if (group_harmonic_active()) return group_harmonic_eval(n, om, D, chi0_opt, chi0_low_opt, wave_opt);
+  if (group_omega_active() && n > LAT_BATCH) return group_omega_eval(n, om, D, chi0_opt, chi0_low_opt, wave_opt);
+  if (comm_omega_active() && !aux && n > LAT_BATCH) return comm_omega_eval(n, om, D);
+  return eval_host(n, om, D, chi0_opt, chi0_low_opt, wave_opt, n);
 }
 
 // Signature of everything a captured chain of n omegas bakes in.
@@ -1357,7 +1676,7 @@ static int disp_via_graph(int n, int* used) {
 // n <= LAT_BATCH omegas (host) through the captured chain when possible; *used = 0: caller takes the plain path
 static int small_batch_graph(int n, const double* om, double* D, int* used) {
   *used = 0;
-  if (S.graph_off || S.stream == nullptr || S.ext_any || n < 1 || n > LAT_BATCH) return 0;
+  if (S.graph_off || S.stream == nullptr || S.ext_any || n < 1 || n > LAT_BATCH || comm_harmonic()) return 0;
   int rc;
   if ((rc = bind_batch(n))) return rc;
   if ((rc = ensure_pinned(64 * sizeof(double)))) return rc;
@@ -1371,6 +1690,10 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   int rc = check_ready();
   if (rc) return rc;
   if (!om) return fail(ALPS_B200_ERR_USAGE, "om is NULL");
+  if (group_harmonic_active()) {
+    double Dl[2];
+    return group_harmonic_eval(1, om, D ? D : Dl, chi0, chi0_low, wave);
+  }
   const bool plain_D = !chi0 && !chi0_low && !wave && !S.ext_any;
   if (plain_D && S.memo_on) {
     const bool hit = memo_lookup(om, D);
@@ -1408,7 +1731,7 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   if ((rc = ensure_pinned(64 * sizeof(double)))) return rc;
   S.h_pin[ZC_OM] = om[0];
   S.h_pin[ZC_OM + 1] = om[1];
-  if (plain_D && !S.graph_off && S.stream != nullptr) {
+  if (plain_D && !S.graph_off && S.stream != nullptr && !comm_harmonic()) {
     int used = 0;
     if ((rc = disp_via_graph(1, &used))) return rc;
     if (used) {
@@ -1490,6 +1813,7 @@ int alps_b200_add_external_chi(int is, const double* chi, const double* chi_low)
 
 int alps_b200_set_bm_species(int is, int bM_nmaxs, double bM_Bessel_zeros, double bM_betas, double bM_alphas,
                              double bM_pdrifts) {
+  if (group_forward()) return group_all([&](int d) { (void)d; return alps_b200_set_bm_species(is, bM_nmaxs, bM_Bessel_zeros, bM_betas, bM_alphas, bM_pdrifts); });
   memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (is < 1 || is > S.cfg.nspec || !S.sp[is - 1].set) return fail(ALPS_B200_ERR_USAGE, "species %d not set", is);
@@ -1604,6 +1928,7 @@ int alps_b200_assemble_dev(int n, const double* d_om, const double* d_partial, d
 }
 
 int alps_b200_set_mode(int mode) {
+  if (group_forward()) return group_all([&](int d) { (void)d; return alps_b200_set_mode(mode); });
   memo_clear();
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   if (mode != 0 && mode != 1) return fail(ALPS_B200_ERR_USAGE, "mode must be 0 (direct) or 1 (k-hoisted)");
@@ -1620,6 +1945,7 @@ int alps_b200_set_stream(void* cuda_stream) {
 }
 
 int alps_b200_sync(void) {
+  if (group_forward()) return group_all([&](int d) { (void)d; return alps_b200_sync(); });
   if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
   return check_device_errors();
 }
@@ -1635,14 +1961,25 @@ int alps_b200_get_info(int what, double* out) {
       *out = t;
       return 0;
     }
-    case ALPS_B200_INFO_LAUNCHES: *out = (double)S.launches; return 0;
+    case ALPS_B200_INFO_LAUNCHES: {
+      double t = 0.0;
+      for (int d = 0; d < (tl_worker ? 1 : G.ngpu); d++) t += (double)(tl_worker ? S.launches : g_states[d].launches);
+      *out = t;
+      return 0;
+    }
+    case ALPS_B200_INFO_NGPU: *out = (double)(G.ngpu * (G.comm ? G.nranks : 1)); return 0;
     case ALPS_B200_INFO_SM_COUNT: *out = S.sm_count; return 0;
     case ALPS_B200_INFO_LAST_KERNEL_MS: *out = S.last_kernel_ms; return 0;
     case ALPS_B200_INFO_BATCH: *out = S.have_k ? auto_batch() : 0; return 0;
     case ALPS_B200_INFO_DFMA_NOREUSE: *out = run_dfma_peak_noreuse(S.stream); S.launches += 3; return 0;
     case ALPS_B200_INFO_DMMA_PEAK: *out = run_dmma_peak(S.stream); S.launches += 3; return 0;
     case ALPS_B200_INFO_QUAD_VARIANT: *out = S.qv.id; return 0;
-    case ALPS_B200_INFO_D_EVALS: *out = (double)S.d_evals; return 0;
+    case ALPS_B200_INFO_D_EVALS: {
+      double t = 0.0;
+      for (int d = 0; d < (tl_worker ? 1 : G.ngpu); d++) t += (double)(tl_worker ? S.d_evals : g_states[d].d_evals);
+      *out = t;
+      return 0;
+    }
     case ALPS_B200_INFO_SET_K_CALLS: *out = (double)S.set_k_calls; return 0;
     case ALPS_B200_INFO_MEMO_HITS: *out = (double)S.memo_hits; return 0;
     case ALPS_B200_INFO_PREFETCHED: *out = (double)(S.prefetched + S.speculated); return 0;
@@ -1694,6 +2031,195 @@ int alps_b200_dfma_peak(double* tflops) {
   if (!S.inited || !tflops) return fail(ALPS_B200_ERR_USAGE, "bad arguments");
   *tflops = run_dfma_peak(S.stream);
   S.launches += 3;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+// ----------------------------------------------------------------------------- OMEGA partition, device group
+// Contiguous slices of the caller's host arrays, one per device; every slice is evaluated in the batch class of the
+// whole call, so the bits do not depend on the number of devices.  No gather: the slices land in the caller's D.
+int group_omega_eval(int n, const double* om, double* D, double* chi0, double* chi0_low, double* wave) {
+  const int nparts = std::min(G.ngpu, std::max(1, n / LAT_BATCH));
+  const int nspec = g_states[0].cfg.nspec;
+  return group_all([&](int d) {
+    int lo = 0, hi = 0;
+    if (d >= nparts) return 0;
+    alps_b200_omega_slice(n, d, nparts, &lo, &hi);
+    if (hi <= lo) return 0;
+    return eval_host(hi - lo, om + 2 * (size_t)lo, D + 2 * (size_t)lo, chi0 ? chi0 + (size_t)lo * nspec * 18 : nullptr,
+                     chi0_low ? chi0_low + (size_t)lo * nspec * 54 : nullptr, wave ? wave + (size_t)lo * 18 : nullptr, n);
+  });
+}
+
+// -------------------------------------------------------------------------- HARMONIC partition, device group
+// Every device evaluates the chi partials of its harmonic shard for all omegas of the chunk on its own stream and
+// records an event; device 0's stream waits for the events, sums the partial rows of its peers (k_reduce_partials reads
+// them through peer memory over NVLink, in device order: deterministic) or, with ALPS_B200_REDUCE=nccl, every device
+// joins an ncclAllReduce; device 0 then assembles D.  Replaces the two MPI_REDUCEs of disp() (src/ALPS_fns.f90:519-523).
+int group_harmonic_eval(int n, const double* om, double* D, double* chi0, double* chi0_low, double* wave) {
+  const int N = G.ngpu;
+  State& S0 = g_states[0];
+  const bool aux = chi0 || chi0_low || wave;
+  const int nspec = S0.cfg.nspec;
+  if (S0.ext_any) return fail(ALPS_B200_ERR_UNSUPPORTED, "external chi with the harmonic partition of a device group");
+  if (G.reduce_nccl && !G.dev_comm[0]) {
+    int rc = nccl_load();
+    if (rc) return rc;
+    int devs[MAXDEV];
+    for (int d = 0; d < N; d++) devs[d] = g_states[d].device;
+    NCK(G.nccl.CommInitAll(G.dev_comm, N, devs));
+    cudaSetDevice(S0.device);
+  }
+  int B = 0;
+  {
+    int rc = group_all([&](int) { return bind_batch(n); });
+    if (rc) return rc;
+    B = g_states[0].batch;
+    for (int d = 1; d < N; d++) B = std::min(B, g_states[d].batch);
+  }
+  const size_t per = (size_t)nspec * PARTIAL_PER_SPEC;
+  for (int o = 0; o < n; o += B) {
+    const int m = std::min(B, n - o);
+    int rc = group_all([&](int) {
+      int r;
+      if ((r = ensure_pinned((size_t)S.batch * 4 * sizeof(double)))) return r;
+      ClassScope cls(n);
+      memcpy(S.h_pin, om + 2 * (size_t)o, (size_t)m * 2 * sizeof(double));
+      CK(cudaMemcpyAsync(S.d_om, S.h_pin, (size_t)m * 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+      if ((r = run_chunk(m, S.d_om, nullptr, S.d_partial, nullptr, false))) return r;
+      if (G.reduce_nccl)
+        NCK(G.nccl.AllReduce(S.d_partial, S.d_partial, (size_t)m * per, ncclDouble, ncclSum,
+                             G.dev_comm[(int)(&S - g_states)], S.stream));
+      CK(cudaEventRecord(S.ev_part, S.stream));
+      return 0;
+    });
+    if (rc) return rc;
+    // device 0 (the caller's thread)
+    if (!G.reduce_nccl) {
+      const double* src[MAXDEV] = {nullptr};
+      for (int d = 1; d < N; d++) {
+        CK(cudaStreamWaitEvent(S0.stream, g_states[d].ev_part, 0));
+        src[d - 1] = g_states[d].d_partial;
+      }
+      launch_reduce_partials(S0.d_partial, src, N - 1, (size_t)m * per, S0.stream);
+      S0.launches += 1;
+    }
+    {
+      ClassScope cls(n);
+      if ((rc = run_chunk(m, S0.d_om, S0.d_D, nullptr, S0.d_partial, aux))) return rc;
+    }
+    double* h_D = S0.h_pin + 2 * (size_t)S0.batch;
+    CK(cudaMemcpyAsync(h_D, S0.d_D, (size_t)m * 2 * sizeof(double), cudaMemcpyDeviceToHost, S0.stream));
+    if (chi0)
+      CK(cudaMemcpyAsync(chi0 + (size_t)o * nspec * 18, S0.d_chi0, (size_t)m * nspec * 18 * sizeof(double),
+                         cudaMemcpyDeviceToHost, S0.stream));
+    if (chi0_low)
+      CK(cudaMemcpyAsync(chi0_low + (size_t)o * nspec * 54, S0.d_chi0_low, (size_t)m * nspec * 54 * sizeof(double),
+                         cudaMemcpyDeviceToHost, S0.stream));
+    if (wave)
+      CK(cudaMemcpyAsync(wave + (size_t)o * 18, S0.d_wave, (size_t)m * 18 * sizeof(double), cudaMemcpyDeviceToHost,
+                         S0.stream));
+    if ((rc = check_device_errors())) return rc;     // synchronises device 0: its peers' rows have been read
+    memcpy(D + 2 * (size_t)o, h_D, (size_t)m * 2 * sizeof(double));
+  }
+  // error words of the other devices (resonance-window overflow, alps_error(8)) -- their streams are idle by now
+  return group_all([&](int d) { return d ? check_device_errors() : 0; });
+}
+
+// ------------------------------------------------------------------- OMEGA partition, one process per GPU
+// Every rank calls with the same n omegas; rank r evaluates the slice [r per, (r+1) per) into its part of a device
+// buffer that holds all slices, one in-place ncclAllGather on the library's stream completes it on every rank.
+int comm_omega_eval(int n, const double* om, double* D) {
+  const int R = G.nranks, per = (n + R - 1) / R;
+  const int lo = std::min(n, G.rank * per), hi = std::min(n, lo + per);
+  int rc;
+  if ((rc = bind_batch(std::max(1, hi - lo)))) return rc;
+  const size_t need = (size_t)2 * per * R;
+  if (need > S.gather_cap) {
+    if (dalloc(&S.d_gather, need)) return ALPS_B200_ERR_CUDA;
+    S.gather_cap = need;
+  }
+  if ((rc = ensure_pinned(std::max((size_t)S.batch * 4, need) * sizeof(double)))) return rc;
+  ClassScope cls(n);
+  for (int o = lo; o < hi; o += S.batch) {
+    const int m = std::min(S.batch, hi - o);
+    memcpy(S.h_pin, om + 2 * (size_t)o, (size_t)m * 2 * sizeof(double));
+    CK(cudaMemcpyAsync(S.d_om, S.h_pin, (size_t)m * 2 * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    if ((rc = run_chunk(m, S.d_om, S.d_gather + 2 * (size_t)o, nullptr, nullptr, false))) return rc;
+    if (o + m < hi) CK(cudaStreamSynchronize(S.stream));   // h_pin / d_om are reused by the next chunk
+  }
+  NCK(G.nccl.AllGather(S.d_gather + (size_t)2 * per * G.rank, S.d_gather, (size_t)2 * per, ncclDouble, G.comm, S.stream));
+  CK(cudaMemcpyAsync(S.h_pin, S.d_gather, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
+  if ((rc = check_device_errors())) return rc;
+  memcpy(D, S.h_pin, (size_t)n * 2 * sizeof(double));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int alps_b200_omega_slice(int n, int rank, int nparts, int* lo, int* hi) {
+  if (n < 0 || nparts < 1 || rank < 0 || rank >= nparts || !lo || !hi) return ALPS_B200_ERR_USAGE;
+  const int base = n / nparts, rem = n % nparts;
+  *lo = rank * base + std::min(rank, rem);
+  *hi = *lo + base + (rank < rem ? 1 : 0);
+  return 0;
+}
+
+int alps_b200_set_partition(int kind) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (kind != ALPS_B200_PARTITION_OMEGA && kind != ALPS_B200_PARTITION_HARMONIC)
+    return fail(ALPS_B200_ERR_USAGE, "partition must be ALPS_B200_PARTITION_OMEGA or _HARMONIC");
+  G.partition = kind;
+  const bool harm = kind == ALPS_B200_PARTITION_HARMONIC;
+  if (G.ngpu > 1) {
+    const int N = G.ngpu;
+    return group_all([&](int d) { return alps_b200_set_harmonic_shard(harm ? d : 0, harm ? N : 1); });
+  }
+  if (G.comm) return alps_b200_set_harmonic_shard(harm ? G.rank : 0, harm ? G.nranks : 1);
+  return 0;      // one GPU, one process: nothing to partition
+}
+
+int alps_b200_comm_unique_id(char id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (!id) return fail(ALPS_B200_ERR_USAGE, "id is NULL");
+  int rc = nccl_load();
+  if (rc) return rc;
+  ncclUniqueId u;
+  NCK(G.nccl.GetUniqueId(&u));
+  memcpy(id, &u, sizeof(u));
+  return 0;
+}
+
+int alps_b200_comm_init(int rank, int nranks, const char id[128]) {
+  if (!S.inited) return fail(ALPS_B200_ERR_USAGE, "alps_b200_init has not been called");
+  if (G.ngpu > 1) return fail(ALPS_B200_ERR_USAGE, "a device group (ngpu > 1) cannot also join a communicator");
+  if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(ALPS_B200_ERR_USAGE, "bad communicator arguments");
+  int rc = nccl_load();
+  if (rc) return rc;
+  if (G.comm) alps_b200_comm_finalize();
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  CK(cudaSetDevice(S.device));
+  NCK(G.nccl.CommInitRank(&G.comm, nranks, u, rank));
+  G.rank = rank;
+  G.nranks = nranks;
+  memo_clear();
+  return 0;
+}
+
+int alps_b200_comm_finalize(void) {
+  if (G.comm && G.nccl.CommDestroy) {
+    cudaDeviceSynchronize();
+    G.nccl.CommDestroy(G.comm);
+  }
+  G.comm = nullptr;
+  G.rank = 0;
+  G.nranks = 1;
   return 0;
 }
 

@@ -100,7 +100,7 @@ void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int 
 bool plan_fused_ok(const GlobalDev& gh, int n_om);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
-                     int* tickets, cudaStream_t st, int gx = 148);
+                     int* tickets, cudaStream_t st, int gx = 148, int class_n = 0);   // class_n: omegas of the whole call
 constexpr int RESLAT_GX_NARROW = 16, RESLAT_GX_WIDE = 148;   // block columns per omega of k_resonant_lat (api.cu adapts)
 constexpr int RES_PART_DOUBLES = 11 * 16;   // k_resonant_lat: partial rows per item (LAT_PARTS x LAT_STRIDE)
 // chi partial layout per omega: [nspec][PARTIAL_PER_SPEC] doubles (see resonant.cu)
@@ -146,6 +146,8 @@ struct NhdsDev {
 };
 void launch_nhds_bessel(double z, int count, double* I, cudaStream_t st);
 void launch_nhds(const NhdsDev* nd, const double* om, int n_om, int nspec, int accumulate, double* ext, cudaStream_t st);
+// HARMONIC partition of a device group: dst += sum of the peers' partial rows, read through peer memory (multi_gpu.cu)
+void launch_reduce_partials(double* dst, const double* const* src, int nsrc, size_t count, cudaStream_t st);
 double run_dfma_peak(cudaStream_t st);
 double run_dfma_peak_noreuse(cudaStream_t st);
 

@@ -11,6 +11,8 @@
 //   k_assemble   the rank-0 part of disp() (:536-624): chi0, eps, wave, determinant
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -983,9 +985,9 @@ bool plan_fused_ok(const GlobalDev& gh, int n_om) {
 }
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
-                     int* tickets, cudaStream_t st, int gx) {
+                     int* tickets, cudaStream_t st, int gx, int class_n) {
   if (n_om <= 0) return;
-  if (n_om <= 64 && Spart && tickets) {
+  if (std::max(class_n, n_om) <= 64 && Spart && tickets) {
     // gx block columns per omega loop over the list of resonant harmonics: usually only n = 0 is resonant and a
     // narrow grid saves waves of idle blocks (C1: -2.8 us per D), many resonances (large k_par) want all SMs
     launch_chain(k_resonant_lat, dim3(min(148, max(1, gx * n_om)), LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan,

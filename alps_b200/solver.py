@@ -29,14 +29,16 @@ class Solver:
     global instance, like the reference's module state."""
 
     def __init__(self, plasma: Plasma, emulate_nproc: int = 0, device: int = -1, batch_max: int = 0,
-                 nmax_cap: int = 0, nmax_force: int = 0):
+                 nmax_cap: int = 0, nmax_force: int = 0, ngpu: int = 1):
+        """ngpu > 1: device group -- this process drives `ngpu` devices starting at `device`; the library keeps the
+        tables on every one and partitions disp_batch / map_search itself (set_partition)."""
         self.L = _lib.lib()
         self.pl = plasma
         maxorder = max(s.poly_order for s in plasma.species)
         cfg = _lib.Cfg(plasma.nspec, plasma.nperp, plasma.npar, plasma.ngamma, plasma.npparbar,
                        plasma.vA, plasma.Bessel_zero, plasma.Tlim, plasma.positions_principal,
                        plasma.n_resonance_interval, int(plasma.kperp_norm), emulate_nproc,
-                       plasma.maxfits, maxorder, device, nmax_cap, batch_max, nmax_force)
+                       plasma.maxfits, maxorder, device, nmax_cap, batch_max, nmax_force, ngpu)
         _lib.check(self.L.alps_b200_init(C.byref(cfg)))
         for i, s in enumerate(plasma.species):
             ft = np.asarray(s.fit_type, dtype=np.int32)
@@ -84,6 +86,34 @@ class Solver:
         """0 = direct quadrature per omega (default); 1 = k-hoisted tables ("map fast path").
         Call set_k afterwards."""
         _lib.check(self.L.alps_b200_set_mode(mode))
+
+    def set_partition(self, kind: int):
+        """_lib.PARTITION_OMEGA (default: batches are cut into one slice per GPU) or _lib.PARTITION_HARMONIC (every GPU
+        sums a block of harmonics, the chi partials are summed over NVLink).  Call set_k afterwards."""
+        _lib.check(self.L.alps_b200_set_partition(kind))
+
+    def comm_init(self, rank: int, world: int, broadcast):
+        """One process per GPU: join the library-owned NCCL communicator.  `broadcast(buf)` must overwrite the 128-byte
+        numpy uint8 array `buf` on every rank with rank 0's content (torch.distributed.broadcast, MPI_Bcast)."""
+        idb = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(self.L.alps_b200_comm_unique_id(_p(idb)))
+        broadcast(idb)
+        _lib.check(self.L.alps_b200_comm_init(rank, world, _p(idb)))
+
+    def comm_init_torch(self, group=None):
+        """comm_init over an initialised torch.distributed process group (any backend)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+        def bcast(buf):
+            t = torch.from_numpy(buf)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=0, group=group)
+            buf[:] = t.cpu().numpy()
+        self.comm_init(rank, world, bcast)
 
     def set_harmonic_shard(self, rank: int, nranks: int):
         _lib.check(self.L.alps_b200_set_harmonic_shard(rank, nranks))

@@ -53,6 +53,10 @@ typedef struct {
   int batch_max;                 /* omegas processed per internal chunk (0 = auto)            */
   int nmax_force;                /* >0: skip determine_nmax and sum n in [0,nmax_force] for every
                                     table species (synthetic benchmark configs only)          */
+  int ngpu;                      /* devices this PROCESS drives: device, device+1, ... (0 or 1 = one GPU).  With
+                                    ngpu > 1 the library keeps the tables on every device and partitions the work
+                                    itself (alps_b200_set_partition) -- the replacement for `mpirun -np N` when only
+                                    one process calls (the Fortran shim)                  */
 } alps_b200_cfg;
 
 /* replaces: allocation + pass_instructions (src/ALPS_com.f90:28-170) for the path's scalars */
@@ -134,7 +138,36 @@ int alps_b200_nhds_calc_chi(double ns, double qs, double ms, int bM_nmaxs, doubl
 int alps_b200_tps_eval(int n, const double *gc, const double *pc, const double *w, int npts, const double *gx,
                        const double *px, double *out);
 
-/* Harmonic sharding (replaces split_processes + MPI_REDUCE, src/ALPS_fns.f90:4079-4207, 519-523):
+/* ------------------------------------------------------------------------------------------
+ * Partition over the GPUs of one box -- replaces ALPS_com's MPI harmonic split (split_processes + the two MPI_REDUCEs
+ * of disp(), src/ALPS_fns.f90:4079-4207, 519-523).  Two ways to have several GPUs:
+ *   (a) device group: alps_b200_cfg.ngpu = N, ONE process; nothing else changes in the caller;
+ *   (b) one process per GPU (mpirun / torchrun, like the reference's ranks): every rank initialises its own device and
+ *       joins a library-owned NCCL communicator (alps_b200_comm_unique_id on rank 0, the 128 bytes broadcast by the
+ *       caller -- MPI_Bcast / torch.distributed -- then alps_b200_comm_init on every rank).  disp / disp_batch /
+ *       map_search are then COLLECTIVE like the reference's disp(): every rank calls them with the same arguments and
+ *       every rank gets the full result.
+ * and two partitions (alps_b200_set_partition; call alps_b200_set_k afterwards):
+ *   OMEGA     (default) batches of more than 8 omegas -- the nr x ni loop of map_search, batches of roots -- are cut
+ *             into contiguous slices, one per GPU, tables replicated, no communication but the final gather of D
+ *             ((a): the slices land in the caller's host array; (b): one ncclAllGather).  Single omegas run on one GPU.
+ *   HARMONIC  every GPU sums a contiguous block of |n| per species for ALL omegas of the call; the un-normalised chi
+ *             partials (48 complex per species and omega) are summed over NVLink -- (a) by one kernel on device 0 that
+ *             reads its peers' buffers (peer memory; ALPS_B200_REDUCE=nccl: ncclAllReduce), (b) ncclAllReduce on the
+ *             library's stream -- and D is assembled from the sum.  Pays when one D is much more than ~100 us of GPU
+ *             work (C5-sized tables); for the shipped configs the OMEGA partition is the faster one.
+ * The result of a call does not depend on how it was cut: every piece sums in the order of the whole call's batch
+ * class, so ngpu = N and ngpu = 1 (and N ranks vs one) give bitwise identical D under the OMEGA partition. */
+#define ALPS_B200_PARTITION_OMEGA 0
+#define ALPS_B200_PARTITION_HARMONIC 1
+int alps_b200_set_partition(int kind);
+int alps_b200_comm_unique_id(char id[128]);                        /* ncclGetUniqueId (rank 0)               */
+int alps_b200_comm_init(int rank, int nranks, const char id[128]); /* ncclCommInitRank on this rank's device */
+int alps_b200_comm_finalize(void);
+/* host-only: the slice [lo, hi) of n omegas that part `rank` of `nparts` evaluates under the OMEGA partition */
+int alps_b200_omega_slice(int n, int rank, int nparts, int *lo, int *hi);
+
+/* Low-level harmonic sharding for callers that do their own reduction (kept from round 1):
  * restrict this process to harmonics |n| in [nlo,nhi] of species is (is=0: all species),
  * produce un-normalised partial sums (caller all-reduces them over NCCL), then assemble. */
 int alps_b200_set_harmonic_shard(int rank, int nranks);
@@ -163,6 +196,7 @@ int alps_b200_get_info(int what, double *out); /* see ALPS_B200_INFO_* */
 #define ALPS_B200_INFO_D_EVALS 8          /* D(omega,k) evaluations since init (every entry point)             */
 #define ALPS_B200_INFO_SET_K_CALLS 9      /* alps_b200_set_k calls since init                                   */
 #define ALPS_B200_INFO_PREFETCHED 11      /* omegas evaluated ahead of their request by alps_b200_disp_prefetch (part of D_EVALS) */
+#define ALPS_B200_INFO_NGPU 12            /* devices of this process' group x ranks of the communicator       */
 #define ALPS_B200_INFO_MEMO_HITS 10       /* alps_b200_disp calls answered from the memo of the last omegas (same
                                              omega bits, same state: no launch; not counted in D_EVALS)          */
 

@@ -18,13 +18,13 @@ module alps_b200_shim
   use iso_c_binding
   implicit none
   private
-  public :: b200_setup, b200_set_k, b200_disp, b200_map, b200_finalize
+  public :: b200_setup, b200_set_k, b200_disp, b200_map, b200_finalize, b200_ngpu
 
   type, bind(c) :: alps_b200_cfg            ! include/alps_b200.h : alps_b200_cfg
      integer(c_int) :: nspec, nperp, npar, ngamma, npparbar
      real(c_double) :: vA, Bessel_zero, Tlim
      integer(c_int) :: positions_principal, n_resonance_interval, kperp_norm, emulate_nproc
-     integer(c_int) :: maxfits, maxorder, device, nmax_cap, batch_max, nmax_force
+     integer(c_int) :: maxfits, maxorder, device, nmax_cap, batch_max, nmax_force, ngpu
   end type alps_b200_cfg
 
   interface
@@ -100,6 +100,7 @@ contains
     cfg%kperp_norm = merge(1, 0, kperp_norm); cfg%emulate_nproc = nproc
     cfg%maxfits = maxval(n_fits); cfg%maxorder = maxval(poly_order)
     cfg%device = -1; cfg%nmax_cap = 0; cfg%batch_max = 0; cfg%nmax_force = 0
+    cfg%ngpu = b200_ngpu()          ! every GPU of the box: the library partitions b200_map's batch itself
     ierr = alps_b200_init(cfg)
     if (ierr /= 0) call alps_error(ierr)
     do is = 1, nspec
@@ -162,5 +163,19 @@ contains
   subroutine b200_finalize()
     call alps_b200_finalize()
   end subroutine b200_finalize
+
+  !> Devices the library should drive from this (single) calling rank: environment variable ALPS_B200_NGPU,
+  !> default 1.  With ngpu > 1 nothing else changes on the Fortran side: b200_map's batch is cut into one slice
+  !> per GPU inside alps_b200_disp_batch (OMEGA partition, include/alps_b200.h).
+  integer function b200_ngpu()
+    character(len=16) :: v
+    integer :: stat, n
+    b200_ngpu = 1
+    call get_environment_variable('ALPS_B200_NGPU', v, status=stat)
+    if (stat == 0) then
+       read(v, *, iostat=stat) n
+       if (stat == 0 .and. n >= 1) b200_ngpu = n
+    endif
+  end function b200_ngpu
 
 end module alps_b200_shim

@@ -197,7 +197,7 @@ def test_mode1_parity_battery():
     cases = []
     pl = tables.config_small(24, 48, kind=1)
     dp = pl.pp[0, 2, 2, 1] - pl.pp[0, 2, 1, 1]
-    nodes = [0.05 * pl.pp[0, 2, j, 1] for j in (1, 2, 24, 46, 47)]            # Re p_res on nodes (kpar = 0.05, n = 0)
+    nodes = [0.05 * pl.pp[0, 2, j, 1] for j in (1, 2, 30, 46, 47)]            # Re p_res on nodes (kpar = 0.05, n = 0)
     edge = [0.05 * (pl.pp[0, 2, 47, 1] + 2.4 * dp), 0.05 * (pl.pp[0, 2, 1, 1] - 1.6 * dp)]
     oms = (list(omega_samples(1, 8, (0.02, 1.5), (-0.05, 0.05))) + [0.3 + 0j, 0.011 - 1e-6j, 1.0 + 1e-5j]
            + [complex(x, g) for x in nodes + edge for g in (-1e-3, 0.0, 2e-3)])
