@@ -299,10 +299,13 @@ void launch_fast(const GlobalDev* g, const double* om, int n_om, const FastItem*
   }
   const int nch = (npar - 1 + FT_CH - 1) / FT_CH;
   const size_t smem = ((size_t)FT_STAGES * FT_CH * FT_W + (size_t)nch * FT_CH) * sizeof(double);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaFuncSetAttribute(k_fast_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
+  // opt-in shared memory, per device: raised to the device limit once (the p_par axis of any grid that fits is covered)
+  static PerDeviceOnce once;
+  if (once.first()) {
+    int dev = 0, lim = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncSetAttribute(k_fast_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, lim - 1024);
   }
   dim3 grid((n_om + FT_THREADS - 1) / FT_THREADS, nitems);
   k_fast_tiled<<<grid, FT_THREADS, smem, st>>>(g, om, n_om, items, plan, Sbulk, gwin, kpar);

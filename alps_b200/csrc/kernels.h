@@ -58,6 +58,20 @@ inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block,
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Function attributes (opt-in dynamic shared memory) are per DEVICE: a launcher that raises them remembers the devices
+// it has done so for (a device group launches the same kernels on several devices from several host threads).
+struct PerDeviceOnce {
+  unsigned mask = 0;
+  // true exactly once per device (benign race: two threads never share a device)
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned bit = 1u << (dev & 31);
+    const unsigned old = __atomic_fetch_or(&mask, bit, __ATOMIC_RELAXED);
+    return !(old & bit);
+  }
+};
+
 // set-up (setup_kernels.cu)
 void launch_derivative_f0(const double* f0, const double* pp, double* df0, int nspec, int nperp, int npar,
                           cudaStream_t st);

@@ -348,13 +348,12 @@ __global__ void __launch_bounds__((2 * RG + PW) * 32, 1) k_quad(const __grid_con
 // ---------------------------------------------------------------- variants / launcher
 template <int RG, int BKT, int NST, int PW, int UNR, bool STORE>
 static cudaError_t launch_one(const QuadParams& P, cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceOnce once;
   const size_t smem = sizeof(QuadSmem<RG, BKT, NST>) + 128;
-  if (!attr_set) {
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(k_quad<RG, BKT, NST, PW, UNR, STORE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   k_quad<RG, BKT, NST, PW, UNR, STORE><<<P.n_om * P.ntiles * P.nsplit, (2 * RG + PW) * 32, smem, st>>>(P);
   return cudaGetLastError();

@@ -388,13 +388,12 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
 
 template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0, int PK = 0>
 static cudaError_t launch_mma_one(const QuadParams& P, cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceOnce once;
   const size_t smem = sizeof(MmaSmem<NW, KSTG, NST>) + 128;
-  if (!attr_set) {
+  if (once.first()) {
     cudaError_t e = cudaFuncSetAttribute(k_quad_mma<NW, HS, KSTG, NST, STORE, DBG, PK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   return launch_chain(k_quad_mma<NW, HS, KSTG, NST, STORE, DBG, PK>, dim3(P.n_om * P.ntiles * P.nsplit),
                       dim3(32 * NW * HS), smem, st, P);

@@ -78,6 +78,12 @@ def derivative_f0_rel(pp_s, f0_s, ms, vA, ngamma, npparbar, smoothing=0.0, backe
     inside = f0_rel > -1.0
     integrate = float(np.sum(gamma_rel[inside] * f0_rel[inside]) * 2.0 * np.pi * dgamma * dpparbar * (ms / vA) ** 3)
     f0_rel[f0_rel != -1.0] /= integrate
+    return gamma_rel, pparbar_rel, f0_rel, rel_derivatives(f0_rel, gamma_rel, pparbar_rel), integrate
+
+
+def rel_derivatives(f0_rel, gamma_rel, pparbar_rel):
+    """df0_rel(:, :, 1:2) = d f0_rel / d Gamma, d f0_rel / d pbar_par by centred differences, one-sided next to the cone
+    (f0_rel = -1 outside it): the last block of derivative_f0_rel, src/ALPS_fns_rel.f90:230-270."""
     df = np.zeros(f0_rel.shape + (2,))
     F = f0_rel
     c = (slice(1, -1), slice(1, -1))
@@ -96,4 +102,4 @@ def derivative_f0_rel(pp_s, f0_s, ms, vA, ngamma, npparbar, smoothing=0.0, backe
     d2[e2] = ((rt - mid) / (pr - pm))[e2]
     df[c + (0,)] = d1
     df[c + (1,)] = d2
-    return gamma_rel, pparbar_rel, f0_rel, df, integrate
+    return df

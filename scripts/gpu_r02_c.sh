@@ -1,0 +1,6 @@
+#!/bin/bash
+# round 2, one GPU: full GPU suite, ncu --set full of k_fast_tiled (hoisted map mode)
+mkdir -p gpurun_out
+( time timeout 1700 python -m pytest tests -m gpu -q --durations=8 ) > gpurun_out/r02c_tests.log 2>&1; tail -15 gpurun_out/r02c_tests.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fast_tiled -s 1 -c 1 -f -o gpurun_out/r02c_k_fast_tiled \
+  python scripts/fast_probe.py > gpurun_out/r02c_ncu_fast.log 2>&1; tail -2 gpurun_out/r02c_ncu_fast.log
