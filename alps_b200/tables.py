@@ -244,7 +244,8 @@ def config_small(nperp: int = 24, npar: int = 48, kind: int = 1) -> Plasma:
                        Bessel_zero=1.0e-30)
 
 
-def config_relativistic(nperp: int = 30, npar: int = 60, ngamma: int = 500, npparbar: int = 500) -> Plasma:
+def config_relativistic(nperp: int = 30, npar: int = 60, ngamma: int = 500, npparbar: int = 500,
+                        rel_backend: str = "host") -> Plasma:
     """C3: tests/test_relativistic.in + distribution/test_relativistic_dist.in (Juettner pair plasma,
     vA = 1, both species relativistic, fit type 4).  The (Gamma, pbar_par) tables come from the host-side
     restatement of derivative_f0_rel (alps_b200/relativistic.py)."""
@@ -261,7 +262,7 @@ def config_relativistic(nperp: int = 30, npar: int = 60, ngamma: int = 500, nppa
     cache = None
     for i in range(2):
         if cache is None:     # both species have the same f0 table: one thin-plate-spline solve
-            cache = derivative_f0_rel(pp[i], f0[i], specs[i].ms, vA, ngamma, npparbar)
+            cache = derivative_f0_rel(pp[i], f0[i], specs[i].ms, vA, ngamma, npparbar, backend=rel_backend)
         g, p, f, d, integ = cache
         gam[i], pb[i], f0_rel[i], df0_rel[i] = g, p, f, d
         pf[i, :, 0, 0] = fits[i]["params"][0] / integ          # amplitude of the renormalised table

@@ -45,6 +45,7 @@ static struct {
   int nworkers;
   struct worker { int sproc; int nlim[2]; double *bessel_array; } *w;
   int ncap;
+  int sstride, soffset; /* bench sampling: only harmonics with |n| % sstride == soffset are evaluated */
   int nthreads;
   int ready;
 } S;
@@ -1233,7 +1234,10 @@ int oracle_disp(const double om_[2], double D[2], double *chi0_out, double *chi0
         tn[t] = S.w[iw].nlim[0] + (t - first[iw]);
       }
 #pragma omp parallel for schedule(dynamic, 1) num_threads(S.nthreads > 0 ? S.nthreads : omp_get_max_threads())
-    for (t = 0; t < ntask; t++) disp_harmonic(&S.w[tw[t]], om, tn[t], &H[t]);
+    for (t = 0; t < ntask; t++) {
+      if (S.sstride > 1 && tn[t] % S.sstride != S.soffset) continue; /* bench sampling only: H[t] stays 0 */
+      disp_harmonic(&S.w[tw[t]], om, tn[t], &H[t]);
+    }
     for (iw = 0; iw < S.nworkers; iw++) disp_worker_finish(&S.w[iw], H + first[iw], first[iw + 1] - first[iw], &P[iw]);
     free(first); free(tw); free(tn); free(H);
   }
@@ -1384,6 +1388,8 @@ int oracle_init(const oracle_cfg *cfg) {
   S.fit_type = calloc((size_t)n * (cfg->maxfits > 0 ? cfg->maxfits : 1), sizeof(int));
   S.perp_correction = calloc((size_t)n * (cfg->maxfits > 0 ? cfg->maxfits : 1), sizeof(double));
   S.ncap = -1;
+  S.sstride = 0;
+  S.soffset = 0;
   S.nthreads = 0;
   return 0;
 }
@@ -1489,6 +1495,10 @@ void oracle_set_external_chi(int is, const double *chi, const double *chi_low) {
   g_ext_set[is - 1] = 1;
 }
 void oracle_set_ncap(int ncap) { S.ncap = ncap; }
+void oracle_set_sample(int stride, int offset) {
+  S.sstride = stride;
+  S.soffset = offset;
+}
 void oracle_set_threads(int n) { S.nthreads = n; }
 
 void oracle_get_nlim(int *nworkers, int *sproc, int *nlim1, int *nlim2, int cap) {

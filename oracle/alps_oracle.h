@@ -72,6 +72,10 @@ int oracle_disp(const double om[2], double D[2], double *chi0, double *chi0_low,
 /* chi(3,3), chi_low(3,3,-1:1) of a use_bM species (NHDS calc_chi output) for the following oracle_disp calls */
 void oracle_set_external_chi(int is, const double *chi, const double *chi_low);
 void oracle_set_ncap(int ncap);
+/* Evaluate only the harmonics with |n| % stride == offset (bench sampling only: a strided sample holds the expensive
+ * resonant harmonics in proportion, unlike the |n| <= ncap cut; stride <= 1 = off).  D is then NOT the dispersion
+ * determinant. */
+void oracle_set_sample(int stride, int offset);
 void oracle_set_threads(int nthreads);
 
 /* exposed pieces for unit tests */

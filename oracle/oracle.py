@@ -129,6 +129,10 @@ class Oracle:
     def set_ncap(self, ncap: int):
         self.L.oracle_set_ncap(ncap)
 
+    def set_sample(self, stride: int, offset: int = 0):
+        """bench sampling only: evaluate the harmonics |n| % stride == offset (stride <= 1: all)"""
+        self.L.oracle_set_sample(int(stride), int(offset))
+
     def disp(self, om: complex, full: bool = False, nhds: bool = True):
         """disp(om) of the reference; use_bM species get their chi from the NHDS restatement
         (src/ALPS_fns.f90:344-362) unless nhds=False (the caller then feeds set_external_chi itself)."""

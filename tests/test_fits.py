@@ -97,6 +97,33 @@ def test_chebyshev_series_fit():
     assert np.max(np.abs(rz - np.log10(f0z[2, 7:]))) < 2.0
 
 
+def test_chebyshev_glls_against_an_independent_least_squares_solve():
+    """determine_GLLS / least_squares_fit (src/ALPS_analyt.f90:731-848: normal equations through dgemm / dgesv) at the
+    order the shipped inputs use (30, tests/test_chebyshev.in) on bi-kappa rows, whose log10 is not a polynomial: the
+    coefficients must be the least-squares solution that an orthogonal-factorisation solver (numpy lstsq, SVD) finds
+    on the Chebyshev-Vandermonde matrix of the same nodes, and the series must reproduce the rows."""
+    from numpy.polynomial import chebyshev as Ch
+    npar, order = 300, 30
+    pl = tables.make_plasma([tables.DistSpec(ms=1.0, kappa=4.0, distribution=2)], ns=[1.0], qs=[1.0], nperp=12,
+                            npar=npar)
+    f0 = pl.f0[0]
+    c = fits.determine_GLLS(f0, order, logfit=True)
+    yy = -1.0 + np.arange(npar + 1) * (2.0 / npar)
+    V = Ch.chebvander(yy, order)
+    assert np.array_equal(V, fits.polynomial_basis(npar, order)) or np.max(np.abs(V - fits.polynomial_basis(npar, order))) < 1e-12
+    for iperp in range(f0.shape[0]):
+        ref = np.linalg.lstsq(V, np.log10(f0[iperp]), rcond=None)[0]
+        # the normal equations square the condition number (~1e3 here): 1e-9 of the largest coefficient
+        assert np.max(np.abs(c[iperp] - ref)) < 1e-9 * np.max(np.abs(ref)), iperp
+        rec = Ch.chebval(yy, c[iperp])
+        assert np.max(np.abs(rec - Ch.chebval(yy, ref))) < 1e-9          # the same series ...
+        assert np.max(np.abs(rec - np.log10(f0[iperp]))) < 1e-3         # ... whose truncation error is ~1e-4 in log10
+    # linear fit (logfit = F) goes through the same solver
+    cl = fits.determine_GLLS(f0, order, logfit=False)
+    refl = np.linalg.lstsq(V, f0[3], rcond=None)[0]
+    assert np.max(np.abs(cl[3] - refl)) < 1e-9 * np.max(np.abs(refl))
+
+
 def test_relativistic_rows_fit_type_4():
     """Juettner species on the (Gamma, pbar_par) grid (fit type 4, one amplitude per Gamma row, cone limits of
     lines 577-592): started from the .in value 0.62719 the fit lands on the amplitude that normalises f0_rel."""

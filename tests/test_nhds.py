@@ -79,6 +79,66 @@ def test_table_quadrature_agrees_with_the_closed_form():
         assert abs(chi_tab[0, 1] - chi[0, 1]) < 1e-2 * abs(chi[0, 1])
 
 
+def _bimax_plasma_exact_derivatives(nperp, npar, **kw):
+    """p + e bi-Maxwellian tables of tests/test_kpar_fast.in with the EXACT derivatives of f0 in df0 (the reference's
+    centred differences carry an O(dp^2) error of their own, which is not what is under test here)."""
+    specs = [tables.DistSpec(ms=1.0), tables.DistSpec(ms=5.44662e-4)]
+    pl = tables.make_plasma(specs, ns=[1.0, 1.0], qs=[1.0, -1.0], nperp=nperp, npar=npar, Bessel_zero=1.0e-30, **kw)
+    df0 = np.zeros((2, nperp - 1, npar - 1, 2), order="F")
+    for i, s in enumerate(specs):
+        f = pl.f0[i, 1:nperp, 1:npar]
+        df0[i, :, :, 0] = -2.0 * pl.pp[i, 1:nperp, 1:npar, 0] / s.ms * f
+        df0[i, :, :, 1] = -2.0 * pl.pp[i, 1:nperp, 1:npar, 1] / s.ms * f
+    pl.df0 = df0
+    return pl
+
+
+def test_table_quadrature_converges_to_the_closed_form():
+    """Independent pin of the non-relativistic table path (integrate / integrate_res / funct_g / landau_integrate,
+    src/ALPS_fns.f90:750-1452) AND of the NHDS closed form (calc_chi, src/ALPS_NHDS.f90:59-242) against each other: for a
+    bi-Maxwellian the oracle's table quadrature must converge to the closed-form susceptibility as the grid is refined
+    (120x240 -> 240x480 -> 480x960), at second order, for growing, damped (Landau contour) and real omega, resonant and
+    non-resonant harmonics.  Measured here (max over the tensor, relative to its largest entry), protons:
+      om = 0.9 + 0.05i   1.0e-4, 2.6e-5, 6.4e-6  -> Richardson 7e-7      om = 0.06 + 0.02i  7.4e-4, 1.1e-4, 1.6e-5 -> 3e-5
+      om = 0.06 - 0.02i  2.3e-3, 5.8e-4, 1.4e-4  -> Richardson 9e-6      om = 0.06 (real)   1.5e-3, 1.2e-4, 9e-5
+    (the last is limited by the finite differences of eval_fit inside landau_integrate: the reference's algorithm).
+    Electrons (momentum scale sqrt(m_e/m_p)): the absolute switch Tlim = 0.01 of the near-pole branch is far too coarse
+    for their grid, so they are checked with Tlim = 1e-7 (symmetric-pairing branch): 1.7e-2, 2.7e-3, 6.5e-4 -> 5e-5.
+    Replaces the 1 % check above as the quantitative statement."""
+    from oracle.oracle import Oracle
+    kperp, kpar = 0.3, 0.05
+    grids = (120, 240, 480)
+    oms = (0.9 + 0.05j, 0.06 + 0.02j, 0.06 - 0.02j, 0.06 + 0.0j)
+    closed = {}
+    base = _bimax_plasma_exact_derivatives(8, 16)
+    for i, s in enumerate(base.species):
+        sp = tables.Species(ns=s.ns, qs=s.qs, ms=s.ms, usebM=True, bM_betas=1.0, bM_alphas=1.0, bM_Bessel_zeros=1e-300,
+                            bM_nmaxs=40)
+        for om in oms:
+            closed[(i, om)] = nhds_calc_chi(sp, om, kperp, kpar)[0]
+    for tlim, species in ((0.01, 0), (1.0e-7, 1)):
+        tab = {}
+        for N in grids:
+            pl = _bimax_plasma_exact_derivatives(N, 2 * N, Tlim=tlim)
+            orc = Oracle(pl)
+            orc.set_k(kperp, kpar)
+            for om in oms:
+                tab[(N, om)] = orc.disp(om, full=True)[1][species] * (om * om * pl.vA * pl.vA)
+        for om in oms:
+            ref = closed[(species, om)]
+            sc = np.max(np.abs(ref))
+            err = [np.max(np.abs(tab[(N, om)] - ref)) / sc for N in grids]
+            rich = np.max(np.abs((4.0 * tab[(grids[2], om)] - tab[(grids[1], om)]) / 3.0 - ref)) / sc
+            if species == 0:
+                assert err[0] < 5e-3 and err[2] < 2.5e-4 and err[2] < err[0], (om, err)
+                if om.imag != 0.0:
+                    assert err[2] < err[1] < err[0] and rich < 6e-5, (om, err, rich)
+                if om == oms[0]:
+                    assert 3.0 < err[0] / err[1] < 5.0 and 3.0 < err[1] / err[2] < 5.0 and rich < 2e-6, (err, rich)
+            elif abs(om.real - 0.06) < 1e-12 and om.imag != 0.0:
+                assert err[2] < err[1] < err[0] < 3e-2 and err[2] < 1.5e-3 and rich < 2e-4, (om, err, rich)
+
+
 @pytest.mark.gpu
 def test_device_calc_chi_matches_the_oracle():
     """k_nhds_bessel + k_nhds (alps_b200_nhds_calc_chi) against the CPU restatement: all nine entries of chi and
