@@ -22,7 +22,7 @@ SYMBOLS = [
     "alps_b200_map_search", "alps_b200_map_grid", "alps_b200_map_finish", "alps_b200_calc_eigen", "alps_b200_scan_setup", "alps_b200_om_scan",
     "alps_b200_om_double_scan", "alps_b200_set_root_batching", "alps_b200_tps_eval",
     "alps_b200_set_partition", "alps_b200_comm_unique_id", "alps_b200_comm_init", "alps_b200_comm_finalize",
-    "alps_b200_omega_slice",
+    "alps_b200_omega_slice", "alps_b200_set_map_mode", "alps_b200_map_eval",
 ]
 
 INFO_POINT_HARMONICS, INFO_LAUNCHES, INFO_SM_COUNT, INFO_LAST_KERNEL_MS, INFO_BATCH, INFO_DFMA_NOREUSE, \
@@ -123,6 +123,8 @@ def lib():
         L.alps_b200_comm_unique_id.argtypes = [V]
         L.alps_b200_comm_init.argtypes = [C.c_int, C.c_int, V]
         L.alps_b200_omega_slice.argtypes = [C.c_int, C.c_int, C.c_int, V, V]
+        L.alps_b200_set_map_mode.argtypes = [C.c_int]
+        L.alps_b200_map_eval.argtypes = [C.c_int, V, V]
         _LIB = L
     return _LIB
 

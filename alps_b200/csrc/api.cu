@@ -386,7 +386,11 @@ int build_hoisted_tables() {
   QuadParams P = S.P;
   P.om = S.d_om_i;
   P.n_om = 1;
-  P.nsplit = 1;
+  // one "omega": spread every harmonic tile over its p_par tiles (the STORE epilogue writes by absolute column)
+  {
+    const int bn = S.qv.bn > 0 ? S.qv.bn : BN, NT = (npar - 1 + bn - 1) / bn;
+    P.nsplit = std::max(1, std::min(NT, (4 * S.sm_count) / std::max(1, (int)S.tiles.size())));
+  }
   P.tile_major = 0;
   P.plan = nullptr;
   P.Sbulk = nullptr;
@@ -711,6 +715,7 @@ struct Group {
 } G;
 thread_local bool tl_worker = false;     // this thread is a group worker
 thread_local bool tl_in_group = false;   // the caller's thread is inside group_all (its own share runs on state 0)
+int g_map_mode = 1;                      // alps_b200_set_map_mode
 
 int nccl_load() {
   NcclApi& a = G.nccl;
@@ -859,6 +864,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   if (!tl_worker && !tl_in_group) {
     alps_b200_finalize();      // whole group, workers stopped
     G.partition = ALPS_B200_PARTITION_OMEGA;
+    alps_b200_set_map_mode(1);
     if (cfg->ngpu > 1) {
       // device group: one State + host thread per device, every device initialised like a single one
       if (cfg->ngpu > MAXDEV) return fail(ALPS_B200_ERR_USAGE, "ngpu must be <= %d", MAXDEV);
@@ -2161,6 +2167,28 @@ int comm_omega_eval(int n, const double* om, double* D) {
 }  // namespace
 
 extern "C" {
+
+// map_search's batch (csrc/drivers.cpp): evaluated in the map mode -- k-hoisted tables by default, which need one
+// table build (about one direct D) per k and then O(nmax npar) instead of O(nmax nperp npar) work per omega -- and the
+// previous mode is restored for the root refinement that follows.  Same D up to rounding.
+int alps_b200_set_map_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail(ALPS_B200_ERR_USAGE, "map mode must be 0 (direct) or 1 (k-hoisted)");
+  g_map_mode = mode;
+  return 0;
+}
+int alps_b200_map_eval(int n, const double* om, double* D) {
+  int rc = check_ready();
+  if (rc) return rc;
+  const int old = S.mode;
+  // map mode 0: leave the formulation to alps_b200_set_mode; small maps are not worth a table build
+  if (g_map_mode == 0 || old == 1 || n < 64) return alps_b200_disp_batch(n, om, D, nullptr);
+  const double kperp = S.gh.kperp, kpar = S.gh.kpar;
+  if ((rc = alps_b200_set_mode(1)) || (rc = alps_b200_set_k(kperp, kpar, nullptr))) return rc;
+  rc = alps_b200_disp_batch(n, om, D, nullptr);
+  int rc2 = alps_b200_set_mode(old);
+  if (!rc2) rc2 = alps_b200_set_k(kperp, kpar, nullptr);
+  return rc ? rc : rc2;
+}
 
 int alps_b200_omega_slice(int n, int rank, int nparts, int* lo, int* hi) {
   if (n < 0 || nparts < 1 || rank < 0 || rank >= nparts || !lo || !hi) return ALPS_B200_ERR_USAGE;

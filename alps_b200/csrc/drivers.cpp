@@ -693,8 +693,10 @@ int alps_b200_map_search(const alps_b200_map* m, const char* map_path, double* o
     map_grid(m, om);
     cal.resize(om.size());
     // the nr x ni serial loop of the reference becomes one batch on the GPU
-    int rc = alps_b200_disp_batch((int)om.size(), reinterpret_cast<const double*>(om.data()),
-                                  reinterpret_cast<double*>(cal.data()), nullptr);
+    // (in the map mode of alps_b200_set_map_mode: k-hoisted tables by default; over every GPU of the device group or
+    // of the communicator under the OMEGA partition)
+    int rc = alps_b200_map_eval((int)om.size(), reinterpret_cast<const double*>(om.data()),
+                                reinterpret_cast<double*>(cal.data()));
     if (rc) throw DispError{rc};
     map_finish(m, om, cal, val, map_path, numroots, iroots, nroots_found);
     map_export(om, cal, val, om_out, val_out, cal_out);

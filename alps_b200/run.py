@@ -14,9 +14,10 @@ parameters unless --fit is given.  NHDS calc_chi for use_bM species runs on the 
 (csrc/nhds_kernel.cu).
 
 Several GPUs of one box (replaces `mpirun -np N`): `python -m torch.distributed.run --nproc-per-node N
---master-addr 127.0.0.1 -m alps_b200.run x.in --emulate-nproc 4 ...` -- one process per GPU; the nr x ni loop of map_search is sharded over
-the ranks (sharding.map_search_sharded, one NCCL all_gather of D), rank 0 alone writes the files and runs the
-sequential root refinement and k scans."""
+--master-addr 127.0.0.1 -m alps_b200.run x.in --emulate-nproc 4 ...` -- one process per GPU; the ranks join the library-owned NCCL communicator
+(alps_b200_comm_init) and map_search is collective (OMEGA partition: a slice of the nr x ni grid per rank, one ncclAllGather
+of D inside the library); rank 0 alone writes the files and runs the sequential root refinement and k scans.  Or one
+process for all GPUs: `python -m alps_b200.run x.in --ngpu N` (device group, include/alps_b200.h)."""
 from __future__ import annotations
 
 import argparse
@@ -161,10 +162,13 @@ def main(argv=None):
     ap.add_argument("--emulate-nproc", "--nproc", dest="nproc", type=int, default=0,
                     help="MPI size of the reference run to emulate (under torchrun spell it --emulate-nproc: "
                          "torchrun's own parser claims --nproc as an abbreviation of --nproc-per-node)")
-    ap.add_argument("--map-mode", choices=["direct", "hoisted"], default="direct",
-                    help="map_search only: 'hoisted' evaluates the map with the k-hoisted p_perp sums "
-                         "(alps_b200_set_mode(1): O(nmax*npar) per omega instead of O(nmax*nperp*npar), same D to rounding, "
-                         "DESIGN.md 4b); the root refinement that follows always uses the direct quadrature")
+    ap.add_argument("--map-mode", choices=["direct", "hoisted"], default="hoisted",
+                    help="map_search only: 'hoisted' (default) evaluates the map with the k-hoisted p_perp sums "
+                         "(alps_b200_set_map_mode(1): O(nmax*npar) per omega instead of O(nmax*nperp*npar), same D to "
+                         "rounding, DESIGN.md 4b); the root refinement that follows always uses the direct quadrature")
+    ap.add_argument("--ngpu", type=int, default=1,
+                    help="single process: devices the library drives itself (alps_b200_cfg.ngpu, device group); under "
+                         "torchrun every rank drives one GPU and the ranks join the library's NCCL communicator instead")
     ap.add_argument("--fit", dest="fit", action="store_true", default=None,
                     help="run the twin of determine_param_fit (LM / Chebyshev fits) like the reference always does "
                          "(src/ALPS.f90:114: determine_param_fit before the first disp).  Default whenever the f0 tables "
@@ -188,15 +192,15 @@ def main(argv=None):
     prefix = os.path.join(a.out, runname)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    shard = None
     if world > 1:
         import torch
         import torch.distributed as dist
-        from . import sharding
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        shard = (rank, world, sharding.torch_all_gather())
-    sol = Solver(pl, emulate_nproc=a.nproc, device=local_rank if world > 1 else -1)
+    sol = Solver(pl, emulate_nproc=a.nproc, device=local_rank if world > 1 else -1, ngpu=a.ngpu if world == 1 else 1)
+    if world > 1:
+        # one process per GPU (the reference's ranks): library-owned NCCL communicator, map_search is collective
+        sol.comm_init_torch()
     try:
         kperp, kpar = float(s["kperp"]), float(s["kpar"])
         nmax = sol.set_k(kperp, kpar)
@@ -207,21 +211,18 @@ def main(argv=None):
         nroots = int(s.get("nroots", 1))
         if bool(s.get("use_map", False)):
             m = nl["maps_1"]
-            if a.map_mode == "hoisted":
-                sol.set_mode(1)
-                sol.set_k(kperp, kpar)
+            sol.set_map_mode(1 if a.map_mode == "hoisted" else 0)
             om, val, cal, roots = sol.map_search(float(m["omi"]), float(m["omf"]), float(m["gami"]), float(m["gamf"]),
                                                  int(m["nr"]), int(m["ni"]), bool(m.get("loggridw", False)),
                                                  bool(m.get("loggridg", False)),
-                                                 bool(s.get("determine_minima", True)), map_path=prefix + ".map",
-                                                 shard=shard)
-            if a.map_mode == "hoisted":
-                sol.set_mode(0)
-                sol.set_k(kperp, kpar)
+                                                 bool(s.get("determine_minima", True)),
+                                                 map_path=prefix + ".map" if rank == 0 else None)
             guesses = roots[:min(nroots, len(roots))] if bool(s.get("determine_minima", True)) else []
         else:
             guesses = [complex(float(nl["guess_%d" % i]["g_om"]), float(nl["guess_%d" % i]["g_gam"]))
                        for i in range(1, nroots + 1)]
+        if world > 1:
+            sol.comm_finalize()     # nothing collective from here on
         if rank != 0:      # the root refinement and the k scans are sequential: rank 0 alone
             return 0
         w, D = sol.refine_guess(guesses, opts, roots_path=prefix + ".roots") if guesses else (np.zeros(0, complex), None)

@@ -101,6 +101,9 @@ class Solver:
         broadcast(idb)
         _lib.check(self.L.alps_b200_comm_init(rank, world, _p(idb)))
 
+    def comm_finalize(self):
+        _lib.check(self.L.alps_b200_comm_finalize())
+
     def comm_init_torch(self, group=None):
         """comm_init over an initialised torch.distributed process group (any backend)."""
         import torch
@@ -114,6 +117,10 @@ class Solver:
             dist.broadcast(t, src=0, group=group)
             buf[:] = t.cpu().numpy()
         self.comm_init(rank, world, bcast)
+
+    def set_map_mode(self, mode: int):
+        """formulation of map_search's batch: 1 = k-hoisted tables (default), 0 = the current mode (direct)"""
+        _lib.check(self.L.alps_b200_set_map_mode(mode))
 
     def set_harmonic_shard(self, rank: int, nranks: int):
         _lib.check(self.L.alps_b200_set_harmonic_shard(rank, nranks))

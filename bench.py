@@ -396,6 +396,7 @@ def run_ours(args, w, rank, world, local_rank):
     if not args.no_map:
         if world > 1:
             solf.comm_init_torch()
+        solf.set_map_mode(0)          # the formulation of each map below is chosen explicitly with set_mode
         margs = (w["omr"][0], w["omr"][1], w["omi"][0], w["omi"][1])
         strong = {"parallelism": ("alps_b200_map_search collective over %d ranks: OMEGA partition, one ncclAllGather of D "
                                   "inside alps_b200_disp_batch, every rank finishes the map" % world) if world > 1

@@ -233,6 +233,13 @@ int alps_b200_refine_guess(int nroots, double *wroots, const alps_b200_solver_op
  * writes <runname>.map (5es16.6e3).  om/cal: nr*ni complex (ir fastest), val: nr*ni, iroots(2,numroots) */
 int alps_b200_map_search(const alps_b200_map *m, const char *map_path, double *om_out, double *val_out,
                          double *cal_out, int numroots, int *iroots, int *nroots_found);
+/* Formulation map_search evaluates its nr x ni batch in: 1 (default) = k-hoisted tables (alps_b200_set_mode(1) for the
+ * duration of the batch: one table build per k, then O(nmax npar) per omega; the same D up to rounding, ~1e-12), 0 =
+ * whatever alps_b200_set_mode says (direct quadrature unless changed).  The mode in force before the map is restored
+ * after it, so the root refinement that follows runs the direct quadrature.  alps_b200_map_eval is the batch call
+ * map_search makes (n omegas in, n D out, host buffers). */
+int alps_b200_set_map_mode(int mode);
+int alps_b200_map_eval(int n, const double *om, double *D);
 /* Multi-GPU map_search (omega sharding: replaces the MPI harmonic split for maps).  Host-only
  * halves of alps_b200_map_search so that the nr x ni grid can be evaluated in slices by several processes
  * (one per GPU, alps_b200_disp_batch on each slice, slices gathered by the caller -- NCCL / torch.distributed):

@@ -62,11 +62,19 @@ def test_map_search_finds_the_root_region(tmp_path):
     try:
         sol.set_k(1.0e-2, 1.0e-2)
         path = str(tmp_path / "t.map")
+        sol.set_map_mode(0)       # the batch of map_search in the direct quadrature: bitwise disp_batch
         om, val, cal, roots = sol.map_search(5.0e-3, 1.5e-2, -1.0e-5, 1.0e-5, 50, 50, map_path=path)
         D_direct = sol.disp_batch(om.ravel(order="F")).reshape(om.shape, order="F")
+        sol.set_map_mode(1)       # default: k-hoisted tables for the batch, direct mode restored afterwards
+        om_h, val_h, cal_h, roots_h = sol.map_search(5.0e-3, 1.5e-2, -1.0e-5, 1.0e-5, 50, 50,
+                                                     map_path=str(tmp_path / "h.map"))
+        assert sol.disp_batch(om.ravel(order="F")[:70]).tolist() == D_direct.ravel(order="F")[:70].tolist()
     finally:
         sol.close()
     assert np.array_equal(cal, D_direct)
+    assert np.array_equal(om_h, om) and np.max(np.abs(cal_h - cal) / np.abs(cal)) < 1e-9 and roots_h == roots
+    la, lb = open(path).read().split("\n"), open(str(tmp_path / "h.map")).read().split("\n")
+    assert len(la) == len(lb) and sum(1 for x, y in zip(la, lb) if x != y) <= 0.02 * len(la)   # 6-digit text: last digit at most
     ir, ii = np.unravel_index(np.argmin(val), val.shape)
     assert abs(om[ir, ii].real - 9.98811e-3) < 2.1e-4
     assert any(abs(r.real - 9.98811e-3) < 2.1e-4 for r in roots)
