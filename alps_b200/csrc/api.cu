@@ -96,6 +96,11 @@ struct State {
   int* d_restick = nullptr;
   double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
   int* d_reltick = nullptr;
+  unsigned char* d_relflag = nullptr;   // throughput class of the relativistic species: resonance flags per (omega, tile),
+  int *d_relwork = nullptr, *d_relcount = nullptr, *d_relpos = nullptr;   // per-tile lists of resonant (omega, sign) entries
+  double* d_reldpart = nullptr;   // partial rows of k_rel_direct's Gamma splits
+  size_t reldpart_cap = 0;
+  bool rel_tiled_off = false;    // ALPS_B200_REL_TILED=0: one CTA per (omega, species, |n|) for every batch size (A/B)
   QuadTile* d_tiles = nullptr;
   std::vector<QuadTile> tiles;
   RelTile* d_rtiles = nullptr;
@@ -256,6 +261,8 @@ void free_batch() {
   dfree(&S.d_om); dfree(&S.d_D); dfree(&S.d_Sbulk); dfree(&S.d_Sres); dfree(&S.d_gwin); dfree(&S.d_partial);
   dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work); dfree(&S.d_ext);
   dfree(&S.d_relpart); dfree(&S.d_reltick); dfree(&S.d_respart); dfree(&S.d_restick);
+  dfree(&S.d_relflag); dfree(&S.d_relwork); dfree(&S.d_relcount); dfree(&S.d_relpos); dfree(&S.d_reldpart);
+  S.reldpart_cap = 0;
   S.batch = 0;
   S.sbulk_rows = 0;
 }
@@ -471,6 +478,9 @@ int ensure_batch(int want) {
     if (dalloc(&S.d_relpart, (size_t)SMALL_BATCH * NI * 16 * 12) || dalloc(&S.d_reltick, nt))
       return ALPS_B200_ERR_CUDA;
     CK(cudaMemsetAsync(S.d_reltick, 0, nt * sizeof(int), S.stream));
+    if (dalloc(&S.d_relflag, B * NI) || dalloc(&S.d_relwork, 2 * B * NI) || dalloc(&S.d_relcount, NI) ||
+        dalloc(&S.d_relpos, 2 * B * NI))
+      return ALPS_B200_ERR_CUDA;
   }
   S.batch = want;
   return 0;
@@ -622,9 +632,27 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       // few omegas in flight: spread each (omega, species, |n|) over several CTAs (configuration-only
       // rule, like nsplit_small, so disp() and a small disp_batch() stay bitwise identical)
       const int rsplit = (cn <= SMALL_BATCH) ? nsplit_rel() : 1;
-      launch_rel(gd, d_om, n, S.d_rtiles, (int)S.rtiles.size(), S.d_Sres, S.d_err + 6, rsplit, S.d_relpart,
-                 S.d_reltick, S.stream);
-      S.launches += 1;
+      bool tables = true;     // the omega-tiled kernels read the per-k Bessel tables of every relativistic species
+      for (int s = 0; s < S.cfg.nspec; s++) tables = tables && (!S.gh.sp[s].relativistic || S.gh.sp[s].Jrel != nullptr);
+      // Gamma splits of the direct part: enough CTAs to fill the GPU when only a few harmonics are resonant (the usual
+      // case), within 512 MB of partial rows
+      const size_t nt = S.rtiles.size();
+      int nsB = std::max(1, std::min(32, (int)((6 * 128 * (size_t)S.sm_count / 2 + n - 1) / n)));
+      while (nsB > 1 && nt * 2 * n * nsB * 96 > ((size_t)512 << 20)) nsB--;
+      const size_t need = nt * 2 * (size_t)n * nsB * 12;
+      if (cn > SMALL_BATCH && tables && !S.rel_tiled_off && need * 8 <= ((size_t)1 << 30)) {
+        if (need > S.reldpart_cap) {
+          if (dalloc(&S.d_reldpart, need)) return ALPS_B200_ERR_CUDA;
+          S.reldpart_cap = need;
+        }
+        launch_rel_tiled(gd, d_om, n, S.d_rtiles, (int)nt, S.d_Sres, S.d_err + 6, S.d_relflag, S.d_relwork, S.d_relcount,
+                         S.d_relpos, S.d_reldpart, nsB, S.sm_count, S.stream);
+        S.launches += 4;
+      } else {
+        launch_rel(gd, d_om, n, S.d_rtiles, (int)S.rtiles.size(), S.d_Sres, S.d_err + 6, rsplit, S.d_relpart,
+                   S.d_reltick, S.stream);
+        S.launches += 1;
+      }
     }
     double* part = d_partial_out ? d_partial_out : S.d_partial;
     if (!d_partial_out && cn <= SMALL_BATCH && !S.fuse_off && !comm_harmonic()) {
@@ -981,6 +1009,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
     S.fuse_off = !knob("ALPS_B200_FUSE", LAT_DEFAULT_FUSE);
     S.zc_off = !knob("ALPS_B200_ZC", LAT_DEFAULT_ZC);
     S.omega_major = getenv("ALPS_B200_OMEGA_MAJOR") != nullptr;   // A/B knob: previous block order of k_quad_mma
+    S.rel_tiled_off = !knob("ALPS_B200_REL_TILED", true);
     const char* v = getenv("ALPS_B200_QUAD_VARIANT");   // tuning knob: tile shape of k_quad
     S.qv = quad_variant(v ? atoi(v) : 15);
     const char* fv = getenv("ALPS_B200_FAST_VARIANT");

@@ -140,6 +140,12 @@ void launch_fast(const GlobalDev* g, const double* om, int n_om, const FastItem*
 void launch_fast_tables(const double* G, const double* ppar, int npar, int nrows, double* T, cudaStream_t st);
 void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
                 int* err_flag, int nsplit, double* Mpart, int* tickets, cudaStream_t st);
+// throughput class of the relativistic species (rel_kernel.cu): rflag n_om*ntiles bytes; rwork 2*n_om*ntiles ints (one
+// segment per tile); rcount ntiles ints; rpos 2*n_om*ntiles ints; dpart 2*n_om*ntiles*nsplitB*12 doubles would be the
+// worst case -- api.cu sizes it for REL_DPART_ENTRIES resonant entries per omega and falls back to launch_rel beyond
+void launch_rel_tiled(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
+                      int* err_flag, unsigned char* rflag, int* rwork, int* rcount, int* rpos, double* dpart, int nsplitB,
+                      int sm_count, cudaStream_t st);
 void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, int npb, double zfac, int nmaxord,
                              double* Jrel, cudaStream_t st);
 void launch_int_ee_rel(const double* pbv, const double* dfp, const int* lo, const int* up, int ng, int npb, double qs,

@@ -234,21 +234,55 @@ __device__ REL_NOINLINE void funct_g_rel6(const RelCtx& c, int sg, double p, int
 // around the resonance are evaluated once per (row, sign) into shared memory (win[node - W0][6]); every
 // quadrature point then only selects its node (the same search and cone rules as funct_g_rel6) and
 // interpolates.  Falls back to funct_g_rel6 if a node outside the window is asked for.
-constexpr int REL_WIN = 32;
-__device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, int ig, const cd (*win)[6], int W0,
+constexpr int REL_WIN = 24;      // 2 M_I + 7 window nodes: positions_principal up to 8 (larger: no window cache)
+// per-warp cache of one principal-value window (shared memory): node values, central differences, the node
+// coordinates (one more than the window: the search tests pb(q + 1)) and the outside-the-cone flags
+struct RelWin {
+  cd val[REL_WIN][6];
+  cd dif[REL_WIN][6];          // val[k + 1] - val[k - 1], k = 1 .. nwin - 2
+  double pb[REL_WIN + 1];
+  unsigned char out[REL_WIN + 1];
+  int anyout;                  // any out[] flag set
+};
+__device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, int ig, const RelWin& w, int W0,
                                             int nwin, double inv_dpb, Six2& out) {
   const SpeciesDev& sp = *c.sp;
-  const int ic = funct_g_node(sp, c.g->npparbar, ig, p, inv_dpb);
+  const int npb = c.g->npparbar;
+  // node selection of funct_g_rel (funct_g_node) on the cached coordinates / cone flags when everything it touches lies
+  // in the window -- the normal case; same comparisons on the same values, so the same node.  The cell [pb(q), pb(q+1))
+  // that holds p is unique, so instead of funct_g_node's scan from i0 + 2 downwards the index guess i0 is corrected by
+  // at most one step and then checked with the reference's two comparisons.
+  int ic = -2;
+  bool cached = false;
+  {
+    const int i0 = (int)floor((p - sp.pbrel[0]) * inv_dpb);
+    const int k0 = i0 - W0;
+    if (k0 >= 2 && k0 + 3 <= nwin && i0 >= 4 && i0 + 4 <= npb) {
+      int q = k0;
+      if (w.pb[q] > p) q--;
+      else if (w.pb[q + 1] <= p) q++;
+      if (w.pb[q + 1] > p && w.pb[q] <= p) {
+        ic = q + W0;
+        cached = !w.anyout;   // a node of the window outside the sub-luminal cone (rare: the window lies inside it):
+                              // funct_g_node applies the cone rules
+        // (p == pb(npb) and the clamps ic >= npb - 1, ic <= 1 cannot trigger: 3 <= i0 - 1 <= ic <= i0 + 1 <= npb - 3)
+      }
+    }
+  }
+  if (!cached) ic = funct_g_node(sp, npb, ig, p, inv_dpb);
   const int k = ic - W0;
   if (k < 1 || k + 1 >= nwin) {
-    funct_g_rel6(c, sg, p, ig, ic, inv_dpb, out);
+    Six2 tmp;     // (a temporary: the caller's accumulators must not escape to an out-of-line call)
+    funct_g_rel6(c, sg, p, ig, ic, inv_dpb, tmp);
+#pragma unroll
+    for (int q = 0; q < 6; q++) out.v[q] = tmp.v[q];
     return;
   }
-  const double sx = (0.5 * inv_dpb) * (p - sp.pbrel[ic]);   // central-difference slope factor times the offset
+  const double sx = (0.5 * inv_dpb) * (p - w.pb[k]);   // central-difference slope factor times the offset
 #pragma unroll
   for (int q = 0; q < 6; q++) {
-    const cd a = win[k][q], lo = win[k - 1][q], hi = win[k + 1][q];
-    out.v[q] = mk(fma(sx, hi.x - lo.x, a.x), fma(sx, hi.y - lo.y, a.y));
+    const cd a = w.val[k][q], d = w.dif[k][q];
+    out.v[q] = mk(fma(sx, d.x, a.x), fma(sx, d.y, a.y));
   }
 }
 
@@ -267,17 +301,25 @@ constexpr int REL_THREADS = 256;
 // of one (omega, species, |n|) are dealt round-robin to nsplit CTAs; each leaves a partial row in Mpart and
 // the last one to finish (ticket counter) adds them up in a fixed order.
 // MINB = 2 (throughput batches): 128 registers, two CTAs per SM; MINB = 1 (latency batches): 255 registers
-template <int MINB>
+// MODE 1 (throughput class): only the principal-value and Landau parts, for the resonant (omega, tile, sign) entries of
+// the work list of k_rel_plan (persistent CTAs stride over it); the non-resonant quadrature and the direct part of the
+// resonant rows are k_rel_tiled's.
+template <int MINB, int MODE>
 __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
                                                      int n_om, const RelTile* __restrict__ tiles, int ntiles,
                                                      double* __restrict__ Mrel, int* __restrict__ err_flag, int nsplit,
-                                                     double* __restrict__ Mpart, int* __restrict__ tickets) {
+                                                     double* __restrict__ Mpart, int* __restrict__ tickets,
+                                                     const int* __restrict__ rwork, const int* __restrict__ rcount) {
   const GlobalDev& g = *gp;
   pdl_trigger();
   pdl_wait();
-  const int js = blockIdx.x % nsplit;
-  const int iom = (blockIdx.x / nsplit) / ntiles;
-  const int tile_id = (blockIdx.x / nsplit) % ntiles;
+  // MODE 1: rwork holds one segment of 2 n_om slots per tile (entries (iom << 1) | sign), rcount[tile] its fill
+  for (int etile = 0; etile < (MODE == 1 ? ntiles : 1); etile++)
+  for (int entry = MODE == 1 ? blockIdx.x : 0; entry < (MODE == 1 ? rcount[etile] : 1); entry += MODE == 1 ? gridDim.x : 1) {
+  const int ecode = MODE == 1 ? rwork[(size_t)etile * 2 * n_om + entry] : 0;
+  const int js = MODE == 1 ? 0 : blockIdx.x % nsplit;
+  const int iom = MODE == 1 ? (ecode >> 1) : (blockIdx.x / nsplit) / ntiles;
+  const int tile_id = MODE == 1 ? etile : (blockIdx.x / nsplit) % ntiles;
   const RelTile tl = tiles[tile_id];
   const SpeciesDev& sp = g.sp[tl.s];
   const int nabs = tl.nabs;
@@ -287,7 +329,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
   const double qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar, kperp = g.kperp;
   __shared__ int s_found[2];
   __shared__ cd s_red[REL_THREADS / 32][6];
-  __shared__ cd s_win[REL_THREADS / 32][REL_WIN][6];   // node values of the principal-value window, per warp
+  __shared__ RelWin s_win[REL_THREADS / 32];           // principal-value window of the row a warp works on
   __shared__ double s_rfact[21], s_rgam[23];           // 1/k!, 1/Gamma(|n| + i): series of the Landau term
   if (tid < 21) {
     double fact = 1.0;
@@ -297,11 +339,11 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
     const int m = nabs + (tid - 32);                          // Gamma(m), m = |n| .. |n| + 22
     s_rgam[tid - 32] = m >= 1 ? 1.0 / gamma_ref(1.0 * m) : 0.0;
   }
-  if (tid < 2) s_found[tid] = 0;
+  if (tid < 2) s_found[tid] = MODE == 1 ? 1 : 0;
   __syncthreads();
 
   // ---- determine_resonances, relativistic branch: any (iperp, ipar) cell containing Re p_res
-  {
+  if (MODE == 0) {
     int fp = 0, fm = 0;
     for (int idx = tid; idx < (nperp + 1) * npar; idx += REL_THREADS) {
       const int iperp = idx / npar, ipar = idx - iperp * npar;
@@ -330,6 +372,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
 
   for (int sg = 0; sg < 2; sg++) {
     if (nabs == 0 && sg == 1) break;
+    if (MODE == 1 && sg != (ecode & 1)) continue;
     const double nn = sg ? -(double)nabs : (double)nabs;
     Six2 acc;
     zero6(acc);
@@ -423,7 +466,9 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           upperlimit = npb;
         }
         // direct part
-        if (sp.Jrel) {
+        if (MODE == 1) {
+          // k_rel_tiled
+        } else if (sp.Jrel) {
           // hot loop: the six T components are real multiples of six Bessel moments (like the table species'
           // p_par moments), so the loop accumulates sum U {J^2, J^2 p, J^2 p^2, J J' pp, J J' pp p, J'^2 pp^2}
           // with one reciprocal per node; Bessel factors and pperpbar come from the per-k tables
@@ -504,15 +549,32 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           zero6(pr);
           // node values of the window [ires - M_I - 2, ires + M_I + 4]: one node per lane
           const int W0 = ires - M_I - 2, nwin = (2 * M_I + 7 <= REL_WIN) ? 2 * M_I + 7 : 0;
-          const cd(*win)[6] = s_win[warp];
+          RelWin& win = s_win[warp];
           const double inv_dpb = 1.0 / dpb;
           __syncwarp();
-          if (lane < nwin && W0 + lane >= 0 && W0 + lane <= npb) {
-            double M[6];
-            cd num;
-            node_moments(c, ig, W0 + lane, sg, M, num);
+          if (lane <= nwin && nwin > 0) {
+            const int idx = W0 + lane;
+            const bool in = idx >= 0 && idx <= npb;
+            // coordinates outside the table never match a comparison (NaN): the cached search then misses and the
+            // global one decides
+            win.pb[lane] = in ? pbv[idx] : __longlong_as_double(0x7ff8000000000000LL);
+            win.out[lane] = (in && sp.f0_rel[(size_t)ig * ldr + idx] <= -1.0) ? 1 : 0;
+            const unsigned any = __ballot_sync(__activemask(), win.out[lane] != 0);
+            if (lane == 0) win.anyout = any != 0;
+            if (lane < nwin) {
+              double M[6];
+              cd num = mk(0.0, 0.0);
 #pragma unroll
-            for (int q = 0; q < 6; q++) s_win[warp][lane][q] = M[q] * num;
+              for (int q = 0; q < 6; q++) M[q] = 0.0;
+              if (in) node_moments(c, ig, idx, sg, M, num);
+#pragma unroll
+              for (int q = 0; q < 6; q++) win.val[lane][q] = M[q] * num;
+            }
+          }
+          __syncwarp();
+          if (lane >= 1 && lane + 1 < nwin) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) win.dif[lane][q] = win.val[lane + 1][q] - win.val[lane - 1][q];
           }
           __syncwarp();
           if (fabs(denomI) > g.Tlim) {
@@ -524,9 +586,15 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
               funct_g_win(c, sg, 2.0 * denomR - p, ig, win, W0, nwin, inv_dpb, f2);
               // wj / d1 and wj / d2 with d2 = conj(d1): one reciprocal for the twelve quotients
               const double dx = p - denomR, tt = wj * fast_rcp(fma(dx, dx, denomI * denomI));
-              const cd r1 = mk(dx * tt, denomI * tt), r2 = mk(dx * tt, -(denomI * tt));
+              // f1 r1 - f2 conj(r1), r1 = (x, y)
+              const double rx = dx * tt, ry = denomI * tt;
 #pragma unroll
-              for (int q = 0; q < 6; q++) pr.v[q] += f1.v[q] * r1 - f2.v[q] * r2;
+              for (int q = 0; q < 6; q++) {
+                const double sr = f1.v[q].x - f2.v[q].x, si = f1.v[q].y + f2.v[q].y;
+                const double tr = f1.v[q].x + f2.v[q].x, ti = f1.v[q].y - f2.v[q].y;
+                pr.v[q].x += fma(sr, rx, -(si * ry));
+                pr.v[q].y += fma(tr, ry, ti * rx);
+              }
             }
           } else {
             Six2 fp_, fm_;
@@ -636,7 +704,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
     }
     __syncthreads();
   }
-  if (nsplit > 1) {
+  if (MODE == 0 && nsplit > 1) {
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
@@ -655,6 +723,399 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
       }
       if (tid == 0) tickets[iom * ntiles + tile_id] = 0;   // ready for the next launch
     }
+  }
+  if (MODE == 1) __syncthreads();   // the shared tables of this entry are rebuilt by the next one
+  }
+}
+
+// =====================================================================================================================
+// Throughput class (batches of more than 64 omegas): k_rel_plan -> k_rel<.,1> -> k_rel_tiled.
+//
+// k_rel above gives one CTA to every (omega, species, |n|) and streams the (Gamma, pbar_par) tables -- 56 B per node for
+// ~45 FP64 operations -- from L2 again for every omega: L2-bound at a fifth of the FP64 pipe (profiles/r01_k_rel_ncu_full.csv).
+// Here the bulk of the work -- the regular quadrature of the non-resonant harmonics on the (p_perp, p_par) grid and the
+// direct part of integrate_resU_rel on the (Gamma, pbar_par) grid -- is tiled over OMEGA instead: one CTA = 128 omegas
+// (one per thread) x one (species, |n|).  The omega-independent half of every grid node -- numerator coefficients,
+// denominator coefficients and the six real Bessel moments of which the T components are constant multiples; identical
+// for +n and -n because J_-n = (-1)^n J_n enters them squared or as J J' -- is computed ONCE per node by one thread into a
+// shared-memory packet, and every thread then applies its own omega to the packet (warp-uniform LDS broadcasts): per
+// (node, omega, sign) one reciprocal and 12 FMAs.  The principal-value window and the Landau term of the resonant
+// harmonics keep their warp-per-Gamma-row form (k_rel, MODE 1) but run only for the resonant (omega, species, n, sign)
+// entries that k_rel_plan lists.
+// ---------------------------------------------------------------------------------------------------------------------
+
+// determine_resonances, relativistic branch (src/ALPS_fns.f90:683-701): one warp per (omega, tile); flags + work list
+__global__ void __launch_bounds__(256) k_rel_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om,
+                                                  const RelTile* __restrict__ tiles, int ntiles,
+                                                  unsigned char* __restrict__ rflag, int* __restrict__ rwork,
+                                                  int* __restrict__ rcount, int* __restrict__ rpos) {
+  const GlobalDev& g = *gp;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_om * ntiles) return;
+  const int iom = w / ntiles, tile_id = w % ntiles;
+  const RelTile tl = tiles[tile_id];
+  const SpeciesDev& sp = g.sp[tl.s];
+  const int nabs = tl.nabs, nperp = g.nperp, npar = g.npar;
+  const double omr = om[2 * iom], qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar;
+  int fp = 0, fm = 0;
+  for (int idx = lane; idx < (nperp + 1) * npar; idx += 32) {
+    const int iperp = idx / npar, ipar = idx - iperp * npar;
+    const double pp1 = sp.pperp[iperp], pp2 = sp.ppar[ipar];
+    const double gamma = sqrt((pp1 * pp1 + pp2 * pp2) * (vA * vA) / (ms * ms) + 1.0);
+    const double prp = (gamma * ms * omr - 1.0 * nabs * qs) / kpar;
+    const double prm = (gamma * ms * omr + 1.0 * nabs * qs) / kpar;
+    if (sp.ppar[ipar] <= prp && sp.ppar[ipar + 1] > prp) fp = 1;
+    if (sp.ppar[ipar] <= prm && sp.ppar[ipar + 1] > prm) fm = 1;
+  }
+  fp = __any_sync(0xffffffffu, fp);
+  fm = nabs > 0 ? __any_sync(0xffffffffu, fm) : 0;
+  if (lane == 0) {
+    rflag[w] = (unsigned char)(fp | (fm << 1));
+    // the resonant (omega, sign) entries of a tile: one segment of 2 n_om slots per tile, filled in any order (every
+    // entry is evaluated on its own), and where each entry sits (k_rel_tiled collects its partial rows from there)
+    int* seg = rwork + (size_t)tile_id * 2 * n_om;
+    int pp = -1, pm = -1;
+    if (fp) seg[pp = atomicAdd(rcount + tile_id, 1)] = (iom << 1);
+    if (fm) seg[pm = atomicAdd(rcount + tile_id, 1)] = (iom << 1) | 1;
+    rpos[2 * (size_t)w] = pp;
+    rpos[2 * (size_t)w + 1] = pm;
+  }
+}
+
+// limits of integrate_resU_rel for one Gamma row (src/ALPS_fns_rel.f90:591-672); returns 0 on alps_error(8)
+struct RelRow {
+  int int_start, int_end, lowerlimit, upperlimit;
+};
+__device__ __forceinline__ int rel_row_limits(const SpeciesDev& sp, int npb, int M_I, double presx, double g1, int lo_c,
+                                              int up_c, RelRow& r) {
+  const double* __restrict__ pbv = sp.pbrel;
+  const double dpb = sp.dpparbar;
+  int ires = 0, found = 0;
+  if (presx * presx <= g1 * g1 - 1.0) {
+    if (presx >= pbv[1] && presx < pbv[npb - 1]) {
+      // the cell [pbv(lo), pbv(lo+1)) that holds Re p_res, lo in [1, npb-2]: index guess on the uniform grid, then the
+      // reference's comparisons on the actual node values
+      int lo = (int)floor((presx - pbv[0]) / dpb);
+      lo = min(max(lo, 1), npb - 2);
+      while (lo > 1 && pbv[lo] > presx) lo--;
+      while (lo < npb - 2 && pbv[lo + 1] <= presx) lo++;
+      if (pbv[lo + 1] > presx && pbv[lo] <= presx) {
+        ires = lo;
+        found = 1;
+      }
+    }
+  }
+  for (int ip = 0; ip <= M_I; ip++) {
+    if (presx >= pbv[0] - dpb * ip && presx < pbv[0] - dpb * (ip - 1)) {
+      ires = -ip;
+      found = 1;
+    }
+    if (presx >= pbv[npb - 1] + dpb * ip && presx < pbv[npb - 1] + dpb * (ip + 1)) {
+      ires = npb - 1 + ip;
+      found = 1;
+    }
+  }
+  if (found) {
+    r.int_start = lo_c;
+    r.int_end = up_c;
+    r.lowerlimit = ires - M_I;
+    r.upperlimit = ires + M_I + 1;
+    if (ires >= 0 && ires <= npb)
+      if (fabs(presx - pbv[ires]) > 0.5 * dpb) r.upperlimit = r.upperlimit + 1;
+    if (r.lowerlimit < lo_c && r.upperlimit > up_c) return 0;
+    if (r.lowerlimit <= lo_c) {
+      r.int_start = 1;
+      r.lowerlimit = 0;
+      r.upperlimit = lo_c;
+    } else if (r.upperlimit >= up_c) {
+      r.lowerlimit = up_c;
+      r.upperlimit = npb;
+      r.int_end = npb - 1;
+    }
+  } else {
+    r.int_start = lo_c;
+    r.lowerlimit = up_c;
+    r.int_end = npb - 1;
+    r.upperlimit = npb;
+  }
+  return 1;
+}
+
+constexpr int RT_THREADS = 128, RT_CH = 128;
+constexpr int RT_WA = 12;   // packet of a (p_perp, p_par) node: w, a, c, dgm, e, pad, q0..q5
+constexpr int RT_WB = 10;   // packet of a (Gamma, pbar_par) node: pb, dfg, kv dfp, pad, M0..M5
+
+__global__ void __launch_bounds__(RT_THREADS, 3)
+    k_rel_tiled(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om,
+                const RelTile* __restrict__ tiles, int ntiles, const unsigned char* __restrict__ rflag,
+                double* __restrict__ Mrel, const int* __restrict__ rpos, const double* __restrict__ dpart,
+                int nsplitB) {
+  __shared__ __align__(16) double s_pk[2][RT_CH * RT_WA];
+  const GlobalDev& g = *gp;
+  const RelTile tl = tiles[blockIdx.y];
+  const SpeciesDev& sp = g.sp[tl.s];
+  const int nabs = tl.nabs, tid = threadIdx.x;
+  const int iom = blockIdx.x * RT_THREADS + tid;
+  const bool live = iom < n_om;
+  const double omr = live ? om[2 * iom] : 1.0, omi = live ? om[2 * iom + 1] : 1.0;
+  const int flags = live ? rflag[(size_t)iom * ntiles + blockIdx.y] : 0;
+  const int nperp = g.nperp, npar = g.npar, ng = g.ngamma, npb = g.npparbar, M_I = g.M_I;
+  const double qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar, kperp = g.kperp;
+  const double nq = (double)nabs * qs;
+  // moment sums per sign: {q0 .. q5} (re, im)
+  double SP[12], SM[12];
+#pragma unroll
+  for (int q = 0; q < 12; q++) SP[q] = SM[q] = 0.0;
+  const bool resP = (flags & 1) != 0, resM = (flags & 2) != 0;
+  const bool nonP = live && !resP, nonM = live && nabs > 0 && !resM;
+
+  // ---------------------------------------------------------------- (p_perp, p_par) grid: integrate() with gamma in resU
+  if (__syncthreads_or(nonP || nonM)) {
+    const double zb = g.kperp_norm ? kperp / qs : 1.0 / qs;
+    (void)zb;
+    const double* __restrict__ Jn = sp.J + (size_t)(nabs + 1) * sp.ldj;
+    const double* __restrict__ Jm = sp.J + (size_t)nabs * sp.ldj;
+    const double* __restrict__ Jp = sp.J + (size_t)(nabs + 2) * sp.ldj;
+    const int nnode = (nperp - 1) * (npar - 1);
+    const int nch = (nnode + RT_CH - 1) / RT_CH;
+    auto stage = [&](int c, double* pk) {
+      const int idx = c * RT_CH + tid;
+      double* o = pk + tid * RT_WA;
+      if (idx < nnode) {
+        const int iperp = idx / (npar - 1) + 1, ipar = idx % (npar - 1) + 1;
+        const double wperp = (iperp == nperp - 1) ? 1.0 : 2.0;
+        const double wpar = (ipar == 1 || ipar == npar - 1) ? 1.0 : 2.0;
+        const double pp1 = sp.pperp[iperp], pp2 = sp.ppar[ipar];
+        const double gamma = sqrt((pp1 * pp1 + pp2 * pp2) * (vA * vA) / (ms * ms) + 1.0);
+        const size_t oo = (size_t)(iperp - 1) * sp.ldp + (ipar - 1);
+        double bj, bp;
+        bessel_pair(nabs, 0, 0.0, nabs >= 1 ? Jm[iperp] : 0.0, Jn[iperp], Jp[iperp], bj, bp);
+        o[0] = wperp * wpar;
+        o[1] = sp.A[oo];
+        o[2] = (kpar / gamma) * sp.C0[oo];
+        o[3] = gamma * ms;
+        o[4] = kpar * pp2;
+        o[5] = 0.0;
+        o[6] = bj * bj;                       // xx: n^2 J^2 / z^2
+        o[7] = bp * bp * pp1 * pp1;           // yy
+        o[8] = bj * bj * (pp2 * pp2);         // zz
+        o[9] = bj * bp * pp1;                 // xy (times i n / z)
+        o[10] = bj * bj * pp2;                // xz (times n / z)
+        o[11] = bj * bp * pp2 * pp1;          // yz (times -i)
+      } else {
+#pragma unroll
+        for (int q = 0; q < RT_WA; q++) o[q] = 0.0;
+        o[3] = 1.0;   // den = om: finite for the padding nodes (weight 0)
+      }
+    };
+    stage(0, s_pk[0]);
+    __syncthreads();
+    for (int c = 0; c < nch; c++) {
+      if (c + 1 < nch) stage(c + 1, s_pk[(c + 1) & 1]);
+      const double* __restrict__ pk = s_pk[c & 1];
+      if (nonP || nonM) {
+#pragma unroll 2
+        for (int j = 0; j < RT_CH; j++) {
+          const double2* t2 = reinterpret_cast<const double2*>(pk + j * RT_WA);
+          const double2 h0 = t2[0], h1 = t2[1], h2 = t2[2];      // (w, a) (c, dgm) (e, -)
+          const double nr = fma(omr, h0.y, h1.x), ni = omi * h0.y;
+          const double x = fma(h1.y, omr, -h2.x), di = h1.y * omi, di2 = di * di;
+          const double drp = x - nq, drm = x + nq;
+          // both reciprocals from one (a non-resonant denominator is never 0; padding nodes have den = om)
+          // a resonant sign (k_rel's and the (Gamma, pbar_par) part's business) may have den = 0 on this grid: it must not
+          // poison the shared reciprocal
+          const double dp = nonP ? fma(drp, drp, di2) : 1.0, dm = nonM ? fma(drm, drm, di2) : 1.0;
+          const double inv = h0.x * fast_rcp(dp * dm);
+          const double tp = nonP ? dm * inv : 0.0, tm = nonM ? dp * inv : 0.0;
+          const double nrdi = nr * di, nidi = ni * di;
+          const double upr = fma(nr, drp, nidi) * tp, upi = fma(ni, drp, -nrdi) * tp;
+          const double umr = fma(nr, drm, nidi) * tm, umi = fma(ni, drm, -nrdi) * tm;
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            const double2 m = t2[3 + q];
+            SP[4 * q] = fma(upr, m.x, SP[4 * q]);         SP[4 * q + 1] = fma(upi, m.x, SP[4 * q + 1]);
+            SP[4 * q + 2] = fma(upr, m.y, SP[4 * q + 2]); SP[4 * q + 3] = fma(upi, m.y, SP[4 * q + 3]);
+            SM[4 * q] = fma(umr, m.x, SM[4 * q]);         SM[4 * q + 1] = fma(umi, m.x, SM[4 * q + 1]);
+            SM[4 * q + 2] = fma(umr, m.y, SM[4 * q + 2]); SM[4 * q + 3] = fma(umi, m.y, SM[4 * q + 3]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // non-resonant signs: moment sums -> tensor components (modes_real), trapezoid factor
+  cd TP[6], TM[6];
+  {
+    const double zb = g.kperp_norm ? kperp / qs : 1.0 / qs;
+    const double kf1 = g.kperp_norm ? 1.0 : kperp, kf2 = g.kperp_norm ? 1.0 : kperp * kperp;
+    const double fac = 2.0 * PI_ * sp.dpperp * sp.dppar_abs * 0.25;
+#pragma unroll
+    for (int sgn = 0; sgn < 2; sgn++) {
+      const double* S = sgn ? SM : SP;
+      cd* T = sgn ? TM : TP;
+      const double nn = sgn ? -(double)nabs : (double)nabs;
+      const double c0 = 1.0 * (nn * nn) / (zb * zb), c3 = kf1 * (1.0 * nn) / zb;
+      T[0] = fac * mk(c0 * S[0], c0 * S[1]);
+      T[1] = fac * mk(kf2 * S[2], kf2 * S[3]);
+      T[2] = fac * mk(kf2 * S[4], kf2 * S[5]);
+      T[3] = fac * cmul_i(mk(c3 * S[6], c3 * S[7]));
+      T[4] = fac * mk(c3 * S[8], c3 * S[9]);
+      T[5] = fac * (-cmul_i(mk(kf2 * S[10], kf2 * S[11])));
+    }
+  }
+
+  if (!live) return;
+  // non-resonant signs: done.  Resonant signs: k_rel<., 1> has left the principal-value and Landau parts in Mrel; add the
+  // direct part, i.e. the partial rows of the Gamma splits of k_rel_direct in their fixed order
+#pragma unroll
+  for (int sgn = 0; sgn < 2; sgn++) {
+    if (sgn == 1 && nabs == 0) break;
+    const bool res = sgn ? resM : resP;
+    double* o = Mrel + ((size_t)iom * g.NI + sp.item_base + 2 * nabs + sgn) * 12;
+    if (!res) {
+      const cd* T = sgn ? TM : TP;
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        o[2 * q] = T[q].x;
+        o[2 * q + 1] = T[q].y;
+      }
+    } else {
+      const int pos = rpos[2 * ((size_t)iom * ntiles + blockIdx.y) + sgn];
+      const double* pr = dpart + (((size_t)blockIdx.y * 2 * n_om + pos) * nsplitB) * 12;
+      double t[12];
+#pragma unroll
+      for (int q = 0; q < 12; q++) t[q] = 0.0;
+      for (int js = 0; js < nsplitB; js++)
+#pragma unroll
+        for (int q = 0; q < 12; q++) t[q] += pr[(size_t)js * 12 + q];
+#pragma unroll
+      for (int q = 0; q < 12; q++) o[q] += t[q];
+    }
+  }
+}
+
+
+// Direct part of integrate_resU_rel for the resonant entries of one tile: one CTA = 128 entries (one per thread: its
+// omega and sign) x the Gamma rows js, js + nsplitB, ... ; the row's node packets are staged once per CTA.  Leaves the
+// tensor-component partial row of (entry, js) in dpart; k_rel_tiled adds the rows of an entry in order.
+__global__ void __launch_bounds__(RT_THREADS, 3)
+    k_rel_direct(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om,
+                 const RelTile* __restrict__ tiles, int ntiles, const int* __restrict__ rwork,
+                 const int* __restrict__ rcount, double* __restrict__ dpart, int nsplitB, int* __restrict__ err_flag) {
+  const int tile_id = blockIdx.y, js = blockIdx.z;
+  const int cnt_e = rcount[tile_id];
+  if (blockIdx.x * RT_THREADS >= cnt_e) return;
+  __shared__ __align__(16) double s_pk[RT_CH * RT_WB];
+  const GlobalDev& g = *gp;
+  const RelTile tl = tiles[tile_id];
+  const SpeciesDev& sp = g.sp[tl.s];
+  const int nabs = tl.nabs, tid = threadIdx.x;
+  const int e = blockIdx.x * RT_THREADS + tid;
+  const bool live = e < cnt_e;
+  const int ecode = live ? rwork[(size_t)tile_id * 2 * n_om + e] : 0;
+  const int iom = ecode >> 1, sg = ecode & 1;
+  const double omr = om[2 * iom], omi = om[2 * iom + 1];
+  const int ng = g.ngamma, npb = g.npparbar, M_I = g.M_I;
+  const double qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar, kperp = g.kperp;
+  double S[12];
+#pragma unroll
+  for (int q = 0; q < 12; q++) S[q] = 0.0;
+  const double pref = -2.0 * PI_ * ((ms / vA) * (ms / vA) * (ms / vA)) * (qs * vA / (kpar * ms));
+  const double dpb = sp.dpparbar, kv = kpar / vA;
+  const double* __restrict__ pbv = sp.pbrel;
+  const int ldr = npb + 1;
+  const size_t plane = (size_t)(ng + 1) * ldr;
+  const double nn = sg ? -(double)nabs : (double)nabs;
+  const double nqv = nn * qs * vA / (kpar * ms);
+  for (int ig = 1 + js; ig <= ng - 1; ig += nsplitB) {
+    const double wg = (ig == ng - 1) ? 1.0 : 2.0, g1 = sp.grel[ig], cw = wg * dpb;
+    const int lo_c = sp.cone_lo[ig], up_c = sp.cone_up[ig];
+    const double gomx = (g1 * omr) * vA / kpar, gomy = (g1 * omi) * vA / kpar;
+    RelRow r;
+    r.int_start = 1; r.lowerlimit = 0; r.upperlimit = npb; r.int_end = npb - 1;
+    bool ok = live;
+    if (live && !rel_row_limits(sp, npb, M_I, gomx - nqv, g1, lo_c, up_c, r)) {
+      err_flag[0] = 8;   // alps_error(8)
+      ok = false;
+    }
+    // every weighted node of the row lies in the cone [lo_c, up_c], whatever the omega: the pieces
+    // [int_start, lowerlimit] and [upperlimit, int_end] are cut out of it (or empty)
+    const int ra = max(1, lo_c), rb = min(npb - 1, up_c);
+    const double* __restrict__ J0 = sp.Jrel + (size_t)nabs * plane + (size_t)ig * ldr;
+    const double* __restrict__ JP = J0 + plane;
+    const double* __restrict__ JM = nabs >= 1 ? J0 - plane : J0;
+    const double* __restrict__ PPq = sp.Jrel + (size_t)(sp.nhi + 2) * plane + (size_t)ig * ldr;
+    const double* __restrict__ DG = sp.dfg_rel + (size_t)ig * ldr;
+    const double* __restrict__ DP = sp.dfp_rel + (size_t)ig * ldr;
+    for (int base = ra; base <= rb; base += RT_CH) {
+      __syncthreads();      // the previous chunk has been consumed
+      {
+        const int ip = base + tid;
+        double* o = s_pk + tid * RT_WB;
+        if (ip <= rb) {
+          const double j0 = J0[ip], jp = JP[ip], jm = nabs >= 1 ? JM[ip] : 0.0;
+          double bj, bp;
+          bessel_pair(nabs, 0, 0.0, jm, j0, jp, bj, bp);     // the moments are the same for +n and -n
+          const double pb = pbv[ip], pq = PPq[ip];
+          const double b2 = bj * bj, bb = bj * bp * pq, q2 = (bp * pq) * (bp * pq);
+          o[0] = pb;
+          o[1] = DG[ip];
+          o[2] = kv * DP[ip];
+          o[3] = 0.0;
+          o[4] = b2;
+          o[5] = b2 * pb;
+          o[6] = (b2 * pb) * pb;
+          o[7] = bb;
+          o[8] = bb * pb;
+          o[9] = q2;
+        }
+      }
+      __syncthreads();
+      if (!ok) continue;
+      // this thread's weighted nodes of the chunk: [int_start, lowerlimit] and [upperlimit, int_end]
+      const int c1 = min(RT_CH, rb - base + 1);
+#pragma unroll
+      for (int piece = 0; piece < 2; piece++) {
+        const int pa = piece ? r.upperlimit : r.int_start, pb_ = piece ? r.int_end : r.lowerlimit;
+        if (pa > pb_) continue;
+        const int j0 = max(pa - base, 0), j1 = min(pb_ - base, c1 - 1);
+        for (int j = j0; j <= j1; j++) {
+          const int ip = base + j;
+          const double w = (pa == pb_) ? 1.0 : ((ip == pa || ip == pb_) ? 1.0 : 2.0);     // piece_w
+          const double2* t2 = reinterpret_cast<const double2*>(s_pk + j * RT_WB);
+          const double2 h0 = t2[0], h1 = t2[1];      // (pb, dfg) (kv dfp, -)
+          const double nr = pref * fma(omr, h0.y, h1.x), ni = pref * (omi * h0.y);
+          const double di = -gomy, dr = h0.x - gomx + nqv;
+          const double t = (cw * w) * fast_rcp(fma(dr, dr, di * di));
+          const double ur = fma(nr, dr, ni * di) * t, ui = fma(ni, dr, -(nr * di)) * t;
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            const double2 m = t2[2 + q];
+            S[4 * q] = fma(ur, m.x, S[4 * q]);         S[4 * q + 1] = fma(ui, m.x, S[4 * q + 1]);
+            S[4 * q + 2] = fma(ur, m.y, S[4 * q + 2]); S[4 * q + 3] = fma(ui, m.y, S[4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+  if (!live) return;
+  // moment sums {J^2, J^2 p, J^2 p^2, J J' pp, J J' pp p, J'^2 pp^2} -> tensor components (moments_to_modes)
+  const double zbar = g.kperp_norm ? kperp * ms / (vA * qs) : ms / (vA * qs);
+  const double kf1 = g.kperp_norm ? 1.0 : kperp, kf2 = g.kperp_norm ? 1.0 : kperp * kperp;
+  const double rowfac = sp.dgamma * 0.25;
+  const double c0 = (nn * nn) / (zbar * zbar), c3 = kf1 * nn / zbar;
+  cd T[6];
+  T[0] = rowfac * (c0 * mk(S[0], S[1]));
+  T[1] = rowfac * (kf2 * mk(S[10], S[11]));
+  T[2] = rowfac * (kf2 * mk(S[4], S[5]));
+  T[3] = rowfac * cmul_i(c3 * mk(S[6], S[7]));
+  T[4] = rowfac * (c3 * mk(S[2], S[3]));
+  T[5] = rowfac * (-cmul_i(kf2 * mk(S[8], S[9])));
+  double* o = dpart + ((((size_t)tile_id * 2 * n_om + e) * nsplitB) + js) * 12;
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    o[2 * q] = T[q].x;
+    o[2 * q + 1] = T[q].y;
   }
 }
 
@@ -713,11 +1174,34 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
   if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
   static const char* force = getenv("ALPS_B200_REL_MINB");   // A/B knob: "1" = 255-register variant always
   if (nsplit > 1 || n_om * ntiles <= 2 * 148 || (force && force[0] == '1'))
-    launch_chain(k_rel<1>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
-                 err_flag, nsplit, Mpart, tickets);
+    launch_chain(k_rel<1, 0>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
+                 err_flag, nsplit, Mpart, tickets, nullptr, nullptr);
   else
-    launch_chain(k_rel<2>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
-                 err_flag, nsplit, Mpart, tickets);
+    launch_chain(k_rel<2, 0>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
+                 err_flag, nsplit, Mpart, tickets, nullptr, nullptr);
+}
+// throughput class: resonance flags + work list, principal-value / Landau parts of the listed entries, omega-tiled rest
+// (three launches; rflag: n_om * ntiles bytes, rwork: 2 * n_om * ntiles ints, rcount: one int)
+void launch_rel_tiled(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
+                      int* err_flag, unsigned char* rflag, int* rwork, int* rcount, int* rpos, double* dpart, int nsplitB,
+                      int sm_count, cudaStream_t st) {
+  if (n_om <= 0 || ntiles <= 0) return;
+  cudaMemsetAsync(rcount, 0, (size_t)ntiles * sizeof(int), st);
+  const int warps = n_om * ntiles;
+  k_rel_plan<<<(warps + 7) / 8, 256, 0, st>>>(g, om, n_om, tiles, ntiles, rflag, rwork, rcount, rpos);
+  static const char* pvb = getenv("ALPS_B200_REL_PV_MINB");   // A/B knob: "1" = 255 registers, one CTA per SM (measured
+                                                              // C3, 2048 omegas: 145 k D/s against 151 k with two)
+  const int sms = sm_count > 0 ? sm_count : 148;
+  if (!(pvb && pvb[0] == '1'))
+    k_rel<2, 1><<<2 * sms, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, 1, nullptr, nullptr, rwork,
+                                                 rcount);
+  else
+    k_rel<1, 1><<<sms, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, 1, nullptr, nullptr, rwork,
+                                             rcount);
+  k_rel_direct<<<dim3((2 * n_om + RT_THREADS - 1) / RT_THREADS, ntiles, nsplitB), RT_THREADS, 0, st>>>(
+      g, om, n_om, tiles, ntiles, rwork, rcount, dpart, nsplitB, err_flag);
+  k_rel_tiled<<<dim3((n_om + RT_THREADS - 1) / RT_THREADS, ntiles), RT_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, rflag,
+                                                                                        Mrel, rpos, dpart, nsplitB);
 }
 void launch_rel_bessel_table(const double* grel, const double* pbrel, int ng, int npb, double zfac, int nmaxord,
                              double* Jrel, cudaStream_t st) {

