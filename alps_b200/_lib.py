@@ -71,6 +71,14 @@ def build(force: bool = False) -> str:
     return SO_PATH
 
 
+def _sig(L, name, argtypes):
+    """argument types of one entry point; an A/B build given with ALPS_B200_LIB may predate the newest entry points"""
+    if hasattr(L, name):
+        getattr(L, name).argtypes = argtypes
+    elif not os.environ.get("ALPS_B200_LIB"):
+        raise AlpsB200Error(-1, "%s does not export %s" % (SO_PATH, name))
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -79,52 +87,47 @@ def lib():
                                 "__graft_entry__.build()); there is no CPU fallback" % SO_PATH)
         L = C.CDLL(SO_PATH)
         L.alps_b200_last_error.restype = C.c_char_p
-        L.alps_b200_set_species.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
-                                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                            C.c_int, C.c_int, C.c_int, C.c_double]
-        L.alps_b200_upload.argtypes = [C.c_void_p] * 4
-        L.alps_b200_derivative_f0.argtypes = [C.c_void_p] * 2
-        L.alps_b200_upload_rel.argtypes = [C.c_int] + [C.c_void_p] * 4
-        L.alps_b200_set_k.argtypes = [C.c_double, C.c_double, C.c_void_p]
-        L.alps_b200_disp.argtypes = [C.c_void_p] * 5
-        L.alps_b200_disp_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.alps_b200_disp_batch_full.argtypes = [C.c_int] + [C.c_void_p] * 5
-        L.alps_b200_disp_batch_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
-        L.alps_b200_disp_prefetch.argtypes = [C.c_int, C.c_void_p]
-        L.alps_b200_add_external_chi.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
-        L.alps_b200_set_harmonic_shard.argtypes = [C.c_int, C.c_int]
-        L.alps_b200_set_bm_species.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
-        L.alps_b200_nhds_calc_chi.argtypes = [C.c_double] * 3 + [C.c_int] + [C.c_double] * 6 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        L.alps_b200_chi_partial_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
-        L.alps_b200_assemble_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.alps_b200_set_mode.argtypes = [C.c_int]
-        L.alps_b200_set_stream.argtypes = [C.c_void_p]
-        L.alps_b200_get_info.argtypes = [C.c_int, C.c_void_p]
-        L.alps_b200_dfma_peak.argtypes = [C.c_void_p]
-        L.alps_b200_emulate_split.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _sig(L, "alps_b200_set_species", [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double])
+        _sig(L, "alps_b200_upload", [C.c_void_p] * 4)
+        _sig(L, "alps_b200_derivative_f0", [C.c_void_p] * 2)
+        _sig(L, "alps_b200_upload_rel", [C.c_int] + [C.c_void_p] * 4)
+        _sig(L, "alps_b200_set_k", [C.c_double, C.c_double, C.c_void_p])
+        _sig(L, "alps_b200_disp", [C.c_void_p] * 5)
+        _sig(L, "alps_b200_disp_batch", [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
+        _sig(L, "alps_b200_disp_batch_full", [C.c_int] + [C.c_void_p] * 5)
+        _sig(L, "alps_b200_disp_batch_dev", [C.c_int, C.c_void_p, C.c_void_p])
+        _sig(L, "alps_b200_disp_prefetch", [C.c_int, C.c_void_p])
+        _sig(L, "alps_b200_add_external_chi", [C.c_int, C.c_void_p, C.c_void_p])
+        _sig(L, "alps_b200_set_harmonic_shard", [C.c_int, C.c_int])
+        _sig(L, "alps_b200_set_bm_species", [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double])
+        _sig(L, "alps_b200_nhds_calc_chi", [C.c_double] * 3 + [C.c_int] + [C.c_double] * 6 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p])
+        _sig(L, "alps_b200_chi_partial_dev", [C.c_int, C.c_void_p, C.c_void_p])
+        _sig(L, "alps_b200_assemble_dev", [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
+        _sig(L, "alps_b200_set_mode", [C.c_int])
+        _sig(L, "alps_b200_set_stream", [C.c_void_p])
+        _sig(L, "alps_b200_get_info", [C.c_int, C.c_void_p])
+        _sig(L, "alps_b200_dfma_peak", [C.c_void_p])
+        _sig(L, "alps_b200_emulate_split", [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])
         V = C.c_void_p
-        L.alps_b200_secant.argtypes = [V, V, V]
-        L.alps_b200_secant_osc.argtypes = [V, V, V]
-        L.alps_b200_rtsec.argtypes = [V, V, V]
-        L.alps_b200_refine_guess.argtypes = [C.c_int, V, V, C.c_char_p, V]
-        L.alps_b200_map_search.argtypes = [V, C.c_char_p, V, V, V, C.c_int, V, V]
-        L.alps_b200_map_grid.argtypes = [V, V]
-        L.alps_b200_map_finish.argtypes = [V, V, C.c_char_p, V, C.c_int, V, V]
-        L.alps_b200_calc_eigen.argtypes = [V, C.c_int, V, V, V, C.c_double, C.c_double, C.c_double,
-                                           C.c_int, C.c_int, V, V, V, V, V, V, V]
-        L.alps_b200_scan_setup.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
-                                           C.c_int, C.c_int, V, V, V]
-        L.alps_b200_om_scan.argtypes = [V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V,
-                                        C.c_char_p, C.c_int, V]
-        L.alps_b200_om_double_scan.argtypes = [V, V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V, C.c_char_p, V]
-        L.alps_b200_set_root_batching.argtypes = [C.c_int]
-        L.alps_b200_tps_eval.argtypes = [C.c_int, V, V, V, C.c_int, V, V, V]
-        L.alps_b200_set_partition.argtypes = [C.c_int]
-        L.alps_b200_comm_unique_id.argtypes = [V]
-        L.alps_b200_comm_init.argtypes = [C.c_int, C.c_int, V]
-        L.alps_b200_omega_slice.argtypes = [C.c_int, C.c_int, C.c_int, V, V]
-        L.alps_b200_set_map_mode.argtypes = [C.c_int]
-        L.alps_b200_map_eval.argtypes = [C.c_int, V, V]
+        _sig(L, "alps_b200_secant", [V, V, V])
+        _sig(L, "alps_b200_secant_osc", [V, V, V])
+        _sig(L, "alps_b200_rtsec", [V, V, V])
+        _sig(L, "alps_b200_refine_guess", [C.c_int, V, V, C.c_char_p, V])
+        _sig(L, "alps_b200_map_search", [V, C.c_char_p, V, V, V, C.c_int, V, V])
+        _sig(L, "alps_b200_map_grid", [V, V])
+        _sig(L, "alps_b200_map_finish", [V, V, C.c_char_p, V, C.c_int, V, V])
+        _sig(L, "alps_b200_calc_eigen", [V, C.c_int, V, V, V, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, V, V, V, V, V, V, V])
+        _sig(L, "alps_b200_scan_setup", [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, V, V, V])
+        _sig(L, "alps_b200_om_scan", [V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V, C.c_char_p, C.c_int, V])
+        _sig(L, "alps_b200_om_double_scan", [V, V, C.c_int, V, V, C.c_int, V, V, V, C.c_double, V, V, C.c_char_p, V])
+        _sig(L, "alps_b200_set_root_batching", [C.c_int])
+        _sig(L, "alps_b200_tps_eval", [C.c_int, V, V, V, C.c_int, V, V, V])
+        _sig(L, "alps_b200_set_partition", [C.c_int])
+        _sig(L, "alps_b200_comm_unique_id", [V])
+        _sig(L, "alps_b200_comm_init", [C.c_int, C.c_int, V])
+        _sig(L, "alps_b200_omega_slice", [C.c_int, C.c_int, C.c_int, V, V])
+        _sig(L, "alps_b200_set_map_mode", [C.c_int])
+        _sig(L, "alps_b200_map_eval", [C.c_int, V, V])
         _LIB = L
     return _LIB
 

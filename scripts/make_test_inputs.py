@@ -13,7 +13,14 @@ FULL = "--full" in sys.argv
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "inputs",
                    "full" if FULL else "suite")
 NAMES = ["test_ICW", "test_electron_mode", "test_analytical", "test_chebyshev", "test_cold_plasma", "test_bimax",
-         "test_kperp", "test_double_scan", "test_map"] + (["test_kpar_fast", "test_relativistic"] if FULL else [])
+         "test_kperp", "test_kperp_alpha", "test_double_scan", "test_map"] + (["test_kpar_fast", "test_relativistic"] if FULL else [])
+# tests/test_kperp_alpha.in names arrayName='test_kperp_alpha', for which the reference ships no _dist.in: the three
+# Maxwellians its &ffit blocks describe (p, e, alphas with T_j = T_ref: fit_2 = 1/(m_j tau_j) = 1, 1836, 0.25) as a
+# generate_distribution input written here
+EXTRA_DIST = {"test_kperp_alpha": {
+    "system": dict(nspec=3, beta=1.0, va=1.0e-4, nperp=120, npar=240, maxp=6.0, writename="test_kperp_alpha"),
+    **{"spec_%d" % (i + 1): dict(ms_read=m, taus=1.0, alphs=1.0, ps=0.0, kappas=8.0, distributions=1, autoscales=True,
+                                 maxpperps=1.0, maxppars=1.0) for i, m in enumerate((1.0, 5.44662e-4, 4.0))}}}
 os.makedirs(OUT, exist_ok=True)
 
 
@@ -63,4 +70,6 @@ for name in NAMES:
     dist = os.path.join(REF, "distribution", arr + "_dist.in")
     if os.path.exists(dist):
         emit(read_namelists(dist), os.path.join(OUT, name.replace("test_", "cfg_") + "_dist.in"))
+    elif name in EXTRA_DIST:
+        emit(EXTRA_DIST[name], os.path.join(OUT, name.replace("test_", "cfg_") + "_dist.in"))
     print(name, "->", arr, os.path.exists(dist))

@@ -13,7 +13,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 SUITE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "inputs", "suite")
 CONFIGS = ["cfg_ICW", "cfg_electron_mode", "cfg_analytical", "cfg_chebyshev", "cfg_cold_plasma", "cfg_bimax",
-           "cfg_kperp", "cfg_double_scan", "cfg_map"]
+           "cfg_kperp", "cfg_kperp_alpha", "cfg_double_scan", "cfg_map"]
 
 
 @pytest.mark.parametrize("name", CONFIGS)
