@@ -56,3 +56,28 @@ def test_device_spline_evaluation_matches_the_host_statement():
     scale = np.max(np.abs(host[3]))
     assert np.max(np.abs(host[3] - dev[3])) < 1e-8 * scale
     assert abs(host[4] - dev[4]) < 1e-9 * abs(host[4])
+
+
+def test_regrid_against_scipy_rbf_interpolator():
+    """Independent pin of the thin-plate-spline regrid (polyharmonic_spline, src/ALPS_fns_rel.f90:300-426, restated in
+    alps_b200/relativistic.py: r^2 log r kernel + linear polynomial, dense LAPACK solve): scipy's RBFInterpolator with
+    kernel='thin_plate_spline', degree=1 solves the same interpolation problem with its own assembly, scaling and
+    solver.  Both interpolate log f0 of the same Juettner table onto the same (Gamma, pbar_par) grid; inside the cone the
+    two splines agree to ~1e-8 (they are THE interpolant: the problem is unisolvent), and both reproduce the analytic
+    log f0 = const - a Gamma to the spline's own accuracy."""
+    from scipy.interpolate import RBFInterpolator
+    from alps_b200.relativistic import derivative_f0_rel
+    pl = tables.config_relativistic(nperp=20, npar=40, ngamma=40, npparbar=60)
+    pp, f0, ms, vA = pl.pp[0], pl.f0[0], 1.0, 1.0
+    g, p, f, d, integ = derivative_f0_rel(pp, f0, ms, vA, 40, 60, backend="host")
+    gc = np.sqrt(1.0 + (pp[:, :, 0] ** 2 + pp[:, :, 1] ** 2) * vA * vA / (ms * ms)).ravel()
+    pc = (pp[:, :, 1] * vA / ms).ravel()
+    rbf = RBFInterpolator(np.column_stack([gc, pc]), np.log(f0).ravel(), kernel="thin_plate_spline", degree=1)
+    inside = f > 0.0
+    ref = rbf(np.column_stack([g[inside], p[inside]]))
+    ours = np.log(f[inside] * integ)            # undo the renormalisation of derivative_f0_rel
+    assert np.max(np.abs(ours - ref)) < 1e-7, np.max(np.abs(ours - ref))
+    # and against the analytic table: log f0 = log C - a Gamma with a = perp_correction
+    a = pl.species[0].perp_correction[0]
+    lin = ours + a * g[inside]
+    assert np.max(np.abs(lin - np.median(lin))) < 2e-2
