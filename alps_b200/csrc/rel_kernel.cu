@@ -244,6 +244,20 @@ struct RelWin {
   unsigned char out[REL_WIN + 1];
   int anyout;                  // any out[] flag set
 };
+// Window slot k (node W0 + k) that funct_g_rel interpolates around for the point p, when the cached search decides it
+// (see funct_g_win); -1: the caller takes the general path.
+__device__ __forceinline__ int win_locate(const SpeciesDev& sp, int npb, double p, const RelWin& w, int W0, int nwin,
+                                          double inv_dpb) {
+  if (w.anyout) return -1;
+  const int i0 = (int)floor((p - sp.pbrel[0]) * inv_dpb);
+  const int k0 = i0 - W0;
+  if (!(k0 >= 2 && k0 + 3 <= nwin && i0 >= 4 && i0 + 4 <= npb)) return -1;
+  int q = k0;
+  if (w.pb[q] > p) q--;
+  else if (w.pb[q + 1] <= p) q++;
+  if (!(w.pb[q + 1] > p && w.pb[q] <= p)) return -1;
+  return (q >= 1 && q + 1 < nwin) ? q : -1;
+}
 __device__ __forceinline__ void funct_g_win(const RelCtx& c, int sg, double p, int ig, const RelWin& w, int W0,
                                             int nwin, double inv_dpb, Six2& out) {
   const SpeciesDev& sp = *c.sp;
@@ -295,31 +309,195 @@ __device__ __forceinline__ cd warp_sum_cd(cd v) {
   return v;
 }
 
+// principal_integral_rel for one Gamma row (src/ALPS_fns_rel.f90:724-913): window of 2 M_I + 7 nodes around the resonance
+// cached in shared memory (one per warp), symmetric pairing / linearised branch, tiny rest; adds wg smdelta (sum) to Sd.
+// Called by a whole warp with warp-uniform arguments.
+__device__ __forceinline__ void pv_row(const RelCtx& c, const GlobalDev& g, const SpeciesDev& sp, cd omc, int sg, double nn,
+                                       int ig, int ires, int upperlimit, double wg, RelWin& win_, int lane, Six2& Sd) {
+  const int npb = g.npparbar, M_I = g.M_I, M_P = g.M_P, ldr = npb + 1;
+  const double qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar, dpb = sp.dpparbar;
+  const double* pbv = sp.pbrel;
+  const double gres = sp.grel[ig];   // gamma_rel(sproc_rel,igamma,ipparbar_res): separable grid
+  const double denomR = (gres * omc.x * vA / kpar) - (1.0 * nn) * (qs / ms) * vA / kpar;
+  const double denomI = gres * omc.y * vA / kpar;
+  const double capDelta = denomR - pbv[ires - M_I];
+  const double smdelta = capDelta / (1.0 * M_P);
+  Six2 pr;
+  zero6(pr);
+  // node values of the window [ires - M_I - 2, ires + M_I + 4]: one node per lane
+  const int W0 = ires - M_I - 2, nwin = (2 * M_I + 7 <= REL_WIN) ? 2 * M_I + 7 : 0;
+  RelWin& win = win_;
+  const double inv_dpb = 1.0 / dpb;
+  __syncwarp();
+  if (lane <= nwin && nwin > 0) {
+    const int idx = W0 + lane;
+    const bool in = idx >= 0 && idx <= npb;
+    // coordinates outside the table never match a comparison (NaN): the cached search then misses and the
+    // global one decides
+    win.pb[lane] = in ? pbv[idx] : __longlong_as_double(0x7ff8000000000000LL);
+    win.out[lane] = (in && sp.f0_rel[(size_t)ig * ldr + idx] <= -1.0) ? 1 : 0;
+    const unsigned any = __ballot_sync(__activemask(), win.out[lane] != 0);
+    if (lane == 0) win.anyout = any != 0;
+    if (lane < nwin) {
+      double M[6];
+      cd num = mk(0.0, 0.0);
+#pragma unroll
+      for (int q = 0; q < 6; q++) M[q] = 0.0;
+      if (in) node_moments(c, ig, idx, sg, M, num);
+#pragma unroll
+      for (int q = 0; q < 6; q++) win.val[lane][q] = M[q] * num;
+    }
+  }
+  __syncwarp();
+  if (lane >= 1 && lane + 1 < nwin) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) win.dif[lane][q] = win.val[lane + 1][q] - win.val[lane - 1][q];
+  }
+  __syncwarp();
+  if (fabs(denomI) > g.Tlim) {
+    for (int j = lane; j <= M_P; j += 32) {
+      const double wj = (j == 0 || j == M_P) ? 1.0 : 2.0;
+      const double p = (j == 0) ? denomR : (j == M_P ? denomR + capDelta : denomR + smdelta * j);
+      const double p2 = 2.0 * denomR - p;
+      // wj / d1 and wj / d2 with d2 = conj(d1): one reciprocal for the twelve quotients
+      const double dx = p - denomR, tt = wj * fast_rcp(fma(dx, dx, denomI * denomI));
+      // f1 r1 - f2 conj(r1), r1 = (x, y)
+      const double rx = dx * tt, ry = denomI * tt;
+      const int k1 = win_locate(sp, npb, p, win, W0, nwin, inv_dpb);
+      const int k2 = win_locate(sp, npb, p2, win, W0, nwin, inv_dpb);
+      if (k1 >= 0 && k2 >= 0) {
+        // both points interpolate inside the cached window (the normal case): component by component, nothing but
+        // the running sums stays live
+        const double sx1 = (0.5 * inv_dpb) * (p - win.pb[k1]), sx2 = (0.5 * inv_dpb) * (p2 - win.pb[k2]);
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          const cd a1 = win.val[k1][q], d1 = win.dif[k1][q], a2 = win.val[k2][q], d2 = win.dif[k2][q];
+          const double f1x = fma(sx1, d1.x, a1.x), f1y = fma(sx1, d1.y, a1.y);
+          const double f2x = fma(sx2, d2.x, a2.x), f2y = fma(sx2, d2.y, a2.y);
+          pr.v[q].x += fma(f1x - f2x, rx, -((f1y + f2y) * ry));
+          pr.v[q].y += fma(f1x + f2x, ry, (f1y - f2y) * rx);
+        }
+      } else {
+        Six2 f1, f2;
+        funct_g_win(c, sg, p, ig, win, W0, nwin, inv_dpb, f1);
+        funct_g_win(c, sg, p2, ig, win, W0, nwin, inv_dpb, f2);
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          const double sr = f1.v[q].x - f2.v[q].x, si = f1.v[q].y + f2.v[q].y;
+          const double tr = f1.v[q].x + f2.v[q].x, ti = f1.v[q].y - f2.v[q].y;
+          pr.v[q].x += fma(sr, rx, -(si * ry));
+          pr.v[q].y += fma(tr, ry, ti * rx);
+        }
+      }
+    }
+  } else {
+    Six2 fp_, fm_;
+    funct_g_win(c, sg, denomR + dpb, ig, win, W0, nwin, inv_dpb, fp_);
+    funct_g_win(c, sg, denomR - dpb, ig, win, W0, nwin, inv_dpb, fm_);
+    // sum_j 2 wj g' x^2 / (x^2 + denomI^2): g' does not depend on j
+    double sj = 0.0;
+    for (int j = 1 + lane; j <= M_P; j += 32) {
+      const double wj = (j == M_P) ? 1.0 : 2.0;
+      const double p = (j == M_P) ? denomR + capDelta : denomR + smdelta * j;
+      const double x2 = (p - denomR) * (p - denomR);
+      sj += ((wj * 2.0) * x2) * fast_rcp(x2 + denomI * denomI);
+    }
+    const double h2 = 0.5 * inv_dpb;
+#pragma unroll
+    for (int q = 0; q < 6; q++) pr.v[q] += (sj * h2) * (fp_.v[q] - fm_.v[q]);
+    if (lane == 0 && denomI != 0.0) {
+      Six2 f0_;
+      funct_g_win(c, sg, denomR, ig, win, W0, nwin, inv_dpb, f0_);
+      const double sgn = denomI > 0.0 ? 1.0 : -1.0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) pr.v[q] += sgn * (cmul_i((2.0 * PI_) * f0_.v[q]) / smdelta);
+    }
+  }
+  const double rest = pbv[upperlimit] - denomR - capDelta;
+  const int ntiny = (int)(rest / smdelta);
+  if (ntiny > 0) {
+    const double correction = (rest / (1.0 * ntiny)) / smdelta;
+    for (int j = lane; j <= ntiny; j += 32) {
+      const double wj = (j == 0 || j == ntiny) ? 1.0 : 2.0;
+      const double p = (j == 0) ? denomR + capDelta : denomR + capDelta + correction * smdelta * j;
+      Six2 f1;
+      funct_g_win(c, sg, p, ig, win, W0, nwin, inv_dpb, f1);
+      const double dx = p - denomR, tt = (wj * correction) * fast_rcp(fma(dx, dx, denomI * denomI));
+      const cd r1 = mk(dx * tt, denomI * tt);
+#pragma unroll
+      for (int q = 0; q < 6; q++) pr.v[q] += f1.v[q] * r1;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; q++) Sd.v[q] += (wg * smdelta) * pr.v[q];
+}
+
+// landau_integrate_rel (src/ALPS_fns_rel.f90:1005-1092) for Im(om) <= 0: this thread's Gamma rows first + 1, first + 1 +
+// stride, ...; adds i L mult to acc
+__device__ __forceinline__ void landau_rows(const RelCtx& c, const GlobalDev& g, const SpeciesDev& sp, cd omc, int sg,
+                                            double nn, int first, int stride, const double* s_rfact, const double* s_rgam,
+                                            Six2& acc) {
+  const int ng = g.ngamma, nabs = c.nabs;
+  const double qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar, dpb = sp.dpparbar, dgam = sp.dgamma;
+  Six2 L;
+  zero6(L);
+  for (int ig = 1 + first; ig <= ng - 1; ig += stride) {
+    const double g1 = sp.grel[ig];
+    const cd pres = (g1 * omc) * vA / kpar - mk((1.0 * nn) * qs * vA / (kpar * ms), 0.0);
+    if (!(pres.x * pres.x <= g1 * g1 - 1.0)) continue;
+    const double h = (ig == ng - 1) ? 0.5 : 1.0;
+    cd dfg;
+    if (ig == 1) dfg = (eval_fit_rel(g, sp, ig + 1, pres) - eval_fit_rel(g, sp, ig, pres)) / dgam;
+    else dfg = (eval_fit_rel(g, sp, ig + 1, pres) - eval_fit_rel(g, sp, ig - 1, pres)) / (2.0 * dgam);
+    const cd dfp = (eval_fit_rel(g, sp, ig, pres + mk(dpb, 0.0)) - eval_fit_rel(g, sp, ig, pres - mk(dpb, 0.0))) /
+                   (2.0 * dpb);
+    const cd fac = -h * (omc * dfg + (kpar / vA) * dfp);
+    // int_T_res_rel with complex-argument Bessel functions
+    const cd pperpbar = csqrt_(mk(g1 * g1 - 1.0, 0.0) - pres * pres);
+    const cd z = c.zfac * pperpbar;
+    const double par = (nabs & 1) ? -1.0 : 1.0;
+    cd bj, bp, b1, b2;
+    cbessj3(z, nabs - 1, s_rfact, s_rgam, b1, bj, b2);   // J_{|n|-1}, J_|n|, J_{|n|+1}
+    if (sg) bj = par * bj;
+    if (nabs == 0) {
+      bp = -b2;
+    } else {
+      if (!sg) bp = 0.5 * (b1 - b2);
+      else bp = (nabs == 1) ? 0.5 * (b2 - b1) : 0.5 * ((-par) * b2 - (-par) * b1);
+    }
+    cd T[6];
+    T[0] = ((nn * nn) / (c.zbar * c.zbar)) * (bj * bj);
+    T[1] = c.kf2 * (bp * bp * pperpbar * pperpbar);
+    T[2] = c.kf2 * (bj * bj * (pres * pres));
+    T[3] = cmul_i((c.kf1 * nn / c.zbar) * (bj * bp * pperpbar));
+    T[4] = (c.kf1 * nn / c.zbar) * (bj * bj * pres);
+    T[5] = -cmul_i(c.kf2 * (bj * bp * pres * pperpbar));
+#pragma unroll
+    for (int q = 0; q < 6; q++) L.v[q] += fac * T[q];
+  }
+  const double mult = (omc.y < 0.0 ? 2.0 : 1.0) * dgam * PI_ * 2.0 * PI_ * (qs * vA / (kpar * ms)) *
+                      ((ms / vA) * (ms / vA) * (ms / vA));
+#pragma unroll
+  for (int q = 0; q < 6; q++) acc.v[q] += cmul_i(L.v[q]) * mult;
+}
+
 constexpr int REL_THREADS = 256;
 
 // nsplit > 1 (few omegas in flight: sequential root finding is latency bound): the gamma rows / grid points
 // of one (omega, species, |n|) are dealt round-robin to nsplit CTAs; each leaves a partial row in Mpart and
 // the last one to finish (ticket counter) adds them up in a fixed order.
 // MINB = 2 (throughput batches): 128 registers, two CTAs per SM; MINB = 1 (latency batches): 255 registers
-// MODE 1 (throughput class): only the principal-value and Landau parts, for the resonant (omega, tile, sign) entries of
-// the work list of k_rel_plan (persistent CTAs stride over it); the non-resonant quadrature and the direct part of the
-// resonant rows are k_rel_tiled's.
-template <int MINB, int MODE>
+template <int MINB>
 __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
                                                      int n_om, const RelTile* __restrict__ tiles, int ntiles,
                                                      double* __restrict__ Mrel, int* __restrict__ err_flag, int nsplit,
-                                                     double* __restrict__ Mpart, int* __restrict__ tickets,
-                                                     const int* __restrict__ rwork, const int* __restrict__ rcount) {
+                                                     double* __restrict__ Mpart, int* __restrict__ tickets) {
   const GlobalDev& g = *gp;
   pdl_trigger();
   pdl_wait();
-  // MODE 1: rwork holds one segment of 2 n_om slots per tile (entries (iom << 1) | sign), rcount[tile] its fill
-  for (int etile = 0; etile < (MODE == 1 ? ntiles : 1); etile++)
-  for (int entry = MODE == 1 ? blockIdx.x : 0; entry < (MODE == 1 ? rcount[etile] : 1); entry += MODE == 1 ? gridDim.x : 1) {
-  const int ecode = MODE == 1 ? rwork[(size_t)etile * 2 * n_om + entry] : 0;
-  const int js = MODE == 1 ? 0 : blockIdx.x % nsplit;
-  const int iom = MODE == 1 ? (ecode >> 1) : (blockIdx.x / nsplit) / ntiles;
-  const int tile_id = MODE == 1 ? etile : (blockIdx.x / nsplit) % ntiles;
+  const int js = blockIdx.x % nsplit;
+  const int iom = (blockIdx.x / nsplit) / ntiles;
+  const int tile_id = (blockIdx.x / nsplit) % ntiles;
   const RelTile tl = tiles[tile_id];
   const SpeciesDev& sp = g.sp[tl.s];
   const int nabs = tl.nabs;
@@ -339,11 +517,11 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
     const int m = nabs + (tid - 32);                          // Gamma(m), m = |n| .. |n| + 22
     s_rgam[tid - 32] = m >= 1 ? 1.0 / gamma_ref(1.0 * m) : 0.0;
   }
-  if (tid < 2) s_found[tid] = MODE == 1 ? 1 : 0;
+  if (tid < 2) s_found[tid] = 0;
   __syncthreads();
 
   // ---- determine_resonances, relativistic branch: any (iperp, ipar) cell containing Re p_res
-  if (MODE == 0) {
+  {
     int fp = 0, fm = 0;
     for (int idx = tid; idx < (nperp + 1) * npar; idx += REL_THREADS) {
       const int iperp = idx / npar, ipar = idx - iperp * npar;
@@ -372,7 +550,6 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
 
   for (int sg = 0; sg < 2; sg++) {
     if (nabs == 0 && sg == 1) break;
-    if (MODE == 1 && sg != (ecode & 1)) continue;
     const double nn = sg ? -(double)nabs : (double)nabs;
     Six2 acc;
     zero6(acc);
@@ -466,9 +643,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           upperlimit = npb;
         }
         // direct part
-        if (MODE == 1) {
-          // k_rel_tiled
-        } else if (sp.Jrel) {
+        if (sp.Jrel) {
           // hot loop: the six T components are real multiples of six Bessel moments (like the table species'
           // p_par moments), so the loop accumulates sum U {J^2, J^2 p, J^2 p^2, J J' pp, J J' pp p, J'^2 pp^2}
           // with one reciprocal per node; Bessel factors and pperpbar come from the per-k tables
@@ -539,104 +714,8 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
           }
         }
         // principal part
-        if (found && lowerlimit >= int_start && upperlimit <= int_end) {
-          const double gres = sp.grel[ig];   // gamma_rel(sproc_rel,igamma,ipparbar_res): separable grid
-          const double denomR = (gres * omc.x * vA / kpar) - (1.0 * nn) * (qs / ms) * vA / kpar;
-          const double denomI = gres * omc.y * vA / kpar;
-          const double capDelta = denomR - pbv[ires - M_I];
-          const double smdelta = capDelta / (1.0 * M_P);
-          Six2 pr;
-          zero6(pr);
-          // node values of the window [ires - M_I - 2, ires + M_I + 4]: one node per lane
-          const int W0 = ires - M_I - 2, nwin = (2 * M_I + 7 <= REL_WIN) ? 2 * M_I + 7 : 0;
-          RelWin& win = s_win[warp];
-          const double inv_dpb = 1.0 / dpb;
-          __syncwarp();
-          if (lane <= nwin && nwin > 0) {
-            const int idx = W0 + lane;
-            const bool in = idx >= 0 && idx <= npb;
-            // coordinates outside the table never match a comparison (NaN): the cached search then misses and the
-            // global one decides
-            win.pb[lane] = in ? pbv[idx] : __longlong_as_double(0x7ff8000000000000LL);
-            win.out[lane] = (in && sp.f0_rel[(size_t)ig * ldr + idx] <= -1.0) ? 1 : 0;
-            const unsigned any = __ballot_sync(__activemask(), win.out[lane] != 0);
-            if (lane == 0) win.anyout = any != 0;
-            if (lane < nwin) {
-              double M[6];
-              cd num = mk(0.0, 0.0);
-#pragma unroll
-              for (int q = 0; q < 6; q++) M[q] = 0.0;
-              if (in) node_moments(c, ig, idx, sg, M, num);
-#pragma unroll
-              for (int q = 0; q < 6; q++) win.val[lane][q] = M[q] * num;
-            }
-          }
-          __syncwarp();
-          if (lane >= 1 && lane + 1 < nwin) {
-#pragma unroll
-            for (int q = 0; q < 6; q++) win.dif[lane][q] = win.val[lane + 1][q] - win.val[lane - 1][q];
-          }
-          __syncwarp();
-          if (fabs(denomI) > g.Tlim) {
-            for (int j = lane; j <= M_P; j += 32) {
-              const double wj = (j == 0 || j == M_P) ? 1.0 : 2.0;
-              const double p = (j == 0) ? denomR : (j == M_P ? denomR + capDelta : denomR + smdelta * j);
-              Six2 f1, f2;
-              funct_g_win(c, sg, p, ig, win, W0, nwin, inv_dpb, f1);
-              funct_g_win(c, sg, 2.0 * denomR - p, ig, win, W0, nwin, inv_dpb, f2);
-              // wj / d1 and wj / d2 with d2 = conj(d1): one reciprocal for the twelve quotients
-              const double dx = p - denomR, tt = wj * fast_rcp(fma(dx, dx, denomI * denomI));
-              // f1 r1 - f2 conj(r1), r1 = (x, y)
-              const double rx = dx * tt, ry = denomI * tt;
-#pragma unroll
-              for (int q = 0; q < 6; q++) {
-                const double sr = f1.v[q].x - f2.v[q].x, si = f1.v[q].y + f2.v[q].y;
-                const double tr = f1.v[q].x + f2.v[q].x, ti = f1.v[q].y - f2.v[q].y;
-                pr.v[q].x += fma(sr, rx, -(si * ry));
-                pr.v[q].y += fma(tr, ry, ti * rx);
-              }
-            }
-          } else {
-            Six2 fp_, fm_;
-            funct_g_win(c, sg, denomR + dpb, ig, win, W0, nwin, inv_dpb, fp_);
-            funct_g_win(c, sg, denomR - dpb, ig, win, W0, nwin, inv_dpb, fm_);
-            // sum_j 2 wj g' x^2 / (x^2 + denomI^2): g' does not depend on j
-            double sj = 0.0;
-            for (int j = 1 + lane; j <= M_P; j += 32) {
-              const double wj = (j == M_P) ? 1.0 : 2.0;
-              const double p = (j == M_P) ? denomR + capDelta : denomR + smdelta * j;
-              const double x2 = (p - denomR) * (p - denomR);
-              sj += ((wj * 2.0) * x2) * fast_rcp(x2 + denomI * denomI);
-            }
-            const double h2 = 0.5 * inv_dpb;
-#pragma unroll
-            for (int q = 0; q < 6; q++) pr.v[q] += (sj * h2) * (fp_.v[q] - fm_.v[q]);
-            if (lane == 0 && denomI != 0.0) {
-              Six2 f0_;
-              funct_g_win(c, sg, denomR, ig, win, W0, nwin, inv_dpb, f0_);
-              const double sgn = denomI > 0.0 ? 1.0 : -1.0;
-#pragma unroll
-              for (int q = 0; q < 6; q++) pr.v[q] += sgn * (cmul_i((2.0 * PI_) * f0_.v[q]) / smdelta);
-            }
-          }
-          const double rest = pbv[upperlimit] - denomR - capDelta;
-          const int ntiny = (int)(rest / smdelta);
-          if (ntiny > 0) {
-            const double correction = (rest / (1.0 * ntiny)) / smdelta;
-            for (int j = lane; j <= ntiny; j += 32) {
-              const double wj = (j == 0 || j == ntiny) ? 1.0 : 2.0;
-              const double p = (j == 0) ? denomR + capDelta : denomR + capDelta + correction * smdelta * j;
-              Six2 f1;
-              funct_g_win(c, sg, p, ig, win, W0, nwin, inv_dpb, f1);
-              const double dx = p - denomR, tt = (wj * correction) * fast_rcp(fma(dx, dx, denomI * denomI));
-              const cd r1 = mk(dx * tt, denomI * tt);
-#pragma unroll
-              for (int q = 0; q < 6; q++) pr.v[q] += f1.v[q] * r1;
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 6; q++) Sd.v[q] += (wg * smdelta) * pr.v[q];
-        }
+        if (found && lowerlimit >= int_start && upperlimit <= int_end)
+          pv_row(c, g, sp, omc, sg, nn, ig, ires, upperlimit, wg, s_win[warp], lane, Sd);
       }
       // moment sums of the direct and principal parts -> tensor components
       moments_to_modes(c, nn, Sd, acc);
@@ -644,48 +723,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
       for (int q = 0; q < 6; q++) acc.v[q] = (dgam * 0.25) * acc.v[q];
 
       // ---- landau_integrate_rel (Im om <= 0), all threads stride over igamma
-      if (omc.y <= 0.0) {
-        Six2 L;
-        zero6(L);
-        for (int ig = 1 + tid + REL_THREADS * js; ig <= ng - 1; ig += REL_THREADS * nsplit) {
-          const double g1 = sp.grel[ig];
-          const cd pres = (g1 * omc) * vA / kpar - mk((1.0 * nn) * qs * vA / (kpar * ms), 0.0);
-          if (!(pres.x * pres.x <= g1 * g1 - 1.0)) continue;
-          const double h = (ig == ng - 1) ? 0.5 : 1.0;
-          cd dfg;
-          if (ig == 1) dfg = (eval_fit_rel(g, sp, ig + 1, pres) - eval_fit_rel(g, sp, ig, pres)) / dgam;
-          else dfg = (eval_fit_rel(g, sp, ig + 1, pres) - eval_fit_rel(g, sp, ig - 1, pres)) / (2.0 * dgam);
-          const cd dfp = (eval_fit_rel(g, sp, ig, pres + mk(dpb, 0.0)) - eval_fit_rel(g, sp, ig, pres - mk(dpb, 0.0))) /
-                         (2.0 * dpb);
-          const cd fac = -h * (omc * dfg + (kpar / vA) * dfp);
-          // int_T_res_rel with complex-argument Bessel functions
-          const cd pperpbar = csqrt_(mk(g1 * g1 - 1.0, 0.0) - pres * pres);
-          const cd z = c.zfac * pperpbar;
-          const double par = (nabs & 1) ? -1.0 : 1.0;
-          cd bj, bp, b1, b2;
-          cbessj3(z, nabs - 1, s_rfact, s_rgam, b1, bj, b2);   // J_{|n|-1}, J_|n|, J_{|n|+1}
-          if (sg) bj = par * bj;
-          if (nabs == 0) {
-            bp = -b2;
-          } else {
-            if (!sg) bp = 0.5 * (b1 - b2);
-            else bp = (nabs == 1) ? 0.5 * (b2 - b1) : 0.5 * ((-par) * b2 - (-par) * b1);
-          }
-          cd T[6];
-          T[0] = ((nn * nn) / (c.zbar * c.zbar)) * (bj * bj);
-          T[1] = c.kf2 * (bp * bp * pperpbar * pperpbar);
-          T[2] = c.kf2 * (bj * bj * (pres * pres));
-          T[3] = cmul_i((c.kf1 * nn / c.zbar) * (bj * bp * pperpbar));
-          T[4] = (c.kf1 * nn / c.zbar) * (bj * bj * pres);
-          T[5] = -cmul_i(c.kf2 * (bj * bp * pres * pperpbar));
-#pragma unroll
-          for (int q = 0; q < 6; q++) L.v[q] += fac * T[q];
-        }
-        const double mult = (omc.y < 0.0 ? 2.0 : 1.0) * dgam * PI_ * 2.0 * PI_ * (qs * vA / (kpar * ms)) *
-                            ((ms / vA) * (ms / vA) * (ms / vA));
-#pragma unroll
-        for (int q = 0; q < 6; q++) acc.v[q] += cmul_i(L.v[q]) * mult;
-      }
+      if (omc.y <= 0.0) landau_rows(c, g, sp, omc, sg, nn, tid + REL_THREADS * js, REL_THREADS * nsplit, s_rfact, s_rgam, acc);
     }
     // ---- block reduction and store
 #pragma unroll
@@ -704,7 +742,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
     }
     __syncthreads();
   }
-  if (MODE == 0 && nsplit > 1) {
+  if (nsplit > 1) {
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
@@ -724,12 +762,10 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
       if (tid == 0) tickets[iom * ntiles + tile_id] = 0;   // ready for the next launch
     }
   }
-  if (MODE == 1) __syncthreads();   // the shared tables of this entry are rebuilt by the next one
-  }
 }
 
 // =====================================================================================================================
-// Throughput class (batches of more than 64 omegas): k_rel_plan -> k_rel<.,1> -> k_rel_tiled.
+// Throughput class (batches of more than 64 omegas): k_rel_plan -> k_rel_pv -> k_rel_direct -> k_rel_tiled.
 //
 // k_rel above gives one CTA to every (omega, species, |n|) and streams the (Gamma, pbar_par) tables -- 56 B per node for
 // ~45 FP64 operations -- from L2 again for every omega: L2-bound at a fifth of the FP64 pipe (profiles/r01_k_rel_ncu_full.csv).
@@ -740,7 +776,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
 // for +n and -n because J_-n = (-1)^n J_n enters them squared or as J J' -- is computed ONCE per node by one thread into a
 // shared-memory packet, and every thread then applies its own omega to the packet (warp-uniform LDS broadcasts): per
 // (node, omega, sign) one reciprocal and 12 FMAs.  The principal-value window and the Landau term of the resonant
-// harmonics keep their warp-per-Gamma-row form (k_rel, MODE 1) but run only for the resonant (omega, species, n, sign)
+// harmonics keep their warp-per-Gamma-row form (k_rel_pv) but run only for the resonant (omega, species, n, sign)
 // entries that k_rel_plan lists.
 // ---------------------------------------------------------------------------------------------------------------------
 
@@ -785,12 +821,15 @@ __global__ void __launch_bounds__(256) k_rel_plan(const GlobalDev* __restrict__ 
 // limits of integrate_resU_rel for one Gamma row (src/ALPS_fns_rel.f90:591-672); returns 0 on alps_error(8)
 struct RelRow {
   int int_start, int_end, lowerlimit, upperlimit;
+  int ires, pv;      // cell of the resonance; principal_integral_rel applies (resonance well inside the cone)
 };
 __device__ __forceinline__ int rel_row_limits(const SpeciesDev& sp, int npb, int M_I, double presx, double g1, int lo_c,
                                               int up_c, RelRow& r) {
   const double* __restrict__ pbv = sp.pbrel;
   const double dpb = sp.dpparbar;
   int ires = 0, found = 0;
+  r.ires = 0;
+  r.pv = 0;
   if (presx * presx <= g1 * g1 - 1.0) {
     if (presx >= pbv[1] && presx < pbv[npb - 1]) {
       // the cell [pbv(lo), pbv(lo+1)) that holds Re p_res, lo in [1, npb-2]: index guess on the uniform grid, then the
@@ -816,6 +855,7 @@ __device__ __forceinline__ int rel_row_limits(const SpeciesDev& sp, int npb, int
     }
   }
   if (found) {
+    r.ires = ires;
     r.int_start = lo_c;
     r.int_end = up_c;
     r.lowerlimit = ires - M_I;
@@ -838,6 +878,7 @@ __device__ __forceinline__ int rel_row_limits(const SpeciesDev& sp, int npb, int
     r.int_end = npb - 1;
     r.upperlimit = npb;
   }
+  r.pv = found && r.lowerlimit >= r.int_start && r.upperlimit <= r.int_end;
   return 1;
 }
 
@@ -965,7 +1006,7 @@ __global__ void __launch_bounds__(RT_THREADS, 3)
   }
 
   if (!live) return;
-  // non-resonant signs: done.  Resonant signs: k_rel<., 1> has left the principal-value and Landau parts in Mrel; add the
+  // non-resonant signs: done.  Resonant signs: k_rel_pv has left the principal-value and Landau parts in Mrel; add the
   // direct part, i.e. the partial rows of the Gamma splits of k_rel_direct in their fixed order
 #pragma unroll
   for (int sgn = 0; sgn < 2; sgn++) {
@@ -1119,6 +1160,108 @@ __global__ void __launch_bounds__(RT_THREADS, 3)
   }
 }
 
+// Principal-value window, tiny rest and Landau term of the resonant entries (persistent CTAs over the per-tile lists of
+// k_rel_plan).  The row bookkeeping of integrate_resU_rel (cell of the resonance, limits, whether the principal part
+// applies) is computed for 32 Gamma rows at a time, one row per lane, and handed to the warp by shuffles; the warp then
+// works through the rows that have a principal part with pv_row.  Leaves the entry's tensor components in Mrel
+// (k_rel_tiled adds the direct part).
+template <int MINB>
+__global__ void __launch_bounds__(REL_THREADS, MINB)
+    k_rel_pv(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om, const RelTile* __restrict__ tiles,
+             int ntiles, double* __restrict__ Mrel, int* __restrict__ err_flag, const int* __restrict__ rwork,
+             const int* __restrict__ rcount) {
+  const GlobalDev& g = *gp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = REL_THREADS / 32;
+  __shared__ cd s_red[REL_THREADS / 32][6];
+  __shared__ RelWin s_win[REL_THREADS / 32];
+  __shared__ double s_rfact[21], s_rgam[23];
+  const int ng = g.ngamma, npb = g.npparbar, M_I = g.M_I;
+  const double vA = g.vA, kpar = g.kpar, kperp = g.kperp;
+  int last_nabs = -1;
+  for (int etile = 0; etile < ntiles; etile++) {
+    const int cnt = rcount[etile];
+    if (blockIdx.x >= cnt) continue;
+    const RelTile tl = tiles[etile];
+    const SpeciesDev& sp = g.sp[tl.s];
+    const int nabs = tl.nabs;
+    const double qs = sp.qs, ms = sp.ms;
+    if (nabs != last_nabs) {      // series coefficients of the Landau term: 1/k!, 1/Gamma(|n| + i)
+      __syncthreads();
+      if (tid < 21) {
+        double fact = 1.0;
+        for (int k = 2; k <= tid; k++) fact = fact * (1.0 * k);
+        s_rfact[tid] = 1.0 / fact;
+      } else if (tid >= 32 && tid < 32 + 23) {
+        const int m = nabs + (tid - 32);
+        s_rgam[tid - 32] = m >= 1 ? 1.0 / gamma_ref(1.0 * m) : 0.0;
+      }
+      __syncthreads();
+      last_nabs = nabs;
+    }
+    RelCtx c;
+    c.g = gp;
+    c.sp = &sp;
+    c.nabs = nabs;
+    c.pref = -2.0 * PI_ * ((ms / vA) * (ms / vA) * (ms / vA)) * (qs * vA / (kpar * ms));
+    c.zfac = kperp * ms / (vA * qs);
+    c.zbar = g.kperp_norm ? kperp * ms / (vA * qs) : ms / (vA * qs);
+    c.kf1 = g.kperp_norm ? 1.0 : kperp;
+    c.kf2 = g.kperp_norm ? 1.0 : kperp * kperp;
+    for (int entry = blockIdx.x; entry < cnt; entry += gridDim.x) {
+      const int ecode = rwork[(size_t)etile * 2 * n_om + entry];
+      const int iom = ecode >> 1, sg = ecode & 1;
+      const cd omc = mk(om[2 * iom], om[2 * iom + 1]);
+      c.om = omc;
+      const double nn = sg ? -(double)nabs : (double)nabs;
+      const double nqv = nn * qs * vA / (kpar * ms);
+      Six2 Sd, acc;
+      zero6(Sd);
+      // rows interleaved over the warps (warp w: rows 1 + w, 1 + w + nwarps, ...): the rows that need a principal part
+      // cluster in Gamma, so consecutive blocks per warp would leave the warps unevenly loaded
+      for (int b = 0; 1 + warp + nwarps * b <= ng - 1; b += 32) {
+        // one row per lane: limits of integrate_resU_rel
+        const int myig = 1 + warp + nwarps * (b + lane);
+        RelRow r;
+        r.ires = 0; r.pv = 0; r.upperlimit = 0;
+        if (myig <= ng - 1) {
+          const double g1 = sp.grel[myig];
+          const double presx = (g1 * omc.x) * vA / kpar - nqv;
+          if (!rel_row_limits(sp, npb, M_I, presx, g1, sp.cone_lo[myig], sp.cone_up[myig], r)) {
+            err_flag[0] = 8;   // alps_error(8)
+            r.pv = 0;
+          }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, r.pv != 0);
+        while (todo) {
+          const int l = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int ig = 1 + warp + nwarps * (b + l);
+          const int ires = __shfl_sync(0xffffffffu, r.ires, l), upper = __shfl_sync(0xffffffffu, r.upperlimit, l);
+          pv_row(c, g, sp, omc, sg, nn, ig, ires, upper, (ig == ng - 1) ? 1.0 : 2.0, s_win[warp], lane, Sd);
+        }
+      }
+      moments_to_modes(c, nn, Sd, acc);
+#pragma unroll
+      for (int q = 0; q < 6; q++) acc.v[q] = (sp.dgamma * 0.25) * acc.v[q];
+      if (omc.y <= 0.0) landau_rows(c, g, sp, omc, sg, nn, tid, REL_THREADS, s_rfact, s_rgam, acc);
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        cd v = warp_sum_cd(acc.v[q]);
+        if (lane == 0) s_red[warp][q] = v;
+      }
+      __syncthreads();
+      if (tid < 6) {
+        cd t = mk(0.0, 0.0);
+        for (int w = 0; w < nwarps; w++) t += s_red[w][tid];
+        double* o = Mrel + ((size_t)iom * g.NI + sp.item_base + 2 * nabs + sg) * 12;
+        o[2 * tid] = t.x;
+        o[2 * tid + 1] = t.y;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // Bessel factors of int_T_rel (src/ALPS_fns_rel.f90:1297-1322) depend on (igamma, ipparbar) through
 // pperpbar = sqrt(gamma^2 - 1 - pparbar^2) but not on omega: tabulated once per k with the same literal BESSJ.
 // Planes 0..nmaxord hold J_n, plane nmaxord + 1 holds pperpbar.
@@ -1174,11 +1317,11 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
   if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
   static const char* force = getenv("ALPS_B200_REL_MINB");   // A/B knob: "1" = 255-register variant always
   if (nsplit > 1 || n_om * ntiles <= 2 * 148 || (force && force[0] == '1'))
-    launch_chain(k_rel<1, 0>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
-                 err_flag, nsplit, Mpart, tickets, nullptr, nullptr);
+    launch_chain(k_rel<1>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
+                 err_flag, nsplit, Mpart, tickets);
   else
-    launch_chain(k_rel<2, 0>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
-                 err_flag, nsplit, Mpart, tickets, nullptr, nullptr);
+    launch_chain(k_rel<2>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
+                 err_flag, nsplit, Mpart, tickets);
 }
 // throughput class: resonance flags + work list, principal-value / Landau parts of the listed entries, omega-tiled rest
 // (three launches; rflag: n_om * ntiles bytes, rwork: 2 * n_om * ntiles ints, rcount: one int)
@@ -1189,15 +1332,12 @@ void launch_rel_tiled(const GlobalDev* g, const double* om, int n_om, const RelT
   cudaMemsetAsync(rcount, 0, (size_t)ntiles * sizeof(int), st);
   const int warps = n_om * ntiles;
   k_rel_plan<<<(warps + 7) / 8, 256, 0, st>>>(g, om, n_om, tiles, ntiles, rflag, rwork, rcount, rpos);
-  static const char* pvb = getenv("ALPS_B200_REL_PV_MINB");   // A/B knob: "1" = 255 registers, one CTA per SM (measured
-                                                              // C3, 2048 omegas: 145 k D/s against 151 k with two)
+  static const char* pvb = getenv("ALPS_B200_REL_PV_MINB");   // A/B knob: "1" = 255 registers, one CTA per SM
   const int sms = sm_count > 0 ? sm_count : 148;
-  if (!(pvb && pvb[0] == '1'))
-    k_rel<2, 1><<<2 * sms, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, 1, nullptr, nullptr, rwork,
-                                                 rcount);
+  if (pvb && pvb[0] == '1')
+    k_rel_pv<1><<<sms, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, rwork, rcount);
   else
-    k_rel<1, 1><<<sms, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, 1, nullptr, nullptr, rwork,
-                                             rcount);
+    k_rel_pv<2><<<2 * sms, REL_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, Mrel, err_flag, rwork, rcount);
   k_rel_direct<<<dim3((2 * n_om + RT_THREADS - 1) / RT_THREADS, ntiles, nsplitB), RT_THREADS, 0, st>>>(
       g, om, n_om, tiles, ntiles, rwork, rcount, dpart, nsplitB, err_flag);
   k_rel_tiled<<<dim3((n_om + RT_THREADS - 1) / RT_THREADS, ntiles), RT_THREADS, 0, st>>>(g, om, n_om, tiles, ntiles, rflag,

@@ -16,5 +16,5 @@ for r in rows[hi+1:]:
 for k,v in agg.items():
     if 'rel' in k: print("%-50s n=%3d last=%10.1f us" % (k, len(v), v[-1]/1e3))
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_rel$' -s 1 -c 1 -f -o gpurun_out/r02g_k_rel_pv \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^k_rel_pv' -s 1 -c 1 -f -o gpurun_out/r02g_k_rel_pv \
   python scripts/prof_rel.py 2048 > gpurun_out/r02g_ncu.log 2>&1; tail -1 gpurun_out/r02g_ncu.log
