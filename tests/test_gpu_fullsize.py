@@ -73,3 +73,38 @@ def test_full_size_properties_nmax_200(c5):
         assert np.max(np.abs(Df - D) / np.abs(D)) < 1e-10
     finally:
         sol.close()
+
+
+def test_harmonic_shard_after_an_unsharded_small_batch(c5):
+    """the p_par split of small batches depends on the tile list, which a harmonic shard shrinks without
+    changing NI -- the partial-sum rows (Sbulk) allocated for the unsharded split were too few for the sharded one
+    (64 omegas x 16 splits against 64 x 7: an out-of-bounds device write).  Sequence of the report, at full size: set_k,
+    a 64-omega batch, set_harmonic_shard(r, 4), set_k, chi partials of 64 omegas; the shards must add up to the
+    unsharded partials (and compute-sanitizer stays silent, scripts/gpu_sanitizer.sh)."""
+    import torch
+    from alps_b200.solver import Solver
+    rng = np.random.default_rng(9)
+    oms = rng.uniform(0.05, 3.05, 64) + 1j * rng.uniform(-0.05, 0.05, 64)
+    sol = Solver(c5, nmax_force=200)
+    try:
+        sol.set_stream(torch.cuda.current_stream().cuda_stream)
+        sol.set_k(KPERP, KPAR)
+        D = sol.disp_batch(oms)                         # allocates the batch buffers for the unsharded split
+        n, L = oms.size, sol.chi_partial_len()
+        om_d = torch.from_numpy(oms.view(np.float64).copy()).cuda()
+        full = torch.zeros(n * L, dtype=torch.float64, device="cuda")
+        sol.chi_partial_dev(n, om_d.data_ptr(), full.data_ptr())
+        acc = torch.zeros_like(full)
+        for rank in range(4):
+            sol.set_harmonic_shard(rank, 4)
+            sol.set_k(KPERP, KPAR)
+            part = torch.zeros_like(full)
+            sol.chi_partial_dev(n, om_d.data_ptr(), part.data_ptr())
+            torch.cuda.synchronize()
+            acc += part
+        assert float((acc - full).abs().max()) <= 1e-12 * float(full.abs().max())
+        sol.set_harmonic_shard(0, 1)
+        sol.set_k(KPERP, KPAR)
+        assert np.array_equal(sol.disp_batch(oms).view(np.float64), D.view(np.float64))
+    finally:
+        sol.close()

@@ -368,3 +368,38 @@ def test_cli_map_search_with_hoisted_map_mode(tmp_path):
     assert a[1] == b[1]
     assert np.array_equal(a[0][:, :2], b[0][:, :2])
     assert np.max(np.abs(a[0][:, 3:] - b[0][:, 3:])) <= 1e-6 * np.max(np.abs(a[0][:, 3:]))     # 7 printed digits
+
+
+def test_calc_eigen_with_a_drifting_use_bM_species():
+    """derivative_f0 sets current_int(is) = ns qs bM_pdrifts / ms for use_bM species
+    (src/ALPS_fns.f90:161-166); calc_eigen uses it as the parallel flow, so U_z and the density fluctuation of a
+    drifting bi-Maxwellian species depend on it.  tests/test_bimax.in with a proton drift: the C++ twin of calc_eigen
+    on the GPU path against the oracle's restatement (oracle/driver.py)."""
+    from alps_b200.solver import Solver
+    from oracle import driver
+    from oracle.oracle import Oracle
+    pl = tables.config_bimax(60, 120)
+    pl.species[0].bM_pdrifts = 0.35
+    kperp, kpar = 1.0e-3, 3.0e-2
+    om = 3.0e-2 - 1.0e-5j
+    sol = Solver(pl)
+    orc = Oracle(pl)
+    try:
+        sol.set_k(kperp, kpar)
+        orc.set_k(kperp, kpar)
+        ci = sol.current_int()
+        assert abs(ci[0] - 0.35) < 1e-15
+        got = sol.calc_eigen(om)
+        ns = [s.ns for s in pl.species]
+        qs = [s.qs for s in pl.species]
+        e, b, Us, ds, Ps, W = driver.calc_eigen(orc, om, kperp, kpar, pl.vA, ns, qs, current_int=ci)[:6]
+        rel = lambda a, r: np.max(np.abs(np.asarray(a) - np.asarray(r))) / np.max(np.abs(np.asarray(r)))
+        assert rel(got["ef"], e) < 1e-8 and rel(got["bf"], b) < 1e-8
+        assert rel(got["Us"].T, Us) < 1e-8 and rel(got["ds"], ds) < 1e-8
+        # the drift matters: without it the parallel velocity fluctuation of the protons differs (their density
+        # fluctuation does not: the flow cancels out of (U_x k_perp + U_z k_par) / (omega - k_par V) algebraically)
+        e0, b0, Us0, ds0 = driver.calc_eigen(orc, om, kperp, kpar, pl.vA, ns, qs, current_int=np.array([0.0, ci[1]]))[:4]
+        assert abs(Us0[0, 2] - Us[0, 2]) > 0.1 * abs(Us[0, 2])
+        assert abs(got["Us"][2, 0] - Us[0, 2]) < 1e-8 * abs(Us[0, 2])
+    finally:
+        sol.close()
