@@ -154,6 +154,16 @@ struct State {
   CUresult (*encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+  // HARMONIC partition: besides this process' / device's shard view (tiles, rtiles, gd) the UNSHARDED view of the same
+  // tables, for calls that are not worth a reduction over NVLink (a few omegas of a small configuration)
+  std::vector<QuadTile> tiles_full;
+  std::vector<RelTile> rtiles_full;
+  QuadTile* d_tiles_full = nullptr;
+  RelTile* d_rtiles_full = nullptr;
+  GlobalDev* gd_full = nullptr;
+  int ntiles_rem_shard = 0, ntiles_rem_full = 0;
+  bool have_full = false;    // built by set_k (shard_n > 1, DMMA variants)
+  bool view_full = false;    // the current call evaluates the unsharded view
   int class_n = 0;           // batch class override: omegas of the whole API call when a call is evaluated in pieces
                              // (internal chunks, device slices of a group, rank slices): the summation order then
                              // depends on the call, not on how it was cut
@@ -438,19 +448,59 @@ bool use_lat(int n) { return S.have_lat && S.mode == 0 && n <= LAT_BATCH; }
 int nsplit_small(int n) {
   const int bn = use_lat(n) ? LAT_BN : S.qv.bn;
   const int NT = (S.cfg.npar - 1 + bn - 1) / bn;
-  return std::max(1, std::min(NT, (2 * S.sm_count) / std::max(1, (int)S.tiles.size())));
+  const int nt = (int)(S.view_full ? S.tiles_full.size() : S.tiles.size());
+  return std::max(1, std::min(NT, (2 * S.sm_count) / std::max(1, nt)));
 }
 
+inline int cur_nrtiles() { return (int)(S.view_full ? S.rtiles_full.size() : S.rtiles.size()); }
+inline const RelTile* cur_rtiles() { return S.view_full ? S.d_rtiles_full : S.d_rtiles; }
+inline const GlobalDev* cur_gd() { return S.view_full ? S.gd_full : S.gd; }
 int nsplit_rel() {
-  if (S.rtiles.empty()) return 1;
-  return std::max(1, std::min(16, (2 * S.sm_count + (int)S.rtiles.size() - 1) / (int)S.rtiles.size()));
+  if (cur_nrtiles() == 0) return 1;
+  return std::max(1, std::min(16, (2 * S.sm_count + cur_nrtiles() - 1) / cur_nrtiles()));
 }
+// point the launch parameters at the shard view or at the unsharded one (S.view_full)
+void apply_view() {
+  S.P.tiles = S.view_full ? S.d_tiles_full : S.d_tiles;
+  S.P.ntiles = (int)(S.view_full ? S.tiles_full.size() : S.tiles.size());
+  S.P.ntiles_rem = S.view_full ? S.ntiles_rem_full : S.ntiles_rem_shard;
+  S.P.g = cur_gd();
+  if (S.have_lat) {
+    S.Plat.tiles = S.P.tiles;
+    S.Plat.ntiles = S.P.ntiles;
+    S.Plat.ntiles_rem = S.P.ntiles_rem;
+    S.Plat.g = S.P.g;
+  }
+}
+// one call in the unsharded view
+struct ViewScope {
+  bool on;
+  explicit ViewScope(bool full) : on(full && !S.view_full) {
+    if (on) {
+      S.view_full = true;
+      apply_view();
+    }
+  }
+  ~ViewScope() {
+    if (on) {
+      S.view_full = false;
+      apply_view();
+    }
+  }
+};
 
 // Sbulk rows per item: n * nsplit(n) <= max(B, SMALL_BATCH * nsplit_small(SMALL_BATCH), LAT_BATCH * nsplit_small(1)).
 // nsplit_small depends on the tile list (harmonic shard, mode, latency variant), not only on NI: bind_batch checks
 // the allocation against the current value before every use.
 size_t sbulk_rows_needed(size_t B) {
-  return std::max({B, (size_t)SMALL_BATCH * nsplit_small(SMALL_BATCH), (size_t)LAT_BATCH * nsplit_small(1)});
+  size_t need = B;
+  const bool keep = S.view_full;
+  for (int v = 0; v < (S.have_full ? 2 : 1); v++) {      // the shard view and, if there is one, the unsharded view
+    S.view_full = v == 1;
+    need = std::max({need, (size_t)SMALL_BATCH * nsplit_small(SMALL_BATCH), (size_t)LAT_BATCH * nsplit_small(1)});
+  }
+  S.view_full = keep;
+  return need;
 }
 
 int ensure_batch(int want) {
@@ -572,6 +622,7 @@ int prepare_external(int n, const double* d_om, const double** d_ext_out) {
 
 bool comm_harmonic();                                           // multi-process harmonic partition (bottom of the file)
 bool comm_omega_active();
+bool harmonic_small(int n);                                     // HARMONIC partition: this call is evaluated unsharded
 bool group_harmonic_active();                                   // device group of this process: partition in use
 bool group_omega_active();
 int group_harmonic_eval(int n, const double* om, double* D, double* chi0, double* chi0_low, double* wave);
@@ -587,7 +638,7 @@ int comm_allreduce_partials(double* d_partial, size_t count);    // ncclAllReduc
 // run the hot path for n omegas already on the device (n <= S.batch)
 int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, const double* d_partial_in,
               bool want_aux) {
-  const GlobalDev* gd = S.gd;
+  const GlobalDev* gd = cur_gd();
   // batch class (summation order): that of the whole API call when this chunk is a piece of one (S.class_n)
   const int cn = S.class_n > 0 ? std::max(S.class_n, n) : n;
   if (!d_partial_out && !S.capturing) S.d_evals += n;
@@ -628,7 +679,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       S.launches += 1;   // regular tiles + packed remainder tiles: two launches of k_quad_mma
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.d_respart,
                     S.d_restick, S.stream, S.reslat_gx, cn);
-    if (!S.rtiles.empty()) {
+    if (cur_nrtiles() > 0) {
       // few omegas in flight: spread each (omega, species, |n|) over several CTAs (configuration-only
       // rule, like nsplit_small, so disp() and a small disp_batch() stay bitwise identical)
       const int rsplit = (cn <= SMALL_BATCH) ? nsplit_rel() : 1;
@@ -636,7 +687,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       for (int s = 0; s < S.cfg.nspec; s++) tables = tables && (!S.gh.sp[s].relativistic || S.gh.sp[s].Jrel != nullptr);
       // Gamma splits of the direct part: enough CTAs to fill the GPU when only a few harmonics are resonant (the usual
       // case), within 512 MB of partial rows
-      const size_t nt = S.rtiles.size();
+      const size_t nt = (size_t)cur_nrtiles();
       int nsB = std::max(1, std::min(32, (int)((6 * 128 * (size_t)S.sm_count / 2 + n - 1) / n)));
       while (nsB > 1 && nt * 2 * n * nsB * 96 > ((size_t)512 << 20)) nsB--;
       const size_t need = nt * 2 * (size_t)n * nsB * 12;
@@ -645,11 +696,11 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
           if (dalloc(&S.d_reldpart, need)) return ALPS_B200_ERR_CUDA;
           S.reldpart_cap = need;
         }
-        launch_rel_tiled(gd, d_om, n, S.d_rtiles, (int)nt, S.d_Sres, S.d_err + 6, S.d_relflag, S.d_relwork, S.d_relcount,
+        launch_rel_tiled(gd, d_om, n, cur_rtiles(), (int)nt, S.d_Sres, S.d_err + 6, S.d_relflag, S.d_relwork, S.d_relcount,
                          S.d_relpos, S.d_reldpart, nsB, S.sm_count, S.stream);
         S.launches += 4;
       } else {
-        launch_rel(gd, d_om, n, S.d_rtiles, (int)S.rtiles.size(), S.d_Sres, S.d_err + 6, rsplit, S.d_relpart,
+        launch_rel(gd, d_om, n, cur_rtiles(), cur_nrtiles(), S.d_Sres, S.d_err + 6, rsplit, S.d_relpart,
                    S.d_reltick, S.stream);
         S.launches += 1;
       }
@@ -871,9 +922,25 @@ void group_stop_workers() {
   G.p2p = false;
 }
 
-bool comm_harmonic() { return G.comm != nullptr && G.nranks > 1 && G.partition == ALPS_B200_PARTITION_HARMONIC; }
+bool comm_harmonic() {
+  return G.comm != nullptr && G.nranks > 1 && G.partition == ALPS_B200_PARTITION_HARMONIC && !S.view_full;
+}
 bool comm_omega_active() { return G.comm != nullptr && G.nranks > 1 && G.partition == ALPS_B200_PARTITION_OMEGA; }
-bool group_harmonic_active() { return group_forward() && G.partition == ALPS_B200_PARTITION_HARMONIC; }
+bool group_harmonic_active() {
+  return group_forward() && G.partition == ALPS_B200_PARTITION_HARMONIC && !S.view_full;
+}
+// HARMONIC partition, a few omegas of a small configuration: one D is tens of microseconds of latency-bound work and
+// sharding it costs more than it saves (measured, C4: 61 us on one GPU against >= 105 us over 8) -- such calls are
+// evaluated in the unsharded view, on device 0 of a group / redundantly on every rank, without any exchange.  "Small":
+// fewer than 2e8 point-harmonics per D (C1 2e6, C4 7e6, C5 2.5e9: a single C5 D IS worth sharding, 812 -> 325 us).
+bool harmonic_small(int n) {
+  if (G.partition != ALPS_B200_PARTITION_HARMONIC || !(G.ngpu > 1 || (G.comm != nullptr && G.nranks > 1))) return false;
+  if (tl_worker || !S.have_full || S.mode != 0 || n > LAT_BATCH) return false;
+  double ph = 0.0;
+  for (int s = 0; s < S.cfg.nspec; s++)
+    if (S.sp[s].grid) ph += (2.0 * S.gh.sp[s].nhi + 1.0) * (S.cfg.nperp - 1.0) * (S.cfg.npar - 1.0);
+  return ph < 2.0e8;
+}
 bool group_omega_active() { return group_forward() && G.partition == ALPS_B200_PARTITION_OMEGA; }
 
 int comm_allreduce_partials(double* d_partial, size_t count) {
@@ -1062,6 +1129,10 @@ void alps_b200_finalize(void) {
   dfree(&S.d_pp_f); dfree(&S.d_df0_f); dfree(&S.gd); dfree(&S.d_work_count); dfree(&S.d_err);
   dfree(&S.d_tiles);
   dfree(&S.d_rtiles);
+  dfree(&S.d_tiles_full);
+  dfree(&S.d_rtiles_full);
+  dfree(&S.gd_full);
+  S.have_full = S.view_full = false;
   dfree(&S.d_fitems);
   dfree(&S.d_om_i);
   dfree(&S.d_nh);
@@ -1476,7 +1547,7 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
     std::stable_partition(S.tiles.begin(), S.tiles.end(), [&](const QuadTile& t) { return !is_rem(t); });
     for (const QuadTile& t : S.tiles) ntiles_rem += is_rem(t) ? 1 : 0;
   }
-  S.P.ntiles_rem = ntiles_rem;
+  S.ntiles_rem_shard = ntiles_rem;
   const bool ni_changed = item_base != S.gh.NI;
   S.gh.NI = item_base;
   CK(cudaMemcpyAsync(S.gd, &S.gh, sizeof(GlobalDev), cudaMemcpyHostToDevice, S.stream));
@@ -1485,12 +1556,44 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
     CK(cudaMemcpyAsync(S.d_rtiles, S.rtiles.data(), S.rtiles.size() * sizeof(RelTile), cudaMemcpyHostToDevice, S.stream));
   if (!S.tiles.empty())
     CK(cudaMemcpyAsync(S.d_tiles, S.tiles.data(), S.tiles.size() * sizeof(QuadTile), cudaMemcpyHostToDevice, S.stream));
+  // the unsharded view of a harmonic shard (DMMA variants): all harmonics of every species, its own GlobalDev
+  S.have_full = false;
+  S.view_full = false;
+  S.tiles_full.clear();
+  S.rtiles_full.clear();
+  S.ntiles_rem_full = 0;
+  if (S.shard_n > 1 && mma) {
+    GlobalDev gf = S.gh;
+    for (int s = 0; s < nspec; s++) {
+      gf.sp[s].nlo_shard = 0;
+      gf.sp[s].nhi_shard = gf.sp[s].nhi;
+      if (!S.sp[s].grid) continue;
+      if (gf.sp[s].relativistic) {
+        for (int n = 0; n <= gf.sp[s].nhi; n++) S.rtiles_full.push_back(RelTile{s, n});
+        continue;
+      }
+      for (int n0 = 0; n0 <= gf.sp[s].nhi; n0 += MMA_NH) S.tiles_full.push_back(QuadTile{s, n0});
+    }
+    if (!no_pack) {
+      auto is_rem = [&](const QuadTile& t) { return gf.sp[t.s].nhi_shard <= t.n0 + 9; };
+      std::stable_partition(S.tiles_full.begin(), S.tiles_full.end(), [&](const QuadTile& t) { return !is_rem(t); });
+      for (const QuadTile& t : S.tiles_full) S.ntiles_rem_full += is_rem(t) ? 1 : 0;
+    }
+    if (!S.gd_full && dalloc(&S.gd_full, 1)) return ALPS_B200_ERR_CUDA;
+    if (dalloc(&S.d_tiles_full, S.tiles_full.size()) || dalloc(&S.d_rtiles_full, S.rtiles_full.size()))
+      return ALPS_B200_ERR_CUDA;
+    CK(cudaMemcpyAsync(S.gd_full, &gf, sizeof(GlobalDev), cudaMemcpyHostToDevice, S.stream));
+    if (!S.tiles_full.empty())
+      CK(cudaMemcpyAsync(S.d_tiles_full, S.tiles_full.data(), S.tiles_full.size() * sizeof(QuadTile),
+                         cudaMemcpyHostToDevice, S.stream));
+    if (!S.rtiles_full.empty())
+      CK(cudaMemcpyAsync(S.d_rtiles_full, S.rtiles_full.data(), S.rtiles_full.size() * sizeof(RelTile),
+                         cudaMemcpyHostToDevice, S.stream));
+    S.have_full = true;
+  }
   CK(cudaStreamSynchronize(S.stream));
   CK(cudaGetLastError());
   if (ni_changed) free_batch();
-  S.P.tiles = S.d_tiles;
-  S.P.ntiles = (int)S.tiles.size();
-  S.P.g = S.gd;
   S.have_lat = lat && !S.tiles.empty();
   if (S.have_lat) {
     memcpy(&S.Plat, &S.P, sizeof(QuadParams));
@@ -1499,6 +1602,7 @@ int alps_b200_set_k(double kperp, double kpar, int* nmax_out) {
       S.Plat.Cf[s] = Cfs[s];
     }
   }
+  apply_view();
   S.have_k = true;
   S.nh_dirty = S.bm_any;
   if (S.mode == 1) {
@@ -1616,6 +1720,7 @@ int alps_b200_disp_batch_full(int n, const double* om, double* D, double* chi0_o
   if (n <= 0) return 0;
   if (!om || !D) return fail(ALPS_B200_ERR_USAGE, "om / D is NULL");
   const bool aux = chi0_opt || chi0_low_opt || wave_opt;
+  ViewScope view(harmonic_small(n));
   // partitions over the GPUs of the box (bottom of the file): device group of this process, or one process per GPU
   if (group_harmonic_active()) return group_harmonic_eval(n, om, D, chi0_opt, chi0_low_opt, wave_opt);
   if (group_omega_active() && n > LAT_BATCH) return group_omega_eval(n, om, D, chi0_opt, chi0_low_opt, wave_opt);
@@ -1633,10 +1738,10 @@ static void disp_signature(std::vector<unsigned char>& sig, int n) {
   P.om = S.d_om;
   P.n_om = n;
   P.nsplit = (S.mode == 1) ? 1 : nsplit_small(n);
-  const void* ptrs[] = {S.stream, S.gd, S.d_om, S.d_D, S.d_plan, S.d_work, S.d_work_count, S.d_Sbulk, S.d_Sres,
-                        S.d_gwin, S.d_partial, S.d_err, S.d_rtiles, S.d_fitems, S.d_respart, S.d_restick,
+  const void* ptrs[] = {S.stream, cur_gd(), S.d_om, S.d_D, S.d_plan, S.d_work, S.d_work_count, S.d_Sbulk, S.d_Sres,
+                        S.d_gwin, S.d_partial, S.d_err, cur_rtiles(), S.d_fitems, S.d_respart, S.d_restick,
                         S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
-  const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)S.rtiles.size(), (long long)S.fitems.size(), S.mode,
+  const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)cur_nrtiles(), (long long)S.fitems.size(), S.mode,
                             S.qv.id, S.fast_variant, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off,
                             (long long)S.pdl_on, (long long)S.reslat_gx, (long long)n};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
@@ -1725,6 +1830,7 @@ int alps_b200_disp(const double om[2], double D[2], double* chi0, double* chi0_l
   int rc = check_ready();
   if (rc) return rc;
   if (!om) return fail(ALPS_B200_ERR_USAGE, "om is NULL");
+  ViewScope view(harmonic_small(1));
   if (group_harmonic_active()) {
     double Dl[2];
     return group_harmonic_eval(1, om, D ? D : Dl, chi0, chi0_low, wave);

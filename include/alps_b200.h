@@ -156,6 +156,9 @@ int alps_b200_tps_eval(int n, const double *gc, const double *pc, const double *
  *             reads its peers' buffers (peer memory; ALPS_B200_REDUCE=nccl: ncclAllReduce), (b) ncclAllReduce on the
  *             library's stream -- and D is assembled from the sum.  Pays when one D is much more than ~100 us of GPU
  *             work (C5-sized tables); for the shipped configs the OMEGA partition is the faster one.
+ *             Calls of at most 8 omegas on a configuration with fewer than 2e8 point-harmonics per D are therefore
+ *             evaluated UNSHARDED (device 0 of a group / redundantly on every rank, no exchange): a single disp() under
+ *             this partition is never slower than on one GPU, and bitwise the one-GPU value.
  * The result of a call does not depend on how it was cut: every piece sums in the order of the whole call's batch
  * class, so ngpu = N and ngpu = 1 (and N ranks vs one) give bitwise identical D under the OMEGA partition. */
 #define ALPS_B200_PARTITION_OMEGA 0

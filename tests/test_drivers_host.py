@@ -67,3 +67,33 @@ def test_scan_setup_matches_scan_read(built_lib):
     sc = _lib.ScanCfg()
     assert L.alps_b200_scan_setup(7, 1.0, 1.0, 0, 1, 1, 0, 0, C.byref(C.c_double(1.0)), C.byref(C.c_double(1.0)),
                                   C.byref(sc)) != 0
+
+
+def test_omega_slices_partition_the_batch(built_lib):
+    """alps_b200_omega_slice (host only): the contiguous slices of the OMEGA partition tile [0, n) exactly, differ in
+    size by at most one, and agree with alps_b200/sharding.py's omega_shard (the gloo tests' twin)."""
+    from alps_b200 import sharding
+    L = _lib.lib()
+    for n in (0, 1, 7, 8, 9, 64, 65, 1000, 262144):
+        for parts in (1, 2, 3, 8):
+            prev, sizes = 0, []
+            for r in range(parts):
+                lo, hi = C.c_int(-1), C.c_int(-1)
+                assert L.alps_b200_omega_slice(n, r, parts, C.byref(lo), C.byref(hi)) == 0
+                assert lo.value == prev and hi.value >= lo.value
+                assert (lo.value, hi.value) == sharding.omega_shard(n, r, parts)
+                sizes.append(hi.value - lo.value)
+                prev = hi.value
+            assert prev == n and max(sizes) - min(sizes) <= 1
+    lo, hi = C.c_int(0), C.c_int(0)
+    assert L.alps_b200_omega_slice(10, 3, 3, C.byref(lo), C.byref(hi)) != 0       # rank out of range
+
+
+def test_partition_and_communicator_calls_need_an_initialised_library(built_lib):
+    """no GPU here: the multi-GPU entry points refuse to act before alps_b200_init instead of touching a device"""
+    L = _lib.lib()
+    assert L.alps_b200_set_partition(_lib.PARTITION_HARMONIC) == -2
+    buf = (C.c_char * 128)()
+    assert L.alps_b200_comm_init(0, 2, buf) == -2
+    assert L.alps_b200_comm_finalize() == 0
+    assert b"alps_b200_init" in L.alps_b200_last_error()
