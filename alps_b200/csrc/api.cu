@@ -985,16 +985,18 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
       });
       if (!rc) {
         // peer access for the harmonic partition's sum over NVLink (device 0 reads its peers' partial rows)
+        static unsigned long long peer_on[64] = {0};   // peer access stays enabled for the life of the process
         bool p2p = true;
         for (int d = 1; d < G.ngpu && p2p; d++) {
           int can = 0;
           p2p = cudaDeviceCanAccessPeer(&can, base, base + d) == cudaSuccess && can;
-          if (p2p) {
+          if (p2p && base < 64 && base + d < 64 && !((peer_on[base] >> (base + d)) & 1ull)) {
             const cudaError_t e = cudaDeviceEnablePeerAccess(base + d, 0);
             p2p = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+            if (e != cudaSuccess) cudaGetLastError();
+            if (p2p) peer_on[base] |= 1ull << (base + d);
           }
         }
-        cudaGetLastError();
         G.p2p = p2p;
         const char* r = getenv("ALPS_B200_REDUCE");
         G.reduce_nccl = !p2p || (r && !strcmp(r, "nccl"));
