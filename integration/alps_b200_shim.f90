@@ -18,7 +18,7 @@ module alps_b200_shim
   use iso_c_binding
   implicit none
   private
-  public :: b200_setup, b200_set_k, b200_disp, b200_map, b200_finalize, b200_ngpu
+  public :: b200_setup, b200_set_k, b200_disp, b200_map, b200_finalize, b200_ngpu, b200_join_ranks
 
   type, bind(c) :: alps_b200_cfg            ! include/alps_b200.h : alps_b200_cfg
      integer(c_int) :: nspec, nperp, npar, ngamma, npparbar
@@ -77,6 +77,18 @@ module alps_b200_shim
        import; integer(c_int), value :: n, npts
        real(c_double), intent(in) :: gc(*), pc(*), w(*), gx(*), px(*)
        real(c_double) :: out(*)
+     end function
+     integer(c_int) function alps_b200_comm_unique_id(id) bind(c)
+       import; character(kind=c_char) :: id(128)
+     end function
+     integer(c_int) function alps_b200_comm_init(rank, nranks, id) bind(c)
+       import; integer(c_int), value :: rank, nranks; character(kind=c_char), intent(in) :: id(128)
+     end function
+     integer(c_int) function alps_b200_comm_finalize() bind(c)
+       import
+     end function
+     integer(c_int) function alps_b200_set_partition(kind) bind(c)
+       import; integer(c_int), value :: kind
      end function
   end interface
 
@@ -163,6 +175,29 @@ contains
   subroutine b200_finalize()
     call alps_b200_finalize()
   end subroutine b200_finalize
+
+  !> One GPU per MPI rank (the reference's own SPMD layout: every rank runs the same driver and calls disp collectively,
+  !> src/ALPS.f90:107-133).  Call after b200_setup on EVERY rank, with cfg%device = the rank's local GPU (set
+  !> ALPS_B200_DEVICE or edit b200_setup) and cfg%ngpu = 1: rank 0 draws the NCCL id, MPI broadcasts its 128 bytes, every
+  !> rank joins the library's communicator.  From then on b200_map (alps_b200_disp_batch) is collective -- every rank
+  !> evaluates a slice, one ncclAllGather inside the library, every rank gets all of cal -- while single b200_disp calls
+  !> are evaluated by every rank for itself (bitwise the same D everywhere, no exchange).  Replaces split_processes and
+  !> the MPI_REDUCE pair of disp (src/ALPS_fns.f90:4079-4207, 519-523).
+  subroutine b200_join_ranks()
+    use alps_var, only : iproc, nproc
+    use alps_io, only : alps_error
+    use mpi
+    character(kind=c_char) :: id(128)
+    integer :: ierr, ierror
+    id = c_null_char
+    if (iproc == 0) then
+       ierr = alps_b200_comm_unique_id(id)
+       if (ierr /= 0) call alps_error(ierr)
+    endif
+    call mpi_bcast(id, 128, MPI_CHARACTER, 0, MPI_COMM_WORLD, ierror)
+    ierr = alps_b200_comm_init(iproc, nproc, id)
+    if (ierr /= 0) call alps_error(ierr)
+  end subroutine b200_join_ranks
 
   !> Devices the library should drive from this (single) calling rank: environment variable ALPS_B200_NGPU,
   !> default 1.  With ngpu > 1 nothing else changes on the Fortran side: b200_map's batch is cut into one slice
