@@ -93,7 +93,8 @@ struct State {
   bool zc = false, zc_off = false;   // zero-copy chain while capturing: omega read from / D and the error words written to
                                      // pinned host memory by the first / last kernel (no memcpy or memset nodes)
   double* d_respart = nullptr;   // k_resonant_lat partial rows (small batches)
-  int* d_restick = nullptr;
+  int* d_plan_flag = nullptr;    // k_plan's completion flag (single-omega chain, resonant.cu)
+  bool early_off = false;        // ALPS_B200_EARLY=0: the Landau blocks wait for their predecessor like the others
   double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
   int* d_reltick = nullptr;
   unsigned char* d_relflag = nullptr;   // throughput class of the relativistic species: resonance flags per (omega, tile),
@@ -270,7 +271,7 @@ void free_batch() {
   drop_disp_graph();
   dfree(&S.d_om); dfree(&S.d_D); dfree(&S.d_Sbulk); dfree(&S.d_Sres); dfree(&S.d_gwin); dfree(&S.d_partial);
   dfree(&S.d_chi0); dfree(&S.d_chi0_low); dfree(&S.d_wave); dfree(&S.d_plan); dfree(&S.d_work); dfree(&S.d_ext);
-  dfree(&S.d_relpart); dfree(&S.d_reltick); dfree(&S.d_respart); dfree(&S.d_restick);
+  dfree(&S.d_relpart); dfree(&S.d_reltick); dfree(&S.d_respart);
   dfree(&S.d_relflag); dfree(&S.d_relwork); dfree(&S.d_relcount); dfree(&S.d_relpos); dfree(&S.d_reldpart);
   S.reldpart_cap = 0;
   S.batch = 0;
@@ -440,7 +441,7 @@ int build_hoisted_tables() {
 constexpr int SMALL_BATCH = 64;
 // defaults of the latency knobs (ALPS_B200_ZC / _FUSE / _PDL): zero-copy graph chain, fused harmonic-sum +
 // determinant kernel, programmatic dependent launches inside the graph
-constexpr bool LAT_DEFAULT_ZC = true, LAT_DEFAULT_FUSE = true, LAT_DEFAULT_PDL = false;
+constexpr bool LAT_DEFAULT_ZC = true, LAT_DEFAULT_FUSE = true, LAT_DEFAULT_PDL = true;
 constexpr int LAT_VARIANT = 20, LAT_BN = 32, LAT_NPAR_MAX = 1024, LAT_BATCH = 8;
 bool use_lat(int n) { return S.have_lat && S.mode == 0 && n <= LAT_BATCH; }
 // p_par split of the quadrature kernel for n <= SMALL_BATCH omegas; a function of the configuration and of
@@ -517,8 +518,7 @@ int ensure_batch(int want) {
     return ALPS_B200_ERR_CUDA;
   {
     const size_t nt = (size_t)std::min<size_t>(B, SMALL_BATCH) * NI;
-    if (dalloc(&S.d_respart, nt * RES_PART_DOUBLES) || dalloc(&S.d_restick, nt)) return ALPS_B200_ERR_CUDA;
-    CK(cudaMemsetAsync(S.d_restick, 0, nt * sizeof(int), S.stream));
+    if (dalloc(&S.d_respart, nt * RES_PART_DOUBLES)) return ALPS_B200_ERR_CUDA;
   }
   bool any_rel = false;
   for (int s = 0; s < S.cfg.nspec; s++) any_rel = any_rel || S.gh.sp[s].relativistic;
@@ -644,7 +644,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
   if (!d_partial_out && !S.capturing) S.d_evals += n;
   if (!d_partial_in) {
     launch_plan(gd, S.gh, S.zc ? S.h_pin : d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream,
-                S.zc ? S.d_om : nullptr);
+                S.zc ? S.d_om : nullptr, S.d_plan_flag);
     S.P.om = d_om;
     S.P.n_om = n;
     // few omegas in flight (sequential root finding, batched roots): spread each (omega, tile) over
@@ -655,7 +655,9 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     // throughput batches: the CTAs of one (species, harmonic group) tile are adjacent, so the SMs walk the same
     // species table and weight block together (working set in L2: one species instead of all of them)
     S.P.tile_major = (cn > SMALL_BATCH && !S.omega_major) ? 1 : 0;
+    const bool early = g_pdl_launch && S.zc && !S.early_off;   // flag-driven early starts inside the captured chain
     if (use_lat(cn)) {
+      S.Plat.done_ctr = (early && cur_nrtiles() == 0) ? S.d_plan_flag + 1 : nullptr;
       S.Plat.om = d_om;
       S.Plat.n_om = n;
       S.Plat.nsplit = S.P.nsplit;
@@ -677,8 +679,10 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     if (S.mode == 0 && !use_lat(cn) && S.qv.id == 15 && S.P.tile_major && S.P.ntiles_rem > 0 &&
         S.P.ntiles_rem < S.P.ntiles)
       S.launches += 1;   // regular tiles + packed remainder tiles: two launches of k_quad_mma
+    // small batches: the partial rows of k_resonant_lat feed the harmonic sums directly (no Sres)
+    const double* lat_rows = (resonant_lat_class(n, cn) && S.d_respart) ? S.d_respart : nullptr;
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.d_respart,
-                    S.d_restick, S.stream, S.reslat_gx, cn);
+                    S.stream, S.reslat_gx, cn, early ? S.d_plan_flag : nullptr);
     if (cur_nrtiles() > 0) {
       // few omegas in flight: spread each (omega, species, |n|) over several CTAs (configuration-only
       // rule, like nsplit_small, so disp() and a small disp_batch() stay bitwise identical)
@@ -711,14 +715,16 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       const double* d_ext = nullptr;
       int rc = prepare_external(n, d_om, &d_ext);
       if (rc) return rc;
-      launch_chi_assemble(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, part, d_ext,
+      launch_chi_assemble(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, lat_rows, part, d_ext,
                           S.zc ? S.h_pin + ZC_D : d_D, want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr,
                           want_aux ? S.d_wave : nullptr, S.stream, S.zc ? S.d_err : nullptr,
-                          S.zc ? reinterpret_cast<int*>(S.h_pin + ZC_ERR) : nullptr);
+                          S.zc ? reinterpret_cast<int*>(S.h_pin + ZC_ERR) : nullptr,
+                          (use_lat(cn) && S.Plat.done_ctr) ? S.Plat.done_ctr : nullptr,
+                          (use_lat(cn) && S.Plat.done_ctr) ? n * S.Plat.ntiles * S.Plat.nsplit : 0);
       S.launches += 4;
       return 0;
     }
-    launch_chi_partial(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, part, S.stream);
+    launch_chi_partial(gd, S.gh, d_om, n, S.d_plan, S.d_Sbulk, S.P.nsplit, S.d_Sres, lat_rows, part, S.stream);
     S.launches += 4;
     if (d_partial_out) return 0;
     if (comm_harmonic()) {
@@ -1043,6 +1049,16 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
     return fail(ALPS_B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   S.encodeTiled = (decltype(S.encodeTiled))fn;
   memset(&S.gh, 0, sizeof(S.gh));
+#ifdef ALPS_LAT_TRACE
+  {
+    unsigned long long* t = nullptr;
+    CK(cudaMalloc(&t, 64 * sizeof(unsigned long long)));
+    unsigned long long init[64];
+    for (int i = 0; i < 64; i++) init[i] = (i & 1) ? 0ULL : ~0ULL;
+    CK(cudaMemcpy(t, init, sizeof(init), cudaMemcpyHostToDevice));
+    S.gh.trace = t;
+  }
+#endif
   S.gh.nspec = cfg->nspec;
   S.gh.nperp = cfg->nperp;
   S.gh.npar = cfg->npar;
@@ -1057,7 +1073,12 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.gh.maxorder = cfg->maxorder;
   S.gh.vA = cfg->vA;
   S.gh.Tlim = cfg->Tlim;
-  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8)) return ALPS_B200_ERR_CUDA;
+  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8) || dalloc(&S.d_plan_flag, 2))
+    return ALPS_B200_ERR_CUDA;
+  {
+    const int init[2] = {1, 0};   // [0] "plan complete": only the fused k_plan of the single-omega chain ever clears it
+    CK(cudaMemcpy(S.d_plan_flag, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
   for (int s = 0; s < MAXSPEC; s++) S.bm[s] = BmParams();
   S.bm_any = false;
   S.nh_dirty = false;
@@ -1075,6 +1096,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
     S.memo_on = knob("ALPS_B200_MEMO", true);
     S.speculate_on = knob("ALPS_B200_SPECULATE", true);
     S.pdl_on = knob("ALPS_B200_PDL", LAT_DEFAULT_PDL);
+    S.early_off = !knob("ALPS_B200_EARLY", true);
     S.fuse_off = !knob("ALPS_B200_FUSE", LAT_DEFAULT_FUSE);
     S.zc_off = !knob("ALPS_B200_ZC", LAT_DEFAULT_ZC);
     S.omega_major = getenv("ALPS_B200_OMEGA_MAJOR") != nullptr;   // A/B knob: previous block order of k_quad_mma
@@ -1128,7 +1150,7 @@ void alps_b200_finalize(void) {
     h = SpeciesHost();
   }
   free_batch();
-  dfree(&S.d_pp_f); dfree(&S.d_df0_f); dfree(&S.gd); dfree(&S.d_work_count); dfree(&S.d_err);
+  dfree(&S.d_pp_f); dfree(&S.d_df0_f); dfree(&S.gd); dfree(&S.d_work_count); dfree(&S.d_err); dfree(&S.d_plan_flag);
   dfree(&S.d_tiles);
   dfree(&S.d_rtiles);
   dfree(&S.d_tiles_full);
@@ -1739,13 +1761,14 @@ static void disp_signature(std::vector<unsigned char>& sig, int n) {
   P.gwin = S.P.gwin;
   P.om = S.d_om;
   P.n_om = n;
+  P.done_ctr = nullptr;
   P.nsplit = (S.mode == 1) ? 1 : nsplit_small(n);
   const void* ptrs[] = {S.stream, cur_gd(), S.d_om, S.d_D, S.d_plan, S.d_work, S.d_work_count, S.d_Sbulk, S.d_Sres,
-                        S.d_gwin, S.d_partial, S.d_err, cur_rtiles(), S.d_fitems, S.d_respart, S.d_restick,
+                        S.d_gwin, S.d_partial, S.d_err, cur_rtiles(), S.d_fitems, S.d_respart, S.d_plan_flag,
                         S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
   const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)cur_nrtiles(), (long long)S.fitems.size(), S.mode,
                             S.qv.id, S.fast_variant, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off,
-                            (long long)S.pdl_on, (long long)S.reslat_gx, (long long)n};
+                            (long long)S.pdl_on, (long long)S.early_off, (long long)S.reslat_gx, (long long)n};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
   memcpy(sig.data(), &P, sizeof(P));
   memcpy(sig.data() + sizeof(P), ptrs, sizeof(ptrs));
@@ -2389,3 +2412,15 @@ int alps_b200_comm_finalize(void) {
 }
 
 }  // extern "C"
+
+#ifdef ALPS_LAT_TRACE
+// developer build only: fetch and re-arm the 64 time-stamp slots (even = earliest, odd = latest)
+extern "C" int alps_b200_debug_trace(unsigned long long* out) {
+  using namespace alps;
+  unsigned long long init[64];
+  if (out) cudaMemcpy(out, S.gh.trace, sizeof(init), cudaMemcpyDeviceToHost);
+  for (int i = 0; i < 64; i++) init[i] = (i & 1) ? 0ULL : ~0ULL;
+  cudaMemcpy(S.gh.trace, init, sizeof(init), cudaMemcpyHostToDevice);
+  return 0;
+}
+#endif

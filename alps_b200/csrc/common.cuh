@@ -126,7 +126,23 @@ struct GlobalDev {
   int maxfits, maxorder;
   double vA, Tlim, kperp, kpar;
   SpeciesDev sp[MAXSPEC];
+#ifdef ALPS_LAT_TRACE
+  unsigned long long* trace;   // developer build (make trace): time stamps of the single-omega chain
+#endif
 };
+
+// Time stamps of the latency chain (developer build `make trace`, scripts/lat_trace.py): even slots keep the earliest
+// stamp, odd slots the latest.  Compiled out of the product library.
+#ifdef ALPS_LAT_TRACE
+__device__ __forceinline__ void lat_stamp(const GlobalDev& g, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (slot & 1) atomicMax(g.trace + slot, t);
+  else atomicMin(g.trace + slot, t);
+}
+#else
+__device__ __forceinline__ void lat_stamp(const GlobalDev&, int) {}
+#endif
 
 // trapezoid weight of node ipar inside [lo,hi]: ends 1 (a single-node range counts twice,
 // exactly like integrate() with iparmin == iparmax, src/ALPS_fns.f90:838-862)

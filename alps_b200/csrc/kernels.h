@@ -34,6 +34,7 @@ struct QuadParams {
   const double* Cf[MAXSPEC];
   const double* Wf[MAXSPEC];
   int nks;
+  int* done_ctr;           // latency variant: bumped by every CTA once its sums are written (nullptr: not used)
   int tile_major;          // block order: 1 = all omegas of a tile are adjacent (concurrent CTAs share the species tables
                            // and W in L2), 0 = all tiles of an omega are adjacent
 };
@@ -110,25 +111,30 @@ double run_dmma_peak(cudaStream_t st);
 // copies it to om_stage (device) and resets work_count itself
 constexpr int PLAN_FUSED_MAX_OM = 8;
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
-                 int* work, int* work_count, cudaStream_t st, double* om_stage = nullptr);
+                 int* work, int* work_count, cudaStream_t st, double* om_stage = nullptr, int* plan_flag = nullptr);
 bool plan_fused_ok(const GlobalDev& gh, int n_om);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
-                     int* tickets, cudaStream_t st, int gx = 148, int class_n = 0);   // class_n: omegas of the whole call
+                     cudaStream_t st, int gx = 148, int class_n = 0,   // class_n: omegas of the whole call
+                     const int* plan_flag = nullptr);   // early start of the Landau blocks (programmatic launches)
+// k_resonant_lat serves the call (its partial rows, not Sres, feed the harmonic sums: pass Spart to launch_chi_*)
+bool resonant_lat_class(int n_om, int class_n);
 constexpr int RESLAT_GX_NARROW = 16, RESLAT_GX_WIDE = 148;   // block columns per omega of k_resonant_lat (api.cu adapts)
 constexpr int RES_PART_DOUBLES = 11 * 16;   // k_resonant_lat: partial rows per item (LAT_PARTS x LAT_STRIDE)
 // chi partial layout per omega: [nspec][PARTIAL_PER_SPEC] doubles (see resonant.cu)
 constexpr int PARTIAL_PER_SPEC = 2 * (6 + 18);   // chi(6 modes) + chi_low(6 modes x 3) complex
 void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
-                        const double* Sbulk, int nsplit, const double* Sres, double* partial, cudaStream_t st);
+                        const double* Sbulk, int nsplit, const double* Sres, const double* Spart, double* partial,
+                        cudaStream_t st);
 void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
                      const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
                      cudaStream_t st, const int* err_src = nullptr, int* err_dst = nullptr);
 // both in one launch for small batches (one block per omega, one warp per species; bitwise the two-kernel result)
 void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
-                         const double* Sbulk, int nsplit, const double* Sres, double* partial, const double* ext_chi,
-                         double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
-                         const int* err_src = nullptr, int* err_dst = nullptr);
+                         const double* Sbulk, int nsplit, const double* Sres, const double* Spart, double* partial,
+                         const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
+                         const int* err_src = nullptr, int* err_dst = nullptr,
+                         const int* quad_done = nullptr, int nquad = 0);   // early bulk sums (programmatic launches)
 struct FastItem {
   int s;
   int nabs;

@@ -62,7 +62,7 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // the stage hand-over (barrier wait, first fragment loads) of one warp behind the DMMAs of the others.
 // PK = 1: instantiation for the species' last tiles when their upper harmonic group is (nearly) empty -- see `pack`
 template <int NW, int HS, int KSTG, int NST, bool STORE, int DBG = 0, int PK = 0>
-__global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1)) k_quad_mma(const __grid_constant__ QuadParams P) {
+__global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : 1) k_quad_mma(const __grid_constant__ QuadParams P) {
   constexpr int TW = 16 * NW;     // p_par columns per tile
   constexpr int MT = 6 / HS;      // M-tiles per warp
   constexpr int HP = 2 / HS;      // harmonics per thread
@@ -114,24 +114,36 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
   if (threadIdx.x == 0 && DBG != 3)
     for (int it = 0; it < NST - 1 && it < T; it++) issue(it);
 
-  // single-omega chain: launched while k_plan still runs; the barrier set-up and the first table stages above do not depend
-  // on it, the resonance plan and omega do
+  // single-omega chain: launched while k_plan still runs (programmatic dependent launch).  The barrier set-up, the table
+  // stages and the whole p_perp contraction do not depend on k_plan's output; the resonance plan and omega (staged by
+  // k_plan) do, and are needed by the epilogue only.  LATE (the latency variant): the wait for k_plan sits in front of the
+  // first epilogue, so the contraction of the first p_par tile overlaps k_plan.
+  constexpr bool LATE = (NW == 2) && !STORE;
+  // (locals: values of *P.g used after the wait would otherwise be fetched again, one L2 round trip each)
+  const int nhi_shard = sp.nhi_shard, nlo_shard = sp.nlo_shard;
+  const size_t item0 = (size_t)iom * g.NI + sp.item_base;
   pdl_trigger();
-  pdl_wait();
-  if (!STORE && threadIdx.x < 2 * MMA_NH) {
-    const int nabs = tile.n0 + (threadIdx.x >> 1), sg = threadIdx.x & 1;
-    PlanEntry pe;
-    pe.lo1 = 1; pe.hi1 = 0; pe.lo2 = 1; pe.hi2 = 0; pe.flags = 0; pe.ipar_res = 0; pe.upperlimit = 0; pe.pad = 0;
-    if (nabs <= sp.nhi_shard && nabs >= sp.nlo_shard && !(nabs == 0 && sg == 1))
-      pe = P.plan[(size_t)iom * g.NI + sp.item_base + 2 * nabs + sg];
-    sm.plan[threadIdx.x >> 1][sg] = pe;
-  }
-  __syncthreads();
+  if (LATE && threadIdx.x == 0) lat_stamp(g, 2);
+  double omr = 0.0, omi = 0.0;
+  auto fetch_plan = [&]() {
+    pdl_wait();
+    if (!STORE && threadIdx.x < 2 * MMA_NH) {
+      const int nabs = tile.n0 + (threadIdx.x >> 1), sg = threadIdx.x & 1;
+      PlanEntry pe;
+      pe.lo1 = 1; pe.hi1 = 0; pe.lo2 = 1; pe.hi2 = 0; pe.flags = 0; pe.ipar_res = 0; pe.upperlimit = 0; pe.pad = 0;
+      if (nabs <= nhi_shard && nabs >= nlo_shard && !(nabs == 0 && sg == 1))
+        pe = P.plan[item0 + 2 * nabs + sg];
+      sm.plan[threadIdx.x >> 1][sg] = pe;
+    }
+    omr = P.om[2 * iom];
+    omi = P.om[2 * iom + 1];
+    __syncthreads();
+  };
+  if (!LATE) fetch_plan();
+  else __syncthreads();   // the mbarriers are initialised
 
-  const double omr = P.om[2 * iom], omi = P.om[2 * iom + 1];
   const double qs = sp.qs, ms = sp.ms, kpar = g.kpar;
   const double* __restrict__ ppar = sp.ppar;
-  const size_t item0 = (size_t)iom * g.NI + sp.item_base;
   const int WIN = g.WIN, WINX = g.WINX, M_I = g.M_I;
 
   // PK = 1, HS = 2: the 8 harmonics n0 + 8 hsel .. + 7 of this warp's group.  In a species' last tile the group may
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
   int pack_hi = 0;
   if (PK == 1 && HS == 2) {
     const int g0 = tile.n0 + 8 * hsel;
-    const int lo = max(sp.nlo_shard, g0), hi = min(sp.nhi_shard, g0 + 7);
+    const int lo = max(nlo_shard, g0), hi = min(nhi_shard, g0 + 7);
     if (hi < lo) pack = 2;
     else if (lo == g0 && hi - g0 <= 1) pack = 1;
     pack_hi = hi - g0;
@@ -244,6 +256,22 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
           (&acc[x % MT][0][0][0])[q] = __shfl_sync(0xffffffffu, (&acc[0][0][0][0])[q], src);
       }
     }
+    double pp_[2][2];
+    {
+      const int ipar0 = nt * TW + 16 * warp + 2 * tq + 1;
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int ipar = ipar0 + 8 * j + e;
+          pp_[j][e] = (ipar <= npar - 1) ? ppar[ipar] : 0.0;
+        }
+    }
+    if (LATE && ntl == 0) {
+      if (threadIdx.x == 0) lat_stamp(g, 3);
+      fetch_plan();
+      if (threadIdx.x == 0) lat_stamp(g, 5);
+    }
     // ------------------------------------------------------------ epilogue of this p_par tile
     // this thread: harmonics n0 + 8 h + gq (HS = 1: h = 0,1; HS = 2: h = hsel), columns ipar0 + 8 j + e
     const int ipar0 = nt * TW + 16 * warp + 2 * tq + 1;
@@ -253,7 +281,7 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
 #pragma unroll
       for (int h = 0; h < HP; h++) {
         const int nabs = tile.n0 + 8 * (HS == 2 ? hsel : h) + gq;
-        if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
+        if (nabs > nhi_shard || nabs < nlo_shard) continue;
 #pragma unroll
         for (int j = 0; j < 2; j++)
 #pragma unroll
@@ -285,21 +313,13 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
         (&acc[m][1][0][0])[q] = fma(omr, ga, (&acc[m][1][0][0])[q]);
         (&acc[m][0][0][0])[q] = omi * ga;
       }
-    double pp_[2][2];
-#pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int ipar = ipar0 + 8 * j + e;
-        pp_[j][e] = (ipar <= npar - 1) ? ppar[ipar] : 0.0;
-      }
     double Sv[24 * HP];   // [h][sign][12]
 #pragma unroll
     for (int q = 0; q < 24 * HP; q++) Sv[q] = 0.0;
 #pragma unroll
     for (int h = 0; h < HP; h++) {
       const int nabs = tile.n0 + 8 * (HS == 2 ? hsel : h) + gq;
-      if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
+      if (nabs > nhi_shard || nabs < nlo_shard) continue;
 #pragma unroll
       for (int sg = 0; sg < 2; sg++) {
         if (nabs == 0 && sg == 1) continue;
@@ -378,11 +398,23 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : (NW == 2 ? 4 : 1))
   for (int i = threadIdx.x; i < MMA_NH * 24; i += 32 * NW * HS) {
     const int nn = i / 24, sg = (i % 24) / 12, q = i % 12;
     const int nabs = tile.n0 + nn;
-    if (nabs > sp.nhi_shard || nabs < sp.nlo_shard) continue;
+    if (nabs > nhi_shard || nabs < nlo_shard) continue;
     double t = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; w++) t += sm.red[w][nn][sg][q];
     P.Sbulk[((item0 + 2 * nabs + sg) * nsplit + jsplit) * 12 + q] = t;
+  }
+  if (LATE) {
+    // single-omega chain: k_chi_assemble, already resident, starts its bulk sums when all CTAs have got here
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (P.done_ctr) {
+        __threadfence();
+        atomicAdd(P.done_ctr, 1);
+      }
+      lat_stamp(g, 7);
+      lat_stamp(g, 4);
+    }
   }
 }
 

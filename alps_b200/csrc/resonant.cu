@@ -118,29 +118,10 @@ __device__ __forceinline__ void decode_item(const GlobalDev& g, int it, int& s, 
   sg = r & 1;
 }
 
-// FUSED (single-block launches of the single-omega graph, api.cu): the block resets the work counter itself and
-// stages the omegas -- read from pinned host memory -- into om_stage for the kernels downstream, so the chain
-// needs neither a memset nor a host-to-device copy node.
-template <bool FUSED>
-__global__ void __launch_bounds__(FUSED ? 1024 : 256)
-k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n_om, PlanEntry* __restrict__ plan,
-       int* __restrict__ work, int* __restrict__ work_count, double* __restrict__ om_stage) {
-  const GlobalDev& g = *gp;
-  __shared__ double s_om[FUSED ? 2 * PLAN_FUSED_MAX_OM : 2];
-  const double* om = om_in;
-  if (FUSED) {
-    pdl_trigger();
-    if (threadIdx.x < 2 * n_om) {
-      const double v = om_in[threadIdx.x];
-      s_om[threadIdx.x] = v;
-      om_stage[threadIdx.x] = v;
-    }
-    if (threadIdx.x == 0) *work_count = 0;
-    __syncthreads();
-    om = s_om;
-  }
-  size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (idx >= (size_t)n_om * g.NI) return;
+// The resonance plan of item idx = (omega, species, |n|, sign): determine_resonances and the index ranges of
+// integrate / integrate_res (src/ALPS_fns.f90:641-745, 941-1006).
+__device__ __forceinline__ void plan_item(const GlobalDev& g, const double* om, size_t idx, PlanEntry* __restrict__ plan,
+                                          int* __restrict__ work, int* __restrict__ work_count) {
   int iom = (int)(idx / g.NI), it = (int)(idx % g.NI), s, nabs, sg;
   decode_item(g, it, s, nabs, sg);
   const SpeciesDev& sp = g.sp[s];
@@ -209,6 +190,51 @@ k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n
   if (pe.flags & (PLAN_NEAR | PLAN_LANDAU)) work[atomicAdd(work_count, 1)] = (int)idx;
 }
 
+
+// FUSED (single-block launches of the single-omega graph, api.cu): the block resets the work counter itself and
+// stages the omegas -- read from pinned host memory -- into om_stage for the kernels downstream, so the chain
+// needs neither a memset nor a host-to-device copy node.  plan_flag: 0 while the plan of this launch is being written,
+// 1 once it is complete -- the Landau blocks of k_resonant_lat, launched programmatically while k_quad_mma still runs,
+// wait for it instead of for the completion of their predecessor (the flag is cleared before the dependents are allowed
+// to start, so they can never see the previous launch's value).
+template <bool FUSED>
+__global__ void __launch_bounds__(FUSED ? 1024 : 256)
+k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n_om, PlanEntry* __restrict__ plan,
+       int* __restrict__ work, int* __restrict__ work_count, double* __restrict__ om_stage, int* plan_flag) {
+  const GlobalDev& g = *gp;
+  __shared__ double s_om[FUSED ? 2 * PLAN_FUSED_MAX_OM : 2];
+  const double* om = om_in;
+  if (FUSED) {
+    if (threadIdx.x == 0) {
+      lat_stamp(g, 0);
+      *reinterpret_cast<volatile int*>(plan_flag) = 0;
+      *reinterpret_cast<volatile int*>(plan_flag + 1) = 0;   // CTAs of k_quad_mma that have written their sums
+      __threadfence();
+    }
+    __syncthreads();
+    pdl_trigger();
+    if (threadIdx.x < 2 * n_om) {
+      const double v = om_in[threadIdx.x];
+      s_om[threadIdx.x] = v;
+      om_stage[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) *work_count = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) lat_stamp(g, 21);
+    om = s_om;
+  }
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx < (size_t)n_om * g.NI) plan_item(g, om, idx, plan, work, work_count);
+  if (FUSED) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *reinterpret_cast<volatile int*>(plan_flag) = 1;
+      lat_stamp(g, 1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------- resonant
 struct Six {
   cd v[6];   // combos (a,0) (a,1) (a,2) (b,0) (b,1) (c,0)
@@ -220,35 +246,63 @@ __device__ __forceinline__ void six_zero(Six& s) {
 
 // Sum over iperp (with the p_perp trapezoid weights) of funct_g for the six (weight, moment)
 // combinations at real p; linear interpolation around the nearest grid node exactly as
-// funct_g does per iperp (src/ALPS_fns.f90:1284-1319).
-__device__ inline void funct_g6(const GlobalDev& g, const SpeciesDev& sp, const double* __restrict__ gw, int wbase,
-                                double p, Six& out, int* err, int q0 = 0, int nq = 6) {
+// funct_g does per iperp (src/ALPS_fns.f90:1284-1319).  Two steps: the node selection (grid coordinates only) and the
+// interpolation of the window sums gw of k_quad -- k_resonant_lat does the first before it waits for k_quad.
+struct GLoc {
+  int jm, j0, jp;        // window slots of nodes ic - 1, ic, ic + 1
+  int err;
+  double x, pm, p0, pp;  // p - ppar(ic), ppar(ic - 1), ppar(ic), ppar(ic + 1)
+};
+__device__ __forceinline__ GLoc funct_g6_locate(const GlobalDev& g, const SpeciesDev& sp, int wbase, double p) {
   const int npar = g.npar;
   const double* ppar = sp.ppar;
   const double dp = sp.dppar_abs;
   int i0 = (int)floor((p - ppar[0]) / dp + 0.5);
   int ic = 0;
-  for (int c = min(i0 + 2, npar - 1); c >= max(i0 - 2, 1); c--)
-    if (fabs(ppar[c] - p) <= 0.5 * dp) {
-      ic = c;
-      break;
-    }
-  if (ic >= npar - 1) ic = npar - 2;
-  if (ic <= 1) ic = 2;
-  // window slots of nodes ic-1, ic, ic+1 (nodes 1..3 live behind the window, see GlobalDev::WINX)
-  int jm = ic - 1 - wbase, j0 = ic - wbase, jp = ic + 1 - wbase;
-  if (jm < 0 || jp >= g.WIN) {
-    if (ic == 2) {
-      jm = g.WIN;
-      j0 = g.WIN + 1;
-      jp = g.WIN + 2;
-    } else {
-      *err = 1 + (ic & 0xffff) + ((i0 & 0x7fff) << 16);
-      six_zero(out);
-      return;
+  {
+    // nearest node among i0 + 2, ..., i0 - 2 (within [1, npar - 1]), first match in that order; the five candidates are
+    // fetched together (one round trip instead of up to five dependent ones)
+    double cand[5];
+#pragma unroll
+    for (int d = 0; d < 5; d++) cand[d] = ppar[min(max(i0 + 2 - d, 0), npar)];
+#pragma unroll
+    for (int d = 4; d >= 0; d--) {
+      const int c = i0 + 2 - d;
+      if (c <= npar - 1 && c >= 1 && fabs(cand[d] - p) <= 0.5 * dp) ic = c;
     }
   }
-  const double x = p - ppar[ic];
+  if (ic >= npar - 1) ic = npar - 2;
+  if (ic <= 1) ic = 2;
+  GLoc L;
+  L.err = 0;
+  // window slots of nodes ic-1, ic, ic+1 (nodes 1..3 live behind the window, see GlobalDev::WINX)
+  L.jm = ic - 1 - wbase;
+  L.j0 = ic - wbase;
+  L.jp = ic + 1 - wbase;
+  if (L.jm < 0 || L.jp >= g.WIN) {
+    if (ic == 2) {
+      L.jm = g.WIN;
+      L.j0 = g.WIN + 1;
+      L.jp = g.WIN + 2;
+    } else {
+      L.err = 1 + (ic & 0xffff) + ((i0 & 0x7fff) << 16);
+      L.jm = L.j0 = L.jp = 0;
+    }
+  }
+  L.pm = ppar[ic - 1];
+  L.p0 = ppar[ic];
+  L.pp = ppar[ic + 1];
+  L.x = p - L.p0;
+  return L;
+}
+// (dp = |dp_par| of the species, kpar: read by the caller -- k_resonant_lat reads them before its wait)
+__device__ __forceinline__ void funct_g6_at(const double dp, const double kpar, const double* __restrict__ gw,
+                                            const GLoc& L, Six& out, int* err, int q0 = 0, int nq = 6) {
+  if (L.err) {
+    *err = L.err;
+    six_zero(out);
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 6; q++) {
     if (q < q0 || q >= q0 + nq) {   // latency variant: the six combinations are dealt to different blocks
@@ -259,22 +313,27 @@ __device__ inline void funct_g6(const GlobalDev& g, const SpeciesDev& sp, const 
     const int m = (q < 3) ? q : (q < 5 ? q - 3 : 0);  // p_par power
     cd gm, g0, gp;
     {
-      const double* w = gw + ((size_t)jm * 3 + xt) * 2;
-      double pw = m == 0 ? 1.0 : (m == 1 ? ppar[ic - 1] : ppar[ic - 1] * ppar[ic - 1]);
-      gm = -(mk(w[0], w[1]) * pw) / g.kpar;
+      const double* w = gw + ((size_t)L.jm * 3 + xt) * 2;
+      double pw = m == 0 ? 1.0 : (m == 1 ? L.pm : L.pm * L.pm);
+      gm = -(mk(w[0], w[1]) * pw) / kpar;
     }
     {
-      const double* w = gw + ((size_t)j0 * 3 + xt) * 2;
-      double pw = m == 0 ? 1.0 : (m == 1 ? ppar[ic] : ppar[ic] * ppar[ic]);
-      g0 = -(mk(w[0], w[1]) * pw) / g.kpar;
+      const double* w = gw + ((size_t)L.j0 * 3 + xt) * 2;
+      double pw = m == 0 ? 1.0 : (m == 1 ? L.p0 : L.p0 * L.p0);
+      g0 = -(mk(w[0], w[1]) * pw) / kpar;
     }
     {
-      const double* w = gw + ((size_t)jp * 3 + xt) * 2;
-      double pw = m == 0 ? 1.0 : (m == 1 ? ppar[ic + 1] : ppar[ic + 1] * ppar[ic + 1]);
-      gp = -(mk(w[0], w[1]) * pw) / g.kpar;
+      const double* w = gw + ((size_t)L.jp * 3 + xt) * 2;
+      double pw = m == 0 ? 1.0 : (m == 1 ? L.pp : L.pp * L.pp);
+      gp = -(mk(w[0], w[1]) * pw) / kpar;
     }
-    out.v[q] = g0 + (0.5 * ((gp - gm) / dp)) * x;
+    out.v[q] = g0 + (0.5 * ((gp - gm) / dp)) * L.x;
   }
+}
+__device__ inline void funct_g6(const GlobalDev& g, const SpeciesDev& sp, const double* __restrict__ gw, int wbase,
+                                double p, Six& out, int* err, int q0 = 0, int nq = 6) {
+  const GLoc L = funct_g6_locate(g, sp, wbase, p);
+  funct_g6_at(sp.dppar_abs, g.kpar, gw, L, out, err, q0, nq);
 }
 
 __device__ __forceinline__ cd warp_sum_c(cd v) {
@@ -486,40 +545,72 @@ __global__ void __launch_bounds__(RES_THREADS) k_resonant(const GlobalDev* __res
 //   parts 6..8  tiny rest
 //   parts 9,10  Landau residue, alternating groups of 64 p_perp rows: 4 threads per row, one eval_fit
 //               each; the two end rows (iperp = 0, nperp) are ordinary rows of the same scheme
-// Each block leaves 6 complex partial sums (+ zero / error flags); the last block of an item to finish
-// (ticket counter) combines them in a fixed order.  Same arithmetic per term as k_resonant; only the
-// (fixed) summation order differs.
+// Each block leaves 6 complex partial sums (+ zero flag, error code, the factor of the near-pole terms) in its row of
+// Spart; the harmonic sums (chi_partial_block -> lat_parts_combine) add the rows of an item in a fixed order.  Same
+// arithmetic per term as k_resonant; only the (fixed) summation order differs.
+// plan_flag (single-omega chain with programmatic launches): the Landau blocks need the plan but not the window sums of
+// k_quad_mma, so they wait for k_plan's completion flag instead of for their predecessor and run beside k_quad_mma.
 constexpr int LAT_THREADS = 256;
 constexpr int LAT_PARTS = 11;
-constexpr int LAT_STRIDE = 16;   // doubles per partial row: 12 sums, zero flag, error code
+constexpr int LAT_STRIDE = 16;   // doubles per partial row: 12 sums, zero flag, error code, near-pole factor
 static_assert(LAT_PARTS * LAT_STRIDE == RES_PART_DOUBLES, "partial-row buffer size");
 __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* __restrict__ gp,
                                                               const double* __restrict__ om,
                                                               const PlanEntry* __restrict__ plan,
                                                               const int* __restrict__ work,
                                                               const int* __restrict__ work_count,
-                                                              const double* __restrict__ gwin, double* __restrict__ Sres,
+                                                              const double* __restrict__ gwin,
                                                               int* __restrict__ err_flag, double* __restrict__ Spart,
-                                                              int* __restrict__ tickets) {
+                                                              const int* plan_flag) {
   const GlobalDev& g = *gp;
   const int tid = threadIdx.x, wlane = tid & 31, wid = tid >> 5, part = blockIdx.y;
   __shared__ cd s_part[LAT_THREADS / 32][6];
   __shared__ cd s_f[3][2];   // analytic branch: g(p_R + dp), g(p_R - dp), g(p_R) for this block's two combinations
-  __shared__ int s_err, s_last;
+  __shared__ int s_err, s_seen;
   pdl_trigger();
-  pdl_wait();
-  const int nwork = *work_count;
+  if (tid == 0) lat_stamp(g, 8);
+  // quad_waited: this block has waited for its predecessor (k_quad_mma: the window sums gwin).  With plan_flag every
+  // block starts on k_plan's completion flag instead, does everything that needs only the plan and the grids -- work
+  // list, plan entry, species constants, the node selection of its first quadrature point; the Landau blocks all of
+  // their work -- beside k_quad_mma, and waits right before the first use of gwin.
+  bool quad_waited = false;
+  if (plan_flag) {
+    // bounded: if the flag does not show up (it always does), the ordinary wait below is still correct
+    if (tid == 0) {
+      int seen = 0;
+      for (int spin = 0; spin < (1 << 16) && !seen; spin++) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(plan_flag) : "memory");
+      }
+      s_seen = seen;
+    }
+    __syncthreads();
+    if (!s_seen) {
+      pdl_wait();
+      quad_waited = true;
+    }
+  } else {
+    pdl_wait();
+    quad_waited = true;
+  }
+  if (tid == 0) { lat_stamp(g, 10); lat_stamp(g, 23); }
+  // (read through L2: with the early start these are written while this kernel is resident)
+  const int nwork = __ldcg(work_count);
   if (blockIdx.x == 0 && part == 0 && tid == 0) err_flag[7] = nwork;   // feedback for the host's choice of grid width
   for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
-    const size_t idx = (size_t)work[wi];
+    const size_t idx = (size_t)__ldcg(work + wi);
     const int iom = (int)(idx / g.NI), it = (int)(idx % g.NI);
     int s, nabs, sg;
     decode_item(g, it, s, nabs, sg);
     const SpeciesDev& sp = g.sp[s];
-    const PlanEntry pe = plan[idx];
+    PlanEntry pe;
+    {
+      const int4 a = __ldcg(reinterpret_cast<const int4*>(plan + idx)), b = __ldcg(reinterpret_cast<const int4*>(plan + idx) + 1);
+      pe.lo1 = a.x; pe.hi1 = a.y; pe.lo2 = a.z; pe.hi2 = a.w;
+      pe.flags = b.x; pe.ipar_res = b.y; pe.upperlimit = b.z; pe.pad = b.w;
+    }
     const int nperp = g.nperp, M_I = g.M_I, M_P = g.M_P;
     const double* ppar = sp.ppar;
-    const cd omc = mk(om[2 * iom], om[2 * iom + 1]);
+    const cd omc = mk(__ldcg(om + 2 * iom), __ldcg(om + 2 * iom + 1));
     const int nn = sg ? -nabs : nabs;
     const double qs = sp.qs, ms = sp.ms, kpar = g.kpar;
     const double pR = (ms * omc.x - 1.0 * nn * qs) / kpar;
@@ -530,6 +621,7 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
     Six acc;
     six_zero(acc);
     int err = 0, zero = 0;
+    double near_fac = 0.0;   // factor of the near-pole terms (row slot 14)
 
     if ((pe.flags & PLAN_NEAR) && part <= 8) {
       const double* gw = gwin + idx * (size_t)g.WINX * 6;
@@ -539,20 +631,43 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
       const double smdelta = capDelta / (1.0 * M_P);
       const bool pairing = fabs(pI) > g.Tlim;
       const int piece = part / 3, q0 = 2 * (part % 3);   // this block: combinations q0, q0 + 1
+      // quadrature point j of this block's piece
+      const double rest = ppar[pe.upperlimit] - pR - capDelta;
+      const int ntiny = (int)(rest / smdelta);
+      const double correction = ntiny > 0 ? (rest / (1.0 * ntiny)) / smdelta : 0.0;
+      auto point = [&](int j) {
+        if (piece == 2) return (j == 0) ? pR + capDelta : pR + capDelta + correction * smdelta * j;
+        const double p = (j == 0) ? pR : (j == M_P ? pR + capDelta : pR + smdelta * j);
+        return piece == 0 ? p : 2.0 * pR - p;
+      };
+      const int jfirst = (pairing || piece == 2) ? tid : 0;
+      double pfirst = point(jfirst);
+      if (!pairing && piece == 0) pfirst = wid == 0 ? pR + dppar : (wid == 1 ? pR - dppar : pR);   // analytic branch
+      const GLoc Lfirst = funct_g6_locate(g, sp, wbase, pfirst);
+      const double dp_abs = sp.dppar_abs;
+      near_fac = 2.0 * PI * smdelta * sp.dpperp * 0.25;
+      if (!quad_waited) {
+        pdl_wait();
+        quad_waited = true;
+      }
+      if (tid == 0) lat_stamp(g, 37);
       if (pairing && piece <= 1) {
         // Eq. (3.5): symmetric pairing around the pole, src/ALPS_fns.f90:1026-1082
         for (int j = tid; j <= M_P; j += LAT_THREADS) {
           const double wj = (j == 0 || j == M_P) ? 1.0 : 2.0;
           const double p = (j == 0) ? pR : (j == M_P ? pR + capDelta : pR + smdelta * j);
+          const GLoc L = (j == tid) ? Lfirst : funct_g6_locate(g, sp, wbase, point(j));
           Six f;
+          funct_g6_at(dp_abs, kpar, gw, L, f, &err, q0, 2);
+#ifdef ALPS_LAT_TRACE
+          if (tid == 0 && f.v[q0].x != 1.2345e300) lat_stamp(g, 41);
+#endif
           if (piece == 0) {
-            funct_g6(g, sp, gw, wbase, p, f, &err, q0, 2);
             const cd d1 = mk(p - pR, -pI);
 #pragma unroll
             for (int q = 0; q < 6; q++)
               if (q >= q0 && q < q0 + 2) acc.v[q] += wj * (f.v[q] / d1);
           } else {
-            funct_g6(g, sp, gw, wbase, 2.0 * pR - p, f, &err, q0, 2);
             const cd d2 = mk(p - pR, pI);
 #pragma unroll
             for (int q = 0; q < 6; q++)
@@ -564,7 +679,7 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
         // are evaluated once, by three different warps
         if (wlane == 0 && wid < 3) {
           Six f;
-          funct_g6(g, sp, gw, wbase, wid == 0 ? pR + dppar : (wid == 1 ? pR - dppar : pR), f, &err, q0, 2);
+          funct_g6_at(dp_abs, kpar, gw, Lfirst, f, &err, q0, 2);
 #pragma unroll
           for (int q = 0; q < 6; q++)
             if (q >= q0 && q < q0 + 2) s_f[wid][q - q0] = f.v[q];
@@ -591,15 +706,13 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
       }
       if (piece == 2) {
         // tiny rest between p_res + capDelta and the first regular node, :1168-1230
-        const double rest = ppar[pe.upperlimit] - pR - capDelta;
-        const int ntiny = (int)(rest / smdelta);
         if (ntiny > 0) {
-          const double correction = (rest / (1.0 * ntiny)) / smdelta;
           for (int j = tid; j <= ntiny; j += LAT_THREADS) {
             const double wj = (j == 0 || j == ntiny) ? 1.0 : 2.0;
-            const double p = (j == 0) ? pR + capDelta : pR + capDelta + correction * smdelta * j;
+            const double p = point(j);
+            const GLoc L = (j == tid) ? Lfirst : funct_g6_locate(g, sp, wbase, p);
             Six f1;
-            funct_g6(g, sp, gw, wbase, p, f1, &err, q0, 2);
+            funct_g6_at(dp_abs, kpar, gw, L, f1, &err, q0, 2);
             const cd d1 = mk(p - pR, -pI);
 #pragma unroll
             for (int q = 0; q < 6; q++)
@@ -654,6 +767,9 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
       }
     }
 
+#ifdef ALPS_LAT_TRACE
+    if (tid == 0 && acc.v[0].x != 1.2345e300) lat_stamp(g, part >= 9 ? 9 : 11);
+#endif
     // ---- block sum -> partial row of this part
 #pragma unroll
     for (int q = 0; q < 6; q++) {
@@ -662,6 +778,7 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
     }
     if (err) atomicMax(&s_err, err);
     zero = __syncthreads_or(zero);
+    if (tid == 0) lat_stamp(g, 43);
     double* prow = Spart + (idx * LAT_PARTS + part) * LAT_STRIDE;
     if (tid < 6) {
       cd t = s_part[0][tid];
@@ -672,194 +789,373 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
     if (tid == 6) {
       prow[12] = zero ? 1.0 : 0.0;
       prow[13] = (double)s_err;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&tickets[idx], 1) == LAT_PARTS - 1);
-    __syncthreads();
-    if (s_last && tid == 0) {
-      __threadfence();
-      tickets[idx] = 0;   // ready for the next launch
-      const double* pr = Spart + idx * LAT_PARTS * LAT_STRIDE;
-      auto ld = [&](int prt, int q) { return mk(__ldcg(pr + prt * LAT_STRIDE + 2 * q), __ldcg(pr + prt * LAT_STRIDE + 2 * q + 1)); };
-      Six tot;
-      six_zero(tot);
-      int e = 0;
-      for (int prt = 0; prt < LAT_PARTS; prt++) e = max(e, (int)__ldcg(pr + prt * LAT_STRIDE + 13));
-      if (pe.flags & PLAN_NEAR) {
-        const double capDelta = pR - ppar[pe.ipar_res - M_I];
-        const double smdelta = capDelta / (1.0 * M_P);
-        const double near_fac = 2.0 * PI * smdelta * sp.dpperp * 0.25;
-#pragma unroll
-        for (int q = 0; q < 6; q++) tot.v[q] += near_fac * ((ld(q / 2, q) + ld(3 + q / 2, q)) + ld(6 + q / 2, q));
-      }
-      const bool zr = __ldcg(pr + 9 * LAT_STRIDE + 12) != 0.0 || __ldcg(pr + 10 * LAT_STRIDE + 12) != 0.0;
-      if ((pe.flags & PLAN_LANDAU) && !zr) {
-        // landau = -(sum) * i * dpperp * pi * 2 pi ; factor 2 (Im om < 0) or 1 (Im om == 0),
-        // full_integrate src/ALPS_fns.f90:782-789
-        const double mult = (omc.y < 0.0 ? 2.0 : 1.0) * sp.dpperp * PI * 2.0 * PI;
-        const cd ca = cmul_i(-(ld(9, 0) + ld(10, 0))) * mult, cb = cmul_i(-(ld(9, 1) + ld(10, 1))) * mult,
-                 cc = cmul_i(-(ld(9, 2) + ld(10, 2))) * mult;
-        tot.v[0] += ca;
-        tot.v[1] += p_res * ca;
-        tot.v[2] += (p_res * p_res) * ca;
-        tot.v[3] += cb;
-        tot.v[4] += p_res * cb;
-        tot.v[5] += cc;
-      }
-      double* o = Sres + idx * 12;
-#pragma unroll
-      for (int q = 0; q < 6; q++) {
-        o[2 * q] = tot.v[q].x;
-        o[2 * q + 1] = tot.v[q].y;
-      }
-      if (e) {
+      prow[14] = near_fac;
+      if (s_err) {
         err_flag[0] = 1;
         err_flag[1] = (int)idx;
         err_flag[2] = pe.ipar_res;
         err_flag[3] = pe.upperlimit;
         err_flag[4] = pe.flags;
-        err_flag[5] = e;
+        err_flag[5] = s_err;
       }
+      lat_stamp(g, 13);
+      lat_stamp(g, 15);
     }
     __syncthreads();
   }
 }
 
+// The resonant part of moment sum q of one item from the partial rows of k_resonant_lat (pr = the item's LAT_PARTS rows):
+// near-pole pieces 0..8 (rows q/2, 3 + q/2, 6 + q/2 hold combination q) times their factor, plus the Landau residue of
+// rows 9, 10 -- landau = -(sum) * i * dpperp * pi * 2 pi with factor 2 (Im om < 0) or 1 (Im om == 0),
+// full_integrate src/ALPS_fns.f90:782-789 -- times p_res^m for the p_par power m of the combination.
+__device__ __forceinline__ cd lat_parts_combine(const double* pr, int q, int flags, cd omc, cd p_res, double dpperp) {
+  auto ld = [&](int prt, int qq) {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(pr + prt * LAT_STRIDE + 2 * qq));
+    return mk(v.x, v.y);
+  };
+  const int x = (q < 3) ? 0 : (q < 5 ? 1 : 2), m = (q < 3) ? q : (q < 5 ? q - 3 : 0);
+  // all loads first
+  const cd n0 = ld(q / 2, q), n1 = ld(3 + q / 2, q), n2 = ld(6 + q / 2, q), l0 = ld(9, x), l1 = ld(10, x);
+  const double near_fac = __ldcg(pr + (q / 2) * LAT_STRIDE + 14);
+  const double z0 = __ldcg(pr + 9 * LAT_STRIDE + 12), z1 = __ldcg(pr + 10 * LAT_STRIDE + 12);
+  cd tot = mk(0.0, 0.0);
+  if (flags & PLAN_NEAR) tot += near_fac * ((n0 + n1) + n2);
+  const bool zr = z0 != 0.0 || z1 != 0.0;
+  if ((flags & PLAN_LANDAU) && !zr) {
+    const double mult = (omc.y < 0.0 ? 2.0 : 1.0) * dpperp * PI * 2.0 * PI;
+    const cd cx = cmul_i(-(l0 + l1)) * mult;
+    tot += (m == 0) ? cx : (m == 1 ? p_res * cx : (p_res * p_res) * cx);
+  }
+  return tot;
+}
+
 // ---------------------------------------------------------------- chi partial
-// One warp per (omega, species): tensor components of every (n, sign) from its six moment
-// sums, summed over the harmonics of this process' shard.
+// One block per omega: tensor components of every (n, sign) from its six moment sums, summed over the harmonics of
+// this process' shard (the harmonic sums of disp, src/ALPS_fns.f90:364-516).
+// Phase 1: a thread takes (item, moment sum q) units -- a tensor component needs exactly one of the six sums -- and
+// issues every load of its units (plan entry, the p_par split rows of k_quad, the resonant part) before the first use:
+// the whole omega costs one or two L2 round trips instead of one per row and item (the single-omega chain is a chain of
+// such round trips).  The components go to shared memory.  Phase 2: for species s and component c, lane l of a warp adds
+// the items r = l, l + 32, ... in increasing order and a butterfly adds the lanes: the order of operations of a warp per
+// (omega, species) that walks the items itself, whatever the batch size.
 // partial[(iom*nspec + s)*PARTIAL_PER_SPEC + 2*c .. ]: c = mode-1 (0..5) for chi,
 // c = 6 + 3*(mode-1) + (m+1) for chi_low(mode, m), m = -1,0,1.
-// one warp: the partial row of (omega iom, species s)
-__device__ __forceinline__ void chi_partial_warp(const GlobalDev& g, int iom, int s, int lane,
-                                                 const PlanEntry* __restrict__ plan, const double* __restrict__ Sbulk,
-                                                 int nsplit, const double* __restrict__ Sres, double* partial) {
-  const int w = iom * g.nspec + s;
-  const SpeciesDev& sp = g.sp[s];
-  cd chi[6], low[6][3];
-#pragma unroll
-  for (int c = 0; c < 6; c++) {
-    chi[c] = mk(0.0, 0.0);
-    low[c][0] = low[c][1] = low[c][2] = mk(0.0, 0.0);
+constexpr int CHI_WARPS = 8;
+constexpr int CHI_THREADS = 32 * CHI_WARPS;
+constexpr int CHI_WIN = 256;       // items (species after species) per pass
+constexpr int CHI_UNROLL = 3;      // units a thread keeps in flight
+constexpr int CHI_ROWS = 8;        // split rows fetched together
+constexpr int CHI_PAIRS = (6 * MAXSPEC + CHI_WARPS - 1) / CHI_WARPS;   // (species, component) sums per warp
+struct ChiSpec {
+  double z, kf1, kf2, cbulk, ee, norm, qs, ms, dpperp;
+  int base, nitems, fbase, table, ee_on, ee_low, usebM, pad;
+};
+struct ChiGlobals {
+  double kperp, kpar, vA;
+  int kperp_norm, pad;
+};
+struct ChiSmem {
+  cd mode[CHI_WIN][6];
+  cd low[MAXSPEC][6][3];
+  double partial[MAXSPEC][PARTIAL_PER_SPEC];
+  ChiSpec spc[MAXSPEC];
+  int iflags[CHI_WIN];       // summation class of the window's items (chi_partial_block)
+  ChiGlobals gc;
+  double om[2];              // this block's omega
+  int total, seen;
+};
+// Spart != nullptr: the resonant parts come from the partial rows of k_resonant_lat (lat_parts_combine) instead of Sres.
+// do_wait (fused kernel of the single-omega chain, launched programmatically while its predecessors run): the block
+// waits itself -- for its predecessor before the first load of the chain's data, or, with quad_done (a counter the
+// nquad CTAs of k_quad_mma bump when their sums are written; cleared by k_plan), for k_quad_mma only: the bulk sums of
+// every item are then formed while k_resonant_lat still runs and only the resonant parts are added after the wait.
+__device__ __forceinline__ cd chi_component(cd S, int q, double nn, const double z, const double kf1, const double kf2,
+                                            int& cm) {
+  switch (q) {
+    case 0: cm = 0; return ((nn * nn) / (z * z)) * S;        // xx: n^2 J^2 / z^2
+    case 1: cm = 4; return (kf1 * nn / z) * S;               // xz: n J^2 p_par / z
+    case 2: cm = 2; return kf2 * S;                          // zz: J^2 p_par^2
+    case 3: cm = 3; return cmul_i((kf1 * nn / z) * S);       // xy: i p_perp n J J' / z
+    case 4: cm = 5; return -cmul_i(kf2 * S);                 // yz: -i J J' p_par p_perp
+    default: cm = 1; return kf2 * S;                         // yy: p_perp^2 J'^2
   }
-  const bool table = !sp.usebM;
-  if (table) {
-    const double z = g.kperp_norm ? g.kperp / sp.qs : 1.0 / sp.qs;
-    const double kf1 = g.kperp_norm ? 1.0 : g.kperp, kf2 = g.kperp_norm ? 1.0 : g.kperp * g.kperp;
-    const double cbulk = 2.0 * PI * sp.dpperp * sp.dppar_abs * 0.25;
-    const int nitems = 2 * (sp.nhi + 1);
-    for (int r = lane; r < nitems; r += 32) {
-      const size_t idx = (size_t)iom * g.NI + sp.item_base + r;
-      const PlanEntry pe = plan[idx];
-      if (!(pe.flags & PLAN_ACTIVE)) continue;
-      const int nabs = r >> 1, sg = r & 1;
-      const double nn = sg ? -(double)nabs : (double)nabs;
-      cd mode[6];
-      if (pe.flags & PLAN_REL) {
-        // relativistic species: k_rel already produced the six tensor components
-        const double* sr = Sres + idx * 12;
-#pragma unroll
-        for (int q = 0; q < 6; q++) mode[q] = mk(sr[2 * q], sr[2 * q + 1]);
-      } else {
-        cd S[6];
-#pragma unroll
-        for (int q = 0; q < 6; q++) S[q] = mk(0.0, 0.0);
-        // partial rows of the p_par splits of k_quad, added in order; four rows are fetched before they are
-        // added so that a row costs one L2 round trip per four instead of one each (latency chain)
-        for (int j0 = 0; j0 < nsplit; j0 += 4) {
-          double2 row[4][6];
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-            if (j0 + u < nsplit) {
-              const double2* sb = reinterpret_cast<const double2*>(Sbulk + (idx * nsplit + j0 + u) * 12);
-#pragma unroll
-              for (int q = 0; q < 6; q++) row[u][q] = sb[q];
-            }
-#pragma unroll
-          for (int u = 0; u < 4; u++)
-            if (j0 + u < nsplit) {
-#pragma unroll
-              for (int q = 0; q < 6; q++) S[q] += mk(row[u][q].x, row[u][q].y);
-            }
+}
+__device__ __forceinline__ int chi_slot(int q) { return q == 0 ? 0 : (q == 1 ? 4 : (q == 2 ? 2 : (q == 3 ? 3 : (q == 4 ? 5 : 1)))); }
+__device__ __forceinline__ void chi_partial_block(const GlobalDev& g, const double* __restrict__ om, int iom,
+                                                  const PlanEntry* __restrict__ plan, const double* __restrict__ Sbulk,
+                                                  int nsplit, const double* __restrict__ Sres, const double* Spart,
+                                                  double* partial, ChiSmem& sm, bool do_wait = false,
+                                                  const int* quad_done = nullptr, int nquad = 0) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nspec = g.nspec;
+  // (locals: values of *gp used after a wait would otherwise be fetched again, one L2 round trip each)
+  const int NI = g.NI;
+  const double kpar = g.kpar;
+  // ---- phase 0: species constants (nothing of the chain's data)
+  if (tid < nspec) {
+    const SpeciesDev& sp = g.sp[tid];
+    ChiSpec c;
+    c.table = !sp.usebM;
+    c.z = g.kperp_norm ? g.kperp / sp.qs : 1.0 / sp.qs;
+    c.kf1 = g.kperp_norm ? 1.0 : g.kperp;
+    c.kf2 = g.kperp_norm ? 1.0 : g.kperp * g.kperp;
+    c.cbulk = 2.0 * PI * sp.dpperp * sp.dppar_abs * 0.25;
+    c.ee = g.kperp_norm ? sp.int_ee : g.kperp * g.kperp * sp.int_ee;
+    c.ee_on = c.table && sp.nlo_shard == 0;
+    c.ee_low = c.ee_on && !sp.relativistic;   // int_ee_rel goes into chi only (src/ALPS_fns.f90:481-486)
+    c.norm = sp.ns * sp.qs;
+    c.qs = sp.qs;
+    c.ms = sp.ms;
+    c.dpperp = sp.dpperp;
+    c.base = sp.item_base;
+    c.nitems = c.table ? 2 * (sp.nhi + 1) : 0;
+    c.usebM = sp.usebM;
+    int fb = 0;
+    for (int t = 0; t < tid; t++) fb += g.sp[t].usebM ? 0 : 2 * (g.sp[t].nhi + 1);
+    c.fbase = fb;
+    sm.spc[tid] = c;
+    if (tid == nspec - 1) sm.total = fb + c.nitems;
+  }
+  if (tid == 32) {
+    sm.gc.kperp = g.kperp;
+    sm.gc.kpar = g.kpar;
+    sm.gc.vA = g.vA;
+    sm.gc.kperp_norm = g.kperp_norm;
+  }
+  for (int i = tid; i < MAXSPEC * 18; i += CHI_THREADS) (&sm.low[0][0][0])[i] = mk(0.0, 0.0);
+  __syncthreads();
+  if (lane == 0) lat_stamp(g, 25);
+  const int total = sm.total;
+  bool early = false;
+  if (do_wait) {
+    if (quad_done && nquad > 0 && total > 0 && total <= CHI_WIN && Spart) {
+      // bounded: if the count does not show up (it always does), the ordinary wait is still correct
+      if (tid == 0) {
+        int seen = 0;
+        for (int spin = 0; spin < (1 << 16) && seen < nquad; spin++) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(quad_done) : "memory");
         }
-#pragma unroll
-        for (int q = 0; q < 6; q++) S[q] = cbulk * S[q];
-        if (pe.flags & (PLAN_NEAR | PLAN_LANDAU)) {
-          const double* sr = Sres + idx * 12;
-#pragma unroll
-          for (int q = 0; q < 6; q++) S[q] += mk(sr[2 * q], sr[2 * q + 1]);
-        }
-        mode[0] = ((nn * nn) / (z * z)) * S[0];          // xx: n^2 J^2 / z^2
-        mode[1] = kf2 * S[5];                            // yy: p_perp^2 J'^2
-        mode[2] = kf2 * S[2];                            // zz: J^2 p_par^2
-        mode[3] = cmul_i((kf1 * nn / z) * S[3]);         // xy: i p_perp n J J' / z
-        mode[4] = (kf1 * nn / z) * S[1];                 // xz: n J^2 p_par / z
-        mode[5] = -cmul_i(kf2 * S[4]);                   // yz: -i J J' p_par p_perp
+        sm.seen = seen >= nquad;
       }
-      if (nabs == 0) {
+      __syncthreads();
+      early = sm.seen != 0;
+    }
+    if (!early) pdl_wait();
+    if (tid == 0) lat_stamp(g, 18);
+  }
+  const cd omc = mk(__ldcg(om + 2 * iom), __ldcg(om + 2 * iom + 1));
+  if (tid == 0) {
+    sm.om[0] = omc.x;
+    sm.om[1] = omc.y;
+  }
+  // per (species, component) of this warp: ordered lane sums of the non-resonant items, ordered sum of the resonant ones
+  cd acc[CHI_PAIRS], accR[CHI_PAIRS];
+#pragma unroll
+  for (int i = 0; i < CHI_PAIRS; i++) acc[i] = accR[i] = mk(0.0, 0.0);
+
+  for (int f0 = 0; f0 < total; f0 += CHI_WIN) {
+    const int nun = min(CHI_WIN, total - f0) * 6;
+    // ---- phase 1: one tensor component per unit into shared memory (early: the resonant units keep their bulk sum there)
+    for (int u0 = tid; u0 < nun; u0 += CHI_THREADS * CHI_UNROLL) {
+      int sK[CHI_UNROLL], rK[CHI_UNROLL];
+      size_t idxK[CHI_UNROLL];
+      int4 peb[CHI_UNROLL];       // flags, ipar_res, upperlimit, pad of the plan entry
+      double2 row[CHI_UNROLL][CHI_ROWS], sres[CHI_UNROLL];
+#pragma unroll
+      for (int k = 0; k < CHI_UNROLL; k++) {
+        const int u = u0 + k * CHI_THREADS;
+        if (u >= nun) continue;
+        const int fl = u / 6, q = u - 6 * fl, f = f0 + fl;
+        int sx = 0;
+        for (int t = 1; t < nspec; t++)
+          if (f >= sm.spc[t].fbase) sx = t;
+        sK[k] = sx;
+        rK[k] = f - sm.spc[sx].fbase;
+        const size_t idx = (size_t)iom * NI + sm.spc[sx].base + rK[k];
+        idxK[k] = idx;
+        // everything the unit may need, in flight together (rows and resonant parts of inactive items are never used);
+        // through L2: in the early mode the data is written while this kernel is resident
+        peb[k] = __ldcg(reinterpret_cast<const int4*>(plan + idx) + 1);
+#pragma unroll
+        for (int v = 0; v < CHI_ROWS; v++)
+          if (v < nsplit) row[k][v] = __ldcg(reinterpret_cast<const double2*>(Sbulk + (idx * nsplit + v) * 12 + 2 * q));
+        sres[k] = early ? make_double2(0.0, 0.0) : __ldcg(reinterpret_cast<const double2*>(Sres + idx * 12 + 2 * q));
+      }
+#ifdef ALPS_LAT_TRACE
+      if (lane == 0 && (peb[0].x | 1)) lat_stamp(g, 35);   // the first plan entry has arrived
+#endif
+#pragma unroll
+      for (int k = 0; k < CHI_UNROLL; k++) {
+        const int u = u0 + k * CHI_THREADS;
+        if (u >= nun) continue;
+        const int fl = u / 6, q = u - 6 * fl;
+        const int sx = sK[k], r = rK[k], nabs = r >> 1, sg = r & 1, flags = peb[k].x;
+        const ChiSpec& c = sm.spc[sx];
+        const double nn = sg ? -(double)nabs : (double)nabs;
+        cd m = mk(0.0, 0.0);
+        int cm = (flags & PLAN_REL) ? q : chi_slot(q);     // tensor component this sum feeds
+        bool on = (flags & PLAN_ACTIVE) != 0;
         // n = 0: only yy, zz, yz are evaluated (src/ALPS_fns.f90:368-393)
-        chi[1] += mode[1]; chi[2] += mode[2]; chi[5] += mode[5];
-        low[1][1] = mode[1]; low[2][1] = mode[2]; low[5][1] = mode[5];
-      } else {
+        if (nabs == 0 && !(cm == 1 || cm == 2 || cm == 5)) on = false;
+        bool deferred = false;
+        if (on) {
+          if (flags & PLAN_REL) {
+            // relativistic species: k_rel already produced the six tensor components
+            m = mk(sres[k].x, sres[k].y);
+          } else {
+            cd S = mk(0.0, 0.0);
+            // partial rows of the p_par splits of k_quad, added in order
 #pragma unroll
-        for (int c = 0; c < 6; c++) chi[c] += mode[c];
-        if (nabs == 1) {
+            for (int v = 0; v < CHI_ROWS; v++)
+              if (v < nsplit) S += mk(row[k][v].x, row[k][v].y);
+            for (int v = CHI_ROWS; v < nsplit; v++) {
+              const double2 t = __ldcg(reinterpret_cast<const double2*>(Sbulk + (idxK[k] * nsplit + v) * 12 + 2 * q));
+              S += mk(t.x, t.y);
+            }
+            S = c.cbulk * S;
+            if (flags & (PLAN_NEAR | PLAN_LANDAU)) {
+              if (early) {
+                deferred = true;
+                m = S;
+              } else if (Spart) {
+                const int nni = sg ? -nabs : nabs;
+                const double pR = (c.ms * omc.x - 1.0 * nni * c.qs) / kpar;
+                const double pI = (c.ms * omc.y) / kpar;
+                S += lat_parts_combine(Spart + idxK[k] * (size_t)(LAT_PARTS * LAT_STRIDE), q, flags, omc, mk(pR, pI),
+                                       c.dpperp);
+              } else {
+                S += mk(sres[k].x, sres[k].y);
+              }
+            }
+            if (!deferred) m = chi_component(S, q, nn, c.z, c.kf1, c.kf2, cm);
+          }
+        }
+        sm.mode[fl][cm] = m;
+        // the item's summation class: 0 not summed, 1 in the ordered lane sums, 2 resonant (added afterwards, in order)
+        if (q == 0)
+          sm.iflags[fl] = !(flags & PLAN_ACTIVE) ? 0
+                          : (((flags & (PLAN_NEAR | PLAN_LANDAU)) && !(flags & PLAN_REL))
+                                 ? 2 | ((flags & PLAN_NEAR) ? 4 : 0) | ((flags & PLAN_LANDAU) ? 8 : 0) : 1);
+        if (on && !deferred && nabs <= 1) sm.low[sx][cm][nabs == 0 ? 1 : (sg ? 0 : 2)] = m;
+      }
+    }
+    if (lane == 0) lat_stamp(g, 27);
+    __syncthreads();
+    // ---- phase 2: ordered lane sums of the non-resonant items (nothing of k_resonant_lat in them)
 #pragma unroll
-          for (int c = 0; c < 6; c++) low[c][sg ? 0 : 2] = mode[c];
+    for (int i = 0; i < CHI_PAIRS; i++) {
+      const int p = warp + CHI_WARPS * i;
+      if (p >= 6 * nspec) continue;
+      const int sx = p / 6, cc = p - 6 * sx;
+      const int off = sm.spc[sx].fbase - f0;                         // window slot of item 0 of the species
+      const int ra = max(0, -off), rb = min(sm.spc[sx].nitems, CHI_WIN - off);
+      for (int r = ra + ((lane - ra) & 31); r < rb; r += 32)
+        if ((sm.iflags[off + r] & 3) == 1) acc[i] += sm.mode[off + r][cc];
+    }
+    if (lane == 0) lat_stamp(g, 29);
+    if (early) {
+      // ---- the resonant parts, once k_resonant_lat has finished
+      pdl_wait();
+      if (tid == 0) lat_stamp(g, 39);
+      for (int u = tid; u < nun; u += CHI_THREADS) {
+        const int fl = u / 6, q = u - 6 * fl;
+        const int icl = sm.iflags[fl];
+        if ((icl & 3) != 2) continue;
+        const int flags = ((icl & 4) ? PLAN_NEAR : 0) | ((icl & 8) ? PLAN_LANDAU : 0);
+        const int f = f0 + fl;
+        int sx = 0;
+        for (int t = 1; t < nspec; t++)
+          if (f >= sm.spc[t].fbase) sx = t;
+        const ChiSpec& c = sm.spc[sx];
+        const int r = f - c.fbase, nabs = r >> 1, sg = r & 1;
+        int cm = chi_slot(q);
+        if (nabs == 0 && !(cm == 1 || cm == 2 || cm == 5)) continue;
+        const size_t idx = (size_t)iom * NI + c.base + r;
+        const double nn = sg ? -(double)nabs : (double)nabs;
+        const int nni = sg ? -nabs : nabs;
+        const double pR = (c.ms * omc.x - 1.0 * nni * c.qs) / kpar;
+        const double pI = (c.ms * omc.y) / kpar;
+        cd S = sm.mode[fl][cm];
+        S += lat_parts_combine(Spart + idx * (size_t)(LAT_PARTS * LAT_STRIDE), q, flags, omc, mk(pR, pI), c.dpperp);
+#ifdef ALPS_LAT_TRACE
+        if (S.x != 1.2345e300) lat_stamp(g, 47);
+#endif
+        const cd m = chi_component(S, q, nn, c.z, c.kf1, c.kf2, cm);
+        sm.mode[fl][cm] = m;
+        if (nabs <= 1) sm.low[sx][cm][nabs == 0 ? 1 : (sg ? 0 : 2)] = m;
+      }
+      __syncthreads();
+    }
+    // ---- the resonant items, in increasing order (every lane of the warp ends with the same sum)
+#pragma unroll
+    for (int i = 0; i < CHI_PAIRS; i++) {
+      const int p = warp + CHI_WARPS * i;
+      if (p >= 6 * nspec) continue;
+      const int sx = p / 6, cc = p - 6 * sx;
+      const int off = sm.spc[sx].fbase - f0;
+      const int ra = max(0, -off), rb = min(sm.spc[sx].nitems, CHI_WIN - off);
+      for (int r0 = ra; r0 < rb; r0 += 32) {
+        const int r = r0 + lane;
+        const bool res = r < rb && (sm.iflags[off + r] & 3) == 2;
+        const cd mine = res ? sm.mode[off + r][cc] : mk(0.0, 0.0);
+        unsigned mask = __ballot_sync(0xffffffffu, res);
+        while (mask) {
+          const int l = __ffs(mask) - 1;
+          mask &= mask - 1;
+          accR[i] += mk(__shfl_sync(0xffffffffu, mine.x, l), __shfl_sync(0xffffffffu, mine.y, l));
         }
       }
     }
+    __syncthreads();
   }
 #pragma unroll
-  for (int c = 0; c < 6; c++) {
-    chi[c] = warp_sum_c(chi[c]);
-#pragma unroll
-    for (int m = 0; m < 3; m++) low[c][m] = warp_sum_c(low[c][m]);
+  for (int i = 0; i < CHI_PAIRS; i++) {
+    const int p = warp + CHI_WARPS * i;
+    if (p >= 6 * nspec) continue;
+    const int sx = p / 6, cc = p - 6 * sx;
+    cd v = warp_sum_c(acc[i]) + accR[i];
+    if (lane == 0) {
+      const ChiSpec& c = sm.spc[sx];
+      if (cc == 2 && c.ee_on) v.x += c.ee;
+      double* o = partial + ((size_t)iom * nspec + sx) * PARTIAL_PER_SPEC;
+      sm.partial[sx][2 * cc] = o[2 * cc] = c.norm * v.x;
+      sm.partial[sx][2 * cc + 1] = o[2 * cc + 1] = c.norm * v.y;
+    }
   }
-  if (lane == 0) {
-    if (table && sp.nlo_shard == 0) {
-      const double ee = g.kperp_norm ? sp.int_ee : g.kperp * g.kperp * sp.int_ee;
-      chi[2].x += ee;
-      if (!sp.relativistic) low[2][1].x += ee;   // int_ee_rel goes into chi only (src/ALPS_fns.f90:481-486)
-    }
-    const double norm = sp.ns * sp.qs;
-    double* o = partial + (size_t)w * PARTIAL_PER_SPEC;
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      o[2 * c] = norm * chi[c].x;
-      o[2 * c + 1] = norm * chi[c].y;
-#pragma unroll
-      for (int m = 0; m < 3; m++) {
-        o[2 * (6 + 3 * c + m)] = norm * low[c][m].x;
-        o[2 * (6 + 3 * c + m) + 1] = norm * low[c][m].y;
-      }
-    }
+  for (int i = tid; i < nspec * 18; i += CHI_THREADS) {
+    const int sx = i / 18, cc = (i - 18 * sx) / 3, mm = i % 3;
+    const ChiSpec& c = sm.spc[sx];
+    cd v = sm.low[sx][cc][mm];
+    if (cc == 2 && mm == 1 && c.ee_low) v.x += c.ee;
+    double* o = partial + ((size_t)iom * nspec + sx) * PARTIAL_PER_SPEC;
+    sm.partial[sx][2 * (6 + 3 * cc + mm)] = o[2 * (6 + 3 * cc + mm)] = c.norm * v.x;
+    sm.partial[sx][2 * (6 + 3 * cc + mm) + 1] = o[2 * (6 + 3 * cc + mm) + 1] = c.norm * v.y;
   }
 }
 
-__global__ void __launch_bounds__(128) k_chi_partial(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
-                                                     int n_om, const PlanEntry* __restrict__ plan,
-                                                     const double* __restrict__ Sbulk, int nsplit,
-                                                     const double* __restrict__ Sres, double* __restrict__ partial) {
-  (void)om;
-  const GlobalDev& g = *gp;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= n_om * g.nspec) return;
-  chi_partial_warp(g, w / g.nspec, w % g.nspec, threadIdx.x & 31, plan, Sbulk, nsplit, Sres, partial);
+__global__ void __launch_bounds__(CHI_THREADS) k_chi_partial(const GlobalDev* __restrict__ gp,
+                                                                const double* __restrict__ om, int n_om,
+                                                                const PlanEntry* __restrict__ plan,
+                                                                const double* __restrict__ Sbulk, int nsplit,
+                                                                const double* __restrict__ Sres,
+                                                                const double* Spart, double* __restrict__ partial) {
+  (void)n_om;
+  __shared__ ChiSmem sm;
+  chi_partial_block(*gp, om, blockIdx.x, plan, Sbulk, nsplit, Sres, Spart, partial, sm);
 }
 
 // -------------------------------------------------------------------- assemble
 // One thread per omega: src/ALPS_fns.f90:536-624.
-__device__ __forceinline__ void assemble_one(const GlobalDev& g, const double* __restrict__ om, int iom,
-                                             const double* partial, const double* __restrict__ ext_chi,
+// prow: the nspec partial rows of this omega (global memory, or the block's copy in shared memory); gc, usebM (bit s:
+// species s takes its chi from ext_chi): the constants of *gp, read by the caller (the fused kernel reads them before
+// its waits)
+__device__ __forceinline__ void assemble_one(const ChiGlobals gc, int nspec, unsigned usebM, cd omc, int iom,
+                                             const double* prow, const double* __restrict__ ext_chi,
                                              double* __restrict__ D, double* __restrict__ chi0_out,
                                              double* __restrict__ chi0_low_out, double* __restrict__ wave_out) {
-  const int nspec = g.nspec;
-  const cd omc = mk(om[2 * iom], om[2 * iom + 1]);
-  const double kperp = g.kperp, kpar = g.kpar, vA = g.vA;
+  const double kperp = gc.kperp, kpar = gc.kpar, vA = gc.vA;
   cd enx2, enz2, enxnz, norm2;
-  if (g.kperp_norm) {
+  if (gc.kperp_norm) {
     enx2 = mk(kperp * kperp, 0.0);
     enz2 = mk(kpar * kpar, 0.0);
     enxnz = mk(kpar * kperp, 0.0);
@@ -875,9 +1171,9 @@ __device__ __forceinline__ void assemble_one(const GlobalDev& g, const double* _
   cd eps[6];
   for (int c = 0; c < 6; c++) eps[c] = mk(0.0, 0.0);
   for (int s = 0; s < nspec; s++) {
-    const double* p = partial + ((size_t)iom * nspec + s) * PARTIAL_PER_SPEC;
+    const double* p = prow + (size_t)s * PARTIAL_PER_SPEC;
     const double* x = ext_chi ? ext_chi + ((size_t)iom * nspec + s) * PARTIAL_PER_SPEC : nullptr;
-    const bool useext = x && g.sp[s].usebM;
+    const bool useext = x && ((usebM >> s) & 1u);
     for (int c = 0; c < 6; c++) {
       cd v = mk(p[2 * c], p[2 * c + 1]);
       if (useext) v += mk(x[2 * c], x[2 * c + 1]);
@@ -916,7 +1212,7 @@ __device__ __forceinline__ void assemble_one(const GlobalDev& g, const double* _
     }
   }
   const cd ov = omc * vA;
-  const cd unit = g.kperp_norm ? ov * ov : (kperp * ov) * (kperp * ov);
+  const cd unit = gc.kperp_norm ? ov * ov : (kperp * ov) * (kperp * ov);
   eps[0] += unit;
   eps[1] += unit;
   eps[2] += unit;
@@ -946,61 +1242,81 @@ __global__ void k_assemble(const GlobalDev* __restrict__ gp, const double* __res
   // single-omega graph (api.cu): D and err_dst are pinned host memory, so the chain needs no device-to-host copies
   if (err_dst && iom < 8) err_dst[iom] = err_src[iom];
   if (iom >= n_om) return;
-  assemble_one(*gp, om, iom, partial, ext_chi, D, chi0_out, chi0_low_out, wave_out);
+  const GlobalDev& g = *gp;
+  ChiGlobals gc;
+  gc.kperp = g.kperp;
+  gc.kpar = g.kpar;
+  gc.vA = g.vA;
+  gc.kperp_norm = g.kperp_norm;
+  unsigned usebM = 0;
+  for (int s = 0; s < g.nspec; s++) usebM |= g.sp[s].usebM ? (1u << s) : 0u;
+  assemble_one(gc, g.nspec, usebM, mk(om[2 * iom], om[2 * iom + 1]), iom,
+               partial + (size_t)iom * g.nspec * PARTIAL_PER_SPEC, ext_chi, D, chi0_out, chi0_low_out, wave_out);
 }
 
 // k_chi_partial + k_assemble of a small batch in one launch (the single-omega graph and batched roots): block =
-// one omega, warp s = species s; the partial rows go through global memory exactly as between the two kernels
-// (same code, same order of operations: bitwise the two-kernel result), thread 0 assembles after the barrier.
-__global__ void __launch_bounds__(32 * MAXSPEC)
+// one omega; the same device functions in the same order of operations as the two kernels (bitwise the two-kernel
+// result); thread 0 assembles after the barrier from the block's copy of the partial rows.
+__global__ void __launch_bounds__(CHI_THREADS)
 k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, const PlanEntry* __restrict__ plan,
-               const double* __restrict__ Sbulk, int nsplit, const double* __restrict__ Sres, double* partial,
-               const double* __restrict__ ext_chi, double* __restrict__ D, double* __restrict__ chi0_out,
-               double* __restrict__ chi0_low_out, double* __restrict__ wave_out, const int* __restrict__ err_src,
-               int* __restrict__ err_dst) {
+               const double* __restrict__ Sbulk, int nsplit, const double* __restrict__ Sres, const double* Spart,
+               double* partial, const double* __restrict__ ext_chi, double* __restrict__ D, double* __restrict__ chi0_out,
+               double* __restrict__ chi0_low_out, double* __restrict__ wave_out, const int* err_src,
+               int* __restrict__ err_dst, const int* quad_done, int nquad) {
   const GlobalDev& g = *gp;
-  const int iom = blockIdx.x, s = threadIdx.x >> 5;
+  const int iom = blockIdx.x, nspec = g.nspec;
+  __shared__ ChiSmem sm;
   pdl_trigger();
-  pdl_wait();
-  if (s < g.nspec) chi_partial_warp(g, iom, s, threadIdx.x & 31, plan, Sbulk, nsplit, Sres, partial);
-  if (err_dst && iom == 0 && threadIdx.x >= 32 && threadIdx.x < 40) err_dst[threadIdx.x - 32] = err_src[threadIdx.x - 32];
+  if (threadIdx.x == 0) lat_stamp(g, 16);
+  chi_partial_block(g, om, iom, plan, Sbulk, nsplit, Sres, Spart, partial, sm, true, quad_done, nquad);
+  if ((threadIdx.x & 31) == 0) lat_stamp(g, 17);
+  // (after the block's waits: the error words of the whole chain are final)
+  if (err_dst && iom == 0 && threadIdx.x >= 32 * (CHI_WARPS - 1) && threadIdx.x < 32 * (CHI_WARPS - 1) + 8)
+    err_dst[threadIdx.x & 31] = err_src[threadIdx.x & 31];
   __syncthreads();
-  if (threadIdx.x == 0) assemble_one(g, om, iom, partial, ext_chi, D, chi0_out, chi0_low_out, wave_out);
+  if (threadIdx.x == 0) {
+    unsigned usebM = 0;
+    for (int s = 0; s < nspec; s++) usebM |= sm.spc[s].usebM ? (1u << s) : 0u;
+    assemble_one(sm.gc, nspec, usebM, mk(sm.om[0], sm.om[1]), iom, &sm.partial[0][0], ext_chi, D, chi0_out, chi0_low_out,
+                 wave_out);
+    lat_stamp(g, 19);
+  }
 }
 
 // ------------------------------------------------------------------ launchers
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan, int* work,
-                 int* work_count, cudaStream_t st, double* om_stage) {
+                 int* work_count, cudaStream_t st, double* om_stage, int* plan_flag) {
   size_t total = (size_t)n_om * gh.NI;
   if (om_stage) {   // fused single-block variant: caller checked plan_fused_ok()
-    k_plan<true><<<1, 1024, 0, st>>>(g, om, n_om, plan, work, work_count, om_stage);
+    k_plan<true><<<1, 1024, 0, st>>>(g, om, n_om, plan, work, work_count, om_stage, plan_flag);
     return;
   }
   cudaMemsetAsync(work_count, 0, sizeof(int), st);
   if (!total) return;
-  k_plan<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, om, n_om, plan, work, work_count, nullptr);
+  k_plan<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, om, n_om, plan, work, work_count, nullptr, nullptr);
 }
 bool plan_fused_ok(const GlobalDev& gh, int n_om) {
   return n_om >= 1 && n_om <= PLAN_FUSED_MAX_OM && (size_t)n_om * gh.NI <= 1024;
 }
+bool resonant_lat_class(int n_om, int class_n) { return std::max(class_n, n_om) <= 64; }
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
-                     int* tickets, cudaStream_t st, int gx, int class_n) {
+                     cudaStream_t st, int gx, int class_n, const int* plan_flag) {
   if (n_om <= 0) return;
-  if (std::max(class_n, n_om) <= 64 && Spart && tickets) {
+  if (resonant_lat_class(n_om, class_n) && Spart) {
     // gx block columns per omega loop over the list of resonant harmonics: usually only n = 0 is resonant and a
     // narrow grid saves waves of idle blocks (C1: -2.8 us per D), many resonances (large k_par) want all SMs
     launch_chain(k_resonant_lat, dim3(min(148, max(1, gx * n_om)), LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan,
-                 work, work_count, gwin, Sres, err_flag, Spart, tickets);
+                 work, work_count, gwin, err_flag, Spart, plan_flag);
   }
   else
     k_resonant<<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
 }
 void launch_chi_partial(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
-                        const double* Sbulk, int nsplit, const double* Sres, double* partial, cudaStream_t st) {
-  int warps = n_om * gh.nspec;
-  if (warps <= 0) return;
-  k_chi_partial<<<(warps + 3) / 4, 128, 0, st>>>(g, om, n_om, plan, Sbulk, nsplit, Sres, partial);
+                        const double* Sbulk, int nsplit, const double* Sres, const double* Spart, double* partial,
+                        cudaStream_t st) {
+  if (n_om <= 0 || gh.nspec <= 0) return;
+  k_chi_partial<<<n_om, CHI_THREADS, 0, st>>>(g, om, n_om, plan, Sbulk, nsplit, Sres, Spart, partial);
 }
 void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const double* partial,
                      const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave,
@@ -1011,12 +1327,12 @@ void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, 
                                                  err_dst);
 }
 void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
-                         const double* Sbulk, int nsplit, const double* Sres, double* partial, const double* ext_chi,
-                         double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st, const int* err_src,
-                         int* err_dst) {
+                         const double* Sbulk, int nsplit, const double* Sres, const double* Spart, double* partial,
+                         const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
+                         const int* err_src, int* err_dst, const int* quad_done, int nquad) {
   if (n_om <= 0) return;
-  launch_chain(k_chi_assemble, dim3(n_om), dim3(32 * ((gh.nspec + 1) & ~1)), 0, st, g, om, plan, Sbulk, nsplit, Sres,
-               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst);
+  launch_chain(k_chi_assemble, dim3(n_om), dim3(CHI_THREADS), 0, st, g, om, plan, Sbulk, nsplit, Sres, Spart,
+               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst, quad_done, nquad);
 }
 
 }  // namespace alps

@@ -460,7 +460,7 @@ def test_quadrature_variants_and_batch_classes_agree(monkeypatch):
         sol.close()
 
 
-KNOBS = ("ALPS_B200_ZC", "ALPS_B200_FUSE", "ALPS_B200_PDL")
+KNOBS = ("ALPS_B200_ZC", "ALPS_B200_FUSE", "ALPS_B200_PDL", "ALPS_B200_EARLY")
 
 
 def test_single_omega_graph_knobs_are_bitwise_neutral(monkeypatch):
@@ -477,7 +477,7 @@ def test_single_omega_graph_knobs_are_bitwise_neutral(monkeypatch):
               [6.2713e-2 - 4.662e-8j, 1.0 - 1.655e-6j, 0.5 + 0.01j, 0.3 - 0.02j, 2.5 + 0.0j, 0.9 + 1e-3j])]
     for icase, (pl, kw, k, oms) in enumerate(cases):
         out = {}
-        for tag, env in (("fused", "110"), ("plain", "000"), ("pdl", "111")):
+        for tag, env in (("fused", "1100"), ("plain", "0000"), ("pdl", "1110"), ("early", "1111")):
             for name, v in zip(KNOBS, env):
                 monkeypatch.setenv(name, v)
             sol = Solver(pl, **kw)
@@ -493,6 +493,8 @@ def test_single_omega_graph_knobs_are_bitwise_neutral(monkeypatch):
                 sol.close()
         assert np.array_equal(out["fused"][0], out["plain"][0])
         assert np.array_equal(out["fused"][0], out["pdl"][0])       # programmatic dependent launches in the graph
+        assert np.array_equal(out["fused"][0], out["early"][0])     # ... with the Landau blocks started on k_plan's flag
+        assert np.array_equal(out["fused"][2], out["early"][2])
         assert np.array_equal(out["fused"][2], out["plain"][2])
         if icase == 0:
             assert np.array_equal(out["fused"][0][:8], out["fused"][2])      # disp() and a small disp_batch(): same class
