@@ -84,6 +84,7 @@ struct State {
     std::vector<unsigned char> sig;
     long long launches = 0;
     int plain_calls = 0;           // plain calls since the signature last changed (the first one warms up)
+    bool polled = false;           // the chain's D's arrive in pinned host memory as 16-byte stores: the host polls them
   } gslot[9];
   bool capturing = false, graph_off = false, omega_major = false;
   int reslat_gx = RESLAT_GX_NARROW;   // grid width of k_resonant_lat, adapted to the number of resonant harmonics of the
@@ -94,6 +95,8 @@ struct State {
                                      // pinned host memory by the first / last kernel (no memcpy or memset nodes)
   double* d_respart = nullptr;   // k_resonant_lat partial rows (small batches)
   int* d_plan_flag = nullptr;    // k_plan's completion flag (single-omega chain, resonant.cu)
+  bool spin_off = false;         // ALPS_B200_SPIN=0: the host synchronises the stream instead of polling D
+  bool chain_polled = false;     // set while capturing: the chain's last kernel writes every D with one 16-byte store
   bool early_off = false;        // ALPS_B200_EARLY=0: the Landau blocks wait for their predecessor like the others
   double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
   int* d_reltick = nullptr;
@@ -169,6 +172,11 @@ struct State {
                              // (internal chunks, device slices of a group, rank slices): the summation order then
                              // depends on the call, not on how it was cut
   cudaEvent_t ev_part = nullptr;   // group / harmonic partition: this device's chi partials are complete
+  // captured single-omega chain with use_bM species: k_nhds needs only omega, so it runs on a side branch of the graph
+  // (fork after k_plan, join in front of the harmonic sums) instead of between k_resonant_lat and k_chi_assemble
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool nhds_forked = false, fork_off = false;
   double* d_gather = nullptr;      // one process per GPU, OMEGA partition: every rank's D slice (ncclAllGather in place)
   size_t gather_cap = 0;
 };
@@ -224,7 +232,6 @@ void drop_disp_graph() {
   }
 }
 // pinned staging of the captured chains (doubles): omegas, D, error words
-constexpr int ZC_OM = 0, ZC_D = 16, ZC_ERR = 32;
 
 void memo_clear() {
   S.memo_gen++;
@@ -284,6 +291,7 @@ int ensure_pinned(size_t bytes) {
   S.h_pin = nullptr;
   S.h_pin_bytes = 0;
   CK(cudaMallocHost((void**)&S.h_pin, bytes));
+  memset(S.h_pin, 0, bytes);   // (the sequence word of the single-omega chain starts below every sequence number)
   S.h_pin_bytes = bytes;
   return 0;
 }
@@ -607,6 +615,12 @@ int prepare_nhds() {
 int prepare_external(int n, const double* d_om, const double** d_ext_out) {
   *d_ext_out = nullptr;
   if (!S.bm_any && !S.ext_any) return 0;
+  if (S.nhds_forked) {   // already running on the side branch of the captured chain: join
+    S.nhds_forked = false;
+    CK(cudaStreamWaitEvent(S.stream, S.ev_join, 0));
+    *d_ext_out = S.d_ext;
+    return 0;
+  }
   const size_t per = (size_t)S.cfg.nspec * PARTIAL_PER_SPEC;
   if (S.ext_any) {
     CK(cudaMemsetAsync(S.d_ext, 0, (size_t)n * per * sizeof(double), S.stream));
@@ -645,6 +659,14 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
   if (!d_partial_in) {
     launch_plan(gd, S.gh, S.zc ? S.h_pin : d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream,
                 S.zc ? S.d_om : nullptr, S.d_plan_flag);
+    if (S.capturing && S.zc && S.bm_any && !S.ext_any && !S.fork_off) {
+      CK(cudaEventRecord(S.ev_fork, S.stream));
+      CK(cudaStreamWaitEvent(S.side_stream, S.ev_fork, 0));
+      launch_nhds(S.d_nh, d_om, n, S.cfg.nspec, 0, S.d_ext, S.side_stream);
+      S.launches += 1;
+      CK(cudaEventRecord(S.ev_join, S.side_stream));
+      S.nhds_forked = true;
+    }
     S.P.om = d_om;
     S.P.n_om = n;
     // few omegas in flight (sequential root finding, batched roots): spread each (omega, tile) over
@@ -657,7 +679,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     S.P.tile_major = (cn > SMALL_BATCH && !S.omega_major) ? 1 : 0;
     const bool early = g_pdl_launch && S.zc && !S.early_off;   // flag-driven early starts inside the captured chain
     if (use_lat(cn)) {
-      S.Plat.done_ctr = (early && cur_nrtiles() == 0) ? S.d_plan_flag + 1 : nullptr;
+      S.Plat.done_ctr = (early && cur_nrtiles() == 0) ? S.d_plan_flag + CHAIN_QUAD : nullptr;
       S.Plat.om = d_om;
       S.Plat.n_om = n;
       S.Plat.nsplit = S.P.nsplit;
@@ -719,8 +741,10 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
                           S.zc ? S.h_pin + ZC_D : d_D, want_aux ? S.d_chi0 : nullptr, want_aux ? S.d_chi0_low : nullptr,
                           want_aux ? S.d_wave : nullptr, S.stream, S.zc ? S.d_err : nullptr,
                           S.zc ? reinterpret_cast<int*>(S.h_pin + ZC_ERR) : nullptr,
-                          (use_lat(cn) && S.Plat.done_ctr) ? S.Plat.done_ctr : nullptr,
-                          (use_lat(cn) && S.Plat.done_ctr) ? n * S.Plat.ntiles * S.Plat.nsplit : 0);
+                          S.zc ? S.d_plan_flag : nullptr,
+                          (use_lat(cn) && S.Plat.done_ctr) ? n * S.Plat.ntiles * S.Plat.nsplit : 0,
+                          (use_lat(cn) && S.Plat.done_ctr && lat_rows) ? resonant_lat_blocks(n, S.reslat_gx) : 0);
+      if (S.zc && !want_aux && !S.spin_off) S.chain_polled = true;
       S.launches += 4;
       return 0;
     }
@@ -1042,6 +1066,9 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   CK(cudaEventCreate(&S.ev0));
   CK(cudaEventCreate(&S.ev1));
   CK(cudaEventCreateWithFlags(&S.ev_part, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&S.side_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
   cudaDriverEntryPointQueryResult qres;
   void* fn = nullptr;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -1073,10 +1100,10 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   S.gh.maxorder = cfg->maxorder;
   S.gh.vA = cfg->vA;
   S.gh.Tlim = cfg->Tlim;
-  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8) || dalloc(&S.d_plan_flag, 2))
+  if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8) || dalloc(&S.d_plan_flag, CHAIN_INTS))
     return ALPS_B200_ERR_CUDA;
   {
-    const int init[2] = {1, 0};   // [0] "plan complete": only the fused k_plan of the single-omega chain ever clears it
+    const int init[CHAIN_INTS] = {1, 0};   // [0] "plan complete": only the fused k_plan of the single-omega chain clears it
     CK(cudaMemcpy(S.d_plan_flag, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   for (int s = 0; s < MAXSPEC; s++) S.bm[s] = BmParams();
@@ -1097,6 +1124,8 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
     S.speculate_on = knob("ALPS_B200_SPECULATE", true);
     S.pdl_on = knob("ALPS_B200_PDL", LAT_DEFAULT_PDL);
     S.early_off = !knob("ALPS_B200_EARLY", true);
+    S.spin_off = !knob("ALPS_B200_SPIN", true);
+    S.fork_off = !knob("ALPS_B200_FORK", true);
     S.fuse_off = !knob("ALPS_B200_FUSE", LAT_DEFAULT_FUSE);
     S.zc_off = !knob("ALPS_B200_ZC", LAT_DEFAULT_ZC);
     S.omega_major = getenv("ALPS_B200_OMEGA_MAJOR") != nullptr;   // A/B knob: previous block order of k_quad_mma
@@ -1173,6 +1202,11 @@ void alps_b200_finalize(void) {
   if (S.ev1) cudaEventDestroy(S.ev1);
   if (S.ev_part) cudaEventDestroy(S.ev_part);
   S.ev0 = S.ev1 = S.ev_part = nullptr;
+  if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+  if (S.ev_join) cudaEventDestroy(S.ev_join);
+  if (S.side_stream) cudaStreamDestroy(S.side_stream);
+  S.ev_fork = S.ev_join = nullptr;
+  S.side_stream = nullptr;
   dfree(&S.d_gather);
   S.gather_cap = 0;
   if (S.own_stream) cudaStreamDestroy(S.own_stream);
@@ -1768,7 +1802,7 @@ static void disp_signature(std::vector<unsigned char>& sig, int n) {
                         S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
   const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)cur_nrtiles(), (long long)S.fitems.size(), S.mode,
                             S.qv.id, S.fast_variant, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off,
-                            (long long)S.pdl_on, (long long)S.early_off, (long long)S.reslat_gx, (long long)n};
+                            (long long)S.pdl_on, (long long)S.early_off, (long long)S.spin_off, (long long)S.fork_off, (long long)S.reslat_gx, (long long)n};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
   memcpy(sig.data(), &P, sizeof(P));
   memcpy(sig.data() + sizeof(P), ptrs, sizeof(ptrs));
@@ -1800,6 +1834,7 @@ static int disp_via_graph(int n, int* used) {
     }
     S.capturing = true;
     S.zc = !S.zc_off && plan_fused_ok(S.gh, n);
+    S.chain_polled = false;
     g_pdl_launch = S.pdl_on && S.zc;
     const long long l0 = S.launches;
     if (!S.zc) cudaMemcpyAsync(S.d_om, S.h_pin + ZC_OM, 2 * n * sizeof(double), cudaMemcpyHostToDevice, S.stream);
@@ -1811,7 +1846,9 @@ static int disp_via_graph(int n, int* used) {
     S.zc = false;
     g_pdl_launch = false;
     S.capturing = false;
+    S.nhds_forked = false;
     gs.launches = S.launches - l0;
+    gs.polled = S.chain_polled;
     S.launches = l0;
     const cudaError_t e1 = cudaStreamEndCapture(S.stream, &graph);
     cudaError_t e2 = cudaSuccess;
@@ -1824,8 +1861,30 @@ static int disp_via_graph(int n, int* used) {
       return 0;
     }
   }
+  // Polled chains: every D slot holds a NaN pattern no evaluation produces until the chain's last kernel overwrites it
+  // with one 16-byte store; the host polls the slots (bounded) instead of waiting for the stream.  The error words are
+  // written about a microsecond earlier by the same kernel (and stay set on the device until reported).
+  static const double kSentinel = [] {
+    const unsigned long long bits = 0x7ff8dead5eed0b1dULL;
+    double v;
+    memcpy(&v, &bits, sizeof(v));
+    return v;
+  }();
+  volatile unsigned long long* slot = reinterpret_cast<volatile unsigned long long*>(S.h_pin + ZC_D);
+  unsigned long long sbits;
+  memcpy(&sbits, &kSentinel, sizeof(sbits));
+  if (gs.polled)
+    for (int i = 0; i < 2 * n; i++) slot[i] = sbits;
   CK(cudaGraphLaunch(gs.exec, S.stream));
-  CK(cudaStreamSynchronize(S.stream));
+  bool done = false;
+  if (gs.polled) {
+    for (long spin = 0; spin < 40000000L && !done; spin++) {
+      done = true;
+      for (int i = 2 * n - 1; i >= 0 && done; i--) done = slot[i] != sbits;
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  if (!done) CK(cudaStreamSynchronize(S.stream));
   S.launches += gs.launches;
   S.d_evals += n;
   const int* herr = reinterpret_cast<const int*>(S.h_pin + ZC_ERR);

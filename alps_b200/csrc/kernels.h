@@ -110,13 +110,18 @@ double run_dmma_peak(cudaStream_t st);
 // om_stage != nullptr: fused single-block variant (needs plan_fused_ok): om may be pinned host memory, the block
 // copies it to om_stage (device) and resets work_count itself
 constexpr int PLAN_FUSED_MAX_OM = 8;
+// Single-omega chain: slots (doubles) of the pinned host block the chain's first / last kernel read / write (api.cu), and
+// the chain's device words (ints): k_plan's completion flag, CTAs of k_quad_mma done, blocks of k_resonant_lat done.
+constexpr int ZC_OM = 0, ZC_D = 16, ZC_ERR = 32, ZC_DOUBLES = 64;
+constexpr int CHAIN_PLAN = 0, CHAIN_QUAD = 1, CHAIN_RES = 2, CHAIN_INTS = 4;
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
                  int* work, int* work_count, cudaStream_t st, double* om_stage = nullptr, int* plan_flag = nullptr);
 bool plan_fused_ok(const GlobalDev& gh, int n_om);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
                      cudaStream_t st, int gx = 148, int class_n = 0,   // class_n: omegas of the whole call
-                     const int* plan_flag = nullptr);   // early start of the Landau blocks (programmatic launches)
+                     int* chain = nullptr);   // the chain's device words: flag-driven starts (programmatic launches)
+int resonant_lat_blocks(int n_om, int gx);   // grid size of k_resonant_lat for that call
 // k_resonant_lat serves the call (its partial rows, not Sres, feed the harmonic sums: pass Spart to launch_chi_*)
 bool resonant_lat_class(int n_om, int class_n);
 constexpr int RESLAT_GX_NARROW = 16, RESLAT_GX_WIDE = 148;   // block columns per omega of k_resonant_lat (api.cu adapts)
@@ -134,7 +139,7 @@ void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* 
                          const double* Sbulk, int nsplit, const double* Sres, const double* Spart, double* partial,
                          const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
                          const int* err_src = nullptr, int* err_dst = nullptr,
-                         const int* quad_done = nullptr, int nquad = 0);   // early bulk sums (programmatic launches)
+                         int* chain = nullptr, int nquad = 0, int nres = 0);   // early bulk sums (programmatic launches)
 struct FastItem {
   int s;
   int nabs;

@@ -208,7 +208,8 @@ k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n
     if (threadIdx.x == 0) {
       lat_stamp(g, 0);
       *reinterpret_cast<volatile int*>(plan_flag) = 0;
-      *reinterpret_cast<volatile int*>(plan_flag + 1) = 0;   // CTAs of k_quad_mma that have written their sums
+      *reinterpret_cast<volatile int*>(plan_flag + CHAIN_QUAD) = 0;   // CTAs of k_quad_mma that have written their sums
+      *reinterpret_cast<volatile int*>(plan_flag + CHAIN_RES) = 0;    // blocks of k_resonant_lat that have finished
       __threadfence();
     }
     __syncthreads();
@@ -328,6 +329,30 @@ __device__ __forceinline__ void funct_g6_at(const double dp, const double kpar, 
       gp = -(mk(w[0], w[1]) * pw) / kpar;
     }
     out.v[q] = g0 + (0.5 * ((gp - gm) / dp)) * L.x;
+  }
+}
+// The two combinations q0, q0 + 1 of a k_resonant_lat block (same arithmetic as funct_g6_at, a third of its code)
+__device__ __forceinline__ void funct_g2_at(const double dp, const double kpar, const double* __restrict__ gw,
+                                            const GLoc& L, int q0, cd out[2], int* err) {
+  if (L.err) {
+    *err = L.err;
+    out[0] = out[1] = mk(0.0, 0.0);
+    return;
+  }
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const int q = q0 + e;
+    const int xt = (q < 3) ? 0 : (q < 5 ? 1 : 2);   // weight type a,b,c
+    const int m = (q < 3) ? q : (q < 5 ? q - 3 : 0);  // p_par power
+    const double* wm = gw + ((size_t)L.jm * 3 + xt) * 2;
+    const double* w0 = gw + ((size_t)L.j0 * 3 + xt) * 2;
+    const double* wp = gw + ((size_t)L.jp * 3 + xt) * 2;
+    const cd vm = mk(wm[0], wm[1]), v0 = mk(w0[0], w0[1]), vp = mk(wp[0], wp[1]);
+    const double pwm = m == 0 ? 1.0 : (m == 1 ? L.pm : L.pm * L.pm);
+    const double pw0 = m == 0 ? 1.0 : (m == 1 ? L.p0 : L.p0 * L.p0);
+    const double pwp = m == 0 ? 1.0 : (m == 1 ? L.pp : L.pp * L.pp);
+    const cd gm = -(vm * pwm) / kpar, g0 = -(v0 * pw0) / kpar, gp = -(vp * pwp) / kpar;
+    out[e] = g0 + (0.5 * ((gp - gm) / dp)) * L.x;
   }
 }
 __device__ inline void funct_g6(const GlobalDev& g, const SpeciesDev& sp, const double* __restrict__ gw, int wbase,
@@ -561,10 +586,10 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
                                                               const int* __restrict__ work_count,
                                                               const double* __restrict__ gwin,
                                                               int* __restrict__ err_flag, double* __restrict__ Spart,
-                                                              const int* plan_flag) {
+                                                              int* chain) {
   const GlobalDev& g = *gp;
   const int tid = threadIdx.x, wlane = tid & 31, wid = tid >> 5, part = blockIdx.y;
-  __shared__ cd s_part[LAT_THREADS / 32][6];
+  __shared__ cd s_part[LAT_THREADS / 32][3];
   __shared__ cd s_f[3][2];   // analytic branch: g(p_R + dp), g(p_R - dp), g(p_R) for this block's two combinations
   __shared__ int s_err, s_seen;
   pdl_trigger();
@@ -574,6 +599,7 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
   // list, plan entry, species constants, the node selection of its first quadrature point; the Landau blocks all of
   // their work -- beside k_quad_mma, and waits right before the first use of gwin.
   bool quad_waited = false;
+  const int* plan_flag = chain;
   if (plan_flag) {
     // bounded: if the flag does not show up (it always does), the ordinary wait below is still correct
     if (tid == 0) {
@@ -618,10 +644,12 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
     const cd p_res = mk(pR, pI);
     if (tid == 0) s_err = 0;
     __syncthreads();
-    Six acc;
-    six_zero(acc);
+    // this block's sums: combinations q0, q0 + 1 (near-pole pieces) or La, Lb, Lc (Landau blocks)
+    cd acc[3];
+    acc[0] = acc[1] = acc[2] = mk(0.0, 0.0);
     int err = 0, zero = 0;
     double near_fac = 0.0;   // factor of the near-pole terms (row slot 14)
+    const int q0 = 2 * (part % 3);
 
     if ((pe.flags & PLAN_NEAR) && part <= 8) {
       const double* gw = gwin + idx * (size_t)g.WINX * 6;
@@ -630,14 +658,17 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
       const double capDelta = pR - ppar[pe.ipar_res - M_I];
       const double smdelta = capDelta / (1.0 * M_P);
       const bool pairing = fabs(pI) > g.Tlim;
-      const int piece = part / 3, q0 = 2 * (part % 3);   // this block: combinations q0, q0 + 1
+      const int piece = part / 3;
       // quadrature point j of this block's piece
       const double rest = ppar[pe.upperlimit] - pR - capDelta;
       const int ntiny = (int)(rest / smdelta);
       const double correction = ntiny > 0 ? (rest / (1.0 * ntiny)) / smdelta : 0.0;
+      auto base = [&](int j) {   // pieces 0, 1: the point above the pole (piece 1 evaluates g at its mirror image)
+        return (j == 0) ? pR : (j == M_P ? pR + capDelta : pR + smdelta * j);
+      };
       auto point = [&](int j) {
         if (piece == 2) return (j == 0) ? pR + capDelta : pR + capDelta + correction * smdelta * j;
-        const double p = (j == 0) ? pR : (j == M_P ? pR + capDelta : pR + smdelta * j);
+        const double p = base(j);
         return piece == 0 ? p : 2.0 * pR - p;
       };
       const int jfirst = (pairing || piece == 2) ? tid : 0;
@@ -650,86 +681,71 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
         pdl_wait();
         quad_waited = true;
       }
+      // (from here to the end of the kernel the code is kept short: it runs once, after the wait, from L2)
       if (tid == 0) lat_stamp(g, 37);
-      if (pairing && piece <= 1) {
-        // Eq. (3.5): symmetric pairing around the pole, src/ALPS_fns.f90:1026-1082
-        for (int j = tid; j <= M_P; j += LAT_THREADS) {
-          const double wj = (j == 0 || j == M_P) ? 1.0 : 2.0;
-          const double p = (j == 0) ? pR : (j == M_P ? pR + capDelta : pR + smdelta * j);
-          const GLoc L = (j == tid) ? Lfirst : funct_g6_locate(g, sp, wbase, point(j));
-          Six f;
-          funct_g6_at(dp_abs, kpar, gw, L, f, &err, q0, 2);
-#ifdef ALPS_LAT_TRACE
-          if (tid == 0 && f.v[q0].x != 1.2345e300) lat_stamp(g, 41);
-#endif
-          if (piece == 0) {
-            const cd d1 = mk(p - pR, -pI);
-#pragma unroll
-            for (int q = 0; q < 6; q++)
-              if (q >= q0 && q < q0 + 2) acc.v[q] += wj * (f.v[q] / d1);
+      if ((pairing && piece <= 1) || piece == 2) {
+        // Eq. (3.5): symmetric pairing around the pole, src/ALPS_fns.f90:1026-1082 (piece 0: g(p)/(p - p_res), piece 1:
+        // -g(2 p_R - p)/(p - conj p_res)); tiny rest between p_res + capDelta and the first regular node, :1168-1230
+        const int jend = piece == 2 ? (ntiny > 0 ? ntiny : -1) : M_P;
+#pragma unroll 1
+        for (int j = tid; j <= jend; j += LAT_THREADS) {
+          const double wj = (j == 0 || j == jend) ? 1.0 : 2.0;
+          const double pj = point(j);
+          const double p = piece == 2 ? pj : base(j);            // the unmirrored point
+          const GLoc L = (j == tid) ? Lfirst : funct_g6_locate(g, sp, wbase, pj);
+          cd f[2];
+          funct_g2_at(dp_abs, kpar, gw, L, q0, f, &err);
+          const cd d = mk(p - pR, piece == 1 ? pI : -pI);
+          if (piece == 2) {
+            acc[0] += (wj * correction) * (f[0] / d);
+            acc[1] += (wj * correction) * (f[1] / d);
+          } else if (piece == 0) {
+            acc[0] += wj * (f[0] / d);
+            acc[1] += wj * (f[1] / d);
           } else {
-            const cd d2 = mk(p - pR, pI);
-#pragma unroll
-            for (int q = 0; q < 6; q++)
-              if (q >= q0 && q < q0 + 2) acc.v[q] -= wj * (f.v[q] / d2);
+            acc[0] -= wj * (f[0] / d);
+            acc[1] -= wj * (f[1] / d);
           }
         }
       } else if (!pairing && piece == 0) {
         // Eq. (3.6): linearised integrand + pole term, src/ALPS_fns.f90:1088-1165; the three g values
         // are evaluated once, by three different warps
         if (wlane == 0 && wid < 3) {
-          Six f;
-          funct_g6_at(dp_abs, kpar, gw, Lfirst, f, &err, q0, 2);
-#pragma unroll
-          for (int q = 0; q < 6; q++)
-            if (q >= q0 && q < q0 + 2) s_f[wid][q - q0] = f.v[q];
+          cd f[2];
+          funct_g2_at(dp_abs, kpar, gw, Lfirst, q0, f, &err);
+          s_f[wid][0] = f[0];
+          s_f[wid][1] = f[1];
         }
         __syncthreads();
         cd gprime[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) gprime[e] = (s_f[0][e] - s_f[1][e]) / (2.0 * dppar);
+#pragma unroll 1
         for (int j = 1 + tid; j <= M_P; j += LAT_THREADS) {
           const double wj = (j == M_P) ? 1.0 : 2.0;
           const double p = (j == M_P) ? pR + capDelta : pR + smdelta * j;
           const double x2 = (p - pR) * (p - pR);
           const double lor = x2 / (x2 + pI * pI);
-#pragma unroll
-          for (int q = 0; q < 6; q++)
-            if (q >= q0 && q < q0 + 2) acc.v[q] += (wj * 2.0) * gprime[q - q0] * lor;
+          acc[0] += (wj * 2.0) * gprime[0] * lor;
+          acc[1] += (wj * 2.0) * gprime[1] * lor;
         }
         if (tid == 0 && pI != 0.0) {
           const double sgn = pI > 0.0 ? 1.0 : -1.0;
-#pragma unroll
-          for (int q = 0; q < 6; q++)
-            if (q >= q0 && q < q0 + 2) acc.v[q] += sgn * (cmul_i((2.0 * PI) * s_f[2][q - q0]) / smdelta);
-        }
-      }
-      if (piece == 2) {
-        // tiny rest between p_res + capDelta and the first regular node, :1168-1230
-        if (ntiny > 0) {
-          for (int j = tid; j <= ntiny; j += LAT_THREADS) {
-            const double wj = (j == 0 || j == ntiny) ? 1.0 : 2.0;
-            const double p = point(j);
-            const GLoc L = (j == tid) ? Lfirst : funct_g6_locate(g, sp, wbase, p);
-            Six f1;
-            funct_g6_at(dp_abs, kpar, gw, L, f1, &err, q0, 2);
-            const cd d1 = mk(p - pR, -pI);
-#pragma unroll
-            for (int q = 0; q < 6; q++)
-              if (q >= q0 && q < q0 + 2) acc.v[q] += (wj * correction) * (f1.v[q] / d1);
-          }
+          acc[0] += sgn * (cmul_i((2.0 * PI) * s_f[2][0]) / smdelta);
+          acc[1] += sgn * (cmul_i((2.0 * PI) * s_f[2][1]) / smdelta);
         }
       }
     }
 
     if ((pe.flags & PLAN_LANDAU) && part >= 9) {
-      // landau_integrate, src/ALPS_fns.f90:1327-1452; acc.v[0..2] collect La, Lb, Lc
+      // landau_integrate, src/ALPS_fns.f90:1327-1452; acc[0..2] collect La, Lb, Lc
       const double dpperp = sp.dpperp, dppar = sp.dppar_abs;
       const double* Jn = sp.J + (size_t)(nabs + 1) * sp.ldj;
       const double* Jm = sp.J + (size_t)nabs * sp.ldj;
       const double* Jp = sp.J + (size_t)(nabs + 2) * sp.ldj;
       const cd ppl = mk(pR + dppar, pI), pmi = mk(pR - dppar, pI);
       const int gidx = tid >> 2, sub = tid & 3, lbase = wlane & ~3;
+#pragma unroll 1
       for (int r0 = 64 * (part - 9); r0 <= nperp; r0 += 128) {
         const int r = r0 + gidx;
         const bool valid = r <= nperp;
@@ -738,10 +754,10 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
         const int lo = (r == 0) ? 0 : (r == nperp ? nperp - 1 : r - 1);
         cd v = mk(0.0, 0.0);
         if (valid) {
-          if (sub == 0) v = eval_fit(g, s, r, ppl);
-          else if (sub == 1) v = eval_fit(g, s, r, pmi);
-          else if (sub == 2) v = eval_fit(g, s, hi, p_res);
-          else v = eval_fit(g, s, lo, p_res);
+          // one of the four values of the row's differences per thread (one copy of eval_fit in the code)
+          const int row = sub < 2 ? r : (sub == 2 ? hi : lo);
+          const cd pp = sub == 0 ? ppl : (sub == 1 ? pmi : p_res);
+          v = eval_fit(g, s, row, pp);
         }
         cd fpar_i, fpar_f, fperp_i, fperp_f;
         fpar_i.x = __shfl_sync(0xffffffffu, v.x, lbase + 0);  fpar_i.y = __shfl_sync(0xffffffffu, v.y, lbase + 0);
@@ -760,20 +776,20 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
           const cd Q = (qs / fabs(kpar)) * (((pperp * dfpar - p_res * dfperp) * kpar) / ms + omc * dfperp);
           const double bj = Jn[r];
           const double bp = (nabs >= 1) ? 0.5 * (Jm[r] - Jp[r]) : -Jp[r];
-          acc.v[0] += (h * (bj * bj)) * Q;
-          acc.v[1] += (h * (pperp * (bj * bp))) * Q;
-          acc.v[2] += (h * ((pperp * pperp) * (bp * bp))) * Q;
+          acc[0] += (h * (bj * bj)) * Q;
+          acc[1] += (h * (pperp * (bj * bp))) * Q;
+          acc[2] += (h * ((pperp * pperp) * (bp * bp))) * Q;
         }
       }
     }
 
 #ifdef ALPS_LAT_TRACE
-    if (tid == 0 && acc.v[0].x != 1.2345e300) lat_stamp(g, part >= 9 ? 9 : 11);
+    if (tid == 0 && acc[0].x != 1.2345e300) lat_stamp(g, part >= 9 ? 9 : 11);
 #endif
-    // ---- block sum -> partial row of this part
+    // ---- block sum -> partial row of this part (the sums this block does not hold are zero)
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
-      const cd t = warp_sum_c(acc.v[q]);
+    for (int q = 0; q < 3; q++) {
+      const cd t = warp_sum_c(acc[q]);
       if (wlane == 0) s_part[wid][q] = t;
     }
     if (err) atomicMax(&s_err, err);
@@ -781,8 +797,14 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
     if (tid == 0) lat_stamp(g, 43);
     double* prow = Spart + (idx * LAT_PARTS + part) * LAT_STRIDE;
     if (tid < 6) {
-      cd t = s_part[0][tid];
-      for (int w = 1; w < LAT_THREADS / 32; w++) t += s_part[w][tid];
+      // slot of sum tid among this block's three: near-pole blocks hold q0, q0 + 1, Landau blocks 0, 1, 2
+      const int slot = part >= 9 ? (tid < 3 ? tid : -1) : ((tid == q0 || tid == q0 + 1) ? tid - q0 : -1);
+      cd t = mk(0.0, 0.0);
+      if (slot >= 0) {
+        t = s_part[0][slot];
+#pragma unroll 1
+        for (int w = 1; w < LAT_THREADS / 32; w++) t += s_part[w][slot];
+      }
       prow[2 * tid] = t.x;
       prow[2 * tid + 1] = t.y;
     }
@@ -803,13 +825,25 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
     }
     __syncthreads();
   }
+  if (chain) {
+    // k_chi_assemble, already resident, adds the resonant parts when every block has got here
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(chain + CHAIN_RES, 1);
+    }
+  }
 }
 
 // The resonant part of moment sum q of one item from the partial rows of k_resonant_lat (pr = the item's LAT_PARTS rows):
 // near-pole pieces 0..8 (rows q/2, 3 + q/2, 6 + q/2 hold combination q) times their factor, plus the Landau residue of
 // rows 9, 10 -- landau = -(sum) * i * dpperp * pi * 2 pi with factor 2 (Im om < 0) or 1 (Im om == 0),
 // full_integrate src/ALPS_fns.f90:782-789 -- times p_res^m for the p_par power m of the combination.
-__device__ __forceinline__ cd lat_parts_combine(const double* pr, int q, int flags, cd omc, cd p_res, double dpperp) {
+// (mult = (Im om < 0 ? 2 : 1) dpperp pi 2 pi, formed by the caller: lat_landau_mult)
+__device__ __forceinline__ double lat_landau_mult(cd omc, double dpperp) {
+  return (omc.y < 0.0 ? 2.0 : 1.0) * dpperp * PI * 2.0 * PI;
+}
+__device__ __forceinline__ cd lat_parts_combine(const double* pr, int q, int flags, double mult, cd p_res) {
   auto ld = [&](int prt, int qq) {
     const double2 v = __ldcg(reinterpret_cast<const double2*>(pr + prt * LAT_STRIDE + 2 * qq));
     return mk(v.x, v.y);
@@ -823,7 +857,6 @@ __device__ __forceinline__ cd lat_parts_combine(const double* pr, int q, int fla
   if (flags & PLAN_NEAR) tot += near_fac * ((n0 + n1) + n2);
   const bool zr = z0 != 0.0 || z1 != 0.0;
   if ((flags & PLAN_LANDAU) && !zr) {
-    const double mult = (omc.y < 0.0 ? 2.0 : 1.0) * dpperp * PI * 2.0 * PI;
     const cd cx = cmul_i(-(l0 + l1)) * mult;
     tot += (m == 0) ? cx : (m == 1 ? p_res * cx : (p_res * p_res) * cx);
   }
@@ -841,16 +874,24 @@ __device__ __forceinline__ cd lat_parts_combine(const double* pr, int q, int fla
 // (omega, species) that walks the items itself, whatever the batch size.
 // partial[(iom*nspec + s)*PARTIAL_PER_SPEC + 2*c .. ]: c = mode-1 (0..5) for chi,
 // c = 6 + 3*(mode-1) + (m+1) for chi_low(mode, m), m = -1,0,1.
-constexpr int CHI_WARPS = 8;
+constexpr int CHI_WARPS = 24;
 constexpr int CHI_THREADS = 32 * CHI_WARPS;
 constexpr int CHI_WIN = 256;       // items (species after species) per pass
-constexpr int CHI_UNROLL = 3;      // units a thread keeps in flight
+constexpr int CHI_UNROLL = 1;      // units a thread keeps in flight
 constexpr int CHI_ROWS = 8;        // split rows fetched together
 constexpr int CHI_PAIRS = (6 * MAXSPEC + CHI_WARPS - 1) / CHI_WARPS;   // (species, component) sums per warp
 struct ChiSpec {
   double z, kf1, kf2, cbulk, ee, norm, qs, ms, dpperp;
   int base, nitems, fbase, table, ee_on, ee_low, usebM, pad;
 };
+// A resonant unit of the early mode: everything its completion needs once k_resonant_lat has finished
+struct ChiRec {
+  cd S, p_res;            // bulk sum (scaled), resonance
+  double fac, mult;       // component factor, Landau factor
+  const double* pr;       // the item's partial rows
+  short q, rot, cm, lowm, fl, sx, flags, pad;   // lowm: chi_low slot m + 1, or -1
+};
+constexpr int CHI_REC = 96;
 struct ChiGlobals {
   double kperp, kpar, vA;
   int kperp_norm, pad;
@@ -861,6 +902,9 @@ struct ChiSmem {
   double partial[MAXSPEC][PARTIAL_PER_SPEC];
   ChiSpec spc[MAXSPEC];
   int iflags[CHI_WIN];       // summation class of the window's items (chi_partial_block)
+  cd chinr[6 * MAXSPEC], accr[6 * MAXSPEC];   // per (species, component): lane sums added up / resonant items
+  ChiRec rec[CHI_REC];
+  int nrec;
   ChiGlobals gc;
   double om[2];              // this block's omega
   int total, seen;
@@ -870,23 +914,34 @@ struct ChiSmem {
 // waits itself -- for its predecessor before the first load of the chain's data, or, with quad_done (a counter the
 // nquad CTAs of k_quad_mma bump when their sums are written; cleared by k_plan), for k_quad_mma only: the bulk sums of
 // every item are then formed while k_resonant_lat still runs and only the resonant parts are added after the wait.
+// Tensor component fed by moment sum q of harmonic nn: rot(fac * S) with rot = 1 (0), i (1), -i (2); cm = its index
+// (src/ALPS_fns.f90:395-470).
+__device__ __forceinline__ double chi_factor(int q, double nn, const double z, const double kf1, const double kf2,
+                                             int& rot, int& cm) {
+  rot = 0;
+  switch (q) {
+    case 0: cm = 0; return (nn * nn) / (z * z);        // xx: n^2 J^2 / z^2
+    case 1: cm = 4; return kf1 * nn / z;               // xz: n J^2 p_par / z
+    case 2: cm = 2; return kf2;                        // zz: J^2 p_par^2
+    case 3: cm = 3; rot = 1; return kf1 * nn / z;      // xy: i p_perp n J J' / z
+    case 4: cm = 5; rot = 2; return kf2;               // yz: -i J J' p_par p_perp
+    default: cm = 1; return kf2;                       // yy: p_perp^2 J'^2
+  }
+}
+__device__ __forceinline__ cd chi_rotate(cd v, int rot) { return rot == 0 ? v : (rot == 1 ? cmul_i(v) : -cmul_i(v)); }
 __device__ __forceinline__ cd chi_component(cd S, int q, double nn, const double z, const double kf1, const double kf2,
                                             int& cm) {
-  switch (q) {
-    case 0: cm = 0; return ((nn * nn) / (z * z)) * S;        // xx: n^2 J^2 / z^2
-    case 1: cm = 4; return (kf1 * nn / z) * S;               // xz: n J^2 p_par / z
-    case 2: cm = 2; return kf2 * S;                          // zz: J^2 p_par^2
-    case 3: cm = 3; return cmul_i((kf1 * nn / z) * S);       // xy: i p_perp n J J' / z
-    case 4: cm = 5; return -cmul_i(kf2 * S);                 // yz: -i J J' p_par p_perp
-    default: cm = 1; return kf2 * S;                         // yy: p_perp^2 J'^2
-  }
+  int rot;
+  const double fac = chi_factor(q, nn, z, kf1, kf2, rot, cm);
+  return chi_rotate(fac * S, rot);
 }
 __device__ __forceinline__ int chi_slot(int q) { return q == 0 ? 0 : (q == 1 ? 4 : (q == 2 ? 2 : (q == 3 ? 3 : (q == 4 ? 5 : 1)))); }
 __device__ __forceinline__ void chi_partial_block(const GlobalDev& g, const double* __restrict__ om, int iom,
                                                   const PlanEntry* __restrict__ plan, const double* __restrict__ Sbulk,
                                                   int nsplit, const double* __restrict__ Sres, const double* Spart,
                                                   double* partial, ChiSmem& sm, bool do_wait = false,
-                                                  const int* quad_done = nullptr, int nquad = 0) {
+                                                  const int* quad_done = nullptr, int nquad = 0,
+                                                  const int* res_done = nullptr, int nres = 0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nspec = g.nspec;
   // (locals: values of *gp used after a wait would otherwise be fetched again, one L2 round trip each)
   const int NI = g.NI;
@@ -948,10 +1003,15 @@ __device__ __forceinline__ void chi_partial_block(const GlobalDev& g, const doub
     sm.om[0] = omc.x;
     sm.om[1] = omc.y;
   }
-  // per (species, component) of this warp: ordered lane sums of the non-resonant items, ordered sum of the resonant ones
-  cd acc[CHI_PAIRS], accR[CHI_PAIRS];
+  // per (species, component) of this warp: ordered lane sums of the non-resonant items (the ordered sum of the resonant
+  // ones lives in sm.accr).  The code that runs after the last wait is kept short and rolled: it is executed once, from
+  // L2 (the instruction caches hold 32 KB), and costs about 1.5 ns per instruction.
+  cd acc[CHI_PAIRS];
 #pragma unroll
-  for (int i = 0; i < CHI_PAIRS; i++) acc[i] = accR[i] = mk(0.0, 0.0);
+  for (int i = 0; i < CHI_PAIRS; i++) acc[i] = mk(0.0, 0.0);
+  if (tid < 6 * MAXSPEC) sm.accr[tid] = mk(0.0, 0.0);
+  if (tid == 0) sm.nrec = 0;
+  __syncthreads();
 
   for (int f0 = 0; f0 < total; f0 += CHI_WIN) {
     const int nun = min(CHI_WIN, total - f0) * 6;
@@ -1014,15 +1074,29 @@ __device__ __forceinline__ void chi_partial_block(const GlobalDev& g, const doub
             }
             S = c.cbulk * S;
             if (flags & (PLAN_NEAR | PLAN_LANDAU)) {
+              const int nni = sg ? -nabs : nabs;
+              const double pR = (c.ms * omc.x - 1.0 * nni * c.qs) / kpar;
+              const double pI = (c.ms * omc.y) / kpar;
               if (early) {
                 deferred = true;
                 m = S;
+                const int slot = atomicAdd(&sm.nrec, 1);
+                if (slot < CHI_REC) {
+                  ChiRec R;
+                  int rot, cm2;
+                  R.S = S;
+                  R.p_res = mk(pR, pI);
+                  R.fac = chi_factor(q, nn, c.z, c.kf1, c.kf2, rot, cm2);
+                  R.mult = lat_landau_mult(omc, c.dpperp);
+                  R.pr = Spart + idxK[k] * (size_t)(LAT_PARTS * LAT_STRIDE);
+                  R.q = (short)q; R.rot = (short)rot; R.cm = (short)cm2;
+                  R.lowm = (short)(nabs <= 1 ? (nabs == 0 ? 1 : (sg ? 0 : 2)) : -1);
+                  R.fl = (short)fl; R.sx = (short)sx; R.flags = (short)flags; R.pad = 0;
+                  sm.rec[slot] = R;
+                }
               } else if (Spart) {
-                const int nni = sg ? -nabs : nabs;
-                const double pR = (c.ms * omc.x - 1.0 * nni * c.qs) / kpar;
-                const double pI = (c.ms * omc.y) / kpar;
-                S += lat_parts_combine(Spart + idxK[k] * (size_t)(LAT_PARTS * LAT_STRIDE), q, flags, omc, mk(pR, pI),
-                                       c.dpperp);
+                S += lat_parts_combine(Spart + idxK[k] * (size_t)(LAT_PARTS * LAT_STRIDE), q, flags,
+                                       lat_landau_mult(omc, c.dpperp), mk(pR, pI));
               } else {
                 S += mk(sres[k].x, sres[k].y);
               }
@@ -1054,10 +1128,47 @@ __device__ __forceinline__ void chi_partial_block(const GlobalDev& g, const doub
     }
     if (lane == 0) lat_stamp(g, 29);
     if (early) {
-      // ---- the resonant parts, once k_resonant_lat has finished
-      pdl_wait();
+      // (single window) the lane sums are complete: add the lanes now
+#pragma unroll
+      for (int i = 0; i < CHI_PAIRS; i++) {
+        const int p = warp + CHI_WARPS * i;
+        if (p >= 6 * nspec) continue;
+        const cd v = warp_sum_c(acc[i]);
+        if (lane == 0) sm.chinr[p] = v;
+      }
+      // ---- the resonant parts, once k_resonant_lat has finished: its blocks count themselves in res_done (bounded
+      // wait, then the ordinary one, which is always correct)
+      {
+        bool seen_all = false;
+        if (res_done && nres > 0) {
+          if (tid == 0) {
+            int seen = 0;
+            for (int spin = 0; spin < (1 << 16) && seen < nres; spin++) {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(res_done) : "memory");
+            }
+            sm.seen = seen >= nres;
+          }
+          __syncthreads();
+          seen_all = sm.seen != 0;
+        }
+        if (!seen_all) pdl_wait();
+      }
       if (tid == 0) lat_stamp(g, 39);
-      for (int u = tid; u < nun; u += CHI_THREADS) {
+      const int nrec = sm.nrec;
+      // (short code: it runs once, after the chain's last wait, from L2)
+#pragma unroll 1
+      for (int i = tid; i < nrec && nrec <= CHI_REC; i += CHI_THREADS) {
+        const ChiRec& R = sm.rec[i];
+        const cd S = R.S + lat_parts_combine(R.pr, R.q, R.flags, R.mult, R.p_res);
+        const cd m = chi_rotate(R.fac * S, R.rot);
+        sm.mode[R.fl][R.cm] = m;
+        if (R.lowm >= 0) sm.low[R.sx][R.cm][R.lowm] = m;
+#ifdef ALPS_LAT_TRACE
+        if (S.x != 1.2345e300) lat_stamp(g, 47);
+#endif
+      }
+      // more resonant units than records: the general way
+      for (int u = tid; u < nun && nrec > CHI_REC; u += CHI_THREADS) {
         const int fl = u / 6, q = u - 6 * fl;
         const int icl = sm.iflags[fl];
         if ((icl & 3) != 2) continue;
@@ -1076,24 +1187,22 @@ __device__ __forceinline__ void chi_partial_block(const GlobalDev& g, const doub
         const double pR = (c.ms * omc.x - 1.0 * nni * c.qs) / kpar;
         const double pI = (c.ms * omc.y) / kpar;
         cd S = sm.mode[fl][cm];
-        S += lat_parts_combine(Spart + idx * (size_t)(LAT_PARTS * LAT_STRIDE), q, flags, omc, mk(pR, pI), c.dpperp);
-#ifdef ALPS_LAT_TRACE
-        if (S.x != 1.2345e300) lat_stamp(g, 47);
-#endif
+        S += lat_parts_combine(Spart + idx * (size_t)(LAT_PARTS * LAT_STRIDE), q, flags, lat_landau_mult(omc, c.dpperp),
+                               mk(pR, pI));
         const cd m = chi_component(S, q, nn, c.z, c.kf1, c.kf2, cm);
         sm.mode[fl][cm] = m;
         if (nabs <= 1) sm.low[sx][cm][nabs == 0 ? 1 : (sg ? 0 : 2)] = m;
       }
       __syncthreads();
     }
-    // ---- the resonant items, in increasing order (every lane of the warp ends with the same sum)
-#pragma unroll
-    for (int i = 0; i < CHI_PAIRS; i++) {
-      const int p = warp + CHI_WARPS * i;
-      if (p >= 6 * nspec) continue;
+    // ---- the resonant items, in increasing order
+#pragma unroll 1
+    for (int p = warp; p < 6 * nspec; p += CHI_WARPS) {
       const int sx = p / 6, cc = p - 6 * sx;
       const int off = sm.spc[sx].fbase - f0;
       const int ra = max(0, -off), rb = min(sm.spc[sx].nitems, CHI_WIN - off);
+      cd a = sm.accr[p];
+#pragma unroll 1
       for (int r0 = ra; r0 < rb; r0 += 32) {
         const int r = r0 + lane;
         const bool res = r < rb && (sm.iflags[off + r] & 3) == 2;
@@ -1102,25 +1211,32 @@ __device__ __forceinline__ void chi_partial_block(const GlobalDev& g, const doub
         while (mask) {
           const int l = __ffs(mask) - 1;
           mask &= mask - 1;
-          accR[i] += mk(__shfl_sync(0xffffffffu, mine.x, l), __shfl_sync(0xffffffffu, mine.y, l));
+          a += mk(__shfl_sync(0xffffffffu, mine.x, l), __shfl_sync(0xffffffffu, mine.y, l));
         }
       }
+      if (lane == 0) sm.accr[p] = a;
     }
     __syncthreads();
   }
+  if (!early) {
 #pragma unroll
-  for (int i = 0; i < CHI_PAIRS; i++) {
-    const int p = warp + CHI_WARPS * i;
-    if (p >= 6 * nspec) continue;
-    const int sx = p / 6, cc = p - 6 * sx;
-    cd v = warp_sum_c(acc[i]) + accR[i];
-    if (lane == 0) {
-      const ChiSpec& c = sm.spc[sx];
-      if (cc == 2 && c.ee_on) v.x += c.ee;
-      double* o = partial + ((size_t)iom * nspec + sx) * PARTIAL_PER_SPEC;
-      sm.partial[sx][2 * cc] = o[2 * cc] = c.norm * v.x;
-      sm.partial[sx][2 * cc + 1] = o[2 * cc + 1] = c.norm * v.y;
+    for (int i = 0; i < CHI_PAIRS; i++) {
+      const int p = warp + CHI_WARPS * i;
+      if (p >= 6 * nspec) continue;
+      const cd v = warp_sum_c(acc[i]);
+      if (lane == 0) sm.chinr[p] = v;
     }
+    __syncthreads();
+  }
+  // chi = (lane sums of the non-resonant items) + (resonant items); int_ee and the species' normalisation
+  if (tid < 6 * nspec) {
+    const int sx = tid / 6, cc = tid - 6 * sx;
+    const ChiSpec& c = sm.spc[sx];
+    cd v = sm.chinr[tid] + sm.accr[tid];
+    if (cc == 2 && c.ee_on) v.x += c.ee;
+    double* o = partial + ((size_t)iom * nspec + sx) * PARTIAL_PER_SPEC;
+    sm.partial[sx][2 * cc] = o[2 * cc] = c.norm * v.x;
+    sm.partial[sx][2 * cc + 1] = o[2 * cc + 1] = c.norm * v.y;
   }
   for (int i = tid; i < nspec * 18; i += CHI_THREADS) {
     const int sx = i / 18, cc = (i - 18 * sx) / 3, mm = i % 3;
@@ -1262,18 +1378,64 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
                const double* __restrict__ Sbulk, int nsplit, const double* __restrict__ Sres, const double* Spart,
                double* partial, const double* __restrict__ ext_chi, double* __restrict__ D, double* __restrict__ chi0_out,
                double* __restrict__ chi0_low_out, double* __restrict__ wave_out, const int* err_src,
-               int* __restrict__ err_dst, const int* quad_done, int nquad) {
+               int* __restrict__ err_dst, int* chain, int nquad, int nres) {
   const GlobalDev& g = *gp;
   const int iom = blockIdx.x, nspec = g.nspec;
   __shared__ ChiSmem sm;
   pdl_trigger();
   if (threadIdx.x == 0) lat_stamp(g, 16);
-  chi_partial_block(g, om, iom, plan, Sbulk, nsplit, Sres, Spart, partial, sm, true, quad_done, nquad);
+  chi_partial_block(g, om, iom, plan, Sbulk, nsplit, Sres, Spart, partial, sm, true, chain ? chain + CHAIN_QUAD : nullptr,
+                    nquad, chain ? chain + CHAIN_RES : nullptr, nres);
   if ((threadIdx.x & 31) == 0) lat_stamp(g, 17);
   // (after the block's waits: the error words of the whole chain are final)
   if (err_dst && iom == 0 && threadIdx.x >= 32 * (CHI_WARPS - 1) && threadIdx.x < 32 * (CHI_WARPS - 1) + 8)
     err_dst[threadIdx.x & 31] = err_src[threadIdx.x & 31];
   __syncthreads();
+  if (!chi0_out && !chi0_low_out && !wave_out) {
+    // D only (the single-omega chain): the same operations as assemble_one in a few rolled instructions -- this code runs
+    // once, after the chain's last wait, from L2.  Threads 0..5 sum a component of epsilon over the species, thread 0
+    // forms the determinant (src/ALPS_fns.f90:598-624).
+    if (threadIdx.x < 6) {
+      const int c = threadIdx.x;
+      cd e = mk(0.0, 0.0);
+#pragma unroll 1
+      for (int s = 0; s < nspec; s++) {
+        cd v = mk(sm.partial[s][2 * c], sm.partial[s][2 * c + 1]);
+        if (ext_chi && sm.spc[s].usebM) {
+          const double* x = ext_chi + ((size_t)iom * nspec + s) * PARTIAL_PER_SPEC;
+          v += mk(x[2 * c], x[2 * c + 1]);
+        }
+        e += v;
+      }
+      sm.chinr[c] = e;
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+      const ChiGlobals gc = sm.gc;
+      const double kperp = gc.kperp, kpar = gc.kpar, vA = gc.vA;
+      const cd omc = mk(sm.om[0], sm.om[1]);
+      cd enx2, enz2, enxnz;
+      if (gc.kperp_norm) {
+        enx2 = mk(kperp * kperp, 0.0);
+        enz2 = mk(kpar * kpar, 0.0);
+        enxnz = mk(kpar * kperp, 0.0);
+      } else {
+        enx2 = mk(kperp * kperp * kperp * kperp, 0.0);
+        enz2 = mk(kpar * kpar * kperp * kperp, 0.0);
+        enxnz = mk(kpar * kperp * kperp * kperp, 0.0);
+      }
+      const cd ov = omc * vA;
+      const cd unit = gc.kperp_norm ? ov * ov : (kperp * ov) * (kperp * ov);
+      const cd e0 = sm.chinr[0] + unit, e1 = sm.chinr[1] + unit, e2 = sm.chinr[2] + unit;
+      const cd w11 = e0 - enz2, w22 = e1 - enz2 - enx2, w33 = e2 - enx2;
+      const cd w13 = sm.chinr[4] + enxnz, w12 = sm.chinr[3], w23 = sm.chinr[5];
+      const cd d = w11 * (w22 * w33 + w23 * w23) + mk(2.0, 0.0) * w12 * w23 * w13 - w13 * w13 * w22 + w12 * w12 * w33;
+      // one 16-byte store: in the single-omega chain D is pinned host memory and the host polls it (api.cu)
+      if (D) *reinterpret_cast<double2*>(D + 2 * iom) = make_double2(d.x, d.y);
+      lat_stamp(g, 19);
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     unsigned usebM = 0;
     for (int s = 0; s < nspec; s++) usebM |= sm.spc[s].usebM ? (1u << s) : 0u;
@@ -1299,15 +1461,16 @@ bool plan_fused_ok(const GlobalDev& gh, int n_om) {
   return n_om >= 1 && n_om <= PLAN_FUSED_MAX_OM && (size_t)n_om * gh.NI <= 1024;
 }
 bool resonant_lat_class(int n_om, int class_n) { return std::max(class_n, n_om) <= 64; }
+int resonant_lat_blocks(int n_om, int gx) { return std::min(148, std::max(1, gx * n_om)) * LAT_PARTS; }
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
-                     cudaStream_t st, int gx, int class_n, const int* plan_flag) {
+                     cudaStream_t st, int gx, int class_n, int* chain) {
   if (n_om <= 0) return;
   if (resonant_lat_class(n_om, class_n) && Spart) {
     // gx block columns per omega loop over the list of resonant harmonics: usually only n = 0 is resonant and a
     // narrow grid saves waves of idle blocks (C1: -2.8 us per D), many resonances (large k_par) want all SMs
     launch_chain(k_resonant_lat, dim3(min(148, max(1, gx * n_om)), LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan,
-                 work, work_count, gwin, err_flag, Spart, plan_flag);
+                 work, work_count, gwin, err_flag, Spart, chain);
   }
   else
     k_resonant<<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
@@ -1329,10 +1492,10 @@ void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, 
 void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
                          const double* Sbulk, int nsplit, const double* Sres, const double* Spart, double* partial,
                          const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
-                         const int* err_src, int* err_dst, const int* quad_done, int nquad) {
+                         const int* err_src, int* err_dst, int* chain, int nquad, int nres) {
   if (n_om <= 0) return;
   launch_chain(k_chi_assemble, dim3(n_om), dim3(CHI_THREADS), 0, st, g, om, plan, Sbulk, nsplit, Sres, Spart,
-               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst, quad_done, nquad);
+               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst, chain, nquad, nres);
 }
 
 }  // namespace alps

@@ -460,7 +460,7 @@ def test_quadrature_variants_and_batch_classes_agree(monkeypatch):
         sol.close()
 
 
-KNOBS = ("ALPS_B200_ZC", "ALPS_B200_FUSE", "ALPS_B200_PDL", "ALPS_B200_EARLY")
+KNOBS = ("ALPS_B200_ZC", "ALPS_B200_FUSE", "ALPS_B200_PDL", "ALPS_B200_EARLY", "ALPS_B200_SPIN", "ALPS_B200_FORK")
 
 
 def test_single_omega_graph_knobs_are_bitwise_neutral(monkeypatch):
@@ -477,7 +477,7 @@ def test_single_omega_graph_knobs_are_bitwise_neutral(monkeypatch):
               [6.2713e-2 - 4.662e-8j, 1.0 - 1.655e-6j, 0.5 + 0.01j, 0.3 - 0.02j, 2.5 + 0.0j, 0.9 + 1e-3j])]
     for icase, (pl, kw, k, oms) in enumerate(cases):
         out = {}
-        for tag, env in (("fused", "1100"), ("plain", "0000"), ("pdl", "1110"), ("early", "1111")):
+        for tag, env in (("fused", "110000"), ("plain", "000000"), ("pdl", "111000"), ("early", "111111")):
             for name, v in zip(KNOBS, env):
                 monkeypatch.setenv(name, v)
             sol = Solver(pl, **kw)
