@@ -1214,6 +1214,7 @@ __device__ __forceinline__ void chi_partial_block(const GlobalDev& g, const doub
           a += mk(__shfl_sync(0xffffffffu, mine.x, l), __shfl_sync(0xffffffffu, mine.y, l));
         }
       }
+      __syncwarp();
       if (lane == 0) sm.accr[p] = a;
     }
     __syncthreads();

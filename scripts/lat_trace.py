@@ -2,7 +2,7 @@
 k_chi_assemble) from %globaltimer stamps of the trace build:
 
     make -C alps_b200/csrc trace
-    ALPS_B200_LIB=alps_b200/libalps_b200_trace.so [ALPS_B200_PDL=0|1] python scripts/lat_trace.py [c1|c2|c4]
+    ALPS_B200_LIB=alps_b200/libalps_b200_trace.so [ALPS_B200_PDL=0|1] python scripts/lat_trace.py [c1|c2|c3|c4]
 
 Prints the median over calls of every stamp relative to the start of k_plan, and the host-side time per call."""
 import ctypes, os, sys, time
@@ -25,7 +25,8 @@ NAMES = {0: "plan start", 21: "plan: omega read from host", 1: "plan end (last i
 which = sys.argv[1] if len(sys.argv) > 1 else "c1"
 cfg = {"c1": (tables.config_kpar_fast, (1e-2, 1e-2), 9.98811e-3 - 2.31322e-7j),
        "c2": (tables.config_bimax, (1e-3, 1e-3), 1.0e-3 - 1e-6j),
-       "c4": (tables.config_kpar_fast, (3.0, 1e-3), 9.9e-4 - 2e-6j)}[which]
+       "c4": (tables.config_kpar_fast, (3.0, 1e-3), 9.9e-4 - 2e-6j),
+       "c3": (lambda: tables.config_relativistic(rel_backend="device"), (1e-3, 1e-3), 1.0e-3 - 1e-6j)}[which]
 lib = _lib.lib()
 trace = lib.alps_b200_debug_trace
 trace.argtypes = [ctypes.c_void_p]
