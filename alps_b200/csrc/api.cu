@@ -657,16 +657,18 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
   const int cn = S.class_n > 0 ? std::max(S.class_n, n) : n;
   if (!d_partial_out && !S.capturing) S.d_evals += n;
   if (!d_partial_in) {
-    launch_plan(gd, S.gh, S.zc ? S.h_pin : d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream,
-                S.zc ? S.d_om : nullptr, S.d_plan_flag);
     if (S.capturing && S.zc && S.bm_any && !S.ext_any && !S.fork_off) {
+      // captured single-omega chain: the closed-form chi of use_bM species needs nothing but omega (read from the pinned
+      // host block like k_plan does), so k_nhds is a branch of its own from the root of the graph to the harmonic sums
       CK(cudaEventRecord(S.ev_fork, S.stream));
       CK(cudaStreamWaitEvent(S.side_stream, S.ev_fork, 0));
-      launch_nhds(S.d_nh, d_om, n, S.cfg.nspec, 0, S.d_ext, S.side_stream);
+      launch_nhds(S.d_nh, S.h_pin + ZC_OM, n, S.cfg.nspec, 0, S.d_ext, S.side_stream);
       S.launches += 1;
       CK(cudaEventRecord(S.ev_join, S.side_stream));
       S.nhds_forked = true;
     }
+    launch_plan(gd, S.gh, S.zc ? S.h_pin : d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream,
+                S.zc ? S.d_om : nullptr, S.d_plan_flag);
     S.P.om = d_om;
     S.P.n_om = n;
     // few omegas in flight (sequential root finding, batched roots): spread each (omega, tile) over

@@ -504,6 +504,40 @@ def test_single_omega_graph_knobs_are_bitwise_neutral(monkeypatch):
         monkeypatch.delenv(name, raising=False)
 
 
+def test_single_omega_chain_with_many_resonant_harmonics(monkeypatch):
+    """k_par = 20 at k_perp = 3: dozens of harmonics are resonant at once -- more resonant (item, moment) units than the
+    records of the harmonic sums hold (resonant.cu: CHI_REC), so the captured chain completes them the general way, and
+    k_resonant_lat runs its wide grid.  D of the replayed chain against the oracle, and bitwise against the chain
+    with the flag-driven starts switched off."""
+    from alps_b200.solver import Solver
+    from oracle.oracle import Oracle
+    pl = tables.config_kpar_fast()
+    kperp, kpar = 3.0, 20.0
+    oms = [1.5 - 0.05j, 30.0 + 0.01j, 12.3 - 0.4j, 55.0 + 0.0j]
+    orc = Oracle(pl, nproc=4)
+    orc.set_k(kperp, kpar)
+    want = [orc.disp(om, full=True) for om in oms]
+    got = {}
+    for early in ("1", "0"):
+        monkeypatch.setenv("ALPS_B200_EARLY", early)
+        sol = Solver(pl, emulate_nproc=4)
+        try:
+            sol.set_k(kperp, kpar)
+            rows = []
+            for om in oms:
+                d = [sol.disp(om) for _ in range(3)]      # plain launches, capture, replay
+                assert d[0] == d[1] == d[2]
+                rows.append(d[2])
+            got[early] = rows
+        finally:
+            sol.close()
+    monkeypatch.delenv("ALPS_B200_EARLY", raising=False)
+    assert got["1"] == got["0"]
+    for om, d, (Do, chi_o, _, _) in zip(oms, got["1"], want):
+        ws = wave_scale(chi_o, complex(om), pl.vA, kperp, kpar)
+        assert abs(d - Do) / det_scale(ws) < TOL, (om, d, Do)
+
+
 def test_packed_remainder_tiles_are_bitwise_neutral(monkeypatch):
     """Throughput batches send a species' last harmonic tile through the packed instantiation of k_quad_mma when its
     upper group of 8 harmonics holds at most two harmonics of the summed range (their weight rows share one M-tile,
