@@ -8,7 +8,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | 
 ( time timeout 900 python bench.py ) > gpurun_out/ev_bench.json 2> gpurun_out/ev_bench_err.log; tail -3 gpurun_out/ev_bench_err.log; cut -c1-200 gpurun_out/ev_bench.json
 ( time timeout 900 python bench.py --impl reference ) > gpurun_out/ev_bench_ref.json 2>> gpurun_out/ev_bench_err.log; cut -c1-200 gpurun_out/ev_bench_ref.json
 timeout 900 python scripts/full_configs.py --repeat 2 --out gpurun_out/ev_full_configs.jsonl 2>&1 | tail -14 | cut -c1-200
-timeout 300 python scripts/latency_probe.py 2>&1 | tail -8
+timeout 300 python scripts/lat_chain_probe.py 2>&1 | tail -5
 timeout 300 python scripts/rel_time.py 2>&1 | tail -3
 # launch lists (share of each kernel in a step) and full captures
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/ev_launches_bench.csv \
