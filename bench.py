@@ -51,7 +51,7 @@ FLOPS_EXECUTED_PER_ABSN_POINT = 12.0
 # denominators, 4 Newton steps of the shared reciprocal) + 10 DADD/DMUL  ->  118 flops (alps_b200/csrc/fast_kernel.cu)
 FLOPS_FAST_PER_ABSN_PAR = 118.0
 FP64_NOMINAL_TFLOPS = 37.2          # 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
-TRAFFIC_PROFILE = "profiles/r01_k_quad_traffic.json"   # ncu --set full capture of k_quad_mma (kernel unchanged since)
+TRAFFIC_PROFILE = "profiles/r02_k_quad_traffic.json"   # ncu --set full capture of k_quad_mma (regular-tile launch: 94 % of the step)
 
 WORKLOADS = {
     # name: (description, builder kwargs)
@@ -494,7 +494,8 @@ def run_ours(args, w, rank, world, local_rank):
             tj = json.load(open(tp))
             traffic = tj["dram_bytes_per_launch"] / tj["omegas_per_launch"] * B   # scaled to this launch size
             traffic_src = ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one "
-                           "`ncu --set full` capture of this kernel (%s)" % TRAFFIC_PROFILE)
+                           "`ncu --set full` capture of this kernel's regular-tile launch, 36 of the 39 tiles of a step "
+                           "(%s); the packed remainder launch is not in it" % TRAFFIC_PROFILE)
         except Exception:
             traffic = None
     # one read of A', C' (fragment order, padded) and W per launch + plan (32 B) and moment sums (96 B) per item

@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 1 --no-cpu --no-fast --no-map --no-extra > gpurun_out/ev_ncu_bench.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/ev_launches_fast.csv \
   python scripts/fast_probe.py > gpurun_out/ev_ncu_fast_list.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_quad_mma -s 2 -c 1 -f -o gpurun_out/ev_k_quad_mma \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_quad_mma -s 2 -c 2 -f -o gpurun_out/ev_k_quad_mma \
   python bench.py --steps 1 --warmup 1 --no-cpu --no-fast --no-map --no-extra > gpurun_out/ev_ncu_quad.log 2>&1; tail -1 gpurun_out/ev_ncu_quad.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fast_tiled -s 1 -c 1 -f -o gpurun_out/ev_k_fast_tiled \
   python scripts/fast_probe.py > gpurun_out/ev_ncu_fast.log 2>&1; tail -1 gpurun_out/ev_ncu_fast.log
