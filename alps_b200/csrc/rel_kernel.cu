@@ -1316,7 +1316,9 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
   if (n_om <= 0 || ntiles <= 0) return;
   if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
   static const char* force = getenv("ALPS_B200_REL_MINB");   // A/B knob: "1" = 255-register variant always
-  if (nsplit > 1 || n_om * ntiles <= 2 * 148 || (force && force[0] == '1'))
+  // one CTA of 255 registers per SM up to about two waves of them (measured: C3, one omega); beyond that two CTAs of 128 registers per SM
+  // finish sooner (the same operations in the same order: the results do not depend on the choice)
+  if ((long long)n_om * ntiles * nsplit <= 3 * 148 || (force && force[0] == '1'))
     launch_chain(k_rel<1>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
                  err_flag, nsplit, Mpart, tickets);
   else
