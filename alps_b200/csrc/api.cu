@@ -95,6 +95,7 @@ struct State {
                                      // pinned host memory by the first / last kernel (no memcpy or memset nodes)
   double* d_respart = nullptr;   // k_resonant_lat partial rows (small batches)
   int* d_plan_flag = nullptr;    // k_plan's completion flag (single-omega chain, resonant.cu)
+  bool rel_rows_off = false;     // ALPS_B200_REL_ROWS=0: small batches leave the resonant rows to the CTAs of their tile
   bool spin_off = false;         // ALPS_B200_SPIN=0: the host synchronises the stream instead of polling D
   bool chain_polled = false;     // set while capturing: the chain's last kernel writes every D with one 16-byte store
   bool early_off = false;        // ALPS_B200_EARLY=0: the Landau blocks wait for their predecessor like the others
@@ -533,7 +534,8 @@ int ensure_batch(int want) {
   if (any_rel) {
     // sized for the largest split (16) and any harmonic shard (tiles <= NI)
     const size_t nt = (size_t)SMALL_BATCH * NI;
-    if (dalloc(&S.d_relpart, (size_t)SMALL_BATCH * NI * 16 * 12) || dalloc(&S.d_reltick, nt))
+    const size_t parts = (size_t)std::max(16, rel_rows_chunks(S.gh.ngamma));   // Gamma split of k_rel / chunks of k_rel_rows
+    if (dalloc(&S.d_relpart, (size_t)SMALL_BATCH * NI * parts * 12) || dalloc(&S.d_reltick, nt))
       return ALPS_B200_ERR_CUDA;
     CK(cudaMemsetAsync(S.d_reltick, 0, nt * sizeof(int), S.stream));
     if (dalloc(&S.d_relflag, B * NI) || dalloc(&S.d_relwork, 2 * B * NI) || dalloc(&S.d_relcount, NI) ||
@@ -667,8 +669,14 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       CK(cudaEventRecord(S.ev_join, S.side_stream));
       S.nhds_forked = true;
     }
+    // small batches with relativistic species: the rows of the resonant entries go to k_rel_rows (whole GPU)
+    bool rel_tables = cur_nrtiles() > 0;
+    for (int s = 0; s < S.cfg.nspec; s++) rel_tables = rel_tables && (!S.gh.sp[s].relativistic || S.gh.sp[s].Jrel != nullptr);
+    const bool rel_rows = rel_tables && cn <= SMALL_BATCH && !S.rel_rows_off && cur_nrtiles() <= REL_ROWS_MAXTILES &&
+                          S.d_relcount != nullptr;
     launch_plan(gd, S.gh, S.zc ? S.h_pin : d_om, n, S.d_plan, S.d_work, S.d_work_count, S.stream,
-                S.zc ? S.d_om : nullptr, S.d_plan_flag);
+                S.zc ? S.d_om : nullptr, S.d_plan_flag, (rel_rows && S.zc) ? S.d_relcount : nullptr,
+                (rel_rows && S.zc) ? cur_nrtiles() : 0);
     S.P.om = d_om;
     S.P.n_om = n;
     // few omegas in flight (sequential root finding, batched roots): spread each (omega, tile) over
@@ -727,6 +735,10 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
         launch_rel_tiled(gd, d_om, n, cur_rtiles(), (int)nt, S.d_Sres, S.d_err + 6, S.d_relflag, S.d_relwork, S.d_relcount,
                          S.d_relpos, S.d_reldpart, nsB, S.sm_count, S.stream);
         S.launches += 4;
+      } else if (rel_rows) {
+        launch_rel_small(gd, d_om, n, cur_rtiles(), (int)nt, S.d_Sres, S.d_err + 6, S.d_relflag, S.d_relwork, S.d_relcount,
+                         S.d_relpos, rsplit, S.d_relpart, S.d_reltick, S.sm_count, !S.zc, S.stream);
+        S.launches += 3;
       } else {
         launch_rel(gd, d_om, n, cur_rtiles(), cur_nrtiles(), S.d_Sres, S.d_err + 6, rsplit, S.d_relpart,
                    S.d_reltick, S.stream);
@@ -1128,6 +1140,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
     S.early_off = !knob("ALPS_B200_EARLY", true);
     S.spin_off = !knob("ALPS_B200_SPIN", true);
     S.fork_off = !knob("ALPS_B200_FORK", true);
+    S.rel_rows_off = !knob("ALPS_B200_REL_ROWS", true);
     S.fuse_off = !knob("ALPS_B200_FUSE", LAT_DEFAULT_FUSE);
     S.zc_off = !knob("ALPS_B200_ZC", LAT_DEFAULT_ZC);
     S.omega_major = getenv("ALPS_B200_OMEGA_MAJOR") != nullptr;   // A/B knob: previous block order of k_quad_mma
@@ -1804,7 +1817,7 @@ static void disp_signature(std::vector<unsigned char>& sig, int n) {
                         S.d_relpart, S.d_reltick, S.h_pin, S.d_nh, S.d_ext};
   const long long ints[] = {S.gh.NI, S.gh.nspec, (long long)cur_nrtiles(), (long long)S.fitems.size(), S.mode,
                             S.qv.id, S.fast_variant, nsplit_rel(), (long long)S.bm_any, (long long)S.zc_off, (long long)S.fuse_off,
-                            (long long)S.pdl_on, (long long)S.early_off, (long long)S.spin_off, (long long)S.fork_off, (long long)S.reslat_gx, (long long)n};
+                            (long long)S.pdl_on, (long long)S.early_off, (long long)S.spin_off, (long long)S.fork_off, (long long)S.rel_rows_off, (long long)S.reslat_gx, (long long)n};
   sig.resize(sizeof(P) + sizeof(ptrs) + sizeof(ints));
   memcpy(sig.data(), &P, sizeof(P));
   memcpy(sig.data() + sizeof(P), ptrs, sizeof(ptrs));

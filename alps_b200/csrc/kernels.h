@@ -115,7 +115,8 @@ constexpr int PLAN_FUSED_MAX_OM = 8;
 constexpr int ZC_OM = 0, ZC_D = 16, ZC_ERR = 32, ZC_DOUBLES = 64;
 constexpr int CHAIN_PLAN = 0, CHAIN_QUAD = 1, CHAIN_RES = 2, CHAIN_INTS = 4;
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
-                 int* work, int* work_count, cudaStream_t st, double* om_stage = nullptr, int* plan_flag = nullptr);
+                 int* work, int* work_count, cudaStream_t st, double* om_stage = nullptr, int* plan_flag = nullptr,
+                 int* zero_ints = nullptr, int nzero = 0);   // fused variant: words it clears for the chain (k_rel_plan's counts)
 bool plan_fused_ok(const GlobalDev& gh, int n_om);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
@@ -154,6 +155,11 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
 // throughput class of the relativistic species (rel_kernel.cu): rflag n_om*ntiles bytes; rwork 2*n_om*ntiles ints (one
 // segment per tile); rcount ntiles ints; rpos 2*n_om*ntiles ints; dpart 2*n_om*ntiles*nsplitB*12 doubles would be the
 // worst case -- api.cu sizes it for REL_DPART_ENTRIES resonant entries per omega and falls back to launch_rel beyond
+void launch_rel_small(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
+                      int* err_flag, unsigned char* rflag, int* rwork, int* rcount, int* rpos, int nsplit, double* Mpart,
+                      int* tickets, int sm_count, bool zero_rcount, cudaStream_t st);   // n <= 64 omegas (rel_kernel.cu: k_rel_rows)
+int rel_rows_chunks(int ngamma);   // partial rows per resonant entry of launch_rel_small
+constexpr int REL_ROWS_MAXTILES = 1024;
 void launch_rel_tiled(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
                       int* err_flag, unsigned char* rflag, int* rwork, int* rcount, int* rpos, double* dpart, int nsplitB,
                       int sm_count, cudaStream_t st);

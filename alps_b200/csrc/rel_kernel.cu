@@ -152,6 +152,9 @@ struct RelCtx {
 // Node (ig, ip), sign sg: num = pref (om dfg + (kpar/vA) dfp) (numerator of resU_rel) and the six real Bessel
 // moments M = {J^2, J^2 p, J^2 p^2, J J' pp, J J' pp p, J'^2 pp^2} (J, J' with the sign rules for n < 0, pp =
 // pperpbar, p = pparbar) of which the six components of int_T_rel are constant multiples (moments_to_modes).
+// (the literal BESSJ per point is the fallback without the per-k tables: out of line, one copy, so that the kernels that
+// inline node_moments several times stay small -- their code runs from L2 when it runs once per launch)
+__device__ __noinline__ double bessj_cold(int n, double z) { return bessj_ref(n, z); }
 __device__ inline void node_moments(const RelCtx& c, int ig, int ip, int sg, double* M, cd& num) {
   const SpeciesDev& sp = *c.sp;
   const int ldr = c.g->npparbar + 1;
@@ -166,9 +169,9 @@ __device__ inline void node_moments(const RelCtx& c, int ig, int ip, int sg, dou
     jp = sp.Jrel[(size_t)(c.nabs + 1) * plane + o];
     jm = c.nabs >= 1 ? sp.Jrel[(size_t)(c.nabs - 1) * plane + o] : 0.0;
   } else {
-    j0 = bessj_ref(c.nabs, z);
-    jp = bessj_ref(c.nabs + 1, z);
-    jm = c.nabs >= 1 ? bessj_ref(c.nabs - 1, z) : 0.0;
+    j0 = bessj_cold(c.nabs, z);
+    jp = bessj_cold(c.nabs + 1, z);
+    jm = c.nabs >= 1 ? bessj_cold(c.nabs - 1, z) : 0.0;
   }
   double bj, bp;
   bessel_pair(c.nabs, sg, z, jm, j0, jp, bj, bp);
@@ -446,11 +449,16 @@ __device__ __forceinline__ void landau_rows(const RelCtx& c, const GlobalDev& g,
     const cd pres = (g1 * omc) * vA / kpar - mk((1.0 * nn) * qs * vA / (kpar * ms), 0.0);
     if (!(pres.x * pres.x <= g1 * g1 - 1.0)) continue;
     const double h = (ig == ng - 1) ? 0.5 : 1.0;
-    cd dfg;
-    if (ig == 1) dfg = (eval_fit_rel(g, sp, ig + 1, pres) - eval_fit_rel(g, sp, ig, pres)) / dgam;
-    else dfg = (eval_fit_rel(g, sp, ig + 1, pres) - eval_fit_rel(g, sp, ig - 1, pres)) / (2.0 * dgam);
-    const cd dfp = (eval_fit_rel(g, sp, ig, pres + mk(dpb, 0.0)) - eval_fit_rel(g, sp, ig, pres - mk(dpb, 0.0))) /
-                   (2.0 * dpb);
+    // the four fit evaluations of the two central differences: one copy of eval_fit_rel in the code
+    cd fv[4];
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      const int row = k == 0 ? ig + 1 : (k == 1 ? (ig == 1 ? ig : ig - 1) : ig);
+      const cd pk = k < 2 ? pres : (k == 2 ? pres + mk(dpb, 0.0) : pres - mk(dpb, 0.0));
+      fv[k] = eval_fit_rel(g, sp, row, pk);
+    }
+    const cd dfg = (ig == 1) ? (fv[0] - fv[1]) / dgam : (fv[0] - fv[1]) / (2.0 * dgam);
+    const cd dfp = (fv[2] - fv[3]) / (2.0 * dpb);
     const cd fac = -h * (omc * dfg + (kpar / vA) * dfp);
     // int_T_res_rel with complex-argument Bessel functions
     const cd pperpbar = csqrt_(mk(g1 * g1 - 1.0, 0.0) - pres * pres);
@@ -481,6 +489,145 @@ __device__ __forceinline__ void landau_rows(const RelCtx& c, const GlobalDev& g,
   for (int q = 0; q < 6; q++) acc.v[q] += cmul_i(L.v[q]) * mult;
 }
 
+// One Gamma row of integrate_res_rel (src/ALPS_fns_rel.f90:580-720) for a warp: the limits of integrate_resU_rel, the
+// direct part over the p_par-bar nodes (lanes) and the principal part (pv_row); adds the row's Bessel-moment sums to Sd.
+__device__ __forceinline__ void rel_res_row(const RelCtx& c, const GlobalDev& g, const SpeciesDev& sp, cd omc, int sg,
+                                            double nn, int ig, int lane, RelWin& win, Six2& Sd, int* __restrict__ err_flag) {
+  const int ng = g.ngamma, npb = g.npparbar, M_I = g.M_I, nabs = c.nabs;
+  const double qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar;
+  const double dpb = sp.dpparbar;
+  const double* pbv = sp.pbrel;
+  const int ldr = npb + 1;
+    const double wg = (ig == ng - 1) ? 1.0 : 2.0;
+    const double g1 = sp.grel[ig];
+    const cd pres = (g1 * omc - mk(nn * qs / ms, 0.0)) * vA / kpar;
+    int ires = 0, found = 0;
+    if (pres.x * pres.x <= g1 * g1 - 1.0) {
+      if (pres.x >= pbv[1] && pres.x < pbv[npb - 1]) {
+        int lo = 1, hi = npb - 2;
+        while (lo < hi) {
+          int mid = (lo + hi + 1) >> 1;
+          if (pbv[mid] <= pres.x) lo = mid; else hi = mid - 1;
+        }
+        if (pbv[lo + 1] > pres.x && pbv[lo] <= pres.x) {
+          ires = lo;
+          found = 1;
+        }
+      }
+    }
+    for (int ip = 0; ip <= M_I; ip++) {
+      if (pres.x >= pbv[0] - dpb * ip && pres.x < pbv[0] - dpb * (ip - 1)) {
+        ires = -ip;
+        found = 1;
+      }
+      if (pres.x >= pbv[npb - 1] + dpb * ip && pres.x < pbv[npb - 1] + dpb * (ip + 1)) {
+        ires = npb - 1 + ip;
+        found = 1;
+      }
+    }
+    const int lo_c = sp.cone_lo[ig], up_c = sp.cone_up[ig];
+    int int_start, int_end, lowerlimit, upperlimit;
+    if (found) {
+      int_start = lo_c;
+      int_end = up_c;
+      lowerlimit = ires - M_I;
+      upperlimit = ires + M_I + 1;
+      if (ires >= 0 && ires <= npb)
+        if (fabs(pres.x - pbv[ires]) > 0.5 * dpb) upperlimit = upperlimit + 1;
+      if (lowerlimit < lo_c && upperlimit > up_c) {
+        if (lane == 0) err_flag[0] = 8;   // alps_error(8)
+        return;
+      } else if (lowerlimit <= lo_c) {
+        int_start = 1;
+        lowerlimit = 0;
+        upperlimit = lo_c;
+      } else if (upperlimit >= up_c) {
+        lowerlimit = up_c;
+        upperlimit = npb;
+        int_end = npb - 1;
+      }
+    } else {
+      int_start = lo_c;
+      lowerlimit = up_c;
+      int_end = npb - 1;
+      upperlimit = npb;
+    }
+    // direct part
+    if (sp.Jrel) {
+      // hot loop: the six T components are real multiples of six Bessel moments (like the table species'
+      // p_par moments), so the loop accumulates sum U {J^2, J^2 p, J^2 p^2, J J' pp, J J' pp p, J'^2 pp^2}
+      // with one reciprocal per node; Bessel factors and pperpbar come from the per-k tables
+      const size_t plane = (size_t)(ng + 1) * ldr;
+      const double* __restrict__ J0 = sp.Jrel + (size_t)nabs * plane + (size_t)ig * ldr;
+      const double* __restrict__ JP = J0 + plane;
+      const double* __restrict__ JM = nabs >= 1 ? J0 - plane : J0;
+      const double* __restrict__ PP = sp.Jrel + (size_t)(sp.nhi + 2) * plane + (size_t)ig * ldr;
+      const double* __restrict__ DG = sp.dfg_rel + (size_t)ig * ldr;
+      const double* __restrict__ DP = sp.dfp_rel + (size_t)ig * ldr;
+      const cd gom = (g1 * omc) * vA / kpar;
+      const double nqv = nn * qs * vA / (kpar * ms), kv = kpar / vA, cw = wg * dpb;
+      const double par = (nabs & 1) ? -1.0 : 1.0;
+      // the node range with non-zero weight: the union of [int_start, lowerlimit] and [upperlimit, int_end];
+      // nodes in the gap between them have weight 0 and are predicated off, so the loads of two
+      // iterations can be in flight together
+      int a0 = npb, b0 = 0;
+      if (int_start <= lowerlimit) {
+        a0 = int_start;
+        b0 = lowerlimit;
+      }
+      if (upperlimit <= int_end) {
+        a0 = min(a0, upperlimit);
+        b0 = max(b0, int_end);
+      }
+      a0 = max(a0, 1);
+      b0 = min(b0, npb - 1);
+#pragma unroll 2
+      for (int ip = a0 + lane; ip <= b0; ip += 32) {
+        const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
+        const double j0 = J0[ip], jp = JP[ip], jm = nabs >= 1 ? JM[ip] : 0.0;
+        double bj, bp;
+        if (nabs == 0) {
+          bj = j0;
+          bp = -jp;
+        } else if (!sg) {
+          bj = j0;
+          bp = 0.5 * (jm - jp);
+        } else {
+          bj = par * j0;
+          bp = (nabs == 1) ? 0.5 * (jp - jm) : 0.5 * ((-par) * jp - (-par) * jm);
+        }
+        const double pb = pbv[ip], pq = PP[ip], dfg = DG[ip], dfp = DP[ip];
+        const double nr = c.pref * fma(omc.x, dfg, kv * dfp), ni = c.pref * (omc.y * dfg);
+        const double dr = pb - gom.x + nqv, di = -gom.y;
+        const double t = (w != 0.0) ? (cw * w) * fast_rcp(fma(dr, dr, di * di)) : 0.0;
+        const double ur = fma(nr, dr, ni * di) * t, ui = fma(ni, dr, -(nr * di)) * t;
+        const double b2 = bj * bj, bb = bj * bp * pq, q2 = (bp * pq) * (bp * pq);
+        const double b2p = b2 * pb, b2pp = b2p * pb, bbp = bb * pb;
+        Sd.v[0].x = fma(ur, b2, Sd.v[0].x);   Sd.v[0].y = fma(ui, b2, Sd.v[0].y);
+        Sd.v[1].x = fma(ur, b2p, Sd.v[1].x);  Sd.v[1].y = fma(ui, b2p, Sd.v[1].y);
+        Sd.v[2].x = fma(ur, b2pp, Sd.v[2].x); Sd.v[2].y = fma(ui, b2pp, Sd.v[2].y);
+        Sd.v[3].x = fma(ur, bb, Sd.v[3].x);   Sd.v[3].y = fma(ui, bb, Sd.v[3].y);
+        Sd.v[4].x = fma(ur, bbp, Sd.v[4].x);  Sd.v[4].y = fma(ui, bbp, Sd.v[4].y);
+        Sd.v[5].x = fma(ur, q2, Sd.v[5].x);   Sd.v[5].y = fma(ui, q2, Sd.v[5].y);
+      }
+    } else {
+      for (int ip = 1 + lane; ip <= npb - 1; ip += 32) {
+        const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
+        if (w == 0.0) continue;
+        double M[6];
+        cd num;
+        node_moments(c, ig, ip, sg, M, num);
+        const cd den = mk(pbv[ip], 0.0) - (g1 * omc) * vA / kpar + mk(nn * qs * vA / (kpar * ms), 0.0);
+        const cd U = (wg * dpb * w) * (num / den);
+#pragma unroll
+        for (int q = 0; q < 6; q++) Sd.v[q] += M[q] * U;
+      }
+    }
+    // principal part
+    if (found && lowerlimit >= int_start && upperlimit <= int_end)
+      pv_row(c, g, sp, omc, sg, nn, ig, ires, upperlimit, wg, win, lane, Sd);
+}
+
 constexpr int REL_THREADS = 256;
 
 // nsplit > 1 (few omegas in flight: sequential root finding is latency bound): the gamma rows / grid points
@@ -491,7 +638,10 @@ template <int MINB>
 __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
                                                      int n_om, const RelTile* __restrict__ tiles, int ntiles,
                                                      double* __restrict__ Mrel, int* __restrict__ err_flag, int nsplit,
-                                                     double* __restrict__ Mpart, int* __restrict__ tickets) {
+                                                     double* __restrict__ Mpart, int* __restrict__ tickets,
+                                                     const unsigned char* __restrict__ rflag, int skip_res) {
+  // rflag (from k_rel_plan): the resonance flags of every (omega, tile); skip_res: the resonant signs are left to
+  // k_rel_rows, which spreads their Gamma rows over the whole GPU
   const GlobalDev& g = *gp;
   pdl_trigger();
   pdl_wait();
@@ -521,7 +671,9 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
   __syncthreads();
 
   // ---- determine_resonances, relativistic branch: any (iperp, ipar) cell containing Re p_res
-  {
+  if (rflag) {
+    if (tid < 2) s_found[tid] = (rflag[(size_t)iom * ntiles + tile_id] >> tid) & 1;
+  } else {
     int fp = 0, fm = 0;
     for (int idx = tid; idx < (nperp + 1) * npar; idx += REL_THREADS) {
       const int iperp = idx / npar, ipar = idx - iperp * npar;
@@ -551,6 +703,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
   for (int sg = 0; sg < 2; sg++) {
     if (nabs == 0 && sg == 1) break;
     const double nn = sg ? -(double)nabs : (double)nabs;
+    if (s_found[sg] && skip_res) continue;
     Six2 acc;
     zero6(acc);
     if (!s_found[sg]) {
@@ -587,136 +740,8 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
       const int ldr = npb + 1;
       Six2 Sd;   // Bessel-moment sums of the direct and principal parts
       zero6(Sd);
-      for (int ig = 1 + warp + nwarps * js; ig <= ng - 1; ig += nwarps * nsplit) {
-        const double wg = (ig == ng - 1) ? 1.0 : 2.0;
-        const double g1 = sp.grel[ig];
-        const cd pres = (g1 * omc - mk(nn * qs / ms, 0.0)) * vA / kpar;
-        int ires = 0, found = 0;
-        if (pres.x * pres.x <= g1 * g1 - 1.0) {
-          if (pres.x >= pbv[1] && pres.x < pbv[npb - 1]) {
-            int lo = 1, hi = npb - 2;
-            while (lo < hi) {
-              int mid = (lo + hi + 1) >> 1;
-              if (pbv[mid] <= pres.x) lo = mid; else hi = mid - 1;
-            }
-            if (pbv[lo + 1] > pres.x && pbv[lo] <= pres.x) {
-              ires = lo;
-              found = 1;
-            }
-          }
-        }
-        for (int ip = 0; ip <= M_I; ip++) {
-          if (pres.x >= pbv[0] - dpb * ip && pres.x < pbv[0] - dpb * (ip - 1)) {
-            ires = -ip;
-            found = 1;
-          }
-          if (pres.x >= pbv[npb - 1] + dpb * ip && pres.x < pbv[npb - 1] + dpb * (ip + 1)) {
-            ires = npb - 1 + ip;
-            found = 1;
-          }
-        }
-        const int lo_c = sp.cone_lo[ig], up_c = sp.cone_up[ig];
-        int int_start, int_end, lowerlimit, upperlimit;
-        if (found) {
-          int_start = lo_c;
-          int_end = up_c;
-          lowerlimit = ires - M_I;
-          upperlimit = ires + M_I + 1;
-          if (ires >= 0 && ires <= npb)
-            if (fabs(pres.x - pbv[ires]) > 0.5 * dpb) upperlimit = upperlimit + 1;
-          if (lowerlimit < lo_c && upperlimit > up_c) {
-            if (lane == 0) err_flag[0] = 8;   // alps_error(8)
-            continue;
-          } else if (lowerlimit <= lo_c) {
-            int_start = 1;
-            lowerlimit = 0;
-            upperlimit = lo_c;
-          } else if (upperlimit >= up_c) {
-            lowerlimit = up_c;
-            upperlimit = npb;
-            int_end = npb - 1;
-          }
-        } else {
-          int_start = lo_c;
-          lowerlimit = up_c;
-          int_end = npb - 1;
-          upperlimit = npb;
-        }
-        // direct part
-        if (sp.Jrel) {
-          // hot loop: the six T components are real multiples of six Bessel moments (like the table species'
-          // p_par moments), so the loop accumulates sum U {J^2, J^2 p, J^2 p^2, J J' pp, J J' pp p, J'^2 pp^2}
-          // with one reciprocal per node; Bessel factors and pperpbar come from the per-k tables
-          const size_t plane = (size_t)(ng + 1) * ldr;
-          const double* __restrict__ J0 = sp.Jrel + (size_t)nabs * plane + (size_t)ig * ldr;
-          const double* __restrict__ JP = J0 + plane;
-          const double* __restrict__ JM = nabs >= 1 ? J0 - plane : J0;
-          const double* __restrict__ PP = sp.Jrel + (size_t)(sp.nhi + 2) * plane + (size_t)ig * ldr;
-          const double* __restrict__ DG = sp.dfg_rel + (size_t)ig * ldr;
-          const double* __restrict__ DP = sp.dfp_rel + (size_t)ig * ldr;
-          const cd gom = (g1 * omc) * vA / kpar;
-          const double nqv = nn * qs * vA / (kpar * ms), kv = kpar / vA, cw = wg * dpb;
-          const double par = (nabs & 1) ? -1.0 : 1.0;
-          // the node range with non-zero weight: the union of [int_start, lowerlimit] and [upperlimit, int_end];
-          // nodes in the gap between them have weight 0 and are predicated off, so the loads of two
-          // iterations can be in flight together
-          int a0 = npb, b0 = 0;
-          if (int_start <= lowerlimit) {
-            a0 = int_start;
-            b0 = lowerlimit;
-          }
-          if (upperlimit <= int_end) {
-            a0 = min(a0, upperlimit);
-            b0 = max(b0, int_end);
-          }
-          a0 = max(a0, 1);
-          b0 = min(b0, npb - 1);
-#pragma unroll 2
-          for (int ip = a0 + lane; ip <= b0; ip += 32) {
-            const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
-            const double j0 = J0[ip], jp = JP[ip], jm = nabs >= 1 ? JM[ip] : 0.0;
-            double bj, bp;
-            if (nabs == 0) {
-              bj = j0;
-              bp = -jp;
-            } else if (!sg) {
-              bj = j0;
-              bp = 0.5 * (jm - jp);
-            } else {
-              bj = par * j0;
-              bp = (nabs == 1) ? 0.5 * (jp - jm) : 0.5 * ((-par) * jp - (-par) * jm);
-            }
-            const double pb = pbv[ip], pq = PP[ip], dfg = DG[ip], dfp = DP[ip];
-            const double nr = c.pref * fma(omc.x, dfg, kv * dfp), ni = c.pref * (omc.y * dfg);
-            const double dr = pb - gom.x + nqv, di = -gom.y;
-            const double t = (w != 0.0) ? (cw * w) * fast_rcp(fma(dr, dr, di * di)) : 0.0;
-            const double ur = fma(nr, dr, ni * di) * t, ui = fma(ni, dr, -(nr * di)) * t;
-            const double b2 = bj * bj, bb = bj * bp * pq, q2 = (bp * pq) * (bp * pq);
-            const double b2p = b2 * pb, b2pp = b2p * pb, bbp = bb * pb;
-            Sd.v[0].x = fma(ur, b2, Sd.v[0].x);   Sd.v[0].y = fma(ui, b2, Sd.v[0].y);
-            Sd.v[1].x = fma(ur, b2p, Sd.v[1].x);  Sd.v[1].y = fma(ui, b2p, Sd.v[1].y);
-            Sd.v[2].x = fma(ur, b2pp, Sd.v[2].x); Sd.v[2].y = fma(ui, b2pp, Sd.v[2].y);
-            Sd.v[3].x = fma(ur, bb, Sd.v[3].x);   Sd.v[3].y = fma(ui, bb, Sd.v[3].y);
-            Sd.v[4].x = fma(ur, bbp, Sd.v[4].x);  Sd.v[4].y = fma(ui, bbp, Sd.v[4].y);
-            Sd.v[5].x = fma(ur, q2, Sd.v[5].x);   Sd.v[5].y = fma(ui, q2, Sd.v[5].y);
-          }
-        } else {
-          for (int ip = 1 + lane; ip <= npb - 1; ip += 32) {
-            const double w = piece_w(ip, int_start, lowerlimit) + piece_w(ip, upperlimit, int_end);
-            if (w == 0.0) continue;
-            double M[6];
-            cd num;
-            node_moments(c, ig, ip, sg, M, num);
-            const cd den = mk(pbv[ip], 0.0) - (g1 * omc) * vA / kpar + mk(nn * qs * vA / (kpar * ms), 0.0);
-            const cd U = (wg * dpb * w) * (num / den);
-#pragma unroll
-            for (int q = 0; q < 6; q++) Sd.v[q] += M[q] * U;
-          }
-        }
-        // principal part
-        if (found && lowerlimit >= int_start && upperlimit <= int_end)
-          pv_row(c, g, sp, omc, sg, nn, ig, ires, upperlimit, wg, s_win[warp], lane, Sd);
-      }
+      for (int ig = 1 + warp + nwarps * js; ig <= ng - 1; ig += nwarps * nsplit)
+        rel_res_row(c, g, sp, omc, sg, nn, ig, lane, s_win[warp], Sd, err_flag);
       // moment sums of the direct and principal parts -> tensor components
       moments_to_modes(c, nn, Sd, acc);
 #pragma unroll
@@ -752,7 +777,7 @@ __global__ void __launch_bounds__(REL_THREADS, MINB) k_rel(const GlobalDev* __re
       __threadfence();
       if (tid < 24) {
         const int sg = tid / 12, q = tid % 12;
-        if (!(nabs == 0 && sg == 1)) {
+        if (!(nabs == 0 && sg == 1) && !(s_found[sg] && skip_res)) {
           const size_t item = (size_t)iom * g.NI + sp.item_base + 2 * nabs + sg;
           double t = 0.0;
           for (int j = 0; j < nsplit; j++) t += __ldcg(Mpart + (item * nsplit + j) * 12 + q);
@@ -787,6 +812,10 @@ __global__ void __launch_bounds__(256) k_rel_plan(const GlobalDev* __restrict__ 
                                                   int* __restrict__ rcount, int* __restrict__ rpos) {
   const GlobalDev& g = *gp;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  // (small batches launch it programmatically inside the captured chain: completion of this kernel must imply that of
+  // its predecessors)
+  pdl_trigger();
+  pdl_wait();
   if (w >= n_om * ntiles) return;
   const int iom = w / ntiles, tile_id = w % ntiles;
   const RelTile tl = tiles[tile_id];
@@ -809,6 +838,45 @@ __global__ void __launch_bounds__(256) k_rel_plan(const GlobalDev* __restrict__ 
     rflag[w] = (unsigned char)(fp | (fm << 1));
     // the resonant (omega, sign) entries of a tile: one segment of 2 n_om slots per tile, filled in any order (every
     // entry is evaluated on its own), and where each entry sits (k_rel_tiled collects its partial rows from there)
+    int* seg = rwork + (size_t)tile_id * 2 * n_om;
+    int pp = -1, pm = -1;
+    if (fp) seg[pp = atomicAdd(rcount + tile_id, 1)] = (iom << 1);
+    if (fm) seg[pm = atomicAdd(rcount + tile_id, 1)] = (iom << 1) | 1;
+    rpos[2 * (size_t)w] = pp;
+    rpos[2 * (size_t)w + 1] = pm;
+  }
+}
+
+// The same flags and lists with one 256-thread block per (omega, tile): small batches have few (omega, tile) pairs and
+// the 1860-cell scan of a warp is then a chain of its own (12 us on C3)
+__global__ void __launch_bounds__(256) k_rel_plan_blk(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
+                                                      int n_om, const RelTile* __restrict__ tiles, int ntiles,
+                                                      unsigned char* __restrict__ rflag, int* __restrict__ rwork,
+                                                      int* __restrict__ rcount, int* __restrict__ rpos) {
+  const GlobalDev& g = *gp;
+  pdl_trigger();
+  pdl_wait();
+  const int w = blockIdx.x, tid = threadIdx.x;
+  const int iom = w / ntiles, tile_id = w % ntiles;
+  const RelTile tl = tiles[tile_id];
+  const SpeciesDev& sp = g.sp[tl.s];
+  const int nabs = tl.nabs, nperp = g.nperp, npar = g.npar;
+  const double omr = om[2 * iom], qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar;
+  int fp = 0, fm = 0;
+  for (int idx = tid; idx < (nperp + 1) * npar; idx += 256) {
+    const int iperp = idx / npar, ipar = idx - iperp * npar;
+    const double pp1 = sp.pperp[iperp], pp2 = sp.ppar[ipar];
+    const double gamma = sqrt((pp1 * pp1 + pp2 * pp2) * (vA * vA) / (ms * ms) + 1.0);
+    const double prp = (gamma * ms * omr - 1.0 * nabs * qs) / kpar;
+    const double prm = (gamma * ms * omr + 1.0 * nabs * qs) / kpar;
+    if (sp.ppar[ipar] <= prp && sp.ppar[ipar + 1] > prp) fp = 1;
+    if (sp.ppar[ipar] <= prm && sp.ppar[ipar + 1] > prm) fm = 1;
+  }
+  fp = __syncthreads_or(fp);
+  fm = __syncthreads_or(fm);
+  if (nabs == 0) fm = 0;
+  if (tid == 0) {
+    rflag[w] = (unsigned char)((fp ? 1 : 0) | (fm ? 2 : 0));
     int* seg = rwork + (size_t)tile_id * 2 * n_om;
     int pp = -1, pm = -1;
     if (fp) seg[pp = atomicAdd(rcount + tile_id, 1)] = (iom << 1);
@@ -1262,6 +1330,214 @@ __global__ void __launch_bounds__(REL_THREADS, MINB)
   }
 }
 
+// The non-resonant signs of a small batch: integrate() on the (p_perp, p_par) grid with gamma in resU, exactly the
+// non-resonant branch of k_rel (same operations, same split of the nodes over nsplit CTAs and the same order of the
+// partial rows) as a kernel of its own -- a few hundred instructions instead of k_rel's thousands, which matters for
+// code that runs once per launch, from L2.
+__global__ void __launch_bounds__(REL_THREADS) k_rel_nonres(const GlobalDev* __restrict__ gp, const double* __restrict__ om,
+                                                            int n_om, const RelTile* __restrict__ tiles, int ntiles,
+                                                            double* __restrict__ Mrel, int nsplit, double* __restrict__ Mpart,
+                                                            int* __restrict__ tickets, const unsigned char* __restrict__ rflag) {
+  const GlobalDev& g = *gp;
+  pdl_trigger();
+  pdl_wait();
+  const int js = blockIdx.x % nsplit;
+  const int iom = (blockIdx.x / nsplit) / ntiles;
+  const int tile_id = (blockIdx.x / nsplit) % ntiles;
+  const RelTile tl = tiles[tile_id];
+  const SpeciesDev& sp = g.sp[tl.s];
+  const int nabs = tl.nabs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = REL_THREADS / 32;
+  const cd omc = mk(om[2 * iom], om[2 * iom + 1]);
+  const int nperp = g.nperp, npar = g.npar;
+  const double qs = sp.qs, ms = sp.ms, vA = g.vA, kpar = g.kpar, kperp = g.kperp;
+  const int found = rflag[(size_t)iom * ntiles + tile_id];
+  __shared__ cd s_red[REL_THREADS / 32][6];
+  __shared__ int s_last;
+  const double kf1 = g.kperp_norm ? 1.0 : kperp, kf2 = g.kperp_norm ? 1.0 : kperp * kperp;
+  const double zb = g.kperp_norm ? kperp / qs : 1.0 / qs;
+  const double* Jn = sp.J + (size_t)(nabs + 1) * sp.ldj;
+  const double* Jm = sp.J + (size_t)nabs * sp.ldj;
+  const double* Jp = sp.J + (size_t)(nabs + 2) * sp.ldj;
+#pragma unroll 1
+  for (int sg = 0; sg < 2; sg++) {
+    if (nabs == 0 && sg == 1) break;
+    if ((found >> sg) & 1) continue;       // resonant: k_rel_rows
+    const double nn = sg ? -(double)nabs : (double)nabs;
+    Six2 acc;
+    zero6(acc);
+#pragma unroll 1
+    for (int idx = tid + REL_THREADS * js; idx < (nperp - 1) * (npar - 1); idx += REL_THREADS * nsplit) {
+      const int iperp = idx / (npar - 1) + 1, ipar = idx % (npar - 1) + 1;
+      const double wperp = (iperp == nperp - 1) ? 1.0 : 2.0;
+      const double wpar = (ipar == 1 || ipar == npar - 1) ? 1.0 : 2.0;
+      const double pp1 = sp.pperp[iperp], pp2 = sp.ppar[ipar];
+      const double gamma = sqrt((pp1 * pp1 + pp2 * pp2) * (vA * vA) / (ms * ms) + 1.0);
+      const size_t o = (size_t)(iperp - 1) * sp.ldp + (ipar - 1);
+      // resU = (om A' + (kpar/gamma) C0) / (gamma ms om - kpar p_par - n qs)
+      const cd num = omc * sp.A[o] + mk((kpar / gamma) * sp.C0[o], 0.0);
+      const cd den = mk(gamma * ms * omc.x - kpar * pp2 - nn * qs, gamma * ms * omc.y);
+      const cd U = (wperp * wpar) * (num / den);
+      double bj, bp;
+      bessel_pair(nabs, sg, 0.0, nabs >= 1 ? Jm[iperp] : 0.0, Jn[iperp], Jp[iperp], bj, bp);
+      Six2 T;
+      modes_real(bj, bp, pp1, pp2, zb, nn, kf1, kf2, T);
+#pragma unroll
+      for (int q = 0; q < 6; q++) acc.v[q] += U * T.v[q];
+    }
+    const double fac = 2.0 * PI_ * sp.dpperp * sp.dppar_abs * 0.25;
+#pragma unroll
+    for (int q = 0; q < 6; q++) acc.v[q] = fac * acc.v[q];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      cd v = warp_sum_cd(acc.v[q]);
+      if (lane == 0) s_red[warp][q] = v;
+    }
+    __syncthreads();
+    if (tid < 6) {
+      cd t = mk(0.0, 0.0);
+      for (int w = 0; w < nwarps; w++) t += s_red[w][tid];
+      const size_t item = (size_t)iom * g.NI + sp.item_base + 2 * nabs + sg;
+      double* o = (nsplit == 1) ? Mrel + item * 12 : Mpart + (item * nsplit + js) * 12;
+      o[2 * tid] = t.x;
+      o[2 * tid + 1] = t.y;
+    }
+    __syncthreads();
+  }
+  if (nsplit > 1) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&tickets[iom * ntiles + tile_id], 1) == nsplit - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (tid < 24) {
+        const int sg = tid / 12, q = tid % 12;
+        if (!(nabs == 0 && sg == 1) && !((found >> sg) & 1)) {
+          const size_t item = (size_t)iom * g.NI + sp.item_base + 2 * nabs + sg;
+          double t = 0.0;
+          for (int j = 0; j < nsplit; j++) t += __ldcg(Mpart + (item * nsplit + j) * 12 + q);
+          Mrel[item * 12 + q] = t;
+        }
+      }
+      if (tid == 0) tickets[iom * ntiles + tile_id] = 0;   // ready for the next launch
+    }
+  }
+}
+
+// Small batches (n <= 64 omegas: sequential root finding): the resonant (omega, species, |n|, sign) entries that
+// k_rel_plan lists are few, and each is a chain of ~500 Gamma rows per warp when it is left to the CTAs of its own tile
+// (k_rel) -- the critical path of a relativistic disp().  Here their rows are dealt in chunks of RR_CH to ALL the CTAs of
+// a persistent grid: work item = (entry, chunk); a CTA leaves the chunk's tensor components (direct + principal part of
+// its rows, Landau term of its rows) in Mpart and the last chunk of an entry to finish (ticket) adds the chunks in order.
+constexpr int RR_CH = 8;           // Gamma rows per work item: one per warp
+constexpr int RR_MAXTILES = 1024;  // (species, |n|) tiles the prefix table holds
+template <int MINB>
+__global__ void __launch_bounds__(REL_THREADS, MINB)
+    k_rel_rows(const GlobalDev* __restrict__ gp, const double* __restrict__ om, int n_om, const RelTile* __restrict__ tiles,
+               int ntiles, double* __restrict__ Mrel, int* __restrict__ err_flag, const int* __restrict__ rwork,
+               const int* __restrict__ rcount, double* __restrict__ Mpart, int* __restrict__ tickets) {
+  const GlobalDev& g = *gp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = REL_THREADS / 32;
+  __shared__ int s_pref[RR_MAXTILES + 1];
+  __shared__ cd s_red[REL_THREADS / 32][6];
+  __shared__ RelWin s_win[REL_THREADS / 32];
+  __shared__ double s_rfact[21], s_rgam[23];
+  __shared__ int s_last;
+  pdl_trigger();
+  pdl_wait();
+  for (int t = tid; t < ntiles; t += REL_THREADS) s_pref[t + 1] = rcount[t];
+  if (tid == 0) s_pref[0] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (int t = 0; t < ntiles; t++) s_pref[t + 1] += s_pref[t];
+  __syncthreads();
+  const int ng = g.ngamma;
+  const int nch = (ng - 1 + RR_CH - 1) / RR_CH;
+  const long long total = (long long)s_pref[ntiles] * nch;
+  const double vA = g.vA, kpar = g.kpar, kperp = g.kperp;
+  int last_nabs = -1;
+  for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+    const int e = (int)(w / nch), ch = (int)(w - (long long)e * nch);
+    int lo = 0, hi = ntiles - 1;      // the tile whose segment holds entry e
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_pref[mid + 1] > e) hi = mid; else lo = mid + 1;
+    }
+    const int tile_id = lo;
+    const int ecode = rwork[(size_t)tile_id * 2 * n_om + (e - s_pref[tile_id])];
+    const int iom = ecode >> 1, sg = ecode & 1;
+    const RelTile tl = tiles[tile_id];
+    const SpeciesDev& sp = g.sp[tl.s];
+    const int nabs = tl.nabs;
+    const double qs = sp.qs, ms = sp.ms;
+    const cd omc = mk(om[2 * iom], om[2 * iom + 1]);
+    if (nabs != last_nabs) {      // series coefficients of the Landau term: 1/k!, 1/Gamma(|n| + i)
+      __syncthreads();
+      if (tid < 21) {
+        double fact = 1.0;
+        for (int k = 2; k <= tid; k++) fact = fact * (1.0 * k);
+        s_rfact[tid] = 1.0 / fact;
+      } else if (tid >= 32 && tid < 32 + 23) {
+        const int m = nabs + (tid - 32);
+        s_rgam[tid - 32] = m >= 1 ? 1.0 / gamma_ref(1.0 * m) : 0.0;
+      }
+      __syncthreads();
+      last_nabs = nabs;
+    }
+    RelCtx c;
+    c.g = gp;
+    c.sp = &sp;
+    c.om = omc;
+    c.nabs = nabs;
+    c.pref = -2.0 * PI_ * ((ms / vA) * (ms / vA) * (ms / vA)) * (qs * vA / (kpar * ms));
+    c.zfac = kperp * ms / (vA * qs);
+    c.zbar = g.kperp_norm ? kperp * ms / (vA * qs) : ms / (vA * qs);
+    c.kf1 = g.kperp_norm ? 1.0 : kperp;
+    c.kf2 = g.kperp_norm ? 1.0 : kperp * kperp;
+    const double nn = sg ? -(double)nabs : (double)nabs;
+    Six2 Sd, acc;
+    zero6(Sd);
+    const int row0 = 1 + ch * RR_CH, row1 = min(ng - 1, row0 + RR_CH - 1);
+    for (int ig = row0 + warp; ig <= row1; ig += nwarps) rel_res_row(c, g, sp, omc, sg, nn, ig, lane, s_win[warp], Sd, err_flag);
+    moments_to_modes(c, nn, Sd, acc);
+#pragma unroll
+    for (int q = 0; q < 6; q++) acc.v[q] = (sp.dgamma * 0.25) * acc.v[q];
+    // landau_integrate_rel (Im om <= 0): one thread per row of the chunk
+    if (omc.y <= 0.0 && tid < RR_CH && row0 + tid <= row1)
+      landau_rows(c, g, sp, omc, sg, nn, row0 - 1 + tid, ng, s_rfact, s_rgam, acc);
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      cd v = warp_sum_cd(acc.v[q]);
+      if (lane == 0) s_red[warp][q] = v;
+    }
+    __syncthreads();
+    const size_t item = (size_t)iom * g.NI + sp.item_base + 2 * nabs + sg;
+    if (tid < 6) {
+      cd t = mk(0.0, 0.0);
+      for (int ww = 0; ww < nwarps; ww++) t += s_red[ww][tid];
+      double* o = Mpart + (item * nch + ch) * 12;
+      o[2 * tid] = t.x;
+      o[2 * tid + 1] = t.y;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&tickets[item], 1) == nch - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (tid < 12) {
+        double t = 0.0;
+        for (int j = 0; j < nch; j++) t += __ldcg(Mpart + (item * nch + j) * 12 + tid);
+        Mrel[item * 12 + tid] = t;
+      }
+      if (tid == 0) tickets[item] = 0;   // ready for the next launch
+    }
+    __syncthreads();
+  }
+}
+int rel_rows_chunks(int ngamma) { return (ngamma - 1 + RR_CH - 1) / RR_CH; }
+
 // Bessel factors of int_T_rel (src/ALPS_fns_rel.f90:1297-1322) depend on (igamma, ipparbar) through
 // pperpbar = sqrt(gamma^2 - 1 - pparbar^2) but not on omega: tabulated once per k with the same literal BESSJ.
 // Planes 0..nmaxord hold J_n, plane nmaxord + 1 holds pperpbar.
@@ -1311,6 +1587,30 @@ __global__ void k_int_ee_rel(const double* __restrict__ pbv, const double* __res
   }
 }
 
+// small batches: resonance flags + entry lists (k_rel_plan), the non-resonant signs per tile (k_rel), the rows of the
+// resonant entries over the whole GPU (k_rel_rows).  rcount must be zero when k_rel_plan starts: zero_rcount, or the
+// chain's k_plan has cleared it (launch_plan).
+void launch_rel_small(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
+                      int* err_flag, unsigned char* rflag, int* rwork, int* rcount, int* rpos, int nsplit, double* Mpart,
+                      int* tickets, int sm_count, bool zero_rcount, cudaStream_t st) {
+  if (n_om <= 0 || ntiles <= 0) return;
+  if (zero_rcount) cudaMemsetAsync(rcount, 0, (size_t)ntiles * sizeof(int), st);
+  launch_chain(k_rel_plan_blk, dim3(n_om * ntiles), dim3(256), 0, st, g, om, n_om, tiles, ntiles, rflag, rwork, rcount, rpos);
+  if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
+  launch_chain(k_rel_nonres, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel, nsplit,
+               Mpart, tickets, (const unsigned char*)rflag);
+  const int sms = sm_count > 0 ? sm_count : 148;
+  // one or two omegas: few work items, 255 registers and one CTA per SM; more: two CTAs of 128 registers per SM (the same
+  // operations in the same order either way)
+  static const char* rb = getenv("ALPS_B200_REL_ROWS_MINB");   // A/B knob: "1" / "2" forces the variant
+  const bool two = rb ? rb[0] == '2' : n_om > 2;
+  if (two)
+    launch_chain(k_rel_rows<2>, dim3(2 * sms), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel, err_flag,
+                 (const int*)rwork, (const int*)rcount, Mpart, tickets);
+  else
+    launch_chain(k_rel_rows<1>, dim3(sms), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel, err_flag,
+                 (const int*)rwork, (const int*)rcount, Mpart, tickets);
+}
 void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
                 int* err_flag, int nsplit, double* Mpart, int* tickets, cudaStream_t st) {
   if (n_om <= 0 || ntiles <= 0) return;
@@ -1320,10 +1620,10 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
   // finish sooner (the same operations in the same order: the results do not depend on the choice)
   if ((long long)n_om * ntiles * nsplit <= 3 * 148 || (force && force[0] == '1'))
     launch_chain(k_rel<1>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
-                 err_flag, nsplit, Mpart, tickets);
+                 err_flag, nsplit, Mpart, tickets, (const unsigned char*)nullptr, 0);
   else
     launch_chain(k_rel<2>, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel,
-                 err_flag, nsplit, Mpart, tickets);
+                 err_flag, nsplit, Mpart, tickets, (const unsigned char*)nullptr, 0);
 }
 // throughput class: resonance flags + work list, principal-value / Landau parts of the listed entries, omega-tiled rest
 // (three launches; rflag: n_om * ntiles bytes, rwork: 2 * n_om * ntiles ints, rcount: one int)

@@ -200,18 +200,20 @@ __device__ __forceinline__ void plan_item(const GlobalDev& g, const double* om, 
 template <bool FUSED>
 __global__ void __launch_bounds__(FUSED ? 1024 : 256)
 k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n_om, PlanEntry* __restrict__ plan,
-       int* __restrict__ work, int* __restrict__ work_count, double* __restrict__ om_stage, int* plan_flag) {
+       int* __restrict__ work, int* __restrict__ work_count, double* __restrict__ om_stage, int* plan_flag,
+       int* __restrict__ zero_ints, int nzero) {
   const GlobalDev& g = *gp;
   __shared__ double s_om[FUSED ? 2 * PLAN_FUSED_MAX_OM : 2];
   const double* om = om_in;
   if (FUSED) {
+    for (int t = threadIdx.x; t < nzero; t += blockDim.x) zero_ints[t] = 0;   // (counts of k_rel_plan, relativistic species)
     if (threadIdx.x == 0) {
       lat_stamp(g, 0);
       *reinterpret_cast<volatile int*>(plan_flag) = 0;
       *reinterpret_cast<volatile int*>(plan_flag + CHAIN_QUAD) = 0;   // CTAs of k_quad_mma that have written their sums
       *reinterpret_cast<volatile int*>(plan_flag + CHAIN_RES) = 0;    // blocks of k_resonant_lat that have finished
-      __threadfence();
     }
+    __threadfence();
     __syncthreads();
     pdl_trigger();
     if (threadIdx.x < 2 * n_om) {
@@ -1448,15 +1450,15 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
 
 // ------------------------------------------------------------------ launchers
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan, int* work,
-                 int* work_count, cudaStream_t st, double* om_stage, int* plan_flag) {
+                 int* work_count, cudaStream_t st, double* om_stage, int* plan_flag, int* zero_ints, int nzero) {
   size_t total = (size_t)n_om * gh.NI;
   if (om_stage) {   // fused single-block variant: caller checked plan_fused_ok()
-    k_plan<true><<<1, 1024, 0, st>>>(g, om, n_om, plan, work, work_count, om_stage, plan_flag);
+    k_plan<true><<<1, 1024, 0, st>>>(g, om, n_om, plan, work, work_count, om_stage, plan_flag, zero_ints, nzero);
     return;
   }
   cudaMemsetAsync(work_count, 0, sizeof(int), st);
   if (!total) return;
-  k_plan<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, om, n_om, plan, work, work_count, nullptr, nullptr);
+  k_plan<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, om, n_om, plan, work, work_count, nullptr, nullptr, nullptr, 0);
 }
 bool plan_fused_ok(const GlobalDev& gh, int n_om) {
   return n_om >= 1 && n_om <= PLAN_FUSED_MAX_OM && (size_t)n_om * gh.NI <= 1024;
