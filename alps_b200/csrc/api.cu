@@ -534,10 +534,11 @@ int ensure_batch(int want) {
   if (any_rel) {
     // sized for the largest split (16) and any harmonic shard (tiles <= NI)
     const size_t nt = (size_t)SMALL_BATCH * NI;
-    const size_t parts = (size_t)std::max(16, rel_rows_chunks(S.gh.ngamma));   // Gamma split of k_rel / chunks of k_rel_rows
-    if (dalloc(&S.d_relpart, (size_t)SMALL_BATCH * NI * parts * 12) || dalloc(&S.d_reltick, nt))
+    // partial rows / tickets: [Gamma split of k_rel or k_rel_nonres: 16 rows per item][chunks of k_rel_rows]
+    const size_t parts = 16 + (size_t)rel_rows_chunks(S.gh.ngamma);
+    if (dalloc(&S.d_relpart, (size_t)SMALL_BATCH * NI * parts * 12) || dalloc(&S.d_reltick, 2 * nt))
       return ALPS_B200_ERR_CUDA;
-    CK(cudaMemsetAsync(S.d_reltick, 0, nt * sizeof(int), S.stream));
+    CK(cudaMemsetAsync(S.d_reltick, 0, 2 * nt * sizeof(int), S.stream));
     if (dalloc(&S.d_relflag, B * NI) || dalloc(&S.d_relwork, 2 * B * NI) || dalloc(&S.d_relcount, NI) ||
         dalloc(&S.d_relpos, 2 * B * NI))
       return ALPS_B200_ERR_CUDA;
@@ -737,7 +738,8 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
         S.launches += 4;
       } else if (rel_rows) {
         launch_rel_small(gd, d_om, n, cur_rtiles(), (int)nt, S.d_Sres, S.d_err + 6, S.d_relflag, S.d_relwork, S.d_relcount,
-                         S.d_relpos, rsplit, S.d_relpart, S.d_reltick, S.sm_count, !S.zc, S.stream);
+                         S.d_relpos, rsplit, S.d_relpart, S.d_reltick, (size_t)SMALL_BATCH * S.gh.NI * 16 * 12,
+                         (size_t)SMALL_BATCH * S.gh.NI, S.sm_count, !S.zc, S.stream);
         S.launches += 3;
       } else {
         launch_rel(gd, d_om, n, cur_rtiles(), cur_nrtiles(), S.d_Sres, S.d_err + 6, rsplit, S.d_relpart,

@@ -157,7 +157,8 @@ void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* t
 // worst case -- api.cu sizes it for REL_DPART_ENTRIES resonant entries per omega and falls back to launch_rel beyond
 void launch_rel_small(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
                       int* err_flag, unsigned char* rflag, int* rwork, int* rcount, int* rpos, int nsplit, double* Mpart,
-                      int* tickets, int sm_count, bool zero_rcount, cudaStream_t st);   // n <= 64 omegas (rel_kernel.cu: k_rel_rows)
+                      int* tickets, size_t rows_part_offset, size_t rows_ticket_offset, int sm_count, bool zero_rcount,
+                      cudaStream_t st);   // n <= 64 omegas (rel_kernel.cu: k_rel_rows)
 int rel_rows_chunks(int ngamma);   // partial rows per resonant entry of launch_rel_small
 constexpr int REL_ROWS_MAXTILES = 1024;
 void launch_rel_tiled(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,

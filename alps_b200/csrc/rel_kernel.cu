@@ -1339,8 +1339,9 @@ __global__ void __launch_bounds__(REL_THREADS) k_rel_nonres(const GlobalDev* __r
                                                             double* __restrict__ Mrel, int nsplit, double* __restrict__ Mpart,
                                                             int* __restrict__ tickets, const unsigned char* __restrict__ rflag) {
   const GlobalDev& g = *gp;
+  // launched after k_rel_rows has seen k_rel_plan_blk complete (see there): the flags are final; the wait at the end
+  // makes this kernel's completion imply that of k_rel_rows
   pdl_trigger();
-  pdl_wait();
   const int js = blockIdx.x % nsplit;
   const int iom = (blockIdx.x / nsplit) / ntiles;
   const int tile_id = (blockIdx.x / nsplit) % ntiles;
@@ -1423,6 +1424,7 @@ __global__ void __launch_bounds__(REL_THREADS) k_rel_nonres(const GlobalDev* __r
       if (tid == 0) tickets[iom * ntiles + tile_id] = 0;   // ready for the next launch
     }
   }
+  pdl_wait();
 }
 
 // Small batches (n <= 64 omegas: sequential root finding): the resonant (omega, species, |n|, sign) entries that
@@ -1444,8 +1446,10 @@ __global__ void __launch_bounds__(REL_THREADS, MINB)
   __shared__ RelWin s_win[REL_THREADS / 32];
   __shared__ double s_rfact[21], s_rgam[23];
   __shared__ int s_last;
-  pdl_trigger();
+  // (its dependent, k_rel_nonres, needs k_rel_plan_blk's flags and nothing of this kernel: it may start once this kernel
+  // has seen k_rel_plan_blk complete, and runs beside it)
   pdl_wait();
+  pdl_trigger();
   for (int t = tid; t < ntiles; t += REL_THREADS) s_pref[t + 1] = rcount[t];
   if (tid == 0) s_pref[0] = 0;
   __syncthreads();
@@ -1592,13 +1596,13 @@ __global__ void k_int_ee_rel(const double* __restrict__ pbv, const double* __res
 // chain's k_plan has cleared it (launch_plan).
 void launch_rel_small(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
                       int* err_flag, unsigned char* rflag, int* rwork, int* rcount, int* rpos, int nsplit, double* Mpart,
-                      int* tickets, int sm_count, bool zero_rcount, cudaStream_t st) {
+                      int* tickets, size_t rows_part_offset, size_t rows_ticket_offset, int sm_count, bool zero_rcount,
+                      cudaStream_t st) {
   if (n_om <= 0 || ntiles <= 0) return;
   if (zero_rcount) cudaMemsetAsync(rcount, 0, (size_t)ntiles * sizeof(int), st);
   launch_chain(k_rel_plan_blk, dim3(n_om * ntiles), dim3(256), 0, st, g, om, n_om, tiles, ntiles, rflag, rwork, rcount, rpos);
   if (nsplit < 1 || !Mpart || !tickets) nsplit = 1;
-  launch_chain(k_rel_nonres, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel, nsplit,
-               Mpart, tickets, (const unsigned char*)rflag);
+  // k_rel_rows and k_rel_nonres run side by side: separate partial rows and tickets (the caller sizes both for two users)
   const int sms = sm_count > 0 ? sm_count : 148;
   // one or two omegas: few work items, 255 registers and one CTA per SM; more: two CTAs of 128 registers per SM (the same
   // operations in the same order either way)
@@ -1606,10 +1610,12 @@ void launch_rel_small(const GlobalDev* g, const double* om, int n_om, const RelT
   const bool two = rb ? rb[0] == '2' : n_om > 2;
   if (two)
     launch_chain(k_rel_rows<2>, dim3(2 * sms), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel, err_flag,
-                 (const int*)rwork, (const int*)rcount, Mpart, tickets);
+                 (const int*)rwork, (const int*)rcount, Mpart + rows_part_offset, tickets + rows_ticket_offset);
   else
     launch_chain(k_rel_rows<1>, dim3(sms), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel, err_flag,
-                 (const int*)rwork, (const int*)rcount, Mpart, tickets);
+                 (const int*)rwork, (const int*)rcount, Mpart + rows_part_offset, tickets + rows_ticket_offset);
+  launch_chain(k_rel_nonres, dim3(n_om * ntiles * nsplit), dim3(REL_THREADS), 0, st, g, om, n_om, tiles, ntiles, Mrel, nsplit,
+               Mpart, tickets, (const unsigned char*)rflag);
 }
 void launch_rel(const GlobalDev* g, const double* om, int n_om, const RelTile* tiles, int ntiles, double* Mrel,
                 int* err_flag, int nsplit, double* Mpart, int* tickets, cudaStream_t st) {
