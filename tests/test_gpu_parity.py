@@ -162,6 +162,45 @@ def test_relativistic_error_8_is_reported_like_the_reference():
         sol.close()
 
 
+def test_relativistic_small_batches_every_size(monkeypatch):
+    """Batches of 1 .. 64 omegas of a relativistic pair plasma: k_rel_plan_blk + k_rel_rows (the rows of the resonant
+    entries over the whole GPU, both register variants) + k_rel_nonres against the oracle, and against the path that leaves
+    the rows to the CTAs of their tile (ALPS_B200_REL_ROWS=0).  Oblique k: a dozen harmonics per species, several of them
+    resonant, resonances inside the cone for many Gamma rows; omegas with Im > 0, = 0 and < 0 (Landau rows)."""
+    from alps_b200.solver import Solver
+    from oracle.oracle import Oracle
+    pl = tables.config_relativistic(nperp=20, npar=40, ngamma=120, npparbar=400)
+    kperp, kpar = 0.4, 0.3
+    base = [1.0 - 1.655e-6j, 0.5 + 0.01j, 0.3 - 0.02j, 0.8 + 0.0j, 1.7 - 0.05j]
+    oms = np.array([base[i % len(base)] * (1.0 + 0.003 * (i // len(base))) for i in range(64)])
+    orc = Oracle(pl)
+    orc.set_k(kperp, kpar)
+    want = {i: orc.disp(complex(oms[i]), full=True) for i in (0, 1, 2, 3, 4, 7, 19, 63)}
+    got = {}
+    for rows in ("1", "0"):
+        monkeypatch.setenv("ALPS_B200_REL_ROWS", rows)
+        sol = Solver(pl)
+        try:
+            sol.set_k(kperp, kpar)
+            out = {n: sol.disp_batch(oms[:n]) for n in (1, 2, 3, 8, 20, 64)}
+            out["single"] = np.array([[sol.disp(complex(o)) for _ in range(3)][-1] for o in oms[:5]])   # replayed chain
+            got[rows] = out
+        finally:
+            sol.close()
+    monkeypatch.delenv("ALPS_B200_REL_ROWS", raising=False)
+    for i, (Do, chi_o, _, _) in want.items():
+        sc = det_scale(wave_scale(chi_o, complex(oms[i]), pl.vA, kperp, kpar))
+        for n in (1, 2, 3, 8, 20, 64):
+            if i < n:
+                assert abs(got["1"][n][i] - Do) / sc < TOL, (n, i)
+                assert abs(got["1"][n][i] - got["0"][n][i]) / sc < 1e-10, (n, i)
+        if i < 5:
+            assert abs(got["1"]["single"][i] - Do) / sc < TOL, i
+    # within the latency class a single disp() and a batch are the same bits
+    assert np.array_equal(got["1"]["single"][:3], got["1"][3])
+    assert np.array_equal(got["1"][8][:3], got["1"][3])
+
+
 def test_relativistic_config_c3():
     """C3 at full size (ngamma = npparbar = 500, 30x60 input table) near its two roots."""
     pl = tables.config_relativistic()
