@@ -177,7 +177,7 @@ struct State {
   // (fork after k_plan, join in front of the harmonic sums) instead of between k_resonant_lat and k_chi_assemble
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool nhds_forked = false, fork_off = false;
+  bool nhds_forked = false, fork_off = false, nhds_by_flag = false, nhds_join_pending = false;
   double* d_gather = nullptr;      // one process per GPU, OMEGA partition: every rank's D slice (ncclAllGather in place)
   size_t gather_cap = 0;
 };
@@ -618,9 +618,10 @@ int prepare_nhds() {
 int prepare_external(int n, const double* d_om, const double** d_ext_out) {
   *d_ext_out = nullptr;
   if (!S.bm_any && !S.ext_any) return 0;
-  if (S.nhds_forked) {   // already running on the side branch of the captured chain: join
+  if (S.nhds_forked) {   // already running on the side branch of the captured chain: join (now, or behind the consumer)
     S.nhds_forked = false;
-    CK(cudaStreamWaitEvent(S.stream, S.ev_join, 0));
+    if (S.nhds_by_flag) S.nhds_join_pending = true;
+    else CK(cudaStreamWaitEvent(S.stream, S.ev_join, 0));
     *d_ext_out = S.d_ext;
     return 0;
   }
@@ -665,7 +666,12 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       // host block like k_plan does), so k_nhds is a branch of its own from the root of the graph to the harmonic sums
       CK(cudaEventRecord(S.ev_fork, S.stream));
       CK(cudaStreamWaitEvent(S.side_stream, S.ev_fork, 0));
-      launch_nhds(S.d_nh, S.h_pin + ZC_OM, n, S.cfg.nspec, 0, S.d_ext, S.side_stream);
+      // its result reaches the harmonic sums through a counter (the fused D-only kernel, flag-driven chain) -- the
+      // branch then joins behind that kernel -- or through the graph edge of the join in front of it
+      S.nhds_by_flag = g_pdl_launch && !S.early_off && !want_aux && !d_partial_out && cn <= SMALL_BATCH && !S.fuse_off &&
+                       !comm_harmonic();
+      launch_nhds(S.d_nh, S.h_pin + ZC_OM, n, S.cfg.nspec, 0, S.d_ext, S.side_stream,
+                  S.nhds_by_flag ? S.d_plan_flag + CHAIN_NHDS : nullptr);
       S.launches += 1;
       CK(cudaEventRecord(S.ev_join, S.side_stream));
       S.nhds_forked = true;
@@ -759,7 +765,12 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
                           S.zc ? reinterpret_cast<int*>(S.h_pin + ZC_ERR) : nullptr,
                           S.zc ? S.d_plan_flag : nullptr,
                           (use_lat(cn) && S.Plat.done_ctr) ? n * S.Plat.ntiles * S.Plat.nsplit : 0,
-                          (use_lat(cn) && S.Plat.done_ctr && lat_rows) ? resonant_lat_blocks(n, S.reslat_gx) : 0);
+                          (use_lat(cn) && S.Plat.done_ctr && lat_rows) ? resonant_lat_blocks(n, S.reslat_gx) : 0,
+                          S.nhds_join_pending ? nhds_blocks(n, S.cfg.nspec) : 0);
+      if (S.nhds_join_pending) {
+        S.nhds_join_pending = false;
+        CK(cudaStreamWaitEvent(S.stream, S.ev_join, 0));
+      }
       if (S.zc && !want_aux && !S.spin_off) S.chain_polled = true;
       S.launches += 4;
       return 0;
@@ -1864,6 +1875,7 @@ static int disp_via_graph(int n, int* used) {
     g_pdl_launch = false;
     S.capturing = false;
     S.nhds_forked = false;
+    S.nhds_join_pending = false;
     gs.launches = S.launches - l0;
     gs.polled = S.chain_polled;
     S.launches = l0;

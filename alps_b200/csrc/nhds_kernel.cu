@@ -226,11 +226,8 @@ constexpr int NHDS_WARPS = 4;
 
 // one warp per (omega, species): rows of non-bM species are zeroed (or left alone when accumulating on top of
 // caller-supplied external chi)
-__global__ void __launch_bounds__(32 * NHDS_WARPS)
-k_nhds(const NhdsDev* __restrict__ nd, const double* __restrict__ om, int n_om, int nspec, int accumulate,
-       double* __restrict__ ext) {
-  const int w = blockIdx.x * NHDS_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (w >= n_om * nspec) return;
+__device__ __forceinline__ void nhds_warp(const NhdsDev* __restrict__ nd, const double* __restrict__ om, int w, int nspec,
+                                          int accumulate, double* __restrict__ ext, int lane) {
   const int iom = w / nspec, s = w % nspec;
   double* o = ext + (size_t)w * PARTIAL_PER_SPEC;
   const NhdsSpec& p = nd->sp[s];
@@ -322,15 +319,32 @@ k_nhds(const NhdsDev* __restrict__ nd, const double* __restrict__ om, int n_om, 
   }
 }
 
+__global__ void __launch_bounds__(32 * NHDS_WARPS)
+k_nhds(const NhdsDev* __restrict__ nd, const double* __restrict__ om, int n_om, int nspec, int accumulate,
+       double* __restrict__ ext, int* done_ctr) {
+  const int w = blockIdx.x * NHDS_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w < n_om * nspec) nhds_warp(nd, om, w, nspec, accumulate, ext, lane);
+  if (done_ctr) {
+    // single-omega chain: this kernel is a branch of its own in the graph; the determinant (k_chi_assemble) waits for the
+    // count of finished blocks instead of for a graph edge, so that it can be resident and working meanwhile
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(done_ctr, 1);
+    }
+  }
+}
+int nhds_blocks(int n_om, int nspec) { return (n_om * nspec + NHDS_WARPS - 1) / NHDS_WARPS; }
+
 void launch_nhds_bessel(double z, int count, double* I, cudaStream_t st) {
   if (count <= 0) return;
   k_nhds_bessel<<<(count + 63) / 64, 64, 0, st>>>(z, count, I);
 }
 
-void launch_nhds(const NhdsDev* nd, const double* om, int n_om, int nspec, int accumulate, double* ext, cudaStream_t st) {
+void launch_nhds(const NhdsDev* nd, const double* om, int n_om, int nspec, int accumulate, double* ext, cudaStream_t st,
+                 int* done_ctr) {
   if (n_om <= 0) return;
-  const int items = n_om * nspec;
-  k_nhds<<<(items + NHDS_WARPS - 1) / NHDS_WARPS, 32 * NHDS_WARPS, 0, st>>>(nd, om, n_om, nspec, accumulate, ext);
+  k_nhds<<<nhds_blocks(n_om, nspec), 32 * NHDS_WARPS, 0, st>>>(nd, om, n_om, nspec, accumulate, ext, done_ctr);
 }
 
 }  // namespace alps

@@ -212,6 +212,7 @@ k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n
       *reinterpret_cast<volatile int*>(plan_flag) = 0;
       *reinterpret_cast<volatile int*>(plan_flag + CHAIN_QUAD) = 0;   // CTAs of k_quad_mma that have written their sums
       *reinterpret_cast<volatile int*>(plan_flag + CHAIN_RES) = 0;    // blocks of k_resonant_lat that have finished
+      *reinterpret_cast<volatile int*>(plan_flag + CHAIN_NHDS) = 0;   // blocks of k_nhds (side branch) that have finished
     }
     __threadfence();
     __syncthreads();
@@ -1381,7 +1382,7 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
                const double* __restrict__ Sbulk, int nsplit, const double* __restrict__ Sres, const double* Spart,
                double* partial, const double* __restrict__ ext_chi, double* __restrict__ D, double* __restrict__ chi0_out,
                double* __restrict__ chi0_low_out, double* __restrict__ wave_out, const int* err_src,
-               int* __restrict__ err_dst, int* chain, int nquad, int nres) {
+               int* __restrict__ err_dst, int* chain, int nquad, int nres, int nnh) {
   const GlobalDev& g = *gp;
   const int iom = blockIdx.x, nspec = g.nspec;
   __shared__ ChiSmem sm;
@@ -1394,6 +1395,19 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
   if (err_dst && iom == 0 && threadIdx.x >= 32 * (CHI_WARPS - 1) && threadIdx.x < 32 * (CHI_WARPS - 1) + 8)
     err_dst[threadIdx.x & 31] = err_src[threadIdx.x & 31];
   __syncthreads();
+  if (nnh > 0 && chain) {
+    // the closed-form chi of use_bM species comes from k_nhds on a side branch of the graph, which joins behind this
+    // kernel: wait for its blocks' count (it is a serial chain of ~25 us that started with the graph; no other kernel
+    // of the chain waits for it, so there is nothing to fall back to -- a count that never arrives is a bug: trap)
+    if (threadIdx.x == 0) {
+      int seen = 0;
+      for (long long spin = 0; seen < nnh; spin++) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(chain + CHAIN_NHDS) : "memory");
+        if (spin > (1LL << 26)) __trap();
+      }
+    }
+    __syncthreads();
+  }
   if (!chi0_out && !chi0_low_out && !wave_out) {
     // D only (the single-omega chain): the same operations as assemble_one in a few rolled instructions -- this code runs
     // once, after the chain's last wait, from L2.  Threads 0..5 sum a component of epsilon over the species, thread 0
@@ -1406,7 +1420,7 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
         cd v = mk(sm.partial[s][2 * c], sm.partial[s][2 * c + 1]);
         if (ext_chi && sm.spc[s].usebM) {
           const double* x = ext_chi + ((size_t)iom * nspec + s) * PARTIAL_PER_SPEC;
-          v += mk(x[2 * c], x[2 * c + 1]);
+          v += mk(__ldcg(x + 2 * c), __ldcg(x + 2 * c + 1));   // (through L2: written while this kernel is resident)
         }
         e += v;
       }
@@ -1495,10 +1509,10 @@ void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, 
 void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
                          const double* Sbulk, int nsplit, const double* Sres, const double* Spart, double* partial,
                          const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
-                         const int* err_src, int* err_dst, int* chain, int nquad, int nres) {
+                         const int* err_src, int* err_dst, int* chain, int nquad, int nres, int nnh) {
   if (n_om <= 0) return;
   launch_chain(k_chi_assemble, dim3(n_om), dim3(CHI_THREADS), 0, st, g, om, plan, Sbulk, nsplit, Sres, Spart,
-               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst, chain, nquad, nres);
+               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst, chain, nquad, nres, nnh);
 }
 
 }  // namespace alps
