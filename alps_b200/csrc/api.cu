@@ -84,6 +84,7 @@ struct State {
     std::vector<unsigned char> sig;
     long long launches = 0;
     int plain_calls = 0;           // plain calls since the signature last changed (the first one warms up)
+    int nnh = 0;                   // k_nhds blocks per launch that the determinant waits for (0: none)
     bool polled = false;           // the chain's D's arrive in pinned host memory as 16-byte stores: the host polls them
   } gslot[9];
   bool capturing = false, graph_off = false, omega_major = false;
@@ -97,6 +98,8 @@ struct State {
   int* d_plan_flag = nullptr;    // k_plan's completion flag (single-omega chain, resonant.cu)
   bool rel_rows_off = false;     // ALPS_B200_REL_ROWS=0: small batches leave the resonant rows to the CTAs of their tile
   bool spin_off = false;         // ALPS_B200_SPIN=0: the host synchronises the stream instead of polling D
+  int chain_nnh = 0;             // set while capturing: blocks of k_nhds a launch of the chain adds to the chain's count
+  unsigned long long nh_total = 0;   // k_nhds blocks launched by the captured chains so far (kernels.h: CHAIN_NHDS64)
   bool chain_polled = false;     // set while capturing: the chain's last kernel writes every D with one 16-byte store
   bool early_off = false;        // ALPS_B200_EARLY=0: the Landau blocks wait for their predecessor like the others
   double* d_relpart = nullptr;   // k_rel partial rows of the gamma split (small batches)
@@ -671,7 +674,7 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
       S.nhds_by_flag = g_pdl_launch && !S.early_off && !want_aux && !d_partial_out && cn <= SMALL_BATCH && !S.fuse_off &&
                        !comm_harmonic();
       launch_nhds(S.d_nh, S.h_pin + ZC_OM, n, S.cfg.nspec, 0, S.d_ext, S.side_stream,
-                  S.nhds_by_flag ? S.d_plan_flag + CHAIN_NHDS : nullptr);
+                  S.nhds_by_flag ? reinterpret_cast<unsigned long long*>(S.d_plan_flag + CHAIN_NHDS64) : nullptr);
       S.launches += 1;
       CK(cudaEventRecord(S.ev_join, S.side_stream));
       S.nhds_forked = true;
@@ -766,9 +769,10 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
                           S.zc ? S.d_plan_flag : nullptr,
                           (use_lat(cn) && S.Plat.done_ctr) ? n * S.Plat.ntiles * S.Plat.nsplit : 0,
                           (use_lat(cn) && S.Plat.done_ctr && lat_rows) ? resonant_lat_blocks(n, S.reslat_gx) : 0,
-                          S.nhds_join_pending ? nhds_blocks(n, S.cfg.nspec) : 0);
+                          S.nhds_join_pending ? S.h_pin + ZC_NHT : nullptr);
       if (S.nhds_join_pending) {
         S.nhds_join_pending = false;
+        S.chain_nnh = nhds_blocks(n, S.cfg.nspec);
         CK(cudaStreamWaitEvent(S.stream, S.ev_join, 0));
       }
       if (S.zc && !want_aux && !S.spin_off) S.chain_polled = true;
@@ -1130,6 +1134,7 @@ int alps_b200_init(const alps_b200_cfg* cfg) {
   if (dalloc(&S.gd, 1) || dalloc(&S.d_work_count, 1) || dalloc(&S.d_err, 8) || dalloc(&S.d_plan_flag, CHAIN_INTS))
     return ALPS_B200_ERR_CUDA;
   {
+    S.nh_total = 0;
     const int init[CHAIN_INTS] = {1, 0};   // [0] "plan complete": only the fused k_plan of the single-omega chain clears it
     CK(cudaMemcpy(S.d_plan_flag, init, sizeof(init), cudaMemcpyHostToDevice));
   }
@@ -1863,6 +1868,7 @@ static int disp_via_graph(int n, int* used) {
     S.capturing = true;
     S.zc = !S.zc_off && plan_fused_ok(S.gh, n);
     S.chain_polled = false;
+    S.chain_nnh = 0;
     g_pdl_launch = S.pdl_on && S.zc;
     const long long l0 = S.launches;
     if (!S.zc) cudaMemcpyAsync(S.d_om, S.h_pin + ZC_OM, 2 * n * sizeof(double), cudaMemcpyHostToDevice, S.stream);
@@ -1878,6 +1884,7 @@ static int disp_via_graph(int n, int* used) {
     S.nhds_join_pending = false;
     gs.launches = S.launches - l0;
     gs.polled = S.chain_polled;
+    gs.nnh = S.chain_nnh;
     S.launches = l0;
     const cudaError_t e1 = cudaStreamEndCapture(S.stream, &graph);
     cudaError_t e2 = cudaSuccess;
@@ -1904,6 +1911,10 @@ static int disp_via_graph(int n, int* used) {
   memcpy(&sbits, &kSentinel, sizeof(sbits));
   if (gs.polled)
     for (int i = 0; i < 2 * n; i++) slot[i] = sbits;
+  if (gs.nnh > 0) {   // the count of finished k_nhds blocks this launch will reach (kernels.h: CHAIN_NHDS64)
+    S.nh_total += (unsigned long long)gs.nnh;
+    S.h_pin[ZC_NHT] = (double)S.nh_total;
+  }
   CK(cudaGraphLaunch(gs.exec, S.stream));
   bool done = false;
   if (gs.polled) {

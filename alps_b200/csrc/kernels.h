@@ -112,9 +112,13 @@ double run_dmma_peak(cudaStream_t st);
 constexpr int PLAN_FUSED_MAX_OM = 8;
 // Single-omega chain: slots (doubles) of the pinned host block the chain's first / last kernel read / write (api.cu), and
 // the chain's device words (ints): k_plan's completion flag, CTAs of k_quad_mma done, blocks of k_resonant_lat done,
-// blocks of k_nhds (side branch of the graph) done.
-constexpr int ZC_OM = 0, ZC_D = 16, ZC_ERR = 32, ZC_DOUBLES = 64;
-constexpr int CHAIN_PLAN = 0, CHAIN_QUAD = 1, CHAIN_RES = 2, CHAIN_NHDS = 3, CHAIN_INTS = 4;
+// blocks of k_nhds (side branch of the graph) done (CHAIN_NHDS64).
+constexpr int ZC_OM = 0, ZC_D = 16, ZC_ERR = 32, ZC_NHT = 40, ZC_DOUBLES = 64;   // ZC_NHT: see CHAIN_NHDS64
+constexpr int CHAIN_PLAN = 0, CHAIN_QUAD = 1, CHAIN_RES = 2, CHAIN_INTS = 8;
+// ints 4..5: a 64-bit count of finished k_nhds blocks that is never reset (k_nhds sits at the root of the graph, beside
+// k_plan, so nothing could reset it safely): the host writes the count the call will reach into the pinned block
+// (ZC_NHT, a double) before it launches the graph, and the determinant waits until the counter has got there.
+constexpr int CHAIN_NHDS64 = 4;
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
                  int* work, int* work_count, cudaStream_t st, double* om_stage = nullptr, int* plan_flag = nullptr,
                  int* zero_ints = nullptr, int nzero = 0);   // fused variant: words it clears for the chain (k_rel_plan's counts)
@@ -142,7 +146,7 @@ void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* 
                          const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
                          const int* err_src = nullptr, int* err_dst = nullptr,
                          int* chain = nullptr, int nquad = 0, int nres = 0,   // early bulk sums (programmatic launches)
-                         int nnh = 0);   // blocks of k_nhds the determinant waits for (its branch joins behind this kernel)
+                         const double* nh_target = nullptr);   // pinned host word: the k_nhds block count to wait for (0: none)
 struct FastItem {
   int s;
   int nabs;
@@ -186,7 +190,7 @@ struct NhdsDev {
 };
 void launch_nhds_bessel(double z, int count, double* I, cudaStream_t st);
 void launch_nhds(const NhdsDev* nd, const double* om, int n_om, int nspec, int accumulate, double* ext, cudaStream_t st,
-                 int* done_ctr = nullptr);   // single-omega chain: every block bumps it at its end (kernels.h: CHAIN_NHDS)
+                 unsigned long long* done_ctr = nullptr);   // single-omega chain: every block bumps it (CHAIN_NHDS64)
 int nhds_blocks(int n_om, int nspec);       // grid size of k_nhds for that call
 // HARMONIC partition of a device group: dst += sum of the peers' partial rows, read through peer memory (multi_gpu.cu)
 void launch_reduce_partials(double* dst, const double* const* src, int nsrc, size_t count, cudaStream_t st);

@@ -321,7 +321,7 @@ __device__ __forceinline__ void nhds_warp(const NhdsDev* __restrict__ nd, const 
 
 __global__ void __launch_bounds__(32 * NHDS_WARPS)
 k_nhds(const NhdsDev* __restrict__ nd, const double* __restrict__ om, int n_om, int nspec, int accumulate,
-       double* __restrict__ ext, int* done_ctr) {
+       double* __restrict__ ext, unsigned long long* done_ctr) {
   const int w = blockIdx.x * NHDS_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (w < n_om * nspec) nhds_warp(nd, om, w, nspec, accumulate, ext, lane);
   if (done_ctr) {
@@ -330,7 +330,7 @@ k_nhds(const NhdsDev* __restrict__ nd, const double* __restrict__ om, int n_om, 
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
-      atomicAdd(done_ctr, 1);
+      atomicAdd(done_ctr, 1ULL);
     }
   }
 }
@@ -342,7 +342,7 @@ void launch_nhds_bessel(double z, int count, double* I, cudaStream_t st) {
 }
 
 void launch_nhds(const NhdsDev* nd, const double* om, int n_om, int nspec, int accumulate, double* ext, cudaStream_t st,
-                 int* done_ctr) {
+                 unsigned long long* done_ctr) {
   if (n_om <= 0) return;
   k_nhds<<<nhds_blocks(n_om, nspec), 32 * NHDS_WARPS, 0, st>>>(nd, om, n_om, nspec, accumulate, ext, done_ctr);
 }

@@ -212,7 +212,6 @@ k_plan(const GlobalDev* __restrict__ gp, const double* __restrict__ om_in, int n
       *reinterpret_cast<volatile int*>(plan_flag) = 0;
       *reinterpret_cast<volatile int*>(plan_flag + CHAIN_QUAD) = 0;   // CTAs of k_quad_mma that have written their sums
       *reinterpret_cast<volatile int*>(plan_flag + CHAIN_RES) = 0;    // blocks of k_resonant_lat that have finished
-      *reinterpret_cast<volatile int*>(plan_flag + CHAIN_NHDS) = 0;   // blocks of k_nhds (side branch) that have finished
     }
     __threadfence();
     __syncthreads();
@@ -1382,12 +1381,15 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
                const double* __restrict__ Sbulk, int nsplit, const double* __restrict__ Sres, const double* Spart,
                double* partial, const double* __restrict__ ext_chi, double* __restrict__ D, double* __restrict__ chi0_out,
                double* __restrict__ chi0_low_out, double* __restrict__ wave_out, const int* err_src,
-               int* __restrict__ err_dst, int* chain, int nquad, int nres, int nnh) {
+               int* __restrict__ err_dst, int* chain, int nquad, int nres, const double* nh_target) {
   const GlobalDev& g = *gp;
   const int iom = blockIdx.x, nspec = g.nspec;
   __shared__ ChiSmem sm;
   pdl_trigger();
   if (threadIdx.x == 0) lat_stamp(g, 16);
+  // (the host's announcement for the k_nhds count -- a read over PCIe -- is fetched first, behind everything else)
+  double nh_tgt = 0.0;
+  if (nh_target && threadIdx.x == 0) nh_tgt = *reinterpret_cast<const volatile double*>(nh_target);
   chi_partial_block(g, om, iom, plan, Sbulk, nsplit, Sres, Spart, partial, sm, true, chain ? chain + CHAIN_QUAD : nullptr,
                     nquad, chain ? chain + CHAIN_RES : nullptr, nres);
   if ((threadIdx.x & 31) == 0) lat_stamp(g, 17);
@@ -1395,14 +1397,18 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
   if (err_dst && iom == 0 && threadIdx.x >= 32 * (CHI_WARPS - 1) && threadIdx.x < 32 * (CHI_WARPS - 1) + 8)
     err_dst[threadIdx.x & 31] = err_src[threadIdx.x & 31];
   __syncthreads();
-  if (nnh > 0 && chain) {
+  if (nh_target && chain) {
     // the closed-form chi of use_bM species comes from k_nhds on a side branch of the graph, which joins behind this
-    // kernel: wait for its blocks' count (it is a serial chain of ~25 us that started with the graph; no other kernel
-    // of the chain waits for it, so there is nothing to fall back to -- a count that never arrives is a bug: trap)
+    // kernel: wait until the (never reset) count of its finished blocks has reached what the host announced for this
+    // call.  k_nhds is a serial chain of ~25 us that started with the graph; no other kernel of the chain waits for it, so
+    // there is nothing to fall back to -- a count that never arrives is a bug: trap.
     if (threadIdx.x == 0) {
-      int seen = 0;
-      for (long long spin = 0; seen < nnh; spin++) {
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(chain + CHAIN_NHDS) : "memory");
+      const double target = nh_tgt;
+      const unsigned long long* ctr = reinterpret_cast<const unsigned long long*>(chain + CHAIN_NHDS64);
+      unsigned long long seen = 0;
+      for (long long spin = 0;; spin++) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(ctr) : "memory");
+        if ((double)seen >= target) break;
         if (spin > (1LL << 26)) __trap();
       }
     }
@@ -1509,10 +1515,10 @@ void launch_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, 
 void launch_chi_assemble(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, const PlanEntry* plan,
                          const double* Sbulk, int nsplit, const double* Sres, const double* Spart, double* partial,
                          const double* ext_chi, double* D, double* chi0, double* chi0_low, double* wave, cudaStream_t st,
-                         const int* err_src, int* err_dst, int* chain, int nquad, int nres, int nnh) {
+                         const int* err_src, int* err_dst, int* chain, int nquad, int nres, const double* nh_target) {
   if (n_om <= 0) return;
   launch_chain(k_chi_assemble, dim3(n_om), dim3(CHI_THREADS), 0, st, g, om, plan, Sbulk, nsplit, Sres, Spart,
-               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst, chain, nquad, nres, nnh);
+               partial, ext_chi, D, chi0, chi0_low, wave, err_src, err_dst, chain, nquad, nres, nh_target);
 }
 
 }  // namespace alps
