@@ -22,6 +22,23 @@ def probe(name, pl, k, om, **kw):
                 for i in range(N): sol.disp_batch(oms[i])
             best = min(best, (time.perf_counter() - t) / N * 1e6)
         out.append("n=%d %.1f us" % (nb, best))
+    # the C ABI itself: alps_b200_disp with preallocated buffers (Solver.disp allocates two arrays and builds the pointers
+    # on every call: ~5 us of Python)
+    import ctypes
+    from alps_b200 import _lib
+    omv, D = np.zeros(2), np.zeros(2)
+    p_om, p_D = omv.ctypes.data_as(ctypes.c_void_p), D.ctypes.data_as(ctypes.c_void_p)
+    f = sol.L.alps_b200_disp
+    best = 1e9
+    for rep in range(5):
+        N = 400
+        t = time.perf_counter()
+        for i in range(N):
+            o = om * (1 + 1e-6 * (7777 + rep * N + i))
+            omv[0] = o.real; omv[1] = o.imag
+            f(p_om, p_D, None, None, None)
+        best = min(best, (time.perf_counter() - t) / N * 1e6)
+    out.append("C ABI n=1 %.1f us" % best)
     print("%-16s %s   D(om) = %r" % (name, "  ".join(out), sol.disp(om)), flush=True)
     sol.close()
 
