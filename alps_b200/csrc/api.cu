@@ -483,6 +483,11 @@ void apply_view() {
     S.Plat.ntiles = S.P.ntiles;
     S.Plat.ntiles_rem = S.P.ntiles_rem;
     S.Plat.g = S.P.g;
+    const std::vector<QuadTile>& tv = S.view_full ? S.tiles_full : S.tiles;
+    S.Plat.ntiles_inline = (int)std::min<size_t>(tv.size(), 16);
+    for (int t = 0; t < S.Plat.ntiles_inline; t++) S.Plat.tile_inline[t] = tv[t];
+    for (int t = S.Plat.ntiles_inline; t < 16; t++) S.Plat.tile_inline[t] = QuadTile{0, 0};
+    S.Plat.npar_inline = S.cfg.npar;
   }
 }
 // one call in the unsharded view
@@ -1848,7 +1853,7 @@ static int disp_via_graph(int n, int* used) {
   static_assert(LAT_BATCH + 1 <= (int)(sizeof(S.gslot) / sizeof(S.gslot[0])) && 2 * LAT_BATCH <= ZC_D, "graph slots");
   if (n < 1 || n > LAT_BATCH) return 0;
   State::GraphSlot& gs = S.gslot[n];
-  std::vector<unsigned char> sig;
+  static thread_local std::vector<unsigned char> sig;   // (reused: no allocation per call)
   disp_signature(sig, n);
   if (sig != gs.sig) {
     if (gs.exec) cudaGraphExecDestroy(gs.exec);

@@ -34,6 +34,10 @@ struct QuadParams {
   const double* Cf[MAXSPEC];
   const double* Wf[MAXSPEC];
   int nks;
+  // latency variant: the first tiles and the grid size inline, so that a CTA can issue its first table loads without a
+  // round trip to P.tiles / P.g (ntiles_inline = 0: not filled)
+  QuadTile tile_inline[16];
+  int ntiles_inline, npar_inline;
   int* done_ctr;           // latency variant: bumped by every CTA once its sums are written (nullptr: not used)
   int tile_major;          // block order: 1 = all omegas of a tile are adjacent (concurrent CTAs share the species tables
                            // and W in L2), 0 = all tiles of an omega are adjacent

@@ -79,10 +79,11 @@ __global__ void __launch_bounds__(32 * NW * HS, NW == 4 ? 2 : 1) k_quad_mma(cons
   const int bq = blockIdx.x / nsplit;
   const int tile_id = P.tile_major ? bq / P.n_om : bq % P.ntiles;
   const int iom = P.tile_major ? bq % P.n_om : bq / P.ntiles;
-  const QuadTile tile = P.tiles[tile_id];
+  constexpr bool LATV = (NW == 2) && !STORE;   // the latency variant of the single-omega chain
+  const QuadTile tile = (LATV && tile_id < P.ntiles_inline) ? P.tile_inline[tile_id] : P.tiles[tile_id];
   const GlobalDev& g = *P.g;
   const SpeciesDev& sp = g.sp[tile.s];
-  const int npar = g.npar;
+  const int npar = (LATV && P.ntiles_inline > 0) ? P.npar_inline : g.npar;
   const int NKS = P.nks;
   const int KC = NKS / KSTG;
   const int NTall = (npar - 1 + TW - 1) / TW;
