@@ -1473,7 +1473,9 @@ void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int 
                  int* work_count, cudaStream_t st, double* om_stage, int* plan_flag, int* zero_ints, int nzero) {
   size_t total = (size_t)n_om * gh.NI;
   if (om_stage) {   // fused single-block variant: caller checked plan_fused_ok()
-    k_plan<true><<<1, 1024, 0, st>>>(g, om, n_om, plan, work, work_count, om_stage, plan_flag, zero_ints, nzero);
+    // (as many warps as there are items: the dependents of the chain start when all of them have passed the trigger)
+    const int threads = (int)std::min<size_t>(1024, std::max<size_t>(64, (total + 31) / 32 * 32));
+    k_plan<true><<<1, threads, 0, st>>>(g, om, n_om, plan, work, work_count, om_stage, plan_flag, zero_ints, nzero);
     return;
   }
   cudaMemsetAsync(work_count, 0, sizeof(int), st);
