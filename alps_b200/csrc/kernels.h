@@ -123,6 +123,10 @@ constexpr int CHAIN_PLAN = 0, CHAIN_QUAD = 1, CHAIN_RES = 2, CHAIN_INTS = 8;
 // k_plan, so nothing could reset it safely): the host writes the count the call will reach into the pinned block
 // (ZC_NHT, a double) before it launches the graph, and the determinant waits until the counter has got there.
 constexpr int CHAIN_NHDS64 = 4;
+static_assert(CHAIN_NHDS64 % 2 == 0 && CHAIN_NHDS64 > CHAIN_RES && CHAIN_NHDS64 + 2 <= CHAIN_INTS,
+              "the 64-bit count sits on an 8-byte boundary behind the 32-bit words");
+static_assert(ZC_OM + 2 * PLAN_FUSED_MAX_OM <= ZC_D && ZC_D + 2 * PLAN_FUSED_MAX_OM <= ZC_ERR && ZC_ERR + 4 <= ZC_NHT &&
+              ZC_NHT < ZC_DOUBLES, "slots of the pinned host block do not overlap");
 void launch_plan(const GlobalDev* g, const GlobalDev& gh, const double* om, int n_om, PlanEntry* plan,
                  int* work, int* work_count, cudaStream_t st, double* om_stage = nullptr, int* plan_flag = nullptr,
                  int* zero_ints = nullptr, int nzero = 0);   // fused variant: words it clears for the chain (k_rel_plan's counts)
