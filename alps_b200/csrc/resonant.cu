@@ -1393,9 +1393,20 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
   chi_partial_block(g, om, iom, plan, Sbulk, nsplit, Sres, Spart, partial, sm, true, chain ? chain + CHAIN_QUAD : nullptr,
                     nquad, chain ? chain + CHAIN_RES : nullptr, nres);
   if ((threadIdx.x & 31) == 0) lat_stamp(g, 17);
-  // (after the block's waits: the error words of the whole chain are final)
-  if (err_dst && iom == 0 && threadIdx.x >= 32 * (CHI_WARPS - 1) && threadIdx.x < 32 * (CHI_WARPS - 1) + 8)
-    err_dst[threadIdx.x & 31] = err_src[threadIdx.x & 31];
+  // (after the block's waits: the error words of the whole chain are final).  A D-only call is polled by the host on its
+  // D slots: there the thread that stores D stores the error words first (fetched here, so that they cost it nothing)
+  const bool d_only = !chi0_out && !chi0_low_out && !wave_out;
+  int4 ew0 = make_int4(0, 0, 0, 0), ew1 = ew0;
+  if (err_dst && iom == 0) {
+    if (d_only) {
+      if (threadIdx.x == 0) {
+        ew0 = __ldcg(reinterpret_cast<const int4*>(err_src));
+        ew1 = __ldcg(reinterpret_cast<const int4*>(err_src) + 1);
+      }
+    } else if (threadIdx.x >= 32 * (CHI_WARPS - 1) && threadIdx.x < 32 * (CHI_WARPS - 1) + 8) {
+      err_dst[threadIdx.x & 31] = err_src[threadIdx.x & 31];
+    }
+  }
   __syncthreads();
   if (nh_target && chain) {
     // the closed-form chi of use_bM species comes from k_nhds on a side branch of the graph, which joins behind this
@@ -1414,7 +1425,7 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
     }
     __syncthreads();
   }
-  if (!chi0_out && !chi0_low_out && !wave_out) {
+  if (d_only) {
     // D only (the single-omega chain): the same operations as assemble_one in a few rolled instructions -- this code runs
     // once, after the chain's last wait, from L2.  Threads 0..5 sum a component of epsilon over the species, thread 0
     // forms the determinant (src/ALPS_fns.f90:598-624).
@@ -1453,6 +1464,10 @@ k_chi_assemble(const GlobalDev* __restrict__ gp, const double* __restrict__ om, 
       const cd w11 = e0 - enz2, w22 = e1 - enz2 - enx2, w33 = e2 - enx2;
       const cd w13 = sm.chinr[4] + enxnz, w12 = sm.chinr[3], w23 = sm.chinr[5];
       const cd d = w11 * (w22 * w33 + w23 * w23) + mk(2.0, 0.0) * w12 * w23 * w13 - w13 * w13 * w22 + w12 * w12 * w33;
+      if (err_dst && iom == 0) {
+        reinterpret_cast<int4*>(err_dst)[0] = ew0;
+        reinterpret_cast<int4*>(err_dst)[1] = ew1;
+      }
       // one 16-byte store: in the single-omega chain D is pinned host memory and the host polls it (api.cu)
       if (D) *reinterpret_cast<double2*>(D + 2 * iom) = make_double2(d.x, d.y);
       lat_stamp(g, 19);
