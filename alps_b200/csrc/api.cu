@@ -729,7 +729,8 @@ int run_chunk(int n, const double* d_om, double* d_D, double* d_partial_out, con
     // small batches: the partial rows of k_resonant_lat feed the harmonic sums directly (no Sres)
     const double* lat_rows = (resonant_lat_class(n, cn) && S.d_respart) ? S.d_respart : nullptr;
     launch_resonant(gd, d_om, n, S.d_plan, S.d_work, S.d_work_count, S.d_gwin, S.d_Sres, S.d_err, S.d_respart,
-                    S.stream, S.reslat_gx, cn, early ? S.d_plan_flag : nullptr);
+                    S.stream, S.reslat_gx, cn, early ? S.d_plan_flag : nullptr,
+                    (early && use_lat(cn) && S.Plat.done_ctr) ? n * S.Plat.ntiles * S.Plat.nsplit : 0);
     if (cur_nrtiles() > 0) {
       // few omegas in flight: spread each (omega, species, |n|) over several CTAs (configuration-only
       // rule, like nsplit_small, so disp() and a small disp_batch() stay bitwise identical)

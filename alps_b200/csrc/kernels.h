@@ -134,7 +134,8 @@ bool plan_fused_ok(const GlobalDev& gh, int n_om);
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
                      cudaStream_t st, int gx = 148, int class_n = 0,   // class_n: omegas of the whole call
-                     int* chain = nullptr);   // the chain's device words: flag-driven starts (programmatic launches)
+                     int* chain = nullptr,    // the chain's device words: flag-driven starts (programmatic launches)
+                     int nquad = 0);          // CTAs of k_quad_mma whose count releases the near-pole blocks (0: kernel boundary)
 int resonant_lat_blocks(int n_om, int gx);   // grid size of k_resonant_lat for that call
 // k_resonant_lat serves the call (its partial rows, not Sres, feed the harmonic sums: pass Spart to launch_chi_*)
 bool resonant_lat_class(int n_om, int class_n);

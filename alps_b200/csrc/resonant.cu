@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
                                                               const int* __restrict__ work_count,
                                                               const double* __restrict__ gwin,
                                                               int* __restrict__ err_flag, double* __restrict__ Spart,
-                                                              int* chain) {
+                                                              int* chain, int nquad) {
   const GlobalDev& g = *gp;
   const int tid = threadIdx.x, wlane = tid & 31, wid = tid >> 5, part = blockIdx.y;
   __shared__ cd s_part[LAT_THREADS / 32][3];
@@ -680,7 +680,21 @@ __global__ void __launch_bounds__(LAT_THREADS) k_resonant_lat(const GlobalDev* _
       const double dp_abs = sp.dppar_abs;
       near_fac = 2.0 * PI * smdelta * sp.dpperp * 0.25;
       if (!quad_waited) {
-        pdl_wait();
+        // the window sums are complete when every CTA of k_quad_mma has counted itself done (bounded; then the
+        // ordinary wait for the predecessor, which is always sufficient)
+        bool seen_all = false;
+        if (chain && nquad > 0) {
+          if (tid == 0) {
+            int seen = 0;
+            for (int spin = 0; spin < (1 << 16) && seen < nquad; spin++) {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(chain + CHAIN_QUAD) : "memory");
+            }
+            s_seen = seen >= nquad;
+          }
+          __syncthreads();
+          seen_all = s_seen != 0;
+        }
+        if (!seen_all) pdl_wait();
         quad_waited = true;
       }
       // (from here to the end of the kernel the code is kept short: it runs once, after the wait, from L2)
@@ -1504,13 +1518,13 @@ bool resonant_lat_class(int n_om, int class_n) { return std::max(class_n, n_om) 
 int resonant_lat_blocks(int n_om, int gx) { return std::min(148, std::max(1, gx * n_om)) * LAT_PARTS; }
 void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanEntry* plan, const int* work,
                      const int* work_count, const double* gwin, double* Sres, int* err_flag, double* Spart,
-                     cudaStream_t st, int gx, int class_n, int* chain) {
+                     cudaStream_t st, int gx, int class_n, int* chain, int nquad) {
   if (n_om <= 0) return;
   if (resonant_lat_class(n_om, class_n) && Spart) {
     // gx block columns per omega loop over the list of resonant harmonics: usually only n = 0 is resonant and a
     // narrow grid saves waves of idle blocks (C1: -2.8 us per D), many resonances (large k_par) want all SMs
     launch_chain(k_resonant_lat, dim3(min(148, max(1, gx * n_om)), LAT_PARTS), dim3(LAT_THREADS), 0, st, g, om, plan,
-                 work, work_count, gwin, err_flag, Spart, chain);
+                 work, work_count, gwin, err_flag, Spart, chain, nquad);
   }
   else
     k_resonant<<<148 * 8, RES_THREADS, 0, st>>>(g, om, plan, work, work_count, gwin, Sres, err_flag);
