@@ -886,8 +886,10 @@ __device__ __forceinline__ cd lat_parts_combine(const double* pr, int q, int fla
 // issues every load of its units (plan entry, the p_par split rows of k_quad, the resonant part) before the first use:
 // the whole omega costs one or two L2 round trips instead of one per row and item (the single-omega chain is a chain of
 // such round trips).  The components go to shared memory.  Phase 2: for species s and component c, lane l of a warp adds
-// the items r = l, l + 32, ... in increasing order and a butterfly adds the lanes: the order of operations of a warp per
-// (omega, species) that walks the items itself, whatever the batch size.
+// the NON-RESONANT items r = l, l + 32, ... in increasing order and a butterfly adds the lanes; the resonant items (those
+// whose sum needs k_resonant's output) are then added in increasing order: chi = butterfly(lane sums) + (resonant sum).
+// The order depends on the configuration only, whatever the batch size -- and it lets the single-omega chain form
+// everything but the resonant items while k_resonant_lat still runs.
 // partial[(iom*nspec + s)*PARTIAL_PER_SPEC + 2*c .. ]: c = mode-1 (0..5) for chi,
 // c = 6 + 3*(mode-1) + (m+1) for chi_low(mode, m), m = -1,0,1.
 constexpr int CHI_WARPS = 24;
