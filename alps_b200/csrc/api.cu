@@ -1937,8 +1937,12 @@ static int disp_via_graph(int n, int* used) {
   if (herr[0] || herr[6]) return check_device_errors();   // reports and clears the device error words
   // herr[7] = resonant harmonics of this call: widen / narrow the next call's k_resonant_lat grid (the signature
   // changes, so the graph is captured again -- rare, the count changes slowly along a scan)
+  // (three widths with hysteresis: every block of the grid, idle or not, is launched, drained and counted by the chain)
   if (herr[7] > RESLAT_GX_NARROW * n) S.reslat_gx = RESLAT_GX_WIDE;
-  else if (herr[7] <= (RESLAT_GX_NARROW / 2) * n) S.reslat_gx = RESLAT_GX_NARROW;
+  else if (herr[7] > RESLAT_GX_TINY * n) S.reslat_gx = std::max(S.reslat_gx, RESLAT_GX_NARROW) == RESLAT_GX_WIDE &&
+                                                          herr[7] > (RESLAT_GX_NARROW / 2) * n ? RESLAT_GX_WIDE : RESLAT_GX_NARROW;
+  else if (herr[7] <= (RESLAT_GX_TINY / 2) * n) S.reslat_gx = RESLAT_GX_TINY;
+  else if (S.reslat_gx == RESLAT_GX_WIDE) S.reslat_gx = RESLAT_GX_NARROW;
   *used = 1;
   return 0;
 }

@@ -139,7 +139,7 @@ void launch_resonant(const GlobalDev* g, const double* om, int n_om, const PlanE
 int resonant_lat_blocks(int n_om, int gx);   // grid size of k_resonant_lat for that call
 // k_resonant_lat serves the call (its partial rows, not Sres, feed the harmonic sums: pass Spart to launch_chi_*)
 bool resonant_lat_class(int n_om, int class_n);
-constexpr int RESLAT_GX_NARROW = 16, RESLAT_GX_WIDE = 148;   // block columns per omega of k_resonant_lat (api.cu adapts)
+constexpr int RESLAT_GX_TINY = 4, RESLAT_GX_NARROW = 16, RESLAT_GX_WIDE = 148;   // block columns per omega of k_resonant_lat (api.cu adapts)
 constexpr int RES_PART_DOUBLES = 11 * 16;   // k_resonant_lat: partial rows per item (LAT_PARTS x LAT_STRIDE)
 // chi partial layout per omega: [nspec][PARTIAL_PER_SPEC] doubles (see resonant.cu)
 constexpr int PARTIAL_PER_SPEC = 2 * (6 + 18);   // chi(6 modes) + chi_low(6 modes x 3) complex
